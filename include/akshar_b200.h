@@ -1,0 +1,121 @@
+/* akshar_b200 -- C ABI of the B200-native batch path for Akshar's hot path.
+ *
+ * The reference (Bhasha-Open/Akshar) has no FFI: its boundary is the Python API in src/akshar.  Each entry point
+ * below replaces, for a whole BATCH of sentences resident in HBM, the per-string Python call cited next to it.
+ * INTEGRATION.md shows the ctypes binding a maintainer adds on the reference side.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every `d_` pointer is DEVICE memory owned by the caller.
+ *   - text layout: concatenated UTF-8 `d_text`, `d_row_offsets[n_rows + 1]` (int64, absolute byte indices into
+ *     d_text, non-decreasing); the host passes the first and last offset (`text_begin`, `text_end`) by value.
+ *   - all work is enqueued on `stream` (a cudaStream_t passed as void*); nothing synchronises.
+ *   - ragged outputs: values + `row_splits[n_rows + 1]` (int64).  Capacities are in elements; writes beyond a
+ *     capacity are dropped, totals stay exact and AKSHAR_ST_OVERFLOW is raised in the result block.
+ *   - `d_result` is 4 x int64 in device memory: [0] primary total, [1] secondary total, [2] status bits, [3] 0.
+ *   - return value: 0 on success, negative AKSHAR_E_* for host-side errors (bad argument, CUDA launch failure).
+ *   - one context per device; a context is not thread-safe.
+ */
+#ifndef AKSHAR_B200_H
+#define AKSHAR_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct akshar_ctx akshar_ctx;
+
+enum {
+    AKSHAR_OK = 0,
+    AKSHAR_E_ARG = -1,
+    AKSHAR_E_CUDA = -2,
+    AKSHAR_E_MODEL = -3,      /* model file could not be parsed / unsupported configuration */
+    AKSHAR_E_NOMODEL = -4,    /* encode called before the matching akshar_load_* */
+    AKSHAR_E_WORKSPACE = -5,
+};
+
+/* status bits in d_result[2] */
+enum {
+    AKSHAR_ST_OVERFLOW = 1,      /* an output capacity was too small: re-run with capacity >= total */
+    AKSHAR_ST_NFC_SEGMENT = 2,   /* a combining sequence needing NFC work exceeds 64 decomposed code points */
+    AKSHAR_ST_PATHOLOGICAL = 4,  /* bounded look-back gave up: re-run the same call with AKSHAR_MODE_ROWS */
+    AKSHAR_ST_ALPHABET = 8,      /* BPE encode met a code point outside normalize_text's closed alphabet */
+    AKSHAR_ST_SPIN = 16,
+    AKSHAR_ST_WORD = 32,         /* BPE word longer than the per-word capacity: re-run with AKSHAR_MODE_ROWS */
+};
+
+/* normalize flags == reference normalize_text(text, normalize_roman, clean_hinglish)  (normalize.py:117) */
+#define AKSHAR_NORM_ROMAN 1u
+#define AKSHAR_NORM_CLEAN 2u
+/* segment flags */
+#define AKSHAR_SEG_CLUSTERS 1u   /* segment_akshars(text)               (segment.py:40-78)  */
+#define AKSHAR_SEG_MATRAS 2u     /* segment_akshars(text, matras=True)  (segment.py:80-125) */
+#define AKSHAR_SEG_RUNS 4u       /* detect_code_switches(text)          (segment.py:150-201) */
+/* mode */
+#define AKSHAR_MODE_TILES 0      /* fixed-size byte spans, one thread per span (fast path) */
+#define AKSHAR_MODE_ROWS 1       /* one span per row (exact for any input, slow for very long rows) */
+
+int akshar_version(void);
+const char* akshar_status_str(int code);
+int akshar_ctx_create(int device, akshar_ctx** out);
+void akshar_ctx_destroy(akshar_ctx* ctx);
+const char* akshar_last_error(akshar_ctx* ctx);
+
+/* bytes of device workspace the batch calls need for a buffer of n_bytes / n_rows */
+size_t akshar_workspace_bytes(int64_t n_bytes, int64_t n_rows);
+
+/* normalize_text over a batch (normalize.py:13-56, 92-148).  d_out_text capacity in bytes;
+ * d_out_row_offsets[n_rows + 1] always written.  result[0] = output bytes. */
+int akshar_normalize_batch(akshar_ctx* ctx, const uint8_t* d_text, const int64_t* d_row_offsets, int64_t n_rows,
+                           int64_t text_begin, int64_t text_end, uint32_t flags, int mode, uint8_t* d_out_text,
+                           int64_t out_capacity, int64_t* d_out_row_offsets, int64_t* d_result, void* d_workspace,
+                           size_t workspace_bytes, void* stream);
+
+/* segment_akshars / detect_code_switches over a batch (segment.py:40-201).
+ * cluster_ends / run_ends: int32 byte offset of each cluster / run END relative to its row start;
+ * run_tags: 0 devanagari 1 roman 2 digit 3 punct 4 other 255 None (identify_script, segment.py:128-147).
+ * Outputs not selected by `flags` may be NULL.  result[0] = clusters, result[1] = runs. */
+int akshar_segment_batch(akshar_ctx* ctx, const uint8_t* d_text, const int64_t* d_row_offsets, int64_t n_rows,
+                         int64_t text_begin, int64_t text_end, uint32_t flags, int mode, int32_t* d_cluster_ends,
+                         int64_t cluster_capacity, int64_t* d_cluster_splits, int32_t* d_run_ends, uint8_t* d_run_tags,
+                         int64_t run_capacity, int64_t* d_run_splits, int64_t* d_result, void* d_workspace,
+                         size_t workspace_bytes, void* stream);
+
+/* roman_phonetic_signature over a batch of words (normalize.py:59-89); one word per row. result[0] = out bytes */
+int akshar_signature_batch(akshar_ctx* ctx, const uint8_t* d_text, const int64_t* d_row_offsets, int64_t n_rows,
+                           int64_t text_begin, int64_t text_end, uint8_t* d_out_text, int64_t out_capacity,
+                           int64_t* d_out_row_offsets, int64_t* d_result, void* d_workspace, size_t workspace_bytes,
+                           void* stream);
+
+/* model loading (host buffers): the HF tokenizers JSON written by scripts/train_bpe.py:68-98 and the SentencePiece
+ * ModelProto written by scripts/train_spm.py:80-108 -- replaces Tokenizer.from_file / SentencePieceProcessor.Load
+ * (tokenizer.py:88-98). */
+int akshar_load_bpe_json(akshar_ctx* ctx, const char* json, size_t len);
+int akshar_load_spm_model(akshar_ctx* ctx, const void* proto, size_t len);
+/* vocabulary access for host-side decode / vocab_size (tokenizer.py:195-219, 278-288); kind 0 = BPE, 1 = Unigram */
+int akshar_vocab_size(akshar_ctx* ctx, int kind);
+/* returns the UTF-8 bytes of token `id` (not NUL-terminated) and its type:
+ * BPE: 0 normal, 1 special; Unigram: SentencePiece type (1 NORMAL 2 UNKNOWN 3 CONTROL 4 USER_DEFINED 5 UNUSED 6 BYTE) */
+int akshar_vocab_token(akshar_ctx* ctx, int kind, int id, const char** bytes, int* len, int* type);
+
+/* Tokenizer.encode(norm).ids over a batch of ALREADY NORMALIZED rows (tokenizer.py:193): ids include <s> / </s>
+ * from the template post-processor.  result[0] = ids. */
+int akshar_encode_bpe_batch(akshar_ctx* ctx, const uint8_t* d_text, const int64_t* d_row_offsets, int64_t n_rows,
+                            int64_t text_begin, int64_t text_end, int mode, int32_t* d_ids, int64_t id_capacity,
+                            int64_t* d_id_splits, int64_t* d_result, void* d_workspace, size_t workspace_bytes,
+                            void* stream);
+
+/* SentencePieceProcessor.EncodeAsIds(norm) over a batch of ALREADY NORMALIZED rows (tokenizer.py:191). */
+int akshar_encode_unigram_batch(akshar_ctx* ctx, const uint8_t* d_text, const int64_t* d_row_offsets, int64_t n_rows,
+                                int64_t text_begin, int64_t text_end, int mode, int32_t* d_ids, int64_t id_capacity,
+                                int64_t* d_id_splits, int64_t* d_result, void* d_workspace, size_t workspace_bytes,
+                                void* stream);
+
+/* number of kernels this library has launched on this context since creation (bench.py's gpu_launches) */
+int64_t akshar_launch_count(akshar_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

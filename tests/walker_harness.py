@@ -1,0 +1,72 @@
+"""ctypes wrapper around tests/_build/libak_host_harness.so (CPU build of the span walkers; test aid only)."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SO = os.path.join(ROOT, 'tests', '_build', 'libak_host_harness.so')
+_lib = None
+
+
+def build():
+    os.makedirs(os.path.dirname(SO), exist_ok=True)
+    src = os.path.join(ROOT, 'tests', 'csrc', 'host_harness.cpp')
+    deps = [src] + [os.path.join(ROOT, 'akshar_b200', 'csrc', f) for f in
+                    ('ak_unicode.cuh', 'ak_text_core.cuh', 'unicode_tables.inc')]
+    if not os.path.exists(SO) or any(os.path.getmtime(d) > os.path.getmtime(SO) for d in deps):
+        subprocess.check_call(['g++', '-O2', '-std=c++17', '-shared', '-fPIC', '-o', SO, src])
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        _lib = ctypes.CDLL(SO)
+        _lib.hh_normalize.restype = ctypes.c_int64
+    return _lib
+
+
+def _p(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+def make_spans(off, span, rng=None):
+    """span boundaries from off[0] to off[-1]+1; span=int fixed size, or random sizes in [1, span] with rng"""
+    lo, hi = int(off[0]), int(off[-1]) + 1
+    b = [lo]
+    while b[-1] < hi:
+        step = span if rng is None else int(rng.integers(1, span + 1))
+        b.append(min(hi, b[-1] + step))
+    return np.array(b, dtype=np.int64)
+
+
+def normalize(data, off, flags=3, span=32, limit=0, rng=None):
+    data = np.ascontiguousarray(data, dtype=np.uint8)
+    off = np.ascontiguousarray(off, dtype=np.int64)
+    spans = make_spans(off, span, rng)
+    out = np.zeros(int(data.size) * 3 + 16, dtype=np.uint8)
+    out_off = np.full(off.size, -1, dtype=np.int64)
+    st = ctypes.c_uint32(0)
+    n = lib().hh_normalize(_p(data), _p(off), ctypes.c_int64(off.size - 1), ctypes.c_uint32(flags), _p(spans),
+                           ctypes.c_int64(spans.size - 1), ctypes.c_int64(limit), _p(out), _p(out_off), ctypes.byref(st))
+    return out[:n], out_off, st.value
+
+
+def segment(data, off, flags=1, span=32, limit=0, rng=None):
+    data = np.ascontiguousarray(data, dtype=np.uint8)
+    off = np.ascontiguousarray(off, dtype=np.int64)
+    spans = make_spans(off, span, rng)
+    cap = int(data.size) + 1
+    ce = np.zeros(cap, dtype=np.int32)
+    cs = np.full(off.size, -1, dtype=np.int64)
+    re_ = np.zeros(cap, dtype=np.int32)
+    rt = np.zeros(cap, dtype=np.uint8)
+    rs = np.full(off.size, -1, dtype=np.int64)
+    tot = np.zeros(2, dtype=np.int64)
+    st = ctypes.c_uint32(0)
+    lib().hh_segment(_p(data), _p(off), ctypes.c_int64(off.size - 1), ctypes.c_uint32(flags), _p(spans),
+                     ctypes.c_int64(spans.size - 1), ctypes.c_int64(limit), _p(ce), _p(cs), _p(re_), _p(rt), _p(rs),
+                     ctypes.c_int64(cap), _p(tot), ctypes.byref(st))
+    return ce[:tot[0]], cs, re_[:tot[1]], rt[:tot[1]], rs, st.value
