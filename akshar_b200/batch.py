@@ -1,0 +1,349 @@
+"""Batch engine: the host side of the CUDA hot path.
+
+One `Engine` per device wraps a C-ABI context (include/akshar_b200.h).  Inputs are a batch of sentences as
+concatenated UTF-8 in HBM (`uint8[total]`) + `int64 row_offsets[n + 1]`; outputs are ragged device tensors
+(`Ragged(values, splits)`).  torch is used for device memory and streams only; all arithmetic is in
+libakshar_b200.so.  Each method mirrors, for a whole batch, the reference call named in its docstring.
+"""
+import ctypes
+from dataclasses import dataclass
+
+import torch
+
+from . import _lib as C
+
+
+@dataclass
+class Ragged:
+    """values[splits[i]:splits[i+1]] belongs to row i; `extra` carries a parallel values tensor (run tags)"""
+    values: torch.Tensor
+    splits: torch.Tensor
+    extra: torch.Tensor = None
+
+    def rows(self):
+        v = self.values.cpu().numpy()
+        s = self.splits.cpu().numpy()
+        return [v[s[i]:s[i + 1]] for i in range(len(s) - 1)]
+
+
+@dataclass
+class TextBatch:
+    """concatenated UTF-8 rows resident on the device"""
+    data: torch.Tensor         # uint8 [total]
+    offsets: torch.Tensor      # int64 [n + 1], absolute byte offsets into data
+    begin: int
+    end: int
+
+    @property
+    def n_rows(self):
+        return self.offsets.numel() - 1
+
+    @property
+    def n_bytes(self):
+        return self.end - self.begin
+
+    def to_strings(self):
+        b = self.data.cpu().numpy().tobytes()
+        o = self.offsets.cpu().numpy()
+        return [b[o[i]:o[i + 1]].decode('utf-8') for i in range(len(o) - 1)]
+
+
+class BatchStatusError(RuntimeError):
+    def __init__(self, bits, what):
+        self.bits = bits
+        names = [n for b, n in ((C.ST_OVERFLOW, 'overflow'), (C.ST_NFC_SEGMENT, 'combining sequence longer than 64'),
+                                (C.ST_PATHOLOGICAL, 'look-back limit'), (C.ST_ALPHABET, 'code point outside the closed alphabet'),
+                                (C.ST_SPIN, 'tile-prefix spin limit'), (C.ST_WORD, 'word longer than the scratch pool')) if bits & b]
+        super().__init__('%s: %s' % (what, ', '.join(names)))
+
+
+def pack_host(lines):
+    """list[str] -> (pinned uint8 tensor, pinned int64 offsets) on the host"""
+    enc = [s.encode('utf-8') for s in lines]
+    total = sum(len(e) for e in enc)
+    data = torch.empty(max(total, 1), dtype=torch.uint8).pin_memory()
+    off = torch.empty(len(enc) + 1, dtype=torch.int64).pin_memory()
+    if total:
+        data[:total] = torch.frombuffer(bytearray(b''.join(enc)), dtype=torch.uint8)
+    o = 0
+    offs = [0]
+    for e in enc:
+        o += len(e)
+        offs.append(o)
+    off.copy_(torch.tensor(offs, dtype=torch.int64))
+    return data[:total], off
+
+
+class Engine:
+    def __init__(self, device=0):
+        if not torch.cuda.is_available():
+            raise C.AksharCudaError('akshar_b200: no CUDA device; the batch path has no CPU fallback')
+        self.lib = C.load()
+        self.device = torch.device('cuda', device if isinstance(device, int) else torch.device(device).index or 0)
+        h = ctypes.c_void_p()
+        rc = self.lib.akshar_ctx_create(self.device.index, ctypes.byref(h))
+        self._h = h
+        if rc != 0:
+            msg = self.lib.akshar_last_error(h).decode() if h else 'out of memory'
+            raise C.AksharCudaError('akshar_ctx_create: ' + msg)
+        self._ws = None
+        self._vocab = {}
+
+    def __del__(self):
+        try:
+            if getattr(self, '_h', None):
+                self.lib.akshar_ctx_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ plumbing
+    def _err(self, rc, what):
+        raise C.AksharCudaError('%s: %s (%s)' % (what, self.lib.akshar_status_str(rc).decode(),
+                                                 self.lib.akshar_last_error(self._h).decode()))
+
+    def _workspace(self, n_bytes, n_rows):
+        need = self.lib.akshar_workspace_bytes(n_bytes, n_rows)
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = None
+            self._ws = torch.empty(need + (need >> 3), dtype=torch.uint8, device=self.device)
+        return self._ws
+
+    @staticmethod
+    def _stream():
+        return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    def launch_count(self):
+        return int(self.lib.akshar_launch_count(self._h))
+
+    def put(self, lines):
+        """host list[str] (or (uint8 tensor, int64 offsets) host tensors) -> TextBatch on the device"""
+        if isinstance(lines, TextBatch):
+            return lines
+        if isinstance(lines, (list, tuple)) and (len(lines) == 0 or isinstance(lines[0], str)):
+            data, off = pack_host(lines)
+        else:
+            data, off = lines
+        d = torch.empty(max(data.numel(), 1), dtype=torch.uint8, device=self.device)
+        d[:data.numel()].copy_(data, non_blocking=True)
+        o = off.to(self.device, non_blocking=True)
+        return TextBatch(d, o, int(off[0]), int(off[-1]))
+
+    def _finish(self, result, what, check):
+        if not check:
+            return None
+        r = result.cpu()
+        bits = int(r[2])
+        return int(r[0]), int(r[1]), bits
+
+    # ------------------------------------------------------------------ K1
+    def normalize_batch(self, batch, normalize_roman=True, clean_hinglish=True, mode=C.MODE_TILES, capacity=None, check=True):
+        """normalize_text over a batch (reference normalize.py:117-148) -> TextBatch"""
+        b = self.put(batch)
+        flags = (C.NORM_ROMAN if normalize_roman else 0) | (C.NORM_CLEAN if clean_hinglish else 0)
+        cap = capacity if capacity is not None else b.n_bytes + (b.n_bytes >> 3) + 1024
+        ws = self._workspace(b.n_bytes, b.n_rows)
+        while True:
+            out = torch.empty(max(cap, 1), dtype=torch.uint8, device=self.device)
+            out_off = torch.empty(b.n_rows + 1, dtype=torch.int64, device=self.device)
+            result = torch.empty(4, dtype=torch.int64, device=self.device)
+            rc = self.lib.akshar_normalize_batch(self._h, b.data.data_ptr(), b.offsets.data_ptr(), b.n_rows, b.begin, b.end,
+                                                 flags, mode, out.data_ptr(), cap, out_off.data_ptr(), result.data_ptr(),
+                                                 ws.data_ptr(), ws.numel(), self._stream())
+            if rc != 0:
+                self._err(rc, 'akshar_normalize_batch')
+            if not check:
+                return TextBatch(out, out_off, 0, -1), result
+            total, _, bits = self._finish(result, 'normalize', True)
+            if bits & C.ST_PATHOLOGICAL and mode == C.MODE_TILES:
+                mode = C.MODE_ROWS
+                continue
+            if bits & C.ST_OVERFLOW:
+                cap = total
+                continue
+            if bits:
+                raise BatchStatusError(bits, 'normalize_batch')
+            return TextBatch(out, out_off, 0, total)
+
+    # ------------------------------------------------------------------ K2 / K3
+    def segment_batch(self, batch, clusters=True, matras=False, runs=False, mode=C.MODE_TILES, capacity=None, check=True):
+        """segment_akshars / detect_code_switches over a batch (reference segment.py:40-201).
+        -> (clusters Ragged | None, runs Ragged | None); values are int32 END byte offsets relative to the row start"""
+        b = self.put(batch)
+        flags = (C.SEG_CLUSTERS if clusters else 0) | (C.SEG_MATRAS if matras else 0) | (C.SEG_RUNS if runs else 0)
+        ccap = rcap = 0
+        if clusters:
+            ccap = capacity if capacity is not None else (b.n_bytes >> 1) + b.n_rows + 1024
+        if runs:
+            rcap = capacity if capacity is not None else (b.n_bytes >> 3) + b.n_rows + 1024
+        ws = self._workspace(b.n_bytes, b.n_rows)
+        while True:
+            dev = self.device
+            ce = torch.empty(max(ccap, 1), dtype=torch.int32, device=dev) if clusters else None
+            cs = torch.empty(b.n_rows + 1, dtype=torch.int64, device=dev) if clusters else None
+            re_ = torch.empty(max(rcap, 1), dtype=torch.int32, device=dev) if runs else None
+            rt = torch.empty(max(rcap, 1), dtype=torch.uint8, device=dev) if runs else None
+            rs = torch.empty(b.n_rows + 1, dtype=torch.int64, device=dev) if runs else None
+            result = torch.empty(4, dtype=torch.int64, device=dev)
+            p = lambda t: t.data_ptr() if t is not None else None
+            rc = self.lib.akshar_segment_batch(self._h, b.data.data_ptr(), b.offsets.data_ptr(), b.n_rows, b.begin, b.end, flags,
+                                               mode, p(ce), ccap, p(cs), p(re_), p(rt), rcap, p(rs), result.data_ptr(),
+                                               ws.data_ptr(), ws.numel(), self._stream())
+            if rc != 0:
+                self._err(rc, 'akshar_segment_batch')
+            if check:
+                nc, nr, bits = self._finish(result, 'segment', True)
+                if bits & C.ST_PATHOLOGICAL and mode == C.MODE_TILES:
+                    mode = C.MODE_ROWS
+                    continue
+                if bits & C.ST_OVERFLOW:
+                    ccap, rcap = (nc if clusters else 0), (nr if runs else 0)
+                    continue
+                if bits:
+                    raise BatchStatusError(bits, 'segment_batch')
+                if clusters:
+                    ce = ce[:nc]
+                if runs:
+                    re_, rt = re_[:nr], rt[:nr]
+            co = Ragged(ce, cs) if clusters else None
+            ro = Ragged(re_, rs, rt) if runs else None
+            return (co, ro) if check else (co, ro, result)
+
+    # ------------------------------------------------------------------ K1b
+    def signature_batch(self, batch):
+        """roman_phonetic_signature over a batch of words, one per row (reference normalize.py:59-89) -> TextBatch"""
+        b = self.put(batch)
+        cap = b.n_bytes + (b.n_bytes >> 1) + 16
+        ws = self._workspace(b.n_bytes, b.n_rows)
+        out = torch.empty(max(cap, 1), dtype=torch.uint8, device=self.device)
+        out_off = torch.empty(b.n_rows + 1, dtype=torch.int64, device=self.device)
+        result = torch.empty(4, dtype=torch.int64, device=self.device)
+        rc = self.lib.akshar_signature_batch(self._h, b.data.data_ptr(), b.offsets.data_ptr(), b.n_rows, b.begin, b.end,
+                                             out.data_ptr(), cap, out_off.data_ptr(), result.data_ptr(), ws.data_ptr(),
+                                             ws.numel(), self._stream())
+        if rc != 0:
+            self._err(rc, 'akshar_signature_batch')
+        total, _, bits = self._finish(result, 'signature', True)
+        if bits:
+            raise BatchStatusError(bits, 'signature_batch')
+        return TextBatch(out, out_off, 0, total)
+
+    # ------------------------------------------------------------------ K4
+    def load_bpe(self, path_or_bytes):
+        """Tokenizer.from_file for the CUDA path (reference tokenizer.py:96-98)"""
+        data = path_or_bytes if isinstance(path_or_bytes, (bytes, bytearray)) else open(path_or_bytes, 'rb').read()
+        rc = self.lib.akshar_load_bpe_json(self._h, bytes(data), len(data))
+        if rc != 0:
+            self._err(rc, 'akshar_load_bpe_json')
+        self._vocab.pop(0, None)
+
+    def load_spm(self, path_or_bytes):
+        """SentencePieceProcessor.Load for the CUDA path (reference tokenizer.py:88-91)"""
+        data = path_or_bytes if isinstance(path_or_bytes, (bytes, bytearray)) else open(path_or_bytes, 'rb').read()
+        rc = self.lib.akshar_load_spm_model(self._h, bytes(data), len(data))
+        if rc != 0:
+            self._err(rc, 'akshar_load_spm_model')
+        self._vocab.pop(1, None)
+
+    def vocab(self, kind):
+        """[(token str, type)] by id; kind 0 BPE, 1 Unigram"""
+        if kind not in self._vocab:
+            n = self.lib.akshar_vocab_size(self._h, kind)
+            if n < 0:
+                self._err(n, 'akshar_vocab_size')
+            out = []
+            p, ln, ty = ctypes.c_void_p(), ctypes.c_int(), ctypes.c_int()
+            i = 0
+            while True:
+                rc = self.lib.akshar_vocab_token(self._h, kind, i, ctypes.byref(p), ctypes.byref(ln), ctypes.byref(ty))
+                if rc != 0:
+                    break
+                raw = ctypes.string_at(p.value, ln.value) if ln.value else b''
+                out.append((raw.decode('utf-8', errors='replace'), ty.value))
+                i += 1
+            self._vocab[kind] = (n, out)
+        return self._vocab[kind]
+
+    def _encode(self, fn, what, batch, mode, capacity, check):
+        b = self.put(batch)
+        cap = capacity if capacity is not None else (b.n_bytes >> 1) + 2 * b.n_rows + 1024
+        ws = self._workspace(b.n_bytes, b.n_rows)
+        while True:
+            ids = torch.empty(max(cap, 1), dtype=torch.int32, device=self.device)
+            splits = torch.empty(b.n_rows + 1, dtype=torch.int64, device=self.device)
+            result = torch.empty(4, dtype=torch.int64, device=self.device)
+            rc = fn(self._h, b.data.data_ptr(), b.offsets.data_ptr(), b.n_rows, b.begin, b.end, mode, ids.data_ptr(), cap,
+                    splits.data_ptr(), result.data_ptr(), ws.data_ptr(), ws.numel(), self._stream())
+            if rc != 0:
+                self._err(rc, what)
+            if not check:
+                return Ragged(ids, splits), result
+            total, _, bits = self._finish(result, what, True)
+            if bits & C.ST_PATHOLOGICAL and mode == C.MODE_TILES:
+                mode = C.MODE_ROWS
+                continue
+            if bits & C.ST_OVERFLOW:
+                cap = total
+                continue
+            if bits:
+                raise BatchStatusError(bits, what)
+            return Ragged(ids[:total], splits)
+
+    def encode_bpe_batch(self, batch, mode=C.MODE_TILES, capacity=None, check=True):
+        """Tokenizer.encode(norm).ids over ALREADY NORMALIZED rows (reference tokenizer.py:193) -> Ragged int32 ids"""
+        return self._encode(self.lib.akshar_encode_bpe_batch, 'encode_bpe_batch', batch, mode, capacity, check)
+
+    def encode_unigram_batch(self, batch, capacity=None, check=True):
+        """SentencePieceProcessor.EncodeAsIds(norm) over ALREADY NORMALIZED rows (reference tokenizer.py:191)"""
+        return self._encode(self.lib.akshar_encode_unigram_batch, 'encode_unigram_batch', batch, C.MODE_ROWS, capacity, check)
+
+
+    def tokenizer_encode_batch(self, batch, kind, normalize_roman=True, clean_hinglish=True, mode=C.MODE_TILES,
+                               capacity=None, check=True):
+        """aksharTokenizer.encode over RAW rows (reference tokenizer.py:167-193): normalize_text then the model, with no
+        host synchronisation in between.  kind 0 BPE, 1 Unigram.  -> (ids Ragged, normalized TextBatch)"""
+        b = self.put(batch)
+        flags = (C.NORM_ROMAN if normalize_roman else 0) | (C.NORM_CLEAN if clean_hinglish else 0)
+        ncap = b.n_bytes + (b.n_bytes >> 3) + 1024
+        cap = capacity if capacity is not None else (b.n_bytes >> 1) + 2 * b.n_rows + 1024
+        ws = self._workspace(ncap, b.n_rows)
+        while True:
+            dev = self.device
+            norm = torch.empty(max(ncap, 1), dtype=torch.uint8, device=dev)
+            norm_off = torch.empty(b.n_rows + 1, dtype=torch.int64, device=dev)
+            ids = torch.empty(max(cap, 1), dtype=torch.int32, device=dev)
+            splits = torch.empty(b.n_rows + 1, dtype=torch.int64, device=dev)
+            result = torch.empty(4, dtype=torch.int64, device=dev)
+            rc = self.lib.akshar_tokenizer_encode_batch(self._h, b.data.data_ptr(), b.offsets.data_ptr(), b.n_rows, b.begin,
+                                                        b.end, flags, kind, mode, norm.data_ptr(), ncap, norm_off.data_ptr(),
+                                                        ids.data_ptr(), cap, splits.data_ptr(), result.data_ptr(),
+                                                        ws.data_ptr(), ws.numel(), self._stream())
+            if rc != 0:
+                self._err(rc, 'akshar_tokenizer_encode_batch')
+            if not check:
+                return Ragged(ids, splits), TextBatch(norm, norm_off, 0, -1), result
+            total, nbytes, bits = self._finish(result, 'tokenizer_encode', True)
+            if bits & C.ST_PATHOLOGICAL and mode == C.MODE_TILES:
+                mode = C.MODE_ROWS
+                continue
+            if bits & C.ST_OVERFLOW:
+                # totals are exact even when a capacity was too small
+                cap = max(cap, total)
+                if nbytes > ncap:
+                    ncap = nbytes
+                    ws = self._workspace(ncap, b.n_rows)
+                    cap = max(cap, (ncap >> 1) + 2 * b.n_rows + 1024)
+                continue
+            if bits:
+                raise BatchStatusError(bits, 'tokenizer_encode_batch')
+            return Ragged(ids[:total], splits), TextBatch(norm, norm_off, 0, nbytes)
+
+
+_engines = {}
+
+
+def engine(device=0):
+    """process-wide engine per device"""
+    if device not in _engines:
+        _engines[device] = Engine(device)
+    return _engines[device]

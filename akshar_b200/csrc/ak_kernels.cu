@@ -1,0 +1,966 @@
+// libakshar_b200.so -- CUDA kernels (sm_100a) + the C ABI declared in include/akshar_b200.h.
+//
+// Every batch kernel is persistent (gridDim = SMs x resident CTAs); a CTA draws tile numbers from an atomic
+// ticket, each thread walks one byte span of the tile (ak_text_core.cuh / ak_subword.cuh), output positions
+// come from a block scan plus the single-pass ordered tile prefix in ak_scan.cuh, so the text is read from HBM
+// once and every output is written once.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/akshar_b200.h"
+#include "ak_models.h"
+#include "ak_scan.cuh"
+#include "ak_subword.cuh"
+#include "unicode_tables.inc"
+
+#define AK_BLOCK 256
+#define AK_SPAN 32
+#define AK_TILE (AK_BLOCK * AK_SPAN)
+#define AK_LOOKBACK_LIMIT 4096          // bytes a span may walk backwards in AKSHAR_MODE_TILES
+#define AK_BPE_STAGE 40                 // ids per thread staged in shared memory (>= AK_SPAN + a few <s> / </s>)
+#define AK_ROWS_BLOCK 128               // rows per tile for the row-per-thread kernels
+
+static_assert((int)AK_ST_OVERFLOW == (int)AKSHAR_ST_OVERFLOW && (int)AK_ST_NFC_SEGMENT == (int)AKSHAR_ST_NFC_SEGMENT &&
+              (int)AK_ST_PATHOLOGICAL == (int)AKSHAR_ST_PATHOLOGICAL && (int)AK_ST_ALPHABET == (int)AKSHAR_ST_ALPHABET &&
+              (int)AK_ST_SPIN == (int)AKSHAR_ST_SPIN && (int)AK_ST_WORD == (int)AKSHAR_ST_WORD, "status bits out of sync");
+static_assert(AK_NORM_ROMAN == AKSHAR_NORM_ROMAN && AK_NORM_CLEAN == AKSHAR_NORM_CLEAN && AK_NORM_FILTER == AKSHAR_NORM_FILTER &&
+              AK_NORM_COLLAPSE == AKSHAR_NORM_COLLAPSE && AK_NORM_NO_NFC == AKSHAR_NORM_NO_NFC, "flags out of sync");
+static_assert(AK_SEG_CLUSTERS == AKSHAR_SEG_CLUSTERS && AK_SEG_MATRAS == AKSHAR_SEG_MATRAS &&
+              AK_SEG_RUNS == AKSHAR_SEG_RUNS, "flags out of sync");
+
+// ------------------------------------------------------------------------------------------------
+// common kernel plumbing
+// ------------------------------------------------------------------------------------------------
+struct AkBatch {
+    const uint8_t* text;
+    const int64_t* off;
+    int64_t n_rows, text_begin, text_end;
+    int mode;
+    int n_tiles;
+    int* ticket;
+    unsigned long long* state0;
+    unsigned long long* state1;
+    int64_t* result;           // [4]; status bits are OR-ed into result[2]
+    int64_t* totals;           // [2]; normally == result
+    const unsigned int* run_if;   // non-null: the kernel is a no-op unless *run_if != 0
+    const int64_t* dyn_end;       // non-null: text_end = text_begin + *dyn_end (length produced by an earlier kernel)
+};
+
+// start-of-kernel resolution of the device-side conditionals; false = nothing to do
+__device__ __forceinline__ bool ak_batch_begin(AkBatch& B) {
+    if (B.run_if && *B.run_if == 0) return false;
+    if (B.dyn_end) {
+        B.text_end = B.text_begin + *B.dyn_end;
+        if (B.mode == AKSHAR_MODE_TILES) B.n_tiles = (int)((B.text_end - B.text_begin + AK_TILE) / AK_TILE);
+    }
+    return true;
+}
+
+struct AkSpan {
+    int64_t s, e, r_lo, r_hi, limit;
+};
+
+__device__ __forceinline__ void ak_raise(int64_t* result, uint32_t bits) {
+    if (bits) atomicOr((unsigned long long*)&result[2], (unsigned long long)bits);
+}
+
+// span of this thread inside `tile`; sh[0..1] is CTA scratch for the tile's row window
+__device__ __forceinline__ AkSpan ak_span_of(const AkBatch& B, int tile, int64_t* sh) {
+    AkSpan sp;
+    if (B.mode == AKSHAR_MODE_TILES) {
+        const int64_t t0 = B.text_begin + (int64_t)tile * AK_TILE;
+        int64_t t1 = t0 + AK_TILE;
+        if (t1 > B.text_end + 1) t1 = B.text_end + 1;
+        if (threadIdx.x == 0) {
+            int64_t lo = ak_row_lower_bound(B.off, 0, B.n_rows, t0);
+            sh[0] = lo > 0 ? lo - 1 : 0;
+            sh[1] = ak_row_lower_bound(B.off, lo, B.n_rows, t1);
+        }
+        __syncthreads();
+        sp.r_lo = sh[0];
+        sp.r_hi = sh[1];
+        sp.s = t0 + (int64_t)threadIdx.x * AK_SPAN;
+        sp.e = sp.s + AK_SPAN;
+        if (sp.e > t1) sp.e = t1;
+        if (sp.s > sp.e) sp.s = sp.e;
+        sp.limit = AK_LOOKBACK_LIMIT;
+    } else {
+        const int64_t r = (int64_t)tile * AK_BLOCK + threadIdx.x;
+        sp.r_lo = 0;
+        sp.r_hi = B.n_rows;
+        sp.limit = 0;
+        if (r < B.n_rows) {
+            sp.s = B.off[r];
+            sp.e = (r == B.n_rows - 1) ? B.text_end + 1 : B.off[r + 1];
+        } else {
+            sp.s = sp.e = 0;
+        }
+    }
+    return sp;
+}
+
+__device__ __forceinline__ int ak_next_tile(int* ticket, int* sh) {
+    __syncthreads();
+    if (threadIdx.x == 0) *sh = atomicAdd(ticket, 1);
+    __syncthreads();
+    return *sh;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1 normalize_text  (reference normalize.py:117-148)
+// ------------------------------------------------------------------------------------------------
+struct AkNormArgs {
+    AkBatch B;
+    AkTables T;
+    uint32_t flags;
+    uint8_t* out;
+    int64_t out_cap;
+    int64_t* out_off;
+};
+
+__global__ void __launch_bounds__(AK_BLOCK) ak_normalize_kernel(const AkNormArgs A) {
+    __shared__ int ws[33];
+    __shared__ int s_tile;
+    __shared__ int64_t s_win[2];
+    __shared__ long long s_base;
+    AkBatch B = A.B;
+    if (!ak_batch_begin(B)) return;
+    for (;;) {
+        const int tile = ak_next_tile(B.ticket, &s_tile);
+        if (tile >= B.n_tiles) break;
+        const AkSpan sp = ak_span_of(B, tile, s_win);
+        uint32_t st = 0;
+        int cnt = 0;
+        if (sp.s < sp.e)
+            cnt = (int)ak_norm_span(A.T, B.text, B.off, B.n_rows, sp.r_lo, sp.r_hi, sp.s, sp.e, A.flags, sp.limit, nullptr,
+                                    nullptr, 0, st);
+        int total;
+        const int pre = ak_block_exscan<AK_BLOCK>(cnt, ws, total);
+        if (threadIdx.x < 32) {
+            long long b = ak_tile_prefix(B.state0, tile, total, (unsigned int*)&B.result[2], AK_ST_SPIN);
+            if (threadIdx.x == 0) {
+                s_base = b;
+                if (tile == B.n_tiles - 1) B.totals[0] = b + total;
+            }
+        }
+        __syncthreads();
+        const int64_t obase = s_base + pre;
+        if (sp.s < sp.e) {
+            uint8_t* o = nullptr;
+            if (obase + cnt <= A.out_cap) o = A.out + obase;
+            else if (cnt > 0) st |= AK_ST_OVERFLOW;
+            uint32_t st2 = 0;
+            ak_norm_span(A.T, B.text, B.off, B.n_rows, sp.r_lo, sp.r_hi, sp.s, sp.e, A.flags, sp.limit, o, A.out_off, obase, st2);
+        }
+        ak_raise(B.result, st);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2 + K3 grapheme clusters and script runs  (reference segment.py:40-201)
+// ------------------------------------------------------------------------------------------------
+struct AkSegArgs {
+    AkBatch B;
+    AkTables T;
+    uint32_t flags;
+    AkSegOut o;
+};
+
+__global__ void __launch_bounds__(AK_BLOCK) ak_segment_kernel(const AkSegArgs A) {
+    __shared__ int ws[33];
+    __shared__ int s_tile;
+    __shared__ int64_t s_win[2];
+    __shared__ long long s_base[2];
+    AkBatch B = A.B;
+    if (!ak_batch_begin(B)) return;
+    for (;;) {
+        const int tile = ak_next_tile(B.ticket, &s_tile);
+        if (tile >= B.n_tiles) break;
+        const AkSpan sp = ak_span_of(B, tile, s_win);
+        uint32_t st = 0;
+        int64_t cc = 0, rc = 0;
+        AkSegOut o = A.o;
+        if (sp.s < sp.e)
+            ak_seg_span(A.T, B.text, B.off, B.n_rows, sp.r_lo, sp.r_hi, sp.s, sp.e, A.flags, sp.limit, false, o, cc, rc, st);
+        int ctot, rtot;
+        const int cpre = ak_block_exscan<AK_BLOCK>((int)cc, ws, ctot);
+        const int rpre = ak_block_exscan<AK_BLOCK>((int)rc, ws, rtot);
+        if (threadIdx.x < 32) {
+            long long cb = ak_tile_prefix(B.state0, tile, ctot, (unsigned int*)&B.result[2], AK_ST_SPIN);
+            long long rb = ak_tile_prefix(B.state1, tile, rtot, (unsigned int*)&B.result[2], AK_ST_SPIN);
+            if (threadIdx.x == 0) {
+                s_base[0] = cb;
+                s_base[1] = rb;
+                if (tile == B.n_tiles - 1) { B.totals[0] = cb + ctot; B.totals[1] = rb + rtot; }
+            }
+        }
+        __syncthreads();
+        if (sp.s < sp.e) {
+            o.cbase = s_base[0] + cpre;
+            o.rbase = s_base[1] + rpre;
+            if (o.cbase + cc > o.ccap || o.rbase + rc > o.rcap) st |= AK_ST_OVERFLOW;
+            uint32_t st2 = 0;
+            int64_t c2, r2;
+            ak_seg_span(A.T, B.text, B.off, B.n_rows, sp.r_lo, sp.r_hi, sp.s, sp.e, A.flags, sp.limit, true, o, c2, r2, st2);
+        }
+        ak_raise(B.result, st);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K4a BPE encode  (reference tokenizer.py:193)
+// ------------------------------------------------------------------------------------------------
+struct AkBpeArgs {
+    AkBatch B;
+    AkTables T;
+    AkBpeDev M;
+    AkPool pool;
+    int32_t* ids;
+    int64_t id_cap;
+    int64_t* id_splits;
+    unsigned int* changed;          // set when NFC would change the text (results are then recomputed)
+};
+
+__global__ void __launch_bounds__(AK_BLOCK) ak_bpe_kernel(const AkBpeArgs A) {
+    __shared__ int ws[33];
+    __shared__ int s_tile;
+    __shared__ int64_t s_win[2];
+    __shared__ long long s_base;
+    __shared__ int32_t stage[AK_BPE_STAGE * AK_BLOCK];
+    AkBatch B = A.B;
+    if (!ak_batch_begin(B)) return;
+    for (;;) {
+        const int tile = ak_next_tile(B.ticket, &s_tile);
+        if (tile >= B.n_tiles) break;
+        const AkSpan sp = ak_span_of(B, tile, s_win);
+        uint32_t st = 0;
+        bool changed = false;
+        AkIdSink sink;
+        sink.buf = stage + threadIdx.x;
+        sink.cap = AK_BPE_STAGE;
+        sink.stride = AK_BLOCK;
+        sink.cnt = 0;
+        sink.direct = false;
+        sink.gout = A.ids;
+        sink.gbase = 0;
+        sink.gcap = A.id_cap;
+        int64_t row_first = 0, row_last = 0;
+        if (sp.s < sp.e)
+            ak_bpe_span(A.M, A.T, B.text, B.off, B.n_rows, sp.r_lo, sp.r_hi, sp.s, sp.e, sp.limit, sink, A.id_splits, 0,
+                        row_first, row_last, A.pool, changed, st);
+        const int cnt = sink.cnt;
+        int total;
+        const int pre = ak_block_exscan<AK_BLOCK>(cnt, ws, total);
+        if (threadIdx.x < 32) {
+            long long b = ak_tile_prefix(B.state0, tile, total, (unsigned int*)&B.result[2], AK_ST_SPIN);
+            if (threadIdx.x == 0) {
+                s_base = b;
+                if (tile == B.n_tiles - 1) B.totals[0] = b + total;
+            }
+        }
+        __syncthreads();
+        const int64_t obase = s_base + pre;
+        if (sp.s < sp.e) {
+            if (obase + cnt > A.id_cap) st |= AK_ST_OVERFLOW;
+            for (int64_t r = row_first; r < row_last; ++r) A.id_splits[r] += obase;     // span-relative -> global
+            if (cnt <= AK_BPE_STAGE) {
+                for (int i = 0; i < cnt; ++i)
+                    if (obase + i < A.id_cap) A.ids[obase + i] = stage[i * AK_BLOCK + threadIdx.x];
+            } else {
+                // did not fit the stage (many empty rows or very dense words): walk again straight to global memory
+                AkIdSink s2 = sink;
+                s2.cnt = 0;
+                s2.direct = true;
+                s2.gbase = obase;
+                uint32_t st2 = 0;
+                bool ch2 = false;
+                int64_t a, b;
+                ak_bpe_span(A.M, A.T, B.text, B.off, B.n_rows, sp.r_lo, sp.r_hi, sp.s, sp.e, sp.limit, s2, nullptr, 0, a, b,
+                            A.pool, ch2, st2);
+            }
+        }
+        if (changed) atomicOr(A.changed, 1u);
+        ak_raise(B.result, st);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K4b Unigram encode  (reference tokenizer.py:191): one row per thread, Viterbi ring in registers / local memory,
+// final back-pointers in a global scratch (4 B per code point), ids written backwards from the row's end.
+// ------------------------------------------------------------------------------------------------
+struct AkUniArgs {
+    AkBatch B;
+    AkUniDev U;
+    uint32_t* back;            // scratch: row r uses back[(off[r] - text_begin) + 2 r ...]
+    int32_t* ids;
+    int64_t id_cap;
+    int64_t* id_splits;
+};
+
+__global__ void __launch_bounds__(AK_ROWS_BLOCK) ak_unigram_kernel(const AkUniArgs A) {
+    __shared__ int ws[33];
+    __shared__ int s_tile;
+    __shared__ long long s_base;
+    AkBatch B = A.B;
+    if (!ak_batch_begin(B)) return;
+    for (;;) {
+        const int tile = ak_next_tile(B.ticket, &s_tile);
+        if (tile >= B.n_tiles) break;
+        const int64_t r = (int64_t)tile * AK_ROWS_BLOCK + threadIdx.x;
+        int64_t n = 0, cnt = 0;
+        uint32_t* back = nullptr;
+        if (r < B.n_rows) {
+            const int64_t rs = B.off[r], re = B.off[r + 1];
+            back = A.back + (rs - B.text_begin) + 2 * r;
+            n = ak_unigram_forward(A.U, B.text, rs, re, back);
+            cnt = ak_unigram_backtrack(A.U, back, n, nullptr, 0, 0);
+        }
+        int total;
+        const int pre = ak_block_exscan<AK_ROWS_BLOCK>((int)cnt, ws, total);
+        if (threadIdx.x < 32) {
+            long long b = ak_tile_prefix(B.state0, tile, total, (unsigned int*)&B.result[2], AK_ST_SPIN);
+            if (threadIdx.x == 0) {
+                s_base = b;
+                if (tile == B.n_tiles - 1) B.totals[0] = b + total;
+            }
+        }
+        __syncthreads();
+        if (r < B.n_rows) {
+            const int64_t obase = s_base + pre;
+            A.id_splits[r] = obase;
+            if (r == B.n_rows - 1) A.id_splits[B.n_rows] = obase + cnt;
+            if (obase + cnt > A.id_cap) ak_raise(B.result, AK_ST_OVERFLOW);
+            ak_unigram_backtrack(A.U, back, n, A.ids, obase + cnt, A.id_cap);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1b roman_phonetic_signature  (reference normalize.py:59-89): one word per row, one row per thread.
+// lower() [all scripts, Final_Sigma] -> collapse runs >= 3 -> ee$ -> i, oo$ -> u -> aa kh gh ch th ph bh dh.
+// ------------------------------------------------------------------------------------------------
+struct AkSigArgs {
+    AkBatch B;
+    AkTables T;
+    uint32_t* cps;             // scratch: one uint32 per input byte
+    uint8_t* out;
+    int64_t out_cap;
+    int64_t* out_off;
+};
+
+__global__ void __launch_bounds__(AK_ROWS_BLOCK) ak_signature_kernel(const AkSigArgs A) {
+    __shared__ int ws[33];
+    __shared__ int s_tile;
+    __shared__ long long s_base;
+    AkBatch B = A.B;
+    if (!ak_batch_begin(B)) return;
+    for (;;) {
+        const int tile = ak_next_tile(B.ticket, &s_tile);
+        if (tile >= B.n_tiles) break;
+        const int64_t r = (int64_t)tile * AK_ROWS_BLOCK + threadIdx.x;
+        int n = 0, cnt = 0;
+        uint32_t* a = nullptr;
+        if (r < B.n_rows) {
+            const int64_t rs = B.off[r], re = B.off[r + 1];
+            a = A.cps + (rs - B.text_begin);
+            n = ak_signature_row(A.T, B.text, rs, re, a);
+            for (int i = 0; i < n; ++i) cnt += ak_utf8_len(a[i]);
+        }
+        int total;
+        const int pre = ak_block_exscan<AK_ROWS_BLOCK>(cnt, ws, total);
+        if (threadIdx.x < 32) {
+            long long b = ak_tile_prefix(B.state0, tile, total, (unsigned int*)&B.result[2], AK_ST_SPIN);
+            if (threadIdx.x == 0) {
+                s_base = b;
+                if (tile == B.n_tiles - 1) B.totals[0] = b + total;
+            }
+        }
+        __syncthreads();
+        if (r < B.n_rows) {
+            const int64_t obase = s_base + pre;
+            A.out_off[r] = obase;
+            if (r == B.n_rows - 1) A.out_off[B.n_rows] = obase + cnt;
+            if (obase + cnt <= A.out_cap) {
+                uint8_t* o = A.out + obase;
+                for (int i = 0; i < n; ++i) o += ak_encode(a[i], o);
+            } else {
+                ak_raise(B.result, AK_ST_OVERFLOW);
+            }
+        }
+    }
+}
+
+// ================================================================================================
+// host side: context, model upload, C ABI
+// ================================================================================================
+struct akshar_ctx {
+    int device = 0;
+    int sm_count = 148;
+    AkTables T{};
+    std::vector<void*> allocs;
+    std::string err;
+    int64_t launches = 0;
+    bool has_bpe = false, has_uni = false;
+    AkBpeHost bpe_h;
+    AkBpeDev bpe_d{};
+    AkUniHost uni_h;
+    AkUniDev uni_d{};
+    std::vector<void*> bpe_allocs, uni_allocs;
+    int occ_norm = 0, occ_seg = 0, occ_bpe = 0, occ_uni = 0, occ_sig = 0;
+};
+
+#define AK_CUDA(ctx, call)                                                                         \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            (ctx)->err = std::string(#call) + ": " + cudaGetErrorString(e_);                       \
+            return AKSHAR_E_CUDA;                                                                  \
+        }                                                                                          \
+    } while (0)
+
+template <class V>
+static int ak_upload(akshar_ctx* ctx, std::vector<void*>& owner, const V* src, size_t n, const V** dst) {
+    void* d = nullptr;
+    size_t bytes = (n ? n : 1) * sizeof(V);
+    AK_CUDA(ctx, cudaMalloc(&d, bytes));
+    owner.push_back(d);
+    if (n) AK_CUDA(ctx, cudaMemcpy(d, src, n * sizeof(V), cudaMemcpyHostToDevice));
+    *dst = (const V*)d;
+    return 0;
+}
+
+extern "C" {
+
+int akshar_version(void) { return 100; }
+
+const char* akshar_status_str(int code) {
+    switch (code) {
+        case AKSHAR_OK: return "ok";
+        case AKSHAR_E_ARG: return "bad argument";
+        case AKSHAR_E_CUDA: return "CUDA error";
+        case AKSHAR_E_MODEL: return "model could not be parsed or uses an unsupported configuration";
+        case AKSHAR_E_NOMODEL: return "no model loaded for this encoder";
+        case AKSHAR_E_WORKSPACE: return "workspace too small";
+        default: return "unknown";
+    }
+}
+
+int akshar_ctx_create(int device, akshar_ctx** out) {
+    if (!out) return AKSHAR_E_ARG;
+    *out = nullptr;
+    akshar_ctx* ctx = new (std::nothrow) akshar_ctx();
+    if (!ctx) return AKSHAR_E_ARG;
+    ctx->device = device;
+    *out = ctx;      // returned even on failure so that akshar_last_error can be read; caller destroys it
+    AK_CUDA(ctx, cudaSetDevice(device));
+    cudaDeviceProp prop;
+    AK_CUDA(ctx, cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) {
+        ctx->err = "akshar_b200 is built for sm_100a (B200); device is sm_" + std::to_string(prop.major * 10 + prop.minor);
+        return AKSHAR_E_CUDA;
+    }
+    ctx->sm_count = prop.multiProcessorCount;
+    int rc;
+#define UP(field, arr, n, type) \
+    if ((rc = ak_upload<type>(ctx, ctx->allocs, (const type*)(arr), (size_t)(n), (const type**)&ctx->T.field))) return rc;
+    UP(page_index, ak_tbl_page_index, AK_N_PAGES, uint16_t)
+    UP(leaves, ak_tbl_leaves, AK_N_LEAF_PAGES * 256, uint32_t)
+    UP(decomp_keys, ak_tbl_decomp_keys, AK_N_DECOMP, uint32_t)
+    UP(decomp_off, ak_tbl_decomp_off, AK_N_DECOMP + 1, uint16_t)
+    UP(decomp_data, ak_tbl_decomp_data, AK_N_DECOMP_DATA, uint32_t)
+    UP(pair_keys, ak_tbl_pair_keys, AK_N_PAIRS, unsigned long long)
+    UP(pair_vals, ak_tbl_pair_vals, AK_N_PAIRS, uint32_t)
+    UP(ll_keys, ak_tbl_latin_lower_keys, AK_N_LATIN_LOWER, uint32_t)
+    UP(ll_vals, ak_tbl_latin_lower_vals, AK_N_LATIN_LOWER, uint32_t)
+    UP(fl_keys, ak_tbl_full_lower_keys, AK_N_FULL_LOWER, uint32_t)
+    UP(fl_vals, ak_tbl_full_lower_vals, AK_N_FULL_LOWER, uint32_t)
+#undef UP
+    ctx->T.n_decomp = AK_N_DECOMP;
+    ctx->T.n_pairs = AK_N_PAIRS;
+    ctx->T.n_ll = AK_N_LATIN_LOWER;
+    ctx->T.n_fl = AK_N_FULL_LOWER;
+    AK_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_norm, ak_normalize_kernel, AK_BLOCK, 0));
+    AK_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_seg, ak_segment_kernel, AK_BLOCK, 0));
+    AK_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_bpe, ak_bpe_kernel, AK_BLOCK, 0));
+    AK_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_uni, ak_unigram_kernel, AK_ROWS_BLOCK, 0));
+    AK_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_sig, ak_signature_kernel, AK_ROWS_BLOCK, 0));
+    return AKSHAR_OK;
+}
+
+static void ak_free_list(std::vector<void*>& v) {
+    for (void* p : v) cudaFree(p);
+    v.clear();
+}
+
+void akshar_ctx_destroy(akshar_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    ak_free_list(ctx->allocs);
+    ak_free_list(ctx->bpe_allocs);
+    ak_free_list(ctx->uni_allocs);
+    delete ctx;
+}
+
+const char* akshar_last_error(akshar_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int64_t akshar_launch_count(akshar_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+// workspace layout (all regions 256-byte aligned):
+//   [0, 256)            control block: tickets[8] (int), changed flag, pool cursor
+//   state regions       4 x n_tiles x 8 bytes (two counters x two passes)
+//   scratch             max(unigram back-pointers 4 (n_bytes + 2 n_rows + 2), signature code points 4 n_bytes,
+//                           BPE: NFC'd text n_bytes + n_bytes / 8 + 1024, its row offsets 8 (n_rows + 1), long-word pool)
+static inline size_t ak_align(size_t x) { return (x + 255) & ~(size_t)255; }
+static inline int64_t ak_tiles_of(int64_t n_bytes, int64_t n_rows) {
+    int64_t a = (n_bytes + n_bytes / 8 + 1024 + 1 + AK_TILE - 1) / AK_TILE;     // covers the NFC'd copy too
+    int64_t b = (n_rows + AK_ROWS_BLOCK - 1) / AK_ROWS_BLOCK;
+    return (a > b ? a : b) + 1;
+}
+static inline size_t ak_pool_ints(int64_t n_bytes) {
+    int64_t p = n_bytes / 2 + (1 << 16);
+    return (size_t)p;
+}
+struct AkWsLayout {
+    size_t control, state, nfc_text, nfc_off, pool, scratch, total;
+    int64_t nfc_cap;
+};
+static AkWsLayout ak_ws_layout(int64_t n_bytes, int64_t n_rows) {
+    AkWsLayout L;
+    size_t tiles = (size_t)ak_tiles_of(n_bytes, n_rows);
+    L.control = 0;
+    L.state = 256;
+    size_t at = L.state + ak_align(4 * tiles * 8);
+    L.scratch = at;
+    size_t uni = 4 * (size_t)(n_bytes + 2 * n_rows + 2);
+    L.nfc_cap = n_bytes + n_bytes / 8 + 1024;
+    L.nfc_text = at;
+    L.nfc_off = L.nfc_text + ak_align((size_t)L.nfc_cap);
+    L.pool = L.nfc_off + ak_align(8 * (size_t)(n_rows + 1));
+    size_t bpe = (L.pool + ak_align(4 * ak_pool_ints(n_bytes))) - at;
+    L.total = at + ak_align(uni > bpe ? uni : bpe);
+    return L;
+}
+
+size_t akshar_workspace_bytes(int64_t n_bytes, int64_t n_rows) {
+    if (n_bytes < 0 || n_rows < 0) return 0;
+    return ak_ws_layout(n_bytes, n_rows).total;
+}
+
+struct AkCall {
+    akshar_ctx* ctx;
+    AkBatch B;
+    AkWsLayout L;
+    char* ws;
+    cudaStream_t stream;
+};
+
+// validates the common arguments, clears the control block + result, fills AkBatch (tiles for `mode`)
+static int ak_begin(akshar_ctx* ctx, const uint8_t* d_text, const int64_t* d_row_offsets, int64_t n_rows, int64_t text_begin,
+                    int64_t text_end, int mode, int rows_block, int64_t* d_result, void* d_workspace, size_t workspace_bytes,
+                    void* stream, AkCall& C) {
+    if (!ctx) return AKSHAR_E_ARG;
+    if (!d_row_offsets || !d_result || n_rows < 0 || text_end < text_begin || (!d_text && text_end > text_begin) ||
+        (mode != AKSHAR_MODE_TILES && mode != AKSHAR_MODE_ROWS)) {
+        ctx->err = "bad argument";
+        return AKSHAR_E_ARG;
+    }
+    const int64_t n_bytes = text_end - text_begin;
+    C.ctx = ctx;
+    C.L = ak_ws_layout(n_bytes, n_rows);
+    if (!d_workspace || workspace_bytes < C.L.total) {
+        ctx->err = "workspace too small: need " + std::to_string(C.L.total) + " bytes";
+        return AKSHAR_E_WORKSPACE;
+    }
+    C.ws = (char*)d_workspace;
+    C.stream = (cudaStream_t)stream;
+    AK_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t tiles = (size_t)ak_tiles_of(n_bytes, n_rows);
+    AK_CUDA(ctx, cudaMemsetAsync(C.ws, 0, 256 + ak_align(4 * tiles * 8), C.stream));
+    AK_CUDA(ctx, cudaMemsetAsync(d_result, 0, 4 * sizeof(int64_t), C.stream));
+    AkBatch& B = C.B;
+    B.text = d_text;
+    B.off = d_row_offsets;
+    B.n_rows = n_rows;
+    B.text_begin = text_begin;
+    B.text_end = text_end;
+    B.mode = mode;
+    if (rows_block > 0) B.n_tiles = (int)((n_rows + rows_block - 1) / rows_block);
+    else if (mode == AKSHAR_MODE_TILES) B.n_tiles = (int)((n_bytes + 1 + AK_TILE - 1) / AK_TILE);
+    else B.n_tiles = (int)((n_rows + AK_BLOCK - 1) / AK_BLOCK);
+    B.ticket = (int*)C.ws;
+    B.state0 = (unsigned long long*)(C.ws + C.L.state);
+    B.state1 = B.state0 + tiles;
+    B.result = d_result;
+    B.totals = d_result;
+    B.run_if = nullptr;
+    B.dyn_end = nullptr;
+    return AKSHAR_OK;
+}
+
+static int ak_grid(akshar_ctx* ctx, int occ, int n_tiles) {
+    int g = ctx->sm_count * (occ > 0 ? occ : 1);
+    return n_tiles < g ? (n_tiles > 0 ? n_tiles : 1) : g;
+}
+
+static int ak_after_launch(akshar_ctx* ctx, const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        ctx->err = std::string(what) + " launch: " + cudaGetErrorString(e);
+        return AKSHAR_E_CUDA;
+    }
+    ctx->launches++;
+    return AKSHAR_OK;
+}
+
+// a batch with no rows: every ragged output is just splits[0] = 0
+static int ak_empty_rows(akshar_ctx* ctx, int64_t* a, int64_t* b, cudaStream_t s) {
+    if (a) AK_CUDA(ctx, cudaMemsetAsync(a, 0, sizeof(int64_t), s));
+    if (b) AK_CUDA(ctx, cudaMemsetAsync(b, 0, sizeof(int64_t), s));
+    return AKSHAR_OK;
+}
+
+int akshar_normalize_batch(akshar_ctx* ctx, const uint8_t* d_text, const int64_t* d_row_offsets, int64_t n_rows,
+                           int64_t text_begin, int64_t text_end, uint32_t flags, int mode, uint8_t* d_out_text,
+                           int64_t out_capacity, int64_t* d_out_row_offsets, int64_t* d_result, void* d_workspace,
+                           size_t workspace_bytes, void* stream) {
+    AkCall C;
+    int rc = ak_begin(ctx, d_text, d_row_offsets, n_rows, text_begin, text_end, mode, 0, d_result, d_workspace, workspace_bytes,
+                      stream, C);
+    if (rc) return rc;
+    if (!d_out_row_offsets || out_capacity < 0 || (!d_out_text && out_capacity > 0) || (flags & ~15u)) {
+        ctx->err = "bad argument";
+        return AKSHAR_E_ARG;
+    }
+    if (n_rows == 0) return ak_empty_rows(ctx, d_out_row_offsets, nullptr, C.stream);
+    AkNormArgs A;
+    A.B = C.B;
+    A.T = ctx->T;
+    A.flags = flags;
+    A.out = d_out_text;
+    A.out_cap = out_capacity;
+    A.out_off = d_out_row_offsets;
+    ak_normalize_kernel<<<ak_grid(ctx, ctx->occ_norm, A.B.n_tiles), AK_BLOCK, 0, C.stream>>>(A);
+    return ak_after_launch(ctx, "normalize");
+}
+
+int akshar_segment_batch(akshar_ctx* ctx, const uint8_t* d_text, const int64_t* d_row_offsets, int64_t n_rows,
+                         int64_t text_begin, int64_t text_end, uint32_t flags, int mode, int32_t* d_cluster_ends,
+                         int64_t cluster_capacity, int64_t* d_cluster_splits, int32_t* d_run_ends, uint8_t* d_run_tags,
+                         int64_t run_capacity, int64_t* d_run_splits, int64_t* d_result, void* d_workspace,
+                         size_t workspace_bytes, void* stream) {
+    AkCall C;
+    int rc = ak_begin(ctx, d_text, d_row_offsets, n_rows, text_begin, text_end, mode, 0, d_result, d_workspace, workspace_bytes,
+                      stream, C);
+    if (rc) return rc;
+    const bool want_c = (flags & AKSHAR_SEG_CLUSTERS) != 0, want_r = (flags & AKSHAR_SEG_RUNS) != 0;
+    if ((flags & ~7u) || (!want_c && !want_r) || ((flags & AKSHAR_SEG_MATRAS) && !want_c) ||
+        (want_c && (!d_cluster_splits || cluster_capacity < 0 || (!d_cluster_ends && cluster_capacity > 0))) ||
+        (want_r && (!d_run_splits || run_capacity < 0 || ((!d_run_ends || !d_run_tags) && run_capacity > 0)))) {
+        ctx->err = "bad argument";
+        return AKSHAR_E_ARG;
+    }
+    if (n_rows == 0) return ak_empty_rows(ctx, want_c ? d_cluster_splits : nullptr, want_r ? d_run_splits : nullptr, C.stream);
+    AkSegArgs A;
+    A.B = C.B;
+    A.T = ctx->T;
+    A.flags = flags;
+    A.o.cluster_ends = d_cluster_ends;
+    A.o.cluster_splits = d_cluster_splits;
+    A.o.run_ends = d_run_ends;
+    A.o.run_tags = d_run_tags;
+    A.o.run_splits = d_run_splits;
+    A.o.cbase = A.o.rbase = 0;
+    A.o.ccap = want_c ? cluster_capacity : 0;
+    A.o.rcap = want_r ? run_capacity : 0;
+    ak_segment_kernel<<<ak_grid(ctx, ctx->occ_seg, A.B.n_tiles), AK_BLOCK, 0, C.stream>>>(A);
+    return ak_after_launch(ctx, "segment");
+}
+
+int akshar_signature_batch(akshar_ctx* ctx, const uint8_t* d_text, const int64_t* d_row_offsets, int64_t n_rows,
+                           int64_t text_begin, int64_t text_end, uint8_t* d_out_text, int64_t out_capacity,
+                           int64_t* d_out_row_offsets, int64_t* d_result, void* d_workspace, size_t workspace_bytes,
+                           void* stream) {
+    AkCall C;
+    int rc = ak_begin(ctx, d_text, d_row_offsets, n_rows, text_begin, text_end, AKSHAR_MODE_ROWS, AK_ROWS_BLOCK, d_result,
+                      d_workspace, workspace_bytes, stream, C);
+    if (rc) return rc;
+    if (!d_out_row_offsets || out_capacity < 0 || (!d_out_text && out_capacity > 0)) {
+        ctx->err = "bad argument";
+        return AKSHAR_E_ARG;
+    }
+    if (n_rows == 0) return ak_empty_rows(ctx, d_out_row_offsets, nullptr, C.stream);
+    AkSigArgs A;
+    A.B = C.B;
+    A.T = ctx->T;
+    A.cps = (uint32_t*)(C.ws + C.L.scratch);
+    A.out = d_out_text;
+    A.out_cap = out_capacity;
+    A.out_off = d_out_row_offsets;
+    ak_signature_kernel<<<ak_grid(ctx, ctx->occ_sig, A.B.n_tiles), AK_ROWS_BLOCK, 0, C.stream>>>(A);
+    return ak_after_launch(ctx, "signature");
+}
+
+int akshar_load_bpe_json(akshar_ctx* ctx, const char* json, size_t len) {
+    if (!ctx || !json) return AKSHAR_E_ARG;
+    AkBpeHost h;
+    std::string e = ak_parse_bpe_json(json, len, h);
+    if (!e.empty()) {
+        ctx->err = e;
+        return AKSHAR_E_MODEL;
+    }
+    AK_CUDA(ctx, cudaSetDevice(ctx->device));
+    AK_CUDA(ctx, cudaDeviceSynchronize());
+    ak_free_list(ctx->bpe_allocs);
+    ctx->has_bpe = false;
+    AkBpeDev d{};
+    int rc;
+    if ((rc = ak_upload<int32_t>(ctx, ctx->bpe_allocs, h.cp_direct.data(), h.cp_direct.size(), &d.cp_direct))) return rc;
+    if ((rc = ak_upload<uint32_t>(ctx, ctx->bpe_allocs, h.cp_keys.data(), h.cp_keys.size(), &d.cp_keys))) return rc;
+    if ((rc = ak_upload<int32_t>(ctx, ctx->bpe_allocs, h.cp_ids.data(), h.cp_ids.size(), &d.cp_ids))) return rc;
+    if ((rc = ak_upload<unsigned long long>(ctx, ctx->bpe_allocs, h.mkeys.data(), h.mkeys.size(), &d.mkeys))) return rc;
+    if ((rc = ak_upload<unsigned long long>(ctx, ctx->bpe_allocs, h.mvals.data(), h.mvals.size(), &d.mvals))) return rc;
+    d.n_cp = (int)h.cp_keys.size();
+    d.mbits = h.mbits;
+    d.bos = h.bos;
+    d.eos = h.eos;
+    ctx->bpe_d = d;
+    ctx->bpe_h = std::move(h);
+    ctx->has_bpe = true;
+    return AKSHAR_OK;
+}
+
+int akshar_load_spm_model(akshar_ctx* ctx, const void* proto, size_t len) {
+    if (!ctx || !proto) return AKSHAR_E_ARG;
+    AkUniHost h;
+    std::string e = ak_parse_spm_model(proto, len, h);
+    if (!e.empty()) {
+        ctx->err = e;
+        return AKSHAR_E_MODEL;
+    }
+    AK_CUDA(ctx, cudaSetDevice(ctx->device));
+    AK_CUDA(ctx, cudaDeviceSynchronize());
+    ak_free_list(ctx->uni_allocs);
+    ctx->has_uni = false;
+    AkUniDev d{};
+    int rc;
+    if ((rc = ak_upload<unsigned long long>(ctx, ctx->uni_allocs, h.tkeys.data(), h.tkeys.size(), &d.tkeys))) return rc;
+    if ((rc = ak_upload<unsigned long long>(ctx, ctx->uni_allocs, h.tvals.data(), h.tvals.size(), &d.tvals))) return rc;
+    if ((rc = ak_upload<float>(ctx, ctx->uni_allocs, h.score.data(), h.score.size(), &d.score))) return rc;
+    if ((rc = ak_upload<uint8_t>(ctx, ctx->uni_allocs, h.usable.data(), h.usable.size(), &d.usable))) return rc;
+    if ((rc = ak_upload<int32_t>(ctx, ctx->uni_allocs, h.byte_id, 256, &d.byte_id))) return rc;
+    d.tbits = h.tbits;
+    d.unk_id = h.unk_id;
+    d.unk_score = h.unk_score;
+    d.flags = h.flags;
+    ctx->uni_d = d;
+    ctx->uni_h = std::move(h);
+    ctx->has_uni = true;
+    return AKSHAR_OK;
+}
+
+int akshar_vocab_size(akshar_ctx* ctx, int kind) {
+    if (!ctx) return AKSHAR_E_ARG;
+    if (kind == 0) return ctx->has_bpe ? ctx->bpe_h.vocab_size : AKSHAR_E_NOMODEL;
+    if (kind == 1) return ctx->has_uni ? (int)ctx->uni_h.piece.size() : AKSHAR_E_NOMODEL;
+    return AKSHAR_E_ARG;
+}
+
+int akshar_vocab_token(akshar_ctx* ctx, int kind, int id, const char** bytes, int* len, int* type) {
+    if (!ctx || !bytes || !len || !type) return AKSHAR_E_ARG;
+    if (kind == 0) {
+        if (!ctx->has_bpe) return AKSHAR_E_NOMODEL;
+        if (id < 0 || (size_t)id >= ctx->bpe_h.id_to_token.size()) return AKSHAR_E_ARG;
+        *bytes = ctx->bpe_h.id_to_token[(size_t)id].data();
+        *len = (int)ctx->bpe_h.id_to_token[(size_t)id].size();
+        *type = ctx->bpe_h.is_special[(size_t)id];
+        return AKSHAR_OK;
+    }
+    if (kind == 1) {
+        if (!ctx->has_uni) return AKSHAR_E_NOMODEL;
+        if (id < 0 || (size_t)id >= ctx->uni_h.piece.size()) return AKSHAR_E_ARG;
+        *bytes = ctx->uni_h.piece[(size_t)id].data();
+        *len = (int)ctx->uni_h.piece[(size_t)id].size();
+        *type = ctx->uni_h.type[(size_t)id];
+        return AKSHAR_OK;
+    }
+    return AKSHAR_E_ARG;
+}
+
+// the three BPE launches over batch B (B may carry dyn_end / run_if from an earlier stage of a pipeline)
+static int ak_run_bpe(akshar_ctx* ctx, AkCall& C, const AkBatch& B, int64_t max_bytes, int32_t* d_ids, int64_t id_capacity,
+                      int64_t* d_id_splits) {
+    int rc;
+    const size_t tiles = (size_t)ak_tiles_of(max_bytes, B.n_rows);
+    int* tickets = (int*)C.ws;
+    unsigned int* changed = (unsigned int*)(C.ws + 64);
+    AkPool pool;
+    pool.base = (int32_t*)(C.ws + C.L.pool);
+    pool.used = (unsigned long long*)(C.ws + 128);
+    pool.cap = ak_pool_ints(max_bytes);
+    // pass 1: encode the text as it is; raises `changed` when some NFC segment is not already normalized
+    AkBpeArgs A;
+    A.B = B;
+    A.B.ticket = tickets + 1;
+    A.B.state0 = C.B.state0 + 1 * tiles;
+    A.T = ctx->T;
+    A.M = ctx->bpe_d;
+    A.pool = pool;
+    A.ids = d_ids;
+    A.id_cap = id_capacity;
+    A.id_splits = d_id_splits;
+    A.changed = changed;
+    const int bpe_tiles = B.dyn_end ? (int)tiles : B.n_tiles;
+    ak_bpe_kernel<<<ak_grid(ctx, ctx->occ_bpe, bpe_tiles), AK_BLOCK, 0, C.stream>>>(A);
+    if ((rc = ak_after_launch(ctx, "bpe"))) return rc;
+    // passes 2 + 3 (device-side conditional: both exit at once while `changed` is clear): NFC into the workspace,
+    // then encode that copy over the same outputs.  HF's NFKC == NFC on the closed alphabet (the exotic spaces it
+    // folds to U+0020 are all \\s and never reach a word).
+    int64_t* nfc_total = (int64_t*)(C.ws + 192);
+    AkNormArgs N;
+    N.B = B;
+    N.B.ticket = tickets + 2;
+    N.B.state0 = C.B.state0 + 2 * tiles;
+    N.B.totals = nfc_total;
+    N.B.run_if = changed;
+    N.T = ctx->T;
+    N.flags = 0;
+    N.out = (uint8_t*)(C.ws + C.L.nfc_text);
+    N.out_cap = C.L.nfc_cap;
+    N.out_off = (int64_t*)(C.ws + C.L.nfc_off);
+    ak_normalize_kernel<<<ak_grid(ctx, ctx->occ_norm, bpe_tiles), AK_BLOCK, 0, C.stream>>>(N);
+    if ((rc = ak_after_launch(ctx, "bpe-nfc"))) return rc;
+    AkBpeArgs A2 = A;
+    A2.B.text = N.out;
+    A2.B.off = N.out_off;
+    A2.B.text_begin = 0;
+    A2.B.text_end = 0;
+    A2.B.dyn_end = nfc_total;
+    A2.B.run_if = changed;
+    A2.B.ticket = tickets + 3;
+    A2.B.state0 = C.B.state0 + 3 * tiles;
+    A2.changed = (unsigned int*)(C.ws + 68);      // scratch flag: the copy is in NFC by construction
+    ak_bpe_kernel<<<ak_grid(ctx, ctx->occ_bpe, (int)tiles), AK_BLOCK, 0, C.stream>>>(A2);
+    return ak_after_launch(ctx, "bpe-renormalized");
+}
+
+static int ak_run_unigram(akshar_ctx* ctx, AkCall& C, const AkBatch& B, int64_t max_bytes, int32_t* d_ids,
+                          int64_t id_capacity, int64_t* d_id_splits) {
+    const size_t tiles = (size_t)ak_tiles_of(max_bytes, B.n_rows);
+    AkUniArgs A;
+    A.B = B;
+    A.B.mode = AKSHAR_MODE_ROWS;
+    A.B.n_tiles = (int)((B.n_rows + AK_ROWS_BLOCK - 1) / AK_ROWS_BLOCK);
+    A.B.ticket = (int*)C.ws + 1;
+    A.B.state0 = C.B.state0 + 1 * tiles;
+    A.U = ctx->uni_d;
+    A.back = (uint32_t*)(C.ws + C.L.scratch);
+    A.ids = d_ids;
+    A.id_cap = id_capacity;
+    A.id_splits = d_id_splits;
+    ak_unigram_kernel<<<ak_grid(ctx, ctx->occ_uni, A.B.n_tiles), AK_ROWS_BLOCK, 0, C.stream>>>(A);
+    return ak_after_launch(ctx, "unigram");
+}
+
+int akshar_encode_bpe_batch(akshar_ctx* ctx, const uint8_t* d_text, const int64_t* d_row_offsets, int64_t n_rows,
+                            int64_t text_begin, int64_t text_end, int mode, int32_t* d_ids, int64_t id_capacity,
+                            int64_t* d_id_splits, int64_t* d_result, void* d_workspace, size_t workspace_bytes,
+                            void* stream) {
+    AkCall C;
+    int rc = ak_begin(ctx, d_text, d_row_offsets, n_rows, text_begin, text_end, mode, 0, d_result, d_workspace, workspace_bytes,
+                      stream, C);
+    if (rc) return rc;
+    if (!ctx->has_bpe) {
+        ctx->err = "no BPE model loaded";
+        return AKSHAR_E_NOMODEL;
+    }
+    if (!d_id_splits || id_capacity < 0 || (!d_ids && id_capacity > 0)) {
+        ctx->err = "bad argument";
+        return AKSHAR_E_ARG;
+    }
+    if (n_rows == 0) return ak_empty_rows(ctx, d_id_splits, nullptr, C.stream);
+    return ak_run_bpe(ctx, C, C.B, text_end - text_begin, d_ids, id_capacity, d_id_splits);
+}
+
+int akshar_encode_unigram_batch(akshar_ctx* ctx, const uint8_t* d_text, const int64_t* d_row_offsets, int64_t n_rows,
+                                int64_t text_begin, int64_t text_end, int mode, int32_t* d_ids, int64_t id_capacity,
+                                int64_t* d_id_splits, int64_t* d_result, void* d_workspace, size_t workspace_bytes,
+                                void* stream) {
+    AkCall C;
+    (void)mode;      // the lattice is always built row by row
+    int rc = ak_begin(ctx, d_text, d_row_offsets, n_rows, text_begin, text_end, AKSHAR_MODE_ROWS, AK_ROWS_BLOCK, d_result,
+                      d_workspace, workspace_bytes, stream, C);
+    if (rc) return rc;
+    if (!ctx->has_uni) {
+        ctx->err = "no Unigram model loaded";
+        return AKSHAR_E_NOMODEL;
+    }
+    if (!d_id_splits || id_capacity < 0 || (!d_ids && id_capacity > 0)) {
+        ctx->err = "bad argument";
+        return AKSHAR_E_ARG;
+    }
+    if (n_rows == 0) return ak_empty_rows(ctx, d_id_splits, nullptr, C.stream);
+    return ak_run_unigram(ctx, C, C.B, text_end - text_begin, d_ids, id_capacity, d_id_splits);
+}
+
+int akshar_tokenizer_encode_batch(akshar_ctx* ctx, const uint8_t* d_text, const int64_t* d_row_offsets, int64_t n_rows,
+                                  int64_t text_begin, int64_t text_end, uint32_t norm_flags, int kind, int mode,
+                                  uint8_t* d_norm_text, int64_t norm_capacity, int64_t* d_norm_row_offsets, int32_t* d_ids,
+                                  int64_t id_capacity, int64_t* d_id_splits, int64_t* d_result, void* d_workspace,
+                                  size_t workspace_bytes, void* stream) {
+    if (!ctx) return AKSHAR_E_ARG;
+    if (norm_capacity < 0 || !d_norm_row_offsets || (!d_norm_text && norm_capacity > 0) || (norm_flags & ~15u) ||
+        (kind != 0 && kind != 1) || !d_id_splits || id_capacity < 0 || (!d_ids && id_capacity > 0)) {
+        ctx->err = "bad argument";
+        return AKSHAR_E_ARG;
+    }
+    if (kind == 0 ? !ctx->has_bpe : !ctx->has_uni) {
+        ctx->err = "no model loaded for this encoder";
+        return AKSHAR_E_NOMODEL;
+    }
+    const int64_t n_bytes = text_end - text_begin;
+    const int64_t max_bytes = n_bytes > norm_capacity ? n_bytes : norm_capacity;
+    // the workspace must cover both stages: validate against the larger text
+    if (workspace_bytes < ak_ws_layout(max_bytes, n_rows).total) {
+        ctx->err = "workspace too small: need " + std::to_string(ak_ws_layout(max_bytes, n_rows).total) + " bytes";
+        return AKSHAR_E_WORKSPACE;
+    }
+    AkCall C;
+    int rc = ak_begin(ctx, d_text, d_row_offsets, n_rows, text_begin, text_end, mode, 0, d_result, d_workspace, workspace_bytes,
+                      stream, C);
+    if (rc) return rc;
+    C.L = ak_ws_layout(max_bytes, n_rows);
+    const size_t tiles = (size_t)ak_tiles_of(max_bytes, n_rows);
+    AK_CUDA(ctx, cudaMemsetAsync(C.ws, 0, 256 + ak_align(4 * tiles * 8), C.stream));
+    C.B.state0 = (unsigned long long*)(C.ws + C.L.state);
+    C.B.state1 = C.B.state0 + tiles;
+    if (n_rows == 0) return ak_empty_rows(ctx, d_norm_row_offsets, d_id_splits, C.stream);
+    // stage 1: normalize_text (tokenizer.py:185 preprocess); its byte total lands in result[1]
+    AkNormArgs N;
+    N.B = C.B;
+    N.B.totals = d_result + 1;
+    N.T = ctx->T;
+    N.flags = norm_flags;
+    N.out = d_norm_text;
+    N.out_cap = norm_capacity;
+    N.out_off = d_norm_row_offsets;
+    ak_normalize_kernel<<<ak_grid(ctx, ctx->occ_norm, N.B.n_tiles), AK_BLOCK, 0, C.stream>>>(N);
+    if ((rc = ak_after_launch(ctx, "normalize"))) return rc;
+    // stage 2: the model on the normalized rows; their length is only known on the device (dyn_end)
+    AkBatch B2 = C.B;
+    B2.text = d_norm_text;
+    B2.off = d_norm_row_offsets;
+    B2.text_begin = 0;
+    B2.text_end = 0;
+    B2.dyn_end = d_result + 1;
+    if (mode != AKSHAR_MODE_TILES) B2.n_tiles = (int)((n_rows + AK_BLOCK - 1) / AK_BLOCK);
+    if (kind == 0) return ak_run_bpe(ctx, C, B2, max_bytes, d_ids, id_capacity, d_id_splits);
+    return ak_run_unigram(ctx, C, B2, max_bytes, d_ids, id_capacity, d_id_splits);
+}
+
+}  // extern "C"

@@ -21,8 +21,11 @@ enum {
     AK_ST_SPIN = 16,           // decoupled look-back exceeded its spin budget (never expected)
     AK_ST_WORD = 32,           // BPE word longer than the per-word symbol capacity
 };
-#define AK_NORM_ROMAN 1u       // reference normalize_text(normalize_roman=True)
-#define AK_NORM_CLEAN 2u       // reference normalize_text(clean_hinglish=True)
+#define AK_NORM_ROMAN 1u       // semantic_normalize: reference normalize_text(normalize_roman=True)
+#define AK_NORM_FILTER 2u      // filter_garbage      \ together: normalize_hinglish =
+#define AK_NORM_COLLAPSE 4u    // remove_elongations  /  reference normalize_text(clean_hinglish=True)
+#define AK_NORM_CLEAN 6u
+#define AK_NORM_NO_NFC 8u      // skip normalize_unicode (the stand-alone stage functions of normalize.py)
 #define AK_SEG_CLUSTERS 1u
 #define AK_SEG_MATRAS 2u       // reference segment_akshars(matras=True)
 #define AK_SEG_RUNS 4u
@@ -60,9 +63,9 @@ AK_HD int ak_post_nfc(const AkTables& T, uint32_t cp, uint32_t props, uint32_t f
     if ((flags & AK_NORM_ROMAN) && AK_LATIN_LOWER(props)) {
         o[0] = ak_latin_lower(T, cp);
         if (cp == 0x130u) { o[1] = 0x307u; n = 2; }
-        if (flags & AK_NORM_CLEAN) props = ak_props(T, o[0]);
+        if (flags & AK_NORM_FILTER) props = ak_props(T, o[0]);
     }
-    if (flags & AK_NORM_CLEAN) {
+    if (flags & AK_NORM_FILTER) {
         int m = 0;
         if (AK_ALLOW(props)) o[m++] = o[0];
         if (n == 2 && AK_ALLOW(ak_props(T, o[1]))) o[m++] = o[1];
@@ -150,10 +153,13 @@ AK_HD_NOINLINE int ak_prev_kept(const AkTables& T, const uint8_t* t, int64_t p, 
     while (nk < 3 && q > rs) {
         if (limit > 0 && p - q > limit) { status |= AK_ST_PATHOLOGICAL; break; }
         int64_t last = ak_prev_start(t, q, rs);
-        int64_t h = ak_find_head(T, t, last, rs, re, limit, status);
+        int64_t h = last;
         bool trouble = false;
-        // whole-segment verdict (on the first step the segment may extend past p, but only when it is inert)
-        ak_scan_segment(T, t, h, re, trouble, limit, status);
+        if (!(flags & AK_NORM_NO_NFC)) {
+            h = ak_find_head(T, t, last, rs, re, limit, status);
+            // whole-segment verdict (on the first step the segment may extend past p, but only when it is inert)
+            ak_scan_segment(T, t, h, re, trouble, limit, status);
+        }
         if (!trouble) {
             // inert: code points map one by one; walk them backwards
             int64_t c = q;
@@ -188,7 +194,8 @@ AK_HD_NOINLINE int64_t ak_norm_span(const AkTables& T, const uint8_t* t, const i
                                     int64_t r_lo, int64_t r_hi, int64_t s, int64_t e, uint32_t flags, int64_t limit,
                                     uint8_t* out, int64_t* out_off, int64_t out_base, uint32_t& status) {
     const int64_t total_end = off[n_rows];
-    const bool clean = (flags & AK_NORM_CLEAN) != 0;
+    const bool clean = (flags & AK_NORM_COLLAPSE) != 0;
+    const bool nfc = (flags & AK_NORM_NO_NFC) == 0;
     AkNormSink sink;
     sink.out = out;
     sink.cnt = 0;
@@ -210,7 +217,7 @@ AK_HD_NOINLINE int64_t ak_norm_span(const AkTables& T, const uint8_t* t, const i
         // mid-row start: which NFC segment are we in, and what did the row keep so far?
         int len;
         uint32_t cp = ak_decode(t, p, re, len);
-        if (!AK_NFC_HEAD(ak_props(T, cp))) {
+        if (nfc && !AK_NFC_HEAD(ak_props(T, cp))) {
             int64_t h = ak_find_head(T, t, p, rs, re, limit, status);
             bool trouble;
             int64_t hend = ak_scan_segment(T, t, h, re, trouble, limit, status);
@@ -251,7 +258,7 @@ AK_HD_NOINLINE int64_t ak_norm_span(const AkTables& T, const uint8_t* t, const i
         uint32_t w = ak_props(T, cp);
         bool slow = false;
         int64_t hend = p + len;
-        if (p >= inert_until && (p == rs || AK_NFC_HEAD(w))) {
+        if (nfc && p >= inert_until && (p == rs || AK_NFC_HEAD(w))) {
             // segment start: peek at the next code point; only scan when it is not itself a head
             bool trouble = AK_QC(w) != 0;
             if (hend < re) {
@@ -466,3 +473,90 @@ AK_HD_NOINLINE void ak_seg_span(const AkTables& T, const uint8_t* t, const int64
     n_clusters = cc;
     n_runs = rc;
 }
+
+// =================================================================================================
+// roman_phonetic_signature (reference normalize.py:59-89): lower() [all scripts, Final_Sigma] -> collapse runs
+// >= 3 -> ee$ -> i, oo$ -> u -> aa kh gh ch th ph bh dh, on a code-point scratch `a` (one slot per input byte)
+// =================================================================================================
+AK_HD bool ak_final_sigma(const AkTables& T, const uint8_t* t, int64_t p, int len, int64_t rs, int64_t re) {
+    // CPython handle_capital_sigma: \p{cased}\p{case-ignorable}* SIGMA !(\p{case-ignorable}* \p{cased})
+    int64_t q = p;
+    bool before = false;
+    while (q > rs) {
+        q = ak_prev_start(t, q, rs);
+        int l;
+        uint32_t w = ak_props(T, ak_decode(t, q, re, l));
+        if ((w >> 26) & 1u) continue;
+        before = ((w >> 27) & 1u) != 0;
+        break;
+    }
+    if (!before) return false;
+    q = p + len;
+    while (q < re) {
+        int l;
+        uint32_t w = ak_props(T, ak_decode(t, q, re, l));
+        q += l;
+        if ((w >> 26) & 1u) continue;
+        return ((w >> 27) & 1u) == 0;
+    }
+    return true;
+}
+
+AK_HD int ak_replace2(uint32_t* a, int n, uint32_t x, uint32_t y, uint32_t r) {
+    int m = 0;
+    for (int i = 0; i < n;) {
+        if (i + 1 < n && a[i] == x && a[i + 1] == y) { a[m++] = r; i += 2; }
+        else a[m++] = a[i++];
+    }
+    return m;
+}
+
+AK_HD_NOINLINE int ak_signature_row(const AkTables& T, const uint8_t* t, int64_t rs, int64_t re, uint32_t* a) {
+    int n = 0;
+    int64_t p = rs;
+    // lower() then run collapse, streaming
+    uint32_t last = 0xFFFFFFFFu;
+    int run = 0;
+#define AK_SIG_FEED(c_)                                   \
+    do {                                                  \
+        uint32_t c = (c_);                                \
+        if (c == last) {                                  \
+            if (c == 0x0Au) a[n++] = c;                   \
+            else if (run < 3) ++run;                      \
+        } else {                                          \
+            if (run == 2) a[n++] = last;                  \
+            a[n++] = c;                                   \
+            last = c;                                     \
+            run = 1;                                      \
+        }                                                 \
+    } while (0)
+    while (p < re) {
+        int len;
+        uint32_t cp = ak_decode(t, p, re, len);
+        uint32_t w = ak_props(T, cp);
+        if (cp == 0x3A3u) AK_SIG_FEED(ak_final_sigma(T, t, p, len, rs, re) ? 0x3C2u : 0x3C3u);
+        else if (AK_FULL_LOWER(w) || (cp >= 'A' && cp <= 'Z')) {
+            AK_SIG_FEED(ak_full_lower(T, cp));
+            if (cp == 0x130u) AK_SIG_FEED(0x307u);
+        } else AK_SIG_FEED(cp);
+        p += len;
+    }
+    if (run == 2) a[n++] = last;
+#undef AK_SIG_FEED
+    // ee$ -> i, oo$ -> u   (`$` also matches before one trailing newline)
+    for (int pass = 0; pass < 2; ++pass) {
+        const uint32_t v = pass == 0 ? 'e' : 'o', r = pass == 0 ? 'i' : 'u';
+        if (n >= 2 && a[n - 1] == v && a[n - 2] == v) { a[n - 2] = r; --n; }
+        else if (n >= 3 && a[n - 1] == 0x0Au && a[n - 2] == v && a[n - 3] == v) { a[n - 3] = r; a[n - 2] = 0x0Au; --n; }
+    }
+    n = ak_replace2(a, n, 'a', 'a', 'a');
+    n = ak_replace2(a, n, 'k', 'h', 'k');
+    n = ak_replace2(a, n, 'g', 'h', 'g');
+    n = ak_replace2(a, n, 'c', 'h', 'c');
+    n = ak_replace2(a, n, 't', 'h', 't');
+    n = ak_replace2(a, n, 'p', 'h', 'p');
+    n = ak_replace2(a, n, 'b', 'h', 'b');
+    n = ak_replace2(a, n, 'd', 'h', 'd');
+    return n;
+}
+

@@ -45,9 +45,15 @@ enum {
     AKSHAR_ST_WORD = 32,         /* BPE word longer than the per-word capacity: re-run with AKSHAR_MODE_ROWS */
 };
 
-/* normalize flags == reference normalize_text(text, normalize_roman, clean_hinglish)  (normalize.py:117) */
+/* normalize flags: normalize_text(text, normalize_roman, clean_hinglish) (normalize.py:117) is
+ * (normalize_roman ? ROMAN : 0) | (clean_hinglish ? CLEAN : 0); the single stages map to the stand-alone functions:
+ * ROMAN|NO_NFC = semantic_normalize (:21), FILTER|NO_NFC = filter_garbage (:92), COLLAPSE|NO_NFC =
+ * remove_elongations (:48), CLEAN|NO_NFC = normalize_hinglish (:110), 0 = normalize_unicode (:13). */
 #define AKSHAR_NORM_ROMAN 1u
-#define AKSHAR_NORM_CLEAN 2u
+#define AKSHAR_NORM_FILTER 2u
+#define AKSHAR_NORM_COLLAPSE 4u
+#define AKSHAR_NORM_CLEAN 6u
+#define AKSHAR_NORM_NO_NFC 8u
 /* segment flags */
 #define AKSHAR_SEG_CLUSTERS 1u   /* segment_akshars(text)               (segment.py:40-78)  */
 #define AKSHAR_SEG_MATRAS 2u     /* segment_akshars(text, matras=True)  (segment.py:80-125) */
@@ -111,6 +117,17 @@ int akshar_encode_unigram_batch(akshar_ctx* ctx, const uint8_t* d_text, const in
                                 int64_t text_begin, int64_t text_end, int mode, int32_t* d_ids, int64_t id_capacity,
                                 int64_t* d_id_splits, int64_t* d_result, void* d_workspace, size_t workspace_bytes,
                                 void* stream);
+
+/* aksharTokenizer.encode(text) over a batch of RAW rows (tokenizer.py:167-193): preprocess (= normalize_text with
+ * `norm_flags`) then the model selected by `kind` (0 BPE, 1 Unigram), enqueued back to back with no host
+ * synchronisation in between (the normalized length stays on the device).  The normalized rows are returned too
+ * (d_norm_text / d_norm_row_offsets) because token offsets refer to them.  The workspace must be sized for
+ * max(text_end - text_begin, norm_capacity) bytes.  result[0] = ids, result[1] = normalized bytes. */
+int akshar_tokenizer_encode_batch(akshar_ctx* ctx, const uint8_t* d_text, const int64_t* d_row_offsets, int64_t n_rows,
+                                  int64_t text_begin, int64_t text_end, uint32_t norm_flags, int kind, int mode,
+                                  uint8_t* d_norm_text, int64_t norm_capacity, int64_t* d_norm_row_offsets, int32_t* d_ids,
+                                  int64_t id_capacity, int64_t* d_id_splits, int64_t* d_result, void* d_workspace,
+                                  size_t workspace_bytes, void* stream);
 
 /* number of kernels this library has launched on this context since creation (bench.py's gpu_launches) */
 int64_t akshar_launch_count(akshar_ctx* ctx);

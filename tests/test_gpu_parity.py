@@ -1,0 +1,271 @@
+"""Parity of the CUDA path (through the C ABI) with (1) vectors recorded from the unmodified reference,
+(2) the oracle on seeded synthetic / adversarial inputs, (3) size-independent properties at large sizes."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+import akshar_oracle as O
+import oracle_batch as OB
+import synth_corpus as sc
+
+
+@pytest.fixture(scope='module')
+def A():
+    import torch
+    assert torch.cuda.is_available(), 'GPU tests need a CUDA device'
+    import __graft_entry__ as g
+    g.build()
+    import akshar_b200
+    return akshar_b200
+
+
+@pytest.fixture(scope='module')
+def eng(A):
+    return A.engine()
+
+
+def _np(t):
+    return t.cpu().numpy()
+
+
+# ------------------------------------------------------------------ golden vectors (unmodified reference)
+@pytest.mark.parametrize('nr,nc,key', [(True, True, 'norm'), (False, True, 'norm_nr'), (True, False, 'norm_nc'),
+                                       (False, False, 'norm_raw')])
+def test_normalize_golden(A, golden, nr, nc, key):
+    ins = [r['in'] for r in golden['rows']]
+    assert A.normalize_batch(ins, nr, nc) == [r[key] for r in golden['rows']]
+
+
+@pytest.mark.parametrize('name,key', [('normalize_unicode', 'nfc'), ('semantic_normalize', 'sem'), ('filter_garbage', 'filt'),
+                                      ('remove_elongations', 'elong')])
+def test_single_stages_golden(A, golden, name, key):
+    from akshar_b200.normalize import stage_batch
+    ins = [r['in'] for r in golden['rows']]
+    assert stage_batch(name, ins) == [r[key] for r in golden['rows']]
+
+
+def test_segment_golden(A, golden):
+    rows = golden['rows']
+    norm = [r['norm'] for r in rows]
+    raw = [r['in'] for r in rows]
+    assert A.segment_akshars_batch(norm) == [r['seg'] for r in rows]
+    assert A.segment_akshars_batch(raw) == [r['seg_raw'] for r in rows]
+    assert A.segment_akshars_batch(norm, matras=True) == [r['seg_m'] for r in rows]
+    assert A.segment_akshars_batch(raw, matras=True) == [r['segm_raw'] for r in rows]
+
+
+def test_code_switch_golden(A, golden):
+    rows = golden['rows']
+    got = A.detect_code_switches_batch([r['norm'] for r in rows])
+    assert [[list(x) for x in g] for g in got] == [r['cs'] for r in rows]
+    got = A.detect_code_switches_batch([r['in'] for r in rows])
+    assert [[list(x) for x in g] for g in got] == [r['cs_raw'] for r in rows]
+    assert A.analyze_text_composition_batch([r['norm'] for r in rows]) == [r['comp'] for r in rows]
+
+
+def test_signature_golden(A, golden):
+    words = list(golden['signature'])
+    assert A.roman_phonetic_signature_batch(words) == [golden['signature'][w] for w in words]
+
+
+@pytest.mark.parametrize('name,kind', [('bpe24k', 'bpe'), ('bpe_corpus', 'bpe'), ('spm24k', 'sentencepiece'),
+                                       ('spm_corpus', 'sentencepiece')])
+def test_encode_golden(A, golden, models_dir, name, kind):
+    path = os.path.join(models_dir, name + ('.json' if kind == 'bpe' else '.model'))
+    tk = A.aksharTokenizer(path, kind)
+    assert tk.vocab_size() == golden['vocab_size'][name]
+    rows = golden['rows']
+    # raw text through the fused normalize + encode pipeline (aksharTokenizer.encode over a batch)
+    assert tk.encode_batch([r['in'] for r in rows]) == [r['ids_' + name] for r in rows]
+    # already-normalized rows through the stand-alone encoders
+    e = tk._eng.encode_bpe_batch if kind == 'bpe' else tk._eng.encode_unigram_batch
+    got = [x.tolist() for x in e([r['norm'] for r in rows]).rows()]
+    assert got == [r['ids_' + name] for r in rows]
+
+
+def test_pieces_and_decode_golden(A, golden, models_dir):
+    tb = A.aksharTokenizer(os.path.join(models_dir, 'bpe24k.json'), 'bpe')
+    tu = A.aksharTokenizer(os.path.join(models_dir, 'spm24k.model'))
+    rows = golden['rows'][:400]
+    assert tb.tokenize_batch([r['in'] for r in rows]) == [r['pieces_bpe24k'] for r in rows]
+    assert tu.tokenize_batch([r['in'] for r in rows]) == [r['pieces_spm24k'] for r in rows]
+    for r in rows[:200]:
+        assert tb.decode(r['ids_bpe24k']) == r['dec_bpe24k']
+        assert tu.decode(r['ids_spm24k']) == r['dec_spm24k']
+
+
+# ------------------------------------------------------------------ the reference's own test expectations, via the drop-in API
+def test_reference_unit_expectations(A):
+    # reference tests/test_normalize.py
+    assert len(A.normalize_unicode("नमस्ते")) == len("नमस्ते")
+    assert A.semantic_normalize("Hello World") == "hello world"
+    assert A.semantic_normalize("नमस्ते") == "नमस्ते"
+    assert A.semantic_normalize("hello नमस्ते world") == "hello नमस्ते world"
+    for s in ("yaaaaar", "bohoooot", "hiiii", "normal"):
+        assert len(A.remove_elongations(s)) <= len(s)
+    assert A.remove_elongations("yaaaaar") == "yar"
+    assert isinstance(A.roman_phonetic_signature("nahi"), str)
+    r = A.normalize_text("Heyyy यार kya HAAL hai")
+    assert "यार" in r and "heyyy" not in r
+    # reference tests/test_segment.py
+    assert A.segment_akshars("") == []
+    assert len(A.segment_akshars("नमस्ते")) > 0
+    assert any('क्ष' in a for a in A.segment_akshars("क्षेत्रे"))
+    for ch, t in (('न', 'devanagari'), ('म', 'devanagari'), ('a', 'roman'), ('Z', 'roman'), ('5', 'digit'), ('.', 'punct'),
+                  (' ', 'punct')):
+        assert A.identify_script(ch) == t
+    segs = A.detect_code_switches("aaj मौसम अच्छा hai")
+    assert len(segs) > 1 and {s for _, s in segs} >= {'roman', 'devanagari'}
+    assert A.detect_code_switches("") == []
+    assert A.segment_by_script("hello नमस्ते world")
+    st = A.analyze_text_composition("aaj मौसम अच्छा hai")
+    assert set(st) >= {'akshar_count', 'script_switches', 'devanagari_ratio', 'roman_ratio'}
+    # reference tests/test_tokenizer.py
+    tk = A.AksharTokenizer()
+    assert tk.model is None and tk.vocab_size() == 0
+    assert isinstance(tk.tokenize("नमस्ते"), list)
+    meta = tk.tokenize("hello नमस्ते", return_metadata=True)
+    assert 'tokens' in meta and meta['token_count'] == len(meta['tokens'])
+    ex = tk.explain("aaj मौसम अच्छा hai")
+    assert set(ex) == {'original', 'normalized', 'akshars', 'code_switches', 'tokens', 'stats'}
+    with pytest.raises(ValueError):
+        tk.encode("hello")
+    with pytest.raises(ValueError):
+        tk.decode([1, 2])
+    assert tk.detokenize(['a', 'b']) == 'ab'
+    with pytest.raises(ValueError):
+        A.aksharTokenizer(os.path.join(os.path.dirname(__file__), 'conftest.py'), 'nonsense')
+    # executed notebook cell
+    assert tk.tokenize("aaj मौसम बहुत अच्छा है") == ['a', 'a', 'j', ' ', 'मौ', 'स', 'म', ' ', 'ब', 'हु', 'त', ' ', 'अ', 'च्छा', ' ', 'है']
+
+
+# ------------------------------------------------------------------ oracle on seeded synthetic + adversarial input
+def _mixed_lines():
+    lines = sc.adversarial(3000, 31, 80) + sc.Corpus('social', 11).lines(300000) + sc.Corpus('hindi', 12).lines(200000)
+    lines += ['', '', '\n\n\n', ' ', 'a' * 5000, 'क' + 'ु' * 300 + 'ख', '🇮' * 201, 'अ' + '्क' * 400, '']
+    return lines
+
+
+def test_oracle_parity_mixed(A, eng):
+    lines = _mixed_lines()
+    exp, exp_off = OB.normalize_batch(lines)
+    tb = eng.normalize_batch(lines)
+    assert np.array_equal(_np(tb.offsets), exp_off)
+    assert _np(tb.data)[:tb.end].tobytes() == exp.tobytes()
+    norm = tb.to_strings()
+    for src in (lines, norm):
+        c, r = eng.segment_batch(src, clusters=True, runs=True)
+        ce, cs = OB.segment_batch(src)
+        re_, rt, rs = OB.runs_batch(src)
+        assert np.array_equal(_np(c.splits), cs) and np.array_equal(_np(c.values), ce)
+        assert np.array_equal(_np(r.splits), rs) and np.array_equal(_np(r.values), re_) and np.array_equal(_np(r.extra), rt)
+        m, _ = eng.segment_batch(src, clusters=True, matras=True)
+        me, ms = OB.segment_batch(src, matras=True)
+        assert np.array_equal(_np(m.splits), ms) and np.array_equal(_np(m.values), me)
+
+
+def test_modes_agree(A, eng):
+    from akshar_b200 import _lib as C
+    lines = _mixed_lines()[:2500] + ['', 'x']
+    a = eng.normalize_batch(lines, mode=C.MODE_TILES)
+    b = eng.normalize_batch(lines, mode=C.MODE_ROWS)
+    assert a.end == b.end and np.array_equal(_np(a.offsets), _np(b.offsets))
+    assert np.array_equal(_np(a.data)[:a.end], _np(b.data)[:b.end])
+    ca, ra = eng.segment_batch(lines, runs=True, mode=C.MODE_TILES)
+    cb, rb = eng.segment_batch(lines, runs=True, mode=C.MODE_ROWS)
+    assert np.array_equal(_np(ca.values), _np(cb.values)) and np.array_equal(_np(ra.values), _np(rb.values))
+
+
+def test_long_combining_run_falls_back_to_rows(A, eng):
+    # > AK_LOOKBACK_LIMIT bytes of Extend characters: the tile path gives up loudly and the engine re-runs row-wise
+    s = 'क' + 'ु' * 3000 + 'ख'
+    assert A.segment_akshars_batch([s, 'ab']) == [O.segment_akshars(s), ['a', 'b']]
+
+
+def test_edge_batches(A, eng, models_dir):
+    assert A.normalize_batch([]) == []
+    assert A.segment_akshars_batch([]) == []
+    assert A.normalize_batch(['', '', '']) == ['', '', '']
+    assert A.segment_akshars_batch(['', 'a', '']) == [[], ['a'], []]
+    assert A.detect_code_switches_batch(['', '123', '']) == [[], [('123', None)], []]
+    tk = A.aksharTokenizer(os.path.join(models_dir, 'bpe24k.json'), 'bpe')
+    assert tk.encode_batch(['', '']) == [[2, 3], [2, 3]]
+    assert tk.encode_batch([]) == []
+    tu = A.aksharTokenizer(os.path.join(models_dir, 'spm24k.model'))
+    assert tu.encode_batch(['', ' ', 'a']) [:2] == [[], []]
+    # capacities far too small: totals stay exact and the engine retries
+    lines = sc.Corpus('hinglish', 2).lines(50000)
+    tb = eng.normalize_batch(lines, capacity=16)
+    assert tb.to_strings() == [O.normalize_text(s) for s in lines]
+    c, _ = eng.segment_batch(lines, capacity=3)
+    assert np.array_equal(_np(c.values), OB.segment_batch(lines)[0])
+    r = tk._eng.encode_bpe_batch(tb.to_strings(), capacity=5)
+    om = O.BpeModel(os.path.join(models_dir, 'bpe24k.json'))
+    assert [x.tolist() for x in r.rows()] == [O.bpe_encode(om, s) for s in tb.to_strings()]
+
+
+def test_bpe_renormalizes_on_device(A, models_dir):
+    # rows that are not in NFC make the kernel take its conditional NFC + re-encode passes
+    tk = A.aksharTokenizer(os.path.join(models_dir, 'bpe24k.json'), 'bpe', clean_hinglish=True)
+    om = O.BpeModel(os.path.join(models_dir, 'bpe24k.json'))
+    lines = ['ऩ क्ष', 'abc', 'ऱा', 'x'] * 50
+    got = [x.tolist() for x in tk._eng.encode_bpe_batch(lines).rows()]
+    assert got == [O.bpe_encode(om, s) for s in lines]
+    long_word = ['ab' * 200 + ' ' + 'कख' * 90, 'ok']
+    got = [x.tolist() for x in tk._eng.encode_bpe_batch(long_word).rows()]
+    assert got == [O.bpe_encode(om, s) for s in long_word]
+
+
+# ------------------------------------------------------------------ large sizes: size-independent properties
+def test_large_properties(A, eng, models_dir):
+    import torch
+    nbytes = 256 << 20
+    data, off = sc.Corpus('social', 77).generate(nbytes)
+    host = (torch.from_numpy(data), torch.from_numpy(off))
+    tb_in = eng.put(host)
+    norm = eng.normalize_batch(tb_in)
+    # (1) idempotence: normalize_text(normalize_text(x)) == normalize_text(x)
+    again = eng.normalize_batch(norm)
+    assert again.end == norm.end
+    assert torch.equal(again.data[:again.end], norm.data[:norm.end]) and torch.equal(again.offsets, norm.offsets)
+    # (2) batch-split invariance: the two halves processed separately give the same bytes / clusters / ids
+    n = off.size - 1
+    h = n // 2
+    for lo, hi in ((0, h), (h, n)):
+        sub = (torch.from_numpy(data[off[lo]:off[hi]].copy()), torch.from_numpy(off[lo:hi + 1] - off[lo]))
+        part = eng.normalize_batch(sub)
+        o = norm.offsets[lo:hi + 1]
+        assert torch.equal(part.offsets, o - o[0])
+        assert torch.equal(part.data[:part.end], norm.data[int(o[0]):int(o[-1])])
+    # (3) cluster ends are strictly increasing inside a row and end at the row length
+    c, r = eng.segment_batch(norm, clusters=True, runs=True)
+    lens = (norm.offsets[1:] - norm.offsets[:-1])
+    last = c.values[(c.splits[1:] - 1).clamp(min=0)]
+    nonempty = lens > 0
+    assert torch.equal(last[nonempty].long(), lens[nonempty])
+    d = c.values[1:] - c.values[:-1]
+    is_first = torch.zeros(c.values.numel(), dtype=torch.bool, device=c.values.device)
+    is_first[c.splits[:-1][nonempty]] = True
+    assert bool((d[~is_first[1:]] > 0).all())
+    # (4) oracle on a seeded sample of rows
+    rng = np.random.default_rng(5)
+    pick = np.sort(rng.choice(n, size=3000, replace=False))
+    b = data.tobytes()
+    nb = norm.data[:norm.end].cpu().numpy().tobytes()
+    no = norm.offsets.cpu().numpy()
+    ce = c.values.cpu().numpy()
+    cs = c.splits.cpu().numpy()
+    tk = A.aksharTokenizer(os.path.join(models_dir, 'bpe24k.json'), 'bpe')
+    ids, _ = tk._eng.tokenizer_encode_batch(tb_in, 0)
+    iv, isp = ids.values.cpu().numpy(), ids.splits.cpu().numpy()
+    om = O.BpeModel(os.path.join(models_dir, 'bpe24k.json'))
+    for i in pick:
+        s = b[off[i]:off[i + 1]].decode('utf-8')
+        e = O.normalize_text(s)
+        assert nb[no[i]:no[i + 1]].decode('utf-8') == e
+        cps = [ord(ch) for ch in e]
+        assert ce[cs[i]:cs[i + 1]].tolist() == O.cp_ends_to_byte_ends(cps, O.segment_breaks(cps))
+        assert iv[isp[i]:isp[i + 1]].tolist() == O.bpe_encode(om, e)

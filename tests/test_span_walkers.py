@@ -21,7 +21,7 @@ def _lines():
 
 @functools.lru_cache(None)
 def _exp_norm(flags):
-    return OB.normalize_batch(_lines(), bool(flags & 1), bool(flags & 2))
+    return OB.normalize_batch(_lines(), bool(flags & 1), bool(flags & 6))
 
 
 @functools.lru_cache(None)
@@ -34,7 +34,7 @@ def _exp_runs():
     return OB.runs_batch(_lines())
 
 
-@pytest.mark.parametrize('flags', [3, 2, 1, 0])
+@pytest.mark.parametrize('flags', [7, 6, 1, 0])
 @pytest.mark.parametrize('span', [1, 3, 16, 64, 100000])
 def test_normalize_spans(flags, span):
     lines = _lines()
@@ -49,10 +49,10 @@ def test_normalize_spans(flags, span):
 def test_normalize_random_spans():
     lines = _lines()
     data, off = sc.pack(lines)
-    exp, exp_off = _exp_norm(3)
+    exp, exp_off = _exp_norm(7)
     rng = np.random.default_rng(3)
     for _ in range(3):
-        out, out_off, st = W.normalize(data, off, flags=3, span=40, rng=rng)
+        out, out_off, st = W.normalize(data, off, flags=7, span=40, rng=rng)
         assert st == 0
         assert np.array_equal(out_off, exp_off)
         assert out.tobytes() == exp.tobytes()
@@ -83,3 +83,16 @@ def test_bounded_lookback_flags_pathological():
     ce, cs = OB.segment_batch(lines)
     gce, gcs, _, _, _, st = W.segment(data, off, flags=1, span=16, limit=0)
     assert st == 0 and np.array_equal(gce, ce)
+
+
+@pytest.mark.parametrize('flags,fn', [(1 | 8, O.semantic_normalize), (2 | 8, O.filter_garbage), (4 | 8, O.remove_elongations),
+                                      (6 | 8, O.normalize_hinglish), (0, O.normalize_unicode)])
+def test_single_stage_flags(flags, fn):
+    lines = _lines()
+    data, off = sc.pack(lines)
+    exp = [fn(s).encode('utf-8') for s in lines]
+    for span in (4, 32):
+        out, out_off, st = W.normalize(data, off, flags=flags, span=span)
+        assert st == 0
+        b = out.tobytes()
+        assert [b[out_off[i]:out_off[i + 1]] for i in range(len(lines))] == exp

@@ -1,0 +1,101 @@
+"""CPU build of the model loaders (ak_models.cpp) and subword cores (ak_subword.cuh, signature in ak_text_core.cuh)
+against the vectors recorded from the unmodified reference (tests/golden) and the oracle.  Test aid only: the
+product runs these same functions inside the CUDA kernels."""
+import os
+
+import numpy as np
+import pytest
+
+import akshar_oracle as O
+import synth_corpus as sc
+import walker_harness as W
+
+
+def _rows(golden, limit=None):
+    rows = golden['rows'] if limit is None else golden['rows'][:limit]
+    return rows
+
+
+@pytest.mark.parametrize('name', ['bpe24k', 'bpe_corpus'])
+@pytest.mark.parametrize('span', [32, 7, 100000])
+def test_bpe_ids_match_reference(golden, models_dir, name, span):
+    assert W.load_bpe(os.path.join(models_dir, name + '.json')) == golden['vocab_size'][name]
+    rows = _rows(golden)
+    data, off = sc.pack([r['norm'] for r in rows])
+    ids, splits, st, attempt = W.bpe(data, off, span=span)
+    assert st == 0
+    exp = [r['ids_' + name] for r in rows]
+    exp_splits = np.zeros(len(rows) + 1, dtype=np.int64)
+    np.cumsum([len(e) for e in exp], out=exp_splits[1:])
+    assert np.array_equal(splits, exp_splits)
+    assert ids.tolist() == [i for e in exp for i in e]
+
+
+def test_bpe_small_stage_and_random_spans(golden, models_dir):
+    W.load_bpe(os.path.join(models_dir, 'bpe24k.json'))
+    rows = _rows(golden, 3000)
+    lines = [r['norm'] for r in rows] + ['', '', '']
+    exp = [r['ids_bpe24k'] for r in rows] + [[2, 3]] * 3
+    data, off = sc.pack(lines)
+    ids, splits, st, _ = W.bpe(data, off, span=50, rng=np.random.default_rng(1), stage_cap=3)
+    assert st == 0
+    assert ids.tolist() == [i for e in exp for i in e]
+    assert splits[-1] == len(ids)
+
+
+def test_bpe_renormalizes_when_needed(models_dir):
+    # text that is NOT in NFC (what normalize_text can leave behind after filtering: U+0928 + U+093C adjacent)
+    m = O.BpeModel(os.path.join(models_dir, 'bpe24k.json'))
+    W.load_bpe(os.path.join(models_dir, 'bpe24k.json'))
+    lines = ['ऩ क्ष', 'abc', 'ऱा', 'x']
+    data, off = sc.pack(lines)
+    ids, splits, st, attempt = W.bpe(data, off, span=16)
+    assert attempt == 1 and st == 0
+    exp = [O.bpe_encode(m, s) for s in lines]
+    assert ids.tolist() == [i for e in exp for i in e]
+
+
+def test_bpe_long_word_uses_pool(models_dir):
+    m = O.BpeModel(os.path.join(models_dir, 'bpe24k.json'))
+    W.load_bpe(os.path.join(models_dir, 'bpe24k.json'))
+    lines = ['ab' * 200 + ' ' + 'कख' * 90, 'ok']
+    data, off = sc.pack(lines)
+    ids, splits, st, _ = W.bpe(data, off, span=32)
+    assert st == 0
+    exp = [O.bpe_encode(m, s) for s in lines]
+    assert ids.tolist() == [i for e in exp for i in e]
+
+
+@pytest.mark.parametrize('name', ['spm24k', 'spm_corpus'])
+def test_unigram_ids_match_reference(golden, models_dir, name):
+    assert W.load_spm(os.path.join(models_dir, name + '.model')) == golden['vocab_size'][name]
+    rows = _rows(golden)
+    data, off = sc.pack([r['norm'] for r in rows])
+    ids, splits = W.unigram(data, off)
+    exp = [r['ids_' + name] for r in rows]
+    exp_splits = np.zeros(len(rows) + 1, dtype=np.int64)
+    np.cumsum([len(e) for e in exp], out=exp_splits[1:])
+    assert np.array_equal(splits, exp_splits)
+    assert ids.tolist() == [i for e in exp for i in e]
+
+
+def test_signature_matches_reference(golden):
+    words = list(golden['signature'].keys())
+    data, off = sc.pack(words)
+    out, out_off = W.signature(data, off)
+    b = out.tobytes()
+    got = [b[out_off[i]:out_off[i + 1]].decode('utf-8') for i in range(len(words))]
+    assert got == [golden['signature'][w] for w in words]
+
+
+def test_loader_rejects_unsupported(models_dir):
+    import json
+    j = json.load(open(os.path.join(models_dir, 'bpe_corpus.json'), encoding='utf-8'))
+    j['pre_tokenizer'] = {'type': 'ByteLevel'}
+    p = '/tmp/_ak_bad.json'
+    json.dump(j, open(p, 'w'))
+    with pytest.raises(ValueError):
+        W.load_bpe(p)
+    open(p, 'wb').write(b'\x00\x01garbage')
+    with pytest.raises(ValueError):
+        W.load_spm(p)

@@ -13,10 +13,12 @@ _lib = None
 def build():
     os.makedirs(os.path.dirname(SO), exist_ok=True)
     src = os.path.join(ROOT, 'tests', 'csrc', 'host_harness.cpp')
-    deps = [src] + [os.path.join(ROOT, 'akshar_b200', 'csrc', f) for f in
-                    ('ak_unicode.cuh', 'ak_text_core.cuh', 'unicode_tables.inc')]
+    csrc = os.path.join(ROOT, 'akshar_b200', 'csrc')
+    models = os.path.join(csrc, 'ak_models.cpp')
+    deps = [src, models] + [os.path.join(csrc, f) for f in
+                            ('ak_unicode.cuh', 'ak_text_core.cuh', 'ak_subword.cuh', 'ak_models.h', 'unicode_tables.inc')]
     if not os.path.exists(SO) or any(os.path.getmtime(d) > os.path.getmtime(SO) for d in deps):
-        subprocess.check_call(['g++', '-O2', '-std=c++17', '-shared', '-fPIC', '-o', SO, src])
+        subprocess.check_call(['g++', '-O2', '-std=c++17', '-shared', '-fPIC', '-o', SO, src, models])
 
 
 def lib():
@@ -25,6 +27,10 @@ def lib():
         build()
         _lib = ctypes.CDLL(SO)
         _lib.hh_normalize.restype = ctypes.c_int64
+        _lib.hh_signature.restype = ctypes.c_int64
+        _lib.hh_bpe.restype = ctypes.c_int64
+        _lib.hh_unigram.restype = ctypes.c_int64
+        _lib.hh_error.restype = ctypes.c_char_p
     return _lib
 
 
@@ -42,7 +48,7 @@ def make_spans(off, span, rng=None):
     return np.array(b, dtype=np.int64)
 
 
-def normalize(data, off, flags=3, span=32, limit=0, rng=None):
+def normalize(data, off, flags=7, span=32, limit=0, rng=None):
     data = np.ascontiguousarray(data, dtype=np.uint8)
     off = np.ascontiguousarray(off, dtype=np.int64)
     spans = make_spans(off, span, rng)
@@ -70,3 +76,58 @@ def segment(data, off, flags=1, span=32, limit=0, rng=None):
                      ctypes.c_int64(spans.size - 1), ctypes.c_int64(limit), _p(ce), _p(cs), _p(re_), _p(rt), _p(rs),
                      ctypes.c_int64(cap), _p(tot), ctypes.byref(st))
     return ce[:tot[0]], cs, re_[:tot[1]], rt[:tot[1]], rs, st.value
+
+
+def signature(data, off):
+    data = np.ascontiguousarray(data, dtype=np.uint8)
+    off = np.ascontiguousarray(off, dtype=np.int64)
+    out = np.zeros(int(data.size) * 2 + 16, dtype=np.uint8)
+    out_off = np.zeros(off.size, dtype=np.int64)
+    n = lib().hh_signature(_p(data), _p(off), ctypes.c_int64(off.size - 1), _p(out), _p(out_off))
+    return out[:n], out_off
+
+
+def load_bpe(path):
+    b = open(path, 'rb').read()
+    if lib().hh_load_bpe(b, ctypes.c_int64(len(b))) != 0:
+        raise ValueError(lib().hh_error().decode())
+    return lib().hh_bpe_vocab_size()
+
+
+def load_spm(path):
+    b = open(path, 'rb').read()
+    if lib().hh_load_spm(b, ctypes.c_int64(len(b))) != 0:
+        raise ValueError(lib().hh_error().decode())
+    return lib().hh_spm_vocab_size()
+
+
+def bpe(data, off, span=32, limit=0, rng=None, stage_cap=40):
+    """the kernel's three-pass protocol: encode; if NFC would change the text, NFC it and encode the copy"""
+    data = np.ascontiguousarray(data, dtype=np.uint8)
+    off = np.ascontiguousarray(off, dtype=np.int64)
+    for attempt in range(2):
+        spans = make_spans(off, span, rng)
+        cap = int(data.size) + 2 * off.size + 16
+        ids = np.zeros(cap, dtype=np.int32)
+        splits = np.full(off.size, -1, dtype=np.int64)
+        ch = ctypes.c_int(0)
+        st = ctypes.c_uint32(0)
+        n = lib().hh_bpe(_p(data), _p(off), ctypes.c_int64(off.size - 1), _p(spans), ctypes.c_int64(spans.size - 1),
+                         ctypes.c_int64(limit), ctypes.c_int(stage_cap), _p(ids), ctypes.c_int64(cap), _p(splits),
+                         ctypes.byref(ch), ctypes.byref(st))
+        if not ch.value:
+            return ids[:n], splits, st.value, attempt
+        assert attempt == 0, 'NFC copy still not normalized'
+        data, off, _ = normalize(data, off, flags=0, span=span, limit=limit, rng=rng)
+        data = np.ascontiguousarray(data)
+    raise AssertionError
+
+
+def unigram(data, off):
+    data = np.ascontiguousarray(data, dtype=np.uint8)
+    off = np.ascontiguousarray(off, dtype=np.int64)
+    cap = int(data.size) * 4 + 2 * off.size + 16
+    ids = np.zeros(cap, dtype=np.int32)
+    splits = np.zeros(off.size, dtype=np.int64)
+    n = lib().hh_unigram(_p(data), _p(off), ctypes.c_int64(off.size - 1), _p(ids), ctypes.c_int64(cap), _p(splits))
+    return ids[:n], splits

@@ -160,6 +160,21 @@ def main():
           "full_lower", len(full_lower), "qc_no", sum(1 for x in nfc_qc if x == 1), "qc_maybe",
           sum(1 for x in nfc_qc if x == 2), "ccc!=0", sum(1 for x in ccc if x))
 
+    # ---- Final_Sigma context classes of str.lower() (normalize.py:72 `word.lower()`), probed through lower() itself
+    case_ign = bytearray(NCP)
+    cased = bytearray(NCP)          # cased AND not case-ignorable (the only place CPython consults `cased`)
+    for cp in range(NCP):
+        if 0xD800 <= cp <= 0xDFFF:
+            continue
+        ch = chr(cp)
+        a = ('a\u03a3' + ch).lower()[1]
+        b = ('a\u03a3' + ch + 'a').lower()[1]
+        if a == '\u03c2' and b == '\u03c3':
+            case_ign[cp] = 1
+        elif a == '\u03c3':
+            cased[cp] = 1
+    print("case_ignorable", sum(case_ign), "cased", sum(cased))
+
     # ---- script tag, exactly the order of segment.py:128-147
     tag = bytearray(NCP)
     punct = set(' .,!?;:\'"()-[]{}')
@@ -211,6 +226,7 @@ def main():
         w = gcb[cp] | (incb[cp] << 4) | (extpict[cp] << 6) | (tag[cp] << 7) | (allow[cp] << 10)
         w |= (nfc_qc[cp] << 11) | ((1 if cp in latin_lower else 0) << 13) | (hf[cp] << 14) | (ccc[cp] << 16)
         w |= ((1 if cp in full_lower else 0) << 24) | ((1 if (cp in decomp or 0xAC00 <= cp <= 0xD7A3) else 0) << 25)
+        w |= (case_ign[cp] << 26) | (cased[cp] << 27)
         props[cp] = w
     pages = {}
     page_index = []
@@ -251,7 +267,7 @@ def main():
     out.append("// sources: regex %s (grapheme props), CPython %s unicodedata %s (NFC/lower/isdigit), tokenizers %s (pre-tokenizer classes)"
                % (ver["regex"], ver["python"], ver["unicodedata"], ver["tokenizers"]))
     out.append("// property word: [0:4) GCB  [4:6) InCB  [6] ExtPict  [7:10) script tag  [10] allow-list  [11:13) NFC_QC (0 yes,1 no,2 maybe)")
-    out.append("//   [13] latin-lower changes  [14:16) HF pretok class (0 other,1 \\w,2 \\s)  [16:24) ccc  [24] str.lower changes  [25] has canonical decomposition")
+    out.append("//   [13] latin-lower changes  [14:16) HF pretok class (0 other,1 \\w,2 \\s)  [16:24) ccc  [24] str.lower changes  [25] has canonical decomposition  [26] case-ignorable  [27] cased (and not case-ignorable)")
     out.append("#define AK_N_PAGES %d" % len(page_index))
     out.append("#define AK_N_LEAF_PAGES %d" % len(pages))
     out.append("#define AK_N_DECOMP %d" % len(dec_keys))
@@ -294,6 +310,8 @@ def main():
         "latin_lower": {"%x" % k: latin_lower[k] for k in ll_keys},
         "full_lower": {"%x" % k: full_lower[k] for k in fl_keys},
         "hf_class": value_ranges(hf),
+        "case_ignorable": to_ranges(case_ign),
+        "cased": to_ranges(cased),
     }
     oj_path = os.path.join(ROOT, "oracle", "ucd_tables.json")
     with open(oj_path, "w") as f:
