@@ -17,6 +17,7 @@
 #include "ak_models.h"
 #include "ak_scan.cuh"
 #include "ak_subword.cuh"
+#include "ak_fast.cuh"
 #include "unicode_tables.inc"
 
 #define AK_BLOCK 256
@@ -25,6 +26,9 @@
 #define AK_LOOKBACK_LIMIT 4096          // bytes a span may walk backwards in AKSHAR_MODE_TILES
 #define AK_BPE_STAGE 40                 // ids per thread staged in shared memory (>= AK_SPAN + a few <s> / </s>)
 #define AK_ROWS_BLOCK 128               // rows per tile for the row-per-thread kernels
+#define AKF_WARPS (AK_BLOCK / 32)
+#define AKF_TILE (AKF_WARPS * AKF_WARP_BYTES)     // 3840 text bytes per CTA tile in the fast kernels
+#define AKF_STAGE (AKF_TILE + 1280)               // shared-memory output stage (normalize can expand a little)
 
 static_assert((int)AK_ST_OVERFLOW == (int)AKSHAR_ST_OVERFLOW && (int)AK_ST_NFC_SEGMENT == (int)AKSHAR_ST_NFC_SEGMENT &&
               (int)AK_ST_PATHOLOGICAL == (int)AKSHAR_ST_PATHOLOGICAL && (int)AK_ST_ALPHABET == (int)AKSHAR_ST_ALPHABET &&
@@ -157,6 +161,198 @@ __global__ void __launch_bounds__(AK_BLOCK) ak_normalize_kernel(const AkNormArgs
             else if (cnt > 0) st |= AK_ST_OVERFLOW;
             uint32_t st2 = 0;
             ak_norm_span(A.T, B.text, B.off, B.n_rows, sp.r_lo, sp.r_hi, sp.s, sp.e, A.flags, sp.limit, o, A.out_off, obase, st2);
+        }
+        ak_raise(B.result, st);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1 fast: normalize_text with the default flags (NFC + Roman lowercase + allow-list + elongation collapse).
+// 16 bytes per thread in registers, emit-mask fast lane (ak_fast.cuh), exact walker as the per-thread slow lane,
+// shared-memory output stage flushed with 16-byte stores, row offsets from per-chunk prefix + emit mask.
+// ------------------------------------------------------------------------------------------------
+struct AkFastNormArgs {
+    AkBatch B;
+    AkTables T;
+    uint8_t* out;
+    int64_t out_cap;
+    int64_t* out_off;
+    const int64_t* tile_row;     // [n_tiles + 1]: first row r in [0, n_rows] with off[r] >= start of tile k (n_rows + 1 if none)
+    int64_t base0;               // 16-byte aligned (as an address) start of tile 0, <= text_begin
+};
+
+// tile_row for the fast kernels; one thread per tile
+__global__ void ak_tile_rows_kernel(const int64_t* off, int64_t n_rows, int64_t base0, int n_entries, int64_t* tile_row,
+                                    const unsigned int* run_if, const int64_t* dyn_end, int64_t text_begin) {
+    if (run_if && *run_if == 0) return;
+    (void)dyn_end;
+    (void)text_begin;
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n_entries) return;
+    const int64_t pos = base0 + (int64_t)k * AKF_TILE;
+    int64_t r = ak_row_lower_bound(off, 0, n_rows, pos);
+    if (off[r] < pos) r = n_rows + 1;
+    tile_row[k] = r;
+}
+
+__device__ __forceinline__ void akf_load_chunk(const uint8_t* text, int64_t cs, int64_t tb, int64_t te, AkChunk& c) {
+    int64_t lo = tb - cs, hi = te - cs;
+    lo = lo < 0 ? 0 : (lo > 16 ? 16 : lo);
+    hi = hi < 0 ? 0 : (hi > 16 ? 16 : hi);
+    c.own = hi > lo ? (((1u << hi) - 1u) & ~((1u << lo) - 1u)) : 0u;
+    if (c.own == 0xFFFFu) {
+        const uint4 v = *reinterpret_cast<const uint4*>(text + cs);
+        c.w[0] = v.x; c.w[1] = v.y; c.w[2] = v.z; c.w[3] = v.w;
+    } else {
+        c.w[0] = c.w[1] = c.w[2] = c.w[3] = 0;
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+            if (i >= (int)lo && i < (int)hi) c.w[i >> 2] |= (uint32_t)text[cs + i] << ((i & 3) * 8);
+    }
+}
+
+__global__ void __launch_bounds__(AK_BLOCK) ak_normalize_fast_kernel(const AkFastNormArgs A) {
+    __shared__ uint32_t lut[384];
+    __shared__ uint32_t rowbits[(AKF_TILE + 64) / 32 + 2];
+    __shared__ __align__(16) uint8_t stage[AKF_STAGE + 32];
+    __shared__ uint32_t s_emit[AK_BLOCK];
+    __shared__ uint32_t s_pre[AK_BLOCK];
+    __shared__ int ws[33];
+    __shared__ int s_tile;
+    __shared__ long long s_base;
+    AkBatch B = A.B;
+    if (!ak_batch_begin(B)) return;
+    if (B.dyn_end) B.n_tiles = (int)((B.text_end - A.base0 + AKF_TILE) / AKF_TILE);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int i = tid; i < 384; i += AK_BLOCK)
+        lut[i] = i < 128 ? A.T.leaves[((uint32_t)A.T.page_index[0] << 8) | i] : A.T.leaves[((uint32_t)A.T.page_index[9] << 8) | (i - 128)];
+    const uint32_t NFLAGS = AK_NORM_ROMAN | AK_NORM_CLEAN;
+    for (;;) {
+        const int tile = ak_next_tile(B.ticket, &s_tile);
+        if (tile >= B.n_tiles) break;
+        const int64_t tile_start = A.base0 + (int64_t)tile * AKF_TILE;
+        const int64_t lo_pos = tile_start - 16, hi_pos = tile_start + AKF_TILE + 16 + 3;
+        const int64_t r0 = A.tile_row[tile], r1 = A.tile_row[tile + 1];
+        for (int i = tid; i < (AKF_TILE + 64) / 32 + 2; i += AK_BLOCK) rowbits[i] = 0;
+        __syncthreads();
+        for (int64_t r = r0 + tid; r <= B.n_rows; r += AK_BLOCK) {
+            const int64_t p = B.off[r];
+            if (p > hi_pos) break;
+            atomicOr(&rowbits[(p - lo_pos) >> 5], 1u << ((p - lo_pos) & 31));
+        }
+        for (int64_t r = r0 - 1 - tid; r >= 0; r -= AK_BLOCK) {
+            const int64_t p = B.off[r];
+            if (p < lo_pos) break;
+            atomicOr(&rowbits[(p - lo_pos) >> 5], 1u << ((p - lo_pos) & 31));
+        }
+        __syncthreads();
+        // ---- this thread's chunk
+        AkChunk c;
+        const int64_t cs = tile_start + (int64_t)warp * AKF_WARP_BYTES + (int64_t)(lane - 1) * 16;
+        akf_load_chunk(B.text, cs, B.text_begin, B.text_end, c);
+        {
+            uint32_t nx = __shfl_down_sync(0xFFFFFFFFu, c.w[0], 1);
+            if (lane == 31) {
+                nx = 0;
+                for (int i = 0; i < 4; ++i) {
+                    const int64_t q = cs + 16 + i;
+                    if (q >= B.text_begin && q < B.text_end) nx |= (uint32_t)B.text[q] << (i * 8);
+                }
+            }
+            c.w[4] = nx;
+            const int bo = (int)(cs - lo_pos);
+            c.rows = (rowbits[bo >> 5] >> (bo & 31)) & 0xFFFFu;
+        }
+        if (c.own == 0 && c.rows == 0) {
+            // entirely outside the text: acts as a row boundary for its neighbours
+            c.kept = c.lead = 0;
+            c.flags = AKF_BOUNDARY | AKF_ROWSTART;
+            c.first_w = c.last_w = c.F = c.L1 = c.L2 = AKF_NONE;
+        } else {
+            akf_phase_a(A.T, lut, c);
+        }
+        // the first owned code point against the previous chunk's last one (unknown for the left halo: conservative)
+        {
+            uint32_t pl = __shfl_up_sync(0xFFFFFFFFu, c.last_w, 1);
+            if (lane == 0) {
+                if (c.first_w != AKF_NONE && (AK_QC(c.first_w) != 0u || AK_CCC(c.first_w) != 0u)) {
+                    c.flags |= AKF_TROUBLE;
+                    if (c.flags & AKF_FIRST_DEP) c.flags |= AKF_LEAD_TROUBLE;
+                }
+            } else {
+                akf_resolve_first(c, pl);
+            }
+        }
+        AkNeighbor pv, nx;
+        pv.flags = __shfl_up_sync(0xFFFFFFFFu, c.flags, 1);
+        pv.F = AKF_NONE;
+        pv.L1 = __shfl_up_sync(0xFFFFFFFFu, c.L1, 1);
+        pv.L2 = __shfl_up_sync(0xFFFFFFFFu, c.L2, 1);
+        nx.flags = __shfl_down_sync(0xFFFFFFFFu, c.flags, 1);
+        nx.F = __shfl_down_sync(0xFFFFFFFFu, c.F, 1);
+        nx.L1 = nx.L2 = AKF_NONE;
+        const bool real = lane >= 1 && lane <= AKF_REAL;
+        bool slow = false;
+        uint32_t emit = 0;
+        int cnt = 0;
+        uint32_t st = 0;
+        int64_t ss = cs < B.text_begin ? B.text_begin : cs;
+        int64_t se = cs + 16 > B.text_end + 1 ? B.text_end + 1 : cs + 16;
+        const int64_t rlo = r0 > 0 ? r0 - 1 : 0, rhi = r1 > B.n_rows ? B.n_rows : r1;
+        if (real && ss < se) {
+            slow = akf_is_slow(c, pv, nx) || !akf_collapse(c, pv, nx, emit);
+            if (slow)
+                cnt = (int)ak_norm_span(A.T, B.text, B.off, B.n_rows, rlo, rhi, ss, se, NFLAGS, AK_LOOKBACK_LIMIT, nullptr, nullptr,
+                                        0, st);
+            else
+                cnt = __popc(emit);
+        }
+        int total;
+        const int pre = ak_block_exscan<AK_BLOCK>(cnt, ws, total);
+        if (tid < 32) {
+            long long b = ak_tile_prefix(B.state0, tile, total, (unsigned int*)&B.result[2], AK_ST_SPIN);
+            if (tid == 0) {
+                s_base = b;
+                if (tile == B.n_tiles - 1) B.totals[0] = b + total;
+            }
+        }
+        s_emit[tid] = slow ? 0x80000000u : emit;
+        s_pre[tid] = (uint32_t)pre;
+        __syncthreads();
+        const int64_t base = s_base;
+        const bool fits = base + total <= A.out_cap;
+        const bool staged = fits && total <= AKF_STAGE;
+        const int pad = (int)((uintptr_t)(A.out + base) & 15);
+        if (!fits && tid == 0 && total > 0) st |= AK_ST_OVERFLOW;
+        if (real && ss < se) {
+            uint8_t* dst = !fits ? nullptr : (staged ? stage + pad + pre : A.out + base + pre);
+            if (slow) {
+                uint32_t st2 = 0;
+                ak_norm_span(A.T, B.text, B.off, B.n_rows, rlo, rhi, ss, se, NFLAGS, AK_LOOKBACK_LIMIT, dst, A.out_off, base + pre, st2);
+            } else if (dst) {
+                akf_write(c, emit, dst);
+            }
+        }
+        __syncthreads();
+        if (staged) {
+            // stage[pad .. pad + total) -> out[base ..): stage and global share their alignment modulo 16
+            uint8_t* g = A.out + base;
+            int head = (16 - pad) & 15;
+            if (head > total) head = total;
+            if (tid < head) g[tid] = stage[pad + tid];
+            const int body = (total - head) >> 4;
+            for (int i = tid; i < body; i += AK_BLOCK)
+                *reinterpret_cast<uint4*>(g + head + 16 * i) = *reinterpret_cast<const uint4*>(stage + pad + head + 16 * i);
+            const int tail0 = head + (body << 4);
+            if (tid < total - tail0) g[tail0 + tid] = stage[pad + tail0 + tid];
+        }
+        // row offsets of the rows that start in this tile and were not written by a slow lane
+        for (int64_t r = r0 + tid; r < r1 && r <= B.n_rows; r += AK_BLOCK) {
+            const int rel = (int)(B.off[r] - tile_start);
+            const int wq = rel / AKF_WARP_BYTES, within = rel - wq * AKF_WARP_BYTES;
+            const int th = wq * 32 + 1 + (within >> 4), i = within & 15;
+            const uint32_t e = s_emit[th];
+            if (!(e & 0x80000000u)) A.out_off[r] = base + s_pre[th] + __popc(e & ((1u << i) - 1u));
         }
         ak_raise(B.result, st);
     }
@@ -412,7 +608,7 @@ struct akshar_ctx {
     AkUniHost uni_h;
     AkUniDev uni_d{};
     std::vector<void*> bpe_allocs, uni_allocs;
-    int occ_norm = 0, occ_seg = 0, occ_bpe = 0, occ_uni = 0, occ_sig = 0;
+    int occ_norm = 0, occ_seg = 0, occ_bpe = 0, occ_uni = 0, occ_sig = 0, occ_fast = 0;
 };
 
 #define AK_CUDA(ctx, call)                                                                         \
@@ -486,6 +682,7 @@ int akshar_ctx_create(int device, akshar_ctx** out) {
     ctx->T.n_ll = AK_N_LATIN_LOWER;
     ctx->T.n_fl = AK_N_FULL_LOWER;
     AK_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_norm, ak_normalize_kernel, AK_BLOCK, 0));
+    AK_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_fast, ak_normalize_fast_kernel, AK_BLOCK, 0));
     AK_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_seg, ak_segment_kernel, AK_BLOCK, 0));
     AK_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_bpe, ak_bpe_kernel, AK_BLOCK, 0));
     AK_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_uni, ak_unigram_kernel, AK_ROWS_BLOCK, 0));
@@ -518,7 +715,7 @@ int64_t akshar_launch_count(akshar_ctx* ctx) { return ctx ? ctx->launches : 0; }
 //                           BPE: NFC'd text n_bytes + n_bytes / 8 + 1024, its row offsets 8 (n_rows + 1), long-word pool)
 static inline size_t ak_align(size_t x) { return (x + 255) & ~(size_t)255; }
 static inline int64_t ak_tiles_of(int64_t n_bytes, int64_t n_rows) {
-    int64_t a = (n_bytes + n_bytes / 8 + 1024 + 1 + AK_TILE - 1) / AK_TILE;     // covers the NFC'd copy too
+    int64_t a = (n_bytes + n_bytes / 8 + 1024 + 32 + AKF_TILE - 1) / AKF_TILE;     // fast-kernel tiles; covers the NFC'd copy too
     int64_t b = (n_rows + AK_ROWS_BLOCK - 1) / AK_ROWS_BLOCK;
     return (a > b ? a : b) + 1;
 }
@@ -527,7 +724,7 @@ static inline size_t ak_pool_ints(int64_t n_bytes) {
     return (size_t)p;
 }
 struct AkWsLayout {
-    size_t control, state, nfc_text, nfc_off, pool, scratch, total;
+    size_t control, state, tile_row, nfc_text, nfc_off, pool, scratch, total;
     int64_t nfc_cap;
 };
 static AkWsLayout ak_ws_layout(int64_t n_bytes, int64_t n_rows) {
@@ -535,7 +732,8 @@ static AkWsLayout ak_ws_layout(int64_t n_bytes, int64_t n_rows) {
     size_t tiles = (size_t)ak_tiles_of(n_bytes, n_rows);
     L.control = 0;
     L.state = 256;
-    size_t at = L.state + ak_align(4 * tiles * 8);
+    L.tile_row = L.state + ak_align(4 * tiles * 8);
+    size_t at = L.tile_row + ak_align(8 * (tiles + 2));
     L.scratch = at;
     size_t uni = 4 * (size_t)(n_bytes + 2 * n_rows + 2);
     L.nfc_cap = n_bytes + n_bytes / 8 + 1024;
@@ -625,6 +823,39 @@ static int ak_empty_rows(akshar_ctx* ctx, int64_t* a, int64_t* b, cudaStream_t s
     return AKSHAR_OK;
 }
 
+// normalize_text launch: the fast kernel for the default flags in tile mode, the generic walker kernel otherwise
+static int ak_run_normalize(akshar_ctx* ctx, AkCall& C, const AkBatch& B, uint32_t flags, uint8_t* out, int64_t out_cap,
+                            int64_t* out_off) {
+    if (flags == (AK_NORM_ROMAN | AK_NORM_CLEAN) && B.mode == AKSHAR_MODE_TILES && !B.dyn_end) {
+        AkFastNormArgs F;
+        F.B = B;
+        F.T = ctx->T;
+        F.out = out;
+        F.out_cap = out_cap;
+        F.out_off = out_off;
+        F.base0 = B.text_begin - (int64_t)(((uintptr_t)B.text + (uintptr_t)B.text_begin) & 15u);
+        F.B.n_tiles = (int)((B.text_end - F.base0 + AKF_TILE) / AKF_TILE);
+        int64_t* tile_row = (int64_t*)(C.ws + C.L.tile_row);
+        F.tile_row = tile_row;
+        const int entries = F.B.n_tiles + 1;
+        ak_tile_rows_kernel<<<(entries + 255) / 256, 256, 0, C.stream>>>(B.off, B.n_rows, F.base0, entries, tile_row, B.run_if,
+                                                                        nullptr, B.text_begin);
+        int rc = ak_after_launch(ctx, "tile-rows");
+        if (rc) return rc;
+        ak_normalize_fast_kernel<<<ak_grid(ctx, ctx->occ_fast, F.B.n_tiles), AK_BLOCK, 0, C.stream>>>(F);
+        return ak_after_launch(ctx, "normalize-fast");
+    }
+    AkNormArgs A;
+    A.B = B;
+    A.T = ctx->T;
+    A.flags = flags;
+    A.out = out;
+    A.out_cap = out_cap;
+    A.out_off = out_off;
+    ak_normalize_kernel<<<ak_grid(ctx, ctx->occ_norm, A.B.n_tiles), AK_BLOCK, 0, C.stream>>>(A);
+    return ak_after_launch(ctx, "normalize");
+}
+
 int akshar_normalize_batch(akshar_ctx* ctx, const uint8_t* d_text, const int64_t* d_row_offsets, int64_t n_rows,
                            int64_t text_begin, int64_t text_end, uint32_t flags, int mode, uint8_t* d_out_text,
                            int64_t out_capacity, int64_t* d_out_row_offsets, int64_t* d_result, void* d_workspace,
@@ -638,15 +869,7 @@ int akshar_normalize_batch(akshar_ctx* ctx, const uint8_t* d_text, const int64_t
         return AKSHAR_E_ARG;
     }
     if (n_rows == 0) return ak_empty_rows(ctx, d_out_row_offsets, nullptr, C.stream);
-    AkNormArgs A;
-    A.B = C.B;
-    A.T = ctx->T;
-    A.flags = flags;
-    A.out = d_out_text;
-    A.out_cap = out_capacity;
-    A.out_off = d_out_row_offsets;
-    ak_normalize_kernel<<<ak_grid(ctx, ctx->occ_norm, A.B.n_tiles), AK_BLOCK, 0, C.stream>>>(A);
-    return ak_after_launch(ctx, "normalize");
+    return ak_run_normalize(ctx, C, C.B, flags, d_out_text, out_capacity, d_out_row_offsets);
 }
 
 int akshar_segment_batch(akshar_ctx* ctx, const uint8_t* d_text, const int64_t* d_row_offsets, int64_t n_rows,
@@ -941,16 +1164,9 @@ int akshar_tokenizer_encode_batch(akshar_ctx* ctx, const uint8_t* d_text, const 
     C.B.state1 = C.B.state0 + tiles;
     if (n_rows == 0) return ak_empty_rows(ctx, d_norm_row_offsets, d_id_splits, C.stream);
     // stage 1: normalize_text (tokenizer.py:185 preprocess); its byte total lands in result[1]
-    AkNormArgs N;
-    N.B = C.B;
-    N.B.totals = d_result + 1;
-    N.T = ctx->T;
-    N.flags = norm_flags;
-    N.out = d_norm_text;
-    N.out_cap = norm_capacity;
-    N.out_off = d_norm_row_offsets;
-    ak_normalize_kernel<<<ak_grid(ctx, ctx->occ_norm, N.B.n_tiles), AK_BLOCK, 0, C.stream>>>(N);
-    if ((rc = ak_after_launch(ctx, "normalize"))) return rc;
+    AkBatch B1 = C.B;
+    B1.totals = d_result + 1;
+    if ((rc = ak_run_normalize(ctx, C, B1, norm_flags, d_norm_text, norm_capacity, d_norm_row_offsets))) return rc;
     // stage 2: the model on the normalized rows; their length is only known on the device (dyn_end)
     AkBatch B2 = C.B;
     B2.text = d_norm_text;

@@ -54,6 +54,7 @@ AK_HD void ak_sink_put(AkNormSink& s, uint32_t cp) {
 struct AkCollapse {
     uint32_t c;        // last kept code point of the row, 0xFFFFFFFF if none
     int n;             // min(length of the run of c ending here, 3); '\n' always 1
+    bool pending;      // the span's own 2nd element of a run awaits the next kept code point (emit iff it differs)
 };
 
 // one code point of the NFC stream through lowercase + filter; returns how many code points survive (0..2)
@@ -74,26 +75,32 @@ AK_HD int ak_post_nfc(const AkTables& T, uint32_t cp, uint32_t props, uint32_t f
     return n;
 }
 
-// elongation collapse with deferred emission of the 2nd element of a run (decided when the run ends)
+// Elongation collapse, reference normalize.py:56 `(.)\1{2,}` -> `\1`: in a maximal run of equal kept code points
+// (never '\n') the 1st is emitted, the 2nd iff the run stops there, the rest never.  Every element is emitted by
+// the span that owns it: the 2nd of a run is held back until the next kept code point is known (look-ahead past the
+// span end when necessary), nothing is ever emitted on behalf of another span.
 AK_HD void ak_collapse_feed(AkCollapse& st, uint32_t y, AkNormSink& sink) {
-    if (y == st.c) {
-        if (y == 0x0Au) ak_sink_put(sink, y);
-        else if (st.n < 3) st.n++;
+    if (y == st.c && y != 0x0Au) {
+        if (st.n == 1) { st.n = 2; st.pending = true; }
+        else { st.n = 3; st.pending = false; }
     } else {
-        if (st.n == 2) ak_sink_put(sink, st.c);
+        if (st.pending) { ak_sink_put(sink, st.c); st.pending = false; }
         ak_sink_put(sink, y);
         st.c = y;
         st.n = 1;
     }
 }
-AK_HD void ak_collapse_flush(AkCollapse& st, AkNormSink& sink) {
-    if (st.n == 2) ak_sink_put(sink, st.c);
-    st.c = 0xFFFFFFFFu;
-    st.n = 0;
+// the run is over (row end: next == 0xFFFFFFFF) or the span is: resolve the held-back element
+AK_HD void ak_collapse_close(AkCollapse& st, uint32_t next, AkNormSink& sink) {
+    if (st.pending) {
+        if (next != st.c) ak_sink_put(sink, st.c);
+        st.pending = false;
+    }
 }
 
 // scan the NFC segment that starts at p (p is a head, or the first code point of a row): returns its end and
-// whether NFC can change it.  `scan_limit` > 0 bounds the scan (bytes).
+// whether NFC can change it ("troubled").  The fast lane of the kernels uses the SAME definition code point by code
+// point, so both agree on which segments are emitted whole by the owner of their head.  `scan_limit` bounds the scan.
 AK_HD int64_t ak_scan_segment(const AkTables& T, const uint8_t* t, int64_t p, int64_t re, bool& trouble,
                               int64_t scan_limit, uint32_t& status) {
     int len;
@@ -101,13 +108,17 @@ AK_HD int64_t ak_scan_segment(const AkTables& T, const uint8_t* t, int64_t p, in
     uint32_t w = ak_props(T, cp);
     trouble = AK_QC(w) != 0;
     uint32_t prev_ccc = AK_CCC(w);
+    // a QC=Maybe mark directly after an atomic starter that composes with nothing cannot change (ak_unicode.cuh)
+    bool after_inert_base = AK_INERT_BASE(w);
     int64_t q = p + len;
     while (q < re) {
         cp = ak_decode(t, q, re, len);
         w = ak_props(T, cp);
         if (AK_NFC_HEAD(w)) break;
         uint32_t cc = AK_CCC(w);
-        if (AK_QC(w) != 0 || (cc != 0 && prev_ccc > cc)) trouble = true;
+        uint32_t qc = AK_QC(w);
+        if (qc == 1u || (qc == 2u && !after_inert_base) || (cc != 0 && prev_ccc > cc)) trouble = true;
+        after_inert_base = false;
         prev_ccc = cc;
         q += len;
         if (scan_limit > 0 && q - p > scan_limit) { status |= AK_ST_PATHOLOGICAL; break; }
@@ -186,6 +197,38 @@ AK_HD_NOINLINE int ak_prev_kept(const AkTables& T, const uint8_t* t, int64_t p, 
     return nk;
 }
 
+// first kept code point produced by the text from q (a code-point start inside row [rs, re)) on, or 0xFFFFFFFF
+// when the row ends first.  q is either a segment start or inside an inert segment (a troubled one is always
+// consumed whole by the main loop).
+AK_HD_NOINLINE uint32_t ak_next_kept(const AkTables& T, const uint8_t* t, int64_t q, int64_t rs, int64_t re, uint32_t flags,
+                                     int64_t limit, uint32_t& status) {
+    const int64_t q0 = q;
+    while (q < re) {
+        if (limit > 0 && q - q0 > limit) { status |= AK_ST_PATHOLOGICAL; break; }
+        int len;
+        uint32_t cp = ak_decode(t, q, re, len);
+        uint32_t w = ak_props(T, cp);
+        if (!(flags & AK_NORM_NO_NFC) && (q == rs || AK_NFC_HEAD(w))) {
+            bool trouble;
+            int64_t hend = ak_scan_segment(T, t, q, re, trouble, limit, status);
+            if (trouble) {
+                uint32_t buf[AK_MAXSEG];
+                int n = ak_nfc_segment(T, t, q, hend, buf, status);
+                for (int i = 0; i < n; ++i) {
+                    uint32_t o[2];
+                    if (ak_post_nfc(T, buf[i], ak_props(T, buf[i]), flags, o) > 0) return o[0];
+                }
+                q = hend;
+                continue;
+            }
+        }
+        uint32_t o[2];
+        if (ak_post_nfc(T, cp, w, flags, o) > 0) return o[0];
+        q += len;
+    }
+    return 0xFFFFFFFFu;
+}
+
 // Walk span [s, e).  `off` = absolute row offsets (n_rows + 1 entries), search window [r_lo, r_hi] must satisfy
 // off[r_lo] <= first owned position or r_lo == 0, and off[r_hi] >= e or r_hi == n_rows.
 // out: nullptr for the counting pass, else the address where THIS span's first output byte goes.
@@ -212,6 +255,7 @@ AK_HD_NOINLINE int64_t ak_norm_span(const AkTables& T, const uint8_t* t, const i
     AkCollapse st;
     st.c = 0xFFFFFFFFu;
     st.n = 0;
+    st.pending = false;
     int64_t inert_until = -1;
     if (p != rs && p < total_end) {
         // mid-row start: which NFC segment are we in, and what did the row keep so far?
@@ -239,7 +283,6 @@ AK_HD_NOINLINE int64_t ak_norm_span(const AkTables& T, const uint8_t* t, const i
             nr = ak_row_lower_bound(off, nr, r_hi, p);
         }
     }
-    bool touched = false;      // did this span process a code point of the current row?
     for (;;) {
         if (p >= e) break;
         while (nr <= n_rows && off[nr] == p) {     // row-start events (several for empty rows)
@@ -248,8 +291,8 @@ AK_HD_NOINLINE int64_t ak_norm_span(const AkTables& T, const uint8_t* t, const i
             rs = p;
             st.c = 0xFFFFFFFFu;
             st.n = 0;
+            st.pending = false;
             inert_until = -1;
-            touched = false;
         }
         if (p >= total_end) break;
         re = off[nr];
@@ -290,9 +333,10 @@ AK_HD_NOINLINE int64_t ak_norm_span(const AkTables& T, const uint8_t* t, const i
             }
             p = hend;
         }
-        touched = true;
-        if (p >= re && touched && clean) ak_collapse_flush(st, sink);      // row ended inside / at the end of this span
+        if (p >= re) ak_collapse_close(st, 0xFFFFFFFFu, sink);      // the row ended with a code point of this span
     }
+    // the span ended inside a row while holding back the 2nd element of a run: look ahead for the next kept one
+    if (st.pending) ak_collapse_close(st, ak_next_kept(T, t, p, rs, re, flags, limit, status), sink);
     return sink.cnt;
 }
 

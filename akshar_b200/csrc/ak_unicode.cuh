@@ -24,6 +24,12 @@
 #define AK_CCC(w) (((w) >> 16) & 255u)
 #define AK_FULL_LOWER(w) (((w) >> 24) & 1u)
 #define AK_HAS_DECOMP(w) (((w) >> 25) & 1u)
+#define AK_CASE_IGNORABLE(w) (((w) >> 26) & 1u)
+#define AK_CASED(w) (((w) >> 27) & 1u)
+#define AK_COMP_FIRST(w) (((w) >> 28) & 1u)
+// an atomic starter that can neither decompose nor compose with a following mark: a QC=Maybe mark right after it
+// is left alone by NFC (e.g. Devanagari consonant + nukta, except U+0928 / U+0930 / U+0933)
+#define AK_INERT_BASE(w) (((w) & ((255u << 16) | (3u << 11) | (1u << 25) | (1u << 28))) == 0u)
 // a code point that starts an NFC segment: starter that neither decomposes nor composes backwards
 #define AK_NFC_HEAD(w) (((w) & ((255u << 16) | (3u << 11))) == 0u)
 

@@ -7,6 +7,7 @@
 #include <vector>
 #include <math.h>
 #include "../../akshar_b200/csrc/ak_subword.cuh"
+#include "../../akshar_b200/csrc/ak_fast.cuh"
 #include "../../akshar_b200/csrc/ak_models.h"
 #include "../../akshar_b200/csrc/unicode_tables.inc"
 
@@ -67,6 +68,92 @@ void hh_segment(const uint8_t* text, const int64_t* off, int64_t n_rows, uint32_
     *status = st;
 }
 
+
+// The fast normalize kernel's structure on the CPU: 16-byte chunks, "warps" of `real` chunks + 2 halo chunks, the
+// same phase functions (ak_fast.cuh), the walker for slow chunks.  n_slow counts the chunks that took the slow lane.
+static void hh_make_chunk(const uint8_t* text, int64_t cs, int64_t tb, int64_t te, const std::vector<uint8_t>& rowstart,
+                          int64_t base0, AkChunk& c) {
+    c.w[0] = c.w[1] = c.w[2] = c.w[3] = c.w[4] = 0;
+    c.own = 0;
+    c.rows = 0;
+    for (int i = 0; i < 20; ++i) {
+        int64_t q = cs + i;
+        if (q >= tb && q < te) {
+            c.w[i >> 2] |= (uint32_t)text[q] << ((i & 3) * 8);
+            if (i < 16) c.own |= 1u << i;
+        }
+        if (i < 16 && q >= base0 && q - base0 < (int64_t)rowstart.size() && rowstart[(size_t)(q - base0)]) c.rows |= 1u << i;
+    }
+}
+
+int64_t hh_fast_normalize(const uint8_t* text, const int64_t* off, int64_t n_rows, int real, uint8_t* out, int64_t* out_off,
+                          uint32_t* status, int64_t* n_slow) {
+    AkTables T = host_tables();
+    std::vector<uint32_t> lut(384);
+    for (int i = 0; i < 384; ++i) lut[(size_t)i] = i < 128 ? ak_props(T, (uint32_t)i) : ak_props(T, 0x900u + (uint32_t)(i - 128));
+    const int64_t tb = off[0], te = off[n_rows], base0 = tb;
+    std::vector<uint8_t> rowstart((size_t)(te - base0) + 64, 0);
+    for (int64_t r = 0; r <= n_rows; ++r) rowstart[(size_t)(off[r] - base0)] = 1;
+    const int64_t n_chunks = (te - base0 + 1 + 15) / 16;
+    const uint32_t NFLAGS = AK_NORM_ROMAN | AK_NORM_CLEAN;
+    int64_t base = 0, row = 0, slow_cnt = 0;
+    uint32_t st = 0;
+    std::vector<AkChunk> lanes((size_t)real + 2);
+    for (int64_t w0 = 0; w0 < n_chunks; w0 += real) {
+        for (int l = 0; l < real + 2; ++l) {
+            AkChunk& c = lanes[(size_t)l];
+            int64_t cs = base0 + (w0 - 1 + l) * 16;
+            hh_make_chunk(text, cs, tb, te, rowstart, base0, c);
+            if (c.own == 0 && c.rows == 0) {
+                c.kept = c.lead = 0;
+                c.flags = AKF_BOUNDARY | AKF_ROWSTART;
+                c.first_w = c.last_w = c.F = c.L1 = c.L2 = AKF_NONE;
+            } else {
+                akf_phase_a(T, lut.data(), c);
+            }
+        }
+        for (int l = 0; l < real + 2; ++l) {
+            AkChunk& c = lanes[(size_t)l];
+            if (l == 0) {
+                if (c.first_w != AKF_NONE && (AK_QC(c.first_w) != 0u || AK_CCC(c.first_w) != 0u)) {
+                    c.flags |= AKF_TROUBLE;
+                    if (c.flags & AKF_FIRST_DEP) c.flags |= AKF_LEAD_TROUBLE;
+                }
+            } else {
+                akf_resolve_first(c, lanes[(size_t)l - 1].last_w);
+            }
+        }
+        for (int l = 1; l <= real; ++l) {
+            AkChunk& c = lanes[(size_t)l];
+            int64_t cs = base0 + (w0 - 1 + l) * 16;
+            int64_t ss = cs < tb ? tb : cs, se = cs + 16 > te + 1 ? te + 1 : cs + 16;
+            if (ss >= se) continue;
+            AkNeighbor pv, nx;
+            pv.flags = lanes[(size_t)l - 1].flags; pv.F = AKF_NONE; pv.L1 = lanes[(size_t)l - 1].L1; pv.L2 = lanes[(size_t)l - 1].L2;
+            nx.flags = lanes[(size_t)l + 1].flags; nx.F = lanes[(size_t)l + 1].F; nx.L1 = nx.L2 = AKF_NONE;
+            uint32_t emit = 0;
+            bool slow = akf_is_slow(c, pv, nx) || !akf_collapse(c, pv, nx, emit);
+            while (row <= n_rows && off[row] < ss) ++row;
+            if (slow) {
+                ++slow_cnt;
+                base += ak_norm_span(T, text, off, n_rows, 0, n_rows, ss, se, NFLAGS, 0, out + base, out_off, base, st);
+                while (row <= n_rows && off[row] < se) ++row;
+            } else {
+                while (row <= n_rows && off[row] < se) {
+                    int i = (int)(off[row] - cs);
+                    int before = 0;
+                    for (int b = 0; b < i; ++b) before += (emit >> b) & 1u;
+                    out_off[row] = base + before;
+                    ++row;
+                }
+                base += akf_write(c, emit, out + base);
+            }
+        }
+    }
+    *status = st;
+    *n_slow = slow_cnt;
+    return base;
+}
 
 // roman_phonetic_signature of every row; returns output bytes
 int64_t hh_signature(const uint8_t* text, const int64_t* off, int64_t n_rows, uint8_t* out, int64_t* out_off) {

@@ -96,3 +96,27 @@ def test_single_stage_flags(flags, fn):
         assert st == 0
         b = out.tobytes()
         assert [b[out_off[i]:out_off[i + 1]] for i in range(len(lines))] == exp
+
+
+@pytest.mark.parametrize('real', [30, 1, 2, 7])
+def test_fast_lane_structure(real):
+    """the fast kernel's chunk / halo / slow-lane structure gives the oracle's bytes and row offsets"""
+    lines = list(_lines())
+    data, off = sc.pack(lines)
+    exp, exp_off = _exp_norm(7)
+    out, out_off, st, n_slow = W.fast_normalize(data, off, real=real)
+    assert st == 0
+    assert np.array_equal(out_off, exp_off)
+    assert out.tobytes() == exp.tobytes()
+
+
+def test_fast_lane_is_mostly_fast():
+    for kind in ('hinglish', 'hindi', 'social'):
+        lines = sc.Corpus(kind, 8).lines(200000)
+        data, off = sc.pack(lines)
+        out, out_off, st, n_slow = W.fast_normalize(data, off)
+        exp, exp_off = OB.normalize_batch(lines)
+        assert st == 0 and np.array_equal(out_off, exp_off) and out.tobytes() == exp.tobytes()
+        n_chunks = data.size / 16
+        print(kind, 'slow chunks: %.2f %%' % (100.0 * n_slow / n_chunks))
+        assert n_slow / n_chunks < 0.05

@@ -221,12 +221,15 @@ def main():
         assert v == [0x20] and hf[cp] == 2, hex(cp)
 
     # ---- pack the 32-bit property word
+    # first element of some canonical composition pair (incl. the algorithmic Hangul L + V; LV + T is covered by
+    # the decomposition bit): a mark after such a starter may compose, after any other atomic starter it cannot
+    comp_first = set(a for (a, b) in pairs) | set(range(0x1100, 0x1113))
     props = [0] * NCP
     for cp in range(NCP):
         w = gcb[cp] | (incb[cp] << 4) | (extpict[cp] << 6) | (tag[cp] << 7) | (allow[cp] << 10)
         w |= (nfc_qc[cp] << 11) | ((1 if cp in latin_lower else 0) << 13) | (hf[cp] << 14) | (ccc[cp] << 16)
         w |= ((1 if cp in full_lower else 0) << 24) | ((1 if (cp in decomp or 0xAC00 <= cp <= 0xD7A3) else 0) << 25)
-        w |= (case_ign[cp] << 26) | (cased[cp] << 27)
+        w |= (case_ign[cp] << 26) | (cased[cp] << 27) | ((1 if cp in comp_first else 0) << 28)
         props[cp] = w
     pages = {}
     page_index = []
@@ -267,7 +270,7 @@ def main():
     out.append("// sources: regex %s (grapheme props), CPython %s unicodedata %s (NFC/lower/isdigit), tokenizers %s (pre-tokenizer classes)"
                % (ver["regex"], ver["python"], ver["unicodedata"], ver["tokenizers"]))
     out.append("// property word: [0:4) GCB  [4:6) InCB  [6] ExtPict  [7:10) script tag  [10] allow-list  [11:13) NFC_QC (0 yes,1 no,2 maybe)")
-    out.append("//   [13] latin-lower changes  [14:16) HF pretok class (0 other,1 \\w,2 \\s)  [16:24) ccc  [24] str.lower changes  [25] has canonical decomposition  [26] case-ignorable  [27] cased (and not case-ignorable)")
+    out.append("//   [13] latin-lower changes  [14:16) HF pretok class (0 other,1 \\w,2 \\s)  [16:24) ccc  [24] str.lower changes  [25] has canonical decomposition  [26] case-ignorable  [27] cased (and not case-ignorable)  [28] first of a composition pair")
     out.append("#define AK_N_PAGES %d" % len(page_index))
     out.append("#define AK_N_LEAF_PAGES %d" % len(pages))
     out.append("#define AK_N_DECOMP %d" % len(dec_keys))
