@@ -211,56 +211,78 @@ __device__ __forceinline__ void akf_load_chunk(const uint8_t* text, int64_t cs, 
     }
 }
 
-__global__ void __launch_bounds__(AK_BLOCK) ak_normalize_fast_kernel(const AkFastNormArgs A) {
+// Slow chunks are not processed where they are found: a lane that cannot take the fast lane appends its chunk to a
+// work list, and two small kernels run the exact walker over that list with one thread per entry.  A 16-byte walk
+// costs tens of microseconds of dependent instructions; inside the tile kernels it would stall its whole CTA (and,
+// through an ordered tile prefix, every later tile), on the list thousands of them overlap.
+struct AkSlowEntry {
+    int64_t pos;         // chunk start (absolute byte index)
+    int64_t out_base;    // filled by the write kernel: where this chunk's output starts
+    int32_t cnt;         // filled by the slow count kernel
+    int32_t tile;
+};
+
+struct AkNfWork {
+    uint32_t* info;            // [n_tiles * AK_BLOCK] per lane: emit mask, or 0x80000000 | work-list index
+    int32_t* tile_total;       // [n_tiles] output bytes of the tile
+    int64_t* tile_base;        // [n_tiles + 1] exclusive prefix
+    AkSlowEntry* slow;
+    unsigned int* n_slow;
+    unsigned int slow_cap;
+};
+
+__device__ __forceinline__ void akf_tile_rows(const AkBatch& B, const int64_t* tile_row, int tile, int64_t tile_start,
+                                             uint32_t* rowbits) {
+    const int tid = threadIdx.x;
+    const int64_t lo_pos = tile_start - 16, hi_pos = tile_start + AKF_TILE + 16 + 3;
+    const int64_t r0 = tile_row[tile];
+    for (int i = tid; i < (AKF_TILE + 64) / 32 + 2; i += AK_BLOCK) rowbits[i] = 0;
+    __syncthreads();
+    for (int64_t r = r0 + tid; r <= B.n_rows; r += AK_BLOCK) {
+        const int64_t p = B.off[r];
+        if (p > hi_pos) break;
+        atomicOr(&rowbits[(p - lo_pos) >> 5], 1u << ((p - lo_pos) & 31));
+    }
+    for (int64_t r = r0 - 1 - tid; r >= 0; r -= AK_BLOCK) {
+        const int64_t p = B.off[r];
+        if (p < lo_pos) break;
+        atomicOr(&rowbits[(p - lo_pos) >> 5], 1u << ((p - lo_pos) & 31));
+    }
+    __syncthreads();
+}
+
+// chunk bytes + the 4 bytes that follow (from the next lane; the right halo reads them itself)
+__device__ __forceinline__ void akf_load_lane(const AkBatch& B, int64_t cs, AkChunk& c) {
+    akf_load_chunk(B.text, cs, B.text_begin, B.text_end, c);
+    uint32_t nx = __shfl_down_sync(0xFFFFFFFFu, c.w[0], 1);
+    if ((threadIdx.x & 31) == 31) {
+        nx = 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int64_t q = cs + 16 + i;
+            if (q >= B.text_begin && q < B.text_end) nx |= (uint32_t)B.text[q] << (i * 8);
+        }
+    }
+    c.w[4] = nx;
+}
+
+// ---- K1a: classify every chunk: emit mask for the fast lane, work-list entry otherwise; per-tile fast byte counts
+__global__ void __launch_bounds__(AK_BLOCK) ak_nf_classify_kernel(const AkFastNormArgs A, const AkNfWork W) {
     __shared__ uint32_t lut[384];
     __shared__ uint32_t rowbits[(AKF_TILE + 64) / 32 + 2];
-    __shared__ __align__(16) uint8_t stage[AKF_STAGE + 32];
-    __shared__ uint32_t s_emit[AK_BLOCK];
-    __shared__ uint32_t s_pre[AK_BLOCK];
-    __shared__ int ws[33];
-    __shared__ int s_tile;
-    __shared__ long long s_base;
-    AkBatch B = A.B;
-    if (!ak_batch_begin(B)) return;
-    if (B.dyn_end) B.n_tiles = (int)((B.text_end - A.base0 + AKF_TILE) / AKF_TILE);
+    __shared__ int s_red[AKF_WARPS];
+    const AkBatch& B = A.B;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int i = tid; i < 384; i += AK_BLOCK)
         lut[i] = i < 128 ? A.T.leaves[((uint32_t)A.T.page_index[0] << 8) | i] : A.T.leaves[((uint32_t)A.T.page_index[9] << 8) | (i - 128)];
-    const uint32_t NFLAGS = AK_NORM_ROMAN | AK_NORM_CLEAN;
-    for (;;) {
-        const int tile = ak_next_tile(B.ticket, &s_tile);
-        if (tile >= B.n_tiles) break;
+    for (int tile = blockIdx.x; tile < B.n_tiles; tile += gridDim.x) {
         const int64_t tile_start = A.base0 + (int64_t)tile * AKF_TILE;
-        const int64_t lo_pos = tile_start - 16, hi_pos = tile_start + AKF_TILE + 16 + 3;
-        const int64_t r0 = A.tile_row[tile], r1 = A.tile_row[tile + 1];
-        for (int i = tid; i < (AKF_TILE + 64) / 32 + 2; i += AK_BLOCK) rowbits[i] = 0;
-        __syncthreads();
-        for (int64_t r = r0 + tid; r <= B.n_rows; r += AK_BLOCK) {
-            const int64_t p = B.off[r];
-            if (p > hi_pos) break;
-            atomicOr(&rowbits[(p - lo_pos) >> 5], 1u << ((p - lo_pos) & 31));
-        }
-        for (int64_t r = r0 - 1 - tid; r >= 0; r -= AK_BLOCK) {
-            const int64_t p = B.off[r];
-            if (p < lo_pos) break;
-            atomicOr(&rowbits[(p - lo_pos) >> 5], 1u << ((p - lo_pos) & 31));
-        }
-        __syncthreads();
-        // ---- this thread's chunk
+        akf_tile_rows(B, A.tile_row, tile, tile_start, rowbits);      // contains the barriers that also protect lut / s_red
         AkChunk c;
         const int64_t cs = tile_start + (int64_t)warp * AKF_WARP_BYTES + (int64_t)(lane - 1) * 16;
-        akf_load_chunk(B.text, cs, B.text_begin, B.text_end, c);
+        akf_load_lane(B, cs, c);
         {
-            uint32_t nx = __shfl_down_sync(0xFFFFFFFFu, c.w[0], 1);
-            if (lane == 31) {
-                nx = 0;
-                for (int i = 0; i < 4; ++i) {
-                    const int64_t q = cs + 16 + i;
-                    if (q >= B.text_begin && q < B.text_end) nx |= (uint32_t)B.text[q] << (i * 8);
-                }
-            }
-            c.w[4] = nx;
-            const int bo = (int)(cs - lo_pos);
+            const int bo = (int)(cs - (tile_start - 16));
             c.rows = (rowbits[bo >> 5] >> (bo & 31)) & 0xFFFFu;
         }
         if (c.own == 0 && c.rows == 0) {
@@ -271,17 +293,21 @@ __global__ void __launch_bounds__(AK_BLOCK) ak_normalize_fast_kernel(const AkFas
         } else {
             akf_phase_a(A.T, lut, c);
         }
-        // the first owned code point against the previous chunk's last one (unknown for the left halo: conservative)
+        // the first owned code point against the last one of the previous chunk
         {
             uint32_t pl = __shfl_up_sync(0xFFFFFFFFu, c.last_w, 1);
             if (lane == 0) {
-                if (c.first_w != AKF_NONE && (AK_QC(c.first_w) != 0u || AK_CCC(c.first_w) != 0u)) {
-                    c.flags |= AKF_TROUBLE;
-                    if (c.flags & AKF_FIRST_DEP) c.flags |= AKF_LEAD_TROUBLE;
+                // left halo: decode the code point that ends right before the chunk (same row only)
+                pl = AKF_NONE;
+                if (c.first_w != AKF_NONE && cs > B.text_begin) {
+                    int64_t q = cs - 1;
+                    int k = 0;
+                    while (q > B.text_begin && k < 3 && (B.text[q] & 0xC0u) == 0x80u) { --q; ++k; }
+                    int len;
+                    pl = akf_props(A.T, lut, ak_decode(B.text, q, B.text_end, len));
                 }
-            } else {
-                akf_resolve_first(c, pl);
             }
+            akf_resolve_first(c, pl);
         }
         AkNeighbor pv, nx;
         pv.flags = __shfl_up_sync(0xFFFFFFFFu, c.flags, 1);
@@ -292,50 +318,162 @@ __global__ void __launch_bounds__(AK_BLOCK) ak_normalize_fast_kernel(const AkFas
         nx.F = __shfl_down_sync(0xFFFFFFFFu, c.F, 1);
         nx.L1 = nx.L2 = AKF_NONE;
         const bool real = lane >= 1 && lane <= AKF_REAL;
-        bool slow = false;
-        uint32_t emit = 0;
+        const int64_t ss = cs < B.text_begin ? B.text_begin : cs;
+        const int64_t se = cs + 16 > B.text_end + 1 ? B.text_end + 1 : cs + 16;
+        uint32_t info = 0;
         int cnt = 0;
-        uint32_t st = 0;
-        int64_t ss = cs < B.text_begin ? B.text_begin : cs;
-        int64_t se = cs + 16 > B.text_end + 1 ? B.text_end + 1 : cs + 16;
-        const int64_t rlo = r0 > 0 ? r0 - 1 : 0, rhi = r1 > B.n_rows ? B.n_rows : r1;
         if (real && ss < se) {
-            slow = akf_is_slow(c, pv, nx) || !akf_collapse(c, pv, nx, emit);
-            if (slow)
-                cnt = (int)ak_norm_span(A.T, B.text, B.off, B.n_rows, rlo, rhi, ss, se, NFLAGS, AK_LOOKBACK_LIMIT, nullptr, nullptr,
-                                        0, st);
-            else
+            uint32_t emit = 0;
+            const bool slow = akf_is_slow(c, pv, nx) || !akf_collapse(c, pv, nx, emit);
+            if (slow) {
+                const unsigned int idx = atomicAdd(W.n_slow, 1u);
+                if (idx < W.slow_cap) {
+                    AkSlowEntry e;
+                    e.pos = cs;
+                    e.out_base = 0;
+                    e.cnt = 0;
+                    e.tile = tile;
+                    W.slow[idx] = e;
+                } else {
+                    ak_raise(B.result, AK_ST_PATHOLOGICAL);     // too many slow chunks: the host re-runs row by row
+                }
+                info = 0x80000000u | idx;
+            } else {
+                info = emit;
                 cnt = __popc(emit);
-        }
-        int total;
-        const int pre = ak_block_exscan<AK_BLOCK>(cnt, ws, total);
-        if (tid < 32) {
-            long long b = ak_tile_prefix(B.state0, tile, total, (unsigned int*)&B.result[2], AK_ST_SPIN);
-            if (tid == 0) {
-                s_base = b;
-                if (tile == B.n_tiles - 1) B.totals[0] = b + total;
             }
         }
-        s_emit[tid] = slow ? 0x80000000u : emit;
-        s_pre[tid] = (uint32_t)pre;
+        W.info[(size_t)tile * AK_BLOCK + tid] = info;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) cnt += __shfl_xor_sync(0xFFFFFFFFu, cnt, d);
+        if (lane == 0) s_red[warp] = cnt;
         __syncthreads();
-        const int64_t base = s_base;
+        if (tid == 0) {
+            int t = 0;
+#pragma unroll
+            for (int w = 0; w < AKF_WARPS; ++w) t += s_red[w];
+            W.tile_total[tile] = t;
+        }
+    }
+}
+
+// ---- K1b / K1e: the walker over the work list (count pass, then write pass)
+struct AkNfSlowArgs {
+    AkBatch B;
+    AkTables T;
+    AkNfWork W;
+    const int64_t* tile_row;
+    uint8_t* out;
+    int64_t out_cap;
+    int64_t* out_off;
+    int write;
+};
+
+__global__ void __launch_bounds__(128) ak_nf_slow_kernel(const AkNfSlowArgs A) {
+    const AkBatch& B = A.B;
+    unsigned int n = *A.W.n_slow;
+    if (n > A.W.slow_cap) n = A.W.slow_cap;
+    const uint32_t NFLAGS = AK_NORM_ROMAN | AK_NORM_CLEAN;
+    for (unsigned int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+        AkSlowEntry e = A.W.slow[j];
+        const int64_t ss = e.pos < B.text_begin ? B.text_begin : e.pos;
+        const int64_t se = e.pos + 16 > B.text_end + 1 ? B.text_end + 1 : e.pos + 16;
+        const int64_t r0 = A.tile_row[e.tile], r1 = A.tile_row[e.tile + 1];
+        const int64_t rlo = r0 > 0 ? r0 - 1 : 0, rhi = r1 > B.n_rows ? B.n_rows : r1;
+        uint32_t st = 0;
+        if (!A.write) {
+            const int cnt = (int)ak_norm_span(A.T, B.text, B.off, B.n_rows, rlo, rhi, ss, se, NFLAGS, AK_LOOKBACK_LIMIT, nullptr,
+                                              nullptr, 0, st);
+            A.W.slow[j].cnt = cnt;
+            atomicAdd(&A.W.tile_total[e.tile], cnt);
+        } else {
+            uint8_t* dst = (e.out_base + e.cnt <= A.out_cap) ? A.out + e.out_base : nullptr;
+            ak_norm_span(A.T, B.text, B.off, B.n_rows, rlo, rhi, ss, se, NFLAGS, AK_LOOKBACK_LIMIT, dst, A.out_off, e.out_base, st);
+        }
+        ak_raise(B.result, st);
+    }
+}
+
+// ---- K1c: exclusive prefix of the tile totals (one CTA; the array has one entry per 3840 bytes of text)
+__global__ void __launch_bounds__(1024) ak_nf_scan_kernel(const int32_t* tile_total, int64_t* tile_base, int n_tiles,
+                                                          int64_t* total_out) {
+    __shared__ long long ws[33];
+    __shared__ long long carry;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) carry = 0;
+    __syncthreads();
+    for (int b = 0; b < n_tiles; b += 1024) {
+        const int i = b + tid;
+        long long v = i < n_tiles ? tile_total[i] : 0;
+        long long inc = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            long long y = __shfl_up_sync(0xFFFFFFFFu, inc, d);
+            if (lane >= d) inc += y;
+        }
+        if (lane == 31) ws[warp] = inc;
+        __syncthreads();
+        if (warp == 0) {
+            long long x = ws[lane], xi = x;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                long long y = __shfl_up_sync(0xFFFFFFFFu, xi, d);
+                if (lane >= d) xi += y;
+            }
+            ws[lane] = xi - x;
+            if (lane == 31) ws[32] = xi;
+        }
+        __syncthreads();
+        const long long ex = carry + ws[warp] + inc - v;
+        if (i < n_tiles) tile_base[i] = ex;
+        __syncthreads();
+        if (tid == 0) carry += ws[32];
+        __syncthreads();
+    }
+    if (tid == 0) {
+        tile_base[n_tiles] = carry;
+        *total_out = carry;
+    }
+}
+
+// ---- K1d: write the fast lanes' bytes (staged in shared memory, 16-byte stores) and the row offsets
+__global__ void __launch_bounds__(AK_BLOCK) ak_nf_write_kernel(const AkFastNormArgs A, const AkNfWork W) {
+    __shared__ __align__(16) uint8_t stage[AKF_STAGE + 32];
+    __shared__ uint32_t s_emit[AK_BLOCK];
+    __shared__ uint32_t s_pre[AK_BLOCK];
+    __shared__ int ws[33];
+    const AkBatch& B = A.B;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int tile = blockIdx.x; tile < B.n_tiles; tile += gridDim.x) {
+        const int64_t tile_start = A.base0 + (int64_t)tile * AKF_TILE;
+        const int64_t r0 = A.tile_row[tile], r1 = A.tile_row[tile + 1];
+        const int64_t cs = tile_start + (int64_t)warp * AKF_WARP_BYTES + (int64_t)(lane - 1) * 16;
+        AkChunk c;
+        akf_load_lane(B, cs, c);
+        const uint32_t info = W.info[(size_t)tile * AK_BLOCK + tid];
+        const bool slow = (info & 0x80000000u) != 0;
+        const unsigned int sidx = info & 0x7FFFFFFFu;
+        int cnt = 0;
+        if (slow) { if (sidx < W.slow_cap) cnt = W.slow[sidx].cnt; }
+        else cnt = __popc(info);
+        int total;
+        const int pre = ak_block_exscan<AK_BLOCK>(cnt, ws, total);
+        const int64_t base = W.tile_base[tile];
         const bool fits = base + total <= A.out_cap;
         const bool staged = fits && total <= AKF_STAGE;
         const int pad = (int)((uintptr_t)(A.out + base) & 15);
-        if (!fits && tid == 0 && total > 0) st |= AK_ST_OVERFLOW;
-        if (real && ss < se) {
-            uint8_t* dst = !fits ? nullptr : (staged ? stage + pad + pre : A.out + base + pre);
-            if (slow) {
-                uint32_t st2 = 0;
-                ak_norm_span(A.T, B.text, B.off, B.n_rows, rlo, rhi, ss, se, NFLAGS, AK_LOOKBACK_LIMIT, dst, A.out_off, base + pre, st2);
-            } else if (dst) {
-                akf_write(c, emit, dst);
-            }
+        if (!fits && tid == 0 && total > 0) ak_raise(B.result, AK_ST_OVERFLOW);
+        s_emit[tid] = info;
+        s_pre[tid] = (uint32_t)pre;
+        if (slow) {
+            if (sidx < W.slow_cap) W.slow[sidx].out_base = base + pre;
+        } else if (info && fits) {
+            akf_write(c, info, staged ? stage + pad + pre : A.out + base + pre);
         }
         __syncthreads();
         if (staged) {
-            // stage[pad .. pad + total) -> out[base ..): stage and global share their alignment modulo 16
+            // stage[pad .. pad + total) -> out[base ..): stage and global share their alignment modulo 16.  The holes
+            // of slow chunks are copied as garbage here and filled by the slow write kernel afterwards.
             uint8_t* g = A.out + base;
             int head = (16 - pad) & 15;
             if (head > total) head = total;
@@ -346,7 +484,7 @@ __global__ void __launch_bounds__(AK_BLOCK) ak_normalize_fast_kernel(const AkFas
             const int tail0 = head + (body << 4);
             if (tid < total - tail0) g[tail0 + tid] = stage[pad + tail0 + tid];
         }
-        // row offsets of the rows that start in this tile and were not written by a slow lane
+        // row offsets of the rows that start in a fast chunk of this tile (slow chunks write their own)
         for (int64_t r = r0 + tid; r < r1 && r <= B.n_rows; r += AK_BLOCK) {
             const int rel = (int)(B.off[r] - tile_start);
             const int wq = rel / AKF_WARP_BYTES, within = rel - wq * AKF_WARP_BYTES;
@@ -354,7 +492,7 @@ __global__ void __launch_bounds__(AK_BLOCK) ak_normalize_fast_kernel(const AkFas
             const uint32_t e = s_emit[th];
             if (!(e & 0x80000000u)) A.out_off[r] = base + s_pre[th] + __popc(e & ((1u << i) - 1u));
         }
-        ak_raise(B.result, st);
+        __syncthreads();
     }
 }
 
@@ -608,7 +746,7 @@ struct akshar_ctx {
     AkUniHost uni_h;
     AkUniDev uni_d{};
     std::vector<void*> bpe_allocs, uni_allocs;
-    int occ_norm = 0, occ_seg = 0, occ_bpe = 0, occ_uni = 0, occ_sig = 0, occ_fast = 0;
+    int occ_norm = 0, occ_seg = 0, occ_bpe = 0, occ_uni = 0, occ_sig = 0, occ_nf_classify = 0, occ_nf_write = 0;
 };
 
 #define AK_CUDA(ctx, call)                                                                         \
@@ -682,7 +820,8 @@ int akshar_ctx_create(int device, akshar_ctx** out) {
     ctx->T.n_ll = AK_N_LATIN_LOWER;
     ctx->T.n_fl = AK_N_FULL_LOWER;
     AK_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_norm, ak_normalize_kernel, AK_BLOCK, 0));
-    AK_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_fast, ak_normalize_fast_kernel, AK_BLOCK, 0));
+    AK_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_nf_classify, ak_nf_classify_kernel, AK_BLOCK, 0));
+    AK_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_nf_write, ak_nf_write_kernel, AK_BLOCK, 0));
     AK_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_seg, ak_segment_kernel, AK_BLOCK, 0));
     AK_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_bpe, ak_bpe_kernel, AK_BLOCK, 0));
     AK_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_uni, ak_unigram_kernel, AK_ROWS_BLOCK, 0));
@@ -741,7 +880,11 @@ static AkWsLayout ak_ws_layout(int64_t n_bytes, int64_t n_rows) {
     L.nfc_off = L.nfc_text + ak_align((size_t)L.nfc_cap);
     L.pool = L.nfc_off + ak_align(8 * (size_t)(n_rows + 1));
     size_t bpe = (L.pool + ak_align(4 * ak_pool_ints(n_bytes))) - at;
-    L.total = at + ak_align(uni > bpe ? uni : bpe);
+    // fast normalize: per-lane info words, tile totals / bases, slow work list
+    size_t nf = ak_align(tiles * AK_BLOCK * 4) + ak_align(tiles * 4) + ak_align((tiles + 1) * 8) +
+                ak_align((tiles * AK_BLOCK / 16 + 1024) * sizeof(AkSlowEntry));
+    size_t m = uni > bpe ? uni : bpe;
+    L.total = at + ak_align(m > nf ? m : nf);
     return L;
 }
 
@@ -842,8 +985,36 @@ static int ak_run_normalize(akshar_ctx* ctx, AkCall& C, const AkBatch& B, uint32
                                                                         nullptr, B.text_begin);
         int rc = ak_after_launch(ctx, "tile-rows");
         if (rc) return rc;
-        ak_normalize_fast_kernel<<<ak_grid(ctx, ctx->occ_fast, F.B.n_tiles), AK_BLOCK, 0, C.stream>>>(F);
-        return ak_after_launch(ctx, "normalize-fast");
+        AkNfWork W;
+        const size_t nt = (size_t)F.B.n_tiles;
+        char* wp = C.ws + C.L.scratch;
+        W.info = (uint32_t*)wp;                         wp += ak_align(nt * AK_BLOCK * 4);
+        W.tile_total = (int32_t*)wp;                    wp += ak_align(nt * 4);
+        W.tile_base = (int64_t*)wp;                     wp += ak_align((nt + 1) * 8);
+        W.slow = (AkSlowEntry*)wp;
+        W.n_slow = (unsigned int*)(C.ws + 72);
+        W.slow_cap = (unsigned int)(nt * AK_BLOCK / 16 + 1024);
+        ak_nf_classify_kernel<<<ak_grid(ctx, ctx->occ_nf_classify, F.B.n_tiles), AK_BLOCK, 0, C.stream>>>(F, W);
+        if ((rc = ak_after_launch(ctx, "normalize-classify"))) return rc;
+        AkNfSlowArgs S;
+        S.B = B;
+        S.T = ctx->T;
+        S.W = W;
+        S.tile_row = tile_row;
+        S.out = out;
+        S.out_cap = out_cap;
+        S.out_off = out_off;
+        S.write = 0;
+        const int slow_grid = ctx->sm_count * 4;
+        ak_nf_slow_kernel<<<slow_grid, 128, 0, C.stream>>>(S);
+        if ((rc = ak_after_launch(ctx, "normalize-slow-count"))) return rc;
+        ak_nf_scan_kernel<<<1, 1024, 0, C.stream>>>(W.tile_total, W.tile_base, F.B.n_tiles, B.totals);
+        if ((rc = ak_after_launch(ctx, "normalize-scan"))) return rc;
+        ak_nf_write_kernel<<<ak_grid(ctx, ctx->occ_nf_write, F.B.n_tiles), AK_BLOCK, 0, C.stream>>>(F, W);
+        if ((rc = ak_after_launch(ctx, "normalize-write"))) return rc;
+        S.write = 1;
+        ak_nf_slow_kernel<<<slow_grid, 128, 0, C.stream>>>(S);
+        return ak_after_launch(ctx, "normalize-slow-write");
     }
     AkNormArgs A;
     A.B = B;

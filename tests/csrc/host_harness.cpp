@@ -2,6 +2,7 @@
 // It lets tests/test_span_walkers.py check, without a GPU, that cutting the buffer into arbitrary spans never
 // changes the result (the property the CUDA kernels rely on).  Not linked into libakshar_b200.so.
 #include <stdint.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 #include <vector>
@@ -115,10 +116,17 @@ int64_t hh_fast_normalize(const uint8_t* text, const int64_t* off, int64_t n_row
         for (int l = 0; l < real + 2; ++l) {
             AkChunk& c = lanes[(size_t)l];
             if (l == 0) {
-                if (c.first_w != AKF_NONE && (AK_QC(c.first_w) != 0u || AK_CCC(c.first_w) != 0u)) {
-                    c.flags |= AKF_TROUBLE;
-                    if (c.flags & AKF_FIRST_DEP) c.flags |= AKF_LEAD_TROUBLE;
+                // left halo: the kernel decodes the code point that ends right before the chunk
+                uint32_t pl = AKF_NONE;
+                int64_t cs = base0 + (w0 - 1) * 16;
+                if (c.first_w != AKF_NONE && cs > tb) {
+                    int64_t q = cs - 1;
+                    int k = 0;
+                    while (q > tb && k < 3 && (text[q] & 0xC0u) == 0x80u) { --q; ++k; }
+                    int len;
+                    pl = akf_props(T, lut.data(), ak_decode(text, q, te, len));
                 }
+                akf_resolve_first(c, pl);
             } else {
                 akf_resolve_first(c, lanes[(size_t)l - 1].last_w);
             }
@@ -133,6 +141,20 @@ int64_t hh_fast_normalize(const uint8_t* text, const int64_t* off, int64_t n_row
             nx.flags = lanes[(size_t)l + 1].flags; nx.F = lanes[(size_t)l + 1].F; nx.L1 = nx.L2 = AKF_NONE;
             uint32_t emit = 0;
             bool slow = akf_is_slow(c, pv, nx) || !akf_collapse(c, pv, nx, emit);
+            if (slow && getenv("AKF_REASONS")) {
+                int why = (c.flags & AKF_TROUBLE) ? 0 : ((c.flags & AKF_FIRST_DEP) && ((pv.flags & AKF_TROUBLE) || !(pv.flags & AKF_BOUNDARY))) ? 1
+                        : ((nx.flags & AKF_LEAD_TROUBLE) || !(nx.flags & AKF_BOUNDARY)) ? 2
+                        : ((c.flags & AKF_KEPT_BEFORE_ROW) && ((pv.flags & AKF_TROUBLE) || (!(pv.flags & AKF_ROWSTART) && pv.L2 == AKF_NONE))) ? 3 : 4;
+                static long cnts[5];
+                cnts[why]++;
+                if ((cnts[0] + cnts[1] + cnts[2] + cnts[3] + cnts[4]) % 500 == 0)
+                    fprintf(stderr, "reasons own-trouble %ld first-dep %ld next %ld prev-kept %ld lookahead %ld\n", cnts[0], cnts[1], cnts[2], cnts[3], cnts[4]);
+                if (why == 0 && cnts[0] < 12) {
+                    fprintf(stderr, "  trouble chunk: ");
+                    for (int i = 0; i < 19; ++i) fprintf(stderr, "%02x ", akf_byte(c, i));
+                    fprintf(stderr, "\n");
+                }
+            }
             while (row <= n_rows && off[row] < ss) ++row;
             if (slow) {
                 ++slow_cnt;
