@@ -60,6 +60,9 @@ struct AkBatch {
 __device__ __forceinline__ bool ak_batch_begin(AkBatch& B) {
     if (B.run_if && *B.run_if == 0) return false;
     if (B.dyn_end) {
+        // second stage of a pipeline: the first stage's output is unusable once it gave up or overflowed (the host
+        // re-runs the whole call), so do not walk over it
+        if (B.result[2] & (AK_ST_OVERFLOW | AK_ST_PATHOLOGICAL | AK_ST_NFC_SEGMENT | AK_ST_SPIN)) return false;
         B.text_end = B.text_begin + *B.dyn_end;
         if (B.mode == AKSHAR_MODE_TILES) B.n_tiles = (int)((B.text_end - B.text_begin + AK_TILE) / AK_TILE);
     }
