@@ -1,0 +1,334 @@
+// Fast lane of the BPE encoder (reference tokenizer.py:193 -> HF tokenizers `Tokenizer.encode(norm).ids`).
+//
+// Same work unit as the normalize fast lane (ak_fast.cuh): 16-byte chunks, 30 real + 2 halo chunks per warp.  A
+// lane classifies its bytes (HF pre-tokenizer class per code point), finds the words that START in its chunk and
+// encodes each one through a WORD CACHE in global memory (L2 resident): key = the word's bytes (<= 24, compared
+// exactly), value = its token ids (<= 8).  HF's own BPE keeps the same kind of cache.  The cache image is built at
+// model load from the vocabulary (every token string that is one pre-tokenizer word, encoded with the merge loop) and
+// restored at the start of every call; words met during the call are added to it.  A miss runs the exact merge loop
+// (ak_bpe_word) in place.  Row starts emit </s> <s> and the row split exactly like the walker ak_bpe_span.
+#pragma once
+#include "ak_fast.cuh"
+#include "ak_subword.cuh"
+
+#define AKW_MAXLEN 24
+#define AKW_MAXTOK 8
+#define AKW_PROBES 4
+#define AKW_READY 1ull
+#define AKW_BUSY 2ull
+
+struct AkWordCache {
+    unsigned long long* e;      // (1 << bits) entries of 8 x u64: tag, 3 x key bytes, 4 x (2 ids)
+    uint32_t bits;
+};
+
+AK_HD unsigned long long akw_ld(const unsigned long long* p) {
+#ifdef __CUDA_ARCH__
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+#else
+    return *p;
+#endif
+}
+AK_HD void akw_st(unsigned long long* p, unsigned long long v) {
+#ifdef __CUDA_ARCH__
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+#else
+    *p = v;
+#endif
+}
+
+AK_HD unsigned long long akw_hash(unsigned long long k0, unsigned long long k1, unsigned long long k2, uint32_t len) {
+    unsigned long long h = (k0 + 0x9E3779B97F4A7C15ull) * 0xBF58476D1CE4E5B9ull;
+    h ^= (k1 + len) * 0x94D049BB133111EBull;
+    h = (h << 29) | (h >> 35);
+    h ^= k2 * 0xD6E8FEB86659FD93ull;
+    h ^= h >> 31;
+    h *= 0xFF51AFD7ED558CCDull;
+    h ^= h >> 33;
+    return h;
+}
+// tag: [63:16] hash, [15:8] byte length, [7:4] token count, bit 1 busy, bit 0 ready
+AK_HD unsigned long long akw_want(unsigned long long h, uint32_t len) { return (h & ~0xFFFFull) | ((unsigned long long)len << 8) | AKW_READY; }
+
+// -> token count (ids filled) or -1; *free_slot = an empty slot seen on the probe path (or -1)
+AK_HD int akw_lookup(const AkWordCache& C, unsigned long long h, unsigned long long want, unsigned long long k0,
+                     unsigned long long k1, unsigned long long k2, int32_t* ids, long long* free_slot) {
+    const unsigned long long mask = (1ull << C.bits) - 1ull;
+    *free_slot = -1;
+    for (int j = 0; j < AKW_PROBES; ++j) {
+        const unsigned long long slot = (h + (unsigned long long)j) & mask;
+        const unsigned long long* e = C.e + slot * 8ull;
+        const unsigned long long tag = akw_ld(e);
+        if (tag == 0ull) { *free_slot = (long long)slot; return -1; }
+        if ((tag & ~0xF0ull) != want) continue;
+        if (akw_ld(e + 1) != k0 || akw_ld(e + 2) != k1 || akw_ld(e + 3) != k2) continue;
+        const int n = (int)((tag >> 4) & 15ull);
+        for (int i = 0; i < n; i += 2) {
+            const unsigned long long v = akw_ld(e + 4 + (i >> 1));
+            ids[i] = (int32_t)(uint32_t)v;
+            if (i + 1 < n) ids[i + 1] = (int32_t)(uint32_t)(v >> 32);
+        }
+        return n;
+    }
+    return -1;
+}
+
+AK_HD void akw_insert(const AkWordCache& C, long long slot, unsigned long long want, unsigned long long k0,
+                      unsigned long long k1, unsigned long long k2, const int32_t* ids, int n) {
+    unsigned long long* e = C.e + (unsigned long long)slot * 8ull;
+#ifdef __CUDA_ARCH__
+    if (atomicCAS(e, 0ull, AKW_BUSY) != 0ull) return;
+#else
+    if (*e != 0ull) return;
+    *e = AKW_BUSY;
+#endif
+    akw_st(e + 1, k0);
+    akw_st(e + 2, k1);
+    akw_st(e + 3, k2);
+    for (int i = 0; i < n; i += 2) {
+        unsigned long long v = (uint32_t)ids[i];
+        if (i + 1 < n) v |= (unsigned long long)(uint32_t)ids[i + 1] << 32;
+        akw_st(e + 4 + (i >> 1), v);
+    }
+#ifdef __CUDA_ARCH__
+    __threadfence();
+#endif
+    akw_st(e, want | ((unsigned long long)n << 4));
+}
+
+// the word's bytes [s, s + len), len <= 24, zero padded, as three little-endian u64
+AK_HD void akw_key(const uint8_t* t, int64_t s, uint32_t len, unsigned long long& k0, unsigned long long& k1,
+                   unsigned long long& k2) {
+    k0 = k1 = k2 = 0ull;
+    for (uint32_t i = 0; i < len; ++i) {
+        const unsigned long long b = t[s + i];
+        if (i < 8u) k0 |= b << (8u * i);
+        else if (i < 16u) k1 |= b << (8u * (i - 8u));
+        else k2 |= b << (8u * (i - 16u));
+    }
+}
+
+// encode the word [s, e) of pre-tokenizer class k into `sink`: cache hit, or the merge loop + insert
+AK_HD_NOINLINE void akb_word(const AkBpeDev& M, const AkTables& T, const AkWordCache& C, const uint8_t* t, int64_t s,
+                             int64_t e, uint32_t k, AkIdSink& sink, const AkPool& pool, uint32_t& status) {
+    const uint32_t len = (uint32_t)(e - s);
+    if (len <= AKW_MAXLEN && C.e) {
+        unsigned long long k0, k1, k2;
+        akw_key(t, s, len, k0, k1, k2);
+        const unsigned long long h = akw_hash(k0, k1, k2, len);
+        const unsigned long long want = akw_want(h, len);
+        int32_t ids[AKW_MAXTOK];
+        long long slot;
+        const int n = akw_lookup(C, h, want, k0, k1, k2, ids, &slot);
+        if (n >= 0) {
+            for (int i = 0; i < n; ++i) ak_id_put(sink, ids[i]);
+            return;
+        }
+        // miss: exact merge loop into a private list, then publish
+        int32_t tmp[AKW_MAXTOK + 1];
+        AkIdSink local;
+        local.buf = tmp;
+        local.cap = AKW_MAXTOK + 1;
+        local.stride = 1;
+        local.cnt = 0;
+        local.direct = false;
+        local.gout = nullptr;
+        local.gbase = 0;
+        local.gcap = 0;
+        ak_bpe_word(M, T, t, s, e, k, local, pool, status);
+        if (local.cnt <= AKW_MAXTOK) {
+            for (int i = 0; i < local.cnt; ++i) ak_id_put(sink, tmp[i]);
+            if (slot >= 0) akw_insert(C, slot, want, k0, k1, k2, tmp, local.cnt);
+            return;
+        }
+    }
+    ak_bpe_word(M, T, t, s, e, k, sink, pool, status);
+}
+
+// ------------------------------------------------------------------------------------------------
+// per-chunk classification
+// ------------------------------------------------------------------------------------------------
+struct AkBChunk {
+    uint32_t w[5];
+    uint32_t rows, own;
+    // phase A
+    uint32_t lead;        // owned lead bytes
+    uint32_t bnd;         // word boundaries: row starts, and owned leads whose class differs from the previous code point's
+    uint32_t cls;         // 2 bits per byte position: HF pre-tokenizer class of the code point led there
+    uint32_t last_cls;    // class of the last owned code point (2 = space when none)
+    uint32_t last_w;      // its props (AKF_NONE when none)
+    uint32_t first_pos;   // position of the first owned lead when it is not on a row start, else 32
+    uint32_t first_w;     // its props
+    uint32_t flags;       // AKF_TROUBLE (needs the NFC check), bit 8: outside the closed alphabet
+    uint32_t trb;         // positions of the code points that raised AKF_TROUBLE
+};
+#define AKB_ALPHABET 256u
+
+AK_HD uint32_t akb_byte(const AkBChunk& c, int i) { return (c.w[i >> 2] >> ((i & 3) * 8)) & 0xFFu; }
+
+AK_HD void akb_phase_a(const AkTables& T, const uint32_t* lut, AkBChunk& c) {
+    uint32_t lead = 0, bnd = c.rows, cls = 0, flags = 0, trb = 0;
+    uint32_t prev_w = AKF_NONE, prev_cls = 2;
+    bool have_prev = false, first_seen = false;
+    uint32_t first_pos = 32, first_w = AKF_NONE, last_w = AKF_NONE, last_cls = 2;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const bool row_here = (c.rows >> i) & 1u;
+        if (row_here) { have_prev = false; prev_cls = 2; }
+        const uint32_t b = akb_byte(c, i);
+        if (!((c.own >> i) & 1u) || (b & 0xC0u) == 0x80u) continue;
+        const uint32_t b1 = akb_byte(c, i + 1) & 0x3Fu, b2 = akb_byte(c, i + 2) & 0x3Fu, b3 = akb_byte(c, i + 3) & 0x3Fu;
+        uint32_t cp;
+        if (b < 0x80u) cp = b;
+        else if (b < 0xE0u) cp = ((b & 0x1Fu) << 6) | b1;
+        else if (b < 0xF0u) cp = ((b & 0x0Fu) << 12) | (b1 << 6) | b2;
+        else cp = ((b & 0x07u) << 18) | (b1 << 12) | (b2 << 6) | b3;
+        const uint32_t w = akf_props(T, lut, cp);
+        const uint32_t k = AK_HFCLASS(w);
+        lead |= 1u << i;
+        cls |= k << (2 * i);
+        if (!AK_ALLOW(w)) flags |= AKB_ALPHABET;
+        if (!first_seen && !row_here) {
+            first_pos = (uint32_t)i;
+            first_w = w;
+            if (AK_QC(w) == 1u) { flags |= AKF_TROUBLE; trb |= 1u << i; }
+        } else {
+            if (!have_prev ? (AK_QC(w) != 0u) : akf_trouble_after(prev_w, w)) { flags |= AKF_TROUBLE; trb |= 1u << i; }
+            if (row_here || k != prev_cls) bnd |= 1u << i;
+        }
+        first_seen = true;
+        prev_w = w;
+        prev_cls = k;
+        have_prev = true;
+        last_w = w;
+        last_cls = k;
+    }
+    c.lead = lead;
+    c.bnd = bnd;
+    c.cls = cls;
+    c.flags = flags;
+    c.trb = trb;
+    c.first_pos = first_pos;
+    c.first_w = first_w;
+    c.last_w = last_w;
+    c.last_cls = last_cls;
+}
+
+// the first owned code point against the previous chunk's last one
+AK_HD void akb_resolve_first(AkBChunk& c, uint32_t prev_last_w, uint32_t prev_last_cls) {
+    if (c.first_pos >= 32u) return;
+    if (prev_last_w == AKF_NONE ? (AK_QC(c.first_w) != 0u) : akf_trouble_after(prev_last_w, c.first_w)) {
+        c.flags |= AKF_TROUBLE;
+        c.trb |= 1u << c.first_pos;
+    }
+    const uint32_t k = (c.cls >> (2 * c.first_pos)) & 3u;
+    if (prev_last_w == AKF_NONE || k != prev_last_cls) c.bnd |= 1u << c.first_pos;
+}
+
+// end of the word that starts at chunk byte s: next boundary in this chunk, else in the next one, else a forward scan
+AK_HD int64_t akb_word_end(const AkTables& T, const uint8_t* t, int64_t cs, int s, uint32_t k, uint32_t bnd, uint32_t next_bnd,
+                           const int64_t* off, int64_t n_rows, int64_t r_lo) {
+    const uint32_t above = bnd & ~((2u << s) - 1u) & 0xFFFFu;
+    if (above) {
+#ifdef __CUDA_ARCH__
+        return cs + (__ffs(above) - 1);
+#else
+        return cs + __builtin_ctz(above);
+#endif
+    }
+    if (next_bnd & 0xFFFFu) {
+#ifdef __CUDA_ARCH__
+        return cs + 16 + (__ffs(next_bnd & 0xFFFFu) - 1);
+#else
+        return cs + 16 + __builtin_ctz(next_bnd & 0xFFFFu);
+#endif
+    }
+    // long word: walk code points up to the end of its row (no boundary before cs + 32)
+    const int64_t re = off[ak_row_lower_bound(off, r_lo, n_rows, cs + s + 1)];
+    int64_t q = cs + 32;
+    if (q > re) q = re;
+    while (q < re && (t[q] & 0xC0u) == 0x80u) ++q;
+    while (q < re) {
+        int len;
+        const uint32_t cp = ak_decode(t, q, re, len);
+        if (AK_HFCLASS(ak_props(T, cp)) != k) break;
+        q += len;
+    }
+    return q;
+}
+
+
+// Everything one lane emits for its chunk, in stream order: </s> <s> + split at the row starts it holds, the ids of
+// the words that start in it.  Mirrors ak_bpe_span.  id_splits[r] receives the lane-relative index for the rows
+// [row_first, row_last) (the caller makes them global).
+struct AkBLaneCtx {
+    const AkBpeDev* M;
+    const AkTables* T;
+    const AkWordCache* C;
+    const uint8_t* text;
+    const int64_t* off;
+    int64_t n_rows, r_lo, r_hi;
+    const AkPool* pool;
+};
+
+AK_HD_NOINLINE void akb_lane_emit(const AkBLaneCtx& X, const AkBChunk& c, uint32_t next_bnd, int64_t cs, AkIdSink& sink,
+                                  int64_t* id_splits, int64_t& row_first, int64_t& row_last, uint32_t& status) {
+    uint32_t wstart = 0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i)
+        if (((c.bnd & c.lead) >> i) & 1u)
+            if (((c.cls >> (2 * i)) & 3u) != 2u) wstart |= 1u << i;
+    uint32_t ev = (c.rows | wstart) & 0xFFFFu;
+    int64_t nr = -1;
+    row_first = row_last = 0;
+    while (ev) {
+#ifdef __CUDA_ARCH__
+        const int i = __ffs(ev) - 1;
+#else
+        const int i = __builtin_ctz(ev);
+#endif
+        ev &= ev - 1u;
+        const int64_t p = cs + i;
+        if ((c.rows >> i) & 1u) {
+            if (nr < 0) {
+                nr = ak_row_lower_bound(X.off, X.r_lo, X.r_hi, p);
+                row_first = nr;
+            }
+            while (nr <= X.n_rows && X.off[nr] == p) {
+                if (nr > 0 && X.M->eos >= 0) ak_id_put(sink, X.M->eos);
+                if (id_splits) id_splits[nr] = sink.cnt;
+                if (nr < X.n_rows && X.M->bos >= 0) ak_id_put(sink, X.M->bos);
+                ++nr;
+            }
+            row_last = nr;
+        }
+        if ((wstart >> i) & 1u) {
+            const uint32_t k = (c.cls >> (2 * i)) & 3u;
+            const int64_t e = akb_word_end(*X.T, X.text, cs, i, k, c.bnd, next_bnd, X.off, X.n_rows, X.r_lo);
+            akb_word(*X.M, *X.T, *X.C, X.text, p, e, k, sink, *X.pool, status);
+        }
+    }
+}
+
+// exact NFC check of the troubled code points of a chunk (cold): does NFC change the text?
+AK_HD_NOINLINE bool akb_chunk_changes(const AkBLaneCtx& X, const AkBChunk& c, int64_t cs, int64_t limit, uint32_t& status) {
+    uint32_t m = c.trb & 0xFFFFu;
+    bool changed = false;
+    int64_t checked_until = -1;
+    while (m) {
+#ifdef __CUDA_ARCH__
+        const int i = __ffs(m) - 1;
+#else
+        const int i = __builtin_ctz(m);
+#endif
+        m &= m - 1u;
+        const int64_t p = cs + i;
+        if (p < checked_until) continue;
+        const int64_t r = ak_row_lower_bound(X.off, X.r_lo, X.n_rows, p + 1);     // first row that starts after p
+        const int64_t rs = X.off[r - 1], re = X.off[r];
+        if (ak_segment_changes(*X.T, X.text, p, rs, re, limit, &checked_until, status)) changed = true;
+    }
+    return changed;
+}

@@ -18,6 +18,7 @@
 #include "ak_scan.cuh"
 #include "ak_subword.cuh"
 #include "ak_fast.cuh"
+#include "ak_bpe_fast.cuh"
 #include "unicode_tables.inc"
 
 #define AK_BLOCK 256
@@ -25,6 +26,7 @@
 #define AK_TILE (AK_BLOCK * AK_SPAN)
 #define AK_LOOKBACK_LIMIT 4096          // bytes a span may walk backwards in AKSHAR_MODE_TILES
 #define AK_BPE_STAGE 40                 // ids per thread staged in shared memory (>= AK_SPAN + a few <s> / </s>)
+#define AKB_STAGE 24                    // same, fast kernel (16-byte chunks)
 #define AK_ROWS_BLOCK 128               // rows per tile for the row-per-thread kernels
 #define AKF_WARPS (AK_BLOCK / 32)
 #define AKF_TILE (AKF_WARPS * AKF_WARP_BYTES)     // 3840 text bytes per CTA tile in the fast kernels
@@ -198,7 +200,8 @@ __global__ void ak_tile_rows_kernel(const int64_t* off, int64_t n_rows, int64_t 
     tile_row[k] = r;
 }
 
-__device__ __forceinline__ void akf_load_chunk(const uint8_t* text, int64_t cs, int64_t tb, int64_t te, AkChunk& c) {
+template <class CH>
+__device__ __forceinline__ void akf_load_chunk(const uint8_t* text, int64_t cs, int64_t tb, int64_t te, CH& c) {
     int64_t lo = tb - cs, hi = te - cs;
     lo = lo < 0 ? 0 : (lo > 16 ? 16 : lo);
     hi = hi < 0 ? 0 : (hi > 16 ? 16 : hi);
@@ -255,7 +258,8 @@ __device__ __forceinline__ void akf_tile_rows(const AkBatch& B, const int64_t* t
 }
 
 // chunk bytes + the 4 bytes that follow (from the next lane; the right halo reads them itself)
-__device__ __forceinline__ void akf_load_lane(const AkBatch& B, int64_t cs, AkChunk& c) {
+template <class CH>
+__device__ __forceinline__ void akf_load_lane(const AkBatch& B, int64_t cs, CH& c) {
     akf_load_chunk(B.text, cs, B.text_begin, B.text_end, c);
     uint32_t nx = __shfl_down_sync(0xFFFFFFFFu, c.w[0], 1);
     if ((threadIdx.x & 31) == 31) {
@@ -399,9 +403,11 @@ __global__ void __launch_bounds__(128) ak_nf_slow_kernel(const AkNfSlowArgs A) {
 
 // ---- K1c: exclusive prefix of the tile totals (one CTA; the array has one entry per 3840 bytes of text)
 __global__ void __launch_bounds__(1024) ak_nf_scan_kernel(const int32_t* tile_total, int64_t* tile_base, int n_tiles,
-                                                          int64_t* total_out) {
+                                                          int64_t* total_out, AkBatch B, int64_t base0) {
     __shared__ long long ws[33];
     __shared__ long long carry;
+    if (!ak_batch_begin(B)) return;
+    if (B.dyn_end) n_tiles = (int)((B.text_end - base0 + AKF_TILE) / AKF_TILE);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) carry = 0;
     __syncthreads();
@@ -628,6 +634,158 @@ __global__ void __launch_bounds__(AK_BLOCK) ak_bpe_kernel(const AkBpeArgs A) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// K4a fast: BPE through the word cache (ak_bpe_fast.cuh).  No ordered dependency between tiles: a tile appends its
+// ids to a temporary stream at an atomically reserved offset, a scan of the tile totals gives the final positions,
+// a copy kernel moves every tile's block there and makes the row splits global.
+// ------------------------------------------------------------------------------------------------
+struct AkBfArgs {
+    AkBatch B;
+    AkTables T;
+    AkBpeDev M;
+    AkWordCache C;
+    AkPool pool;
+    const int64_t* tile_row;
+    int64_t base0;
+    int32_t* temp;               // temporary id stream
+    int64_t temp_cap;
+    unsigned long long* temp_cursor;
+    int32_t* tile_total;
+    int64_t* tile_toff;          // where the tile's block starts in temp
+    int64_t* tile_base;          // exclusive prefix of tile_total (after the scan)
+    int32_t* ids;
+    int64_t id_cap;
+    int64_t* id_splits;
+    unsigned int* changed;
+};
+
+__device__ __forceinline__ int akb_n_tiles(const AkBatch& B, int64_t base0) {
+    if (!B.dyn_end) return B.n_tiles;
+    return (int)((B.text_begin + *B.dyn_end - base0 + AKF_TILE) / AKF_TILE);
+}
+
+__global__ void __launch_bounds__(AK_BLOCK) ak_bf_encode_kernel(const AkBfArgs A) {
+    __shared__ uint32_t lut[384];
+    __shared__ uint32_t rowbits[(AKF_TILE + 64) / 32 + 2];
+    __shared__ int32_t stage[AKB_STAGE * AK_BLOCK];
+    __shared__ int ws[33];
+    __shared__ long long s_toff;
+    AkBatch B = A.B;
+    if (!ak_batch_begin(B)) return;
+    B.n_tiles = akb_n_tiles(A.B, A.base0);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int i = tid; i < 384; i += AK_BLOCK)
+        lut[i] = i < 128 ? A.T.leaves[((uint32_t)A.T.page_index[0] << 8) | i] : A.T.leaves[((uint32_t)A.T.page_index[9] << 8) | (i - 128)];
+    for (int tile = blockIdx.x; tile < B.n_tiles; tile += gridDim.x) {
+        const int64_t tile_start = A.base0 + (int64_t)tile * AKF_TILE;
+        akf_tile_rows(B, A.tile_row, tile, tile_start, rowbits);
+        const int64_t r0 = A.tile_row[tile], r1 = A.tile_row[tile + 1];
+        AkBChunk c;
+        const int64_t cs = tile_start + (int64_t)warp * AKF_WARP_BYTES + (int64_t)(lane - 1) * 16;
+        akf_load_lane(B, cs, c);
+        {
+            const int bo = (int)(cs - (tile_start - 16));
+            c.rows = (rowbits[bo >> 5] >> (bo & 31)) & 0xFFFFu;
+        }
+        akb_phase_a(A.T, lut, c);
+        {
+            uint32_t pw = __shfl_up_sync(0xFFFFFFFFu, c.last_w, 1);
+            uint32_t pk = __shfl_up_sync(0xFFFFFFFFu, c.last_cls, 1);
+            if (lane == 0) {
+                pw = AKF_NONE;
+                pk = 2;
+                if (c.first_pos < 32u && cs > B.text_begin) {
+                    int64_t q = cs - 1;
+                    int k = 0;
+                    while (q > B.text_begin && k < 3 && (B.text[q] & 0xC0u) == 0x80u) { --q; ++k; }
+                    int len;
+                    pw = akf_props(A.T, lut, ak_decode(B.text, q, B.text_end, len));
+                    pk = AK_HFCLASS(pw);
+                }
+            }
+            akb_resolve_first(c, pw, pk);
+        }
+        const uint32_t next_bnd = __shfl_down_sync(0xFFFFFFFFu, c.bnd, 1);
+        const bool real = lane >= 1 && lane <= AKF_REAL;
+        const int64_t ss = cs < B.text_begin ? B.text_begin : cs;
+        const int64_t se = cs + 16 > B.text_end + 1 ? B.text_end + 1 : cs + 16;
+        const bool active = real && ss < se;
+        AkBLaneCtx X;
+        X.M = &A.M;
+        X.T = &A.T;
+        X.C = &A.C;
+        X.text = B.text;
+        X.off = B.off;
+        X.n_rows = B.n_rows;
+        X.r_lo = r0 > 0 ? r0 - 1 : 0;
+        X.r_hi = r1 > B.n_rows ? B.n_rows : r1;
+        X.pool = &A.pool;
+        AkIdSink sink;
+        sink.buf = stage + tid;
+        sink.cap = AKB_STAGE;
+        sink.stride = AK_BLOCK;
+        sink.cnt = 0;
+        sink.direct = false;
+        sink.gout = A.temp;
+        sink.gbase = 0;
+        sink.gcap = A.temp_cap;
+        uint32_t st = 0;
+        int64_t row_first = 0, row_last = 0;
+        if (active) {
+            if (c.flags & AKB_ALPHABET) st |= AK_ST_ALPHABET;
+            if ((c.flags & AKF_TROUBLE) && akb_chunk_changes(X, c, cs, AK_LOOKBACK_LIMIT, st)) atomicOr(A.changed, 1u);
+            akb_lane_emit(X, c, next_bnd, cs, sink, A.id_splits, row_first, row_last, st);
+        }
+        const int cnt = sink.cnt;
+        int total;
+        const int pre = ak_block_exscan<AK_BLOCK>(cnt, ws, total);
+        if (tid == 0) {
+            const long long toff = (long long)atomicAdd(A.temp_cursor, (unsigned long long)total);
+            s_toff = toff;
+            A.tile_total[tile] = total;
+            A.tile_toff[tile] = toff;
+            if (toff + total > A.temp_cap) st |= AK_ST_OVERFLOW;
+        }
+        __syncthreads();
+        const int64_t tbase = s_toff + pre;
+        if (active) {
+            for (int64_t r = row_first; r < row_last; ++r) A.id_splits[r] += pre;      // lane-relative -> tile-relative
+            if (cnt <= AKB_STAGE) {
+                for (int i = 0; i < cnt; ++i)
+                    if (tbase + i < A.temp_cap) A.temp[tbase + i] = stage[i * AK_BLOCK + tid];
+            } else {
+                AkIdSink s2 = sink;
+                s2.cnt = 0;
+                s2.direct = true;
+                s2.gbase = tbase;
+                uint32_t st2 = 0;
+                int64_t a, b;
+                akb_lane_emit(X, c, next_bnd, cs, s2, nullptr, a, b, st2);
+            }
+        }
+        ak_raise(B.result, st);
+    }
+}
+
+// copy every tile's block to its final place and make the row splits global
+__global__ void __launch_bounds__(AK_BLOCK) ak_bf_copy_kernel(const AkBfArgs A) {
+    AkBatch B = A.B;
+    if (!ak_batch_begin(B)) return;
+    B.n_tiles = akb_n_tiles(A.B, A.base0);
+    const int tid = threadIdx.x;
+    for (int tile = blockIdx.x; tile < B.n_tiles; tile += gridDim.x) {
+        const int total = A.tile_total[tile];
+        const int64_t toff = A.tile_toff[tile], base = A.tile_base[tile];
+        const bool ok = toff + total <= A.temp_cap;
+        if (base + total > A.id_cap && tid == 0 && total > 0) ak_raise(B.result, AK_ST_OVERFLOW);
+        if (ok)
+            for (int i = tid; i < total; i += AK_BLOCK)
+                if (base + i < A.id_cap) A.ids[base + i] = A.temp[toff + i];
+        const int64_t r0 = A.tile_row[tile], r1 = A.tile_row[tile + 1];
+        for (int64_t r = r0 + tid; r < r1 && r <= B.n_rows; r += AK_BLOCK) A.id_splits[r] += base;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // K4b Unigram encode  (reference tokenizer.py:191): one row per thread, Viterbi ring in registers / local memory,
 // final back-pointers in a global scratch (4 B per code point), ids written backwards from the row's end.
 // ------------------------------------------------------------------------------------------------
@@ -749,6 +907,10 @@ struct akshar_ctx {
     AkUniHost uni_h;
     AkUniDev uni_d{};
     std::vector<void*> bpe_allocs, uni_allocs;
+    AkWordCache wc{};              // working copy, restored from wc_image at the start of every BPE call
+    unsigned long long* wc_image = nullptr;
+    size_t wc_bytes = 0;
+    int occ_bf = 0;
     int occ_norm = 0, occ_seg = 0, occ_bpe = 0, occ_uni = 0, occ_sig = 0, occ_nf_classify = 0, occ_nf_write = 0;
 };
 
@@ -825,6 +987,7 @@ int akshar_ctx_create(int device, akshar_ctx** out) {
     AK_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_norm, ak_normalize_kernel, AK_BLOCK, 0));
     AK_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_nf_classify, ak_nf_classify_kernel, AK_BLOCK, 0));
     AK_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_nf_write, ak_nf_write_kernel, AK_BLOCK, 0));
+    AK_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_bf, ak_bf_encode_kernel, AK_BLOCK, 0));
     AK_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_seg, ak_segment_kernel, AK_BLOCK, 0));
     AK_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_bpe, ak_bpe_kernel, AK_BLOCK, 0));
     AK_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_uni, ak_unigram_kernel, AK_ROWS_BLOCK, 0));
@@ -866,7 +1029,8 @@ static inline size_t ak_pool_ints(int64_t n_bytes) {
     return (size_t)p;
 }
 struct AkWsLayout {
-    size_t control, state, tile_row, nfc_text, nfc_off, pool, scratch, total;
+    size_t control, state, tile_row, nfc_text, nfc_off, pool, bf_tiles, bf_temp, scratch, total;
+    int64_t bf_temp_cap;
     int64_t nfc_cap;
 };
 static AkWsLayout ak_ws_layout(int64_t n_bytes, int64_t n_rows) {
@@ -882,7 +1046,10 @@ static AkWsLayout ak_ws_layout(int64_t n_bytes, int64_t n_rows) {
     L.nfc_text = at;
     L.nfc_off = L.nfc_text + ak_align((size_t)L.nfc_cap);
     L.pool = L.nfc_off + ak_align(8 * (size_t)(n_rows + 1));
-    size_t bpe = (L.pool + ak_align(4 * ak_pool_ints(n_bytes))) - at;
+    L.bf_tiles = L.pool + ak_align(4 * ak_pool_ints(n_bytes));
+    L.bf_temp = L.bf_tiles + ak_align(tiles * 4) + ak_align(tiles * 8) + ak_align((tiles + 1) * 8);
+    L.bf_temp_cap = n_bytes / 2 + 2 * n_rows + 1024;
+    size_t bpe = (L.bf_temp + ak_align(4 * (size_t)L.bf_temp_cap)) - at;
     // fast normalize: per-lane info words, tile totals / bases, slow work list
     size_t nf = ak_align(tiles * AK_BLOCK * 4) + ak_align(tiles * 4) + ak_align((tiles + 1) * 8) +
                 ak_align((tiles * AK_BLOCK / 16 + 1024) * sizeof(AkSlowEntry));
@@ -1011,7 +1178,7 @@ static int ak_run_normalize(akshar_ctx* ctx, AkCall& C, const AkBatch& B, uint32
         const int slow_grid = ctx->sm_count * 4;
         ak_nf_slow_kernel<<<slow_grid, 128, 0, C.stream>>>(S);
         if ((rc = ak_after_launch(ctx, "normalize-slow-count"))) return rc;
-        ak_nf_scan_kernel<<<1, 1024, 0, C.stream>>>(W.tile_total, W.tile_base, F.B.n_tiles, B.totals);
+        ak_nf_scan_kernel<<<1, 1024, 0, C.stream>>>(W.tile_total, W.tile_base, F.B.n_tiles, B.totals, B, F.base0);
         if ((rc = ak_after_launch(ctx, "normalize-scan"))) return rc;
         ak_nf_write_kernel<<<ak_grid(ctx, ctx->occ_nf_write, F.B.n_tiles), AK_BLOCK, 0, C.stream>>>(F, W);
         if ((rc = ak_after_launch(ctx, "normalize-write"))) return rc;
@@ -1126,6 +1293,80 @@ int akshar_load_bpe_json(akshar_ctx* ctx, const char* json, size_t len) {
     d.mbits = h.mbits;
     d.bos = h.bos;
     d.eos = h.eos;
+    // word cache image: every vocabulary string that is exactly one pre-tokenizer word, encoded by the merge loop
+    {
+        AkBpeDev hm{};
+        hm.cp_direct = h.cp_direct.data();
+        hm.cp_keys = h.cp_keys.data();
+        hm.cp_ids = h.cp_ids.data();
+        hm.n_cp = (int)h.cp_keys.size();
+        hm.mkeys = h.mkeys.data();
+        hm.mvals = h.mvals.data();
+        hm.mbits = h.mbits;
+        hm.bos = h.bos;
+        hm.eos = h.eos;
+        AkTables ht{};
+        ht.page_index = ak_tbl_page_index;
+        ht.leaves = ak_tbl_leaves;
+        const uint32_t bits = 18;
+        std::vector<unsigned long long> img((size_t)8 << bits, 0ull);
+        AkWordCache hc;
+        hc.e = img.data();
+        hc.bits = bits;
+        std::vector<int32_t> poolbuf(4096);
+        unsigned long long used = 0;
+        AkPool hp;
+        hp.base = poolbuf.data();
+        hp.used = &used;
+        hp.cap = poolbuf.size();
+        for (size_t id = 0; id < h.id_to_token.size(); ++id) {
+            const std::string& tok = h.id_to_token[id];
+            if (tok.empty() || tok.size() > AKW_MAXLEN || h.is_special[id]) continue;
+            const uint8_t* tb = (const uint8_t*)tok.data();
+            const int64_t n = (int64_t)tok.size();
+            uint32_t k = 3;
+            bool one_word = true;
+            for (int64_t q = 0; q < n;) {
+                int len;
+                const uint32_t cp = ak_decode(tb, q, n, len);
+                const uint32_t kk = AK_HFCLASS(ak_props(ht, cp));
+                if (kk == 2u || (k != 3u && kk != k)) { one_word = false; break; }
+                k = kk;
+                q += len;
+            }
+            if (!one_word || k == 3u) continue;
+            used = 0;
+            uint32_t st = 0;
+            AkIdSink sink;
+            int32_t out_ids[AKW_MAXTOK + 1];
+            sink.buf = out_ids;
+            sink.cap = AKW_MAXTOK + 1;
+            sink.stride = 1;
+            sink.cnt = 0;
+            sink.direct = false;
+            sink.gout = nullptr;
+            sink.gbase = 0;
+            sink.gcap = 0;
+            ak_bpe_word(hm, ht, tb, 0, n, k, sink, hp, st);
+            if (st || sink.cnt > AKW_MAXTOK) continue;
+            unsigned long long k0, k1, k2;
+            akw_key(tb, 0, (uint32_t)n, k0, k1, k2);
+            const unsigned long long hh = akw_hash(k0, k1, k2, (uint32_t)n);
+            const unsigned long long want = akw_want(hh, (uint32_t)n);
+            int32_t got[AKW_MAXTOK];
+            long long slot;
+            if (akw_lookup(hc, hh, want, k0, k1, k2, got, &slot) < 0 && slot >= 0) akw_insert(hc, slot, want, k0, k1, k2, out_ids, sink.cnt);
+        }
+        const unsigned long long* dimg = nullptr;
+        if ((rc = ak_upload<unsigned long long>(ctx, ctx->bpe_allocs, img.data(), img.size(), &dimg))) return rc;
+        void* work = nullptr;
+        AK_CUDA(ctx, cudaMalloc(&work, img.size() * 8));
+        ctx->bpe_allocs.push_back(work);
+        ctx->wc_image = (unsigned long long*)dimg;
+        ctx->wc.e = (unsigned long long*)work;
+        ctx->wc.bits = bits;
+        ctx->wc_bytes = img.size() * 8;
+    }
     ctx->bpe_d = d;
     ctx->bpe_h = std::move(h);
     ctx->has_bpe = true;
@@ -1213,8 +1454,45 @@ static int ak_run_bpe(akshar_ctx* ctx, AkCall& C, const AkBatch& B, int64_t max_
     A.id_splits = d_id_splits;
     A.changed = changed;
     const int bpe_tiles = B.dyn_end ? (int)tiles : B.n_tiles;
-    ak_bpe_kernel<<<ak_grid(ctx, ctx->occ_bpe, bpe_tiles), AK_BLOCK, 0, C.stream>>>(A);
-    if ((rc = ak_after_launch(ctx, "bpe"))) return rc;
+    if (B.mode == AKSHAR_MODE_TILES) {
+        // fast kernels: word cache, no ordered tile dependency
+        AkBfArgs F;
+        F.B = B;
+        F.T = ctx->T;
+        F.M = ctx->bpe_d;
+        F.C = ctx->wc;
+        F.pool = pool;
+        F.base0 = B.text_begin - (int64_t)(((uintptr_t)B.text + (uintptr_t)B.text_begin) & 15u);
+        const int nt_ub = B.dyn_end ? (int)((max_bytes - F.base0 + AKF_TILE) / AKF_TILE) : (int)((B.text_end - F.base0 + AKF_TILE) / AKF_TILE);
+        F.B.n_tiles = nt_ub;
+        int64_t* tile_row = (int64_t*)(C.ws + C.L.tile_row);
+        F.tile_row = tile_row;
+        char* wp = C.ws + C.L.bf_tiles;
+        F.tile_total = (int32_t*)wp;                 wp += ak_align(tiles * 4);
+        F.tile_toff = (int64_t*)wp;                  wp += ak_align(tiles * 8);
+        F.tile_base = (int64_t*)wp;
+        F.temp = (int32_t*)(C.ws + C.L.bf_temp);
+        F.temp_cap = C.L.bf_temp_cap;
+        F.temp_cursor = (unsigned long long*)(C.ws + 80);
+        F.ids = d_ids;
+        F.id_cap = id_capacity;
+        F.id_splits = d_id_splits;
+        F.changed = changed;
+        AK_CUDA(ctx, cudaMemcpyAsync(ctx->wc.e, ctx->wc_image, ctx->wc_bytes, cudaMemcpyDeviceToDevice, C.stream));
+        const int entries = nt_ub + 1;
+        ak_tile_rows_kernel<<<(entries + 255) / 256, 256, 0, C.stream>>>(B.off, B.n_rows, F.base0, entries, tile_row, B.run_if,
+                                                                        nullptr, B.text_begin);
+        if ((rc = ak_after_launch(ctx, "bpe-tile-rows"))) return rc;
+        ak_bf_encode_kernel<<<ak_grid(ctx, ctx->occ_bf, nt_ub), AK_BLOCK, 0, C.stream>>>(F);
+        if ((rc = ak_after_launch(ctx, "bpe-fast"))) return rc;
+        ak_nf_scan_kernel<<<1, 1024, 0, C.stream>>>(F.tile_total, F.tile_base, nt_ub, B.totals, B, F.base0);
+        if ((rc = ak_after_launch(ctx, "bpe-scan"))) return rc;
+        ak_bf_copy_kernel<<<ak_grid(ctx, 8, nt_ub), AK_BLOCK, 0, C.stream>>>(F);
+        if ((rc = ak_after_launch(ctx, "bpe-copy"))) return rc;
+    } else {
+        ak_bpe_kernel<<<ak_grid(ctx, ctx->occ_bpe, bpe_tiles), AK_BLOCK, 0, C.stream>>>(A);
+        if ((rc = ak_after_launch(ctx, "bpe"))) return rc;
+    }
     // passes 2 + 3 (device-side conditional: both exit at once while `changed` is clear): NFC into the workspace,
     // then encode that copy over the same outputs.  HF's NFKC == NFC on the closed alphabet (the exotic spaces it
     // folds to U+0020 are all \\s and never reach a word).

@@ -9,6 +9,7 @@
 #include <math.h>
 #include "../../akshar_b200/csrc/ak_subword.cuh"
 #include "../../akshar_b200/csrc/ak_fast.cuh"
+#include "../../akshar_b200/csrc/ak_bpe_fast.cuh"
 #include "../../akshar_b200/csrc/ak_models.h"
 #include "../../akshar_b200/csrc/unicode_tables.inc"
 
@@ -241,6 +242,88 @@ int64_t hh_bpe(const uint8_t* text, const int64_t* off, int64_t n_rows, const in
             if (s2.cnt != sink.cnt) st |= 0x80000000u;
         }
         base += sink.cnt;
+    }
+    *changed_out = changed ? 1 : 0;
+    *status = st;
+    return base;
+}
+
+// The fast BPE kernel's structure on the CPU: chunks, halo lanes, word cache (starting empty, `cache_bits` slots so
+// that small tables exercise probing / eviction-free misses), lane emit with relative splits.
+int64_t hh_bpe_fast(const uint8_t* text, const int64_t* off, int64_t n_rows, int real, int cache_bits, int stage_cap,
+                    int32_t* ids, int64_t id_cap, int64_t* splits, int* changed_out, uint32_t* status) {
+    AkTables T = host_tables();
+    std::vector<uint32_t> lut(384);
+    for (int i = 0; i < 384; ++i) lut[(size_t)i] = i < 128 ? ak_props(T, (uint32_t)i) : ak_props(T, 0x900u + (uint32_t)(i - 128));
+    AkBpeDev M;
+    M.cp_direct = g_bpe.cp_direct.data(); M.cp_keys = g_bpe.cp_keys.data(); M.cp_ids = g_bpe.cp_ids.data();
+    M.n_cp = (int)g_bpe.cp_keys.size(); M.mkeys = g_bpe.mkeys.data(); M.mvals = g_bpe.mvals.data(); M.mbits = g_bpe.mbits;
+    M.bos = g_bpe.bos; M.eos = g_bpe.eos;
+    std::vector<unsigned long long> img((size_t)8 << cache_bits, 0ull);
+    AkWordCache C; C.e = img.data(); C.bits = (uint32_t)cache_bits;
+    std::vector<int32_t> poolbuf(1 << 20);
+    unsigned long long used = 0;
+    AkPool pool; pool.base = poolbuf.data(); pool.used = &used; pool.cap = poolbuf.size();
+    const int64_t tb = off[0], te = off[n_rows], base0 = tb;
+    std::vector<uint8_t> rowstart((size_t)(te - base0) + 64, 0);
+    for (int64_t r = 0; r <= n_rows; ++r) rowstart[(size_t)(off[r] - base0)] = 1;
+    const int64_t n_chunks = (te - base0 + 1 + 15) / 16;
+    AkBLaneCtx X; X.M = &M; X.T = &T; X.C = &C; X.text = text; X.off = off; X.n_rows = n_rows; X.r_lo = 0; X.r_hi = n_rows; X.pool = &pool;
+    uint32_t st = 0;
+    bool changed = false;
+    int64_t base = 0;
+    std::vector<AkBChunk> lanes((size_t)real + 2);
+    std::vector<int32_t> stage((size_t)stage_cap + 1);
+    for (int64_t w0 = 0; w0 < n_chunks; w0 += real) {
+        for (int l = 0; l < real + 2; ++l) {
+            AkBChunk& c = lanes[(size_t)l];
+            int64_t cs = base0 + (w0 - 1 + l) * 16;
+            AkChunk tmp;
+            hh_make_chunk(text, cs, tb, te, rowstart, base0, tmp);
+            for (int k = 0; k < 5; ++k) c.w[k] = tmp.w[k];
+            c.rows = tmp.rows; c.own = tmp.own;
+            akb_phase_a(T, lut.data(), c);
+        }
+        for (int l = 0; l < real + 2; ++l) {
+            AkBChunk& c = lanes[(size_t)l];
+            uint32_t pw = AKF_NONE, pk = 2;
+            if (l == 0) {
+                int64_t cs = base0 + (w0 - 1) * 16;
+                if (c.first_pos < 32u && cs > tb) {
+                    int64_t q = cs - 1;
+                    int k = 0;
+                    while (q > tb && k < 3 && (text[q] & 0xC0u) == 0x80u) { --q; ++k; }
+                    int len;
+                    pw = akf_props(T, lut.data(), ak_decode(text, q, te, len));
+                    pk = AK_HFCLASS(pw);
+                }
+            } else {
+                pw = lanes[(size_t)l - 1].last_w; pk = lanes[(size_t)l - 1].last_cls;
+            }
+            akb_resolve_first(c, pw, pk);
+        }
+        for (int l = 1; l <= real; ++l) {
+            AkBChunk& c = lanes[(size_t)l];
+            int64_t cs = base0 + (w0 - 1 + l) * 16;
+            int64_t ss = cs < tb ? tb : cs, se = cs + 16 > te + 1 ? te + 1 : cs + 16;
+            if (ss >= se) continue;
+            if (c.flags & AKB_ALPHABET) st |= AK_ST_ALPHABET;
+            if ((c.flags & AKF_TROUBLE) && akb_chunk_changes(X, c, cs, 0, st)) changed = true;
+            AkIdSink sink; sink.buf = stage.data(); sink.cap = stage_cap; sink.stride = 1; sink.cnt = 0; sink.direct = false;
+            sink.gout = ids; sink.gbase = 0; sink.gcap = id_cap;
+            int64_t rf, rl;
+            akb_lane_emit(X, c, lanes[(size_t)l + 1].bnd, cs, sink, splits, rf, rl, st);
+            for (int64_t r = rf; r < rl; ++r) splits[r] += base;
+            if (sink.cnt <= stage_cap) {
+                for (int k = 0; k < sink.cnt; ++k) if (base + k < id_cap) ids[base + k] = stage[(size_t)k];
+            } else {
+                AkIdSink s2 = sink; s2.cnt = 0; s2.direct = true; s2.gbase = base;
+                int64_t a, b;
+                akb_lane_emit(X, c, lanes[(size_t)l + 1].bnd, cs, s2, nullptr, a, b, st);
+                if (s2.cnt != sink.cnt) st |= 0x80000000u;
+            }
+            base += sink.cnt;
+        }
     }
     *changed_out = changed ? 1 : 0;
     *status = st;

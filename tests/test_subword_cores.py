@@ -99,3 +99,31 @@ def test_loader_rejects_unsupported(models_dir):
     open(p, 'wb').write(b'\x00\x01garbage')
     with pytest.raises(ValueError):
         W.load_spm(p)
+
+
+@pytest.mark.parametrize('real,cache_bits,stage_cap', [(30, 14, 24), (1, 4, 2), (3, 8, 24), (30, 2, 24)])
+def test_bpe_fast_structure(golden, models_dir, real, cache_bits, stage_cap):
+    """chunked classification + word cache (tiny tables force probing and misses) == the reference ids"""
+    W.load_bpe(os.path.join(models_dir, 'bpe24k.json'))
+    rows = _rows(golden)
+    lines = [r['norm'] for r in rows] + ['', '', 'ab' * 200 + ' ' + 'कख' * 90, '']
+    m = O.BpeModel(os.path.join(models_dir, 'bpe24k.json'))
+    exp = [r['ids_bpe24k'] for r in rows] + [[2, 3], [2, 3], O.bpe_encode(m, lines[-2]), [2, 3]]
+    data, off = sc.pack(lines)
+    ids, splits, st, _ = W.bpe_fast(data, off, real=real, cache_bits=cache_bits, stage_cap=stage_cap)
+    assert st == 0
+    exp_splits = np.zeros(len(lines) + 1, dtype=np.int64)
+    np.cumsum([len(e) for e in exp], out=exp_splits[1:])
+    assert np.array_equal(splits, exp_splits)
+    assert ids.tolist() == [i for e in exp for i in e]
+
+
+def test_bpe_fast_renormalizes(models_dir):
+    m = O.BpeModel(os.path.join(models_dir, 'bpe24k.json'))
+    W.load_bpe(os.path.join(models_dir, 'bpe24k.json'))
+    lines = ['\u0928\u093c \u0915\u094d\u0937', 'abc', '\u0930\u093c\u093e', 'x']
+    data, off = sc.pack(lines)
+    ids, splits, st, attempt = W.bpe_fast(data, off)
+    assert attempt == 1 and st == 0
+    exp = [O.bpe_encode(m, s) for s in lines]
+    assert ids.tolist() == [i for e in exp for i in e]

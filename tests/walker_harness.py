@@ -16,7 +16,7 @@ def build():
     csrc = os.path.join(ROOT, 'akshar_b200', 'csrc')
     models = os.path.join(csrc, 'ak_models.cpp')
     deps = [src, models] + [os.path.join(csrc, f) for f in
-                            ('ak_unicode.cuh', 'ak_text_core.cuh', 'ak_subword.cuh', 'ak_fast.cuh', 'ak_models.h', 'unicode_tables.inc')]
+                            ('ak_unicode.cuh', 'ak_text_core.cuh', 'ak_subword.cuh', 'ak_fast.cuh', 'ak_bpe_fast.cuh', 'ak_models.h', 'unicode_tables.inc')]
     if not os.path.exists(SO) or any(os.path.getmtime(d) > os.path.getmtime(SO) for d in deps):
         subprocess.check_call(['g++', '-O2', '-std=c++17', '-shared', '-fPIC', '-o', SO, src, models])
 
@@ -30,6 +30,7 @@ def lib():
         _lib.hh_signature.restype = ctypes.c_int64
         _lib.hh_fast_normalize.restype = ctypes.c_int64
         _lib.hh_bpe.restype = ctypes.c_int64
+        _lib.hh_bpe_fast.restype = ctypes.c_int64
         _lib.hh_unigram.restype = ctypes.c_int64
         _lib.hh_error.restype = ctypes.c_char_p
     return _lib
@@ -145,3 +146,23 @@ def fast_normalize(data, off, real=30):
     n = lib().hh_fast_normalize(_p(data), _p(off), ctypes.c_int64(off.size - 1), ctypes.c_int(real), _p(out), _p(out_off),
                                 ctypes.byref(st), ctypes.byref(ns))
     return out[:n], out_off, st.value, ns.value
+
+
+def bpe_fast(data, off, real=30, cache_bits=12, stage_cap=24):
+    """the fast BPE kernel's chunk / word-cache structure; same three-pass protocol as bpe()"""
+    data = np.ascontiguousarray(data, dtype=np.uint8)
+    off = np.ascontiguousarray(off, dtype=np.int64)
+    for attempt in range(2):
+        cap = int(data.size) + 2 * off.size + 16
+        ids = np.zeros(cap, dtype=np.int32)
+        splits = np.full(off.size, -1, dtype=np.int64)
+        ch = ctypes.c_int(0)
+        st = ctypes.c_uint32(0)
+        n = lib().hh_bpe_fast(_p(data), _p(off), ctypes.c_int64(off.size - 1), ctypes.c_int(real), ctypes.c_int(cache_bits),
+                              ctypes.c_int(stage_cap), _p(ids), ctypes.c_int64(cap), _p(splits), ctypes.byref(ch), ctypes.byref(st))
+        if not ch.value:
+            return ids[:n], splits, st.value, attempt
+        assert attempt == 0
+        data, off, _ = normalize(data, off, flags=0, span=32)
+        data = np.ascontiguousarray(data)
+    raise AssertionError
