@@ -11,14 +11,16 @@
 #include "ak_fast.cuh"
 #include "ak_subword.cuh"
 
-#define AKW_MAXLEN 24
-#define AKW_MAXTOK 8
+#define AKW_MAXLEN 56          // key bytes per entry (7 x u64)
+#define AKW_KW 7
+#define AKW_MAXTOK 16          // ids per entry
+#define AKW_ENTRY 16           // u64 per entry: tag, 7 key words, 8 x (2 ids)  = 128 bytes
 #define AKW_PROBES 4
 #define AKW_READY 1ull
 #define AKW_BUSY 2ull
 
 struct AkWordCache {
-    unsigned long long* e;      // (1 << bits) entries of 8 x u64: tag, 3 x key bytes, 4 x (2 ids)
+    unsigned long long* e;      // (1 << bits) entries of AKW_ENTRY x u64
     uint32_t bits;
 };
 
@@ -39,91 +41,130 @@ AK_HD void akw_st(unsigned long long* p, unsigned long long v) {
 #endif
 }
 
-AK_HD unsigned long long akw_hash(unsigned long long k0, unsigned long long k1, unsigned long long k2, uint32_t len) {
-    unsigned long long h = (k0 + 0x9E3779B97F4A7C15ull) * 0xBF58476D1CE4E5B9ull;
-    h ^= (k1 + len) * 0x94D049BB133111EBull;
-    h = (h << 29) | (h >> 35);
-    h ^= k2 * 0xD6E8FEB86659FD93ull;
+struct AkWordKey {
+    unsigned long long k[AKW_KW];     // the word's bytes, zero padded, little endian
+    uint32_t len, nw;                 // bytes, key words in use
+};
+
+AK_HD unsigned long long akw_hash(const AkWordKey& K) {
+    unsigned long long h = 0x9E3779B97F4A7C15ull + K.len;
+#pragma unroll
+    for (int j = 0; j < AKW_KW; ++j) {
+        if ((uint32_t)j < K.nw) {
+            h = (h ^ K.k[j]) * 0xBF58476D1CE4E5B9ull;
+            h = (h << 27) | (h >> 37);
+        }
+    }
     h ^= h >> 31;
     h *= 0xFF51AFD7ED558CCDull;
     h ^= h >> 33;
     return h;
 }
-// tag: [63:16] hash, [15:8] byte length, [7:4] token count, bit 1 busy, bit 0 ready
+// tag: [63:16] hash, [15:8] byte length, [7:3] token count, bit 1 busy, bit 0 ready
 AK_HD unsigned long long akw_want(unsigned long long h, uint32_t len) { return (h & ~0xFFFFull) | ((unsigned long long)len << 8) | AKW_READY; }
+#define AKW_NTOK_MASK 0xF8ull
 
 // -> token count (ids filled) or -1; *free_slot = an empty slot seen on the probe path (or -1)
-AK_HD int akw_lookup(const AkWordCache& C, unsigned long long h, unsigned long long want, unsigned long long k0,
-                     unsigned long long k1, unsigned long long k2, int32_t* ids, long long* free_slot) {
+AK_HD int akw_lookup(const AkWordCache& C, unsigned long long h, unsigned long long want, const AkWordKey& K, int32_t* ids,
+                     long long* free_slot) {
     const unsigned long long mask = (1ull << C.bits) - 1ull;
     *free_slot = -1;
-    for (int j = 0; j < AKW_PROBES; ++j) {
-        const unsigned long long slot = (h + (unsigned long long)j) & mask;
-        const unsigned long long* e = C.e + slot * 8ull;
+    for (int p = 0; p < AKW_PROBES; ++p) {
+        const unsigned long long slot = (h + (unsigned long long)p) & mask;
+        const unsigned long long* e = C.e + slot * AKW_ENTRY;
         const unsigned long long tag = akw_ld(e);
         if (tag == 0ull) { *free_slot = (long long)slot; return -1; }
-        if ((tag & ~0xF0ull) != want) continue;
-        if (akw_ld(e + 1) != k0 || akw_ld(e + 2) != k1 || akw_ld(e + 3) != k2) continue;
-        const int n = (int)((tag >> 4) & 15ull);
-        for (int i = 0; i < n; i += 2) {
-            const unsigned long long v = akw_ld(e + 4 + (i >> 1));
-            ids[i] = (int32_t)(uint32_t)v;
-            if (i + 1 < n) ids[i + 1] = (int32_t)(uint32_t)(v >> 32);
+        if ((tag & ~AKW_NTOK_MASK) != want) continue;
+        bool same = true;
+#pragma unroll
+        for (int j = 0; j < AKW_KW; ++j)
+            if ((uint32_t)j < K.nw && akw_ld(e + 1 + j) != K.k[j]) same = false;
+        if (!same) continue;
+        const int n = (int)((tag & AKW_NTOK_MASK) >> 3);
+#pragma unroll
+        for (int i = 0; i < AKW_MAXTOK; i += 2) {
+            if (i < n) {
+                const unsigned long long v = akw_ld(e + 8 + (i >> 1));
+                ids[i] = (int32_t)(uint32_t)v;
+                ids[i + 1] = (int32_t)(uint32_t)(v >> 32);
+            }
         }
         return n;
     }
     return -1;
 }
 
-AK_HD void akw_insert(const AkWordCache& C, long long slot, unsigned long long want, unsigned long long k0,
-                      unsigned long long k1, unsigned long long k2, const int32_t* ids, int n) {
-    unsigned long long* e = C.e + (unsigned long long)slot * 8ull;
+AK_HD void akw_insert(const AkWordCache& C, long long slot, unsigned long long want, const AkWordKey& K, const int32_t* ids,
+                      int n) {
+    unsigned long long* e = C.e + (unsigned long long)slot * AKW_ENTRY;
 #ifdef __CUDA_ARCH__
     if (atomicCAS(e, 0ull, AKW_BUSY) != 0ull) return;
 #else
     if (*e != 0ull) return;
     *e = AKW_BUSY;
 #endif
-    akw_st(e + 1, k0);
-    akw_st(e + 2, k1);
-    akw_st(e + 3, k2);
+#pragma unroll
+    for (int j = 0; j < AKW_KW; ++j)
+        if ((uint32_t)j < K.nw) akw_st(e + 1 + j, K.k[j]);
     for (int i = 0; i < n; i += 2) {
         unsigned long long v = (uint32_t)ids[i];
         if (i + 1 < n) v |= (unsigned long long)(uint32_t)ids[i + 1] << 32;
-        akw_st(e + 4 + (i >> 1), v);
+        akw_st(e + 8 + (i >> 1), v);
     }
 #ifdef __CUDA_ARCH__
     __threadfence();
 #endif
-    akw_st(e, want | ((unsigned long long)n << 4));
+    akw_st(e, want | ((unsigned long long)n << 3));
 }
 
-// the word's bytes [s, s + len), len <= 24, zero padded, as three little-endian u64
-AK_HD void akw_key(const uint8_t* t, int64_t s, uint32_t len, unsigned long long& k0, unsigned long long& k1,
-                   unsigned long long& k2) {
-    k0 = k1 = k2 = 0ull;
-    for (uint32_t i = 0; i < len; ++i) {
-        const unsigned long long b = t[s + i];
-        if (i < 8u) k0 |= b << (8u * i);
-        else if (i < 16u) k1 |= b << (8u * (i - 8u));
-        else k2 |= b << (8u * (i - 16u));
+// the word's bytes [s, s + len), len <= AKW_MAXLEN, with 8-byte aligned loads (the allocation of `t` must reach
+// the next 8-byte boundary after its last byte, which holds for every CUDA allocation)
+AK_HD void akw_key(const uint8_t* t, int64_t s, uint32_t len, AkWordKey& K) {
+    K.len = len;
+    K.nw = (len + 7u) >> 3;
+#ifdef __CUDA_ARCH__
+    const uintptr_t a = (uintptr_t)(t + s);
+    const unsigned long long* base = (const unsigned long long*)(a & ~(uintptr_t)7);
+    const uint32_t sh = (uint32_t)(a & 7u) * 8u;
+    const uint32_t span = (uint32_t)(a & 7u) + len;           // bytes from base to the word end
+    unsigned long long lo = __ldg(base);
+#pragma unroll
+    for (int j = 0; j < AKW_KW; ++j) {
+        if ((uint32_t)j < K.nw) {
+            unsigned long long hi = 0ull;
+            if (span > 8u * (uint32_t)(j + 1)) hi = __ldg(base + j + 1);
+            unsigned long long v = sh ? ((lo >> sh) | (hi << (64u - sh))) : lo;
+            const uint32_t nb = len - 8u * (uint32_t)j;
+            if (nb < 8u) v &= (1ull << (8u * nb)) - 1ull;
+            K.k[j] = v;
+            lo = hi;
+        } else {
+            K.k[j] = 0ull;
+        }
     }
+#else
+#pragma unroll
+    for (int j = 0; j < AKW_KW; ++j) K.k[j] = 0ull;
+    for (uint32_t i = 0; i < len; ++i) K.k[i >> 3] |= (unsigned long long)t[s + i] << (8u * (i & 7u));
+#endif
 }
 
 // encode the word [s, e) of pre-tokenizer class k into `sink`: cache hit, or the merge loop + insert
 AK_HD_NOINLINE void akb_word(const AkBpeDev& M, const AkTables& T, const AkWordCache& C, const uint8_t* t, int64_t s,
                              int64_t e, uint32_t k, AkIdSink& sink, const AkPool& pool, uint32_t& status) {
     const uint32_t len = (uint32_t)(e - s);
-    if (len <= AKW_MAXLEN && C.e) {
-        unsigned long long k0, k1, k2;
-        akw_key(t, s, len, k0, k1, k2);
-        const unsigned long long h = akw_hash(k0, k1, k2, len);
+    if (e - s <= AKW_MAXLEN && C.e) {
+        AkWordKey K;
+        akw_key(t, s, len, K);
+        const unsigned long long h = akw_hash(K);
         const unsigned long long want = akw_want(h, len);
         int32_t ids[AKW_MAXTOK];
         long long slot;
-        const int n = akw_lookup(C, h, want, k0, k1, k2, ids, &slot);
+        const int n = akw_lookup(C, h, want, K, ids, &slot);
         if (n >= 0) {
-            for (int i = 0; i < n; ++i) ak_id_put(sink, ids[i]);
+#pragma unroll
+            for (int i = 0; i < AKW_MAXTOK; ++i)
+                if (i < n) ak_id_put(sink, ids[i]);
             return;
         }
         // miss: exact merge loop into a private list, then publish
@@ -140,7 +181,7 @@ AK_HD_NOINLINE void akb_word(const AkBpeDev& M, const AkTables& T, const AkWordC
         ak_bpe_word(M, T, t, s, e, k, local, pool, status);
         if (local.cnt <= AKW_MAXTOK) {
             for (int i = 0; i < local.cnt; ++i) ak_id_put(sink, tmp[i]);
-            if (slot >= 0) akw_insert(C, slot, want, k0, k1, k2, tmp, local.cnt);
+            if (slot >= 0) akw_insert(C, slot, want, K, tmp, local.cnt);
             return;
         }
     }

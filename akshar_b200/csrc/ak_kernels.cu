@@ -1309,7 +1309,7 @@ int akshar_load_bpe_json(akshar_ctx* ctx, const char* json, size_t len) {
         ht.page_index = ak_tbl_page_index;
         ht.leaves = ak_tbl_leaves;
         const uint32_t bits = 18;
-        std::vector<unsigned long long> img((size_t)8 << bits, 0ull);
+        std::vector<unsigned long long> img((size_t)AKW_ENTRY << bits, 0ull);
         AkWordCache hc;
         hc.e = img.data();
         hc.bits = bits;
@@ -1349,13 +1349,13 @@ int akshar_load_bpe_json(akshar_ctx* ctx, const char* json, size_t len) {
             sink.gcap = 0;
             ak_bpe_word(hm, ht, tb, 0, n, k, sink, hp, st);
             if (st || sink.cnt > AKW_MAXTOK) continue;
-            unsigned long long k0, k1, k2;
-            akw_key(tb, 0, (uint32_t)n, k0, k1, k2);
-            const unsigned long long hh = akw_hash(k0, k1, k2, (uint32_t)n);
+            AkWordKey K;
+            akw_key(tb, 0, (uint32_t)n, K);
+            const unsigned long long hh = akw_hash(K);
             const unsigned long long want = akw_want(hh, (uint32_t)n);
             int32_t got[AKW_MAXTOK];
             long long slot;
-            if (akw_lookup(hc, hh, want, k0, k1, k2, got, &slot) < 0 && slot >= 0) akw_insert(hc, slot, want, k0, k1, k2, out_ids, sink.cnt);
+            if (akw_lookup(hc, hh, want, K, got, &slot) < 0 && slot >= 0) akw_insert(hc, slot, want, K, out_ids, sink.cnt);
         }
         const unsigned long long* dimg = nullptr;
         if ((rc = ak_upload<unsigned long long>(ctx, ctx->bpe_allocs, img.data(), img.size(), &dimg))) return rc;

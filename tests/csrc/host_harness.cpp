@@ -259,7 +259,7 @@ int64_t hh_bpe_fast(const uint8_t* text, const int64_t* off, int64_t n_rows, int
     M.cp_direct = g_bpe.cp_direct.data(); M.cp_keys = g_bpe.cp_keys.data(); M.cp_ids = g_bpe.cp_ids.data();
     M.n_cp = (int)g_bpe.cp_keys.size(); M.mkeys = g_bpe.mkeys.data(); M.mvals = g_bpe.mvals.data(); M.mbits = g_bpe.mbits;
     M.bos = g_bpe.bos; M.eos = g_bpe.eos;
-    std::vector<unsigned long long> img((size_t)8 << cache_bits, 0ull);
+    std::vector<unsigned long long> img((size_t)AKW_ENTRY << cache_bits, 0ull);
     AkWordCache C; C.e = img.data(); C.bits = (uint32_t)cache_bits;
     std::vector<int32_t> poolbuf(1 << 20);
     unsigned long long used = 0;
