@@ -270,7 +270,7 @@ AK_HD void akb_resolve_first(AkBChunk& c, uint32_t prev_last_w, uint32_t prev_la
 
 // end of the word that starts at chunk byte s: next boundary in this chunk, else in the next one, else a forward scan
 AK_HD int64_t akb_word_end(const AkTables& T, const uint8_t* t, int64_t cs, int s, uint32_t k, uint32_t bnd, uint32_t next_bnd,
-                           const int64_t* off, int64_t n_rows, int64_t r_lo) {
+                           const int64_t* off, int64_t n_rows, int64_t r_lo, int64_t r_hi) {
     const uint32_t above = bnd & ~((2u << s) - 1u) & 0xFFFFu;
     if (above) {
 #ifdef __CUDA_ARCH__
@@ -286,8 +286,18 @@ AK_HD int64_t akb_word_end(const AkTables& T, const uint8_t* t, int64_t cs, int 
         return cs + 16 + __builtin_ctz(next_bnd & 0xFFFFu);
 #endif
     }
-    // long word: walk code points up to the end of its row (no boundary before cs + 32)
-    const int64_t re = off[ak_row_lower_bound(off, r_lo, n_rows, cs + s + 1)];
+    if (next_bnd >> 16) {      // bits 16..31: the chunk after the next one (when the caller has it)
+#ifdef __CUDA_ARCH__
+        return cs + 16 + (__ffs(next_bnd) - 1);
+#else
+        return cs + 16 + __builtin_ctz(next_bnd);
+#endif
+    }
+    // long word: walk code points up to the end of its row (no boundary before cs + 32); the row usually ends
+    // inside the tile's row window, else search the whole offset array
+    int64_t er = ak_row_lower_bound(off, r_lo, r_hi, cs + s + 1);
+    if (off[er] < cs + s + 1) er = ak_row_lower_bound(off, r_hi, n_rows, cs + s + 1);
+    const int64_t re = off[er];
     int64_t q = cs + 32;
     if (q > re) q = re;
     while (q < re && (t[q] & 0xC0u) == 0x80u) ++q;
@@ -315,15 +325,16 @@ struct AkBLaneCtx {
 };
 
 AK_HD_NOINLINE void akb_lane_emit(const AkBLaneCtx& X, const AkBChunk& c, uint32_t next_bnd, int64_t cs, AkIdSink& sink,
-                                  int64_t* id_splits, int64_t& row_first, int64_t& row_last, uint32_t& status) {
+                                  int64_t* id_splits, int64_t& row_first, int64_t& row_last, uint32_t& status,
+                                  int64_t nr_hint = -1) {
     uint32_t wstart = 0;
 #pragma unroll
     for (int i = 0; i < 16; ++i)
         if (((c.bnd & c.lead) >> i) & 1u)
             if (((c.cls >> (2 * i)) & 3u) != 2u) wstart |= 1u << i;
     uint32_t ev = (c.rows | wstart) & 0xFFFFu;
-    int64_t nr = -1;
-    row_first = row_last = 0;
+    int64_t nr = nr_hint;       // index of the first row that starts in this chunk, when the caller knows it
+    row_first = row_last = nr < 0 ? 0 : nr;
     while (ev) {
 #ifdef __CUDA_ARCH__
         const int i = __ffs(ev) - 1;
@@ -347,7 +358,7 @@ AK_HD_NOINLINE void akb_lane_emit(const AkBLaneCtx& X, const AkBChunk& c, uint32
         }
         if ((wstart >> i) & 1u) {
             const uint32_t k = (c.cls >> (2 * i)) & 3u;
-            const int64_t e = akb_word_end(*X.T, X.text, cs, i, k, c.bnd, next_bnd, X.off, X.n_rows, X.r_lo);
+            const int64_t e = akb_word_end(*X.T, X.text, cs, i, k, c.bnd, next_bnd, X.off, X.n_rows, X.r_lo, X.r_hi);
             akb_word(*X.M, *X.T, *X.C, X.text, p, e, k, sink, *X.pool, status);
         }
     }

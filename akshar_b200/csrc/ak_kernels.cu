@@ -274,7 +274,10 @@ __device__ __forceinline__ void akf_load_lane(const AkBatch& B, int64_t cs, CH& 
 }
 
 // ---- K1a: classify every chunk: emit mask for the fast lane, work-list entry otherwise; per-tile fast byte counts
-__global__ void __launch_bounds__(AK_BLOCK) ak_nf_classify_kernel(const AkFastNormArgs A, const AkNfWork W) {
+#ifndef AKN_MINB
+#define AKN_MINB 4
+#endif
+__global__ void __launch_bounds__(AK_BLOCK, AKN_MINB) ak_nf_classify_kernel(const AkFastNormArgs A, const AkNfWork W) {
     __shared__ uint32_t lut[384];
     __shared__ uint32_t rowbits[(AKF_TILE + 64) / 32 + 2];
     __shared__ int s_red[AKF_WARPS];
@@ -663,12 +666,16 @@ __device__ __forceinline__ int akb_n_tiles(const AkBatch& B, int64_t base0) {
     return (int)((B.text_begin + *B.dyn_end - base0 + AKF_TILE) / AKF_TILE);
 }
 
-__global__ void __launch_bounds__(AK_BLOCK) ak_bf_encode_kernel(const AkBfArgs A) {
+#ifndef AKB_MINB
+#define AKB_MINB 2
+#endif
+__global__ void __launch_bounds__(AK_BLOCK, AKB_MINB) ak_bf_encode_kernel(const AkBfArgs A) {
     __shared__ uint32_t lut[384];
     __shared__ uint32_t rowbits[(AKF_TILE + 64) / 32 + 2];
     __shared__ int32_t stage[AKB_STAGE * AK_BLOCK];
     __shared__ int ws[33];
     __shared__ long long s_toff;
+    __shared__ uint16_t rowpref[(AKF_TILE + 64) / 32 + 2];
     AkBatch B = A.B;
     if (!ak_batch_begin(B)) return;
     B.n_tiles = akb_n_tiles(A.B, A.base0);
@@ -679,6 +686,31 @@ __global__ void __launch_bounds__(AK_BLOCK) ak_bf_encode_kernel(const AkBfArgs A
         const int64_t tile_start = A.base0 + (int64_t)tile * AKF_TILE;
         akf_tile_rows(B, A.tile_row, tile, tile_start, rowbits);
         const int64_t r0 = A.tile_row[tile], r1 = A.tile_row[tile + 1];
+        if (warp == 0) {
+            // exclusive prefix of the row-start bit counts per bitmap word (a lane's first row index without a search)
+            constexpr int NW = (AKF_TILE + 64) / 32 + 2;
+            int v[4], sum = 0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int wi = lane * 4 + k;
+                v[k] = wi < NW ? __popc(rowbits[wi]) : 0;
+                sum += v[k];
+            }
+            int inc = sum;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int y = __shfl_up_sync(0xFFFFFFFFu, inc, d);
+                if (lane >= d) inc += y;
+            }
+            int run = inc - sum;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int wi = lane * 4 + k;
+                if (wi < NW) rowpref[wi] = (uint16_t)run;
+                run += v[k];
+            }
+        }
+        __syncthreads();
         AkBChunk c;
         const int64_t cs = tile_start + (int64_t)warp * AKF_WARP_BYTES + (int64_t)(lane - 1) * 16;
         akf_load_lane(B, cs, c);
@@ -704,7 +736,12 @@ __global__ void __launch_bounds__(AK_BLOCK) ak_bf_encode_kernel(const AkBfArgs A
             }
             akb_resolve_first(c, pw, pk);
         }
-        const uint32_t next_bnd = __shfl_down_sync(0xFFFFFFFFu, c.bnd, 1);
+        // word boundaries of the next chunk (bits 0..15) and of the one after it (bits 16..31; unknown for lane 30)
+        uint32_t next_bnd = __shfl_down_sync(0xFFFFFFFFu, c.bnd, 1) & 0xFFFFu;
+        {
+            const uint32_t n2 = __shfl_down_sync(0xFFFFFFFFu, c.bnd, 2) & 0xFFFFu;
+            if (lane < 30) next_bnd |= n2 << 16;
+        }
         const bool real = lane >= 1 && lane <= AKF_REAL;
         const int64_t ss = cs < B.text_begin ? B.text_begin : cs;
         const int64_t se = cs + 16 > B.text_end + 1 ? B.text_end + 1 : cs + 16;
@@ -730,10 +767,21 @@ __global__ void __launch_bounds__(AK_BLOCK) ak_bf_encode_kernel(const AkBfArgs A
         sink.gcap = A.temp_cap;
         uint32_t st = 0;
         int64_t row_first = 0, row_last = 0;
+        int64_t nr_hint = -1;
+        if (active && c.rows) {
+            // rows that start in [tile_start, p) = set bits in the bitmap between them; duplicates (empty rows) are
+            // skipped by the short loop
+            const int b = (int)(cs - (tile_start - 16)) + (__ffs(c.rows) - 1);
+            const int before = (int)rowpref[b >> 5] + __popc(rowbits[b >> 5] & ((1u << (b & 31)) - 1u)) - (int)__popc(rowbits[0] & 0xFFFFu);
+            int64_t g = r0 + before;
+            const int64_t p = cs + (__ffs(c.rows) - 1);
+            while (g < B.n_rows && B.off[g] < p) ++g;
+            nr_hint = g;
+        }
         if (active) {
             if (c.flags & AKB_ALPHABET) st |= AK_ST_ALPHABET;
             if ((c.flags & AKF_TROUBLE) && akb_chunk_changes(X, c, cs, AK_LOOKBACK_LIMIT, st)) atomicOr(A.changed, 1u);
-            akb_lane_emit(X, c, next_bnd, cs, sink, A.id_splits, row_first, row_last, st);
+            akb_lane_emit(X, c, next_bnd, cs, sink, A.id_splits, row_first, row_last, st, nr_hint);
         }
         const int cnt = sink.cnt;
         int total;
@@ -759,7 +807,7 @@ __global__ void __launch_bounds__(AK_BLOCK) ak_bf_encode_kernel(const AkBfArgs A
                 s2.gbase = tbase;
                 uint32_t st2 = 0;
                 int64_t a, b;
-                akb_lane_emit(X, c, next_bnd, cs, s2, nullptr, a, b, st2);
+                akb_lane_emit(X, c, next_bnd, cs, s2, nullptr, a, b, st2, nr_hint);
             }
         }
         ak_raise(B.result, st);

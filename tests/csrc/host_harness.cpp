@@ -312,14 +312,15 @@ int64_t hh_bpe_fast(const uint8_t* text, const int64_t* off, int64_t n_rows, int
             AkIdSink sink; sink.buf = stage.data(); sink.cap = stage_cap; sink.stride = 1; sink.cnt = 0; sink.direct = false;
             sink.gout = ids; sink.gbase = 0; sink.gcap = id_cap;
             int64_t rf, rl;
-            akb_lane_emit(X, c, lanes[(size_t)l + 1].bnd, cs, sink, splits, rf, rl, st);
+            const uint32_t nb = (lanes[(size_t)l + 1].bnd & 0xFFFFu) | (l + 2 <= real + 1 && l < real ? (lanes[(size_t)l + 2].bnd & 0xFFFFu) << 16 : 0u);
+            akb_lane_emit(X, c, nb, cs, sink, splits, rf, rl, st);
             for (int64_t r = rf; r < rl; ++r) splits[r] += base;
             if (sink.cnt <= stage_cap) {
                 for (int k = 0; k < sink.cnt; ++k) if (base + k < id_cap) ids[base + k] = stage[(size_t)k];
             } else {
                 AkIdSink s2 = sink; s2.cnt = 0; s2.direct = true; s2.gbase = base;
                 int64_t a, b;
-                akb_lane_emit(X, c, lanes[(size_t)l + 1].bnd, cs, s2, nullptr, a, b, st);
+                akb_lane_emit(X, c, nb, cs, s2, nullptr, a, b, st);
                 if (s2.cnt != sink.cnt) st |= 0x80000000u;
             }
             base += sink.cnt;
