@@ -425,20 +425,27 @@ AK_HD_NOINLINE void ak_seg_span(const AkTables& T, const uint8_t* t, const int64
     AkGState g;
     g.prev = 0; g.conj = 0; g.pict = 0; g.ri_odd = 0; g.prev_m = 0; g.has_prev = 0;
     uint32_t cur = TAG_NONE;
-    if (p != rs && p < total_end) {
+    // A row is closed (its last cluster end, its last run) by the span that owns the byte position where the row
+    // ENDS, i.e. the start of the next row (or the end of the text) -- the same rule as the fast lane (ak_seg_fast.cuh).
+    // A span that begins exactly there needs the closing row's run label: look back through that row.
+    int64_t back_lo = rs;                  // start of the row whose state must be reconstructed
+    bool need_cur = p != rs && p < total_end;
+    if (p == rs && nr > 0 && off[nr - 1] < p) {
+        rs = off[nr - 1];                  // the row that ends at p; the row-start event below closes it
+        back_lo = rs;
+        need_cur = true;
+    } else if (p != rs && p < total_end) {
         if (want_c) {
             // back up to the nearest code point after which the rule state is history-free, then replay
             int64_t q = p;
-            bool fresh = false;
             for (;;) {
                 q = ak_prev_start(t, q, rs);
                 int len;
                 uint32_t cp = ak_decode(t, q, re, len);
                 if (ak_g_sync(ak_props(T, cp))) break;
-                if (q == rs) { fresh = true; break; }
+                if (q == rs) break;
                 if (limit > 0 && p - q > limit) { status |= AK_ST_PATHOLOGICAL; break; }
             }
-            (void)fresh;
             while (q < p) {
                 int len;
                 uint32_t cp = ak_decode(t, q, re, len);
@@ -446,21 +453,34 @@ AK_HD_NOINLINE void ak_seg_span(const AkTables& T, const uint8_t* t, const int64
                 q += len;
             }
         }
-        if (want_r) {
-            int64_t q = p;
-            while (q > rs) {
-                q = ak_prev_start(t, q, rs);
-                int len;
-                uint32_t cp = ak_decode(t, q, re, len);
-                uint32_t tg = AK_TAG(ak_props(T, cp));
-                if (tg != TAG_DIGIT && tg != TAG_PUNCT) { cur = tg; break; }
-                if (limit > 0 && p - q > limit) { status |= AK_ST_PATHOLOGICAL; break; }
-            }
+    }
+    if (want_r && need_cur) {
+        int64_t q = p;
+        while (q > back_lo) {
+            q = ak_prev_start(t, q, back_lo);
+            int len;
+            uint32_t cp = ak_decode(t, q, p, len);
+            uint32_t tg = AK_TAG(ak_props(T, cp));
+            if (tg != TAG_DIGIT && tg != TAG_PUNCT) { cur = tg; break; }
+            if (limit > 0 && p - q > limit) { status |= AK_ST_PATHOLOGICAL; break; }
         }
     }
     for (;;) {
         if (p >= e) break;
         while (nr <= n_rows && off[nr] == p) {
+            if (nr > 0 && p > rs) {        // the row in progress is not empty: it ends here
+                if (want_c) {
+                    if (write && o.cbase + cc < o.ccap) o.cluster_ends[o.cbase + cc] = (int32_t)(p - rs);
+                    ++cc;
+                }
+                if (want_r) {
+                    if (write && o.rbase + rc < o.rcap) {
+                        o.run_ends[o.rbase + rc] = (int32_t)(p - rs);
+                        o.run_tags[o.rbase + rc] = (uint8_t)cur;
+                    }
+                    ++rc;
+                }
+            }
             if (write) {
                 if (want_c) o.cluster_splits[nr] = o.cbase + cc;
                 if (want_r) o.run_splits[nr] = o.rbase + rc;
@@ -500,19 +520,6 @@ AK_HD_NOINLINE void ak_seg_span(const AkTables& T, const uint8_t* t, const int64
             }
         }
         p += len;
-        if (p >= re) {       // the row ends with the code point this span just consumed
-            if (want_c) {
-                if (write && o.cbase + cc < o.ccap) o.cluster_ends[o.cbase + cc] = (int32_t)(p - rs);
-                ++cc;
-            }
-            if (want_r) {
-                if (write && o.rbase + rc < o.rcap) {
-                    o.run_ends[o.rbase + rc] = (int32_t)(p - rs);
-                    o.run_tags[o.rbase + rc] = (uint8_t)cur;
-                }
-                ++rc;
-            }
-        }
     }
     n_clusters = cc;
     n_runs = rc;

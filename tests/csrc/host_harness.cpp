@@ -10,6 +10,7 @@
 #include "../../akshar_b200/csrc/ak_subword.cuh"
 #include "../../akshar_b200/csrc/ak_fast.cuh"
 #include "../../akshar_b200/csrc/ak_bpe_fast.cuh"
+#include "../../akshar_b200/csrc/ak_seg_fast.cuh"
 #include "../../akshar_b200/csrc/ak_models.h"
 #include "../../akshar_b200/csrc/unicode_tables.inc"
 
@@ -329,6 +330,78 @@ int64_t hh_bpe_fast(const uint8_t* text, const int64_t* off, int64_t n_rows, int
     *changed_out = changed ? 1 : 0;
     *status = st;
     return base;
+}
+
+// The fast segment kernel's structure on the CPU (chunks, halo lanes, phase A / B, lane emit, walker slow lane).
+void hh_seg_fast(const uint8_t* text, const int64_t* off, int64_t n_rows, uint32_t flags, int real, int stage_cap,
+                 int32_t* cluster_ends, int64_t* cluster_splits, int32_t* run_ends, uint8_t* run_tags, int64_t* run_splits,
+                 int64_t cap, int64_t* totals, uint32_t* status, int64_t* n_slow) {
+    AkTables T = host_tables();
+    std::vector<uint32_t> lut(384);
+    for (int i = 0; i < 384; ++i) lut[(size_t)i] = i < 128 ? ak_props(T, (uint32_t)i) : ak_props(T, 0x900u + (uint32_t)(i - 128));
+    const bool want_c = (flags & AK_SEG_CLUSTERS) != 0, want_r = (flags & AK_SEG_RUNS) != 0, matras = (flags & AK_SEG_MATRAS) != 0;
+    const int64_t tb = off[0], te = off[n_rows], base0 = tb;
+    std::vector<uint8_t> rowstart((size_t)(te - base0) + 64, 0);
+    for (int64_t r = 0; r <= n_rows; ++r) rowstart[(size_t)(off[r] - base0)] = 1;
+    const int64_t n_chunks = (te - base0 + 1 + 15) / 16;
+    uint32_t st = 0;
+    int64_t cbase = 0, rbase = 0, slow_cnt = 0;
+    std::vector<AkSChunk> lanes((size_t)real + 2);
+    std::vector<int32_t> cst((size_t)stage_cap + 1), rst((size_t)stage_cap + 1);
+    std::vector<uint8_t> tst((size_t)stage_cap + 1);
+    for (int64_t w0 = 0; w0 < n_chunks; w0 += real) {
+        for (int l = 0; l < real + 2; ++l) {
+            AkSChunk& c = lanes[(size_t)l];
+            int64_t cs = base0 + (w0 - 1 + l) * 16;
+            AkChunk tmp;
+            hh_make_chunk(text, cs, tb, te, rowstart, base0, tmp);
+            for (int k = 0; k < 5; ++k) c.w[k] = tmp.w[k];
+            c.rows = tmp.rows; c.own = tmp.own;
+            aks_phase_a(T, lut.data(), c, matras);
+        }
+        for (int l = 1; l <= real; ++l) {
+            AkSChunk c = lanes[(size_t)l];
+            int64_t cs = base0 + (w0 - 1 + l) * 16;
+            int64_t ss = cs < tb ? tb : cs, se = cs + 16 > te + 1 ? te + 1 : cs + 16;
+            if (ss >= se) continue;
+            AkSNeighbor pv;
+            pv.g = lanes[(size_t)l - 1].end_g; pv.flags = lanes[(size_t)l - 1].flags; pv.end_cur = lanes[(size_t)l - 1].end_cur;
+            uint32_t in_cur = AKS_CUR_NONE;
+            bool slow = !aks_phase_b(T, lut.data(), c, pv, matras, want_c, want_r, in_cur);
+            if (slow) {
+                ++slow_cnt;
+                AkSegOut o;
+                o.cluster_ends = cluster_ends; o.cluster_splits = cluster_splits; o.run_ends = run_ends; o.run_tags = run_tags;
+                o.run_splits = run_splits; o.ccap = cap; o.rcap = cap; o.cbase = cbase; o.rbase = rbase;
+                int64_t a, b;
+                ak_seg_span(T, text, off, n_rows, 0, n_rows, ss, se, flags, 0, true, o, a, b, st);
+                cbase += a; rbase += b;
+                continue;
+            }
+            int64_t nr = 0;
+            while (nr <= n_rows && off[nr] < ss) ++nr;
+            AkSegSink sink;
+            sink.cbuf = cst.data(); sink.rbuf = rst.data(); sink.tbuf = tst.data(); sink.cap = stage_cap; sink.stride = 1;
+            sink.cc = sink.rc = 0; sink.direct = false; sink.gc = sink.gr = nullptr; sink.gt = nullptr; sink.gccap = sink.grcap = 0;
+            int64_t rf, rl;
+            aks_lane_emit(c, in_cur, cs, off, n_rows, nr, want_c, want_r, sink, want_c ? cluster_splits : nullptr,
+                          want_r ? run_splits : nullptr, rf, rl);
+            for (int64_t r = rf; r < rl; ++r) { if (want_c) cluster_splits[r] += cbase; if (want_r) run_splits[r] += rbase; }
+            if (sink.cc <= stage_cap && sink.rc <= stage_cap) {
+                for (int k = 0; k < sink.cc; ++k) if (cbase + k < cap) cluster_ends[cbase + k] = cst[(size_t)k];
+                for (int k = 0; k < sink.rc; ++k) if (rbase + k < cap) { run_ends[rbase + k] = rst[(size_t)k]; run_tags[rbase + k] = tst[(size_t)k]; }
+            } else {
+                AkSegSink s2 = sink; s2.cc = s2.rc = 0; s2.direct = true; s2.gc = cluster_ends + cbase; s2.gr = run_ends + rbase;
+                s2.gt = run_tags + rbase; s2.gccap = cap - cbase; s2.grcap = cap - rbase;
+                int64_t a, b;
+                aks_lane_emit(c, in_cur, cs, off, n_rows, nr, want_c, want_r, s2, nullptr, nullptr, a, b);
+            }
+            cbase += sink.cc; rbase += sink.rc;
+        }
+    }
+    totals[0] = cbase; totals[1] = rbase;
+    *status = st;
+    *n_slow = slow_cnt;
 }
 
 int64_t hh_unigram(const uint8_t* text, const int64_t* off, int64_t n_rows, int32_t* ids, int64_t id_cap, int64_t* splits) {

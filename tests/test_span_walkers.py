@@ -120,3 +120,32 @@ def test_fast_lane_is_mostly_fast():
         n_chunks = data.size / 16
         print(kind, 'slow chunks: %.2f %%' % (100.0 * n_slow / n_chunks))
         assert n_slow / n_chunks < 0.05
+
+
+@pytest.mark.parametrize('real,stage_cap', [(30, 18), (1, 18), (4, 1)])
+def test_segment_fast_structure(real, stage_cap):
+    lines = list(_lines())
+    data, off = sc.pack(lines)
+    ce, cs = _exp_seg(False)
+    re_, rt, rs = _exp_runs()
+    gce, gcs, gre, grt, grs, st, n_slow = W.seg_fast(data, off, flags=1 | 4, real=real, stage_cap=stage_cap)
+    assert st == 0
+    assert np.array_equal(gcs, cs) and np.array_equal(gce, ce)
+    assert np.array_equal(grs, rs) and np.array_equal(gre, re_) and np.array_equal(grt, rt)
+    me, ms = _exp_seg(True)
+    gce, gcs, _, _, _, st, _ = W.seg_fast(data, off, flags=1 | 2, real=real, stage_cap=stage_cap)
+    assert st == 0
+    assert np.array_equal(gcs, ms) and np.array_equal(gce, me)
+
+
+def test_segment_fast_is_mostly_fast():
+    for kind in ('hinglish', 'hindi', 'social'):
+        lines = sc.Corpus(kind, 8).lines(200000)
+        data, off = sc.pack(lines)
+        gce, gcs, gre, grt, grs, st, n_slow = W.seg_fast(data, off, flags=5)
+        ce, cs = OB.segment_batch(lines)
+        re_, rt, rs = OB.runs_batch(lines)
+        assert st == 0 and np.array_equal(gce, ce) and np.array_equal(gcs, cs)
+        assert np.array_equal(gre, re_) and np.array_equal(grt, rt) and np.array_equal(grs, rs)
+        print(kind, 'slow chunks: %.3f %%' % (100.0 * n_slow / (data.size / 16)))
+        assert n_slow / (data.size / 16) < 0.02
