@@ -102,12 +102,15 @@ class Engine:
         raise C.AksharCudaError('%s: %s (%s)' % (what, self.lib.akshar_status_str(rc).decode(),
                                                  self.lib.akshar_last_error(self._h).decode()))
 
-    def _workspace(self, n_bytes, n_rows):
-        need = self.lib.akshar_workspace_bytes(n_bytes, n_rows)
+    def _workspace(self, n_bytes, n_rows, extra=0):
+        """`extra` bytes beyond the library's minimum enlarge the temporary output streams (grown after an overflow)"""
+        need = self.lib.akshar_workspace_bytes(n_bytes, n_rows) + extra
         if self._ws is None or self._ws.numel() < need:
             self._ws = None
             self._ws = torch.empty(need + (need >> 3), dtype=torch.uint8, device=self.device)
         return self._ws
+
+    MAX_TRIES = 5
 
     @staticmethod
     def _stream():
@@ -143,7 +146,7 @@ class Engine:
         flags = (C.NORM_ROMAN if normalize_roman else 0) | (C.NORM_CLEAN if clean_hinglish else 0)
         cap = capacity if capacity is not None else b.n_bytes + (b.n_bytes >> 3) + 1024
         ws = self._workspace(b.n_bytes, b.n_rows)
-        while True:
+        for _ in range(self.MAX_TRIES):
             out = torch.empty(max(cap, 1), dtype=torch.uint8, device=self.device)
             out_off = torch.empty(b.n_rows + 1, dtype=torch.int64, device=self.device)
             result = torch.empty(4, dtype=torch.int64, device=self.device)
@@ -164,6 +167,7 @@ class Engine:
             if bits:
                 raise BatchStatusError(bits, 'normalize_batch')
             return TextBatch(out, out_off, 0, total)
+        raise BatchStatusError(bits, 'normalize_batch (retries exhausted)')
 
     # ------------------------------------------------------------------ K2 / K3
     def segment_batch(self, batch, clusters=True, matras=False, runs=False, mode=C.MODE_TILES, capacity=None, check=True):
@@ -177,7 +181,7 @@ class Engine:
         if runs:
             rcap = capacity if capacity is not None else (b.n_bytes >> 3) + b.n_rows + 1024
         ws = self._workspace(b.n_bytes, b.n_rows)
-        while True:
+        for _ in range(self.MAX_TRIES):
             dev = self.device
             ce = torch.empty(max(ccap, 1), dtype=torch.int32, device=dev) if clusters else None
             cs = torch.empty(b.n_rows + 1, dtype=torch.int64, device=dev) if clusters else None
@@ -197,7 +201,9 @@ class Engine:
                     mode = C.MODE_ROWS
                     continue
                 if bits & C.ST_OVERFLOW:
-                    ccap, rcap = (nc if clusters else 0), (nr if runs else 0)
+                    # totals are exact: size the outputs and the temporary streams in the workspace for them
+                    ccap, rcap = (max(ccap, nc) if clusters else 0), (max(rcap, nr) if runs else 0)
+                    ws = self._workspace(b.n_bytes, b.n_rows, extra=6 * nc + 20 * nr + (1 << 16))
                     continue
                 if bits:
                     raise BatchStatusError(bits, 'segment_batch')
@@ -208,6 +214,7 @@ class Engine:
             co = Ragged(ce, cs) if clusters else None
             ro = Ragged(re_, rs, rt) if runs else None
             return (co, ro) if check else (co, ro, result)
+        raise BatchStatusError(bits, 'segment_batch (retries exhausted)')
 
     # ------------------------------------------------------------------ K1b
     def signature_batch(self, batch):
@@ -268,7 +275,7 @@ class Engine:
         b = self.put(batch)
         cap = capacity if capacity is not None else (b.n_bytes >> 1) + 2 * b.n_rows + 1024
         ws = self._workspace(b.n_bytes, b.n_rows)
-        while True:
+        for _ in range(self.MAX_TRIES):
             ids = torch.empty(max(cap, 1), dtype=torch.int32, device=self.device)
             splits = torch.empty(b.n_rows + 1, dtype=torch.int64, device=self.device)
             result = torch.empty(4, dtype=torch.int64, device=self.device)
@@ -283,11 +290,13 @@ class Engine:
                 mode = C.MODE_ROWS
                 continue
             if bits & C.ST_OVERFLOW:
-                cap = total
+                cap = max(cap, total)
+                ws = self._workspace(b.n_bytes, b.n_rows, extra=4 * total + (1 << 16))
                 continue
             if bits:
                 raise BatchStatusError(bits, what)
             return Ragged(ids[:total], splits)
+        raise BatchStatusError(bits, what + ' (retries exhausted)')
 
     def encode_bpe_batch(self, batch, mode=C.MODE_TILES, capacity=None, check=True):
         """Tokenizer.encode(norm).ids over ALREADY NORMALIZED rows (reference tokenizer.py:193) -> Ragged int32 ids"""
@@ -307,7 +316,7 @@ class Engine:
         ncap = b.n_bytes + (b.n_bytes >> 3) + 1024
         cap = capacity if capacity is not None else (b.n_bytes >> 1) + 2 * b.n_rows + 1024
         ws = self._workspace(ncap, b.n_rows)
-        while True:
+        for _ in range(self.MAX_TRIES):
             dev = self.device
             norm = torch.empty(max(ncap, 1), dtype=torch.uint8, device=dev)
             norm_off = torch.empty(b.n_rows + 1, dtype=torch.int64, device=dev)
@@ -331,12 +340,13 @@ class Engine:
                 cap = max(cap, total)
                 if nbytes > ncap:
                     ncap = nbytes
-                    ws = self._workspace(ncap, b.n_rows)
                     cap = max(cap, (ncap >> 1) + 2 * b.n_rows + 1024)
+                ws = self._workspace(ncap, b.n_rows, extra=4 * max(cap, total) + (1 << 16))
                 continue
             if bits:
                 raise BatchStatusError(bits, 'tokenizer_encode_batch')
             return Ragged(ids[:total], splits), TextBatch(norm, norm_off, 0, nbytes)
+        raise BatchStatusError(bits, 'tokenizer_encode_batch (retries exhausted)')
 
 
 _engines = {}

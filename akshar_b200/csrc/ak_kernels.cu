@@ -1348,6 +1348,7 @@ struct AkCall {
     AkBatch B;
     AkWsLayout L;
     char* ws;
+    size_t ws_bytes;       // what the caller really passed: the temporary streams use everything beyond the fixed part
     cudaStream_t stream;
 };
 
@@ -1369,6 +1370,7 @@ static int ak_begin(akshar_ctx* ctx, const uint8_t* d_text, const int64_t* d_row
         return AKSHAR_E_WORKSPACE;
     }
     C.ws = (char*)d_workspace;
+    C.ws_bytes = workspace_bytes;
     C.stream = (cudaStream_t)stream;
     AK_CUDA(ctx, cudaSetDevice(ctx->device));
     const size_t tiles = (size_t)ak_tiles_of(n_bytes, n_rows);
@@ -1540,8 +1542,13 @@ int akshar_segment_batch(akshar_ctx* ctx, const uint8_t* d_text, const int64_t* 
         F.r_toff = (int64_t*)wp;    wp += ak_align(tiles * 8);
         F.c_base = (int64_t*)wp;    wp += ak_align((tiles + 1) * 8);
         F.r_base = (int64_t*)wp;    wp += ak_align((tiles + 1) * 8);
-        F.tc_cap = n_bytes / 2 + n_rows + 1024;
-        F.tr_cap = n_bytes / 8 + n_rows + 1024;
+        {
+            // the temporary streams share what is left of the workspace: 4 B per cluster end, 5 B per run end
+            const size_t left = C.ws_bytes - (size_t)(wp - C.ws) - 1024;
+            if (want_c && want_r) { F.tc_cap = (int64_t)(left * 3 / 4 / 4); F.tr_cap = (int64_t)(left / 4 / 5); }
+            else if (want_c) { F.tc_cap = (int64_t)(left / 4); F.tr_cap = 0; }
+            else { F.tc_cap = 0; F.tr_cap = (int64_t)(left / 5); }
+        }
         F.tc = (int32_t*)wp;        wp += ak_align((size_t)F.tc_cap * 4);
         F.tr = (int32_t*)wp;        wp += ak_align((size_t)F.tr_cap * 4);
         F.tt = (uint8_t*)wp;
@@ -1794,7 +1801,7 @@ static int ak_run_bpe(akshar_ctx* ctx, AkCall& C, const AkBatch& B, int64_t max_
         F.tile_toff = (int64_t*)wp;                  wp += ak_align(tiles * 8);
         F.tile_base = (int64_t*)wp;
         F.temp = (int32_t*)(C.ws + C.L.bf_temp);
-        F.temp_cap = C.L.bf_temp_cap;
+        F.temp_cap = (int64_t)((C.ws_bytes - C.L.bf_temp) / 4);      // a larger workspace = a larger temporary stream
         F.temp_cursor = (unsigned long long*)(C.ws + 80);
         F.ids = d_ids;
         F.id_cap = id_capacity;

@@ -25,7 +25,7 @@ def _run_flags(batch, flags, as_device=False, device=0):
     ws = eng._workspace(b.n_bytes, b.n_rows)
     cap = b.n_bytes + (b.n_bytes >> 3) + 1024
     mode = C.MODE_TILES
-    while True:
+    for _ in range(eng.MAX_TRIES):
         out = torch.empty(max(cap, 1), dtype=torch.uint8, device=eng.device)
         out_off = torch.empty(b.n_rows + 1, dtype=torch.int64, device=eng.device)
         result = torch.empty(4, dtype=torch.int64, device=eng.device)
@@ -48,6 +48,8 @@ def _run_flags(batch, flags, as_device=False, device=0):
         from .batch import TextBatch
         tb = TextBatch(out, out_off, 0, total)
         return tb if as_device else tb.to_strings()
+    from .batch import BatchStatusError
+    raise BatchStatusError(bits, 'normalize (retries exhausted)')
 
 
 def _norm_flags(normalize_roman, clean_hinglish):
