@@ -14,12 +14,13 @@ ST_OVERFLOW, ST_NFC_SEGMENT, ST_PATHOLOGICAL, ST_ALPHABET, ST_SPIN, ST_WORD = 1,
 NORM_ROMAN, NORM_FILTER, NORM_COLLAPSE, NORM_CLEAN, NORM_NO_NFC = 1, 2, 4, 6, 8
 SEG_CLUSTERS, SEG_MATRAS, SEG_RUNS = 1, 2, 4
 MODE_TILES, MODE_ROWS = 0, 1
+TIMERS = {'ak_nf_classify_kernel': 0, 'ak_nf_write_kernel': 1, 'ak_bf_encode_kernel': 2, 'ak_sf_kernel': 3, 'ak_unigram_kernel': 4}
 
 SYMBOLS = (
     'akshar_version', 'akshar_status_str', 'akshar_ctx_create', 'akshar_ctx_destroy', 'akshar_last_error',
     'akshar_workspace_bytes', 'akshar_normalize_batch', 'akshar_segment_batch', 'akshar_signature_batch',
     'akshar_load_bpe_json', 'akshar_load_spm_model', 'akshar_vocab_size', 'akshar_vocab_token',
-    'akshar_encode_bpe_batch', 'akshar_encode_unigram_batch', 'akshar_tokenizer_encode_batch', 'akshar_launch_count',
+    'akshar_encode_bpe_batch', 'akshar_encode_unigram_batch', 'akshar_tokenizer_encode_batch', 'akshar_launch_count', 'akshar_timing_enable', 'akshar_timing_read',
 )
 
 _lib = None
@@ -61,6 +62,8 @@ def load():
     L.akshar_encode_bpe_batch.argtypes = [vp, vp, vp, i64, i64, i64, i32, vp, i64, vp, vp, vp, sz, vp]
     L.akshar_encode_unigram_batch.argtypes = [vp, vp, vp, i64, i64, i64, i32, vp, i64, vp, vp, vp, sz, vp]
     L.akshar_tokenizer_encode_batch.argtypes = [vp, vp, vp, i64, i64, i64, u32, i32, i32, vp, i64, vp, vp, i64, vp, vp, vp, sz, vp]
+    L.akshar_timing_enable.argtypes = [vp, i32]
+    L.akshar_timing_read.argtypes = [vp, i32, c.POINTER(c.c_float)]
     L.akshar_launch_count.argtypes = [vp]
     L.akshar_launch_count.restype = i64
     _lib = L

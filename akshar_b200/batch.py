@@ -119,6 +119,18 @@ class Engine:
     def launch_count(self):
         return int(self.lib.akshar_launch_count(self._h))
 
+    def timing(self, enable=True):
+        """CUDA-event timing of the dominant kernel of each stage (see include/akshar_b200.h)"""
+        rc = self.lib.akshar_timing_enable(self._h, 1 if enable else 0)
+        if rc != 0:
+            self._err(rc, 'akshar_timing_enable')
+
+    def kernel_ms(self, name):
+        """duration of kernel `name` in the most recent call, or None if it was not launched"""
+        ms = ctypes.c_float()
+        rc = self.lib.akshar_timing_read(self._h, C.TIMERS[name], ctypes.byref(ms))
+        return float(ms.value) if rc == 0 else None
+
     def put(self, lines):
         """host list[str] (or (uint8 tensor, int64 offsets) host tensors) -> TextBatch on the device"""
         if isinstance(lines, TextBatch):

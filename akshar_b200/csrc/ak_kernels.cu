@@ -1186,6 +1186,10 @@ struct akshar_ctx {
     unsigned long long* wc_image = nullptr;
     size_t wc_bytes = 0;
     int occ_bf = 0, occ_sf = 0;
+    // optional CUDA-event timing of the dominant kernel of each stage (bench.py's roofline line)
+    bool timing = false;
+    cudaEvent_t tev[AKSHAR_TIMER_COUNT][2] = {};
+    bool tev_valid[AKSHAR_TIMER_COUNT] = {};
     int occ_norm = 0, occ_seg = 0, occ_bpe = 0, occ_uni = 0, occ_sig = 0, occ_nf_classify = 0, occ_nf_write = 0;
 };
 
@@ -1282,10 +1286,33 @@ void akshar_ctx_destroy(akshar_ctx* ctx) {
     ak_free_list(ctx->allocs);
     ak_free_list(ctx->bpe_allocs);
     ak_free_list(ctx->uni_allocs);
+    for (int i = 0; i < AKSHAR_TIMER_COUNT; ++i)
+        for (int k = 0; k < 2; ++k)
+            if (ctx->tev[i][k]) cudaEventDestroy(ctx->tev[i][k]);
     delete ctx;
 }
 
 const char* akshar_last_error(akshar_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int akshar_timing_enable(akshar_ctx* ctx, int enable) {
+    if (!ctx) return AKSHAR_E_ARG;
+    AK_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (enable)
+        for (int i = 0; i < AKSHAR_TIMER_COUNT; ++i)
+            for (int k = 0; k < 2; ++k)
+                if (!ctx->tev[i][k]) AK_CUDA(ctx, cudaEventCreate(&ctx->tev[i][k]));
+    ctx->timing = enable != 0;
+    for (int i = 0; i < AKSHAR_TIMER_COUNT; ++i) ctx->tev_valid[i] = false;
+    return AKSHAR_OK;
+}
+
+int akshar_timing_read(akshar_ctx* ctx, int timer, float* ms) {
+    if (!ctx || !ms || timer < 0 || timer >= AKSHAR_TIMER_COUNT) return AKSHAR_E_ARG;
+    if (!ctx->tev_valid[timer]) return AKSHAR_E_ARG;
+    AK_CUDA(ctx, cudaEventSynchronize(ctx->tev[timer][1]));
+    AK_CUDA(ctx, cudaEventElapsedTime(ms, ctx->tev[timer][0], ctx->tev[timer][1]));
+    return AKSHAR_OK;
+}
 
 int64_t akshar_launch_count(akshar_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
@@ -1396,6 +1423,19 @@ static int ak_begin(akshar_ctx* ctx, const uint8_t* d_text, const int64_t* d_row
     return AKSHAR_OK;
 }
 
+// brackets one kernel launch with events when timing is enabled
+struct AkTimed {
+    akshar_ctx* ctx;
+    int slot;
+    cudaStream_t s;
+    AkTimed(akshar_ctx* c, int sl, cudaStream_t st) : ctx(c), slot(sl), s(st) {
+        if (ctx->timing && ctx->tev[slot][0]) cudaEventRecord(ctx->tev[slot][0], s);
+    }
+    ~AkTimed() {
+        if (ctx->timing && ctx->tev[slot][1]) { cudaEventRecord(ctx->tev[slot][1], s); ctx->tev_valid[slot] = true; }
+    }
+};
+
 static int ak_grid(akshar_ctx* ctx, int occ, int n_tiles) {
     int g = ctx->sm_count * (occ > 0 ? occ : 1);
     return n_tiles < g ? (n_tiles > 0 ? n_tiles : 1) : g;
@@ -1446,7 +1486,10 @@ static int ak_run_normalize(akshar_ctx* ctx, AkCall& C, const AkBatch& B, uint32
         W.slow = (AkSlowEntry*)wp;
         W.n_slow = (unsigned int*)(C.ws + 72);
         W.slow_cap = (unsigned int)(nt * AK_BLOCK / 16 + 1024);
-        ak_nf_classify_kernel<<<ak_grid(ctx, ctx->occ_nf_classify, F.B.n_tiles), AK_BLOCK, 0, C.stream>>>(F, W);
+        {
+            AkTimed tm(ctx, AKSHAR_TIMER_NORMALIZE_CLASSIFY, C.stream);
+            ak_nf_classify_kernel<<<ak_grid(ctx, ctx->occ_nf_classify, F.B.n_tiles), AK_BLOCK, 0, C.stream>>>(F, W);
+        }
         if ((rc = ak_after_launch(ctx, "normalize-classify"))) return rc;
         AkNfSlowArgs S;
         S.B = B;
@@ -1462,7 +1505,10 @@ static int ak_run_normalize(akshar_ctx* ctx, AkCall& C, const AkBatch& B, uint32
         if ((rc = ak_after_launch(ctx, "normalize-slow-count"))) return rc;
         ak_nf_scan_kernel<<<1, 1024, 0, C.stream>>>(W.tile_total, W.tile_base, F.B.n_tiles, B.totals, B, F.base0);
         if ((rc = ak_after_launch(ctx, "normalize-scan"))) return rc;
-        ak_nf_write_kernel<<<ak_grid(ctx, ctx->occ_nf_write, F.B.n_tiles), AK_BLOCK, 0, C.stream>>>(F, W);
+        {
+            AkTimed tm(ctx, AKSHAR_TIMER_NORMALIZE_WRITE, C.stream);
+            ak_nf_write_kernel<<<ak_grid(ctx, ctx->occ_nf_write, F.B.n_tiles), AK_BLOCK, 0, C.stream>>>(F, W);
+        }
         if ((rc = ak_after_launch(ctx, "normalize-write"))) return rc;
         S.write = 1;
         ak_nf_slow_kernel<<<slow_grid, 128, 0, C.stream>>>(S);
@@ -1558,7 +1604,10 @@ int akshar_segment_batch(akshar_ctx* ctx, const uint8_t* d_text, const int64_t* 
         ak_tile_rows_kernel<<<(entries + 255) / 256, 256, 0, C.stream>>>(C.B.off, n_rows, F.base0, entries, tile_row, nullptr, nullptr,
                                                                         text_begin);
         if ((rc = ak_after_launch(ctx, "segment-tile-rows"))) return rc;
-        ak_sf_kernel<<<ak_grid(ctx, ctx->occ_sf, F.B.n_tiles), AK_BLOCK, 0, C.stream>>>(F);
+        {
+            AkTimed tm(ctx, AKSHAR_TIMER_SEGMENT, C.stream);
+            ak_sf_kernel<<<ak_grid(ctx, ctx->occ_sf, F.B.n_tiles), AK_BLOCK, 0, C.stream>>>(F);
+        }
         if ((rc = ak_after_launch(ctx, "segment-fast"))) return rc;
         if (want_c) {
             ak_nf_scan_kernel<<<1, 1024, 0, C.stream>>>(F.c_total, F.c_base, F.B.n_tiles, d_result, C.B, F.base0);
@@ -1812,7 +1861,10 @@ static int ak_run_bpe(akshar_ctx* ctx, AkCall& C, const AkBatch& B, int64_t max_
         ak_tile_rows_kernel<<<(entries + 255) / 256, 256, 0, C.stream>>>(B.off, B.n_rows, F.base0, entries, tile_row, B.run_if,
                                                                         nullptr, B.text_begin);
         if ((rc = ak_after_launch(ctx, "bpe-tile-rows"))) return rc;
-        ak_bf_encode_kernel<<<ak_grid(ctx, ctx->occ_bf, nt_ub), AK_BLOCK, 0, C.stream>>>(F);
+        {
+            AkTimed tm(ctx, AKSHAR_TIMER_BPE_ENCODE, C.stream);
+            ak_bf_encode_kernel<<<ak_grid(ctx, ctx->occ_bf, nt_ub), AK_BLOCK, 0, C.stream>>>(F);
+        }
         if ((rc = ak_after_launch(ctx, "bpe-fast"))) return rc;
         ak_nf_scan_kernel<<<1, 1024, 0, C.stream>>>(F.tile_total, F.tile_base, nt_ub, B.totals, B, F.base0);
         if ((rc = ak_after_launch(ctx, "bpe-scan"))) return rc;
@@ -1867,7 +1919,10 @@ static int ak_run_unigram(akshar_ctx* ctx, AkCall& C, const AkBatch& B, int64_t 
     A.ids = d_ids;
     A.id_cap = id_capacity;
     A.id_splits = d_id_splits;
-    ak_unigram_kernel<<<ak_grid(ctx, ctx->occ_uni, A.B.n_tiles), AK_ROWS_BLOCK, 0, C.stream>>>(A);
+    {
+        AkTimed tm(ctx, AKSHAR_TIMER_UNIGRAM, C.stream);
+        ak_unigram_kernel<<<ak_grid(ctx, ctx->occ_uni, A.B.n_tiles), AK_ROWS_BLOCK, 0, C.stream>>>(A);
+    }
     return ak_after_launch(ctx, "unigram");
 }
 

@@ -129,6 +129,20 @@ int akshar_tokenizer_encode_batch(akshar_ctx* ctx, const uint8_t* d_text, const 
                                   int64_t id_capacity, int64_t* d_id_splits, int64_t* d_result, void* d_workspace,
                                   size_t workspace_bytes, void* stream);
 
+/* Optional device-side timing of the dominant kernel of each stage, for roofline reporting: when enabled, the
+ * library brackets that one launch with CUDA events on the caller's stream; akshar_timing_read waits for the
+ * kernel and returns its duration of the most recent call. */
+enum {
+    AKSHAR_TIMER_NORMALIZE_CLASSIFY = 0,   /* ak_nf_classify_kernel */
+    AKSHAR_TIMER_NORMALIZE_WRITE = 1,      /* ak_nf_write_kernel */
+    AKSHAR_TIMER_BPE_ENCODE = 2,           /* ak_bf_encode_kernel */
+    AKSHAR_TIMER_SEGMENT = 3,              /* ak_sf_kernel */
+    AKSHAR_TIMER_UNIGRAM = 4,              /* ak_unigram_kernel */
+    AKSHAR_TIMER_COUNT = 5
+};
+int akshar_timing_enable(akshar_ctx* ctx, int enable);
+int akshar_timing_read(akshar_ctx* ctx, int timer, float* ms);
+
 /* number of kernels this library has launched on this context since creation (bench.py's gpu_launches) */
 int64_t akshar_launch_count(akshar_ctx* ctx);
 
