@@ -41,19 +41,33 @@ AK_HD void akw_st(unsigned long long* p, unsigned long long v) {
 #endif
 }
 
-struct AkWordKey {
-    unsigned long long k[AKW_KW];     // the word's bytes, zero padded, little endian
-    uint32_t len, nw;                 // bytes, key words in use
-};
+// Key word j (bytes [8j, 8j + 8) of the word [s, s + len), zero padded, little endian).  On the device: two 8-byte
+// aligned loads + a funnel shift (the allocation of `t` must reach the next 8-byte boundary after its last byte, which
+// holds for every CUDA allocation).  Everything below streams over the key words with ROLLED loops: this code sits on
+// the hot path of an instruction-cache-bound kernel, compactness beats a few redundant L1 loads.
+AK_HD unsigned long long akw_key_word(const uint8_t* t, int64_t s, uint32_t len, uint32_t j) {
+    const uint32_t nb = len - 8u * j;           // bytes left from this word on (>= 1)
+#ifdef __CUDA_ARCH__
+    const uintptr_t a = (uintptr_t)(t + s) + 8u * j;
+    const unsigned long long* base = (const unsigned long long*)(a & ~(uintptr_t)7);
+    const uint32_t sh = (uint32_t)(a & 7u) * 8u;
+    unsigned long long v = __ldg(base) >> sh;
+    if (sh && (uint32_t)(a & 7u) + nb > 8u) v |= __ldg(base + 1) << (64u - sh);
+#else
+    unsigned long long v = 0ull;
+    for (uint32_t i = 0; i < 8u && i < nb; ++i) v |= (unsigned long long)t[s + 8u * j + i] << (8u * i);
+#endif
+    if (nb < 8u) v &= (1ull << (8u * nb)) - 1ull;
+    return v;
+}
 
-AK_HD unsigned long long akw_hash(const AkWordKey& K) {
-    unsigned long long h = 0x9E3779B97F4A7C15ull + K.len;
-#pragma unroll
-    for (int j = 0; j < AKW_KW; ++j) {
-        if ((uint32_t)j < K.nw) {
-            h = (h ^ K.k[j]) * 0xBF58476D1CE4E5B9ull;
-            h = (h << 27) | (h >> 37);
-        }
+AK_HD unsigned long long akw_hash(const uint8_t* t, int64_t s, uint32_t len) {
+    unsigned long long h = 0x9E3779B97F4A7C15ull + len;
+    const uint32_t nw = (len + 7u) >> 3;
+#pragma unroll 1
+    for (uint32_t j = 0; j < nw; ++j) {
+        h = (h ^ akw_key_word(t, s, len, j)) * 0xBF58476D1CE4E5B9ull;
+        h = (h << 27) | (h >> 37);
     }
     h ^= h >> 31;
     h *= 0xFF51AFD7ED558CCDull;
@@ -64,11 +78,14 @@ AK_HD unsigned long long akw_hash(const AkWordKey& K) {
 AK_HD unsigned long long akw_want(unsigned long long h, uint32_t len) { return (h & ~0xFFFFull) | ((unsigned long long)len << 8) | AKW_READY; }
 #define AKW_NTOK_MASK 0xF8ull
 
-// -> token count (ids filled) or -1; *free_slot = an empty slot seen on the probe path (or -1)
-AK_HD int akw_lookup(const AkWordCache& C, unsigned long long h, unsigned long long want, const AkWordKey& K, int32_t* ids,
-                     long long* free_slot) {
+// -> entry index of the word (its ids are then read by the caller), or -1; *free_slot = an empty slot seen on the probe
+// path (or -1)
+AK_HD long long akw_find(const AkWordCache& C, unsigned long long h, unsigned long long want, const uint8_t* t, int64_t s,
+                         uint32_t len, long long* free_slot) {
     const unsigned long long mask = (1ull << C.bits) - 1ull;
+    const uint32_t nw = (len + 7u) >> 3;
     *free_slot = -1;
+#pragma unroll 1
     for (int p = 0; p < AKW_PROBES; ++p) {
         const unsigned long long slot = (h + (unsigned long long)p) & mask;
         const unsigned long long* e = C.e + slot * AKW_ENTRY;
@@ -76,26 +93,16 @@ AK_HD int akw_lookup(const AkWordCache& C, unsigned long long h, unsigned long l
         if (tag == 0ull) { *free_slot = (long long)slot; return -1; }
         if ((tag & ~AKW_NTOK_MASK) != want) continue;
         bool same = true;
-#pragma unroll
-        for (int j = 0; j < AKW_KW; ++j)
-            if ((uint32_t)j < K.nw && akw_ld(e + 1 + j) != K.k[j]) same = false;
-        if (!same) continue;
-        const int n = (int)((tag & AKW_NTOK_MASK) >> 3);
-#pragma unroll
-        for (int i = 0; i < AKW_MAXTOK; i += 2) {
-            if (i < n) {
-                const unsigned long long v = akw_ld(e + 8 + (i >> 1));
-                ids[i] = (int32_t)(uint32_t)v;
-                ids[i + 1] = (int32_t)(uint32_t)(v >> 32);
-            }
-        }
-        return n;
+#pragma unroll 1
+        for (uint32_t j = 0; j < nw; ++j)
+            if (akw_ld(e + 1 + j) != akw_key_word(t, s, len, j)) { same = false; break; }
+        if (same) return (long long)slot;
     }
     return -1;
 }
 
-AK_HD void akw_insert(const AkWordCache& C, long long slot, unsigned long long want, const AkWordKey& K, const int32_t* ids,
-                      int n) {
+AK_HD void akw_insert(const AkWordCache& C, long long slot, unsigned long long want, const uint8_t* t, int64_t s, uint32_t len,
+                      const int32_t* ids, int n) {
     unsigned long long* e = C.e + (unsigned long long)slot * AKW_ENTRY;
 #ifdef __CUDA_ARCH__
     if (atomicCAS(e, 0ull, AKW_BUSY) != 0ull) return;
@@ -103,9 +110,8 @@ AK_HD void akw_insert(const AkWordCache& C, long long slot, unsigned long long w
     if (*e != 0ull) return;
     *e = AKW_BUSY;
 #endif
-#pragma unroll
-    for (int j = 0; j < AKW_KW; ++j)
-        if ((uint32_t)j < K.nw) akw_st(e + 1 + j, K.k[j]);
+    const uint32_t nw = (len + 7u) >> 3;
+    for (uint32_t j = 0; j < nw; ++j) akw_st(e + 1 + j, akw_key_word(t, s, len, j));
     for (int i = 0; i < n; i += 2) {
         unsigned long long v = (uint32_t)ids[i];
         if (i + 1 < n) v |= (unsigned long long)(uint32_t)ids[i + 1] << 32;
@@ -117,54 +123,24 @@ AK_HD void akw_insert(const AkWordCache& C, long long slot, unsigned long long w
     akw_st(e, want | ((unsigned long long)n << 3));
 }
 
-// the word's bytes [s, s + len), len <= AKW_MAXLEN, with 8-byte aligned loads (the allocation of `t` must reach
-// the next 8-byte boundary after its last byte, which holds for every CUDA allocation)
-AK_HD void akw_key(const uint8_t* t, int64_t s, uint32_t len, AkWordKey& K) {
-    K.len = len;
-    K.nw = (len + 7u) >> 3;
-#ifdef __CUDA_ARCH__
-    const uintptr_t a = (uintptr_t)(t + s);
-    const unsigned long long* base = (const unsigned long long*)(a & ~(uintptr_t)7);
-    const uint32_t sh = (uint32_t)(a & 7u) * 8u;
-    const uint32_t span = (uint32_t)(a & 7u) + len;           // bytes from base to the word end
-    unsigned long long lo = __ldg(base);
-#pragma unroll
-    for (int j = 0; j < AKW_KW; ++j) {
-        if ((uint32_t)j < K.nw) {
-            unsigned long long hi = 0ull;
-            if (span > 8u * (uint32_t)(j + 1)) hi = __ldg(base + j + 1);
-            unsigned long long v = sh ? ((lo >> sh) | (hi << (64u - sh))) : lo;
-            const uint32_t nb = len - 8u * (uint32_t)j;
-            if (nb < 8u) v &= (1ull << (8u * nb)) - 1ull;
-            K.k[j] = v;
-            lo = hi;
-        } else {
-            K.k[j] = 0ull;
-        }
-    }
-#else
-#pragma unroll
-    for (int j = 0; j < AKW_KW; ++j) K.k[j] = 0ull;
-    for (uint32_t i = 0; i < len; ++i) K.k[i >> 3] |= (unsigned long long)t[s + i] << (8u * (i & 7u));
-#endif
-}
-
 // encode the word [s, e) of pre-tokenizer class k into `sink`: cache hit, or the merge loop + insert
 AK_HD_NOINLINE void akb_word(const AkBpeDev& M, const AkTables& T, const AkWordCache& C, const uint8_t* t, int64_t s,
                              int64_t e, uint32_t k, AkIdSink& sink, const AkPool& pool, uint32_t& status) {
     const uint32_t len = (uint32_t)(e - s);
     if (e - s <= AKW_MAXLEN && C.e) {
-        AkWordKey K;
-        akw_key(t, s, len, K);
-        const unsigned long long h = akw_hash(K);
+        const unsigned long long h = akw_hash(t, s, len);
         const unsigned long long want = akw_want(h, len);
-        int32_t ids[AKW_MAXTOK];
         long long slot;
-        const int n = akw_lookup(C, h, want, K, ids, &slot);
-        if (n >= 0) {
-#pragma unroll
-            for (int i = 0; i < AKW_MAXTOK; ++i)
-                if (i < n) ak_id_put(sink, ids[i]);
+        const long long hit = akw_find(C, h, want, t, s, len, &slot);
+        if (hit >= 0) {
+            const unsigned long long* en = C.e + (unsigned long long)hit * AKW_ENTRY;
+            const int n = (int)((akw_ld(en) & AKW_NTOK_MASK) >> 3);
+#pragma unroll 1
+            for (int i = 0; i < n; i += 2) {
+                const unsigned long long v = akw_ld(en + 8 + (i >> 1));
+                ak_id_put(sink, (int32_t)(uint32_t)v);
+                if (i + 1 < n) ak_id_put(sink, (int32_t)(uint32_t)(v >> 32));
+            }
             return;
         }
         // miss: exact merge loop into a private list, then publish
@@ -181,7 +157,7 @@ AK_HD_NOINLINE void akb_word(const AkBpeDev& M, const AkTables& T, const AkWordC
         ak_bpe_word(M, T, t, s, e, k, local, pool, status);
         if (local.cnt <= AKW_MAXTOK) {
             for (int i = 0; i < local.cnt; ++i) ak_id_put(sink, tmp[i]);
-            if (slot >= 0) akw_insert(C, slot, want, K, tmp, local.cnt);
+            if (slot >= 0) akw_insert(C, slot, want, t, s, len, tmp, local.cnt);
             return;
         }
     }
@@ -209,42 +185,54 @@ struct AkBChunk {
 
 AK_HD uint32_t akb_byte(const AkBChunk& c, int i) { return (c.w[i >> 2] >> ((i & 3) * 8)) & 0xFFu; }
 
+// The loop over the 16 byte positions is rolled over the 4 words (4 bytes unrolled inside): a fully unrolled body is
+// ~4x the code, and these kernels are instruction-cache bound as soon as their warps drift apart.
 AK_HD void akb_phase_a(const AkTables& T, const uint32_t* lut, AkBChunk& c) {
     uint32_t lead = 0, bnd = c.rows, cls = 0, flags = 0, trb = 0;
     uint32_t prev_w = AKF_NONE, prev_cls = 2;
     bool have_prev = false, first_seen = false;
     uint32_t first_pos = 32, first_w = AKF_NONE, last_w = AKF_NONE, last_cls = 2;
-#pragma unroll
-    for (int i = 0; i < 16; ++i) {
-        const bool row_here = (c.rows >> i) & 1u;
-        if (row_here) { have_prev = false; prev_cls = 2; }
-        const uint32_t b = akb_byte(c, i);
-        if (!((c.own >> i) & 1u) || (b & 0xC0u) == 0x80u) continue;
-        const uint32_t b1 = akb_byte(c, i + 1) & 0x3Fu, b2 = akb_byte(c, i + 2) & 0x3Fu, b3 = akb_byte(c, i + 3) & 0x3Fu;
-        uint32_t cp;
-        if (b < 0x80u) cp = b;
-        else if (b < 0xE0u) cp = ((b & 0x1Fu) << 6) | b1;
-        else if (b < 0xF0u) cp = ((b & 0x0Fu) << 12) | (b1 << 6) | b2;
-        else cp = ((b & 0x07u) << 18) | (b1 << 12) | (b2 << 6) | b3;
-        const uint32_t w = akf_props(T, lut, cp);
-        const uint32_t k = AK_HFCLASS(w);
-        lead |= 1u << i;
-        cls |= k << (2 * i);
-        if (!AK_ALLOW(w)) flags |= AKB_ALPHABET;
-        if (!first_seen && !row_here) {
-            first_pos = (uint32_t)i;
-            first_w = w;
-            if (AK_QC(w) == 1u) { flags |= AKF_TROUBLE; trb |= 1u << i; }
-        } else {
-            if (!have_prev ? (AK_QC(w) != 0u) : akf_trouble_after(prev_w, w)) { flags |= AKF_TROUBLE; trb |= 1u << i; }
-            if (row_here || k != prev_cls) bnd |= 1u << i;
+#pragma unroll 1
+    for (int k = 0; k < 4; ++k) {
+        // the word's 4 bytes and the 3 that follow, as one 64-bit window
+        const uint32_t wlo = k == 0 ? c.w[0] : k == 1 ? c.w[1] : k == 2 ? c.w[2] : c.w[3];
+        const uint32_t whi = k == 0 ? c.w[1] : k == 1 ? c.w[2] : k == 2 ? c.w[3] : c.w[4];
+        const unsigned long long win = ((unsigned long long)whi << 32) | wlo;
+        const uint32_t rows4 = (c.rows >> (4 * k)) & 15u, own4 = (c.own >> (4 * k)) & 15u;
+#pragma unroll 1
+        for (int j = 0; j < 4; ++j) {
+            const int i = 4 * k + j;
+            const bool row_here = (rows4 >> j) & 1u;
+            if (row_here) { have_prev = false; prev_cls = 2; }
+            const uint32_t v = (uint32_t)(win >> (8 * j));
+            const uint32_t b = v & 0xFFu;
+            if (!((own4 >> j) & 1u) || (b & 0xC0u) == 0x80u) continue;
+            const uint32_t b1 = (v >> 8) & 0x3Fu, b2 = (v >> 16) & 0x3Fu, b3 = (v >> 24) & 0x3Fu;
+            uint32_t cp;
+            if (b < 0x80u) cp = b;
+            else if (b < 0xE0u) cp = ((b & 0x1Fu) << 6) | b1;
+            else if (b < 0xF0u) cp = ((b & 0x0Fu) << 12) | (b1 << 6) | b2;
+            else cp = ((b & 0x07u) << 18) | (b1 << 12) | (b2 << 6) | b3;
+            const uint32_t w = akf_props(T, lut, cp);
+            const uint32_t kc = AK_HFCLASS(w);
+            lead |= 1u << i;
+            cls |= kc << (2 * i);
+            if (!AK_ALLOW(w)) flags |= AKB_ALPHABET;
+            if (!first_seen && !row_here) {
+                first_pos = (uint32_t)i;
+                first_w = w;
+                if (AK_QC(w) == 1u) { flags |= AKF_TROUBLE; trb |= 1u << i; }
+            } else {
+                if (!have_prev ? (AK_QC(w) != 0u) : akf_trouble_after(prev_w, w)) { flags |= AKF_TROUBLE; trb |= 1u << i; }
+                if (row_here || kc != prev_cls) bnd |= 1u << i;
+            }
+            first_seen = true;
+            prev_w = w;
+            prev_cls = kc;
+            have_prev = true;
+            last_w = w;
+            last_cls = kc;
         }
-        first_seen = true;
-        prev_w = w;
-        prev_cls = k;
-        have_prev = true;
-        last_w = w;
-        last_cls = k;
     }
     c.lead = lead;
     c.bnd = bnd;
@@ -327,11 +315,19 @@ struct AkBLaneCtx {
 AK_HD_NOINLINE void akb_lane_emit(const AkBLaneCtx& X, const AkBChunk& c, uint32_t next_bnd, int64_t cs, AkIdSink& sink,
                                   int64_t* id_splits, int64_t& row_first, int64_t& row_last, uint32_t& status,
                                   int64_t nr_hint = -1) {
-    uint32_t wstart = 0;
-#pragma unroll
-    for (int i = 0; i < 16; ++i)
-        if (((c.bnd & c.lead) >> i) & 1u)
-            if (((c.cls >> (2 * i)) & 3u) != 2u) wstart |= 1u << i;
+    // word starts = boundaries at owned leads whose class is not "space" (2 = binary 10: high bit set, low bit clear)
+    uint32_t space = 0;
+    {
+        const uint32_t hi = (c.cls >> 1) & 0x55555555u & ~c.cls;      // bit 2i set <=> class at position i is 2
+        // compress the even bits to 16 bits
+        uint32_t x = hi;
+        x = (x | (x >> 1)) & 0x33333333u;
+        x = (x | (x >> 2)) & 0x0F0F0F0Fu;
+        x = (x | (x >> 4)) & 0x00FF00FFu;
+        x = (x | (x >> 8)) & 0x0000FFFFu;
+        space = x;
+    }
+    const uint32_t wstart = c.bnd & c.lead & ~space;
     uint32_t ev = (c.rows | wstart) & 0xFFFFu;
     int64_t nr = nr_hint;       // index of the first row that starts in this chunk, when the caller knows it
     row_first = row_last = nr < 0 ? 0 : nr;

@@ -28,6 +28,7 @@
 #define AK_LOOKBACK_LIMIT 4096          // bytes a span may walk backwards in AKSHAR_MODE_TILES
 #define AK_BPE_STAGE 40                 // ids per thread staged in shared memory (>= AK_SPAN + a few <s> / </s>)
 #define AKB_STAGE 24                    // same, fast kernel (16-byte chunks)
+#define AKW_GROUP 256                   // warp tiles per scan group (one CTA of the sums / copy kernels)
 #define AKS_STAGE 18                    // cluster / run ends per lane staged in shared memory (fast segment kernel)
 #define AK_ROWS_BLOCK 128               // rows per tile for the row-per-thread kernels
 #define AKF_WARPS (AK_BLOCK / 32)
@@ -408,11 +409,18 @@ __global__ void __launch_bounds__(128) ak_nf_slow_kernel(const AkNfSlowArgs A) {
 
 // ---- K1c: exclusive prefix of the tile totals (one CTA; the array has one entry per 3840 bytes of text)
 __global__ void __launch_bounds__(1024) ak_nf_scan_kernel(const int32_t* tile_total, int64_t* tile_base, int n_tiles,
-                                                          int64_t* total_out, AkBatch B, int64_t base0) {
+                                                          int64_t* total_out, AkBatch B, int64_t base0,
+                                                          int64_t bytes_per_entry = AKF_TILE) {
     __shared__ long long ws[33];
     __shared__ long long carry;
     if (!ak_batch_begin(B)) return;
-    if (B.dyn_end) n_tiles = (int)((B.text_end - base0 + AKF_TILE) / AKF_TILE);
+    if (B.dyn_end) {
+        if (bytes_per_entry == AKF_TILE) n_tiles = (int)((B.text_end - base0 + AKF_TILE) / AKF_TILE);
+        else {
+            const int n_wt = (int)((B.text_end - base0 + AKF_WARP_BYTES) / AKF_WARP_BYTES);
+            n_tiles = (n_wt + AKW_GROUP - 1) / AKW_GROUP;
+        }
+    }
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) carry = 0;
     __syncthreads();
@@ -864,9 +872,78 @@ __global__ void __launch_bounds__(AK_BLOCK) ak_sf_copy_kernel(const AkSfArgs A) 
 }
 
 // ------------------------------------------------------------------------------------------------
-// K4a fast: BPE through the word cache (ak_bpe_fast.cuh).  No ordered dependency between tiles: a tile appends its
-// ids to a temporary stream at an atomically reserved offset, a scan of the tile totals gives the final positions,
-// a copy kernel moves every tile's block there and makes the row splits global.
+// Warp tiles.  The fast BPE and segment kernels are warp-autonomous: a warp owns 480 text bytes (30 real lanes +
+// 2 halo lanes), finds the rows that start in them with shuffles, encodes, and appends its output to its CTA's
+// private slice of a temporary stream (cursor in shared memory) -- no CTA barrier and no global atomic on the hot
+// path, so a slow lane (cache miss, long word, slow-lane walker) only delays its own warp.  A scan over the
+// per-warp-tile totals then gives the final positions and a copy kernel moves the blocks.
+// ------------------------------------------------------------------------------------------------
+
+// wrow[k] = first row r in [0, n_rows] with off[r] >= base0 + k * 480 (n_rows + 1 if none); one thread per entry
+__global__ void ak_warp_rows_kernel(AkBatch B, int64_t base0, int n_entries, int64_t* wrow) {
+    if (!ak_batch_begin(B)) return;
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n_entries) return;
+    const int64_t pos = base0 + (int64_t)k * AKF_WARP_BYTES;
+    int64_t r = ak_row_lower_bound(B.off, 0, B.n_rows, pos);
+    if (B.off[r] < pos) r = B.n_rows + 1;
+    wrow[k] = r;
+}
+
+__device__ __forceinline__ int akw_n_tiles(const AkBatch& B, int64_t base0) {
+    return (int)((B.text_end - base0 + AKF_WARP_BYTES) / AKF_WARP_BYTES);      // covers position text_end itself
+}
+
+// each lane's 16-bit row-start mask for its chunk [cs, cs + 16), from the sorted row offsets (no shared memory)
+__device__ __forceinline__ uint32_t akw_lane_rows(const int64_t* off, int64_t n_rows, int64_t r_w0, int64_t ws, int lane) {
+    uint32_t rows = 0;
+    const int64_t lo = ws - 16, hi = ws + AKF_WARP_BYTES + 16;      // positions of lanes 0 .. 31
+    for (int64_t r = r_w0;; r += 32) {                              // rows at or after ws
+        const int64_t mr = r + lane;
+        const int64_t p = mr <= n_rows ? off[mr] : hi;
+        const unsigned m = __ballot_sync(0xFFFFFFFFu, p < hi);
+        const int cnt = __popc(m);                                  // sorted: the in-range rows are a prefix
+        for (int j = 0; j < cnt; ++j) {
+            const int64_t pj = __shfl_sync(0xFFFFFFFFu, p, j);
+            const int rel = (int)(pj - lo);
+            if ((rel >> 4) == lane) rows |= 1u << (rel & 15);
+        }
+        if (cnt < 32) break;
+    }
+    for (int64_t r = r_w0 - 1;; r -= 32) {                          // rows inside the left halo chunk
+        const int64_t mr = r - lane;
+        const int64_t p = mr >= 0 ? off[mr] : lo - 1;
+        const unsigned m = __ballot_sync(0xFFFFFFFFu, p >= lo);
+        const int cnt = __popc(m);
+        if (cnt && lane == 0) {
+            // all of them fall into lane 0's chunk
+        }
+        for (int j = 0; j < cnt; ++j) {
+            const int64_t pj = __shfl_sync(0xFFFFFFFFu, p, j);
+            const int rel = (int)(pj - lo);
+            if ((rel >> 4) == lane) rows |= 1u << (rel & 15);
+        }
+        if (cnt < 32) break;
+    }
+    return rows;
+}
+
+// sums of AKW_GROUP consecutive warp-tile totals
+__global__ void __launch_bounds__(AKW_GROUP) ak_wt_sums_kernel(AkBatch B, int64_t base0, const int32_t* wt_total, int32_t* sums) {
+    __shared__ int ws[33];
+    if (!ak_batch_begin(B)) return;
+    const int n_wt = akw_n_tiles(B, base0);
+    const int n_groups = (n_wt + AKW_GROUP - 1) / AKW_GROUP;
+    for (int gidx = blockIdx.x; gidx < n_groups; gidx += gridDim.x) {
+        const int t = gidx * AKW_GROUP + threadIdx.x;
+        int total;
+        ak_block_exscan<AKW_GROUP>(t < n_wt ? wt_total[t] : 0, ws, total);
+        if (threadIdx.x == 0) sums[gidx] = total;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K4a fast: BPE through the word cache (ak_bpe_fast.cuh), warp tiles
 // ------------------------------------------------------------------------------------------------
 struct AkBfArgs {
     AkBatch B;
@@ -874,77 +951,49 @@ struct AkBfArgs {
     AkBpeDev M;
     AkWordCache C;
     AkPool pool;
-    const int64_t* tile_row;
+    const int64_t* wrow;         // [n_wt + 1]
     int64_t base0;
-    int32_t* temp;               // temporary id stream
-    int64_t temp_cap;
-    unsigned long long* temp_cursor;
-    int32_t* tile_total;
-    int64_t* tile_toff;          // where the tile's block starts in temp
-    int64_t* tile_base;          // exclusive prefix of tile_total (after the scan)
+    int32_t* temp;               // temporary id stream, one private slice per CTA of the encode kernel
+    int64_t slice_cap;
+    int32_t* wt_total;           // [n_wt]
+    int64_t* wt_toff;            // [n_wt] where the warp tile's block starts in temp
+    int32_t* sums;               // [groups] and their exclusive prefix
+    int64_t* sum_base;
     int32_t* ids;
     int64_t id_cap;
     int64_t* id_splits;
     unsigned int* changed;
 };
 
-__device__ __forceinline__ int akb_n_tiles(const AkBatch& B, int64_t base0) {
-    if (!B.dyn_end) return B.n_tiles;
-    return (int)((B.text_begin + *B.dyn_end - base0 + AKF_TILE) / AKF_TILE);
-}
-
 #ifndef AKB_MINB
-#define AKB_MINB 2
+#define AKB_MINB 4
 #endif
 __global__ void __launch_bounds__(AK_BLOCK, AKB_MINB) ak_bf_encode_kernel(const AkBfArgs A) {
     __shared__ uint32_t lut[384];
-    __shared__ uint32_t rowbits[(AKF_TILE + 64) / 32 + 2];
     __shared__ int32_t stage[AKB_STAGE * AK_BLOCK];
-    __shared__ int ws[33];
-    __shared__ long long s_toff;
-    __shared__ uint16_t rowpref[(AKF_TILE + 64) / 32 + 2];
+    __shared__ unsigned int s_cursor;
     AkBatch B = A.B;
     if (!ak_batch_begin(B)) return;
-    B.n_tiles = akb_n_tiles(A.B, A.base0);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int i = tid; i < 384; i += AK_BLOCK)
         lut[i] = i < 128 ? A.T.leaves[((uint32_t)A.T.page_index[0] << 8) | i] : A.T.leaves[((uint32_t)A.T.page_index[9] << 8) | (i - 128)];
-    for (int tile = blockIdx.x; tile < B.n_tiles; tile += gridDim.x) {
-        const int64_t tile_start = A.base0 + (int64_t)tile * AKF_TILE;
-        akf_tile_rows(B, A.tile_row, tile, tile_start, rowbits);
-        const int64_t r0 = A.tile_row[tile], r1 = A.tile_row[tile + 1];
-        if (warp == 0) {
-            // exclusive prefix of the row-start bit counts per bitmap word (a lane's first row index without a search)
-            constexpr int NW = (AKF_TILE + 64) / 32 + 2;
-            int v[4], sum = 0;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const int wi = lane * 4 + k;
-                v[k] = wi < NW ? __popc(rowbits[wi]) : 0;
-                sum += v[k];
-            }
-            int inc = sum;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const int y = __shfl_up_sync(0xFFFFFFFFu, inc, d);
-                if (lane >= d) inc += y;
-            }
-            int run = inc - sum;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const int wi = lane * 4 + k;
-                if (wi < NW) rowpref[wi] = (uint16_t)run;
-                run += v[k];
-            }
-        }
+    if (tid == 0) s_cursor = 0;
+    __syncthreads();
+    const int n_wt = akw_n_tiles(B, A.base0);
+    const int64_t slice = (int64_t)blockIdx.x * A.slice_cap;
+    for (int wt0 = blockIdx.x * AKF_WARPS; wt0 < n_wt; wt0 += gridDim.x * AKF_WARPS) {
+#ifdef AKB_CTA_SYNC
+        // keep the CTA's warps in the same code region (instruction cache)
         __syncthreads();
+#endif
+        const int wt = wt0 + warp;
+        if (wt >= n_wt) continue;
+        const int64_t ws = A.base0 + (int64_t)wt * AKF_WARP_BYTES;
+        const int64_t r_w0 = A.wrow[wt], r_w1 = A.wrow[wt + 1];
         AkBChunk c;
-        const int64_t cs = tile_start + (int64_t)warp * AKF_WARP_BYTES + (int64_t)(lane - 1) * 16;
+        const int64_t cs = ws + (int64_t)(lane - 1) * 16;
         akf_load_lane(B, cs, c);
-        {
-            const int bo = (int)(cs - (tile_start - 16));
-            c.rows = (rowbits[bo >> 5] >> (bo & 31)) & 0xFFFFu;
-        }
+        c.rows = akw_lane_rows(B.off, B.n_rows, r_w0, ws, lane);
         akb_phase_a(A.T, lut, c);
         {
             uint32_t pw = __shfl_up_sync(0xFFFFFFFFu, c.last_w, 1);
@@ -973,6 +1022,24 @@ __global__ void __launch_bounds__(AK_BLOCK, AKB_MINB) ak_bf_encode_kernel(const 
         const int64_t ss = cs < B.text_begin ? B.text_begin : cs;
         const int64_t se = cs + 16 > B.text_end + 1 ? B.text_end + 1 : cs + 16;
         const bool active = real && ss < se;
+        // index of the first row that starts in this lane's chunk = rows before the warp tile + row-start positions in
+        // the real lanes before this one (+ duplicates = empty rows, skipped by the short loop)
+        int64_t nr_hint = -1;
+        {
+            const int mine = real ? __popc(c.rows) : 0;
+            int inc = mine;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int y = __shfl_up_sync(0xFFFFFFFFu, inc, d);
+                if (lane >= d) inc += y;
+            }
+            if (active && c.rows) {
+                int64_t g = r_w0 + (inc - mine);
+                const int64_t p = cs + (__ffs(c.rows) - 1);
+                while (g < B.n_rows && B.off[g] < p) ++g;
+                nr_hint = g;
+            }
+        }
         AkBLaneCtx X;
         X.M = &A.M;
         X.T = &A.T;
@@ -980,8 +1047,8 @@ __global__ void __launch_bounds__(AK_BLOCK, AKB_MINB) ak_bf_encode_kernel(const 
         X.text = B.text;
         X.off = B.off;
         X.n_rows = B.n_rows;
-        X.r_lo = r0 > 0 ? r0 - 1 : 0;
-        X.r_hi = r1 > B.n_rows ? B.n_rows : r1;
+        X.r_lo = r_w0 > 0 ? r_w0 - 1 : 0;
+        X.r_hi = r_w1 > B.n_rows ? B.n_rows : r_w1;
         X.pool = &A.pool;
         AkIdSink sink;
         sink.buf = stage + tid;
@@ -991,72 +1058,85 @@ __global__ void __launch_bounds__(AK_BLOCK, AKB_MINB) ak_bf_encode_kernel(const 
         sink.direct = false;
         sink.gout = A.temp;
         sink.gbase = 0;
-        sink.gcap = A.temp_cap;
+        sink.gcap = 0;
         uint32_t st = 0;
         int64_t row_first = 0, row_last = 0;
-        int64_t nr_hint = -1;
-        if (active && c.rows) {
-            // rows that start in [tile_start, p) = set bits in the bitmap between them; duplicates (empty rows) are
-            // skipped by the short loop
-            const int b = (int)(cs - (tile_start - 16)) + (__ffs(c.rows) - 1);
-            const int before = (int)rowpref[b >> 5] + __popc(rowbits[b >> 5] & ((1u << (b & 31)) - 1u)) - (int)__popc(rowbits[0] & 0xFFFFu);
-            int64_t g = r0 + before;
-            const int64_t p = cs + (__ffs(c.rows) - 1);
-            while (g < B.n_rows && B.off[g] < p) ++g;
-            nr_hint = g;
-        }
         if (active) {
             if (c.flags & AKB_ALPHABET) st |= AK_ST_ALPHABET;
             if ((c.flags & AKF_TROUBLE) && akb_chunk_changes(X, c, cs, AK_LOOKBACK_LIMIT, st)) atomicOr(A.changed, 1u);
             akb_lane_emit(X, c, next_bnd, cs, sink, A.id_splits, row_first, row_last, st, nr_hint);
         }
+        __syncwarp();
         const int cnt = sink.cnt;
-        int total;
-        const int pre = ak_block_exscan<AK_BLOCK>(cnt, ws, total);
-        if (tid == 0) {
-            const long long toff = (long long)atomicAdd(A.temp_cursor, (unsigned long long)total);
-            s_toff = toff;
-            A.tile_total[tile] = total;
-            A.tile_toff[tile] = toff;
-            if (toff + total > A.temp_cap) st |= AK_ST_OVERFLOW;
+        int inc = cnt;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int y = __shfl_up_sync(0xFFFFFFFFu, inc, d);
+            if (lane >= d) inc += y;
         }
-        __syncthreads();
-        const int64_t tbase = s_toff + pre;
+        const int total = __shfl_sync(0xFFFFFFFFu, inc, 31);
+        const int pre = inc - cnt;
+        unsigned int toff = 0;
+        if (lane == 0) toff = atomicAdd(&s_cursor, (unsigned int)total);
+        toff = __shfl_sync(0xFFFFFFFFu, toff, 0);
+        const bool fits = (int64_t)toff + total <= A.slice_cap;
+        if (lane == 0) {
+            A.wt_total[wt] = total;
+            A.wt_toff[wt] = slice + toff;
+            if (!fits) st |= AK_ST_OVERFLOW;
+        }
         if (active) {
-            for (int64_t r = row_first; r < row_last; ++r) A.id_splits[r] += pre;      // lane-relative -> tile-relative
-            if (cnt <= AKB_STAGE) {
-                for (int i = 0; i < cnt; ++i)
-                    if (tbase + i < A.temp_cap) A.temp[tbase + i] = stage[i * AK_BLOCK + tid];
-            } else {
-                AkIdSink s2 = sink;
-                s2.cnt = 0;
-                s2.direct = true;
-                s2.gbase = tbase;
-                uint32_t st2 = 0;
-                int64_t a, b;
-                akb_lane_emit(X, c, next_bnd, cs, s2, nullptr, a, b, st2, nr_hint);
+            for (int64_t r = row_first; r < row_last; ++r) A.id_splits[r] += pre;      // lane-relative -> warp-tile-relative
+            if (fits) {
+                int32_t* dst = A.temp + slice + toff + pre;
+                if (cnt <= AKB_STAGE) {
+                    for (int i = 0; i < cnt; ++i) dst[i] = stage[i * AK_BLOCK + tid];
+                } else {
+                    AkIdSink s2 = sink;
+                    s2.cnt = 0;
+                    s2.direct = true;
+                    s2.gout = dst;
+                    s2.gbase = 0;
+                    s2.gcap = cnt;
+                    uint32_t st2 = 0;
+                    int64_t a, b;
+                    akb_lane_emit(X, c, next_bnd, cs, s2, nullptr, a, b, st2, nr_hint);
+                }
             }
         }
+        __syncwarp();
         ak_raise(B.result, st);
     }
 }
 
-// copy every tile's block to its final place and make the row splits global
-__global__ void __launch_bounds__(AK_BLOCK) ak_bf_copy_kernel(const AkBfArgs A) {
+// move every warp tile's block to its final place and make the row splits global
+__global__ void __launch_bounds__(AKW_GROUP) ak_bf_copy_kernel(const AkBfArgs A) {
+    __shared__ int ws[33];
+    __shared__ long long s_base[AKW_GROUP];
     AkBatch B = A.B;
     if (!ak_batch_begin(B)) return;
-    B.n_tiles = akb_n_tiles(A.B, A.base0);
-    const int tid = threadIdx.x;
-    for (int tile = blockIdx.x; tile < B.n_tiles; tile += gridDim.x) {
-        const int total = A.tile_total[tile];
-        const int64_t toff = A.tile_toff[tile], base = A.tile_base[tile];
-        const bool ok = toff + total <= A.temp_cap;
-        if (base + total > A.id_cap && tid == 0 && total > 0) ak_raise(B.result, AK_ST_OVERFLOW);
-        if (ok)
-            for (int i = tid; i < total; i += AK_BLOCK)
-                if (base + i < A.id_cap) A.ids[base + i] = A.temp[toff + i];
-        const int64_t r0 = A.tile_row[tile], r1 = A.tile_row[tile + 1];
-        for (int64_t r = r0 + tid; r < r1 && r <= B.n_rows; r += AK_BLOCK) A.id_splits[r] += base;
+    const int n_wt = akw_n_tiles(B, A.base0);
+    const int n_groups = (n_wt + AKW_GROUP - 1) / AKW_GROUP;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int gidx = blockIdx.x; gidx < n_groups; gidx += gridDim.x) {
+        const int t = gidx * AKW_GROUP + tid;
+        const int mine = t < n_wt ? A.wt_total[t] : 0;
+        int total;
+        const int pre = ak_block_exscan<AKW_GROUP>(mine, ws, total);
+        s_base[tid] = A.sum_base[gidx] + pre;
+        __syncthreads();
+        // each warp moves the blocks of its 32 warp tiles, one at a time, coalesced
+        for (int j = 0; j < 32; ++j) {
+            const int tj = gidx * AKW_GROUP + warp * 32 + j;
+            if (tj >= n_wt) break;
+            const int n = A.wt_total[tj];
+            const int64_t src = A.wt_toff[tj], dst = s_base[warp * 32 + j];
+            if (dst + n > A.id_cap) { if (lane == 0 && n > 0) ak_raise(B.result, AK_ST_OVERFLOW); }
+            else for (int i = lane; i < n; i += 32) A.ids[dst + i] = A.temp[src + i];
+            const int64_t r0 = A.wrow[tj], r1 = A.wrow[tj + 1];
+            for (int64_t r = r0 + lane; r < r1 && r <= B.n_rows; r += 32) A.id_splits[r] += dst;
+        }
+        __syncthreads();
     }
 }
 
@@ -1350,7 +1430,10 @@ static AkWsLayout ak_ws_layout(int64_t n_bytes, int64_t n_rows) {
     L.nfc_off = L.nfc_text + ak_align((size_t)L.nfc_cap);
     L.pool = L.nfc_off + ak_align(8 * (size_t)(n_rows + 1));
     L.bf_tiles = L.pool + ak_align(4 * ak_pool_ints(n_bytes));
-    L.bf_temp = L.bf_tiles + ak_align(tiles * 4) + ak_align(tiles * 8) + ak_align((tiles + 1) * 8);
+    {
+        const size_t nwt = tiles * AKF_WARPS + 8, ng = nwt / AKW_GROUP + 2;
+        L.bf_temp = L.bf_tiles + ak_align((nwt + 2) * 8) + ak_align(nwt * 4) + ak_align(nwt * 8) + ak_align(ng * 4) + ak_align((ng + 1) * 8);
+    }
     L.bf_temp_cap = n_bytes / 2 + 2 * n_rows + 1024;
     size_t bpe = (L.bf_temp + ak_align(4 * (size_t)L.bf_temp_cap)) - at;
     // fast normalize: per-lane info words, tile totals / bases, slow work list
@@ -1727,13 +1810,11 @@ int akshar_load_bpe_json(akshar_ctx* ctx, const char* json, size_t len) {
             sink.gcap = 0;
             ak_bpe_word(hm, ht, tb, 0, n, k, sink, hp, st);
             if (st || sink.cnt > AKW_MAXTOK) continue;
-            AkWordKey K;
-            akw_key(tb, 0, (uint32_t)n, K);
-            const unsigned long long hh = akw_hash(K);
+            const unsigned long long hh = akw_hash(tb, 0, (uint32_t)n);
             const unsigned long long want = akw_want(hh, (uint32_t)n);
-            int32_t got[AKW_MAXTOK];
             long long slot;
-            if (akw_lookup(hc, hh, want, K, got, &slot) < 0 && slot >= 0) akw_insert(hc, slot, want, K, out_ids, sink.cnt);
+            if (akw_find(hc, hh, want, tb, 0, (uint32_t)n, &slot) < 0 && slot >= 0)
+                akw_insert(hc, slot, want, tb, 0, (uint32_t)n, out_ids, sink.cnt);
         }
         const unsigned long long* dimg = nullptr;
         if ((rc = ak_upload<unsigned long long>(ctx, ctx->bpe_allocs, img.data(), img.size(), &dimg))) return rc;
@@ -1841,34 +1922,35 @@ static int ak_run_bpe(akshar_ctx* ctx, AkCall& C, const AkBatch& B, int64_t max_
         F.C = ctx->wc;
         F.pool = pool;
         F.base0 = B.text_begin - (int64_t)(((uintptr_t)B.text + (uintptr_t)B.text_begin) & 15u);
-        const int nt_ub = B.dyn_end ? (int)((max_bytes - F.base0 + AKF_TILE) / AKF_TILE) : (int)((B.text_end - F.base0 + AKF_TILE) / AKF_TILE);
-        F.B.n_tiles = nt_ub;
-        int64_t* tile_row = (int64_t*)(C.ws + C.L.tile_row);
-        F.tile_row = tile_row;
+        const int64_t span = (B.dyn_end ? max_bytes : B.text_end) - F.base0;
+        const int nwt_ub = (int)((span + AKF_WARP_BYTES) / AKF_WARP_BYTES);
+        const int ngroups_ub = (nwt_ub + AKW_GROUP - 1) / AKW_GROUP;
         char* wp = C.ws + C.L.bf_tiles;
-        F.tile_total = (int32_t*)wp;                 wp += ak_align(tiles * 4);
-        F.tile_toff = (int64_t*)wp;                  wp += ak_align(tiles * 8);
-        F.tile_base = (int64_t*)wp;
-        F.temp = (int32_t*)(C.ws + C.L.bf_temp);
-        F.temp_cap = (int64_t)((C.ws_bytes - C.L.bf_temp) / 4);      // a larger workspace = a larger temporary stream
-        F.temp_cursor = (unsigned long long*)(C.ws + 80);
+        F.wrow = (int64_t*)wp;                       wp += ak_align(((size_t)nwt_ub + 2) * 8);
+        F.wt_total = (int32_t*)wp;                   wp += ak_align((size_t)nwt_ub * 4);
+        F.wt_toff = (int64_t*)wp;                    wp += ak_align((size_t)nwt_ub * 8);
+        F.sums = (int32_t*)wp;                       wp += ak_align((size_t)ngroups_ub * 4);
+        F.sum_base = (int64_t*)wp;                   wp += ak_align(((size_t)ngroups_ub + 1) * 8);
+        F.temp = (int32_t*)wp;
+        const int grid = ak_grid(ctx, ctx->occ_bf, (nwt_ub + AKF_WARPS - 1) / AKF_WARPS);
+        F.slice_cap = (int64_t)((C.ws_bytes - (size_t)(wp - C.ws)) / 4 / (size_t)grid);      // a larger workspace = larger slices
         F.ids = d_ids;
         F.id_cap = id_capacity;
         F.id_splits = d_id_splits;
         F.changed = changed;
         AK_CUDA(ctx, cudaMemcpyAsync(ctx->wc.e, ctx->wc_image, ctx->wc_bytes, cudaMemcpyDeviceToDevice, C.stream));
-        const int entries = nt_ub + 1;
-        ak_tile_rows_kernel<<<(entries + 255) / 256, 256, 0, C.stream>>>(B.off, B.n_rows, F.base0, entries, tile_row, B.run_if,
-                                                                        nullptr, B.text_begin);
-        if ((rc = ak_after_launch(ctx, "bpe-tile-rows"))) return rc;
+        ak_warp_rows_kernel<<<(nwt_ub + 1 + 255) / 256, 256, 0, C.stream>>>(B, F.base0, nwt_ub + 1, (int64_t*)F.wrow);
+        if ((rc = ak_after_launch(ctx, "bpe-warp-rows"))) return rc;
         {
             AkTimed tm(ctx, AKSHAR_TIMER_BPE_ENCODE, C.stream);
-            ak_bf_encode_kernel<<<ak_grid(ctx, ctx->occ_bf, nt_ub), AK_BLOCK, 0, C.stream>>>(F);
+            ak_bf_encode_kernel<<<grid, AK_BLOCK, 0, C.stream>>>(F);
         }
         if ((rc = ak_after_launch(ctx, "bpe-fast"))) return rc;
-        ak_nf_scan_kernel<<<1, 1024, 0, C.stream>>>(F.tile_total, F.tile_base, nt_ub, B.totals, B, F.base0);
+        ak_wt_sums_kernel<<<ak_grid(ctx, 8, ngroups_ub), AKW_GROUP, 0, C.stream>>>(B, F.base0, F.wt_total, F.sums);
+        if ((rc = ak_after_launch(ctx, "bpe-sums"))) return rc;
+        ak_nf_scan_kernel<<<1, 1024, 0, C.stream>>>(F.sums, F.sum_base, ngroups_ub, B.totals, B, F.base0, AKF_WARP_BYTES * AKW_GROUP);
         if ((rc = ak_after_launch(ctx, "bpe-scan"))) return rc;
-        ak_bf_copy_kernel<<<ak_grid(ctx, 8, nt_ub), AK_BLOCK, 0, C.stream>>>(F);
+        ak_bf_copy_kernel<<<ak_grid(ctx, 8, ngroups_ub), AKW_GROUP, 0, C.stream>>>(F);
         if ((rc = ak_after_launch(ctx, "bpe-copy"))) return rc;
     } else {
         ak_bpe_kernel<<<ak_grid(ctx, ctx->occ_bpe, bpe_tiles), AK_BLOCK, 0, C.stream>>>(A);
