@@ -28,6 +28,7 @@
 #define AK_LOOKBACK_LIMIT 4096          // bytes a span may walk backwards in AKSHAR_MODE_TILES
 #define AK_BPE_STAGE 40                 // ids per thread staged in shared memory (>= AK_SPAN + a few <s> / </s>)
 #define AKB_STAGE 24                    // same, fast kernel (16-byte chunks)
+#define AKB_EVCAP 512                   // events (row starts + word starts) per warp tile kept in shared memory
 #define AKW_GROUP 256                   // warp tiles per scan group (one CTA of the sums / copy kernels)
 #define AKS_STAGE 18                    // cluster / run ends per lane staged in shared memory (fast segment kernel)
 #define AK_ROWS_BLOCK 128               // rows per tile for the row-per-thread kernels
@@ -970,7 +971,9 @@ struct AkBfArgs {
 #endif
 __global__ void __launch_bounds__(AK_BLOCK, AKB_MINB) ak_bf_encode_kernel(const AkBfArgs A) {
     __shared__ uint32_t lut[384];
-    __shared__ int32_t stage[AKB_STAGE * AK_BLOCK];
+    __shared__ uint32_t s_ev[AKB_EVCAP * AKF_WARPS];       // per warp: the tile's events (row starts, word starts)
+    __shared__ uint32_t s_res[AKB_EVCAP * AKF_WARPS];      // per event: cache entry + token count
+    __shared__ uint16_t s_eoff[AKB_EVCAP * AKF_WARPS];     // per event: token offset inside the warp tile's block
     __shared__ unsigned int s_cursor;
     AkBatch B = A.B;
     if (!ak_batch_begin(B)) return;
@@ -1022,24 +1025,6 @@ __global__ void __launch_bounds__(AK_BLOCK, AKB_MINB) ak_bf_encode_kernel(const 
         const int64_t ss = cs < B.text_begin ? B.text_begin : cs;
         const int64_t se = cs + 16 > B.text_end + 1 ? B.text_end + 1 : cs + 16;
         const bool active = real && ss < se;
-        // index of the first row that starts in this lane's chunk = rows before the warp tile + row-start positions in
-        // the real lanes before this one (+ duplicates = empty rows, skipped by the short loop)
-        int64_t nr_hint = -1;
-        {
-            const int mine = real ? __popc(c.rows) : 0;
-            int inc = mine;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const int y = __shfl_up_sync(0xFFFFFFFFu, inc, d);
-                if (lane >= d) inc += y;
-            }
-            if (active && c.rows) {
-                int64_t g = r_w0 + (inc - mine);
-                const int64_t p = cs + (__ffs(c.rows) - 1);
-                while (g < B.n_rows && B.off[g] < p) ++g;
-                nr_hint = g;
-            }
-        }
         AkBLaneCtx X;
         X.M = &A.M;
         X.T = &A.T;
@@ -1050,52 +1035,222 @@ __global__ void __launch_bounds__(AK_BLOCK, AKB_MINB) ak_bf_encode_kernel(const 
         X.r_lo = r_w0 > 0 ? r_w0 - 1 : 0;
         X.r_hi = r_w1 > B.n_rows ? B.n_rows : r_w1;
         X.pool = &A.pool;
-        AkIdSink sink;
-        sink.buf = stage + tid;
-        sink.cap = AKB_STAGE;
-        sink.stride = AK_BLOCK;
-        sink.cnt = 0;
-        sink.direct = false;
-        sink.gout = A.temp;
-        sink.gbase = 0;
-        sink.gcap = 0;
         uint32_t st = 0;
-        int64_t row_first = 0, row_last = 0;
         if (active) {
             if (c.flags & AKB_ALPHABET) st |= AK_ST_ALPHABET;
             if ((c.flags & AKF_TROUBLE) && akb_chunk_changes(X, c, cs, AK_LOOKBACK_LIMIT, st)) atomicOr(A.changed, 1u);
-            akb_lane_emit(X, c, next_bnd, cs, sink, A.id_splits, row_first, row_last, st, nr_hint);
         }
-        __syncwarp();
-        const int cnt = sink.cnt;
-        int inc = cnt;
+        // ---- the warp tile's EVENT LIST: row starts and word starts in position order, so that the words can be
+        // encoded one per lane, 32 at a time, whatever chunk they came from
+        uint32_t wstart = 0;
+        if (active) {
+            const uint32_t hi = (c.cls >> 1) & 0x55555555u & ~c.cls;      // bit 2i set <=> class at byte i is 2 (space)
+            uint32_t x = hi;
+            x = (x | (x >> 1)) & 0x33333333u;
+            x = (x | (x >> 2)) & 0x0F0F0F0Fu;
+            x = (x | (x >> 4)) & 0x00FF00FFu;
+            x = (x | (x >> 8)) & 0x0000FFFFu;
+            wstart = c.bnd & c.lead & ~x;
+        }
+        const uint32_t rowsm = active ? (c.rows & 0xFFFFu) : 0u;
+        const int n_row_ev = __popc(rowsm), n_ev = n_row_ev + __popc(wstart);
+        int e_inc = n_ev, r_inc = n_row_ev;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
-            const int y = __shfl_up_sync(0xFFFFFFFFu, inc, d);
-            if (lane >= d) inc += y;
+            const int y = __shfl_up_sync(0xFFFFFFFFu, e_inc, d);
+            const int z = __shfl_up_sync(0xFFFFFFFFu, r_inc, d);
+            if (lane >= d) { e_inc += y; r_inc += z; }
         }
-        const int total = __shfl_sync(0xFFFFFFFFu, inc, 31);
-        const int pre = inc - cnt;
-        unsigned int toff = 0;
-        if (lane == 0) toff = atomicAdd(&s_cursor, (unsigned int)total);
-        toff = __shfl_sync(0xFFFFFFFFu, toff, 0);
-        const bool fits = (int64_t)toff + total <= A.slice_cap;
-        if (lane == 0) {
-            A.wt_total[wt] = total;
-            A.wt_toff[wt] = slice + toff;
-            if (!fits) st |= AK_ST_OVERFLOW;
+        const int E = __shfl_sync(0xFFFFFFFFu, e_inc, 31);
+        uint32_t* ev = s_ev + warp * AKB_EVCAP;
+        uint32_t* res = s_res + warp * AKB_EVCAP;
+        uint16_t* eoff = s_eoff + warp * AKB_EVCAP;
+        bool use_list = E <= AKB_EVCAP;
+        int total = 0;
+        if (use_list) {
+            {
+                int k = e_inc - n_ev, rord = r_inc - n_row_ev;
+                uint32_t m = rowsm | wstart;
+                while (m) {
+                    const int i = __ffs(m) - 1;
+                    m &= m - 1u;
+                    const uint32_t pos = (uint32_t)(cs + i - ws);
+                    if ((rowsm >> i) & 1u) ev[k++] = pos | (1u << 9) | ((uint32_t)rord++ << 12);
+                    if ((wstart >> i) & 1u) {
+                        const uint32_t kc = (c.cls >> (2 * i)) & 3u;
+                        const int64_t e = akb_word_end(A.T, B.text, cs, i, kc, c.bnd, next_bnd, B.off, B.n_rows, X.r_lo, X.r_hi);
+                        int64_t len = e - (cs + i);
+                        if (len > 0xFFFFF) len = 0xFFFFF;
+                        ev[k++] = pos | (kc << 10) | ((uint32_t)len << 12);
+                    }
+                }
+            }
+            __syncwarp();
+            // ---- pass 1: tokens per event (cache lookup; a miss runs the merge loop and publishes the word)
+            int running = 0;
+            for (int base = 0; base < E; base += 32) {
+                const int e = base + lane;
+                int n = 0;
+                uint32_t rr = 0;
+                if (e < E) {
+                    const uint32_t v = ev[e];
+                    const int64_t p = ws + (v & 511u);
+                    if (v & (1u << 9)) {
+                        int64_t g = r_w0 + (v >> 12);
+                        while (g < B.n_rows && B.off[g] < p) ++g;
+                        while (g <= B.n_rows && B.off[g] == p) {
+                            if (g > 0 && A.M.eos >= 0) ++n;
+                            if (g < B.n_rows && A.M.bos >= 0) ++n;
+                            ++g;
+                        }
+                        rr = 0x40000000u | (uint32_t)n;
+                    } else {
+                        const uint32_t kc = (v >> 10) & 3u;
+                        uint32_t len = v >> 12;
+                        int64_t we = p + len;
+                        bool direct = true;
+                        if (len <= AKW_MAXLEN && A.C.e) {
+                            const unsigned long long h = akw_hash(B.text, p, len);
+                            const unsigned long long want = akw_want(h, len);
+                            long long slot;
+                            long long hit = akw_find(A.C, h, want, B.text, p, len, &slot);
+                            if (hit < 0) {
+                                int32_t tmp[AKW_MAXTOK + 1];
+                                AkIdSink local;
+                                local.buf = tmp; local.cap = AKW_MAXTOK + 1; local.stride = 1; local.cnt = 0; local.direct = false;
+                                local.gout = nullptr; local.gbase = 0; local.gcap = 0;
+                                ak_bpe_word(A.M, A.T, B.text, p, we, kc, local, A.pool, st);
+                                n = local.cnt;
+                                if (n <= AKW_MAXTOK && slot >= 0) {
+                                    akw_insert(A.C, slot, want, B.text, p, len, tmp, n);
+                                    hit = akw_find(A.C, h, want, B.text, p, len, &slot);     // ours, or the same word by another lane
+                                }
+                            }
+                            if (hit >= 0) {
+                                n = (int)((akw_ld(A.C.e + (unsigned long long)hit * AKW_ENTRY) & AKW_NTOK_MASK) >> 3);
+                                rr = ((uint32_t)hit << 5) | (uint32_t)n;
+                                direct = false;
+                            }
+                        }
+                        if (direct) {
+                            if (len == 0xFFFFFu) {      // clamped: find the real end again
+                                we = akb_word_end(A.T, B.text, p, 0, kc, 0u, 0u, B.off, B.n_rows, X.r_lo, X.r_hi);
+                            }
+                            AkIdSink cntsink;
+                            cntsink.buf = nullptr; cntsink.cap = 0; cntsink.stride = 1; cntsink.cnt = 0; cntsink.direct = false;
+                            cntsink.gout = nullptr; cntsink.gbase = 0; cntsink.gcap = 0;
+                            ak_bpe_word(A.M, A.T, B.text, p, we, kc, cntsink, A.pool, st);
+                            n = cntsink.cnt;
+                            rr = 0x80000000u | (uint32_t)n;
+                        }
+                    }
+                }
+                int inc = n;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const int y = __shfl_up_sync(0xFFFFFFFFu, inc, d);
+                    if (lane >= d) inc += y;
+                }
+                if (e < E) {
+                    res[e] = rr;
+                    eoff[e] = (uint16_t)(running + inc - n);
+                }
+                running += __shfl_sync(0xFFFFFFFFu, inc, 31);
+            }
+            total = running;
+            if (total >= 65536) use_list = false;      // offsets are 16-bit (thousands of empty rows at one position)
         }
-        if (active) {
-            for (int64_t r = row_first; r < row_last; ++r) A.id_splits[r] += pre;      // lane-relative -> warp-tile-relative
-            if (fits) {
-                int32_t* dst = A.temp + slice + toff + pre;
-                if (cnt <= AKB_STAGE) {
-                    for (int i = 0; i < cnt; ++i) dst[i] = stage[i * AK_BLOCK + tid];
-                } else {
+        if (use_list) {
+            unsigned int toff = 0;
+            if (lane == 0) toff = atomicAdd(&s_cursor, (unsigned int)total);
+            toff = __shfl_sync(0xFFFFFFFFu, toff, 0);
+            const bool fits = (int64_t)toff + total <= A.slice_cap;
+            if (lane == 0) {
+                A.wt_total[wt] = total;
+                A.wt_toff[wt] = slice + toff;
+                if (!fits) st |= AK_ST_OVERFLOW;
+            }
+            __syncwarp();
+            // ---- pass 2: write the ids (from the cache entries) and the row splits (warp-tile relative)
+            int32_t* tbase = A.temp + slice + toff;
+            for (int base = 0; base < E; base += 32) {
+                const int e = base + lane;
+                if (e >= E) continue;
+                const uint32_t v = ev[e], rr = res[e];
+                const int o = eoff[e];
+                const int64_t p = ws + (v & 511u);
+                if (v & (1u << 9)) {
+                    int64_t g = r_w0 + (v >> 12);
+                    while (g < B.n_rows && B.off[g] < p) ++g;
+                    int k = o;
+                    while (g <= B.n_rows && B.off[g] == p) {
+                        if (g > 0 && A.M.eos >= 0) { if (fits) tbase[k] = A.M.eos; ++k; }
+                        A.id_splits[g] = k;
+                        if (g < B.n_rows && A.M.bos >= 0) { if (fits) tbase[k] = A.M.bos; ++k; }
+                        ++g;
+                    }
+                } else if (fits) {
+                    const int n = (int)(rr & 31u);
+                    if (!(rr & 0x80000000u)) {
+                        const unsigned long long* en = A.C.e + (unsigned long long)((rr >> 5) & 0x3FFFFu) * AKW_ENTRY;
+#pragma unroll 1
+                        for (int i = 0; i < n; i += 2) {
+                            const unsigned long long q = akw_ld(en + 8 + (i >> 1));
+                            tbase[o + i] = (int32_t)(uint32_t)q;
+                            if (i + 1 < n) tbase[o + i + 1] = (int32_t)(uint32_t)(q >> 32);
+                        }
+                    } else {
+                        const uint32_t kc = (v >> 10) & 3u;
+                        const uint32_t len = v >> 12;
+                        int64_t we = p + len;
+                        if (len == 0xFFFFFu) we = akb_word_end(A.T, B.text, p, 0, kc, 0u, 0u, B.off, B.n_rows, X.r_lo, X.r_hi);
+                        AkIdSink ds;
+                        ds.buf = nullptr; ds.cap = 0; ds.stride = 1; ds.cnt = 0; ds.direct = true;
+                        ds.gout = tbase + o; ds.gbase = 0; ds.gcap = (int64_t)(rr & 0x3FFFFFFFu);
+                        uint32_t st2 = 0;
+                        ak_bpe_word(A.M, A.T, B.text, p, we, kc, ds, A.pool, st2);
+                    }
+                }
+            }
+        } else {
+            // more events than the list holds (hundreds of one-byte words / row starts in 480 bytes): lane by lane
+            int64_t nr_hint = -1;
+            if (active && c.rows) {
+                int64_t g = r_w0 + (r_inc - n_row_ev);
+                const int64_t p = cs + (__ffs(c.rows) - 1);
+                while (g < B.n_rows && B.off[g] < p) ++g;
+                nr_hint = g;
+            }
+            AkIdSink sink;
+            sink.buf = nullptr; sink.cap = 0; sink.stride = 1; sink.cnt = 0; sink.direct = false;
+            sink.gout = A.temp; sink.gbase = 0; sink.gcap = 0;
+            int64_t row_first = 0, row_last = 0;
+            if (active) akb_lane_emit(X, c, next_bnd, cs, sink, A.id_splits, row_first, row_last, st, nr_hint);
+            const int cnt = sink.cnt;
+            int inc = cnt;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int y = __shfl_up_sync(0xFFFFFFFFu, inc, d);
+                if (lane >= d) inc += y;
+            }
+            total = __shfl_sync(0xFFFFFFFFu, inc, 31);
+            const int pre = inc - cnt;
+            unsigned int toff = 0;
+            if (lane == 0) toff = atomicAdd(&s_cursor, (unsigned int)total);
+            toff = __shfl_sync(0xFFFFFFFFu, toff, 0);
+            const bool fits = (int64_t)toff + total <= A.slice_cap;
+            if (lane == 0) {
+                A.wt_total[wt] = total;
+                A.wt_toff[wt] = slice + toff;
+                if (!fits) st |= AK_ST_OVERFLOW;
+            }
+            if (active) {
+                for (int64_t r = row_first; r < row_last; ++r) A.id_splits[r] += pre;
+                if (fits) {
                     AkIdSink s2 = sink;
                     s2.cnt = 0;
                     s2.direct = true;
-                    s2.gout = dst;
+                    s2.gout = A.temp + slice + toff + pre;
                     s2.gbase = 0;
                     s2.gcap = cnt;
                     uint32_t st2 = 0;

@@ -207,6 +207,17 @@ def test_edge_batches(A, eng, models_dir):
     assert [x.tolist() for x in r.rows()] == [O.bpe_encode(om, s) for s in tb.to_strings()]
 
 
+def test_bpe_dense_events(A, models_dir):
+    # more row / word starts in one 480-byte warp tile than its event list holds, and tens of thousands of empty
+    # rows at one byte position (16-bit token offsets): both take the lane-by-lane path inside the fast kernel
+    tk = A.aksharTokenizer(os.path.join(models_dir, 'bpe24k.json'), 'bpe')
+    om = O.BpeModel(os.path.join(models_dir, 'bpe24k.json'))
+    lines = ['a'] * 3000 + ['b.c,d!e'] * 200 + [''] * 40000 + ['kya haal hai', '']
+    got = [x.tolist() for x in tk._eng.encode_bpe_batch(lines).rows()]
+    assert got == [O.bpe_encode(om, s) for s in lines]
+    assert tk.encode_batch(lines) == got
+
+
 def test_bpe_renormalizes_on_device(A, models_dir):
     # rows that are not in NFC make the kernel take its conditional NFC + re-encode passes
     tk = A.aksharTokenizer(os.path.join(models_dir, 'bpe24k.json'), 'bpe', clean_hinglish=True)
