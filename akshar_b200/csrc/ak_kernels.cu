@@ -648,231 +648,6 @@ __global__ void __launch_bounds__(AK_BLOCK) ak_bpe_kernel(const AkBpeArgs A) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// K2 + K3 fast: grapheme clusters and script runs (ak_seg_fast.cuh).  Same tile plumbing as the fast BPE kernel:
-// each tile appends its cluster ends / run ends + tags to temporary streams at atomically reserved offsets, the
-// tile totals are scanned, a copy kernel moves the blocks to their final place and makes the row splits global.
-// ------------------------------------------------------------------------------------------------
-struct AkSfArgs {
-    AkBatch B;
-    AkTables T;
-    uint32_t flags;
-    const int64_t* tile_row;
-    int64_t base0;
-    int32_t* tc;                 // temporary streams
-    int32_t* tr;
-    uint8_t* tt;
-    int64_t tc_cap, tr_cap;
-    unsigned long long* cursors; // [2]
-    int32_t* c_total;
-    int64_t* c_toff;
-    int64_t* c_base;
-    int32_t* r_total;
-    int64_t* r_toff;
-    int64_t* r_base;
-    AkSegOut o;                  // final outputs
-};
-
-__device__ __forceinline__ unsigned long long aks_pack_g(const AkGState& g) {
-    return (unsigned long long)g.prev | ((unsigned long long)g.conj << 8) | ((unsigned long long)g.pict << 16) |
-           ((unsigned long long)g.ri_odd << 24) | ((unsigned long long)g.prev_m << 32) | ((unsigned long long)g.has_prev << 40);
-}
-__device__ __forceinline__ AkGState aks_unpack_g(unsigned long long v) {
-    AkGState g;
-    g.prev = (uint8_t)v; g.conj = (uint8_t)(v >> 8); g.pict = (uint8_t)(v >> 16); g.ri_odd = (uint8_t)(v >> 24);
-    g.prev_m = (uint8_t)(v >> 32); g.has_prev = (uint8_t)(v >> 40);
-    return g;
-}
-
-// exclusive prefix of the row-start bit counts per bitmap word (executed by warp 0)
-__device__ __forceinline__ void akf_row_prefix(const uint32_t* rowbits, uint16_t* rowpref, int lane) {
-    constexpr int NW = (AKF_TILE + 64) / 32 + 2;
-    int v[4], sum = 0;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const int wi = lane * 4 + k;
-        v[k] = wi < NW ? __popc(rowbits[wi]) : 0;
-        sum += v[k];
-    }
-    int inc = sum;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const int y = __shfl_up_sync(0xFFFFFFFFu, inc, d);
-        if (lane >= d) inc += y;
-    }
-    int run = inc - sum;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const int wi = lane * 4 + k;
-        if (wi < NW) rowpref[wi] = (uint16_t)run;
-        run += v[k];
-    }
-}
-
-// index of the first row that starts at or after position p of this tile (p >= tile_start)
-__device__ __forceinline__ int64_t akf_row_at(const uint32_t* rowbits, const uint16_t* rowpref, const int64_t* off, int64_t n_rows,
-                                              int64_t r0, int64_t tile_start, int64_t p) {
-    const int b = (int)(p - (tile_start - 16));
-    const int before = (int)rowpref[b >> 5] + __popc(rowbits[b >> 5] & ((1u << (b & 31)) - 1u)) - (int)__popc(rowbits[0] & 0xFFFFu);
-    int64_t g = r0 + before;
-    while (g <= n_rows && off[g] < p) ++g;      // empty rows share a position
-    return g;
-}
-
-__global__ void __launch_bounds__(AK_BLOCK) ak_sf_kernel(const AkSfArgs A) {
-    __shared__ uint32_t lut[384];
-    __shared__ uint32_t rowbits[(AKF_TILE + 64) / 32 + 2];
-    __shared__ uint16_t rowpref[(AKF_TILE + 64) / 32 + 2];
-    __shared__ int32_t cstage[AKS_STAGE * AK_BLOCK];
-    __shared__ int32_t rstage[AKS_STAGE * AK_BLOCK];
-    __shared__ uint8_t tstage[AKS_STAGE * AK_BLOCK];
-    __shared__ int ws[33];
-    __shared__ long long s_toff[2];
-    AkBatch B = A.B;
-    if (!ak_batch_begin(B)) return;
-    const bool want_c = (A.flags & AK_SEG_CLUSTERS) != 0, want_r = (A.flags & AK_SEG_RUNS) != 0;
-    const bool matras = (A.flags & AK_SEG_MATRAS) != 0;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int i = tid; i < 384; i += AK_BLOCK)
-        lut[i] = i < 128 ? A.T.leaves[((uint32_t)A.T.page_index[0] << 8) | i] : A.T.leaves[((uint32_t)A.T.page_index[9] << 8) | (i - 128)];
-    for (int tile = blockIdx.x; tile < B.n_tiles; tile += gridDim.x) {
-        const int64_t tile_start = A.base0 + (int64_t)tile * AKF_TILE;
-        akf_tile_rows(B, A.tile_row, tile, tile_start, rowbits);
-        const int64_t r0 = A.tile_row[tile], r1 = A.tile_row[tile + 1];
-        if (warp == 0) akf_row_prefix(rowbits, rowpref, lane);
-        __syncthreads();
-        AkSChunk c;
-        const int64_t cs = tile_start + (int64_t)warp * AKF_WARP_BYTES + (int64_t)(lane - 1) * 16;
-        akf_load_lane(B, cs, c);
-        {
-            const int bo = (int)(cs - (tile_start - 16));
-            c.rows = (rowbits[bo >> 5] >> (bo & 31)) & 0xFFFFu;
-        }
-        aks_phase_a(A.T, lut, c, matras);
-        AkSNeighbor pv;
-        pv.g = aks_unpack_g(__shfl_up_sync(0xFFFFFFFFu, aks_pack_g(c.end_g), 1));
-        pv.flags = __shfl_up_sync(0xFFFFFFFFu, c.flags, 1);
-        pv.end_cur = __shfl_up_sync(0xFFFFFFFFu, c.end_cur, 1);
-        const bool real = lane >= 1 && lane <= AKF_REAL;
-        const int64_t ss = cs < B.text_begin ? B.text_begin : cs;
-        const int64_t se = cs + 16 > B.text_end + 1 ? B.text_end + 1 : cs + 16;
-        const bool active = real && ss < se;
-        uint32_t in_cur = AKS_CUR_NONE;
-        bool slow = false;
-        uint32_t st = 0;
-        int64_t row_first = 0, row_last = 0, nr = 0;
-        const int64_t rlo = r0 > 0 ? r0 - 1 : 0, rhi = r1 > B.n_rows ? B.n_rows : r1;
-        AkSegSink sink;
-        sink.cbuf = cstage + tid;
-        sink.rbuf = rstage + tid;
-        sink.tbuf = tstage + tid;
-        sink.cap = AKS_STAGE;
-        sink.stride = AK_BLOCK;
-        sink.cc = sink.rc = 0;
-        sink.direct = false;
-        sink.gc = sink.gr = nullptr;
-        sink.gt = nullptr;
-        sink.gccap = sink.grcap = 0;
-        int64_t scc = 0, src = 0;        // slow-lane counts
-        if (active) {
-            slow = !aks_phase_b(A.T, lut, c, pv, matras, want_c, want_r, in_cur);
-            if (slow) {
-                AkSegOut o = A.o;
-                ak_seg_span(A.T, B.text, B.off, B.n_rows, rlo, rhi, ss, se, A.flags, AK_LOOKBACK_LIMIT, false, o, scc, src, st);
-                sink.cc = (int)scc;
-                sink.rc = (int)src;
-            } else {
-                nr = ss > tile_start ? akf_row_at(rowbits, rowpref, B.off, B.n_rows, r0, tile_start, ss) : r0;
-                aks_lane_emit(c, in_cur, cs, B.off, B.n_rows, nr, want_c, want_r, sink, want_c ? A.o.cluster_splits : nullptr,
-                              want_r ? A.o.run_splits : nullptr, row_first, row_last);
-            }
-        }
-        int ctot, rtot;
-        const int cpre = ak_block_exscan<AK_BLOCK>(sink.cc, ws, ctot);
-        const int rpre = ak_block_exscan<AK_BLOCK>(sink.rc, ws, rtot);
-        if (tid == 0) {
-            const long long tc0 = (long long)atomicAdd(A.cursors, (unsigned long long)ctot);
-            const long long tr0 = (long long)atomicAdd(A.cursors + 1, (unsigned long long)rtot);
-            s_toff[0] = tc0;
-            s_toff[1] = tr0;
-            A.c_total[tile] = ctot;
-            A.c_toff[tile] = tc0;
-            A.r_total[tile] = rtot;
-            A.r_toff[tile] = tr0;
-            if (tc0 + ctot > A.tc_cap || tr0 + rtot > A.tr_cap) st |= AK_ST_OVERFLOW;
-        }
-        __syncthreads();
-        const int64_t cb = s_toff[0] + cpre, rb = s_toff[1] + rpre;
-        if (active) {
-            if (slow) {
-                // the walker writes straight into the temporary streams; splits are tile-relative like the fast lanes'
-                AkSegOut o = A.o;
-                o.cluster_ends = A.tc + s_toff[0];
-                o.run_ends = A.tr + s_toff[1];
-                o.run_tags = A.tt + s_toff[1];
-                o.cbase = cpre;
-                o.rbase = rpre;
-                o.ccap = A.tc_cap - s_toff[0] > 0 ? A.tc_cap - s_toff[0] : 0;
-                o.rcap = A.tr_cap - s_toff[1] > 0 ? A.tr_cap - s_toff[1] : 0;
-                uint32_t st2 = 0;
-                int64_t a, b;
-                ak_seg_span(A.T, B.text, B.off, B.n_rows, rlo, rhi, ss, se, A.flags, AK_LOOKBACK_LIMIT, true, o, a, b, st2);
-            } else {
-                for (int64_t r = row_first; r < row_last; ++r) {
-                    if (want_c) A.o.cluster_splits[r] += cpre;
-                    if (want_r) A.o.run_splits[r] += rpre;
-                }
-                if (sink.cc <= AKS_STAGE && sink.rc <= AKS_STAGE) {
-                    for (int i = 0; i < sink.cc; ++i)
-                        if (cb + i < A.tc_cap) A.tc[cb + i] = cstage[i * AK_BLOCK + tid];
-                    for (int i = 0; i < sink.rc; ++i)
-                        if (rb + i < A.tr_cap) { A.tr[rb + i] = rstage[i * AK_BLOCK + tid]; A.tt[rb + i] = tstage[i * AK_BLOCK + tid]; }
-                } else {
-                    AkSegSink s2 = sink;
-                    s2.cc = s2.rc = 0;
-                    s2.direct = true;
-                    s2.gc = A.tc + cb;
-                    s2.gr = A.tr + rb;
-                    s2.gt = A.tt + rb;
-                    s2.gccap = A.tc_cap - cb > 0 ? A.tc_cap - cb : 0;
-                    s2.grcap = A.tr_cap - rb > 0 ? A.tr_cap - rb : 0;
-                    int64_t a, b;
-                    aks_lane_emit(c, in_cur, cs, B.off, B.n_rows, nr, want_c, want_r, s2, nullptr, nullptr, a, b);
-                }
-            }
-        }
-        ak_raise(B.result, st);
-    }
-}
-
-__global__ void __launch_bounds__(AK_BLOCK) ak_sf_copy_kernel(const AkSfArgs A) {
-    AkBatch B = A.B;
-    if (!ak_batch_begin(B)) return;
-    const bool want_c = (A.flags & AK_SEG_CLUSTERS) != 0, want_r = (A.flags & AK_SEG_RUNS) != 0;
-    const int tid = threadIdx.x;
-    for (int tile = blockIdx.x; tile < B.n_tiles; tile += gridDim.x) {
-        const int64_t r0 = A.tile_row[tile], r1 = A.tile_row[tile + 1];
-        if (want_c) {
-            const int total = A.c_total[tile];
-            const int64_t toff = A.c_toff[tile], base = A.c_base[tile];
-            if (base + total > A.o.ccap && tid == 0 && total > 0) ak_raise(B.result, AK_ST_OVERFLOW);
-            if (toff + total <= A.tc_cap)
-                for (int i = tid; i < total; i += AK_BLOCK)
-                    if (base + i < A.o.ccap) A.o.cluster_ends[base + i] = A.tc[toff + i];
-            for (int64_t r = r0 + tid; r < r1 && r <= B.n_rows; r += AK_BLOCK) A.o.cluster_splits[r] += base;
-        }
-        if (want_r) {
-            const int total = A.r_total[tile];
-            const int64_t toff = A.r_toff[tile], base = A.r_base[tile];
-            if (base + total > A.o.rcap && tid == 0 && total > 0) ak_raise(B.result, AK_ST_OVERFLOW);
-            if (toff + total <= A.tr_cap)
-                for (int i = tid; i < total; i += AK_BLOCK)
-                    if (base + i < A.o.rcap) { A.o.run_ends[base + i] = A.tr[toff + i]; A.o.run_tags[base + i] = A.tt[toff + i]; }
-            for (int64_t r = r0 + tid; r < r1 && r <= B.n_rows; r += AK_BLOCK) A.o.run_splits[r] += base;
-        }
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
 // Warp tiles.  The fast BPE and segment kernels are warp-autonomous: a warp owns 480 text bytes (30 real lanes +
 // 2 halo lanes), finds the rows that start in them with shuffles, encodes, and appends its output to its CTA's
 // private slice of a temporary stream (cursor in shared memory) -- no CTA barrier and no global atomic on the hot
@@ -940,6 +715,234 @@ __global__ void __launch_bounds__(AKW_GROUP) ak_wt_sums_kernel(AkBatch B, int64_
         int total;
         ak_block_exscan<AKW_GROUP>(t < n_wt ? wt_total[t] : 0, ws, total);
         if (threadIdx.x == 0) sums[gidx] = total;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2 + K3 fast: grapheme clusters and script runs (ak_seg_fast.cuh), warp tiles.  Two temporary streams (cluster
+// ends; run ends + tags), each with per-CTA slices.
+// ------------------------------------------------------------------------------------------------
+struct AkSfArgs {
+    AkBatch B;
+    AkTables T;
+    uint32_t flags;
+    const int64_t* wrow;
+    int64_t base0;
+    int32_t* tc;                 // temporary streams (sliced per CTA)
+    int32_t* tr;
+    uint8_t* tt;
+    int64_t c_slice, r_slice;
+    int32_t* c_total;            // per warp tile
+    int64_t* c_toff;
+    int32_t* r_total;
+    int64_t* r_toff;
+    int32_t* c_sums;             // per group of AKW_GROUP warp tiles, and their exclusive prefix
+    int64_t* c_sum_base;
+    int32_t* r_sums;
+    int64_t* r_sum_base;
+    AkSegOut o;                  // final outputs
+};
+
+__device__ __forceinline__ unsigned long long aks_pack_g(const AkGState& g) {
+    return (unsigned long long)g.prev | ((unsigned long long)g.conj << 8) | ((unsigned long long)g.pict << 16) |
+           ((unsigned long long)g.ri_odd << 24) | ((unsigned long long)g.prev_m << 32) | ((unsigned long long)g.has_prev << 40);
+}
+__device__ __forceinline__ AkGState aks_unpack_g(unsigned long long v) {
+    AkGState g;
+    g.prev = (uint8_t)v; g.conj = (uint8_t)(v >> 8); g.pict = (uint8_t)(v >> 16); g.ri_odd = (uint8_t)(v >> 24);
+    g.prev_m = (uint8_t)(v >> 32); g.has_prev = (uint8_t)(v >> 40);
+    return g;
+}
+
+
+__global__ void __launch_bounds__(AK_BLOCK, 4) ak_sf_kernel(const AkSfArgs A) {
+    __shared__ uint32_t lut[384];
+    __shared__ int32_t cstage[AKS_STAGE * AK_BLOCK];
+    __shared__ int32_t rstage[AKS_STAGE * AK_BLOCK];
+    __shared__ uint8_t tstage[AKS_STAGE * AK_BLOCK];
+    __shared__ unsigned int s_cursor[2];
+    AkBatch B = A.B;
+    if (!ak_batch_begin(B)) return;
+    const bool want_c = (A.flags & AK_SEG_CLUSTERS) != 0, want_r = (A.flags & AK_SEG_RUNS) != 0;
+    const bool matras = (A.flags & AK_SEG_MATRAS) != 0;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int i = tid; i < 384; i += AK_BLOCK)
+        lut[i] = i < 128 ? A.T.leaves[((uint32_t)A.T.page_index[0] << 8) | i] : A.T.leaves[((uint32_t)A.T.page_index[9] << 8) | (i - 128)];
+    if (tid < 2) s_cursor[tid] = 0;
+    __syncthreads();
+    const int n_wt = akw_n_tiles(B, A.base0);
+    const int64_t cslice = (int64_t)blockIdx.x * A.c_slice, rslice = (int64_t)blockIdx.x * A.r_slice;
+    for (int wt = blockIdx.x * AKF_WARPS + warp; wt < n_wt; wt += gridDim.x * AKF_WARPS) {
+        const int64_t ws = A.base0 + (int64_t)wt * AKF_WARP_BYTES;
+        const int64_t r_w0 = A.wrow[wt], r_w1 = A.wrow[wt + 1];
+        AkSChunk c;
+        const int64_t cs = ws + (int64_t)(lane - 1) * 16;
+        akf_load_lane(B, cs, c);
+        c.rows = akw_lane_rows(B.off, B.n_rows, r_w0, ws, lane);
+        aks_phase_a(A.T, lut, c, matras);
+        AkSNeighbor pv;
+        pv.g = aks_unpack_g(__shfl_up_sync(0xFFFFFFFFu, aks_pack_g(c.end_g), 1));
+        pv.flags = __shfl_up_sync(0xFFFFFFFFu, c.flags, 1);
+        pv.end_cur = __shfl_up_sync(0xFFFFFFFFu, c.end_cur, 1);
+        const bool real = lane >= 1 && lane <= AKF_REAL;
+        const int64_t ss = cs < B.text_begin ? B.text_begin : cs;
+        const int64_t se = cs + 16 > B.text_end + 1 ? B.text_end + 1 : cs + 16;
+        const bool active = real && ss < se;
+        // index of the first row that starts at or after this lane's first position
+        int64_t nr = r_w0;
+        {
+            const int mine = real ? __popc(c.rows & 0xFFFFu) : 0;
+            int inc = mine;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int y = __shfl_up_sync(0xFFFFFFFFu, inc, d);
+                if (lane >= d) inc += y;
+            }
+            nr = r_w0 + (inc - mine);
+            if (active) while (nr <= B.n_rows && B.off[nr] < ss) ++nr;      // empty rows share a position
+        }
+        uint32_t in_cur = AKS_CUR_NONE;
+        bool slow = false;
+        uint32_t st = 0;
+        int64_t row_first = 0, row_last = 0;
+        const int64_t rlo = r_w0 > 0 ? r_w0 - 1 : 0, rhi = r_w1 > B.n_rows ? B.n_rows : r_w1;
+        AkSegSink sink;
+        sink.cbuf = cstage + tid;
+        sink.rbuf = rstage + tid;
+        sink.tbuf = tstage + tid;
+        sink.cap = AKS_STAGE;
+        sink.stride = AK_BLOCK;
+        sink.cc = sink.rc = 0;
+        sink.direct = false;
+        sink.gc = sink.gr = nullptr;
+        sink.gt = nullptr;
+        sink.gccap = sink.grcap = 0;
+        if (active) {
+            slow = !aks_phase_b(A.T, lut, c, pv, matras, want_c, want_r, in_cur);
+            if (slow) {
+                AkSegOut o = A.o;
+                int64_t scc = 0, src = 0;
+                ak_seg_span(A.T, B.text, B.off, B.n_rows, rlo, rhi, ss, se, A.flags, AK_LOOKBACK_LIMIT, false, o, scc, src, st);
+                sink.cc = (int)scc;
+                sink.rc = (int)src;
+            } else {
+                aks_lane_emit(c, in_cur, cs, B.off, B.n_rows, nr, want_c, want_r, sink, want_c ? A.o.cluster_splits : nullptr,
+                              want_r ? A.o.run_splits : nullptr, row_first, row_last);
+            }
+        }
+        __syncwarp();
+        int cinc = sink.cc, rinc = sink.rc;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int y = __shfl_up_sync(0xFFFFFFFFu, cinc, d);
+            const int z = __shfl_up_sync(0xFFFFFFFFu, rinc, d);
+            if (lane >= d) { cinc += y; rinc += z; }
+        }
+        const int ctot = __shfl_sync(0xFFFFFFFFu, cinc, 31), rtot = __shfl_sync(0xFFFFFFFFu, rinc, 31);
+        const int cpre = cinc - sink.cc, rpre = rinc - sink.rc;
+        unsigned int ctoff = 0, rtoff = 0;
+        if (lane == 0) {
+            ctoff = atomicAdd(&s_cursor[0], (unsigned int)ctot);
+            rtoff = atomicAdd(&s_cursor[1], (unsigned int)rtot);
+        }
+        ctoff = __shfl_sync(0xFFFFFFFFu, ctoff, 0);
+        rtoff = __shfl_sync(0xFFFFFFFFu, rtoff, 0);
+        const bool fits = (int64_t)ctoff + ctot <= A.c_slice && (int64_t)rtoff + rtot <= A.r_slice;
+        if (lane == 0) {
+            A.c_total[wt] = ctot;
+            A.c_toff[wt] = cslice + ctoff;
+            A.r_total[wt] = rtot;
+            A.r_toff[wt] = rslice + rtoff;
+            if (!fits) st |= AK_ST_OVERFLOW;
+        }
+        if (active) {
+            int32_t* cdst = A.tc + cslice + ctoff;
+            int32_t* rdst = A.tr + rslice + rtoff;
+            uint8_t* tdst = A.tt + rslice + rtoff;
+            if (slow) {
+                // the walker writes straight into the temporary streams; splits are warp-tile relative like the fast lanes'
+                AkSegOut o = A.o;
+                o.cluster_ends = cdst;
+                o.run_ends = rdst;
+                o.run_tags = tdst;
+                o.cbase = cpre;
+                o.rbase = rpre;
+                o.ccap = fits ? ctot : 0;
+                o.rcap = fits ? rtot : 0;
+                uint32_t st2 = 0;
+                int64_t a, b;
+                ak_seg_span(A.T, B.text, B.off, B.n_rows, rlo, rhi, ss, se, A.flags, AK_LOOKBACK_LIMIT, true, o, a, b, st2);
+            } else {
+                for (int64_t r = row_first; r < row_last; ++r) {
+                    if (want_c) A.o.cluster_splits[r] += cpre;
+                    if (want_r) A.o.run_splits[r] += rpre;
+                }
+                if (fits) {
+                    if (sink.cc <= AKS_STAGE && sink.rc <= AKS_STAGE) {
+                        for (int i = 0; i < sink.cc; ++i) cdst[cpre + i] = cstage[i * AK_BLOCK + tid];
+                        for (int i = 0; i < sink.rc; ++i) { rdst[rpre + i] = rstage[i * AK_BLOCK + tid]; tdst[rpre + i] = tstage[i * AK_BLOCK + tid]; }
+                    } else {
+                        AkSegSink s2 = sink;
+                        s2.cc = s2.rc = 0;
+                        s2.direct = true;
+                        s2.gc = cdst + cpre;
+                        s2.gr = rdst + rpre;
+                        s2.gt = tdst + rpre;
+                        s2.gccap = sink.cc;
+                        s2.grcap = sink.rc;
+                        int64_t a, b;
+                        aks_lane_emit(c, in_cur, cs, B.off, B.n_rows, nr, want_c, want_r, s2, nullptr, nullptr, a, b);
+                    }
+                }
+            }
+        }
+        __syncwarp();
+        ak_raise(B.result, st);
+    }
+}
+
+__global__ void __launch_bounds__(AKW_GROUP) ak_sf_copy_kernel(const AkSfArgs A) {
+    __shared__ int ws[33];
+    __shared__ long long s_cb[AKW_GROUP];
+    __shared__ long long s_rb[AKW_GROUP];
+    AkBatch B = A.B;
+    if (!ak_batch_begin(B)) return;
+    const bool want_c = (A.flags & AK_SEG_CLUSTERS) != 0, want_r = (A.flags & AK_SEG_RUNS) != 0;
+    const int n_wt = akw_n_tiles(B, A.base0);
+    const int n_groups = (n_wt + AKW_GROUP - 1) / AKW_GROUP;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int gidx = blockIdx.x; gidx < n_groups; gidx += gridDim.x) {
+        const int t = gidx * AKW_GROUP + tid;
+        int total;
+        if (want_c) {
+            const int pre = ak_block_exscan<AKW_GROUP>(t < n_wt ? A.c_total[t] : 0, ws, total);
+            s_cb[tid] = A.c_sum_base[gidx] + pre;
+        }
+        if (want_r) {
+            const int pre = ak_block_exscan<AKW_GROUP>(t < n_wt ? A.r_total[t] : 0, ws, total);
+            s_rb[tid] = A.r_sum_base[gidx] + pre;
+        }
+        __syncthreads();
+        for (int j = 0; j < 32; ++j) {
+            const int tj = gidx * AKW_GROUP + warp * 32 + j;
+            if (tj >= n_wt) break;
+            const int64_t r0 = A.wrow[tj], r1 = A.wrow[tj + 1];
+            if (want_c) {
+                const int n = A.c_total[tj];
+                const int64_t src = A.c_toff[tj], dst = s_cb[warp * 32 + j];
+                if (dst + n > A.o.ccap) { if (lane == 0 && n > 0) ak_raise(B.result, AK_ST_OVERFLOW); }
+                else for (int i = lane; i < n; i += 32) A.o.cluster_ends[dst + i] = A.tc[src + i];
+                for (int64_t r = r0 + lane; r < r1 && r <= B.n_rows; r += 32) A.o.cluster_splits[r] += dst;
+            }
+            if (want_r) {
+                const int n = A.r_total[tj];
+                const int64_t src = A.r_toff[tj], dst = s_rb[warp * 32 + j];
+                if (dst + n > A.o.rcap) { if (lane == 0 && n > 0) ak_raise(B.result, AK_ST_OVERFLOW); }
+                else for (int i = lane; i < n; i += 32) { A.o.run_ends[dst + i] = A.tr[src + i]; A.o.run_tags[dst + i] = A.tt[src + i]; }
+                for (int64_t r = r0 + lane; r < r1 && r <= B.n_rows; r += 32) A.o.run_splits[r] += dst;
+            }
+        }
+        __syncthreads();
     }
 }
 
@@ -1595,7 +1598,9 @@ static AkWsLayout ak_ws_layout(int64_t n_bytes, int64_t n_rows) {
     size_t nf = ak_align(tiles * AK_BLOCK * 4) + ak_align(tiles * 4) + ak_align((tiles + 1) * 8) +
                 ak_align((tiles * AK_BLOCK / 16 + 1024) * sizeof(AkSlowEntry));
     // fast segment: tile totals / offsets / bases for two streams + the temporary streams
-    size_t sf = 2 * ak_align(tiles * 4) + 2 * ak_align(tiles * 8) + 2 * ak_align((tiles + 1) * 8) +
+    const size_t sf_nwt = tiles * AKF_WARPS + 8, sf_ng = sf_nwt / AKW_GROUP + 2;
+    size_t sf = ak_align((sf_nwt + 2) * 8) + 2 * ak_align(sf_nwt * 4) + 2 * ak_align(sf_nwt * 8) + 2 * ak_align(sf_ng * 4) +
+                2 * ak_align((sf_ng + 1) * 8) +
                 ak_align((size_t)(n_bytes / 2 + n_rows + 1024) * 4) + ak_align((size_t)(n_bytes / 8 + n_rows + 1024) * 5);
     size_t m = uni > bpe ? uni : bpe;
     if (sf > m) m = sf;
@@ -1816,46 +1821,53 @@ int akshar_segment_batch(akshar_ctx* ctx, const uint8_t* d_text, const int64_t* 
         F.T = ctx->T;
         F.flags = flags;
         F.base0 = text_begin - (int64_t)(((uintptr_t)d_text + (uintptr_t)text_begin) & 15u);
-        F.B.n_tiles = (int)((text_end - F.base0 + AKF_TILE) / AKF_TILE);
-        int64_t* tile_row = (int64_t*)(C.ws + C.L.tile_row);
-        F.tile_row = tile_row;
+        const int nwt = (int)((text_end - F.base0 + AKF_WARP_BYTES) / AKF_WARP_BYTES);
+        const int ngroups = (nwt + AKW_GROUP - 1) / AKW_GROUP;
         char* wp = C.ws + C.L.scratch;
-        F.c_total = (int32_t*)wp;   wp += ak_align(tiles * 4);
-        F.r_total = (int32_t*)wp;   wp += ak_align(tiles * 4);
-        F.c_toff = (int64_t*)wp;    wp += ak_align(tiles * 8);
-        F.r_toff = (int64_t*)wp;    wp += ak_align(tiles * 8);
-        F.c_base = (int64_t*)wp;    wp += ak_align((tiles + 1) * 8);
-        F.r_base = (int64_t*)wp;    wp += ak_align((tiles + 1) * 8);
+        F.wrow = (int64_t*)wp;          wp += ak_align(((size_t)nwt + 2) * 8);
+        F.c_total = (int32_t*)wp;       wp += ak_align((size_t)nwt * 4);
+        F.r_total = (int32_t*)wp;       wp += ak_align((size_t)nwt * 4);
+        F.c_toff = (int64_t*)wp;        wp += ak_align((size_t)nwt * 8);
+        F.r_toff = (int64_t*)wp;        wp += ak_align((size_t)nwt * 8);
+        F.c_sums = (int32_t*)wp;        wp += ak_align((size_t)ngroups * 4);
+        F.r_sums = (int32_t*)wp;        wp += ak_align((size_t)ngroups * 4);
+        F.c_sum_base = (int64_t*)wp;    wp += ak_align(((size_t)ngroups + 1) * 8);
+        F.r_sum_base = (int64_t*)wp;    wp += ak_align(((size_t)ngroups + 1) * 8);
+        const int grid = ak_grid(ctx, ctx->occ_sf, (nwt + AKF_WARPS - 1) / AKF_WARPS);
+        int64_t tc_cap, tr_cap;
         {
             // the temporary streams share what is left of the workspace: 4 B per cluster end, 5 B per run end
             const size_t left = C.ws_bytes - (size_t)(wp - C.ws) - 1024;
-            if (want_c && want_r) { F.tc_cap = (int64_t)(left * 3 / 4 / 4); F.tr_cap = (int64_t)(left / 4 / 5); }
-            else if (want_c) { F.tc_cap = (int64_t)(left / 4); F.tr_cap = 0; }
-            else { F.tc_cap = 0; F.tr_cap = (int64_t)(left / 5); }
+            if (want_c && want_r) { tc_cap = (int64_t)(left * 3 / 4 / 4); tr_cap = (int64_t)(left / 4 / 5); }
+            else if (want_c) { tc_cap = (int64_t)(left / 4); tr_cap = 0; }
+            else { tc_cap = 0; tr_cap = (int64_t)(left / 5); }
         }
-        F.tc = (int32_t*)wp;        wp += ak_align((size_t)F.tc_cap * 4);
-        F.tr = (int32_t*)wp;        wp += ak_align((size_t)F.tr_cap * 4);
+        F.c_slice = tc_cap / grid;
+        F.r_slice = tr_cap / grid;
+        F.tc = (int32_t*)wp;            wp += ak_align((size_t)tc_cap * 4);
+        F.tr = (int32_t*)wp;            wp += ak_align((size_t)tr_cap * 4);
         F.tt = (uint8_t*)wp;
-        F.cursors = (unsigned long long*)(C.ws + 88);
         F.o = A.o;
-        const int entries = F.B.n_tiles + 1;
-        ak_tile_rows_kernel<<<(entries + 255) / 256, 256, 0, C.stream>>>(C.B.off, n_rows, F.base0, entries, tile_row, nullptr, nullptr,
-                                                                        text_begin);
-        if ((rc = ak_after_launch(ctx, "segment-tile-rows"))) return rc;
+        ak_warp_rows_kernel<<<(nwt + 1 + 255) / 256, 256, 0, C.stream>>>(C.B, F.base0, nwt + 1, (int64_t*)F.wrow);
+        if ((rc = ak_after_launch(ctx, "segment-warp-rows"))) return rc;
         {
             AkTimed tm(ctx, AKSHAR_TIMER_SEGMENT, C.stream);
-            ak_sf_kernel<<<ak_grid(ctx, ctx->occ_sf, F.B.n_tiles), AK_BLOCK, 0, C.stream>>>(F);
+            ak_sf_kernel<<<grid, AK_BLOCK, 0, C.stream>>>(F);
         }
         if ((rc = ak_after_launch(ctx, "segment-fast"))) return rc;
         if (want_c) {
-            ak_nf_scan_kernel<<<1, 1024, 0, C.stream>>>(F.c_total, F.c_base, F.B.n_tiles, d_result, C.B, F.base0);
+            ak_wt_sums_kernel<<<ak_grid(ctx, 8, ngroups), AKW_GROUP, 0, C.stream>>>(C.B, F.base0, F.c_total, F.c_sums);
+            if ((rc = ak_after_launch(ctx, "segment-sums"))) return rc;
+            ak_nf_scan_kernel<<<1, 1024, 0, C.stream>>>(F.c_sums, F.c_sum_base, ngroups, d_result, C.B, F.base0, AKF_WARP_BYTES * AKW_GROUP);
             if ((rc = ak_after_launch(ctx, "segment-scan"))) return rc;
         }
         if (want_r) {
-            ak_nf_scan_kernel<<<1, 1024, 0, C.stream>>>(F.r_total, F.r_base, F.B.n_tiles, d_result + 1, C.B, F.base0);
+            ak_wt_sums_kernel<<<ak_grid(ctx, 8, ngroups), AKW_GROUP, 0, C.stream>>>(C.B, F.base0, F.r_total, F.r_sums);
+            if ((rc = ak_after_launch(ctx, "segment-sums"))) return rc;
+            ak_nf_scan_kernel<<<1, 1024, 0, C.stream>>>(F.r_sums, F.r_sum_base, ngroups, d_result + 1, C.B, F.base0, AKF_WARP_BYTES * AKW_GROUP);
             if ((rc = ak_after_launch(ctx, "segment-scan"))) return rc;
         }
-        ak_sf_copy_kernel<<<ak_grid(ctx, 8, F.B.n_tiles), AK_BLOCK, 0, C.stream>>>(F);
+        ak_sf_copy_kernel<<<ak_grid(ctx, 8, ngroups), AKW_GROUP, 0, C.stream>>>(F);
         return ak_after_launch(ctx, "segment-copy");
     }
     ak_segment_kernel<<<ak_grid(ctx, ctx->occ_seg, A.B.n_tiles), AK_BLOCK, 0, C.stream>>>(A);

@@ -47,44 +47,59 @@ AK_HD uint32_t aks_decode_at(const AkSChunk& c, int i, uint32_t b) {
 }
 
 // ---- phase A -------------------------------------------------------------------------------------------------
+// (loops over the byte positions are ROLLED: these kernels are instruction-cache bound)
 AK_HD void aks_phase_a(const AkTables& T, const uint32_t* lut, AkSChunk& c, bool matras) {
     uint32_t lead = 0, brk = 0, fix = 0, rchg = 0, tag_lo = 0, tag_hi = 0, flags = 0;
     uint32_t cur = AKS_CUR_IN, first_strong = AKF_NONE;
     AkGState g;
     aks_g_reset(g);
     bool synced = false;
-#pragma unroll
-    for (int i = 0; i < 16; ++i) {
-        const bool row_here = (c.rows >> i) & 1u;
-        // label in effect after everything before byte i (a row start at i closes its row with it)
-        if (i < 10) tag_lo |= cur << (3 * i); else tag_hi |= cur << (3 * (i - 10));
-        if (row_here) {
-            if (cur == AKS_CUR_IN) flags |= AKS_USES_IN;
-            aks_g_reset(g);
-            synced = true;
-            cur = AKS_CUR_NONE;
-            flags |= AKS_ROWSTART;
-        }
-        const uint32_t b = aks_byte(c, i);
-        if (!((c.own >> i) & 1u) || (b & 0xC0u) == 0x80u) continue;
-        const uint32_t cp = aks_decode_at(c, i, b);
-        const uint32_t w = akf_props(T, lut, cp);
-        lead |= 1u << i;
-        // grapheme clusters
-        if (!synced) fix |= 1u << i;
-        if (g.has_prev) {
-            bool bk = ak_g_break(g, w);
-            if (matras && (g.prev_m || ak_is_matra_or_halant(cp))) bk = true;
-            if (bk) brk |= 1u << i;
-        }
-        ak_g_advance(g, cp, w);
-        if (ak_g_sync(w)) synced = true;
-        // script runs
-        const uint32_t t = AK_TAG(w);
-        if (t != TAG_DIGIT && t != TAG_PUNCT) {
-            if (cur == AKS_CUR_IN) { first_strong = ((uint32_t)i << 8) | t; flags |= AKS_USES_IN; }
-            else if (cur != AKS_CUR_NONE && cur != t) rchg |= 1u << i;
-            cur = t;
+#pragma unroll 1
+    for (int k = 0; k < 4; ++k) {
+        const uint32_t wlo = k == 0 ? c.w[0] : k == 1 ? c.w[1] : k == 2 ? c.w[2] : c.w[3];
+        const uint32_t whi = k == 0 ? c.w[1] : k == 1 ? c.w[2] : k == 2 ? c.w[3] : c.w[4];
+        const unsigned long long win = ((unsigned long long)whi << 32) | wlo;
+        const uint32_t rows4 = (c.rows >> (4 * k)) & 15u, own4 = (c.own >> (4 * k)) & 15u;
+#pragma unroll 1
+        for (int j = 0; j < 4; ++j) {
+            const int i = 4 * k + j;
+            const bool row_here = (rows4 >> j) & 1u;
+            // label in effect after everything before byte i (a row start at i closes its row with it)
+            if (i < 10) tag_lo |= cur << (3 * i); else tag_hi |= cur << (3 * (i - 10));
+            if (row_here) {
+                if (cur == AKS_CUR_IN) flags |= AKS_USES_IN;
+                aks_g_reset(g);
+                synced = true;
+                cur = AKS_CUR_NONE;
+                flags |= AKS_ROWSTART;
+            }
+            const uint32_t v = (uint32_t)(win >> (8 * j));
+            const uint32_t b = v & 0xFFu;
+            if (!((own4 >> j) & 1u) || (b & 0xC0u) == 0x80u) continue;
+            const uint32_t b1 = (v >> 8) & 0x3Fu, b2 = (v >> 16) & 0x3Fu, b3 = (v >> 24) & 0x3Fu;
+            uint32_t cp;
+            if (b < 0x80u) cp = b;
+            else if (b < 0xE0u) cp = ((b & 0x1Fu) << 6) | b1;
+            else if (b < 0xF0u) cp = ((b & 0x0Fu) << 12) | (b1 << 6) | b2;
+            else cp = ((b & 0x07u) << 18) | (b1 << 12) | (b2 << 6) | b3;
+            const uint32_t w = akf_props(T, lut, cp);
+            lead |= 1u << i;
+            // grapheme clusters
+            if (!synced) fix |= 1u << i;
+            if (g.has_prev) {
+                bool bk = ak_g_break(g, w);
+                if (matras && (g.prev_m || ak_is_matra_or_halant(cp))) bk = true;
+                if (bk) brk |= 1u << i;
+            }
+            ak_g_advance(g, cp, w);
+            if (ak_g_sync(w)) synced = true;
+            // script runs
+            const uint32_t t = AK_TAG(w);
+            if (t != TAG_DIGIT && t != TAG_PUNCT) {
+                if (cur == AKS_CUR_IN) { first_strong = ((uint32_t)i << 8) | t; flags |= AKS_USES_IN; }
+                else if (cur != AKS_CUR_NONE && cur != t) rchg |= 1u << i;
+                cur = t;
+            }
         }
     }
     if (synced) flags |= AKS_EXACT_G;
