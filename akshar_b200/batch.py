@@ -361,6 +361,129 @@ class Engine:
         raise BatchStatusError(bits, 'tokenizer_encode_batch (retries exhausted)')
 
 
+    # ------------------------------------------------------------------ host -> ids, pipelined
+    def encode_host_pipelined(self, h_data, h_off, kind, normalize_roman=True, clean_hinglish=True, chunk_bytes=96 << 20,
+                              out_ids=None, out_splits=None):
+        """aksharTokenizer.encode over a batch that lives in (pinned) HOST memory, returning host tensors:
+        the batch is cut into row ranges of ~chunk_bytes; the H2D copy of chunk k+1, the kernels of chunk k and the
+        D2H copy of chunk k-1 run on three streams.  -> (ids int32 [total] pinned, row_splits int64 [n_rows + 1] pinned)"""
+        import numpy as np
+        from . import shard
+        dev = self.device
+        n_rows = h_off.numel() - 1
+        off_np = h_off.numpy()
+        total_bytes = int(off_np[-1] - off_np[0])
+        n_chunks = max(1, (total_bytes + chunk_bytes - 1) // chunk_bytes)
+        ranges = [r for r in shard.shard_rows(off_np, n_chunks) if r[1] > r[0]] or [(0, 0)]
+        max_b = max(int(off_np[hi] - off_np[lo]) for lo, hi in ranges)
+        max_r = max(hi - lo for lo, hi in ranges)
+        flags = (C.NORM_ROMAN if normalize_roman else 0) | (C.NORM_CLEAN if clean_hinglish else 0)
+        ncap = max_b + (max_b >> 3) + 1024
+        cap = (max_b >> 1) + 2 * max_r + 1024
+        ws = self._workspace(ncap, max_r)
+        # pinned result buffers, device double buffers and streams are kept by the engine: repeated calls allocate nothing
+        pc = self.__dict__.setdefault('_pipe_cache', {})
+        est = (total_bytes >> 1) + 2 * n_rows + 1024
+        if out_splits is None:
+            if pc.get('splits') is None or pc['splits'].numel() != n_rows + 1:
+                pc['splits'] = torch.empty(n_rows + 1, dtype=torch.int64).pin_memory()
+            out_splits = pc['splits']
+        if out_ids is None or out_ids.numel() < est:
+            if pc.get('ids') is None or pc['ids'].numel() < est:
+                pc['ids'] = torch.empty(est, dtype=torch.int32).pin_memory()
+            out_ids = pc['ids']
+        if 'streams' not in pc:
+            pc['streams'] = tuple(torch.cuda.Stream(device=dev) for _ in range(3))
+        s_in, s_comp, s_out = pc['streams']
+        key = (max_b, max_r)
+        sets = pc.get('sets') if pc.get('sets_key') == key else None
+        if sets is None:
+            sets = []
+            for _ in range(2):
+                sets.append({
+                    'text': torch.empty(max(max_b, 1), dtype=torch.uint8, device=dev),
+                    'off': torch.empty(max_r + 1, dtype=torch.int64, device=dev),
+                    'norm': torch.empty(max(ncap, 1), dtype=torch.uint8, device=dev),
+                    'norm_off': torch.empty(max_r + 1, dtype=torch.int64, device=dev),
+                    'ids': torch.empty(max(cap, 1), dtype=torch.int32, device=dev),
+                    'splits': torch.empty(max_r + 1, dtype=torch.int64, device=dev),
+                    'result': torch.empty(4, dtype=torch.int64, device=dev),
+                    'h_off': torch.empty(max_r + 1, dtype=torch.int64).pin_memory(),
+                    'ev_in': torch.cuda.Event(), 'ev_comp': torch.cuda.Event(), 'ev_out': torch.cuda.Event(),
+                })
+        pc['sets'], pc['sets_key'] = sets, key
+        cur = torch.cuda.current_stream(dev)
+        for st in (s_in, s_comp, s_out):
+            st.wait_stream(cur)
+        state = {'tok': 0, 'ok': True}
+        out_splits[0] = 0
+
+        def finish(k):
+            lo, hi = ranges[k]
+            S = sets[k & 1]
+            with torch.cuda.stream(s_out):
+                s_out.wait_event(S['ev_comp'])
+                r = S['result'].cpu()          # waits for chunk k's kernels only; later chunks are already enqueued
+                n, bits = int(r[0]), int(r[2])
+                if bits:
+                    state['ok'] = False
+                    return
+                if state['tok'] + n > out_ids.numel():
+                    state['ok'] = False
+                    return
+                out_ids[state['tok']:state['tok'] + n].copy_(S['ids'][:n], non_blocking=True)
+                sp = S['splits'][1:hi - lo + 1]
+                if state['tok']:
+                    sp = sp + state['tok']
+                out_splits[lo + 1:hi + 1].copy_(sp, non_blocking=True)
+                S['ev_out'].record(s_out)
+                state['tok'] += n
+
+        for k, (lo, hi) in enumerate(ranges):
+            S = sets[k & 1]
+            b0, b1 = int(off_np[lo]), int(off_np[hi])
+            nb, nr = b1 - b0, hi - lo
+            np.subtract(off_np[lo:hi + 1], b0, out=S['h_off'].numpy()[:nr + 1]) if k < 2 else None
+            with torch.cuda.stream(s_in):
+                if k >= 2:
+                    s_in.wait_event(S['ev_comp'])      # the kernels that read this input buffer have finished
+                    S['ev_in'].synchronize()            # and its pinned offset staging was consumed
+                    np.subtract(off_np[lo:hi + 1], b0, out=S['h_off'].numpy()[:nr + 1])
+                S['text'][:nb].copy_(h_data[b0:b1], non_blocking=True)
+                S['off'][:nr + 1].copy_(S['h_off'][:nr + 1], non_blocking=True)
+                S['ev_in'].record(s_in)
+            with torch.cuda.stream(s_comp):
+                s_comp.wait_event(S['ev_in'])
+                if k >= 2:
+                    s_comp.wait_event(S['ev_out'])     # chunk k-2's results left this set's output buffers
+                rc = self.lib.akshar_tokenizer_encode_batch(
+                    self._h, S['text'].data_ptr(), S['off'].data_ptr(), nr, 0, nb, flags, kind, C.MODE_TILES, S['norm'].data_ptr(),
+                    ncap, S['norm_off'].data_ptr(), S['ids'].data_ptr(), cap, S['splits'].data_ptr(), S['result'].data_ptr(),
+                    ws.data_ptr(), ws.numel(), ctypes.c_void_p(s_comp.cuda_stream))
+                if rc != 0:
+                    self._err(rc, 'akshar_tokenizer_encode_batch')
+                S['ev_comp'].record(s_comp)
+            if k >= 1:
+                finish(k - 1)
+                if not state['ok']:
+                    break
+        if state['ok']:
+            finish(len(ranges) - 1)
+        for st in (s_in, s_comp, s_out):
+            cur.wait_stream(st)
+        torch.cuda.synchronize(dev)
+        if not state['ok']:
+            # a chunk overflowed or needs the row-by-row mode: the plain path handles retries
+            ids, _ = self.tokenizer_encode_batch((h_data, h_off), kind, normalize_roman, clean_hinglish)
+            n = ids.values.numel()
+            if out_ids.numel() < n:
+                out_ids = torch.empty(n, dtype=torch.int32).pin_memory()
+            out_ids[:n].copy_(ids.values)
+            out_splits.copy_(ids.splits)
+            return out_ids[:n], out_splits
+        return out_ids[:state['tok']], out_splits
+
+
 _engines = {}
 
 

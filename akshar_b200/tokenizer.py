@@ -132,6 +132,14 @@ class aksharTokenizer:
             return ids, norm
         return [r.tolist() for r in ids.rows()]
 
+    def encode_batch_host(self, h_data, h_offsets, out_ids=None, out_splits=None):
+        """encode() over a batch given as pinned host tensors (uint8 text, int64 row offsets) -> pinned host tensors
+        (int32 ids, int64 row_splits); copies and kernels are pipelined over three streams"""
+        if self.model is None:
+            raise ValueError("need model for IDs")
+        return self._eng.encode_host_pipelined(h_data, h_offsets, self.model.kind, self.normalize_roman, self.clean_hinglish,
+                                               out_ids=out_ids, out_splits=out_splits)
+
     def tokenize_batch(self, texts):
         """tokenize() over a batch -> list[list[str]]"""
         if self.model is None:

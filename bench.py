@@ -296,19 +296,12 @@ def main():
 
     # ---- end to end through the public batch API: pinned host text in, ids (or offsets) on the host out
     def e2e_step():
-        b = eng.put((h_data, h_off))
         if mkind is not None:
-            ids, norm, result = eng.tokenizer_encode_batch(b, mkind, check=False)
-            r = result.cpu()
-            n = int(r[0])
-            h_ids = torch.empty(n, dtype=torch.int32).pin_memory() if not hasattr(e2e_step, 'h') or e2e_step.h.numel() != n else e2e_step.h
-            e2e_step.h = h_ids
-            if not hasattr(e2e_step, 'hs'):
-                e2e_step.hs = torch.empty(n_rows + 1, dtype=torch.int64).pin_memory()
-            h_ids.copy_(ids.values[:n], non_blocking=True)
-            e2e_step.hs.copy_(ids.splits, non_blocking=True)
-            torch.cuda.synchronize()
-            return n * 4 + (n_rows + 1) * 8 + 32
+            # the public host -> ids call: H2D of chunk k+1, kernels of chunk k and D2H of chunk k-1 overlap
+            ids, splits = eng.encode_host_pipelined(h_data, h_off, mkind)
+            assert int(splits[-1]) == ids.numel()
+            return ids.numel() * 4 + splits.numel() * 8 + 32
+        b = eng.put((h_data, h_off))
         norm, r1 = eng.normalize_batch(b, check=False)
         norm.end = int(r1[0].item())
         c, r, r2 = eng.segment_batch(norm, clusters=True, runs=True, check=False)

@@ -207,6 +207,20 @@ def test_edge_batches(A, eng, models_dir):
     assert [x.tolist() for x in r.rows()] == [O.bpe_encode(om, s) for s in tb.to_strings()]
 
 
+def test_pipelined_host_encode(A, models_dir):
+    import torch
+    tk = A.aksharTokenizer(os.path.join(models_dir, 'bpe24k.json'), 'bpe')
+    data, off = sc.Corpus('social', 21).generate(24 << 20)
+    h_data, h_off = torch.from_numpy(data).pin_memory(), torch.from_numpy(off).pin_memory()
+    ids, splits = tk._eng.encode_host_pipelined(h_data, h_off, 0, chunk_bytes=3 << 20)       # 8+ chunks
+    ref, _ = tk._eng.tokenizer_encode_batch((h_data, h_off), 0)
+    assert torch.equal(ids, ref.values.cpu()) and torch.equal(splits, ref.splits.cpu())
+    tu = A.aksharTokenizer(os.path.join(models_dir, 'spm24k.model'))
+    ids, splits = tu.encode_batch_host(h_data, h_off)
+    ref, _ = tu._eng.tokenizer_encode_batch((h_data, h_off), 1)
+    assert torch.equal(ids, ref.values.cpu()) and torch.equal(splits, ref.splits.cpu())
+
+
 def test_bpe_dense_events(A, models_dir):
     # more row / word starts in one 480-byte warp tile than its event list holds, and tens of thousands of empty
     # rows at one byte position (16-bit token offsets): both take the lane-by-lane path inside the fast kernel
