@@ -969,6 +969,101 @@ struct AkBfArgs {
     unsigned int* changed;
 };
 
+// cold parts of the event loop (a word that is not in the cache, or cannot be cached), out of line on purpose
+__device__ __noinline__ uint32_t akb_event_slow(const AkBfArgs& A, const AkBatch& B, int64_t p, uint32_t len, uint32_t kc,
+                                                unsigned long long h, unsigned long long want, long long slot, bool cacheable,
+                                                int64_t r_lo, int64_t r_hi, uint32_t& st) {
+    int64_t we = p + len;
+    if (len == 0xFFFFFu)       // clamped in the event record: find the real end again
+        we = akb_word_end(A.T, B.text, p, 0, kc, 0u, 0u, B.off, B.n_rows, r_lo, r_hi);
+    if (cacheable) {
+        int32_t tmp[AKW_MAXTOK + 1];
+        AkIdSink local;
+        local.buf = tmp; local.cap = AKW_MAXTOK + 1; local.stride = 1; local.cnt = 0; local.direct = false;
+        local.gout = nullptr; local.gbase = 0; local.gcap = 0;
+        ak_bpe_word(A.M, A.T, B.text, p, we, kc, local, A.pool, st);
+        const int n = local.cnt;
+        if (n <= AKW_MAXTOK && slot >= 0) {
+            akw_insert(A.C, slot, want, B.text, p, len, tmp, n);
+            long long s2;
+            const long long hit = akw_find(A.C, h, want, B.text, p, len, &s2);      // ours, or the same word by another lane
+            if (hit >= 0) {
+                const int m = (int)((akw_ld(A.C.e + (unsigned long long)hit * AKW_ENTRY) & AKW_NTOK_MASK) >> 3);
+                return ((uint32_t)hit << 5) | (uint32_t)m;
+            }
+        }
+        return 0x80000000u | (uint32_t)n;
+    }
+    AkIdSink cntsink;
+    cntsink.buf = nullptr; cntsink.cap = 0; cntsink.stride = 1; cntsink.cnt = 0; cntsink.direct = false;
+    cntsink.gout = nullptr; cntsink.gbase = 0; cntsink.gcap = 0;
+    ak_bpe_word(A.M, A.T, B.text, p, we, kc, cntsink, A.pool, st);
+    return 0x80000000u | (uint32_t)cntsink.cnt;
+}
+
+__device__ __noinline__ void akb_event_write_direct(const AkBfArgs& A, const AkBatch& B, int64_t p, uint32_t len, uint32_t kc,
+                                                    int64_t r_lo, int64_t r_hi, int32_t* dst, int64_t n) {
+    int64_t we = p + len;
+    if (len == 0xFFFFFu) we = akb_word_end(A.T, B.text, p, 0, kc, 0u, 0u, B.off, B.n_rows, r_lo, r_hi);
+    AkIdSink ds;
+    ds.buf = nullptr; ds.cap = 0; ds.stride = 1; ds.cnt = 0; ds.direct = true;
+    ds.gout = dst; ds.gbase = 0; ds.gcap = n;
+    uint32_t st2 = 0;
+    ak_bpe_word(A.M, A.T, B.text, p, we, kc, ds, A.pool, st2);
+}
+
+// more events than the list holds, or more than 65535 ids in one warp tile (hundreds of one-byte words / thousands of
+// empty rows in 480 bytes): lane by lane, counted then written straight to the temporary stream.  Cold.
+__device__ __noinline__ void akb_tile_fallback(const AkBfArgs& A, const AkBatch& B, const AkBLaneCtx& X, const AkBChunk& c,
+                                               uint32_t next_bnd, int64_t cs, bool active, int lane, int wt, int64_t slice,
+                                               int64_t r_w0, int rows_before, unsigned int* s_cursor_p, uint32_t& st) {
+    int total = 0;
+    int64_t nr_hint = -1;
+    if (active && c.rows) {
+        int64_t g = r_w0 + (rows_before);
+        const int64_t p = cs + (__ffs(c.rows) - 1);
+        while (g < B.n_rows && B.off[g] < p) ++g;
+        nr_hint = g;
+    }
+    AkIdSink sink;
+    sink.buf = nullptr; sink.cap = 0; sink.stride = 1; sink.cnt = 0; sink.direct = false;
+    sink.gout = A.temp; sink.gbase = 0; sink.gcap = 0;
+    int64_t row_first = 0, row_last = 0;
+    if (active) akb_lane_emit(X, c, next_bnd, cs, sink, A.id_splits, row_first, row_last, st, nr_hint);
+    const int cnt = sink.cnt;
+    int inc = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int y = __shfl_up_sync(0xFFFFFFFFu, inc, d);
+        if (lane >= d) inc += y;
+    }
+    total = __shfl_sync(0xFFFFFFFFu, inc, 31);
+    const int pre = inc - cnt;
+    unsigned int toff = 0;
+    if (lane == 0) toff = atomicAdd(s_cursor_p, (unsigned int)total);
+    toff = __shfl_sync(0xFFFFFFFFu, toff, 0);
+    const bool fits = (int64_t)toff + total <= A.slice_cap;
+    if (lane == 0) {
+        A.wt_total[wt] = total;
+        A.wt_toff[wt] = slice + toff;
+        if (!fits) st |= AK_ST_OVERFLOW;
+    }
+    if (active) {
+        for (int64_t r = row_first; r < row_last; ++r) A.id_splits[r] += pre;
+        if (fits) {
+            AkIdSink s2 = sink;
+            s2.cnt = 0;
+            s2.direct = true;
+            s2.gout = A.temp + slice + toff + pre;
+            s2.gbase = 0;
+            s2.gcap = cnt;
+            uint32_t st2 = 0;
+            int64_t a, b;
+            akb_lane_emit(X, c, next_bnd, cs, s2, nullptr, a, b, st2, nr_hint);
+        }
+    }
+}
+
 #ifndef AKB_MINB
 #define AKB_MINB 4
 #endif
@@ -1109,42 +1204,23 @@ __global__ void __launch_bounds__(AK_BLOCK, AKB_MINB) ak_bf_encode_kernel(const 
                         rr = 0x40000000u | (uint32_t)n;
                     } else {
                         const uint32_t kc = (v >> 10) & 3u;
-                        uint32_t len = v >> 12;
-                        int64_t we = p + len;
-                        bool direct = true;
-                        if (len <= AKW_MAXLEN && A.C.e) {
-                            const unsigned long long h = akw_hash(B.text, p, len);
-                            const unsigned long long want = akw_want(h, len);
-                            long long slot;
-                            long long hit = akw_find(A.C, h, want, B.text, p, len, &slot);
-                            if (hit < 0) {
-                                int32_t tmp[AKW_MAXTOK + 1];
-                                AkIdSink local;
-                                local.buf = tmp; local.cap = AKW_MAXTOK + 1; local.stride = 1; local.cnt = 0; local.direct = false;
-                                local.gout = nullptr; local.gbase = 0; local.gcap = 0;
-                                ak_bpe_word(A.M, A.T, B.text, p, we, kc, local, A.pool, st);
-                                n = local.cnt;
-                                if (n <= AKW_MAXTOK && slot >= 0) {
-                                    akw_insert(A.C, slot, want, B.text, p, len, tmp, n);
-                                    hit = akw_find(A.C, h, want, B.text, p, len, &slot);     // ours, or the same word by another lane
-                                }
-                            }
-                            if (hit >= 0) {
-                                n = (int)((akw_ld(A.C.e + (unsigned long long)hit * AKW_ENTRY) & AKW_NTOK_MASK) >> 3);
-                                rr = ((uint32_t)hit << 5) | (uint32_t)n;
-                                direct = false;
-                            }
+                        const uint32_t len = v >> 12;
+                        // hot path: hash, probe, compare -- everything else lives in akb_event_slow (kept out of line so
+                        // that this loop stays small in the instruction cache)
+                        long long hit = -1, slot = -1;
+                        unsigned long long h = 0, want = 0;
+                        const bool cacheable = len <= AKW_MAXLEN && A.C.e != nullptr;
+                        if (cacheable) {
+                            h = akw_hash(B.text, p, len);
+                            want = akw_want(h, len);
+                            hit = akw_find(A.C, h, want, B.text, p, len, &slot);
                         }
-                        if (direct) {
-                            if (len == 0xFFFFFu) {      // clamped: find the real end again
-                                we = akb_word_end(A.T, B.text, p, 0, kc, 0u, 0u, B.off, B.n_rows, X.r_lo, X.r_hi);
-                            }
-                            AkIdSink cntsink;
-                            cntsink.buf = nullptr; cntsink.cap = 0; cntsink.stride = 1; cntsink.cnt = 0; cntsink.direct = false;
-                            cntsink.gout = nullptr; cntsink.gbase = 0; cntsink.gcap = 0;
-                            ak_bpe_word(A.M, A.T, B.text, p, we, kc, cntsink, A.pool, st);
-                            n = cntsink.cnt;
-                            rr = 0x80000000u | (uint32_t)n;
+                        if (hit >= 0) {
+                            n = (int)((akw_ld(A.C.e + (unsigned long long)hit * AKW_ENTRY) & AKW_NTOK_MASK) >> 3);
+                            rr = ((uint32_t)hit << 5) | (uint32_t)n;
+                        } else {
+                            rr = akb_event_slow(A, B, p, len, kc, h, want, slot, cacheable, X.r_lo, X.r_hi, st);
+                            n = (rr & 0x80000000u) ? (int)(rr & 0x3FFFFFFFu) : (int)(rr & 31u);
                         }
                     }
                 }
@@ -1203,64 +1279,12 @@ __global__ void __launch_bounds__(AK_BLOCK, AKB_MINB) ak_bf_encode_kernel(const 
                             if (i + 1 < n) tbase[o + i + 1] = (int32_t)(uint32_t)(q >> 32);
                         }
                     } else {
-                        const uint32_t kc = (v >> 10) & 3u;
-                        const uint32_t len = v >> 12;
-                        int64_t we = p + len;
-                        if (len == 0xFFFFFu) we = akb_word_end(A.T, B.text, p, 0, kc, 0u, 0u, B.off, B.n_rows, X.r_lo, X.r_hi);
-                        AkIdSink ds;
-                        ds.buf = nullptr; ds.cap = 0; ds.stride = 1; ds.cnt = 0; ds.direct = true;
-                        ds.gout = tbase + o; ds.gbase = 0; ds.gcap = (int64_t)(rr & 0x3FFFFFFFu);
-                        uint32_t st2 = 0;
-                        ak_bpe_word(A.M, A.T, B.text, p, we, kc, ds, A.pool, st2);
+                        akb_event_write_direct(A, B, p, v >> 12, (v >> 10) & 3u, X.r_lo, X.r_hi, tbase + o, (int64_t)(rr & 0x3FFFFFFFu));
                     }
                 }
             }
         } else {
-            // more events than the list holds (hundreds of one-byte words / row starts in 480 bytes): lane by lane
-            int64_t nr_hint = -1;
-            if (active && c.rows) {
-                int64_t g = r_w0 + (r_inc - n_row_ev);
-                const int64_t p = cs + (__ffs(c.rows) - 1);
-                while (g < B.n_rows && B.off[g] < p) ++g;
-                nr_hint = g;
-            }
-            AkIdSink sink;
-            sink.buf = nullptr; sink.cap = 0; sink.stride = 1; sink.cnt = 0; sink.direct = false;
-            sink.gout = A.temp; sink.gbase = 0; sink.gcap = 0;
-            int64_t row_first = 0, row_last = 0;
-            if (active) akb_lane_emit(X, c, next_bnd, cs, sink, A.id_splits, row_first, row_last, st, nr_hint);
-            const int cnt = sink.cnt;
-            int inc = cnt;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const int y = __shfl_up_sync(0xFFFFFFFFu, inc, d);
-                if (lane >= d) inc += y;
-            }
-            total = __shfl_sync(0xFFFFFFFFu, inc, 31);
-            const int pre = inc - cnt;
-            unsigned int toff = 0;
-            if (lane == 0) toff = atomicAdd(&s_cursor, (unsigned int)total);
-            toff = __shfl_sync(0xFFFFFFFFu, toff, 0);
-            const bool fits = (int64_t)toff + total <= A.slice_cap;
-            if (lane == 0) {
-                A.wt_total[wt] = total;
-                A.wt_toff[wt] = slice + toff;
-                if (!fits) st |= AK_ST_OVERFLOW;
-            }
-            if (active) {
-                for (int64_t r = row_first; r < row_last; ++r) A.id_splits[r] += pre;
-                if (fits) {
-                    AkIdSink s2 = sink;
-                    s2.cnt = 0;
-                    s2.direct = true;
-                    s2.gout = A.temp + slice + toff + pre;
-                    s2.gbase = 0;
-                    s2.gcap = cnt;
-                    uint32_t st2 = 0;
-                    int64_t a, b;
-                    akb_lane_emit(X, c, next_bnd, cs, s2, nullptr, a, b, st2, nr_hint);
-                }
-            }
+            akb_tile_fallback(A, B, X, c, next_bnd, cs, active, lane, wt, slice, r_w0, r_inc - n_row_ev, &s_cursor, st);
         }
         __syncwarp();
         ak_raise(B.result, st);
