@@ -85,16 +85,19 @@ AK_HD long long akw_find(const AkWordCache& C, unsigned long long h, unsigned lo
     const unsigned long long mask = (1ull << C.bits) - 1ull;
     const uint32_t nw = (len + 7u) >> 3;
     *free_slot = -1;
+    const unsigned long long k0 = akw_key_word(t, s, len, 0);
 #pragma unroll 1
     for (int p = 0; p < AKW_PROBES; ++p) {
         const unsigned long long slot = (h + (unsigned long long)p) & mask;
         const unsigned long long* e = C.e + slot * AKW_ENTRY;
+        // tag and first key word are fetched together: one L2 round trip decides most probes
         const unsigned long long tag = akw_ld(e);
+        const unsigned long long e0 = akw_ld(e + 1);
         if (tag == 0ull) { *free_slot = (long long)slot; return -1; }
-        if ((tag & ~AKW_NTOK_MASK) != want) continue;
+        if ((tag & ~AKW_NTOK_MASK) != want || e0 != k0) continue;
         bool same = true;
 #pragma unroll 1
-        for (uint32_t j = 0; j < nw; ++j)
+        for (uint32_t j = 1; j < nw; ++j)
             if (akw_ld(e + 1 + j) != akw_key_word(t, s, len, j)) { same = false; break; }
         if (same) return (long long)slot;
     }
