@@ -204,6 +204,13 @@ __global__ void ak_tile_rows_kernel(const int64_t* off, int64_t n_rows, int64_t 
     tile_row[k] = r;
 }
 
+// a chunk that straddles the start / end of the text: byte by byte, guarded.  Cold, kept out of line.
+__device__ __noinline__ void akf_load_edge(const uint8_t* text, int64_t cs, int lo, int hi, uint32_t* w) {
+    w[0] = w[1] = w[2] = w[3] = 0;
+#pragma unroll 1
+    for (int i = lo; i < hi; ++i) w[i >> 2] |= (uint32_t)text[cs + i] << ((i & 3) * 8);
+}
+
 template <class CH>
 __device__ __forceinline__ void akf_load_chunk(const uint8_t* text, int64_t cs, int64_t tb, int64_t te, CH& c) {
     int64_t lo = tb - cs, hi = te - cs;
@@ -214,10 +221,9 @@ __device__ __forceinline__ void akf_load_chunk(const uint8_t* text, int64_t cs, 
         const uint4 v = *reinterpret_cast<const uint4*>(text + cs);
         c.w[0] = v.x; c.w[1] = v.y; c.w[2] = v.z; c.w[3] = v.w;
     } else {
-        c.w[0] = c.w[1] = c.w[2] = c.w[3] = 0;
-#pragma unroll
-        for (int i = 0; i < 16; ++i)
-            if (i >= (int)lo && i < (int)hi) c.w[i >> 2] |= (uint32_t)text[cs + i] << ((i & 3) * 8);
+        uint32_t w[4];
+        akf_load_edge(text, cs, (int)lo, (int)hi, w);
+        c.w[0] = w[0]; c.w[1] = w[1]; c.w[2] = w[2]; c.w[3] = w[3];
     }
 }
 

@@ -33,7 +33,7 @@ AK_HD uint32_t ak_hash64(unsigned long long k, uint32_t bits) {
     return (uint32_t)((k * 0x9E3779B97F4A7C15ull) >> (64 - bits));
 }
 
-AK_HD unsigned long long ak_bpe_pair(const AkBpeDev& M, int32_t a, int32_t b) {
+AK_HD_NOINLINE unsigned long long ak_bpe_pair(const AkBpeDev& M, int32_t a, int32_t b) {
     const unsigned long long key = ((unsigned long long)(uint32_t)a << 32) | (uint32_t)b;
     uint32_t h = ak_hash64(key, M.mbits);
     const uint32_t mask = (1u << M.mbits) - 1u;
@@ -54,14 +54,18 @@ AK_HD int32_t ak_bpe_char(const AkBpeDev& M, uint32_t cp) {
 // HF `Word::merge_all` on sym[0..n): returns the new length.  rk[i] caches (rank << 32 | merged id) of the pair
 // (sym[i], sym[i + 1]).
 AK_HD int ak_bpe_merge(const AkBpeDev& M, int32_t* sym, unsigned long long* rk, int n) {
+    // (loops kept rolled: this is the cache-miss path of an instruction-cache-bound kernel)
+#pragma unroll 1
     for (int i = 0; i + 1 < n; ++i) rk[i] = ak_bpe_pair(M, sym[i], sym[i + 1]);
     while (n > 1) {
         unsigned long long best = AK_EMPTY_KEY;
         int bi = -1;
+#pragma unroll 1
         for (int i = 0; i + 1 < n; ++i)
             if (rk[i] < best) { best = rk[i]; bi = i; }
         if (bi < 0) break;
         sym[bi] = (int32_t)(uint32_t)best;
+#pragma unroll 1
         for (int i = bi + 1; i + 1 < n; ++i) { sym[i] = sym[i + 1]; rk[i] = rk[i + 1]; }
         --n;
         rk[bi] = (bi + 1 < n) ? ak_bpe_pair(M, sym[bi], sym[bi + 1]) : AK_EMPTY_KEY;
@@ -113,6 +117,7 @@ AK_HD_NOINLINE int64_t ak_bpe_word(const AkBpeDev& M, const AkTables& T, const u
     unsigned long long rk[AK_BPE_LOCAL];
     int n = 0;
     int64_t q = p;
+#pragma unroll 1
     while (q < re) {
         int len;
         uint32_t cp = ak_decode(t, q, re, len);
@@ -126,6 +131,7 @@ AK_HD_NOINLINE int64_t ak_bpe_word(const AkBpeDev& M, const AkTables& T, const u
     }
     if (n <= AK_BPE_LOCAL) {
         n = ak_bpe_merge(M, sym, rk, n);
+#pragma unroll 1
         for (int i = 0; i < n; ++i) ak_id_put(sink, sym[i]);
         return q;
     }
