@@ -44,10 +44,12 @@ struct AkChunk {
 
 AK_HD uint32_t akf_byte(const AkChunk& c, int i) { return (c.w[i >> 2] >> ((i & 3) * 8)) & 0xFFu; }
 
+// One shared-memory load for ASCII and U+0900-09FF (the closed alphabet of the hot path) through a single index
+// computation -- no divergence between the two -- and the 2-stage global table for everything else.
 AK_HD uint32_t akf_props(const AkTables& T, const uint32_t* lut, uint32_t cp) {
-    if (cp < 0x80u) return lut[cp];
-    uint32_t d = cp - 0x900u;
-    if (d < 0x100u) return lut[128u + d];
+    const uint32_t d = cp - 0x900u;
+    const uint32_t idx = cp < 0x80u ? cp : 128u + d;
+    if (cp < 0x80u || d < 0x100u) return lut[idx];
     return ak_props(T, cp);
 }
 
