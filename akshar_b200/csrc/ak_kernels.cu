@@ -762,7 +762,7 @@ __device__ __forceinline__ AkGState aks_unpack_g(unsigned long long v) {
 
 
 __global__ void __launch_bounds__(AK_BLOCK, 4) ak_sf_kernel(const AkSfArgs A) {
-    __shared__ uint32_t lut[384];
+    __shared__ uint32_t lut[384 + 16];
     __shared__ int32_t cstage[AKS_STAGE * AK_BLOCK];
     __shared__ int32_t rstage[AKS_STAGE * AK_BLOCK];
     __shared__ uint8_t tstage[AKS_STAGE * AK_BLOCK];
@@ -774,6 +774,7 @@ __global__ void __launch_bounds__(AK_BLOCK, 4) ak_sf_kernel(const AkSfArgs A) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int i = tid; i < 384; i += AK_BLOCK)
         lut[i] = i < 128 ? A.T.leaves[((uint32_t)A.T.page_index[0] << 8) | i] : A.T.leaves[((uint32_t)A.T.page_index[9] << 8) | (i - 128)];
+    if (tid < 16) lut[384 + tid] = tid < 14 ? aks_pair_row((uint32_t)tid) : 0u;
     if (tid < 2) s_cursor[tid] = 0;
     __syncthreads();
     const int n_wt = akw_n_tiles(B, A.base0);

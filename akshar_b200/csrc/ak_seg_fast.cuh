@@ -36,6 +36,30 @@ AK_HD uint32_t aks_byte(const AkSChunk& c, int i) { return (c.w[i >> 2] >> ((i &
 AK_HD uint32_t aks_tag_before(const AkSChunk& c, int i) {
     return i < 10 ? (c.tag_lo >> (3 * i)) & 7u : (c.tag_hi >> (3 * (i - 10))) & 7u;
 }
+// GB3 - GB9b decide most pairs from (GCB before, GCB after) alone: one 32-bit word per GCB-before, low half = "no
+// break" pairs, high half = pairs that always break (GB4 / GB5).  Built once per kernel from ak_g_break itself.
+AK_HD uint32_t aks_pair_row(uint32_t ga) {
+    uint32_t row = 0;
+    AkGState g;
+    g.prev = (uint8_t)ga; g.conj = 0; g.pict = 0; g.ri_odd = 0; g.prev_m = 0; g.has_prev = 1;
+    for (uint32_t gb = 0; gb < 14u; ++gb) {
+        const bool ctl_a = ga == GCB_CONTROL || ga == GCB_CR || ga == GCB_LF;
+        const bool ctl_b = gb == GCB_CONTROL || gb == GCB_CR || gb == GCB_LF;
+        if (!ak_g_break(g, gb)) row |= 1u << gb;                                   // props word with only the GCB field set
+        else if ((ctl_a || ctl_b) && !(ga == GCB_CR && gb == GCB_LF)) row |= 1u << (16 + gb);
+    }
+    return row;
+}
+AK_HD bool aks_g_break(const uint32_t* gtab, const AkGState& st, uint32_t wb) {
+    const uint32_t row = gtab[st.prev], gb = AK_GCB(wb);
+    if ((row >> gb) & 1u) return false;
+    if ((row >> (16 + gb)) & 1u) return true;
+    if (st.conj == 2 && AK_INCB(wb) == INCB_CONSONANT) return false;                             // GB9c
+    if (st.pict == 2 && AK_EXTPICT(wb)) return false;                                            // GB11
+    if (st.prev == GCB_RI && gb == GCB_RI && st.ri_odd) return false;                            // GB12/13
+    return true;
+}
+
 AK_HD void aks_g_reset(AkGState& g) { g.prev = 0; g.conj = 0; g.pict = 0; g.ri_odd = 0; g.prev_m = 0; g.has_prev = 0; }
 
 AK_HD uint32_t aks_decode_at(const AkSChunk& c, int i, uint32_t b) {
@@ -49,6 +73,7 @@ AK_HD uint32_t aks_decode_at(const AkSChunk& c, int i, uint32_t b) {
 // ---- phase A -------------------------------------------------------------------------------------------------
 // (loops over the byte positions are ROLLED: these kernels are instruction-cache bound)
 AK_HD void aks_phase_a(const AkTables& T, const uint32_t* lut, AkSChunk& c, bool matras) {
+    const uint32_t* gtab = lut + 384;      // 16 pair-rule rows follow the property table
     uint32_t lead = 0, brk = 0, fix = 0, rchg = 0, tag_lo = 0, tag_hi = 0, flags = 0;
     uint32_t cur = AKS_CUR_IN, first_strong = AKF_NONE;
     AkGState g;
@@ -87,7 +112,7 @@ AK_HD void aks_phase_a(const AkTables& T, const uint32_t* lut, AkSChunk& c, bool
             // grapheme clusters
             if (!synced) fix |= 1u << i;
             if (g.has_prev) {
-                bool bk = ak_g_break(g, w);
+                bool bk = aks_g_break(gtab, g, w);
                 if (matras && (g.prev_m || ak_is_matra_or_halant(cp))) bk = true;
                 if (bk) brk |= 1u << i;
             }
@@ -125,6 +150,7 @@ struct AkSNeighbor {
 AK_HD bool aks_phase_b(const AkTables& T, const uint32_t* lut, AkSChunk& c, const AkSNeighbor& prev, bool matras,
                        bool want_c, bool want_r, uint32_t& in_cur) {
     in_cur = prev.end_cur;
+    const uint32_t* gtab = lut + 384;
     if (want_c && c.fix) {
         if (!(prev.flags & AKS_EXACT_G)) return false;
         AkGState g = prev.g;
@@ -150,7 +176,7 @@ AK_HD bool aks_phase_b(const AkTables& T, const uint32_t* lut, AkSChunk& c, cons
             else cp = ((b & 0x07u) << 18) | (b1 << 12) | (b2 << 6) | b3;
             const uint32_t w = akf_props(T, lut, cp);
             if (g.has_prev) {
-                bool bk = ak_g_break(g, w);
+                bool bk = aks_g_break(gtab, g, w);
                 if (matras && (g.prev_m || ak_is_matra_or_halant(cp))) bk = true;
                 if (bk) brk |= 1u << i;
             }

@@ -339,6 +339,8 @@ void hh_seg_fast(const uint8_t* text, const int64_t* off, int64_t n_rows, uint32
     AkTables T = host_tables();
     std::vector<uint32_t> lut(384);
     for (int i = 0; i < 384; ++i) lut[(size_t)i] = i < 128 ? ak_props(T, (uint32_t)i) : ak_props(T, 0x900u + (uint32_t)(i - 128));
+    lut.resize(400);
+    for (uint32_t ga = 0; ga < 16; ++ga) lut[384 + ga] = ga < 14 ? aks_pair_row(ga) : 0u;
     const bool want_c = (flags & AK_SEG_CLUSTERS) != 0, want_r = (flags & AK_SEG_RUNS) != 0, matras = (flags & AK_SEG_MATRAS) != 0;
     const int64_t tb = off[0], te = off[n_rows], base0 = tb;
     std::vector<uint8_t> rowstart((size_t)(te - base0) + 64, 0);
