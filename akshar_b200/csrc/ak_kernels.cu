@@ -231,11 +231,13 @@ __device__ __forceinline__ void akf_load_chunk(const uint8_t* text, int64_t cs, 
 // work list, and two small kernels run the exact walker over that list with one thread per entry.  A 16-byte walk
 // costs tens of microseconds of dependent instructions; inside the tile kernels it would stall its whole CTA (and,
 // through an ordered tile prefix, every later tile), on the list thousands of them overlap.
+#define AK_SLOW_BYTES 40
 struct AkSlowEntry {
     int64_t pos;         // chunk start (absolute byte index)
     int64_t out_base;    // filled by the write kernel: where this chunk's output starts
-    int32_t cnt;         // filled by the slow count kernel
+    int32_t cnt;         // filled by the slow kernel's first pass
     int32_t tile;
+    uint8_t bytes[AK_SLOW_BYTES];      // the chunk's output when it fits (else the second pass walks again)
 };
 
 struct AkNfWork {
@@ -402,11 +404,12 @@ __global__ void __launch_bounds__(128) ak_nf_slow_kernel(const AkNfSlowArgs A) {
         const int64_t rlo = r0 > 0 ? r0 - 1 : 0, rhi = r1 > B.n_rows ? B.n_rows : r1;
         uint32_t st = 0;
         if (!A.write) {
-            const int cnt = (int)ak_norm_span(A.T, B.text, B.off, B.n_rows, rlo, rhi, ss, se, NFLAGS, AK_LOOKBACK_LIMIT, nullptr,
-                                              nullptr, 0, st);
+            // one walk: bytes into the entry, row offsets relative to the chunk's output (the write kernel rebases them)
+            const int cnt = (int)ak_norm_span(A.T, B.text, B.off, B.n_rows, rlo, rhi, ss, se, NFLAGS, AK_LOOKBACK_LIMIT,
+                                              A.W.slow[j].bytes, A.out_off, 0, st, AK_SLOW_BYTES);
             A.W.slow[j].cnt = cnt;
             atomicAdd(&A.W.tile_total[e.tile], cnt);
-        } else {
+        } else if (e.cnt > AK_SLOW_BYTES) {
             uint8_t* dst = (e.out_base + e.cnt <= A.out_cap) ? A.out + e.out_base : nullptr;
             ak_norm_span(A.T, B.text, B.off, B.n_rows, rlo, rhi, ss, se, NFLAGS, AK_LOOKBACK_LIMIT, dst, A.out_off, e.out_base, st);
         }
@@ -495,7 +498,14 @@ __global__ void __launch_bounds__(AK_BLOCK) ak_nf_write_kernel(const AkFastNormA
         s_emit[tid] = info;
         s_pre[tid] = (uint32_t)pre;
         if (slow) {
-            if (sidx < W.slow_cap) W.slow[sidx].out_base = base + pre;
+            if (sidx < W.slow_cap) {
+                W.slow[sidx].out_base = base + pre;
+                if (cnt <= AK_SLOW_BYTES && fits) {
+                    uint8_t* dst = staged ? stage + pad + pre : A.out + base + pre;
+                    const uint8_t* src = W.slow[sidx].bytes;
+                    for (int i = 0; i < cnt; ++i) dst[i] = src[i];
+                }
+            }
         } else if (info && fits) {
             akf_write(c, info, staged ? stage + pad + pre : A.out + base + pre);
         }
@@ -520,6 +530,7 @@ __global__ void __launch_bounds__(AK_BLOCK) ak_nf_write_kernel(const AkFastNormA
             const int th = wq * 32 + 1 + (within >> 4), i = within & 15;
             const uint32_t e = s_emit[th];
             if (!(e & 0x80000000u)) A.out_off[r] = base + s_pre[th] + __popc(e & ((1u << i) - 1u));
+            else A.out_off[r] += base + s_pre[th];       // the slow pass left it relative to the chunk's output
         }
         __syncthreads();
     }

@@ -45,10 +45,12 @@ AK_HD int64_t ak_row_lower_bound(const int64_t* off, int64_t lo, int64_t hi, int
 struct AkNormSink {
     uint8_t* out;      // nullptr: count only
     int64_t cnt;
+    int64_t cap;       // bytes `out` can take; the count stays exact beyond it
 };
 AK_HD void ak_sink_put(AkNormSink& s, uint32_t cp) {
-    if (s.out) s.cnt += ak_encode(cp, s.out + s.cnt);
-    else s.cnt += ak_utf8_len(cp);
+    const int len = ak_utf8_len(cp);
+    if (s.out && s.cnt + len <= s.cap) ak_encode(cp, s.out + s.cnt);
+    s.cnt += len;
 }
 
 struct AkCollapse {
@@ -235,13 +237,15 @@ AK_HD_NOINLINE uint32_t ak_next_kept(const AkTables& T, const uint8_t* t, int64_
 // out_off: nullptr or the output row-offset array; entry r gets (out_base + bytes emitted before row r).
 AK_HD_NOINLINE int64_t ak_norm_span(const AkTables& T, const uint8_t* t, const int64_t* off, int64_t n_rows,
                                     int64_t r_lo, int64_t r_hi, int64_t s, int64_t e, uint32_t flags, int64_t limit,
-                                    uint8_t* out, int64_t* out_off, int64_t out_base, uint32_t& status) {
+                                    uint8_t* out, int64_t* out_off, int64_t out_base, uint32_t& status,
+                                    int64_t out_cap = 0x7FFFFFFFFFFFFFFFll) {
     const int64_t total_end = off[n_rows];
     const bool clean = (flags & AK_NORM_COLLAPSE) != 0;
     const bool nfc = (flags & AK_NORM_NO_NFC) == 0;
     AkNormSink sink;
     sink.out = out;
     sink.cnt = 0;
+    sink.cap = out_cap;
     int64_t p = s;
     // skip continuation bytes of a code point owned by the previous span (never past a row start: valid UTF-8)
     if (p < total_end && p > off[0]) {
