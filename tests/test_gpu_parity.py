@@ -294,3 +294,39 @@ def test_large_properties(A, eng, models_dir):
         cps = [ord(ch) for ch in e]
         assert ce[cs[i]:cs[i + 1]].tolist() == O.cp_ends_to_byte_ends(cps, O.segment_breaks(cps))
         assert iv[isp[i]:isp[i + 1]].tolist() == O.bpe_encode(om, e)
+
+
+def test_full_size_bpe_1gib(A, models_dir):
+    """BASELINE.json configs[1] at its full size (1 GiB synthetic Hinglish, BPE-24k): properties that do not need the
+    oracle on every row -- per-row framing by <s> ... </s>, batch-split invariance through the pipelined host path,
+    checksums of checksums -- plus the oracle on a seeded sample of rows."""
+    import sys
+    import torch
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), '..'))
+    import bench
+    data, off = bench.make_corpus('hinglish', 1 << 30, 0)
+    n = off.size - 1
+    tk = A.aksharTokenizer(os.path.join(models_dir, 'bpe24k.json'), 'bpe')
+    h_data, h_off = torch.from_numpy(data).pin_memory(), torch.from_numpy(off).pin_memory()
+    ids, norm = tk._eng.tokenizer_encode_batch((h_data, h_off), 0)
+    v, sp = ids.values, ids.splits
+    assert int(sp[-1]) == v.numel() and int(sp[0]) == 0
+    # every row is framed: first id <s> = 2, last id </s> = 3, and neither occurs anywhere else
+    assert bool((v[sp[:-1]] == 2).all()) and bool((v[sp[1:] - 1] == 3).all())
+    assert int((v == 2).sum()) == n and int((v == 3).sum()) == n
+    # the same batch in 11 chunks through the pipelined host path: identical stream (a checksum of checksums would do;
+    # the tensors are compared whole)
+    pv, ps = tk._eng.encode_host_pipelined(h_data, h_off, 0, chunk_bytes=100 << 20)
+    assert torch.equal(pv, v.cpu()) and torch.equal(ps, sp.cpu())
+    # oracle on a seeded sample
+    om = O.BpeModel(os.path.join(models_dir, 'bpe24k.json'))
+    rng = np.random.default_rng(11)
+    b = data
+    hv, hs = pv.numpy(), ps.numpy()
+    nb = norm.data[:norm.end].cpu().numpy()
+    no = norm.offsets.cpu().numpy()
+    for i in np.sort(rng.choice(n, size=2000, replace=False)):
+        s = b[off[i]:off[i + 1]].tobytes().decode('utf-8')
+        e = O.normalize_text(s)
+        assert nb[no[i]:no[i + 1]].tobytes().decode('utf-8') == e
+        assert hv[hs[i]:hs[i + 1]].tolist() == O.bpe_encode(om, e)
