@@ -362,13 +362,16 @@ class Engine:
 
 
     # ------------------------------------------------------------------ host -> ids, pipelined
-    def encode_host_pipelined(self, h_data, h_off, kind, normalize_roman=True, clean_hinglish=True, chunk_bytes=96 << 20,
+    def encode_host_pipelined(self, h_data, h_off, kind, normalize_roman=True, clean_hinglish=True, chunk_bytes=None,
                               out_ids=None, out_splits=None):
         """aksharTokenizer.encode over a batch that lives in (pinned) HOST memory, returning host tensors:
         the batch is cut into row ranges of ~chunk_bytes; the H2D copy of chunk k+1, the kernels of chunk k and the
         D2H copy of chunk k-1 run on three streams.  -> (ids int32 [total] pinned, row_splits int64 [n_rows + 1] pinned)"""
+        import os
         import numpy as np
         from . import shard
+        if chunk_bytes is None:
+            chunk_bytes = int(os.environ.get('AKSHAR_CHUNK_MB', '128')) << 20
         dev = self.device
         n_rows = h_off.numel() - 1
         off_np = h_off.numpy()
