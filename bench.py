@@ -29,8 +29,14 @@ for p in (ROOT, os.path.join(ROOT, 'tools')):
         sys.path.insert(0, p)
 
 MODELS = os.path.join(ROOT, 'tests', 'golden', 'models')
-# dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu --set full captures in profiles/ (1 GiB runs)
-TRAFFIC = {}
+# DRAM traffic per INPUT byte of each hot kernel: (dram__bytes_read.sum + dram__bytes_write.sum) / input bytes from the
+# `ncu --set full` captures at 256 MiB summarised in profiles/r01_ncu_full_summary.csv; scaled to the run's size below
+TRAFFIC_PER_INPUT_BYTE = {
+    'ak_nf_classify_kernel': (286.12 + 60.63) / 268.44,
+    'ak_nf_write_kernel': (362.62 + 249.38) / 268.44,
+    'ak_bf_encode_kernel': (977.09 + 891.86) / 268.44,      # local-memory (stack) spill traffic included
+    'ak_sf_kernel': (335.89 + 663.33) / 268.44,
+}
 CHUNK = 32 << 20
 SEED = 20261018
 
@@ -387,7 +393,10 @@ def main():
                 'd2h_bytes_per_step': int(tot_d2h / world), 'ms_per_step': e2e_ms},
         'gpu_launches': int(tot_launch),
         'roofline': {'bound': 'hbm', 'kernel': dom, 'achieved': ach, 'peak': peak, 'peak_source': peak_kind, 'unit': 'GB/s',
-                     'frac': ach / peak, 'traffic': TRAFFIC.get(dom), 'ms': stages[dom][0], 'algorithmic_bytes': stages[dom][1],
+                     'frac': ach / peak,
+                     'traffic': (int(TRAFFIC_PER_INPUT_BYTE[dom] * nbytes) if dom in TRAFFIC_PER_INPUT_BYTE else None),
+                     'traffic_source': 'ncu --set full at 256 MiB, scaled by input bytes (profiles/r01_ncu_full_summary.csv)',
+                     'ms': stages[dom][0], 'algorithmic_bytes': stages[dom][1],
                      'kernels_ms': {k: v[0] for k, v in stages.items()},
                      'kernels_frac': {k: v[1] / (v[0] * 1e-3) / 1e9 / peak for k, v in stages.items()}},
         'cpu_baseline': cpu, 'clocks': clocks,
