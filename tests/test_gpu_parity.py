@@ -296,6 +296,25 @@ def test_large_properties(A, eng, models_dir):
         assert iv[isp[i]:isp[i + 1]].tolist() == O.bpe_encode(om, e)
 
 
+def test_corpus_front_end(A, models_dir, tmp_path):
+    from akshar_b200 import corpus
+    lines = sc.Corpus('social', 31).lines(400000)
+    src = tmp_path / 'corpus.txt'
+    src.write_text('\n'.join(['  ' + l + ' \t' if i % 7 == 0 else l for i, l in enumerate(lines)]) + '\n\n  \n', encoding='utf-8')
+    out = tmp_path / 'corpus.preprocessed.txt'
+    corpus.preprocess_corpus(str(src), str(out))
+    exp = [O.normalize_text(l.strip()) for l in src.read_text(encoding='utf-8').split('\n') if l.strip()]
+    assert out.read_text(encoding='utf-8') == ''.join(e + '\n' for e in exp)
+    # the whole file as ONE string, like `akshar tokenize -i FILE --format id` (one long row for the kernels)
+    tk = A.aksharTokenizer(os.path.join(models_dir, 'bpe24k.json'), 'bpe')
+    om = O.BpeModel(os.path.join(models_dir, 'bpe24k.json'))
+    text = src.read_text(encoding='utf-8')
+    assert corpus.tokenize_file(tk, str(src), 'id') == ' '.join(map(str, O.bpe_encode(om, O.normalize_text(text))))
+    fb = A.aksharTokenizer()
+    assert corpus.tokenize_file(fb, str(src), 'text') == ' '.join(O.segment_akshars(O.normalize_text(text)))
+    assert corpus.encode_lines(tk, str(src))[:50] == [O.bpe_encode(om, e) for e in exp[:50]]
+
+
 def test_full_size_bpe_1gib(A, models_dir):
     """BASELINE.json configs[1] at its full size (1 GiB synthetic Hinglish, BPE-24k): properties that do not need the
     oracle on every row -- per-row framing by <s> ... </s>, batch-split invariance through the pipelined host path,
