@@ -220,7 +220,7 @@ AK_HD void akb_phase_a(const AkTables& T, const uint32_t* lut, AkBChunk& c) {
             const uint32_t kc = AK_HFCLASS(w);
             lead |= 1u << i;
             cls |= kc << (2 * i);
-            if (!AK_ALLOW(w)) flags |= AKB_ALPHABET;
+            if (!AK_BPE_SAFE(w)) flags |= AKB_ALPHABET;
             if (!first_seen && !row_here) {
                 first_pos = (uint32_t)i;
                 first_w = w;

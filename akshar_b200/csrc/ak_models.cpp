@@ -501,7 +501,7 @@ std::string ak_parse_spm_model(const void* proto, size_t len, AkUniHost& out) {
         if (node_piece[node] < 0) node_piece[node] = (int32_t)i;     // first id wins for duplicated surface forms
         if (ncp > out.max_len) out.max_len = ncp;
         if (t == 1) { out.score[i] = out.raw_score[i]; out.usable[i] = 1; }
-        else if (t == 4) { out.score[i] = (float)ncp * out.max_score - 0.1f; out.usable[i] = 1; }
+        else if (t == 4) return "USER_DEFINED pieces are not supported (scripts/train_spm.py defines none)";
     }
     if (out.max_len >= 62) return "piece longer than 61 code points";
     out.tbits = 4;

@@ -225,7 +225,7 @@ AK_HD_NOINLINE void ak_bpe_span(const AkBpeDev& M, const AkTables& T, const uint
         int len;
         uint32_t cp = ak_decode(t, p, re, len);
         uint32_t w = ak_props(T, cp);
-        if (!AK_ALLOW(w)) status |= AK_ST_ALPHABET;
+        if (!AK_BPE_SAFE(w)) status |= AK_ST_ALPHABET;
         uint32_t cc = AK_CCC(w);
         if ((AK_QC(w) != 0 || (cc != 0 && prev_ccc > cc)) && p >= checked_until) {
             if (ak_segment_changes(T, t, p, rs, re, limit, &checked_until, status)) changed = true;
@@ -287,7 +287,13 @@ AK_HD_NOINLINE int64_t ak_unigram_forward(const AkUniDev& U, const uint8_t* t, i
     int64_t ts = rs, te = re;
     if (U.flags & 2) {
         while (ts < te && t[ts] == 0x20u) ++ts;
-        while (te > ts && t[te - 1] == 0x20u) --te;
+        // trailing whitespace is removed from the ESCAPED output (sentencepiece normalizer.cc): with
+        // escape_whitespaces a literal U+2581 (E2 96 81) at the end of the row goes too
+        for (;;) {
+            if (te > ts && t[te - 1] == 0x20u) --te;
+            else if ((U.flags & 4) && te - ts >= 3 && t[te - 3] == 0xE2u && t[te - 2] == 0x96u && t[te - 1] == 0x81u) te -= 3;
+            else break;
+        }
     }
     if (ts >= te) return 0;
     float best[AK_UNI_RING];
@@ -325,9 +331,12 @@ AK_HD_NOINLINE int64_t ak_unigram_forward(const AkUniDev& U, const uint8_t* t, i
                 if (pid1) {
                     uint32_t pid = pid1 - 1u;
                     if (U.usable[pid]) {
-                        float cand = bi + U.score[pid];
+                        // sentencepiece 0.2.1 unigram_model.cc: the piece score is promoted to double by a ?: whose other
+                        // arm is a double expression; the candidate is a DOUBLE sum, compared as a double against the
+                        // stored float and rounded to float only when stored.  Reproduced operation for operation.
+                        const double cand = (double)U.score[pid] + (double)bi;
                         int slot = (int)((i + k) & (AK_UNI_RING - 1));
-                        if (cand > best[slot]) { best[slot] = cand; bk[slot] = ((uint32_t)k << 24) | pid; }
+                        if (cand > (double)best[slot]) { best[slot] = (float)cand; bk[slot] = ((uint32_t)k << 24) | pid; }
                         if (k == 1) single = true;
                     }
                 }

@@ -27,6 +27,7 @@
 #define AK_CASE_IGNORABLE(w) (((w) >> 26) & 1u)
 #define AK_CASED(w) (((w) >> 27) & 1u)
 #define AK_COMP_FIRST(w) (((w) >> 28) & 1u)
+#define AK_BPE_SAFE(w) (((w) >> 29) & 1u)      // HF's NFKC (Unicode <= 12) acts on it like the NFC implemented here
 // an atomic starter that can neither decompose nor compose with a following mark: a QC=Maybe mark right after it
 // is left alone by NFC (e.g. Devanagari consonant + nukta, except U+0928 / U+0930 / U+0933)
 #define AK_INERT_BASE(w) (((w) & ((255u << 16) | (3u << 11) | (1u << 25) | (1u << 28))) == 0u)

@@ -40,7 +40,8 @@ enum {
     AKSHAR_ST_OVERFLOW = 1,      /* an output capacity was too small: re-run with capacity >= total */
     AKSHAR_ST_NFC_SEGMENT = 2,   /* a combining sequence needing NFC work exceeds 64 decomposed code points */
     AKSHAR_ST_PATHOLOGICAL = 4,  /* bounded look-back gave up: re-run the same call with AKSHAR_MODE_ROWS */
-    AKSHAR_ST_ALPHABET = 8,      /* BPE encode met a code point outside normalize_text's closed alphabet */
+    AKSHAR_ST_ALPHABET = 8,      /* BPE encode met a code point on which HF's NFKC differs from NFC (compatibility
+                                  * characters, marks newer than its Unicode tables) or a '<' (added-token syntax) */
     AKSHAR_ST_SPIN = 16,
     AKSHAR_ST_WORD = 32,         /* BPE word longer than the per-word capacity: re-run with AKSHAR_MODE_ROWS */
 };

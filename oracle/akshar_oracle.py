@@ -58,6 +58,7 @@ class _Tables:
         self.ccc = vals('ccc')
         self.nfc_qc = vals('nfc_qc')
         self.hf_class = vals('hf_class')
+        self.bpe_safe = flags('bpe_safe')
         self.decomp = {int(k, 16): v for k, v in j['decomp'].items()}
         self.pairs = {(a, b): c for a, b, c in j['pairs']}
         self.latin_lower = {int(k, 16): v for k, v in j['latin_lower'].items()}
@@ -537,12 +538,12 @@ def bpe_encode(model, text):
     T = tables()
     cps = [ord(c) for c in text]
     for c in cps:
-        if not T.allow[c] or T.nfc_qc[c] == 1:
-            raise NotImplementedError('BPE oracle covers the closed alphabet produced by normalize_text (U+%04X)' % c)
-    # HF NFKC restricted to this alphabet: the exotic spaces fold to U+0020, nothing decomposes (NFC already ran),
-    # but marks that became adjacent only after filter_garbage / remove_elongations are still canonically
-    # reordered and composed (e.g. U+0928 ZWNJ U+093C -> U+0928 U+093C -> U+0929).
-    cps = nfc_cps([0x20 if c in _NFKC_SPACE else c for c in cps])
+        if not T.bpe_safe[c]:
+            raise NotImplementedError('BPE oracle: HF NFKC differs from NFC on U+%04X (or it is "<")' % c)
+    # HF NFKC restricted to these code points == NFC, except that the exotic spaces fold to U+0020 (all of them are
+    # \\s, so the fold never shows); marks that became adjacent only after filter_garbage / remove_elongations are
+    # canonically reordered and composed (e.g. U+0928 ZWNJ U+093C -> U+0928 U+093C -> U+0929).
+    cps = nfc_cps([0x20 if (T.hf_class[c] == 2) else c for c in cps])
     ids = []
     i, n = 0, len(cps)
     hf = T.hf_class
@@ -697,7 +698,9 @@ def spm_normalize(model, text):
             else:
                 prev_space = False
             out.append(c)
-        while out and out[-1] == 0x20:
+        # trailing whitespace is removed from the ESCAPED output (sentencepiece normalizer.cc "Ignores tailing space"):
+        # with escape_whitespaces a literal U+2581 at the end of the input goes too
+        while out and (out[-1] == 0x20 or (model.escape_whitespaces and out[-1] == 0x2581)):
             out.pop()
         cps = out
     if not cps:
@@ -737,10 +740,13 @@ def unigram_encode(model, text):
                 continue
             if typ == model.USER_DEFINED:
                 sc = np.float32(np.float32(ln) * model.max_score - np.float32(0.1))
-            cand = np.float32(bi + sc)
+            # sentencepiece 0.2.1 unigram_model.cc (EncodeOptimized): `score` is the result of a ?: whose other arm is a
+            # double expression, so the piece score is PROMOTED TO DOUBLE, the candidate is a double sum, it is compared
+            # against the stored float as a double, and rounded to float only when stored
+            cand = float(sc) + float(bi)
             t = i + ln
-            if best[t] is NEG or cand > best[t]:
-                best[t] = cand
+            if best[t] is NEG or cand > float(best[t]):
+                best[t] = np.float32(cand)
                 back[t] = (i, pid)
             if ln == 1:
                 single = True

@@ -27,3 +27,20 @@ def golden():
 @pytest.fixture(scope='session')
 def models_dir():
     return MODELS
+
+
+@pytest.fixture(scope='session')
+def bpe_rows(golden):
+    """golden rows whose normalized text the BPE path accepts: every code point BPE-safe (HF's NFKC acts on it like NFC;
+    U+09FE, newer than HF's Unicode tables, is the one member of normalize_text's alphabet that is not).  The other
+    rows must make the encoder fail loudly (AKSHAR_ST_ALPHABET)."""
+    import akshar_oracle as O
+    T = O.tables()
+    return [r for r in golden['rows'] if all(T.bpe_safe[ord(c)] for c in r['norm'])]
+
+
+@pytest.fixture(scope='session')
+def golden_raw():
+    """vectors recorded from the unmodified reference with clean_hinglish=False (tools/make_golden_raw.py)"""
+    with gzip.open(os.path.join(GOLDEN, 'reference_vectors_raw.json.gz'), 'rb') as f:
+        return json.loads(f.read().decode('utf-8'))

@@ -73,11 +73,11 @@ def test_signature_golden(A, golden):
 
 @pytest.mark.parametrize('name,kind', [('bpe24k', 'bpe'), ('bpe_corpus', 'bpe'), ('spm24k', 'sentencepiece'),
                                        ('spm_corpus', 'sentencepiece')])
-def test_encode_golden(A, golden, models_dir, name, kind):
+def test_encode_golden(A, golden, bpe_rows, models_dir, name, kind):
     path = os.path.join(models_dir, name + ('.json' if kind == 'bpe' else '.model'))
     tk = A.aksharTokenizer(path, kind)
     assert tk.vocab_size() == golden['vocab_size'][name]
-    rows = golden['rows']
+    rows = bpe_rows if kind == 'bpe' else golden['rows']
     # raw text through the fused normalize + encode pipeline (aksharTokenizer.encode over a batch)
     assert tk.encode_batch([r['in'] for r in rows]) == [r['ids_' + name] for r in rows]
     # already-normalized rows through the stand-alone encoders
@@ -86,12 +86,14 @@ def test_encode_golden(A, golden, models_dir, name, kind):
     assert got == [r['ids_' + name] for r in rows]
 
 
-def test_pieces_and_decode_golden(A, golden, models_dir):
+def test_pieces_and_decode_golden(A, golden, bpe_rows, models_dir):
     tb = A.aksharTokenizer(os.path.join(models_dir, 'bpe24k.json'), 'bpe')
     tu = A.aksharTokenizer(os.path.join(models_dir, 'spm24k.model'))
-    rows = golden['rows'][:400]
+    rows = bpe_rows[:400]
     assert tb.tokenize_batch([r['in'] for r in rows]) == [r['pieces_bpe24k'] for r in rows]
+    rows = golden['rows'][:400]
     assert tu.tokenize_batch([r['in'] for r in rows]) == [r['pieces_spm24k'] for r in rows]
+    rows = bpe_rows[:400]
     for r in rows[:200]:
         assert tb.decode(r['ids_bpe24k']) == r['dec_bpe24k']
         assert tu.decode(r['ids_spm24k']) == r['dec_spm24k']
@@ -294,6 +296,27 @@ def test_large_properties(A, eng, models_dir):
         cps = [ord(ch) for ch in e]
         assert ce[cs[i]:cs[i + 1]].tolist() == O.cp_ends_to_byte_ends(cps, O.segment_breaks(cps))
         assert iv[isp[i]:isp[i + 1]].tolist() == O.bpe_encode(om, e)
+
+
+def test_raw_mode_golden(A, golden_raw, models_dir):
+    """clean_hinglish=False (reference vectors): emoji, accents and other scripts reach the models"""
+    from akshar_b200.batch import BatchStatusError
+    T = O.tables()
+    rows = golden_raw['rows']
+    tu = A.aksharTokenizer(os.path.join(models_dir, 'spm24k.model'), 'sentencepiece', clean_hinglish=False)
+    assert tu.encode_batch([r['in'] for r in rows]) == [r['ids_spm24k'] for r in rows]
+    tb = A.aksharTokenizer(os.path.join(models_dir, 'bpe24k.json'), 'bpe', clean_hinglish=False)
+    safe = [r for r in rows if all(T.bpe_safe[ord(c)] for c in r['norm_nc'])]
+    assert len(safe) > 1500
+    assert tb.encode_batch([r['in'] for r in safe]) == [r['ids_bpe24k'] for r in safe]
+    tb2 = A.aksharTokenizer(os.path.join(models_dir, 'bpe24k.json'), 'bpe', normalize_roman=False, clean_hinglish=False)
+    safe2 = [r for r in rows if all(T.bpe_safe[ord(c)] for c in O.normalize_text(r['in'], False, False))]
+    assert tb2.encode_batch([r['in'] for r in safe2]) == [r['ids_bpe24k_raw'] for r in safe2]
+    # compatibility characters / added-token syntax: refused loudly, never answered wrongly
+    with pytest.raises(BatchStatusError):
+        tb.encode_batch(['ok', 'x\ufb01y'])
+    with pytest.raises(BatchStatusError):
+        tb.encode_batch(['<s> hi </s>'])
 
 
 def test_corpus_front_end(A, models_dir, tmp_path):

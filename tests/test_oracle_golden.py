@@ -70,7 +70,7 @@ def test_signature(golden):
 
 
 @pytest.mark.parametrize('name,kind', [('bpe24k', 'bpe'), ('bpe_corpus', 'bpe'), ('spm24k', 'spm'), ('spm_corpus', 'spm')])
-def test_subword_ids(golden, models_dir, name, kind):
+def test_subword_ids(golden, bpe_rows, models_dir, name, kind):
     if kind == 'bpe':
         m = O.BpeModel(os.path.join(models_dir, name + '.json'))
         enc = lambda t: O.bpe_encode(m, t)
@@ -78,14 +78,39 @@ def test_subword_ids(golden, models_dir, name, kind):
         m = O.UnigramModel(os.path.join(models_dir, name + '.model'))
         enc = lambda t: O.unigram_encode(m, t)
     assert m.vocab_size() == golden['vocab_size'][name]
-    for r in golden['rows']:
+    rows = bpe_rows if kind == 'bpe' else golden['rows']
+    assert len(rows) > 2000
+    for r in rows:
         assert enc(r['norm']) == r['ids_' + name], r['in']
+    if kind == 'bpe':
+        with pytest.raises(NotImplementedError):
+            enc('a\u09fe')
 
 
-def test_pieces_and_decode(golden, models_dir):
+def test_pieces_and_decode(golden, bpe_rows, models_dir):
     bm = O.BpeModel(os.path.join(models_dir, 'bpe24k.json'))
     um = O.UnigramModel(os.path.join(models_dir, 'spm24k.model'))
     for r in golden['rows'][:600]:
         assert O.unigram_pieces(um, r['norm']) == r['pieces_spm24k']
+    for r in bpe_rows[:600]:
         assert [bm.id_to_token[i] for i in r['ids_bpe24k']] == r['pieces_bpe24k']
         assert O.bpe_decode(bm, r['ids_bpe24k']) == r['dec_bpe24k']
+
+
+def test_raw_mode_ids(golden_raw, models_dir):
+    """clean_hinglish=False: text outside the closed alphabet reaches the models (emoji, accents, other scripts)"""
+    T = O.tables()
+    bm = O.BpeModel(os.path.join(models_dir, 'bpe24k.json'))
+    um = O.UnigramModel(os.path.join(models_dir, 'spm24k.model'))
+    n_bpe = 0
+    for r in golden_raw['rows']:
+        n = r['norm_nc']
+        assert O.normalize_text(r['in'], clean_hinglish=False) == n
+        assert O.unigram_encode(um, n) == r['ids_spm24k'], r['in']
+        if all(T.bpe_safe[ord(c)] for c in n):
+            n_bpe += 1
+            assert O.bpe_encode(bm, n) == r['ids_bpe24k'], r['in']
+        raw = O.normalize_text(r['in'], normalize_roman=False, clean_hinglish=False)
+        if all(T.bpe_safe[ord(c)] for c in raw):
+            assert O.bpe_encode(bm, raw) == r['ids_bpe24k_raw'], r['in']
+    assert n_bpe > 1500

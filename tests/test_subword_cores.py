@@ -18,9 +18,9 @@ def _rows(golden, limit=None):
 
 @pytest.mark.parametrize('name', ['bpe24k', 'bpe_corpus'])
 @pytest.mark.parametrize('span', [32, 7, 100000])
-def test_bpe_ids_match_reference(golden, models_dir, name, span):
+def test_bpe_ids_match_reference(golden, bpe_rows, models_dir, name, span):
     assert W.load_bpe(os.path.join(models_dir, name + '.json')) == golden['vocab_size'][name]
-    rows = _rows(golden)
+    rows = bpe_rows
     data, off = sc.pack([r['norm'] for r in rows])
     ids, splits, st, attempt = W.bpe(data, off, span=span)
     assert st == 0
@@ -31,9 +31,9 @@ def test_bpe_ids_match_reference(golden, models_dir, name, span):
     assert ids.tolist() == [i for e in exp for i in e]
 
 
-def test_bpe_small_stage_and_random_spans(golden, models_dir):
+def test_bpe_small_stage_and_random_spans(golden, bpe_rows, models_dir):
     W.load_bpe(os.path.join(models_dir, 'bpe24k.json'))
-    rows = _rows(golden, 3000)
+    rows = bpe_rows
     lines = [r['norm'] for r in rows] + ['', '', '']
     exp = [r['ids_bpe24k'] for r in rows] + [[2, 3]] * 3
     data, off = sc.pack(lines)
@@ -102,10 +102,10 @@ def test_loader_rejects_unsupported(models_dir):
 
 
 @pytest.mark.parametrize('real,cache_bits,stage_cap', [(30, 14, 24), (1, 4, 2), (3, 8, 24), (30, 2, 24)])
-def test_bpe_fast_structure(golden, models_dir, real, cache_bits, stage_cap):
+def test_bpe_fast_structure(golden, bpe_rows, models_dir, real, cache_bits, stage_cap):
     """chunked classification + word cache (tiny tables force probing and misses) == the reference ids"""
     W.load_bpe(os.path.join(models_dir, 'bpe24k.json'))
-    rows = _rows(golden)
+    rows = bpe_rows
     lines = [r['norm'] for r in rows] + ['', '', 'ab' * 200 + ' ' + 'कख' * 90, '']
     m = O.BpeModel(os.path.join(models_dir, 'bpe24k.json'))
     exp = [r['ids_bpe24k'] for r in rows] + [[2, 3], [2, 3], O.bpe_encode(m, lines[-2]), [2, 3]]
@@ -127,3 +127,22 @@ def test_bpe_fast_renormalizes(models_dir):
     assert attempt == 1 and st == 0
     exp = [O.bpe_encode(m, s) for s in lines]
     assert ids.tolist() == [i for e in exp for i in e]
+
+
+def test_raw_mode_cores(golden_raw, models_dir):
+    T = O.tables()
+    W.load_bpe(os.path.join(models_dir, 'bpe24k.json'))
+    W.load_spm(os.path.join(models_dir, 'spm24k.model'))
+    rows = golden_raw['rows']
+    data, off = sc.pack([r['norm_nc'] for r in rows])
+    ids, splits = W.unigram(data, off)
+    assert ids.tolist() == [i for r in rows for i in r['ids_spm24k']]
+    safe = [r for r in rows if all(T.bpe_safe[ord(c)] for c in r['norm_nc'])]
+    data, off = sc.pack([r['norm_nc'] for r in safe])
+    for fn in (W.bpe, W.bpe_fast):
+        ids, splits, st, _ = fn(data, off)
+        assert st == 0
+        assert ids.tolist() == [i for r in safe for i in r['ids_bpe24k']]
+    # anything else must be refused loudly (status bit 8 = AKSHAR_ST_ALPHABET)
+    data, off = sc.pack(['ok', 'x\ufb01y', '<s>'])
+    assert W.bpe_fast(data, off)[2] & 8 and W.bpe(data, off)[2] & 8

@@ -220,6 +220,33 @@ def main():
     for cp, v in nfkc_changes.items():
         assert v == [0x20] and hf[cp] == 2, hex(cp)
 
+    # ---- code points the BPE encoder may meet without a full NFKC: HF's NFKC (Unicode <= 12) must act on them exactly
+    # like the NFC the kernels implement (Unicode 15), alone and next to marks; whitespace that NFKC folds to U+0020
+    # is fine too (never inside a word).  '<' stays out: it starts every added token ("<s>", "</s>", ...), which HF
+    # matches in the raw text before normalizing.
+    comp_first0 = set(a for (a, b) in pairs) | set(range(0x1100, 0x1113))
+    ctxs = [lambda c: c, lambda c: 'a' + c, lambda c: c + '\u0301', lambda c: 'a' + c + '\u0301', lambda c: 'a\u0301' + c,
+            lambda c: '\u0915' + c, lambda c: c + '\u093c', lambda c: '\u0323' + c]
+    bpe_safe = bytearray(NCP)
+    for cp in range(NCP):
+        if 0xD800 <= cp <= 0xDFFF or cp == 0x3C:
+            continue
+        ch = chr(cp)
+        k = nfkc.normalize_str(ch)
+        ok = k == unicodedata.normalize('NFC', ch)
+        if not ok and hf[cp] == 2 and k == ' ':
+            bpe_safe[cp] = 1
+            continue
+        if ok and (ccc[cp] or nfc_qc[cp] or cp in decomp or cp in comp_first0 or 0x1100 <= cp <= 0x11FF or 0xAC00 <= cp <= 0xD7A3):
+            for f in ctxs:
+                t = f(ch)
+                if nfkc.normalize_str(t) != unicodedata.normalize('NFC', t):
+                    ok = False
+                    break
+        if ok:
+            bpe_safe[cp] = 1
+    print("bpe_safe", sum(bpe_safe), "allow-list members not safe:", [hex(c) for c in range(NCP) if allow[c] and not bpe_safe[c] and nfc_qc[c] != 1])
+
     # ---- pack the 32-bit property word
     # first element of some canonical composition pair (incl. the algorithmic Hangul L + V; LV + T is covered by
     # the decomposition bit): a mark after such a starter may compose, after any other atomic starter it cannot
@@ -229,7 +256,7 @@ def main():
         w = gcb[cp] | (incb[cp] << 4) | (extpict[cp] << 6) | (tag[cp] << 7) | (allow[cp] << 10)
         w |= (nfc_qc[cp] << 11) | ((1 if cp in latin_lower else 0) << 13) | (hf[cp] << 14) | (ccc[cp] << 16)
         w |= ((1 if cp in full_lower else 0) << 24) | ((1 if (cp in decomp or 0xAC00 <= cp <= 0xD7A3) else 0) << 25)
-        w |= (case_ign[cp] << 26) | (cased[cp] << 27) | ((1 if cp in comp_first else 0) << 28)
+        w |= (case_ign[cp] << 26) | (cased[cp] << 27) | ((1 if cp in comp_first else 0) << 28) | (bpe_safe[cp] << 29)
         props[cp] = w
     pages = {}
     page_index = []
@@ -270,7 +297,7 @@ def main():
     out.append("// sources: regex %s (grapheme props), CPython %s unicodedata %s (NFC/lower/isdigit), tokenizers %s (pre-tokenizer classes)"
                % (ver["regex"], ver["python"], ver["unicodedata"], ver["tokenizers"]))
     out.append("// property word: [0:4) GCB  [4:6) InCB  [6] ExtPict  [7:10) script tag  [10] allow-list  [11:13) NFC_QC (0 yes,1 no,2 maybe)")
-    out.append("//   [13] latin-lower changes  [14:16) HF pretok class (0 other,1 \\w,2 \\s)  [16:24) ccc  [24] str.lower changes  [25] has canonical decomposition  [26] case-ignorable  [27] cased (and not case-ignorable)  [28] first of a composition pair")
+    out.append("//   [13] latin-lower changes  [14:16) HF pretok class (0 other,1 \\w,2 \\s)  [16:24) ccc  [24] str.lower changes  [25] has canonical decomposition  [26] case-ignorable  [27] cased (and not case-ignorable)  [28] first of a composition pair  [29] BPE-safe (HF NFKC acts like NFC)")
     out.append("#define AK_N_PAGES %d" % len(page_index))
     out.append("#define AK_N_LEAF_PAGES %d" % len(pages))
     out.append("#define AK_N_DECOMP %d" % len(dec_keys))
@@ -315,6 +342,7 @@ def main():
         "hf_class": value_ranges(hf),
         "case_ignorable": to_ranges(case_ign),
         "cased": to_ranges(cased),
+        "bpe_safe": to_ranges(bpe_safe),
     }
     oj_path = os.path.join(ROOT, "oracle", "ucd_tables.json")
     with open(oj_path, "w") as f:
