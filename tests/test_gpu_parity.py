@@ -372,3 +372,41 @@ def test_full_size_bpe_1gib(A, models_dir):
         e = O.normalize_text(s)
         assert nb[no[i]:no[i + 1]].tobytes().decode('utf-8') == e
         assert hv[hs[i]:hs[i + 1]].tolist() == O.bpe_encode(om, e)
+
+
+def test_cabi_error_codes(A, eng, models_dir):
+    """status codes of the C ABI: bad arguments, workspace too small, encode before load -- nothing is enqueued"""
+    import ctypes
+    import torch
+    from akshar_b200 import _lib as C
+    from akshar_b200.batch import Engine
+    lib = eng.lib
+    b = eng.put(['hello', 'नमस्ते'])
+    dev = eng.device
+    out = torch.empty(64, dtype=torch.uint8, device=dev)
+    off = torch.empty(3, dtype=torch.int64, device=dev)
+    res = torch.empty(4, dtype=torch.int64, device=dev)
+    ws = torch.empty(lib.akshar_workspace_bytes(b.n_bytes, 2), dtype=torch.uint8, device=dev)
+    call = lambda flags, mode, wsz, text_end: lib.akshar_normalize_batch(
+        eng._h, b.data.data_ptr(), b.offsets.data_ptr(), 2, 0, text_end, flags, mode, out.data_ptr(), 64, off.data_ptr(),
+        res.data_ptr(), ws.data_ptr(), wsz, None)
+    assert call(7, 0, ws.numel(), b.end) == C.OK
+    assert call(1 << 6, 0, ws.numel(), b.end) == C.E_ARG            # unknown flag bit
+    assert call(7, 5, ws.numel(), b.end) == C.E_ARG                 # unknown mode
+    assert call(7, 0, ws.numel(), -1) == C.E_ARG                    # text_end < text_begin
+    assert call(7, 0, 16, b.end) == C.E_WORKSPACE
+    assert b'workspace' in lib.akshar_last_error(eng._h)
+    fresh = Engine(0)                                               # a context without models
+    ids = torch.empty(64, dtype=torch.int32, device=dev)
+    rc = lib.akshar_encode_bpe_batch(fresh._h, b.data.data_ptr(), b.offsets.data_ptr(), 2, 0, b.end, 0, ids.data_ptr(), 64,
+                                     off.data_ptr(), res.data_ptr(), ws.data_ptr(), ws.numel(), None)
+    assert rc == C.E_NOMODEL
+    assert lib.akshar_vocab_size(fresh._h, 0) == C.E_NOMODEL and lib.akshar_vocab_size(fresh._h, 7) == C.E_ARG
+    assert lib.akshar_load_bpe_json(fresh._h, b'{"not": "a tokenizer"}', 22) == C.E_MODEL
+    assert lib.akshar_load_spm_model(fresh._h, b'\x00\x01\x02', 3) == C.E_MODEL
+    # the Python layer maps them onto the reference's exceptions (tokenizer.py:88-102)
+    with pytest.raises(RuntimeError):
+        A.aksharTokenizer(os.path.join(models_dir, 'bpe24k.json'))            # a BPE JSON loaded as sentencepiece
+    with pytest.raises(Exception):
+        A.aksharTokenizer(os.path.join(models_dir, 'spm24k.model'), 'bpe')
+    assert A.aksharTokenizer('/nonexistent/model').model_type == 'akshar'      # silent fallback, like the reference
