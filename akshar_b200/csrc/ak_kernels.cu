@@ -190,20 +190,6 @@ struct AkFastNormArgs {
     int64_t base0;               // 16-byte aligned (as an address) start of tile 0, <= text_begin
 };
 
-// tile_row for the fast kernels; one thread per tile
-__global__ void ak_tile_rows_kernel(const int64_t* off, int64_t n_rows, int64_t base0, int n_entries, int64_t* tile_row,
-                                    const unsigned int* run_if, const int64_t* dyn_end, int64_t text_begin) {
-    if (run_if && *run_if == 0) return;
-    (void)dyn_end;
-    (void)text_begin;
-    int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= n_entries) return;
-    const int64_t pos = base0 + (int64_t)k * AKF_TILE;
-    int64_t r = ak_row_lower_bound(off, 0, n_rows, pos);
-    if (off[r] < pos) r = n_rows + 1;
-    tile_row[k] = r;
-}
-
 // a chunk that straddles the start / end of the text: byte by byte, guarded.  Cold, kept out of line.
 __device__ __noinline__ void akf_load_edge(const uint8_t* text, int64_t cs, int lo, int hi, uint32_t* w) {
     w[0] = w[1] = w[2] = w[3] = 0;
@@ -224,6 +210,77 @@ __device__ __forceinline__ void akf_load_chunk(const uint8_t* text, int64_t cs, 
         uint32_t w[4];
         akf_load_edge(text, cs, (int)lo, (int)hi, w);
         c.w[0] = w[0]; c.w[1] = w[1]; c.w[2] = w[2]; c.w[3] = w[3];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Warp tiles.  The fast BPE and segment kernels are warp-autonomous: a warp owns 480 text bytes (30 real lanes +
+// 2 halo lanes), finds the rows that start in them with shuffles, encodes, and appends its output to its CTA's
+// private slice of a temporary stream (cursor in shared memory) -- no CTA barrier and no global atomic on the hot
+// path, so a slow lane (cache miss, long word, slow-lane walker) only delays its own warp.  A scan over the
+// per-warp-tile totals then gives the final positions and a copy kernel moves the blocks.
+// ------------------------------------------------------------------------------------------------
+
+// wrow[k] = first row r in [0, n_rows] with off[r] >= base0 + k * 480 (n_rows + 1 if none); one thread per entry
+__global__ void ak_warp_rows_kernel(AkBatch B, int64_t base0, int n_entries, int64_t* wrow) {
+    if (!ak_batch_begin(B)) return;
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n_entries) return;
+    const int64_t pos = base0 + (int64_t)k * AKF_WARP_BYTES;
+    int64_t r = ak_row_lower_bound(B.off, 0, B.n_rows, pos);
+    if (B.off[r] < pos) r = B.n_rows + 1;
+    wrow[k] = r;
+}
+
+__device__ __forceinline__ int akw_n_tiles(const AkBatch& B, int64_t base0) {
+    return (int)((B.text_end - base0 + AKF_WARP_BYTES) / AKF_WARP_BYTES);      // covers position text_end itself
+}
+
+// each lane's 16-bit row-start mask for its chunk [cs, cs + 16), from the sorted row offsets (no shared memory)
+__device__ __forceinline__ uint32_t akw_lane_rows(const int64_t* off, int64_t n_rows, int64_t r_w0, int64_t ws, int lane) {
+    uint32_t rows = 0;
+    const int64_t lo = ws - 16, hi = ws + AKF_WARP_BYTES + 16;      // positions of lanes 0 .. 31
+    for (int64_t r = r_w0;; r += 32) {                              // rows at or after ws
+        const int64_t mr = r + lane;
+        const int64_t p = mr <= n_rows ? off[mr] : hi;
+        const unsigned m = __ballot_sync(0xFFFFFFFFu, p < hi);
+        const int cnt = __popc(m);                                  // sorted: the in-range rows are a prefix
+        for (int j = 0; j < cnt; ++j) {
+            const int64_t pj = __shfl_sync(0xFFFFFFFFu, p, j);
+            const int rel = (int)(pj - lo);
+            if ((rel >> 4) == lane) rows |= 1u << (rel & 15);
+        }
+        if (cnt < 32) break;
+    }
+    for (int64_t r = r_w0 - 1;; r -= 32) {                          // rows inside the left halo chunk
+        const int64_t mr = r - lane;
+        const int64_t p = mr >= 0 ? off[mr] : lo - 1;
+        const unsigned m = __ballot_sync(0xFFFFFFFFu, p >= lo);
+        const int cnt = __popc(m);
+        if (cnt && lane == 0) {
+            // all of them fall into lane 0's chunk
+        }
+        for (int j = 0; j < cnt; ++j) {
+            const int64_t pj = __shfl_sync(0xFFFFFFFFu, p, j);
+            const int rel = (int)(pj - lo);
+            if ((rel >> 4) == lane) rows |= 1u << (rel & 15);
+        }
+        if (cnt < 32) break;
+    }
+    return rows;
+}
+
+// sums of AKW_GROUP consecutive warp-tile totals
+__global__ void __launch_bounds__(AKW_GROUP) ak_wt_sums_kernel(AkBatch B, int64_t base0, const int32_t* wt_total, int32_t* sums) {
+    __shared__ int ws[33];
+    if (!ak_batch_begin(B)) return;
+    const int n_wt = akw_n_tiles(B, base0);
+    const int n_groups = (n_wt + AKW_GROUP - 1) / AKW_GROUP;
+    for (int gidx = blockIdx.x; gidx < n_groups; gidx += gridDim.x) {
+        const int t = gidx * AKW_GROUP + threadIdx.x;
+        int total;
+        ak_block_exscan<AKW_GROUP>(t < n_wt ? wt_total[t] : 0, ws, total);
+        if (threadIdx.x == 0) sums[gidx] = total;
     }
 }
 
@@ -249,26 +306,6 @@ struct AkNfWork {
     unsigned int slow_cap;
 };
 
-__device__ __forceinline__ void akf_tile_rows(const AkBatch& B, const int64_t* tile_row, int tile, int64_t tile_start,
-                                             uint32_t* rowbits) {
-    const int tid = threadIdx.x;
-    const int64_t lo_pos = tile_start - 16, hi_pos = tile_start + AKF_TILE + 16 + 3;
-    const int64_t r0 = tile_row[tile];
-    for (int i = tid; i < (AKF_TILE + 64) / 32 + 2; i += AK_BLOCK) rowbits[i] = 0;
-    __syncthreads();
-    for (int64_t r = r0 + tid; r <= B.n_rows; r += AK_BLOCK) {
-        const int64_t p = B.off[r];
-        if (p > hi_pos) break;
-        atomicOr(&rowbits[(p - lo_pos) >> 5], 1u << ((p - lo_pos) & 31));
-    }
-    for (int64_t r = r0 - 1 - tid; r >= 0; r -= AK_BLOCK) {
-        const int64_t p = B.off[r];
-        if (p < lo_pos) break;
-        atomicOr(&rowbits[(p - lo_pos) >> 5], 1u << ((p - lo_pos) & 31));
-    }
-    __syncthreads();
-}
-
 // chunk bytes + the 4 bytes that follow (from the next lane; the right halo reads them itself)
 template <class CH>
 __device__ __forceinline__ void akf_load_lane(const AkBatch& B, int64_t cs, CH& c) {
@@ -291,22 +328,20 @@ __device__ __forceinline__ void akf_load_lane(const AkBatch& B, int64_t cs, CH& 
 #endif
 __global__ void __launch_bounds__(AK_BLOCK, AKN_MINB) ak_nf_classify_kernel(const AkFastNormArgs A, const AkNfWork W) {
     __shared__ uint32_t lut[384];
-    __shared__ uint32_t rowbits[(AKF_TILE + 64) / 32 + 2];
     __shared__ int s_red[AKF_WARPS];
     const AkBatch& B = A.B;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int i = tid; i < 384; i += AK_BLOCK)
         lut[i] = i < 128 ? A.T.leaves[((uint32_t)A.T.page_index[0] << 8) | i] : A.T.leaves[((uint32_t)A.T.page_index[9] << 8) | (i - 128)];
+    __syncthreads();
     for (int tile = blockIdx.x; tile < B.n_tiles; tile += gridDim.x) {
         const int64_t tile_start = A.base0 + (int64_t)tile * AKF_TILE;
-        akf_tile_rows(B, A.tile_row, tile, tile_start, rowbits);      // contains the barriers that also protect lut / s_red
+        const int64_t ws = tile_start + (int64_t)warp * AKF_WARP_BYTES;
         AkChunk c;
-        const int64_t cs = tile_start + (int64_t)warp * AKF_WARP_BYTES + (int64_t)(lane - 1) * 16;
+        const int64_t cs = ws + (int64_t)(lane - 1) * 16;
         akf_load_lane(B, cs, c);
-        {
-            const int bo = (int)(cs - (tile_start - 16));
-            c.rows = (rowbits[bo >> 5] >> (bo & 31)) & 0xFFFFu;
-        }
+        // row starts of the warp's 32 chunks straight from the sorted offsets (tile_row has one entry per warp tile)
+        c.rows = akw_lane_rows(B.off, B.n_rows, A.tile_row[(size_t)tile * AKF_WARPS + warp], ws, lane);
         if (c.own == 0 && c.rows == 0) {
             // entirely outside the text: acts as a row boundary for its neighbours
             c.kept = c.lead = 0;
@@ -376,6 +411,7 @@ __global__ void __launch_bounds__(AK_BLOCK, AKN_MINB) ak_nf_classify_kernel(cons
             for (int w = 0; w < AKF_WARPS; ++w) t += s_red[w];
             W.tile_total[tile] = t;
         }
+        __syncthreads();       // s_red is reused by the next tile
     }
 }
 
@@ -400,7 +436,7 @@ __global__ void __launch_bounds__(128) ak_nf_slow_kernel(const AkNfSlowArgs A) {
         AkSlowEntry e = A.W.slow[j];
         const int64_t ss = e.pos < B.text_begin ? B.text_begin : e.pos;
         const int64_t se = e.pos + 16 > B.text_end + 1 ? B.text_end + 1 : e.pos + 16;
-        const int64_t r0 = A.tile_row[e.tile], r1 = A.tile_row[e.tile + 1];
+        const int64_t r0 = A.tile_row[(size_t)e.tile * AKF_WARPS], r1 = A.tile_row[(size_t)(e.tile + 1) * AKF_WARPS];
         const int64_t rlo = r0 > 0 ? r0 - 1 : 0, rhi = r1 > B.n_rows ? B.n_rows : r1;
         uint32_t st = 0;
         if (!A.write) {
@@ -478,7 +514,7 @@ __global__ void __launch_bounds__(AK_BLOCK) ak_nf_write_kernel(const AkFastNormA
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int tile = blockIdx.x; tile < B.n_tiles; tile += gridDim.x) {
         const int64_t tile_start = A.base0 + (int64_t)tile * AKF_TILE;
-        const int64_t r0 = A.tile_row[tile], r1 = A.tile_row[tile + 1];
+        const int64_t r0 = A.tile_row[(size_t)tile * AKF_WARPS], r1 = A.tile_row[(size_t)(tile + 1) * AKF_WARPS];
         const int64_t cs = tile_start + (int64_t)warp * AKF_WARP_BYTES + (int64_t)(lane - 1) * 16;
         AkChunk c;
         akf_load_lane(B, cs, c);
@@ -661,77 +697,6 @@ __global__ void __launch_bounds__(AK_BLOCK) ak_bpe_kernel(const AkBpeArgs A) {
         }
         if (changed) atomicOr(A.changed, 1u);
         ak_raise(B.result, st);
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
-// Warp tiles.  The fast BPE and segment kernels are warp-autonomous: a warp owns 480 text bytes (30 real lanes +
-// 2 halo lanes), finds the rows that start in them with shuffles, encodes, and appends its output to its CTA's
-// private slice of a temporary stream (cursor in shared memory) -- no CTA barrier and no global atomic on the hot
-// path, so a slow lane (cache miss, long word, slow-lane walker) only delays its own warp.  A scan over the
-// per-warp-tile totals then gives the final positions and a copy kernel moves the blocks.
-// ------------------------------------------------------------------------------------------------
-
-// wrow[k] = first row r in [0, n_rows] with off[r] >= base0 + k * 480 (n_rows + 1 if none); one thread per entry
-__global__ void ak_warp_rows_kernel(AkBatch B, int64_t base0, int n_entries, int64_t* wrow) {
-    if (!ak_batch_begin(B)) return;
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= n_entries) return;
-    const int64_t pos = base0 + (int64_t)k * AKF_WARP_BYTES;
-    int64_t r = ak_row_lower_bound(B.off, 0, B.n_rows, pos);
-    if (B.off[r] < pos) r = B.n_rows + 1;
-    wrow[k] = r;
-}
-
-__device__ __forceinline__ int akw_n_tiles(const AkBatch& B, int64_t base0) {
-    return (int)((B.text_end - base0 + AKF_WARP_BYTES) / AKF_WARP_BYTES);      // covers position text_end itself
-}
-
-// each lane's 16-bit row-start mask for its chunk [cs, cs + 16), from the sorted row offsets (no shared memory)
-__device__ __forceinline__ uint32_t akw_lane_rows(const int64_t* off, int64_t n_rows, int64_t r_w0, int64_t ws, int lane) {
-    uint32_t rows = 0;
-    const int64_t lo = ws - 16, hi = ws + AKF_WARP_BYTES + 16;      // positions of lanes 0 .. 31
-    for (int64_t r = r_w0;; r += 32) {                              // rows at or after ws
-        const int64_t mr = r + lane;
-        const int64_t p = mr <= n_rows ? off[mr] : hi;
-        const unsigned m = __ballot_sync(0xFFFFFFFFu, p < hi);
-        const int cnt = __popc(m);                                  // sorted: the in-range rows are a prefix
-        for (int j = 0; j < cnt; ++j) {
-            const int64_t pj = __shfl_sync(0xFFFFFFFFu, p, j);
-            const int rel = (int)(pj - lo);
-            if ((rel >> 4) == lane) rows |= 1u << (rel & 15);
-        }
-        if (cnt < 32) break;
-    }
-    for (int64_t r = r_w0 - 1;; r -= 32) {                          // rows inside the left halo chunk
-        const int64_t mr = r - lane;
-        const int64_t p = mr >= 0 ? off[mr] : lo - 1;
-        const unsigned m = __ballot_sync(0xFFFFFFFFu, p >= lo);
-        const int cnt = __popc(m);
-        if (cnt && lane == 0) {
-            // all of them fall into lane 0's chunk
-        }
-        for (int j = 0; j < cnt; ++j) {
-            const int64_t pj = __shfl_sync(0xFFFFFFFFu, p, j);
-            const int rel = (int)(pj - lo);
-            if ((rel >> 4) == lane) rows |= 1u << (rel & 15);
-        }
-        if (cnt < 32) break;
-    }
-    return rows;
-}
-
-// sums of AKW_GROUP consecutive warp-tile totals
-__global__ void __launch_bounds__(AKW_GROUP) ak_wt_sums_kernel(AkBatch B, int64_t base0, const int32_t* wt_total, int32_t* sums) {
-    __shared__ int ws[33];
-    if (!ak_batch_begin(B)) return;
-    const int n_wt = akw_n_tiles(B, base0);
-    const int n_groups = (n_wt + AKW_GROUP - 1) / AKW_GROUP;
-    for (int gidx = blockIdx.x; gidx < n_groups; gidx += gridDim.x) {
-        const int t = gidx * AKW_GROUP + threadIdx.x;
-        int total;
-        ak_block_exscan<AKW_GROUP>(t < n_wt ? wt_total[t] : 0, ws, total);
-        if (threadIdx.x == 0) sums[gidx] = total;
     }
 }
 
@@ -1622,7 +1587,7 @@ static AkWsLayout ak_ws_layout(int64_t n_bytes, int64_t n_rows) {
     L.control = 0;
     L.state = 256;
     L.tile_row = L.state + ak_align(4 * tiles * 8);
-    size_t at = L.tile_row + ak_align(8 * (tiles + 2));
+    size_t at = L.tile_row + ak_align(8 * (tiles * AKF_WARPS + 2));
     L.scratch = at;
     size_t uni = 4 * (size_t)(n_bytes + 2 * n_rows + 2);
     L.nfc_cap = n_bytes + n_bytes / 8 + 1024;
@@ -1757,10 +1722,9 @@ static int ak_run_normalize(akshar_ctx* ctx, AkCall& C, const AkBatch& B, uint32
         F.B.n_tiles = (int)((B.text_end - F.base0 + AKF_TILE) / AKF_TILE);
         int64_t* tile_row = (int64_t*)(C.ws + C.L.tile_row);
         F.tile_row = tile_row;
-        const int entries = F.B.n_tiles + 1;
-        ak_tile_rows_kernel<<<(entries + 255) / 256, 256, 0, C.stream>>>(B.off, B.n_rows, F.base0, entries, tile_row, B.run_if,
-                                                                        nullptr, B.text_begin);
-        int rc = ak_after_launch(ctx, "tile-rows");
+        const int entries = F.B.n_tiles * AKF_WARPS + 1;       // one entry per warp tile (480 bytes)
+        ak_warp_rows_kernel<<<(entries + 255) / 256, 256, 0, C.stream>>>(B, F.base0, entries, tile_row);
+        int rc = ak_after_launch(ctx, "warp-rows");
         if (rc) return rc;
         AkNfWork W;
         const size_t nt = (size_t)F.B.n_tiles;
