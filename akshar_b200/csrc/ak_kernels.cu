@@ -7,6 +7,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <new>
@@ -18,6 +19,7 @@
 #include "ak_scan.cuh"
 #include "ak_subword.cuh"
 #include "ak_fast.cuh"
+#include "ak_norm3.cuh"
 #include "ak_bpe_fast.cuh"
 #include "ak_seg_fast.cuh"
 #include "unicode_tables.inc"
@@ -412,6 +414,159 @@ __global__ void __launch_bounds__(AK_BLOCK, AKN_MINB) ak_nf_classify_kernel(cons
             W.tile_total[tile] = t;
         }
         __syncthreads();       // s_red is reused by the next tile
+    }
+}
+
+// ---- K1a v3: the same classification as parallel bit streams (ak_norm3.cuh): 32 bytes per lane, 30 real lanes per
+// warp (960 bytes = two 480-byte warp tiles of the v2 geometry), 4 warps per 3840-byte tile.  Produces exactly what
+// ak_nf_classify_kernel produces -- one 19-bit emit mask per 16-byte chunk, work-list entries for the slow chunks,
+// the tile's fast byte count -- so the scan / write / slow kernels are shared.
+#define AKN3_THREADS 128
+#define AKN3_WARP_BYTES 960
+
+// row-start mask of the lane's 32 bytes [ws + 32 (lane - 1), +32) from the sorted offsets; r_w0 = first row at or after ws
+__device__ __forceinline__ uint32_t akn3_lane_rows(const int64_t* off, int64_t n_rows, int64_t r_w0, int64_t ws, int lane) {
+    uint32_t rows = 0;
+    const int64_t lo = ws - 32, hi = ws + AKN3_WARP_BYTES + 32;
+    for (int64_t r = r_w0;; r += 32) {
+        const int64_t mr = r + lane;
+        const int64_t p = mr <= n_rows ? off[mr] : hi;
+        const unsigned m = __ballot_sync(0xFFFFFFFFu, p < hi);
+        const int cnt = __popc(m);
+        for (int j = 0; j < cnt; ++j) {
+            const int rel = (int)(__shfl_sync(0xFFFFFFFFu, p, j) - lo);
+            if ((rel >> 5) == lane) rows |= 1u << (rel & 31);
+        }
+        if (cnt < 32) break;
+    }
+    for (int64_t r = r_w0 - 1;; r -= 32) {
+        const int64_t mr = r - lane;
+        const int64_t p = mr >= 0 ? off[mr] : lo - 1;
+        const unsigned m = __ballot_sync(0xFFFFFFFFu, p >= lo);
+        const int cnt = __popc(m);
+        for (int j = 0; j < cnt; ++j) {
+            const int rel = (int)(__shfl_sync(0xFFFFFFFFu, p, j) - lo);
+            if ((rel >> 5) == lane) rows |= 1u << (rel & 31);
+        }
+        if (cnt < 32) break;
+    }
+    return rows;
+}
+
+__device__ __noinline__ void akn3_load_edge(const uint8_t* text, int64_t cs, int lo, int hi, uint32_t* x) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) x[i] = 0;
+#pragma unroll 1
+    for (int i = lo; i < hi; ++i) x[i >> 2] |= (uint32_t)text[cs + i] << ((i & 3) * 8);
+}
+
+#ifndef AKN3_MINB
+#define AKN3_MINB 6
+#endif
+__global__ void __launch_bounds__(AKN3_THREADS, AKN3_MINB) ak_nf3_classify_kernel(const AkFastNormArgs A, const AkNfWork W) {
+    __shared__ int s_red[AKN3_THREADS / 32];
+    const AkBatch& B = A.B;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t tb = B.text_begin, te = B.text_end;
+    for (int tile = blockIdx.x; tile < B.n_tiles; tile += gridDim.x) {
+        const int64_t tile_start = A.base0 + (int64_t)tile * AKF_TILE;
+        const int64_t ws = tile_start + (int64_t)warp * AKN3_WARP_BYTES;
+        const int64_t cs = ws + (int64_t)(lane - 1) * 32;
+        AkN3Lane L;
+        {
+            uint32_t x[8];
+            int64_t lo = tb - cs, hi = te - cs;
+            lo = lo < 0 ? 0 : (lo > 32 ? 32 : lo);
+            hi = hi < 0 ? 0 : (hi > 32 ? 32 : hi);
+            if (lo == 0 && hi == 32) {
+                const uint4 v0 = *reinterpret_cast<const uint4*>(B.text + cs);
+                const uint4 v1 = *reinterpret_cast<const uint4*>(B.text + cs + 16);
+                x[0] = v0.x; x[1] = v0.y; x[2] = v0.z; x[3] = v0.w;
+                x[4] = v1.x; x[5] = v1.y; x[6] = v1.z; x[7] = v1.w;
+                L.own = 0xFFFFFFFFu;
+            } else {
+                akn3_load_edge(B.text, cs, (int)lo, (int)hi, x);
+                L.own = hi > lo ? ((hi == 32 ? 0xFFFFFFFFu : ((1u << hi) - 1u)) & ~((1u << lo) - 1u)) : 0u;
+            }
+            L.rows = akn3_lane_rows(B.off, B.n_rows, A.tile_row[(size_t)tile * AKF_WARPS + 2 * warp], ws, lane);
+            akn3_phase1(x, L);
+        }
+        uint32_t up1p = __shfl_up_sync(0xFFFFFFFFu, L.up1, 1);
+        uint32_t dn1n = __shfl_down_sync(0xFFFFFFFFu, L.dn1, 1);
+        if (lane == 0) {
+            uint32_t b[3];
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                const int64_t q = cs - 3 + i;
+                b[i] = (q >= tb && q < te) ? B.text[q] : 0u;
+            }
+            up1p = akn3_up1_from_bytes(b[0], b[1], b[2]);
+        }
+        if (lane == 31) dn1n = 0;
+        akn3_phase2(L, up1p, dn1n);
+        uint32_t up2p = __shfl_up_sync(0xFFFFFFFFu, L.up2, 1);
+        uint32_t dn2n = __shfl_down_sync(0xFFFFFFFFu, L.dn2, 1);
+        if (lane == 0) up2p = akn3_up2_from_text(A.T, B.text, cs, tb, te);
+        if (lane == 31) dn2n = 0;
+        akn3_phase3(A.T, B.text, cs, te, L, up2p, dn2n);
+        {
+            uint32_t rest = 0;
+            if (L.ge) rest = akn3_gaps_local(B.text, cs, te, L);
+            if (__any_sync(0xFFFFFFFFu, rest != 0u)) {
+                const uint32_t lk = akn3_last_kept(B.text, cs, te, L);
+                uint32_t plk = __shfl_up_sync(0xFFFFFFFFu, lk, 1);
+                if (lane == 0) plk = 0;
+                akn3_gaps_remote(B.text, cs, te, L, rest, plk);
+            }
+        }
+        akn3_phase3b(L);
+        const uint32_t up3p = __shfl_up_sync(0xFFFFFFFFu, L.up3, 1);
+        const uint32_t dn3n = __shfl_down_sync(0xFFFFFFFFu, L.dn3, 1);
+        uint32_t info[2] = {0u, 0u};
+        const bool fast = akn3_phase4(L, up3p, dn1n, dn3n, info[0], info[1]);
+        int cnt = 0;
+        if (lane >= 1 && lane <= 30) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int64_t hs = cs + 16 * h;
+                const int64_t ss = hs < tb ? tb : hs;
+                const int64_t se = hs + 16 > te + 1 ? te + 1 : hs + 16;
+                const int k = (int)((hs - tile_start) >> 4);                 // 16-byte chunk of the tile, 0 .. 239
+                uint32_t v = 0;
+                if (ss < se) {
+                    if (fast) {
+                        v = info[h];
+                        cnt += __popc(v);
+                    } else {
+                        const unsigned int idx = atomicAdd(W.n_slow, 1u);
+                        if (idx < W.slow_cap) {
+                            AkSlowEntry e;
+                            e.pos = hs;
+                            e.out_base = 0;
+                            e.cnt = 0;
+                            e.tile = tile;
+                            W.slow[idx] = e;
+                        } else {
+                            ak_raise(B.result, AK_ST_PATHOLOGICAL);
+                        }
+                        v = 0x80000000u | idx;
+                    }
+                }
+                W.info[(size_t)tile * AK_BLOCK + (k / AKF_REAL) * 32 + 1 + (k % AKF_REAL)] = v;
+            }
+        }
+        if (tid < 2 * AKF_WARPS) W.info[(size_t)tile * AK_BLOCK + (tid >> 1) * 32 + (tid & 1) * 31] = 0;   // the v2 halo slots
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) cnt += __shfl_xor_sync(0xFFFFFFFFu, cnt, d);
+        if (lane == 0) s_red[warp] = cnt;
+        __syncthreads();
+        if (tid == 0) {
+            int t = 0;
+#pragma unroll
+            for (int w = 0; w < AKN3_THREADS / 32; ++w) t += s_red[w];
+            W.tile_total[tile] = t;
+        }
+        __syncthreads();
     }
 }
 
@@ -1435,7 +1590,7 @@ struct akshar_ctx {
     bool timing = false;
     cudaEvent_t tev[AKSHAR_TIMER_COUNT][2] = {};
     bool tev_valid[AKSHAR_TIMER_COUNT] = {};
-    int occ_norm = 0, occ_seg = 0, occ_bpe = 0, occ_uni = 0, occ_sig = 0, occ_nf_classify = 0, occ_nf_write = 0;
+    int occ_norm = 0, occ_seg = 0, occ_bpe = 0, occ_uni = 0, occ_sig = 0, occ_nf_classify = 0, occ_nf_write = 0, occ_nf3 = 0;
 };
 
 #define AK_CUDA(ctx, call)                                                                         \
@@ -1511,6 +1666,7 @@ int akshar_ctx_create(int device, akshar_ctx** out) {
     AK_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_norm, ak_normalize_kernel, AK_BLOCK, 0));
     AK_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_nf_classify, ak_nf_classify_kernel, AK_BLOCK, 0));
     AK_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_nf_write, ak_nf_write_kernel, AK_BLOCK, 0));
+    AK_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_nf3, ak_nf3_classify_kernel, AKN3_THREADS, 0));
     AK_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_bf, ak_bf_encode_kernel, AK_BLOCK, 0));
     AK_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_sf, ak_sf_kernel, AK_BLOCK, 0));
     AK_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_seg, ak_segment_kernel, AK_BLOCK, 0));
@@ -1737,7 +1893,10 @@ static int ak_run_normalize(akshar_ctx* ctx, AkCall& C, const AkBatch& B, uint32
         W.slow_cap = (unsigned int)(nt * AK_BLOCK / 16 + 1024);
         {
             AkTimed tm(ctx, AKSHAR_TIMER_NORMALIZE_CLASSIFY, C.stream);
-            ak_nf_classify_kernel<<<ak_grid(ctx, ctx->occ_nf_classify, F.B.n_tiles), AK_BLOCK, 0, C.stream>>>(F, W);
+            if (getenv("AKSHAR_NORM_V2"))
+                ak_nf_classify_kernel<<<ak_grid(ctx, ctx->occ_nf_classify, F.B.n_tiles), AK_BLOCK, 0, C.stream>>>(F, W);
+            else
+                ak_nf3_classify_kernel<<<ak_grid(ctx, ctx->occ_nf3, F.B.n_tiles), AKN3_THREADS, 0, C.stream>>>(F, W);
         }
         if ((rc = ak_after_launch(ctx, "normalize-classify"))) return rc;
         AkNfSlowArgs S;

@@ -9,6 +9,7 @@
 #include <math.h>
 #include "../../akshar_b200/csrc/ak_subword.cuh"
 #include "../../akshar_b200/csrc/ak_fast.cuh"
+#include "../../akshar_b200/csrc/ak_norm3.cuh"
 #include "../../akshar_b200/csrc/ak_bpe_fast.cuh"
 #include "../../akshar_b200/csrc/ak_seg_fast.cuh"
 #include "../../akshar_b200/csrc/ak_models.h"
@@ -171,6 +172,124 @@ int64_t hh_fast_normalize(const uint8_t* text, const int64_t* off, int64_t n_row
                     ++row;
                 }
                 base += akf_write(c, emit, out + base);
+            }
+        }
+    }
+    *status = st;
+    *n_slow = slow_cnt;
+    return base;
+}
+
+
+// ---- bit-parallel normalize (ak_norm3.cuh): 32-byte lanes, `real` lanes + 2 halo lanes per "warp", the kernel's
+// three exchange rounds, its emit masks fed to the same 16-byte writer, the walker for slow lanes.
+// roles of one byte value (for the exhaustive predicate test): the lane is filled with that byte
+uint32_t hh_n3_roles(uint32_t byte) {
+    uint32_t x[8];
+    for (int i = 0; i < 8; ++i) x[i] = byte * 0x01010101u;
+    AkN3Lane L;
+    memset(&L, 0, sizeof(L));
+    L.own = 0xFFFFFFFFu;
+    akn3_phase1(x, L);
+    uint32_t r = 0;
+    const uint32_t m[18] = {L.cont, L.K, L.NL, L.E0b, L.F0b, L.LXo, L.A4b, L.A5b, L.A6b, L.A7b, L.x9Fb, L.NKb, L.NIb, L.R2b, L.R3b, L.QNb, L.B6b, L.B7b};
+    for (int i = 0; i < 18; ++i) {
+        if (m[i] != 0u && m[i] != 0xFFFFFFFFu) return 0xFFFFFFFFu;       // must be uniform
+        if (m[i]) r |= 1u << i;
+    }
+    if (L.PL[5] & 1u) r |= 1u << 18;     // lowered bit 5
+    return r;
+}
+// planes of 32 arbitrary bytes (transpose test)
+void hh_n3_planes(const uint8_t* b, uint32_t* P) {
+    uint32_t x[8];
+    memcpy(x, b, 32);
+    akb_planes(x, P);
+}
+
+int64_t hh_fast_normalize3(const uint8_t* text, const int64_t* off, int64_t n_rows, int real, uint8_t* out, int64_t* out_off,
+                           uint32_t* status, int64_t* n_slow) {
+    AkTables T = host_tables();
+    const int64_t tb = off[0], te = off[n_rows], base0 = tb;
+    std::vector<uint8_t> rowstart((size_t)(te - base0) + 128, 0);
+    for (int64_t r = 0; r <= n_rows; ++r) rowstart[(size_t)(off[r] - base0)] = 1;
+    const int64_t n_lanes = (te - base0 + 1 + 31) / 32;
+    const uint32_t NFLAGS = AK_NORM_ROMAN | AK_NORM_CLEAN;
+    int64_t base = 0, row = 0, slow_cnt = 0;
+    uint32_t st = 0;
+    const int NL = real + 2;
+    std::vector<AkN3Lane> lanes((size_t)NL);
+    std::vector<uint32_t> lastk((size_t)NL), rest((size_t)NL);
+    for (int64_t w0 = 0; w0 < n_lanes; w0 += real) {
+        for (int l = 0; l < NL; ++l) {
+            AkN3Lane& L = lanes[(size_t)l];
+            memset(&L, 0, sizeof(L));
+            const int64_t cs = base0 + (w0 - 1 + l) * 32;
+            uint32_t x[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            for (int i = 0; i < 32; ++i) {
+                const int64_t q = cs + i;
+                if (q >= tb && q < te) { x[i >> 2] |= (uint32_t)text[q] << ((i & 3) * 8); L.own |= 1u << i; }
+                if (q >= base0 && q - base0 < (int64_t)rowstart.size() && rowstart[(size_t)(q - base0)]) L.rows |= 1u << i;
+            }
+            akn3_phase1(x, L);
+        }
+        for (int l = 0; l < NL; ++l) {
+            uint32_t up1p;
+            if (l > 0) up1p = lanes[(size_t)l - 1].up1;
+            else {
+                const int64_t cs = base0 + (w0 - 1) * 32;
+                uint32_t b[3];
+                for (int i = 0; i < 3; ++i) { const int64_t q = cs - 3 + i; b[i] = (q >= tb && q < te) ? text[q] : 0u; }
+                up1p = akn3_up1_from_bytes(b[0], b[1], b[2]);
+            }
+            akn3_phase2(lanes[(size_t)l], up1p, l + 1 < NL ? lanes[(size_t)l + 1].dn1 : 0u);
+        }
+        for (int l = 0; l < NL; ++l) {
+            const int64_t cs = base0 + (w0 - 1 + l) * 32;
+            // lane 0 has no left neighbour: conservative carries (previous not inert, previous an accent, previous dropped)
+            akn3_phase3(T, text, cs, te, lanes[(size_t)l], l > 0 ? lanes[(size_t)l - 1].up2 : akn3_up2_from_text(T, text, cs, tb, te), l + 1 < NL ? lanes[(size_t)l + 1].dn2 : 0u);
+            rest[(size_t)l] = akn3_gaps_local(text, cs, te, lanes[(size_t)l]);
+            lastk[(size_t)l] = akn3_last_kept(text, cs, te, lanes[(size_t)l]);
+        }
+        for (int l = 0; l < NL; ++l) {
+            const int64_t cs = base0 + (w0 - 1 + l) * 32;
+            akn3_gaps_remote(text, cs, te, lanes[(size_t)l], rest[(size_t)l], l > 0 ? lastk[(size_t)l - 1] : 0u);
+            akn3_phase3b(lanes[(size_t)l]);
+        }
+        for (int l = 1; l <= real; ++l) {
+            AkN3Lane& L = lanes[(size_t)l];
+            const int64_t cs = base0 + (w0 - 1 + l) * 32;
+            uint32_t info[2] = {0, 0};
+            const bool fast = akn3_phase4(L, lanes[(size_t)l - 1].up3, lanes[(size_t)l + 1].dn1, lanes[(size_t)l + 1].dn3, info[0], info[1]);
+            for (int h = 0; h < 2; ++h) {
+                const int64_t hs = cs + 16 * h;
+                const int64_t ss = hs < tb ? tb : hs, se = hs + 16 > te + 1 ? te + 1 : hs + 16;
+                if (ss >= se) continue;
+                while (row <= n_rows && off[row] < ss) ++row;
+                if (!fast && h == 0 && getenv("AKN3_REASONS")) {
+                    static long cnt[10], tot;
+                    for (int b = 0; b < 10; ++b) if (L.flags & (0x100u << b)) cnt[b]++;
+                    if (++tot % 200 == 0)
+                        fprintf(stderr, "slow lanes %ld: loop-kept %ld gap-eq %ld gap-unknown %ld gap-remote-eq %ld own-T %ld first-dep %ld next %ld prev-T %ld pend-gap %ld pend-nextT %ld\n",
+                                tot, cnt[0], cnt[1], cnt[2], cnt[3], cnt[4], cnt[5], cnt[6], cnt[7], cnt[8], cnt[9]);
+                }
+                if (!fast) {
+                    ++slow_cnt;
+                    base += ak_norm_span(T, text, off, n_rows, 0, n_rows, ss, se, NFLAGS, 0, out + base, out_off, base, st);
+                    while (row <= n_rows && off[row] < se) ++row;
+                } else {
+                    AkChunk c;
+                    hh_make_chunk(text, hs, tb, te, rowstart, base0, c);
+                    const uint32_t emit = info[h];
+                    while (row <= n_rows && off[row] < se) {
+                        int i = (int)(off[row] - hs);
+                        int before = 0;
+                        for (int b = 0; b < i; ++b) before += (emit >> b) & 1u;
+                        out_off[row] = base + before;
+                        ++row;
+                    }
+                    base += akf_write(c, emit, out + base);
+                }
             }
         }
     }

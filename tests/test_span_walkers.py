@@ -122,6 +122,98 @@ def test_fast_lane_is_mostly_fast():
         assert n_slow / n_chunks < 0.05
 
 
+# ---- bit-parallel normalize (ak_bits.cuh / ak_norm3.cuh): the kernel's lane phases and exchange rounds on the CPU
+def test_basis_planes():
+    rng = np.random.default_rng(1)
+    for _ in range(100):
+        b = rng.integers(0, 256, 32).astype(np.uint8)
+        P = W.n3_planes(b)
+        for k in range(8):
+            assert int(P[k]) == sum(((int(b[i]) >> k) & 1) << i for i in range(32))
+
+
+def test_byte_roles_match_the_tables():
+    """the plane logic hard-codes byte classes; they must agree with the modules that own each rule"""
+    import unicodedata as u
+    import regex
+    allowed = regex.compile(r'[\u0900-\u097F\u0980-\u09FFa-zA-Z0-9\s.,!?;:\'\"\-]')
+    names = ['cont', 'K', 'NL', 'E0b', 'F0b', 'LXo', 'A4b', 'A5b', 'A6b', 'A7b', 'x9Fb', 'NKb', 'NIb', 'R2b', 'R3b', 'QNb', 'B6b',
+             'B7b', 'low5']
+    sets = {'A4b': {0xA4}, 'A5b': {0xA5}, 'A6b': {0xA6}, 'A7b': {0xA7}, 'x9Fb': {0x9F}, 'NKb': {0xBC}, 'R2b': {0x8D},
+            'R3b': set(range(0x91, 0x95)), 'QNb': set(range(0x98, 0xA0)), 'NIb': {0xA8, 0xA9, 0xB0, 0xB1, 0xB3, 0xB4},
+            'B6b': {0xBC, 0xBE}, 'B7b': {0x87, 0x8B, 0x8C, 0x8D, 0x97, 0x9C, 0x9D, 0x9F, 0xBE}, 'NL': {0x0A}, 'E0b': {0xE0},
+            'F0b': {0xF0}, 'cont': set(range(0x80, 0xC0)), 'LXo': set(range(0xC0, 0x100)) - {0xE0, 0xF0}}
+    for b in range(256):
+        r = W.n3_roles(b)
+        assert r != 0xFFFFFFFF
+        g = lambda n: (r >> names.index(n)) & 1
+        assert g('K') == (b < 0x80 and bool(allowed.match(chr(b))))
+        for n, st in sets.items():
+            assert g(n) == (b in st), (n, hex(b))
+        low = (b | 0x20) if 0x41 <= b <= 0x5A else b
+        assert g('low5') == ((low >> 5) & 1)
+    # U+0900-09FF: the code points NFC can touch are exactly the ones the role masks single out
+    for c in range(0x900, 0xA00):
+        ch = chr(c)
+        special = bool(u.combining(ch) or u.normalize('NFC', ch) != ch or u.decomposition(ch)
+                       or c in (0x928, 0x930, 0x933, 0x9C7, 0x9BE, 0x9D7))
+        b1, b2 = 0xA4 + ((c - 0x900) >> 6), 0x80 + (c & 63)
+        if b1 == 0xA4:
+            mine = b2 in sets['NKb'] | sets['NIb']
+        elif b1 == 0xA5:
+            mine = b2 in sets['R2b'] | sets['R3b'] | sets['QNb']
+        elif b1 == 0xA6:
+            mine = b2 in sets['B6b']
+        else:
+            mine = b2 in sets['B7b']
+        assert special == mine, hex(c)
+    # U+0928 / 0930 / 0933 are the bases a nukta composes with; 09C7 + 09BE / 09D7 likewise
+    for a, m in ((0x928, 0x93C), (0x930, 0x93C), (0x933, 0x93C), (0x9C7, 0x9BE), (0x9C7, 0x9D7)):
+        assert len(u.normalize('NFC', chr(a) + chr(m))) == 1
+    # F0 9F xx xx (U+1F000-1FFFF) is dropped without a table look-up: plain for NFC, not allowed, no lower()
+    for c in range(0x1F000, 0x20000):
+        ch = chr(c)
+        assert u.combining(ch) == 0 and u.normalize('NFC', 'a' + ch) == 'a' + ch and not allowed.match(ch)
+        assert ch.lower() == ch
+
+
+@pytest.mark.parametrize('real', [30, 1, 4])
+def test_bit_parallel_lane_structure(real):
+    lines = list(_lines())
+    data, off = sc.pack(lines)
+    exp, exp_off = _exp_norm(7)
+    out, out_off, st, n_slow = W.fast_normalize3(data, off, real=real)
+    assert st == 0
+    assert np.array_equal(out_off, exp_off)
+    assert out.tobytes() == exp.tobytes()
+
+
+def test_bit_parallel_fuzz():
+    """alphabets that keep most lanes fast: elongations across dropped stretches, row starts everywhere, rare trouble"""
+    alpha = ['a', 'A', 'e', ' ', ' ', '\U0001F600', '\u0915', '\u093e', '\u094d', '\n', '!', '#', 'x', '\u0921', '\u0950',
+             '\u0995', '_', '\t', '\U0001F468\u200d\U0001F469\u200d\U0001F467', 'a', 'a', ' ', '\u0915', '\u0915', '\u09bf', '\u09e6']
+    tr = ['\u093c', '\u0928', '\u0951', 'e\u0301', '\u095c', '\u0130', '\u00a0', '\u00c9']
+    rng = np.random.default_rng(5)
+    for seed, (max_len, real) in enumerate([(120, 30), (40, 30), (300, 7), (8, 2), (64, 13)]):
+        lines = sc.adversarial(1500, 500 + seed, max_len, alphabet=alpha)
+        if seed >= 3:
+            lines = [s if rng.random() < 0.7 else s[:len(s) // 2] + tr[int(rng.integers(len(tr)))] + s[len(s) // 2:] for s in lines]
+        data, off = sc.pack(lines)
+        exp, exp_off = OB.normalize_batch(lines)
+        out, out_off, st, _ = W.fast_normalize3(data, off, real=real)
+        assert st == 0 and np.array_equal(out_off, exp_off) and out.tobytes() == exp.tobytes()
+
+
+def test_bit_parallel_is_mostly_fast():
+    for kind in ('hinglish', 'hindi', 'social'):
+        lines = sc.Corpus(kind, 8).lines(200000)
+        data, off = sc.pack(lines)
+        out, out_off, st, n_slow = W.fast_normalize3(data, off)
+        exp, exp_off = OB.normalize_batch(lines)
+        assert st == 0 and np.array_equal(out_off, exp_off) and out.tobytes() == exp.tobytes()
+        assert n_slow / (data.size / 16) < 0.03
+
+
 @pytest.mark.parametrize('real,stage_cap', [(30, 18), (1, 18), (4, 1)])
 def test_segment_fast_structure(real, stage_cap):
     lines = list(_lines())

@@ -16,7 +16,7 @@ def build():
     csrc = os.path.join(ROOT, 'akshar_b200', 'csrc')
     models = os.path.join(csrc, 'ak_models.cpp')
     deps = [src, models] + [os.path.join(csrc, f) for f in
-                            ('ak_unicode.cuh', 'ak_text_core.cuh', 'ak_subword.cuh', 'ak_fast.cuh', 'ak_bpe_fast.cuh', 'ak_seg_fast.cuh', 'ak_models.h', 'unicode_tables.inc')]
+                            ('ak_unicode.cuh', 'ak_bits.cuh', 'ak_norm3.cuh', 'ak_text_core.cuh', 'ak_subword.cuh', 'ak_fast.cuh', 'ak_bpe_fast.cuh', 'ak_seg_fast.cuh', 'ak_models.h', 'unicode_tables.inc')]
     if not os.path.exists(SO) or any(os.path.getmtime(d) > os.path.getmtime(SO) for d in deps):
         subprocess.check_call(['g++', '-O2', '-std=c++17', '-shared', '-fPIC', '-o', SO, src, models])
 
@@ -29,6 +29,8 @@ def lib():
         _lib.hh_normalize.restype = ctypes.c_int64
         _lib.hh_signature.restype = ctypes.c_int64
         _lib.hh_fast_normalize.restype = ctypes.c_int64
+        _lib.hh_fast_normalize3.restype = ctypes.c_int64
+        _lib.hh_n3_roles.restype = ctypes.c_uint32
         _lib.hh_bpe.restype = ctypes.c_int64
         _lib.hh_bpe_fast.restype = ctypes.c_int64
         _lib.hh_unigram.restype = ctypes.c_int64
@@ -146,6 +148,30 @@ def fast_normalize(data, off, real=30):
     n = lib().hh_fast_normalize(_p(data), _p(off), ctypes.c_int64(off.size - 1), ctypes.c_int(real), _p(out), _p(out_off),
                                 ctypes.byref(st), ctypes.byref(ns))
     return out[:n], out_off, st.value, ns.value
+
+
+def fast_normalize3(data, off, real=30):
+    """normalize_text (default flags) through the bit-parallel kernel's lane / exchange / slow-lane structure"""
+    data = np.ascontiguousarray(data, dtype=np.uint8)
+    off = np.ascontiguousarray(off, dtype=np.int64)
+    out = np.zeros(int(data.size) * 3 + 64, dtype=np.uint8)
+    out_off = np.full(off.size, -1, dtype=np.int64)
+    st = ctypes.c_uint32(0)
+    ns = ctypes.c_int64(0)
+    n = lib().hh_fast_normalize3(_p(data), _p(off), ctypes.c_int64(off.size - 1), ctypes.c_int(real), _p(out), _p(out_off),
+                                 ctypes.byref(st), ctypes.byref(ns))
+    return out[:n], out_off, st.value, ns.value
+
+
+def n3_roles(byte):
+    return int(lib().hh_n3_roles(ctypes.c_uint32(byte)))
+
+
+def n3_planes(b32):
+    b = np.ascontiguousarray(b32, dtype=np.uint8)
+    P = np.zeros(8, dtype=np.uint32)
+    lib().hh_n3_planes(_p(b), _p(P))
+    return P
 
 
 def bpe_fast(data, off, real=30, cache_bits=12, stage_cap=24):
