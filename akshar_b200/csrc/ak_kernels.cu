@@ -20,6 +20,7 @@
 #include "ak_subword.cuh"
 #include "ak_fast.cuh"
 #include "ak_norm3.cuh"
+#include "ak_seg3.cuh"
 #include "ak_bpe_fast.cuh"
 #include "ak_seg_fast.cuh"
 #include "unicode_tables.inc"
@@ -1039,6 +1040,162 @@ __global__ void __launch_bounds__(AK_BLOCK, 4) ak_sf_kernel(const AkSfArgs A) {
     }
 }
 
+// ---- K2 + K3 v3: the same outputs from parallel bit streams (ak_seg3.cuh): 32 bytes per lane, a warp covers two
+// 480-byte warp tiles (lanes 1-15 and 16-30), so the bookkeeping per warp tile -- totals, temporary-stream offsets,
+// tile-relative splits -- and with it the sums / scan / copy kernels stay as they are.  Counts are popcounts of the
+// event masks, known before anything is written: no shared-memory staging, the events go straight to the lane's
+// place in the temporary stream.
+#define AKS3_THREADS 128
+#ifndef AKS3_MINB
+#define AKS3_MINB 6
+#endif
+__global__ void __launch_bounds__(AKS3_THREADS, AKS3_MINB) ak_sf3_kernel(const AkSfArgs A) {
+    __shared__ unsigned int s_cursor[2];
+    AkBatch B = A.B;
+    if (!ak_batch_begin(B)) return;
+    const bool want_c = (A.flags & AK_SEG_CLUSTERS) != 0, want_r = (A.flags & AK_SEG_RUNS) != 0;
+    const bool matras = (A.flags & AK_SEG_MATRAS) != 0;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid < 2) s_cursor[tid] = 0;
+    __syncthreads();
+    const int n_wt = akw_n_tiles(B, A.base0);
+    const int n_w3 = (n_wt + 1) >> 1;
+    const int64_t tb = B.text_begin, te = B.text_end;
+    const int64_t cslice = (int64_t)blockIdx.x * A.c_slice, rslice = (int64_t)blockIdx.x * A.r_slice;
+    for (int w3 = blockIdx.x * (AKS3_THREADS / 32) + warp; w3 < n_w3; w3 += gridDim.x * (AKS3_THREADS / 32)) {
+        const int wt0 = 2 * w3;
+        const bool two = wt0 + 1 < n_wt;
+        const int64_t ws = A.base0 + (int64_t)wt0 * AKF_WARP_BYTES;
+        const int64_t r_w0 = A.wrow[wt0], r_w2 = A.wrow[two ? wt0 + 2 : wt0 + 1];
+        const int64_t cs = ws + (int64_t)(lane - 1) * 32;
+        AkS3Lane L;
+        {
+            uint32_t x[8];
+            int64_t lo = tb - cs, hi = te - cs;
+            lo = lo < 0 ? 0 : (lo > 32 ? 32 : lo);
+            hi = hi < 0 ? 0 : (hi > 32 ? 32 : hi);
+            if (lo == 0 && hi == 32) {
+                const uint4 v0 = *reinterpret_cast<const uint4*>(B.text + cs);
+                const uint4 v1 = *reinterpret_cast<const uint4*>(B.text + cs + 16);
+                x[0] = v0.x; x[1] = v0.y; x[2] = v0.z; x[3] = v0.w;
+                x[4] = v1.x; x[5] = v1.y; x[6] = v1.z; x[7] = v1.w;
+                L.own = 0xFFFFFFFFu;
+            } else {
+                akn3_load_edge(B.text, cs, (int)lo, (int)hi, x);
+                L.own = hi > lo ? ((hi == 32 ? 0xFFFFFFFFu : ((1u << hi) - 1u)) & ~((1u << lo) - 1u)) : 0u;
+            }
+            L.rows = akn3_lane_rows(B.off, B.n_rows, r_w0, ws, lane);
+            aks3_phase1(x, L);
+        }
+        uint32_t dn1n = __shfl_down_sync(0xFFFFFFFFu, L.dn1, 1);
+        if (lane == 31) dn1n = 0;
+        aks3_phase2(L, dn1n);
+        aks3_summary(L);
+        const uint32_t up2p = __shfl_up_sync(0xFFFFFFFFu, L.up2, 1);
+        const bool real = lane >= 1 && lane <= 30;
+        const int64_t ss = cs < tb ? tb : cs;
+        const int64_t se = cs + 32 > te + 1 ? te + 1 : cs + 32;
+        const bool active = real && ss < se && (two || lane <= 15);
+        // index of the first row that starts at or after this lane's first position
+        int64_t nr;
+        {
+            const int mine = real ? __popc(L.rows) : 0;
+            int inc = mine;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int y = __shfl_up_sync(0xFFFFFFFFu, inc, d);
+                if (lane >= d) inc += y;
+            }
+            nr = r_w0 + (inc - mine);
+            if (active) while (nr <= B.n_rows && B.off[nr] < ss) ++nr;
+        }
+        const uint32_t tb_bit = (tb >= cs && tb < cs + 32) ? 1u << (int)(tb - cs) : 0u;
+        const uint32_t rows_ev = L.rows & ~tb_bit;
+        bool slow = false;
+        uint32_t st = 0;
+        int cc = 0, rc = 0;
+        const int64_t rlo = r_w0 > 0 ? r_w0 - 1 : 0, rhi = r_w2 > B.n_rows ? B.n_rows : r_w2;
+        if (active) {
+            slow = !aks3_phase3(L, up2p, tb_bit, matras, want_c, want_r);
+            if (slow) {
+                AkSegOut o = A.o;
+                int64_t scc = 0, src = 0;
+                ak_seg_span(A.T, B.text, B.off, B.n_rows, rlo, rhi, ss, se, A.flags, AK_LOOKBACK_LIMIT, false, o, scc, src, st);
+                cc = (int)scc;
+                rc = (int)src;
+            } else {
+                const int nre = __popc(rows_ev);
+                if (want_c) cc = __popc(L.brk) + nre;
+                if (want_r) rc = __popc(L.rchg) + nre;
+            }
+        }
+        // one scan for both counts (a lane has at most 33 events per stream)
+        int inc2 = cc | (rc << 16);
+        const int mine2 = inc2;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int y = __shfl_up_sync(0xFFFFFFFFu, inc2, d);
+            if (lane >= d) inc2 += y;
+        }
+        const int tot2 = __shfl_sync(0xFFFFFFFFu, inc2, 31), half2 = __shfl_sync(0xFFFFFFFFu, inc2, 15);
+        const int ctot = tot2 & 0xFFFF, rtot = tot2 >> 16, chalf = half2 & 0xFFFF, rhalf = half2 >> 16;
+        const int cpre = (inc2 - mine2) & 0xFFFF, rpre = (inc2 - mine2) >> 16;
+        unsigned int ctoff = 0, rtoff = 0;
+        if (lane == 0) {
+            ctoff = atomicAdd(&s_cursor[0], (unsigned int)ctot);
+            rtoff = atomicAdd(&s_cursor[1], (unsigned int)rtot);
+        }
+        ctoff = __shfl_sync(0xFFFFFFFFu, ctoff, 0);
+        rtoff = __shfl_sync(0xFFFFFFFFu, rtoff, 0);
+        const bool fits = (int64_t)ctoff + ctot <= A.c_slice && (int64_t)rtoff + rtot <= A.r_slice;
+        if (lane == 0) {
+            A.c_total[wt0] = chalf;
+            A.c_toff[wt0] = cslice + ctoff;
+            A.r_total[wt0] = rhalf;
+            A.r_toff[wt0] = rslice + rtoff;
+            if (two) {
+                A.c_total[wt0 + 1] = ctot - chalf;
+                A.c_toff[wt0 + 1] = cslice + ctoff + chalf;
+                A.r_total[wt0 + 1] = rtot - rhalf;
+                A.r_toff[wt0 + 1] = rslice + rtoff + rhalf;
+            }
+            if (!fits) st |= AK_ST_OVERFLOW;
+        }
+        if (active) {
+            const bool second = lane > 15;
+            const int cpre_t = second ? cpre - chalf : cpre, rpre_t = second ? rpre - rhalf : rpre;      // tile-relative
+            int32_t* cdst = A.tc + cslice + ctoff;
+            int32_t* rdst = A.tr + rslice + rtoff;
+            uint8_t* tdst = A.tt + rslice + rtoff;
+            if (slow) {
+                AkSegOut o = A.o;
+                o.cluster_ends = cdst + (second ? chalf : 0);
+                o.run_ends = rdst + (second ? rhalf : 0);
+                o.run_tags = tdst + (second ? rhalf : 0);
+                o.cbase = cpre_t;
+                o.rbase = rpre_t;
+                o.ccap = fits ? (second ? ctot - chalf : chalf) : 0;
+                o.rcap = fits ? (second ? rtot - rhalf : rhalf) : 0;
+                uint32_t st2 = 0;
+                int64_t a, b;
+                ak_seg_span(A.T, B.text, B.off, B.n_rows, rlo, rhi, ss, se, A.flags, AK_LOOKBACK_LIMIT, true, o, a, b, st2);
+            } else {
+                int64_t row_last = nr;
+                if (want_c) {
+                    aks3_emit(L, L.brk, rows_ev, cs, B.off, B.n_rows, nr, fits ? cdst + cpre : nullptr, nullptr, A.o.cluster_splits, row_last);
+                    for (int64_t r = nr; r < row_last; ++r) A.o.cluster_splits[r] += cpre_t;
+                }
+                if (want_r) {
+                    aks3_emit(L, L.rchg, rows_ev, cs, B.off, B.n_rows, nr, fits ? rdst + rpre : nullptr, fits ? tdst + rpre : nullptr,
+                              A.o.run_splits, row_last);
+                    for (int64_t r = nr; r < row_last; ++r) A.o.run_splits[r] += rpre_t;
+                }
+            }
+        }
+        ak_raise(B.result, st);
+    }
+}
+
 __global__ void __launch_bounds__(AKW_GROUP) ak_sf_copy_kernel(const AkSfArgs A) {
     __shared__ int ws[33];
     __shared__ long long s_cb[AKW_GROUP];
@@ -1590,7 +1747,7 @@ struct akshar_ctx {
     bool timing = false;
     cudaEvent_t tev[AKSHAR_TIMER_COUNT][2] = {};
     bool tev_valid[AKSHAR_TIMER_COUNT] = {};
-    int occ_norm = 0, occ_seg = 0, occ_bpe = 0, occ_uni = 0, occ_sig = 0, occ_nf_classify = 0, occ_nf_write = 0, occ_nf3 = 0;
+    int occ_norm = 0, occ_seg = 0, occ_bpe = 0, occ_uni = 0, occ_sig = 0, occ_nf_classify = 0, occ_nf_write = 0, occ_nf3 = 0, occ_sf3 = 0;
 };
 
 #define AK_CUDA(ctx, call)                                                                         \
@@ -1669,6 +1826,7 @@ int akshar_ctx_create(int device, akshar_ctx** out) {
     AK_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_nf3, ak_nf3_classify_kernel, AKN3_THREADS, 0));
     AK_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_bf, ak_bf_encode_kernel, AK_BLOCK, 0));
     AK_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_sf, ak_sf_kernel, AK_BLOCK, 0));
+    AK_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_sf3, ak_sf3_kernel, AKS3_THREADS, 0));
     AK_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_seg, ak_segment_kernel, AK_BLOCK, 0));
     AK_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_bpe, ak_bpe_kernel, AK_BLOCK, 0));
     AK_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_uni, ak_unigram_kernel, AK_ROWS_BLOCK, 0));
@@ -1998,7 +2156,9 @@ int akshar_segment_batch(akshar_ctx* ctx, const uint8_t* d_text, const int64_t* 
         F.r_sums = (int32_t*)wp;        wp += ak_align((size_t)ngroups * 4);
         F.c_sum_base = (int64_t*)wp;    wp += ak_align(((size_t)ngroups + 1) * 8);
         F.r_sum_base = (int64_t*)wp;    wp += ak_align(((size_t)ngroups + 1) * 8);
-        const int grid = ak_grid(ctx, ctx->occ_sf, (nwt + AKF_WARPS - 1) / AKF_WARPS);
+        const bool v2 = getenv("AKSHAR_SEG_V2") != nullptr;
+        const int grid = v2 ? ak_grid(ctx, ctx->occ_sf, (nwt + AKF_WARPS - 1) / AKF_WARPS)
+                            : ak_grid(ctx, ctx->occ_sf3, ((nwt + 1) / 2 + AKS3_THREADS / 32 - 1) / (AKS3_THREADS / 32));
         int64_t tc_cap, tr_cap;
         {
             // the temporary streams share what is left of the workspace: 4 B per cluster end, 5 B per run end
@@ -2013,11 +2173,12 @@ int akshar_segment_batch(akshar_ctx* ctx, const uint8_t* d_text, const int64_t* 
         F.tr = (int32_t*)wp;            wp += ak_align((size_t)tr_cap * 4);
         F.tt = (uint8_t*)wp;
         F.o = A.o;
-        ak_warp_rows_kernel<<<(nwt + 1 + 255) / 256, 256, 0, C.stream>>>(C.B, F.base0, nwt + 1, (int64_t*)F.wrow);
+        ak_warp_rows_kernel<<<(nwt + 2 + 255) / 256, 256, 0, C.stream>>>(C.B, F.base0, nwt + 2, (int64_t*)F.wrow);
         if ((rc = ak_after_launch(ctx, "segment-warp-rows"))) return rc;
         {
             AkTimed tm(ctx, AKSHAR_TIMER_SEGMENT, C.stream);
-            ak_sf_kernel<<<grid, AK_BLOCK, 0, C.stream>>>(F);
+            if (v2) ak_sf_kernel<<<grid, AK_BLOCK, 0, C.stream>>>(F);
+            else ak_sf3_kernel<<<grid, AKS3_THREADS, 0, C.stream>>>(F);
         }
         if ((rc = ak_after_launch(ctx, "segment-fast"))) return rc;
         if (want_c) {

@@ -10,6 +10,7 @@
 #include "../../akshar_b200/csrc/ak_subword.cuh"
 #include "../../akshar_b200/csrc/ak_fast.cuh"
 #include "../../akshar_b200/csrc/ak_norm3.cuh"
+#include "../../akshar_b200/csrc/ak_seg3.cuh"
 #include "../../akshar_b200/csrc/ak_bpe_fast.cuh"
 #include "../../akshar_b200/csrc/ak_seg_fast.cuh"
 #include "../../akshar_b200/csrc/ak_models.h"
@@ -296,6 +297,98 @@ int64_t hh_fast_normalize3(const uint8_t* text, const int64_t* off, int64_t n_ro
     *status = st;
     *n_slow = slow_cnt;
     return base;
+}
+
+
+// ---- bit-parallel segmentation (ak_seg3.cuh): byte roles of one byte value, and the kernel's lane structure
+uint32_t hh_s3_roles(uint32_t byte) {
+    uint32_t x[8];
+    for (int i = 0; i < 8; ++i) x[i] = byte * 0x01010101u;
+    AkS3Lane L;
+    memset(&L, 0, sizeof(L));
+    L.own = 0xFFFFFFFFu;
+    aks3_phase1(x, L);
+    const uint32_t m[18] = {L.cont, L.E0b, L.A4b, L.A5b, L.X4b, L.S4b, L.C4b, L.X5b, L.S5b, L.C5b, L.LKb, L.M4b, L.M5b, L.CR, L.LF, L.CTL, L.ROM, L.WEAK};
+    uint32_t r = 0;
+    for (int i = 0; i < 18; ++i) {
+        if (m[i] != 0u && m[i] != 0xFFFFFFFFu) return 0xFFFFFFFFu;
+        if (m[i]) r |= 1u << i;
+    }
+    return r;
+}
+
+void hh_seg_fast3(const uint8_t* text, const int64_t* off, int64_t n_rows, uint32_t flags, int real, int32_t* cluster_ends,
+                  int64_t* cluster_splits, int32_t* run_ends, uint8_t* run_tags, int64_t* run_splits, int64_t cap, int64_t* totals,
+                  uint32_t* status, int64_t* n_slow) {
+    AkTables T = host_tables();
+    const bool want_c = (flags & AK_SEG_CLUSTERS) != 0, want_r = (flags & AK_SEG_RUNS) != 0, matras = (flags & AK_SEG_MATRAS) != 0;
+    const int64_t tb = off[0], te = off[n_rows], base0 = tb;
+    std::vector<uint8_t> rowstart((size_t)(te - base0) + 128, 0);
+    for (int64_t r = 0; r <= n_rows; ++r) rowstart[(size_t)(off[r] - base0)] = 1;
+    const int64_t n_lanes = (te - base0 + 1 + 31) / 32;
+    const int NL = real + 2;
+    std::vector<AkS3Lane> lanes((size_t)NL);
+    int64_t cbase = 0, rbase = 0, nr = 0, slow_cnt = 0;
+    uint32_t st = 0;
+    AkSegOut o;
+    memset(&o, 0, sizeof(o));
+    o.cluster_ends = cluster_ends; o.cluster_splits = cluster_splits; o.run_ends = run_ends; o.run_tags = run_tags;
+    o.run_splits = run_splits; o.ccap = cap; o.rcap = cap;
+    for (int64_t w0 = 0; w0 < n_lanes; w0 += real) {
+        for (int l = 0; l < NL; ++l) {
+            AkS3Lane& L = lanes[(size_t)l];
+            memset(&L, 0, sizeof(L));
+            const int64_t cs = base0 + (w0 - 1 + l) * 32;
+            uint32_t x[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            for (int i = 0; i < 32; ++i) {
+                const int64_t q = cs + i;
+                if (q >= tb && q < te) { x[i >> 2] |= (uint32_t)text[q] << ((i & 3) * 8); L.own |= 1u << i; }
+                if (q >= base0 && q - base0 < (int64_t)rowstart.size() && rowstart[(size_t)(q - base0)]) L.rows |= 1u << i;
+            }
+            aks3_phase1(x, L);
+        }
+        for (int l = 0; l < NL; ++l) {
+            aks3_phase2(lanes[(size_t)l], l + 1 < NL ? lanes[(size_t)l + 1].dn1 : 0u);
+            aks3_summary(lanes[(size_t)l]);
+        }
+        for (int l = 1; l <= real; ++l) {
+            AkS3Lane& L = lanes[(size_t)l];
+            const int64_t cs = base0 + (w0 - 1 + l) * 32;
+            const int64_t ss = cs < tb ? tb : cs, se = cs + 32 > te + 1 ? te + 1 : cs + 32;
+            if (ss >= se) continue;
+            while (nr <= n_rows && off[nr] < ss) ++nr;
+            const uint32_t tb_bit = (tb >= cs && tb < cs + 32) ? 1u << (int)(tb - cs) : 0u;
+            const bool fast = aks3_phase3(L, lanes[(size_t)l - 1].up2, tb_bit, matras, want_c, want_r);
+            if (!fast) {
+                ++slow_cnt;
+                int64_t a = 0, b = 0;
+                o.cbase = cbase; o.rbase = rbase;
+                ak_seg_span(T, text, off, n_rows, 0, n_rows, ss, se, flags, 0, true, o, a, b, st);
+                cbase += a; rbase += b;
+                while (nr <= n_rows && off[nr] < se) ++nr;
+            } else {
+                const uint32_t rows_ev = L.rows & ~tb_bit;
+                int64_t rl = nr, rl2 = nr;
+                if (want_c) {
+                    const int k = aks3_emit(L, L.brk, rows_ev, cs, off, n_rows, nr, cluster_ends + cbase, nullptr, cluster_splits, rl);
+                    if (k != akb_popc(L.brk) + akb_popc(rows_ev)) st |= 0x40000000u;
+                    for (int64_t r = nr; r < rl; ++r) cluster_splits[r] += cbase;
+                    cbase += k;
+                }
+                if (want_r) {
+                    const int k = aks3_emit(L, L.rchg, rows_ev, cs, off, n_rows, nr, run_ends + rbase, run_tags + rbase, run_splits, rl2);
+                    if (k != akb_popc(L.rchg) + akb_popc(rows_ev)) st |= 0x40000000u;
+                    for (int64_t r = nr; r < rl2; ++r) run_splits[r] += rbase;
+                    rbase += k;
+                }
+                nr = want_c ? rl : rl2;
+            }
+        }
+    }
+    totals[0] = cbase;
+    totals[1] = rbase;
+    *status = st;
+    *n_slow = slow_cnt;
 }
 
 // roman_phonetic_signature of every row; returns output bytes

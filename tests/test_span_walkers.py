@@ -230,6 +230,90 @@ def test_segment_fast_structure(real, stage_cap):
     assert np.array_equal(gcs, ms) and np.array_equal(gce, me)
 
 
+# ---- bit-parallel segmentation (ak_seg3.cuh)
+def test_segment_byte_roles_match_the_tables():
+    import json
+    import os
+    t = json.load(open(os.path.join(os.path.dirname(O.__file__), 'ucd_tables.json')))
+
+    def expand(name):
+        a = np.zeros(0x110000, dtype=np.int32)
+        for r in t[name]:
+            a[r[0]:r[1] + 1] = r[2]
+        return a
+    gcb, incb = expand('gcb'), expand('incb')
+    names = ['cont', 'E0b', 'A4b', 'A5b', 'X4b', 'S4b', 'C4b', 'X5b', 'S5b', 'C5b', 'LKb', 'M4b', 'M5b', 'CR', 'LF', 'CTL', 'ROM', 'WEAK']
+    is_matra = lambda c: 0x900 <= c <= 0x902 or 0x93E <= c <= 0x94D or 0x951 <= c <= 0x954        # segment.py:20-37
+    for b in range(256):
+        r = W.s3_roles(b)
+        assert r != 0xFFFFFFFF
+        g = lambda n: (r >> names.index(n)) & 1
+        assert g('cont') == (0x80 <= b < 0xC0) and g('E0b') == (b == 0xE0) and g('A4b') == (b == 0xA4) and g('A5b') == (b == 0xA5)
+        if 0x80 <= b < 0xC0:
+            c4, c5 = 0x900 + (b & 63), 0x940 + (b & 63)
+            assert g('X4b') == (gcb[c4] == 4) and g('S4b') == (gcb[c4] == 8) and g('C4b') == (incb[c4] == 1), hex(c4)
+            assert g('X5b') == (gcb[c5] == 4) and g('S5b') == (gcb[c5] == 8) and g('C5b') == (incb[c5] == 1), hex(c5)
+            assert g('LKb') == (incb[c5] == 2) and g('M4b') == is_matra(c4) and g('M5b') == is_matra(c5)
+            for c in (c4, c5):      # what the fast lane assumes about the block
+                assert gcb[c] in (0, 4, 8) and (incb[c] in (2, 3)) == (gcb[c] == 4)
+        if b < 0x80:
+            ch = chr(b)
+            assert g('CR') == (b == 0x0D) and g('LF') == (b == 0x0A) and g('CTL') == (gcb[b] == 3)
+            assert g('ROM') == (O.identify_script(ch) == 'roman')
+            assert g('WEAK') == (O.identify_script(ch) in ('digit', 'punct')), ch
+
+
+def _seg3_check(lines, real):
+    data, off = sc.pack(lines)
+    ce, cs = OB.segment_batch(lines)
+    re_, rt, rs = OB.runs_batch(lines)
+    gce, gcs, gre, grt, grs, st, ns = W.seg_fast3(data, off, flags=1 | 4, real=real)
+    assert st == 0
+    assert np.array_equal(gcs, cs) and np.array_equal(gce, ce)
+    assert np.array_equal(grs, rs) and np.array_equal(gre, re_) and np.array_equal(grt, rt)
+    me, ms = OB.segment_batch(lines, matras=True)
+    gce, gcs, _, _, _, st, _ = W.seg_fast3(data, off, flags=1 | 2, real=real)
+    assert st == 0
+    assert np.array_equal(gcs, ms) and np.array_equal(gce, me)
+    return ns / max(1.0, data.size / 32)
+
+
+@pytest.mark.parametrize('real', [30, 1, 4])
+def test_segment_bit_parallel_structure(real):
+    _seg3_check(list(_lines()), real)
+
+
+def test_segment_bit_parallel_fuzz():
+    alpha = ['a', 'Z', 'e', ' ', ' ', '1', '9', '.', '-', '(', '\u0915', '\u093e', '\u094d', '\u094d', '\u093f', '\u0902', '\u093c',
+             '\u0937', '\u0930', '\r', '\n', '\t', '\x01', '\x7f', '_', '@', '\u0950', '\u0964', '\u0966', '\u0962', '\u0903',
+             '\u0904', '\u0915', '\u0915', '\u0921', '\u097b', '!', '[', '}']
+    rng = np.random.default_rng(9)
+
+    def rand_lines(n, max_len, alpha):
+        out = []
+        for _ in range(n):
+            n_ch = int(rng.integers(0, max_len + 1))
+            if rng.random() < 0.6:
+                s = ''.join(alpha[int(i)] for i in rng.integers(0, len(alpha), size=n_ch))
+            else:
+                s = ''
+                while len(s) < n_ch:
+                    s += alpha[int(rng.integers(len(alpha)))] * int(rng.integers(1, 40))
+            out.append(s)
+        return out
+    for max_len, real in [(120, 30), (400, 7), (6, 2)]:
+        _seg3_check(rand_lines(1500, max_len, alpha), real)                                      # closed alphabet: fast lanes
+        _seg3_check(rand_lines(800, max_len, alpha + ['\U0001F600', '\u0995', '\u200d', '\u00a0', 'e\u0301']), real)     # + foreign
+    _seg3_check(['1234567890' * 20, '.' * 100 + 'a' + '.' * 70 + '\u0915', '\u094d' * 40 + '\u0915', '\u0915' + '\u094d' * 40 + '\u0915',
+                 '\u0915\u094d' + '\u093c' * 30 + '\u0915', '\r\n' * 40, ''], 30)
+
+
+def test_segment_bit_parallel_is_all_fast_on_normalized_text():
+    for kind in ('hinglish', 'hindi', 'social'):
+        lines = [O.normalize_text(s) for s in sc.Corpus(kind, 8).lines(100000)]
+        assert _seg3_check(lines, 30) < 0.001
+
+
 def test_segment_fast_is_mostly_fast():
     for kind in ('hinglish', 'hindi', 'social'):
         lines = sc.Corpus(kind, 8).lines(200000)

@@ -16,7 +16,7 @@ def build():
     csrc = os.path.join(ROOT, 'akshar_b200', 'csrc')
     models = os.path.join(csrc, 'ak_models.cpp')
     deps = [src, models] + [os.path.join(csrc, f) for f in
-                            ('ak_unicode.cuh', 'ak_bits.cuh', 'ak_norm3.cuh', 'ak_text_core.cuh', 'ak_subword.cuh', 'ak_fast.cuh', 'ak_bpe_fast.cuh', 'ak_seg_fast.cuh', 'ak_models.h', 'unicode_tables.inc')]
+                            ('ak_unicode.cuh', 'ak_bits.cuh', 'ak_norm3.cuh', 'ak_seg3.cuh', 'ak_text_core.cuh', 'ak_subword.cuh', 'ak_fast.cuh', 'ak_bpe_fast.cuh', 'ak_seg_fast.cuh', 'ak_models.h', 'unicode_tables.inc')]
     if not os.path.exists(SO) or any(os.path.getmtime(d) > os.path.getmtime(SO) for d in deps):
         subprocess.check_call(['g++', '-O2', '-std=c++17', '-shared', '-fPIC', '-o', SO, src, models])
 
@@ -31,6 +31,7 @@ def lib():
         _lib.hh_fast_normalize.restype = ctypes.c_int64
         _lib.hh_fast_normalize3.restype = ctypes.c_int64
         _lib.hh_n3_roles.restype = ctypes.c_uint32
+        _lib.hh_s3_roles.restype = ctypes.c_uint32
         _lib.hh_bpe.restype = ctypes.c_int64
         _lib.hh_bpe_fast.restype = ctypes.c_int64
         _lib.hh_unigram.restype = ctypes.c_int64
@@ -209,4 +210,26 @@ def seg_fast(data, off, flags=1, real=30, stage_cap=18):
     lib().hh_seg_fast(_p(data), _p(off), ctypes.c_int64(off.size - 1), ctypes.c_uint32(flags), ctypes.c_int(real),
                       ctypes.c_int(stage_cap), _p(ce), _p(cs), _p(re_), _p(rt), _p(rs), ctypes.c_int64(cap), _p(tot),
                       ctypes.byref(st), ctypes.byref(ns))
+    return ce[:tot[0]], cs, re_[:tot[1]], rt[:tot[1]], rs, st.value, ns.value
+
+
+def s3_roles(byte):
+    return int(lib().hh_s3_roles(ctypes.c_uint32(byte)))
+
+
+def seg_fast3(data, off, flags=1, real=30):
+    """clusters / script runs through the bit-parallel kernel's lane structure (ak_seg3.cuh)"""
+    data = np.ascontiguousarray(data, dtype=np.uint8)
+    off = np.ascontiguousarray(off, dtype=np.int64)
+    cap = int(data.size) + off.size + 1
+    ce = np.zeros(cap, dtype=np.int32)
+    cs = np.full(off.size, -1, dtype=np.int64)
+    re_ = np.zeros(cap, dtype=np.int32)
+    rt = np.zeros(cap, dtype=np.uint8)
+    rs = np.full(off.size, -1, dtype=np.int64)
+    tot = np.zeros(2, dtype=np.int64)
+    st = ctypes.c_uint32(0)
+    ns = ctypes.c_int64(0)
+    lib().hh_seg_fast3(_p(data), _p(off), ctypes.c_int64(off.size - 1), ctypes.c_uint32(flags), ctypes.c_int(real),
+                       _p(ce), _p(cs), _p(re_), _p(rt), _p(rs), ctypes.c_int64(cap), _p(tot), ctypes.byref(st), ctypes.byref(ns))
     return ce[:tot[0]], cs, re_[:tot[1]], rt[:tot[1]], rs, st.value, ns.value
