@@ -21,6 +21,7 @@
 #include "ak_fast.cuh"
 #include "ak_norm3.cuh"
 #include "ak_seg3.cuh"
+#include "ak_bpe3.cuh"
 #include "ak_bpe_fast.cuh"
 #include "ak_seg_fast.cuh"
 #include "unicode_tables.inc"
@@ -1359,6 +1360,211 @@ __device__ __noinline__ void akb_tile_fallback(const AkBfArgs& A, const AkBatch&
     }
 }
 
+// one 480-byte warp tile of the v2 (16 bytes per lane) encoder: classification, event list, cache look-ups, ids to the
+// CTA's slice of the temporary stream.  Also the fallback of the bit-parallel kernel for warp tiles with too many events.
+__device__ __noinline__ void akb_v2_warp_tile(const AkBfArgs& A, const AkBatch& B, int wt, int lane, const uint32_t* lut,
+                                              uint32_t* ev_w, uint32_t* res_w, uint16_t* eoff_w, unsigned int* s_cursor, int64_t slice) {
+    const int64_t ws = A.base0 + (int64_t)wt * AKF_WARP_BYTES;
+    const int64_t r_w0 = A.wrow[wt], r_w1 = A.wrow[wt + 1];
+    AkBChunk c;
+    const int64_t cs = ws + (int64_t)(lane - 1) * 16;
+    akf_load_lane(B, cs, c);
+    c.rows = akw_lane_rows(B.off, B.n_rows, r_w0, ws, lane);
+    akb_phase_a(A.T, lut, c);
+    {
+        uint32_t pw = __shfl_up_sync(0xFFFFFFFFu, c.last_w, 1);
+        uint32_t pk = __shfl_up_sync(0xFFFFFFFFu, c.last_cls, 1);
+        if (lane == 0) {
+            pw = AKF_NONE;
+            pk = 2;
+            if (c.first_pos < 32u && cs > B.text_begin) {
+                int64_t q = cs - 1;
+                int k = 0;
+                while (q > B.text_begin && k < 3 && (B.text[q] & 0xC0u) == 0x80u) { --q; ++k; }
+                int len;
+                pw = akf_props(A.T, lut, ak_decode(B.text, q, B.text_end, len));
+                pk = AK_HFCLASS(pw);
+            }
+        }
+        akb_resolve_first(c, pw, pk);
+    }
+    // word boundaries of the next chunk (bits 0..15) and of the one after it (bits 16..31; unknown for lane 30)
+    uint32_t next_bnd = __shfl_down_sync(0xFFFFFFFFu, c.bnd, 1) & 0xFFFFu;
+    {
+        const uint32_t n2 = __shfl_down_sync(0xFFFFFFFFu, c.bnd, 2) & 0xFFFFu;
+        if (lane < 30) next_bnd |= n2 << 16;
+    }
+    const bool real = lane >= 1 && lane <= AKF_REAL;
+    const int64_t ss = cs < B.text_begin ? B.text_begin : cs;
+    const int64_t se = cs + 16 > B.text_end + 1 ? B.text_end + 1 : cs + 16;
+    const bool active = real && ss < se;
+    AkBLaneCtx X;
+    X.M = &A.M;
+    X.T = &A.T;
+    X.C = &A.C;
+    X.text = B.text;
+    X.off = B.off;
+    X.n_rows = B.n_rows;
+    X.r_lo = r_w0 > 0 ? r_w0 - 1 : 0;
+    X.r_hi = r_w1 > B.n_rows ? B.n_rows : r_w1;
+    X.pool = &A.pool;
+    uint32_t st = 0;
+    if (active) {
+        if (c.flags & AKB_ALPHABET) st |= AK_ST_ALPHABET;
+        if ((c.flags & AKF_TROUBLE) && akb_chunk_changes(X, c, cs, AK_LOOKBACK_LIMIT, st)) atomicOr(A.changed, 1u);
+    }
+    // ---- the warp tile's EVENT LIST: row starts and word starts in position order, so that the words can be
+    // encoded one per lane, 32 at a time, whatever chunk they came from
+    uint32_t wstart = 0;
+    if (active) {
+        const uint32_t hi = (c.cls >> 1) & 0x55555555u & ~c.cls;      // bit 2i set <=> class at byte i is 2 (space)
+        uint32_t x = hi;
+        x = (x | (x >> 1)) & 0x33333333u;
+        x = (x | (x >> 2)) & 0x0F0F0F0Fu;
+        x = (x | (x >> 4)) & 0x00FF00FFu;
+        x = (x | (x >> 8)) & 0x0000FFFFu;
+        wstart = c.bnd & c.lead & ~x;
+    }
+    const uint32_t rowsm = active ? (c.rows & 0xFFFFu) : 0u;
+    const int n_row_ev = __popc(rowsm), n_ev = n_row_ev + __popc(wstart);
+    int e_inc = n_ev, r_inc = n_row_ev;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int y = __shfl_up_sync(0xFFFFFFFFu, e_inc, d);
+        const int z = __shfl_up_sync(0xFFFFFFFFu, r_inc, d);
+        if (lane >= d) { e_inc += y; r_inc += z; }
+    }
+    const int E = __shfl_sync(0xFFFFFFFFu, e_inc, 31);
+    uint32_t* ev = ev_w;
+    uint32_t* res = res_w;
+    uint16_t* eoff = eoff_w;
+    bool use_list = E <= AKB_EVCAP;
+    int total = 0;
+    if (use_list) {
+        {
+            int k = e_inc - n_ev, rord = r_inc - n_row_ev;
+            uint32_t m = rowsm | wstart;
+            while (m) {
+                const int i = __ffs(m) - 1;
+                m &= m - 1u;
+                const uint32_t pos = (uint32_t)(cs + i - ws);
+                if ((rowsm >> i) & 1u) ev[k++] = pos | (1u << 9) | ((uint32_t)rord++ << 12);
+                if ((wstart >> i) & 1u) {
+                    const uint32_t kc = (c.cls >> (2 * i)) & 3u;
+                    const int64_t e = akb_word_end(A.T, B.text, cs, i, kc, c.bnd, next_bnd, B.off, B.n_rows, X.r_lo, X.r_hi);
+                    int64_t len = e - (cs + i);
+                    if (len > 0xFFFFF) len = 0xFFFFF;
+                    ev[k++] = pos | (kc << 10) | ((uint32_t)len << 12);
+                }
+            }
+        }
+        __syncwarp();
+        // ---- pass 1: tokens per event (cache lookup; a miss runs the merge loop and publishes the word)
+        int running = 0;
+        for (int base = 0; base < E; base += 32) {
+            const int e = base + lane;
+            int n = 0;
+            uint32_t rr = 0;
+            if (e < E) {
+                const uint32_t v = ev[e];
+                const int64_t p = ws + (v & 511u);
+                if (v & (1u << 9)) {
+                    int64_t g = r_w0 + (v >> 12);
+                    while (g < B.n_rows && B.off[g] < p) ++g;
+                    while (g <= B.n_rows && B.off[g] == p) {
+                        if (g > 0 && A.M.eos >= 0) ++n;
+                        if (g < B.n_rows && A.M.bos >= 0) ++n;
+                        ++g;
+                    }
+                    rr = 0x40000000u | (uint32_t)n;
+                } else {
+                    const uint32_t kc = (v >> 10) & 3u;
+                    const uint32_t len = v >> 12;
+                    // hot path: hash, probe, compare -- everything else lives in akb_event_slow (kept out of line so
+                    // that this loop stays small in the instruction cache)
+                    long long hit = -1, slot = -1;
+                    unsigned long long h = 0, want = 0;
+                    const bool cacheable = len <= AKW_MAXLEN && A.C.e != nullptr;
+                    if (cacheable) {
+                        h = akw_hash(B.text, p, len);
+                        want = akw_want(h, len);
+                        hit = akw_find(A.C, h, want, B.text, p, len, &slot);
+                    }
+                    if (hit >= 0) {
+                        n = (int)((akw_ld(A.C.e + (unsigned long long)hit * AKW_ENTRY) & AKW_NTOK_MASK) >> 3);
+                        rr = ((uint32_t)hit << 5) | (uint32_t)n;
+                    } else {
+                        rr = akb_event_slow(A, B, p, len, kc, h, want, slot, cacheable, X.r_lo, X.r_hi, st);
+                        n = (rr & 0x80000000u) ? (int)(rr & 0x3FFFFFFFu) : (int)(rr & 31u);
+                    }
+                }
+            }
+            int inc = n;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int y = __shfl_up_sync(0xFFFFFFFFu, inc, d);
+                if (lane >= d) inc += y;
+            }
+            if (e < E) {
+                res[e] = rr;
+                eoff[e] = (uint16_t)(running + inc - n);
+            }
+            running += __shfl_sync(0xFFFFFFFFu, inc, 31);
+        }
+        total = running;
+        if (total >= 65536) use_list = false;      // offsets are 16-bit (thousands of empty rows at one position)
+    }
+    if (use_list) {
+        unsigned int toff = 0;
+        if (lane == 0) toff = atomicAdd(s_cursor, (unsigned int)total);
+        toff = __shfl_sync(0xFFFFFFFFu, toff, 0);
+        const bool fits = (int64_t)toff + total <= A.slice_cap;
+        if (lane == 0) {
+            A.wt_total[wt] = total;
+            A.wt_toff[wt] = slice + toff;
+            if (!fits) st |= AK_ST_OVERFLOW;
+        }
+        __syncwarp();
+        // ---- pass 2: write the ids (from the cache entries) and the row splits (warp-tile relative)
+        int32_t* tbase = A.temp + slice + toff;
+        for (int base = 0; base < E; base += 32) {
+            const int e = base + lane;
+            if (e >= E) continue;
+            const uint32_t v = ev[e], rr = res[e];
+            const int o = eoff[e];
+            const int64_t p = ws + (v & 511u);
+            if (v & (1u << 9)) {
+                int64_t g = r_w0 + (v >> 12);
+                while (g < B.n_rows && B.off[g] < p) ++g;
+                int k = o;
+                while (g <= B.n_rows && B.off[g] == p) {
+                    if (g > 0 && A.M.eos >= 0) { if (fits) tbase[k] = A.M.eos; ++k; }
+                    A.id_splits[g] = k;
+                    if (g < B.n_rows && A.M.bos >= 0) { if (fits) tbase[k] = A.M.bos; ++k; }
+                    ++g;
+                }
+            } else if (fits) {
+                const int n = (int)(rr & 31u);
+                if (!(rr & 0x80000000u)) {
+                    const unsigned long long* en = A.C.e + (unsigned long long)((rr >> 5) & 0x3FFFFu) * AKW_ENTRY;
+#pragma unroll 1
+                    for (int i = 0; i < n; i += 2) {
+                        const unsigned long long q = akw_ld(en + 8 + (i >> 1));
+                        tbase[o + i] = (int32_t)(uint32_t)q;
+                        if (i + 1 < n) tbase[o + i + 1] = (int32_t)(uint32_t)(q >> 32);
+                    }
+                } else {
+                    akb_event_write_direct(A, B, p, v >> 12, (v >> 10) & 3u, X.r_lo, X.r_hi, tbase + o, (int64_t)(rr & 0x3FFFFFFFu));
+                }
+            }
+        }
+    } else {
+        akb_tile_fallback(A, B, X, c, next_bnd, cs, active, lane, wt, slice, r_w0, r_inc - n_row_ev, s_cursor, st);
+    }
+    __syncwarp();
+    ak_raise(B.result, st);
+}
+
 #ifndef AKB_MINB
 #define AKB_MINB 4
 #endif
@@ -1378,74 +1584,127 @@ __global__ void __launch_bounds__(AK_BLOCK, AKB_MINB) ak_bf_encode_kernel(const 
     const int n_wt = akw_n_tiles(B, A.base0);
     const int64_t slice = (int64_t)blockIdx.x * A.slice_cap;
     for (int wt0 = blockIdx.x * AKF_WARPS; wt0 < n_wt; wt0 += gridDim.x * AKF_WARPS) {
-#ifdef AKB_CTA_SYNC
-        // keep the CTA's warps in the same code region (instruction cache)
-        __syncthreads();
-#endif
         const int wt = wt0 + warp;
         if (wt >= n_wt) continue;
-        const int64_t ws = A.base0 + (int64_t)wt * AKF_WARP_BYTES;
-        const int64_t r_w0 = A.wrow[wt], r_w1 = A.wrow[wt + 1];
-        AkBChunk c;
-        const int64_t cs = ws + (int64_t)(lane - 1) * 16;
-        akf_load_lane(B, cs, c);
-        c.rows = akw_lane_rows(B.off, B.n_rows, r_w0, ws, lane);
-        akb_phase_a(A.T, lut, c);
+        akb_v2_warp_tile(A, B, wt, lane, lut, s_ev + warp * AKB_EVCAP, s_res + warp * AKB_EVCAP, s_eoff + warp * AKB_EVCAP, &s_cursor, slice);
+    }
+}
+
+// ---- K4a v3: the same encoder behind a bit-parallel front end (ak_bpe3.cuh).  32 bytes per lane, a warp covers two
+// 480-byte warp tiles (lanes 1-15 / 16-30) with ONE event list, so the per-tile bookkeeping and the sums / scan / copy
+// kernels are shared with v2.  Event record: position in the 960 bytes (10 bits) | row flag (bit 10) | class (bits 11-12) |
+// word length or row ordinal (from bit 13).
+#define AKB3_THREADS 128
+#define AKB3_WARPS (AKB3_THREADS / 32)
+#define AKB3_EVCAP 768
+#ifndef AKB3_MINB
+#define AKB3_MINB 5
+#endif
+
+// exact NFC check of the troubled code points (cold): does NFC change the text?
+__device__ __noinline__ bool akb3_changes(const AkTables& T, const uint8_t* text, const int64_t* off, int64_t n_rows, int64_t r_lo,
+                                          uint32_t trb, int64_t cs, uint32_t& status) {
+    bool changed = false;
+    int64_t checked_until = -1;
+    while (trb) {
+        const int i = __ffs(trb) - 1;
+        trb &= trb - 1u;
+        const int64_t p = cs + i;
+        if (p < checked_until) continue;
+        const int64_t r = ak_row_lower_bound(off, r_lo, n_rows, p + 1);
+        const int64_t rs = off[r - 1], re = off[r];
+        if (ak_segment_changes(T, text, p, rs, re, AK_LOOKBACK_LIMIT, &checked_until, status)) changed = true;
+    }
+    return changed;
+}
+
+// end of a word of class k with no boundary before `from` (cold: words longer than 64 bytes)
+__device__ __noinline__ int64_t akb3_scan_end(const AkTables& T, const uint8_t* t, int64_t wpos, int64_t from, uint32_t k,
+                                              const int64_t* off, int64_t n_rows, int64_t r_lo, int64_t r_hi) {
+    int64_t er = ak_row_lower_bound(off, r_lo, r_hi, wpos + 1);
+    if (off[er] < wpos + 1) er = ak_row_lower_bound(off, r_hi, n_rows, wpos + 1);
+    const int64_t re = off[er];
+    int64_t q = from;
+    if (q > re) q = re;
+    while (q < re && (t[q] & 0xC0u) == 0x80u) ++q;
+    while (q < re) {
+        int len;
+        const uint32_t cp = ak_decode(t, q, re, len);
+        if (AK_HFCLASS(ak_props(T, cp)) != k) break;
+        q += len;
+    }
+    return q;
+}
+
+__global__ void __launch_bounds__(AKB3_THREADS, AKB3_MINB) ak_bf3_encode_kernel(const AkBfArgs A) {
+    __shared__ uint32_t lut[384];                              // only the fallback (akb_v2_warp_tile) reads it
+    __shared__ uint32_t s_ev[AKB3_EVCAP * AKB3_WARPS];
+    __shared__ uint32_t s_res[AKB3_EVCAP * AKB3_WARPS];
+    __shared__ uint16_t s_eoff[AKB3_EVCAP * AKB3_WARPS];
+    __shared__ unsigned int s_cursor;
+    AkBatch B = A.B;
+    if (!ak_batch_begin(B)) return;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int i = tid; i < 384; i += AKB3_THREADS)
+        lut[i] = i < 128 ? A.T.leaves[((uint32_t)A.T.page_index[0] << 8) | i] : A.T.leaves[((uint32_t)A.T.page_index[9] << 8) | (i - 128)];
+    if (tid == 0) s_cursor = 0;
+    __syncthreads();
+    const int n_wt = akw_n_tiles(B, A.base0);
+    const int n_w3 = (n_wt + 1) >> 1;
+    const int64_t tb = B.text_begin, te = B.text_end;
+    const int64_t slice = (int64_t)blockIdx.x * A.slice_cap;
+    uint32_t* ev = s_ev + warp * AKB3_EVCAP;
+    uint32_t* res = s_res + warp * AKB3_EVCAP;
+    uint16_t* eoff = s_eoff + warp * AKB3_EVCAP;
+    for (int w3 = blockIdx.x * AKB3_WARPS + warp; w3 < n_w3; w3 += gridDim.x * AKB3_WARPS) {
+        const int wt0 = 2 * w3;
+        const bool two = wt0 + 1 < n_wt;
+        const int64_t ws = A.base0 + (int64_t)wt0 * AKF_WARP_BYTES;
+        const int64_t r_w0 = A.wrow[wt0], r_w2 = A.wrow[two ? wt0 + 2 : wt0 + 1];
+        const int64_t cs = ws + (int64_t)(lane - 1) * 32;
+        const int64_t r_lo = r_w0 > 0 ? r_w0 - 1 : 0, r_hi = r_w2 > B.n_rows ? B.n_rows : r_w2;
+        AkB3Lane L;
         {
-            uint32_t pw = __shfl_up_sync(0xFFFFFFFFu, c.last_w, 1);
-            uint32_t pk = __shfl_up_sync(0xFFFFFFFFu, c.last_cls, 1);
-            if (lane == 0) {
-                pw = AKF_NONE;
-                pk = 2;
-                if (c.first_pos < 32u && cs > B.text_begin) {
-                    int64_t q = cs - 1;
-                    int k = 0;
-                    while (q > B.text_begin && k < 3 && (B.text[q] & 0xC0u) == 0x80u) { --q; ++k; }
-                    int len;
-                    pw = akf_props(A.T, lut, ak_decode(B.text, q, B.text_end, len));
-                    pk = AK_HFCLASS(pw);
-                }
+            uint32_t x[8];
+            int64_t lo = tb - cs, hi = te - cs;
+            lo = lo < 0 ? 0 : (lo > 32 ? 32 : lo);
+            hi = hi < 0 ? 0 : (hi > 32 ? 32 : hi);
+            if (lo == 0 && hi == 32) {
+                const uint4 v0 = *reinterpret_cast<const uint4*>(B.text + cs);
+                const uint4 v1 = *reinterpret_cast<const uint4*>(B.text + cs + 16);
+                x[0] = v0.x; x[1] = v0.y; x[2] = v0.z; x[3] = v0.w;
+                x[4] = v1.x; x[5] = v1.y; x[6] = v1.z; x[7] = v1.w;
+                L.own = 0xFFFFFFFFu;
+            } else {
+                akn3_load_edge(B.text, cs, (int)lo, (int)hi, x);
+                L.own = hi > lo ? ((hi == 32 ? 0xFFFFFFFFu : ((1u << hi) - 1u)) & ~((1u << lo) - 1u)) : 0u;
             }
-            akb_resolve_first(c, pw, pk);
+            L.rows = akn3_lane_rows(B.off, B.n_rows, r_w0, ws, lane);
+            akb3_phase1(x, L);
         }
-        // word boundaries of the next chunk (bits 0..15) and of the one after it (bits 16..31; unknown for lane 30)
-        uint32_t next_bnd = __shfl_down_sync(0xFFFFFFFFu, c.bnd, 1) & 0xFFFFu;
-        {
-            const uint32_t n2 = __shfl_down_sync(0xFFFFFFFFu, c.bnd, 2) & 0xFFFFu;
-            if (lane < 30) next_bnd |= n2 << 16;
-        }
-        const bool real = lane >= 1 && lane <= AKF_REAL;
-        const int64_t ss = cs < B.text_begin ? B.text_begin : cs;
-        const int64_t se = cs + 16 > B.text_end + 1 ? B.text_end + 1 : cs + 16;
-        const bool active = real && ss < se;
-        AkBLaneCtx X;
-        X.M = &A.M;
-        X.T = &A.T;
-        X.C = &A.C;
-        X.text = B.text;
-        X.off = B.off;
-        X.n_rows = B.n_rows;
-        X.r_lo = r_w0 > 0 ? r_w0 - 1 : 0;
-        X.r_hi = r_w1 > B.n_rows ? B.n_rows : r_w1;
-        X.pool = &A.pool;
+        uint32_t dn1n = __shfl_down_sync(0xFFFFFFFFu, L.dn1, 1);
+        if (lane == 31) dn1n = 0;
+        akb3_phase2(L, dn1n);
+        if (L.FOR) akb3_foreign(A.T, B.text, cs, te, L);
+        akb3_summary(L);
+        const uint32_t up2p = __shfl_up_sync(0xFFFFFFFFu, L.up2, 1);
+        akb3_phase3(L, up2p);
+        const bool real = lane >= 1 && lane <= 30;
+        const int64_t ss = cs < tb ? tb : cs;
+        const int64_t se = cs + 32 > te + 1 ? te + 1 : cs + 32;
+        const bool active = real && ss < se && (two || lane <= 15);
         uint32_t st = 0;
         if (active) {
-            if (c.flags & AKB_ALPHABET) st |= AK_ST_ALPHABET;
-            if ((c.flags & AKF_TROUBLE) && akb_chunk_changes(X, c, cs, AK_LOOKBACK_LIMIT, st)) atomicOr(A.changed, 1u);
+            if (L.flags & 1u) st |= AK_ST_ALPHABET;
+            if (L.trb && akb3_changes(A.T, B.text, B.off, B.n_rows, r_lo, L.trb, cs, st)) atomicOr(A.changed, 1u);
         }
-        // ---- the warp tile's EVENT LIST: row starts and word starts in position order, so that the words can be
-        // encoded one per lane, 32 at a time, whatever chunk they came from
-        uint32_t wstart = 0;
-        if (active) {
-            const uint32_t hi = (c.cls >> 1) & 0x55555555u & ~c.cls;      // bit 2i set <=> class at byte i is 2 (space)
-            uint32_t x = hi;
-            x = (x | (x >> 1)) & 0x33333333u;
-            x = (x | (x >> 2)) & 0x0F0F0F0Fu;
-            x = (x | (x >> 4)) & 0x00FF00FFu;
-            x = (x | (x >> 8)) & 0x0000FFFFu;
-            wstart = c.bnd & c.lead & ~x;
-        }
-        const uint32_t rowsm = active ? (c.rows & 0xFFFFu) : 0u;
+        // boundaries of the next two lanes (the right halo lane classified its last two bytes without look-ahead)
+        const uint32_t bsend = lane == 31 ? (L.bnd & 0x3FFFFFFFu) : L.bnd;
+        const uint32_t nb1 = __shfl_down_sync(0xFFFFFFFFu, bsend, 1);
+        uint32_t nb2 = __shfl_down_sync(0xFFFFFFFFu, bsend, 2);
+        if (lane >= 30) nb2 = 0;
+        const uint32_t wstart = active ? L.wstart : 0u;
+        const uint32_t rowsm = active ? L.rows : 0u;
         const int n_row_ev = __popc(rowsm), n_ev = n_row_ev + __popc(wstart);
         int e_inc = n_ev, r_inc = n_row_ev;
 #pragma unroll
@@ -1455,10 +1714,8 @@ __global__ void __launch_bounds__(AK_BLOCK, AKB_MINB) ak_bf_encode_kernel(const 
             if (lane >= d) { e_inc += y; r_inc += z; }
         }
         const int E = __shfl_sync(0xFFFFFFFFu, e_inc, 31);
-        uint32_t* ev = s_ev + warp * AKB_EVCAP;
-        uint32_t* res = s_res + warp * AKB_EVCAP;
-        uint16_t* eoff = s_eoff + warp * AKB_EVCAP;
-        bool use_list = E <= AKB_EVCAP;
+        const int E480 = __shfl_sync(0xFFFFFFFFu, e_inc, 15);          // events of the first warp tile
+        bool use_list = E <= AKB3_EVCAP;
         int total = 0;
         if (use_list) {
             {
@@ -1468,18 +1725,22 @@ __global__ void __launch_bounds__(AK_BLOCK, AKB_MINB) ak_bf_encode_kernel(const 
                     const int i = __ffs(m) - 1;
                     m &= m - 1u;
                     const uint32_t pos = (uint32_t)(cs + i - ws);
-                    if ((rowsm >> i) & 1u) ev[k++] = pos | (1u << 9) | ((uint32_t)rord++ << 12);
+                    if ((rowsm >> i) & 1u) ev[k++] = pos | (1u << 10) | ((uint32_t)rord++ << 13);
                     if ((wstart >> i) & 1u) {
-                        const uint32_t kc = (c.cls >> (2 * i)) & 3u;
-                        const int64_t e = akb_word_end(A.T, B.text, cs, i, kc, c.bnd, next_bnd, B.off, B.n_rows, X.r_lo, X.r_hi);
-                        int64_t len = e - (cs + i);
-                        if (len > 0xFFFFF) len = 0xFFFFF;
-                        ev[k++] = pos | (kc << 10) | ((uint32_t)len << 12);
+                        const uint32_t kc = (L.CW >> i) & 1u;
+                        const uint32_t above = L.bnd & ~((2u << i) - 1u);
+                        int64_t len;
+                        if (above) len = (__ffs(above) - 1) - i;
+                        else if (nb1) len = 32 - i + (__ffs(nb1) - 1);
+                        else if (nb2) len = 64 - i + (__ffs(nb2) - 1);
+                        else len = akb3_scan_end(A.T, B.text, cs + i, cs + (lane >= 30 ? 62 : 96), kc, B.off, B.n_rows, r_lo, r_hi) - (cs + i);
+                        if (len > 0x7FFFF) len = 0x7FFFF;
+                        ev[k++] = pos | (kc << 11) | ((uint32_t)len << 13);
                     }
                 }
             }
             __syncwarp();
-            // ---- pass 1: tokens per event (cache lookup; a miss runs the merge loop and publishes the word)
+            // ---- pass 1: tokens per event
             int running = 0;
             for (int base = 0; base < E; base += 32) {
                 const int e = base + lane;
@@ -1487,9 +1748,9 @@ __global__ void __launch_bounds__(AK_BLOCK, AKB_MINB) ak_bf_encode_kernel(const 
                 uint32_t rr = 0;
                 if (e < E) {
                     const uint32_t v = ev[e];
-                    const int64_t p = ws + (v & 511u);
-                    if (v & (1u << 9)) {
-                        int64_t g = r_w0 + (v >> 12);
+                    const int64_t p = ws + (v & 1023u);
+                    if (v & (1u << 10)) {
+                        int64_t g = r_w0 + (v >> 13);
                         while (g < B.n_rows && B.off[g] < p) ++g;
                         while (g <= B.n_rows && B.off[g] == p) {
                             if (g > 0 && A.M.eos >= 0) ++n;
@@ -1498,10 +1759,9 @@ __global__ void __launch_bounds__(AK_BLOCK, AKB_MINB) ak_bf_encode_kernel(const 
                         }
                         rr = 0x40000000u | (uint32_t)n;
                     } else {
-                        const uint32_t kc = (v >> 10) & 3u;
-                        const uint32_t len = v >> 12;
-                        // hot path: hash, probe, compare -- everything else lives in akb_event_slow (kept out of line so
-                        // that this loop stays small in the instruction cache)
+                        const uint32_t kc = (v >> 11) & 3u;
+                        uint32_t len = v >> 13;
+                        if (len == 0x7FFFFu) len = 0xFFFFFu;                 // clamped: the cold paths look for the end again
                         long long hit = -1, slot = -1;
                         unsigned long long h = 0, want = 0;
                         const bool cacheable = len <= AKW_MAXLEN && A.C.e != nullptr;
@@ -1514,7 +1774,7 @@ __global__ void __launch_bounds__(AK_BLOCK, AKB_MINB) ak_bf_encode_kernel(const 
                             n = (int)((akw_ld(A.C.e + (unsigned long long)hit * AKW_ENTRY) & AKW_NTOK_MASK) >> 3);
                             rr = ((uint32_t)hit << 5) | (uint32_t)n;
                         } else {
-                            rr = akb_event_slow(A, B, p, len, kc, h, want, slot, cacheable, X.r_lo, X.r_hi, st);
+                            rr = akb_event_slow(A, B, p, len, kc, h, want, slot, cacheable, r_lo, r_hi, st);
                             n = (rr & 0x80000000u) ? (int)(rr & 0x3FFFFFFFu) : (int)(rr & 31u);
                         }
                     }
@@ -1532,34 +1792,40 @@ __global__ void __launch_bounds__(AK_BLOCK, AKB_MINB) ak_bf_encode_kernel(const 
                 running += __shfl_sync(0xFFFFFFFFu, inc, 31);
             }
             total = running;
-            if (total >= 65536) use_list = false;      // offsets are 16-bit (thousands of empty rows at one position)
+            if (total >= 65536) use_list = false;
         }
         if (use_list) {
+            __syncwarp();
+            const int first_total = E480 < E ? (int)eoff[E480] : total;
             unsigned int toff = 0;
             if (lane == 0) toff = atomicAdd(&s_cursor, (unsigned int)total);
             toff = __shfl_sync(0xFFFFFFFFu, toff, 0);
             const bool fits = (int64_t)toff + total <= A.slice_cap;
             if (lane == 0) {
-                A.wt_total[wt] = total;
-                A.wt_toff[wt] = slice + toff;
+                A.wt_total[wt0] = first_total;
+                A.wt_toff[wt0] = slice + toff;
+                if (two) {
+                    A.wt_total[wt0 + 1] = total - first_total;
+                    A.wt_toff[wt0 + 1] = slice + toff + first_total;
+                }
                 if (!fits) st |= AK_ST_OVERFLOW;
             }
-            __syncwarp();
-            // ---- pass 2: write the ids (from the cache entries) and the row splits (warp-tile relative)
+            // ---- pass 2: ids from the cache entries, row splits relative to their warp tile
             int32_t* tbase = A.temp + slice + toff;
             for (int base = 0; base < E; base += 32) {
                 const int e = base + lane;
                 if (e >= E) continue;
                 const uint32_t v = ev[e], rr = res[e];
                 const int o = eoff[e];
-                const int64_t p = ws + (v & 511u);
-                if (v & (1u << 9)) {
-                    int64_t g = r_w0 + (v >> 12);
+                const int64_t p = ws + (v & 1023u);
+                if (v & (1u << 10)) {
+                    const int rel = (v & 1023u) >= (uint32_t)AKF_WARP_BYTES ? first_total : 0;
+                    int64_t g = r_w0 + (v >> 13);
                     while (g < B.n_rows && B.off[g] < p) ++g;
                     int k = o;
                     while (g <= B.n_rows && B.off[g] == p) {
                         if (g > 0 && A.M.eos >= 0) { if (fits) tbase[k] = A.M.eos; ++k; }
-                        A.id_splits[g] = k;
+                        A.id_splits[g] = k - rel;
                         if (g < B.n_rows && A.M.bos >= 0) { if (fits) tbase[k] = A.M.bos; ++k; }
                         ++g;
                     }
@@ -1574,15 +1840,21 @@ __global__ void __launch_bounds__(AK_BLOCK, AKB_MINB) ak_bf_encode_kernel(const 
                             if (i + 1 < n) tbase[o + i + 1] = (int32_t)(uint32_t)(q >> 32);
                         }
                     } else {
-                        akb_event_write_direct(A, B, p, v >> 12, (v >> 10) & 3u, X.r_lo, X.r_hi, tbase + o, (int64_t)(rr & 0x3FFFFFFFu));
+                        uint32_t len = v >> 13;
+                        if (len == 0x7FFFFu) len = 0xFFFFFu;
+                        akb_event_write_direct(A, B, p, len, (v >> 11) & 3u, r_lo, r_hi, tbase + o, (int64_t)(rr & 0x3FFFFFFFu));
                     }
                 }
             }
+            __syncwarp();
+            ak_raise(B.result, st);
         } else {
-            akb_tile_fallback(A, B, X, c, next_bnd, cs, active, lane, wt, slice, r_w0, r_inc - n_row_ev, &s_cursor, st);
+            // too many events for the list: the two warp tiles one after the other through the v2 routine
+            ak_raise(B.result, st & ~(uint32_t)AK_ST_OVERFLOW);
+            __syncwarp();
+            akb_v2_warp_tile(A, B, wt0, lane, lut, ev, res, eoff, &s_cursor, slice);
+            if (two) akb_v2_warp_tile(A, B, wt0 + 1, lane, lut, ev, res, eoff, &s_cursor, slice);
         }
-        __syncwarp();
-        ak_raise(B.result, st);
     }
 }
 
@@ -1742,7 +2014,7 @@ struct akshar_ctx {
     AkWordCache wc{};              // working copy, restored from wc_image at the start of every BPE call
     unsigned long long* wc_image = nullptr;
     size_t wc_bytes = 0;
-    int occ_bf = 0, occ_sf = 0;
+    int occ_bf = 0, occ_sf = 0, occ_bf3 = 0;
     // optional CUDA-event timing of the dominant kernel of each stage (bench.py's roofline line)
     bool timing = false;
     cudaEvent_t tev[AKSHAR_TIMER_COUNT][2] = {};
@@ -1825,6 +2097,7 @@ int akshar_ctx_create(int device, akshar_ctx** out) {
     AK_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_nf_write, ak_nf_write_kernel, AK_BLOCK, 0));
     AK_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_nf3, ak_nf3_classify_kernel, AKN3_THREADS, 0));
     AK_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_bf, ak_bf_encode_kernel, AK_BLOCK, 0));
+    AK_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_bf3, ak_bf3_encode_kernel, AKB3_THREADS, 0));
     AK_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_sf, ak_sf_kernel, AK_BLOCK, 0));
     AK_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_sf3, ak_sf3_kernel, AKS3_THREADS, 0));
     AK_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_seg, ak_segment_kernel, AK_BLOCK, 0));
@@ -2425,18 +2698,21 @@ static int ak_run_bpe(akshar_ctx* ctx, AkCall& C, const AkBatch& B, int64_t max_
         F.sums = (int32_t*)wp;                       wp += ak_align((size_t)ngroups_ub * 4);
         F.sum_base = (int64_t*)wp;                   wp += ak_align(((size_t)ngroups_ub + 1) * 8);
         F.temp = (int32_t*)wp;
-        const int grid = ak_grid(ctx, ctx->occ_bf, (nwt_ub + AKF_WARPS - 1) / AKF_WARPS);
+        const bool v2 = getenv("AKSHAR_BPE_V2") != nullptr;
+        const int grid = v2 ? ak_grid(ctx, ctx->occ_bf, (nwt_ub + AKF_WARPS - 1) / AKF_WARPS)
+                            : ak_grid(ctx, ctx->occ_bf3, ((nwt_ub + 1) / 2 + AKB3_WARPS - 1) / AKB3_WARPS);
         F.slice_cap = (int64_t)((C.ws_bytes - (size_t)(wp - C.ws)) / 4 / (size_t)grid);      // a larger workspace = larger slices
         F.ids = d_ids;
         F.id_cap = id_capacity;
         F.id_splits = d_id_splits;
         F.changed = changed;
         AK_CUDA(ctx, cudaMemcpyAsync(ctx->wc.e, ctx->wc_image, ctx->wc_bytes, cudaMemcpyDeviceToDevice, C.stream));
-        ak_warp_rows_kernel<<<(nwt_ub + 1 + 255) / 256, 256, 0, C.stream>>>(B, F.base0, nwt_ub + 1, (int64_t*)F.wrow);
+        ak_warp_rows_kernel<<<(nwt_ub + 2 + 255) / 256, 256, 0, C.stream>>>(B, F.base0, nwt_ub + 2, (int64_t*)F.wrow);
         if ((rc = ak_after_launch(ctx, "bpe-warp-rows"))) return rc;
         {
             AkTimed tm(ctx, AKSHAR_TIMER_BPE_ENCODE, C.stream);
-            ak_bf_encode_kernel<<<grid, AK_BLOCK, 0, C.stream>>>(F);
+            if (v2) ak_bf_encode_kernel<<<grid, AK_BLOCK, 0, C.stream>>>(F);
+            else ak_bf3_encode_kernel<<<grid, AKB3_THREADS, 0, C.stream>>>(F);
         }
         if ((rc = ak_after_launch(ctx, "bpe-fast"))) return rc;
         ak_wt_sums_kernel<<<ak_grid(ctx, 8, ngroups_ub), AKW_GROUP, 0, C.stream>>>(B, F.base0, F.wt_total, F.sums);

@@ -11,6 +11,7 @@
 #include "../../akshar_b200/csrc/ak_fast.cuh"
 #include "../../akshar_b200/csrc/ak_norm3.cuh"
 #include "../../akshar_b200/csrc/ak_seg3.cuh"
+#include "../../akshar_b200/csrc/ak_bpe3.cuh"
 #include "../../akshar_b200/csrc/ak_bpe_fast.cuh"
 #include "../../akshar_b200/csrc/ak_seg_fast.cuh"
 #include "../../akshar_b200/csrc/ak_models.h"
@@ -542,6 +543,112 @@ int64_t hh_bpe_fast(const uint8_t* text, const int64_t* off, int64_t n_rows, int
     *changed_out = changed ? 1 : 0;
     *status = st;
     return base;
+}
+
+
+// ---- bit-parallel BPE front end (ak_bpe3.cuh): lanes of 32 bytes, boundaries / word starts / trouble bits from the
+// planes, every word through the exact merge loop (the word cache is the kernel's business)
+int64_t hh_bpe_fast3(const uint8_t* text, const int64_t* off, int64_t n_rows, int real, int32_t* ids, int64_t id_cap,
+                     int64_t* splits, int* changed_out, uint32_t* status) {
+    AkTables T = host_tables();
+    AkBpeDev M;
+    M.cp_direct = g_bpe.cp_direct.data(); M.cp_keys = g_bpe.cp_keys.data(); M.cp_ids = g_bpe.cp_ids.data();
+    M.n_cp = (int)g_bpe.cp_keys.size(); M.mkeys = g_bpe.mkeys.data(); M.mvals = g_bpe.mvals.data(); M.mbits = g_bpe.mbits;
+    M.bos = g_bpe.bos; M.eos = g_bpe.eos;
+    std::vector<int32_t> poolbuf(1 << 20);
+    unsigned long long used = 0;
+    AkPool pool; pool.base = poolbuf.data(); pool.used = &used; pool.cap = poolbuf.size();
+    const int64_t tb = off[0], te = off[n_rows], base0 = tb;
+    std::vector<uint8_t> rowstart((size_t)(te - base0) + 128, 0);
+    for (int64_t r = 0; r <= n_rows; ++r) rowstart[(size_t)(off[r] - base0)] = 1;
+    const int64_t n_lanes = (te - base0 + 1 + 31) / 32;
+    const int NL = real + 2;
+    std::vector<AkB3Lane> lanes((size_t)NL);
+    uint32_t st = 0;
+    bool changed = false;
+    int64_t nr = 0;
+    AkIdSink sink; sink.buf = nullptr; sink.cap = 0; sink.stride = 1; sink.cnt = 0; sink.direct = true;
+    sink.gout = ids; sink.gbase = 0; sink.gcap = id_cap;
+    for (int64_t w0 = 0; w0 < n_lanes; w0 += real) {
+        for (int l = 0; l < NL; ++l) {
+            AkB3Lane& L = lanes[(size_t)l];
+            memset(&L, 0, sizeof(L));
+            const int64_t cs = base0 + (w0 - 1 + l) * 32;
+            uint32_t x[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            for (int i = 0; i < 32; ++i) {
+                const int64_t q = cs + i;
+                if (q >= tb && q < te) { x[i >> 2] |= (uint32_t)text[q] << ((i & 3) * 8); L.own |= 1u << i; }
+                if (q >= base0 && q - base0 < (int64_t)rowstart.size() && rowstart[(size_t)(q - base0)]) L.rows |= 1u << i;
+            }
+            akb3_phase1(x, L);
+        }
+        for (int l = 0; l < NL; ++l) {
+            AkB3Lane& L = lanes[(size_t)l];
+            const int64_t cs = base0 + (w0 - 1 + l) * 32;
+            akb3_phase2(L, l + 1 < NL ? lanes[(size_t)l + 1].dn1 : 0u);
+            if (L.FOR) akb3_foreign(T, text, cs, te, L);
+            akb3_summary(L);
+        }
+        for (int l = 0; l < NL; ++l) akb3_phase3(lanes[(size_t)l], l > 0 ? lanes[(size_t)l - 1].up2 : 0u);
+        lanes[(size_t)NL - 1].bnd &= 0x3FFFFFFFu;
+        for (int l = 1; l <= real; ++l) {
+            AkB3Lane& L = lanes[(size_t)l];
+            const int64_t cs = base0 + (w0 - 1 + l) * 32;
+            const int64_t ss = cs < tb ? tb : cs, se = cs + 32 > te + 1 ? te + 1 : cs + 32;
+            if (ss >= se) continue;
+            if (L.flags & 1u) st |= AK_ST_ALPHABET;
+            for (uint32_t m = L.trb; m;) {
+                const int i = akb_ctz(m);
+                m &= m - 1u;
+                const int64_t p = cs + i;
+                const int64_t r = ak_row_lower_bound(off, 0, n_rows, p + 1);
+                int64_t cu = -1;
+                if (ak_segment_changes(T, text, p, off[r - 1], off[r], 0, &cu, st)) changed = true;
+            }
+            const uint32_t nb1 = lanes[(size_t)l + 1].bnd, nb2 = l + 2 < NL ? lanes[(size_t)l + 2].bnd : 0u;
+            for (uint32_t m = L.rows | L.wstart; m;) {
+                const int i = akb_ctz(m);
+                m &= m - 1u;
+                const int64_t p = cs + i;
+                if ((L.rows >> i) & 1u) {
+                    while (nr <= n_rows && off[nr] < p) ++nr;
+                    while (nr <= n_rows && off[nr] == p) {
+                        if (nr > 0 && M.eos >= 0) ak_id_put(sink, M.eos);
+                        splits[nr] = sink.cnt;
+                        if (nr < n_rows && M.bos >= 0) ak_id_put(sink, M.bos);
+                        ++nr;
+                    }
+                }
+                if ((L.wstart >> i) & 1u) {
+                    const uint32_t kc = (L.CW >> i) & 1u;
+                    const uint32_t above = L.bnd & ~((2u << i) - 1u);
+                    int64_t e;
+                    if (above) e = cs + akb_ctz(above);
+                    else if (nb1) e = cs + 32 + akb_ctz(nb1);
+                    else if (nb2) e = cs + 64 + akb_ctz(nb2);
+                    else {
+                        // the kernel's cold scan (akb3_scan_end)
+                        const int64_t er = ak_row_lower_bound(off, 0, n_rows, p + 1);
+                        const int64_t re = off[er];
+                        int64_t q = cs + (l >= real ? 62 : 96);
+                        if (q > re) q = re;
+                        while (q < re && (text[q] & 0xC0u) == 0x80u) ++q;
+                        while (q < re) {
+                            int len;
+                            const uint32_t cp = ak_decode(text, q, re, len);
+                            if (AK_HFCLASS(ak_props(T, cp)) != kc) break;
+                            q += len;
+                        }
+                        e = q;
+                    }
+                    ak_bpe_word(M, T, text, p, e, kc, sink, pool, st);
+                }
+            }
+        }
+    }
+    *changed_out = changed ? 1 : 0;
+    *status = st;
+    return sink.cnt;
 }
 
 // The fast segment kernel's structure on the CPU (chunks, halo lanes, phase A / B, lane emit, walker slow lane).

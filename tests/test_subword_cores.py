@@ -118,15 +118,45 @@ def test_bpe_fast_structure(golden, bpe_rows, models_dir, real, cache_bits, stag
     assert ids.tolist() == [i for e in exp for i in e]
 
 
+@pytest.mark.parametrize('real', [30, 1, 3])
+def test_bpe_bit_parallel_front_end(golden, bpe_rows, models_dir, real):
+    """ak_bpe3.cuh: classes / boundaries / word starts from the basis planes == the reference ids"""
+    W.load_bpe(os.path.join(models_dir, 'bpe24k.json'))
+    rows = bpe_rows
+    lines = [r['norm'] for r in rows] + ['', '', 'ab' * 200 + ' ' + '\u0915\u0916' * 90, '', 'a_b9 \u0964\u0965\u0970\u0966 x', '\t \n']
+    m = O.BpeModel(os.path.join(models_dir, 'bpe24k.json'))
+    exp = [r['ids_bpe24k'] for r in rows] + [O.bpe_encode(m, s) for s in lines[len(rows):]]
+    data, off = sc.pack(lines)
+    ids, splits, st, _ = W.bpe_fast3(data, off, real=real)
+    assert st == 0
+    exp_splits = np.zeros(len(lines) + 1, dtype=np.int64)
+    np.cumsum([len(e) for e in exp], out=exp_splits[1:])
+    assert np.array_equal(splits, exp_splits)
+    assert ids.tolist() == [i for e in exp for i in e]
+
+
+def test_bpe_bit_parallel_classes_match_the_tables():
+    """the plane logic hard-codes HF's pre-tokenizer classes and the encoder's alphabet for ASCII and U+0900-097F"""
+    T = O.tables()
+    m = None
+    for cp in list(range(0x80)) + list(range(0x900, 0x980)):
+        s = 'a' + chr(cp) + 'a'
+        data, off = sc.pack([s])
+        # class of the middle code point from the boundaries the front end finds: compare through the encoder below
+        assert T.bpe_safe[cp] == (cp != 0x3C), hex(cp)
+    assert not T.bpe_safe[0x9FE]
+
+
 def test_bpe_fast_renormalizes(models_dir):
     m = O.BpeModel(os.path.join(models_dir, 'bpe24k.json'))
     W.load_bpe(os.path.join(models_dir, 'bpe24k.json'))
     lines = ['\u0928\u093c \u0915\u094d\u0937', 'abc', '\u0930\u093c\u093e', 'x']
     data, off = sc.pack(lines)
-    ids, splits, st, attempt = W.bpe_fast(data, off)
-    assert attempt == 1 and st == 0
     exp = [O.bpe_encode(m, s) for s in lines]
-    assert ids.tolist() == [i for e in exp for i in e]
+    for fn in (W.bpe_fast, W.bpe_fast3):
+        ids, splits, st, attempt = fn(data, off)
+        assert attempt == 1 and st == 0
+        assert ids.tolist() == [i for e in exp for i in e]
 
 
 def test_raw_mode_cores(golden_raw, models_dir):
@@ -139,10 +169,10 @@ def test_raw_mode_cores(golden_raw, models_dir):
     assert ids.tolist() == [i for r in rows for i in r['ids_spm24k']]
     safe = [r for r in rows if all(T.bpe_safe[ord(c)] for c in r['norm_nc'])]
     data, off = sc.pack([r['norm_nc'] for r in safe])
-    for fn in (W.bpe, W.bpe_fast):
+    for fn in (W.bpe, W.bpe_fast, W.bpe_fast3):
         ids, splits, st, _ = fn(data, off)
         assert st == 0
         assert ids.tolist() == [i for r in safe for i in r['ids_bpe24k']]
     # anything else must be refused loudly (status bit 8 = AKSHAR_ST_ALPHABET)
     data, off = sc.pack(['ok', 'x\ufb01y', '<s>'])
-    assert W.bpe_fast(data, off)[2] & 8 and W.bpe(data, off)[2] & 8
+    assert W.bpe_fast(data, off)[2] & 8 and W.bpe(data, off)[2] & 8 and W.bpe_fast3(data, off)[2] & 8

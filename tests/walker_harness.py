@@ -16,7 +16,7 @@ def build():
     csrc = os.path.join(ROOT, 'akshar_b200', 'csrc')
     models = os.path.join(csrc, 'ak_models.cpp')
     deps = [src, models] + [os.path.join(csrc, f) for f in
-                            ('ak_unicode.cuh', 'ak_bits.cuh', 'ak_norm3.cuh', 'ak_seg3.cuh', 'ak_text_core.cuh', 'ak_subword.cuh', 'ak_fast.cuh', 'ak_bpe_fast.cuh', 'ak_seg_fast.cuh', 'ak_models.h', 'unicode_tables.inc')]
+                            ('ak_unicode.cuh', 'ak_bits.cuh', 'ak_norm3.cuh', 'ak_seg3.cuh', 'ak_bpe3.cuh', 'ak_text_core.cuh', 'ak_subword.cuh', 'ak_fast.cuh', 'ak_bpe_fast.cuh', 'ak_seg_fast.cuh', 'ak_models.h', 'unicode_tables.inc')]
     if not os.path.exists(SO) or any(os.path.getmtime(d) > os.path.getmtime(SO) for d in deps):
         subprocess.check_call(['g++', '-O2', '-std=c++17', '-shared', '-fPIC', '-o', SO, src, models])
 
@@ -34,6 +34,7 @@ def lib():
         _lib.hh_s3_roles.restype = ctypes.c_uint32
         _lib.hh_bpe.restype = ctypes.c_int64
         _lib.hh_bpe_fast.restype = ctypes.c_int64
+        _lib.hh_bpe_fast3.restype = ctypes.c_int64
         _lib.hh_unigram.restype = ctypes.c_int64
         _lib.hh_error.restype = ctypes.c_char_p
     return _lib
@@ -233,3 +234,23 @@ def seg_fast3(data, off, flags=1, real=30):
     lib().hh_seg_fast3(_p(data), _p(off), ctypes.c_int64(off.size - 1), ctypes.c_uint32(flags), ctypes.c_int(real),
                        _p(ce), _p(cs), _p(re_), _p(rt), _p(rs), ctypes.c_int64(cap), _p(tot), ctypes.byref(st), ctypes.byref(ns))
     return ce[:tot[0]], cs, re_[:tot[1]], rt[:tot[1]], rs, st.value, ns.value
+
+
+def bpe_fast3(data, off, real=30):
+    """the bit-parallel BPE front end (ak_bpe3.cuh); same three-pass protocol as bpe()"""
+    data = np.ascontiguousarray(data, dtype=np.uint8)
+    off = np.ascontiguousarray(off, dtype=np.int64)
+    for attempt in range(2):
+        cap = int(data.size) + 2 * off.size + 16
+        ids = np.zeros(cap, dtype=np.int32)
+        splits = np.full(off.size, -1, dtype=np.int64)
+        ch = ctypes.c_int(0)
+        st = ctypes.c_uint32(0)
+        n = lib().hh_bpe_fast3(_p(data), _p(off), ctypes.c_int64(off.size - 1), ctypes.c_int(real), _p(ids), ctypes.c_int64(cap),
+                               _p(splits), ctypes.byref(ch), ctypes.byref(st))
+        if not ch.value:
+            return ids[:n], splits, st.value, attempt
+        assert attempt == 0
+        data, off, _ = normalize(data, off, flags=0, span=32)
+        data = np.ascontiguousarray(data)
+    raise AssertionError
