@@ -14,7 +14,7 @@ ST_OVERFLOW, ST_NFC_SEGMENT, ST_PATHOLOGICAL, ST_ALPHABET, ST_SPIN, ST_WORD = 1,
 NORM_ROMAN, NORM_FILTER, NORM_COLLAPSE, NORM_CLEAN, NORM_NO_NFC = 1, 2, 4, 6, 8
 SEG_CLUSTERS, SEG_MATRAS, SEG_RUNS = 1, 2, 4
 MODE_TILES, MODE_ROWS = 0, 1
-TIMERS = {'ak_nf_classify_kernel': 0, 'ak_nf_write_kernel': 1, 'ak_bf_encode_kernel': 2, 'ak_sf_kernel': 3, 'ak_unigram_kernel': 4}
+TIMERS = {'ak_nf3_classify_kernel': 0, 'ak_nf_write_kernel': 1, 'ak_bf3_encode_kernel': 2, 'ak_sf3_kernel': 3, 'ak_unigram_kernel': 4}
 
 SYMBOLS = (
     'akshar_version', 'akshar_status_str', 'akshar_ctx_create', 'akshar_ctx_destroy', 'akshar_last_error',

@@ -33,6 +33,18 @@ AK_HD unsigned long long akw_ld(const unsigned long long* p) {
     return *p;
 #endif
 }
+// look-up side: an ordinary (L1-cacheable) load.  Entries only ever go from empty to ready, the tag is published last
+// behind a fence, and nobody reads an entry's other sectors before its tag matched, so a stale L1 sector can only show
+// "still empty" -- a miss that is recomputed exactly -- never a torn entry.  The frequent words stay in L1.
+AK_HD unsigned long long akw_ldc(const unsigned long long* p) {
+#ifdef __CUDA_ARCH__
+    unsigned long long v;
+    asm volatile("ld.global.ca.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+#else
+    return *p;
+#endif
+}
 AK_HD void akw_st(unsigned long long* p, unsigned long long v) {
 #ifdef __CUDA_ARCH__
     asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
@@ -81,25 +93,77 @@ AK_HD unsigned long long akw_want(unsigned long long h, uint32_t len) { return (
 // -> entry index of the word (its ids are then read by the caller), or -1; *free_slot = an empty slot seen on the probe
 // path (or -1)
 AK_HD long long akw_find(const AkWordCache& C, unsigned long long h, unsigned long long want, const uint8_t* t, int64_t s,
-                         uint32_t len, long long* free_slot) {
+                         uint32_t len, long long* free_slot, unsigned long long* tag_out = nullptr) {
     const unsigned long long mask = (1ull << C.bits) - 1ull;
     const uint32_t nw = (len + 7u) >> 3;
     *free_slot = -1;
     const unsigned long long k0 = akw_key_word(t, s, len, 0);
+    const unsigned long long k1 = nw > 1u ? akw_key_word(t, s, len, 1) : 0ull;
 #pragma unroll 1
     for (int p = 0; p < AKW_PROBES; ++p) {
         const unsigned long long slot = (h + (unsigned long long)p) & mask;
         const unsigned long long* e = C.e + slot * AKW_ENTRY;
-        // tag and first key word are fetched together: one L2 round trip decides most probes
-        const unsigned long long tag = akw_ld(e);
-        const unsigned long long e0 = akw_ld(e + 1);
+        // tag and the first two key words are fetched together (one sector): one round trip decides words up to 16 bytes
+        const unsigned long long tag = akw_ldc(e);
+        const unsigned long long e0 = akw_ldc(e + 1);
+        const unsigned long long e1 = akw_ldc(e + 2);
         if (tag == 0ull) { *free_slot = (long long)slot; return -1; }
-        if ((tag & ~AKW_NTOK_MASK) != want || e0 != k0) continue;
+        if ((tag & ~AKW_NTOK_MASK) != want || e0 != k0 || (nw > 1u && e1 != k1)) continue;
         bool same = true;
 #pragma unroll 1
-        for (uint32_t j = 1; j < nw; ++j)
-            if (akw_ld(e + 1 + j) != akw_key_word(t, s, len, j)) { same = false; break; }
-        if (same) return (long long)slot;
+        for (uint32_t j = 2; j < nw; ++j)
+            if (akw_ldc(e + 1 + j) != akw_key_word(t, s, len, j)) { same = false; break; }
+        if (same) {
+            if (tag_out) *tag_out = tag;
+            return (long long)slot;
+        }
+    }
+    return -1;
+}
+
+// hash + probe with the first two key words computed once (they decide every word up to 16 bytes)
+AK_HD long long akw_lookup(const AkWordCache& C, const uint8_t* t, int64_t s, uint32_t len, unsigned long long* h_out,
+                           unsigned long long* want_out, long long* free_slot, unsigned long long* tag_out) {
+    const uint32_t nw = (len + 7u) >> 3;
+    const unsigned long long k0 = akw_key_word(t, s, len, 0);
+    const unsigned long long k1 = nw > 1u ? akw_key_word(t, s, len, 1) : 0ull;
+    unsigned long long h = 0x9E3779B97F4A7C15ull + len;
+    h = (h ^ k0) * 0xBF58476D1CE4E5B9ull;
+    h = (h << 27) | (h >> 37);
+    if (nw > 1u) {
+        h = (h ^ k1) * 0xBF58476D1CE4E5B9ull;
+        h = (h << 27) | (h >> 37);
+#pragma unroll 1
+        for (uint32_t j = 2; j < nw; ++j) {
+            h = (h ^ akw_key_word(t, s, len, j)) * 0xBF58476D1CE4E5B9ull;
+            h = (h << 27) | (h >> 37);
+        }
+    }
+    h ^= h >> 31;
+    h *= 0xFF51AFD7ED558CCDull;
+    h ^= h >> 33;
+    const unsigned long long want = akw_want(h, len);
+    *h_out = h;
+    *want_out = want;
+    *free_slot = -1;
+    const unsigned long long mask = (1ull << C.bits) - 1ull;
+#pragma unroll 1
+    for (int p = 0; p < AKW_PROBES; ++p) {
+        const unsigned long long slot = (h + (unsigned long long)p) & mask;
+        const unsigned long long* e = C.e + slot * AKW_ENTRY;
+        const unsigned long long tag = akw_ldc(e);
+        const unsigned long long e0 = akw_ldc(e + 1);
+        const unsigned long long e1 = akw_ldc(e + 2);
+        if (tag == 0ull) { *free_slot = (long long)slot; return -1; }
+        if ((tag & ~AKW_NTOK_MASK) != want || e0 != k0 || (nw > 1u && e1 != k1)) continue;
+        bool same = true;
+#pragma unroll 1
+        for (uint32_t j = 2; j < nw; ++j)
+            if (akw_ldc(e + 1 + j) != akw_key_word(t, s, len, j)) { same = false; break; }
+        if (same) {
+            *tag_out = tag;
+            return (long long)slot;
+        }
     }
     return -1;
 }

@@ -292,13 +292,15 @@ __global__ void __launch_bounds__(AKW_GROUP) ak_wt_sums_kernel(AkBatch B, int64_
 // work list, and two small kernels run the exact walker over that list with one thread per entry.  A 16-byte walk
 // costs tens of microseconds of dependent instructions; inside the tile kernels it would stall its whole CTA (and,
 // through an ordered tile prefix, every later tile), on the list thousands of them overlap.
-#define AK_SLOW_BYTES 40
+#define AK_SLOW_BYTES 72
 struct AkSlowEntry {
-    int64_t pos;         // chunk start (absolute byte index)
-    int64_t out_base;    // filled by the write kernel: where this chunk's output starts
+    int64_t pos;         // span start (absolute byte index)
+    int64_t out_base;    // filled by the write kernel: where this span's output starts
     int32_t cnt;         // filled by the slow kernel's first pass
     int32_t tile;
-    uint8_t bytes[AK_SLOW_BYTES];      // the chunk's output when it fits (else the second pass walks again)
+    int32_t span;        // 16, or 32: both chunks of a bit-parallel lane in one walk (the second chunk's info word is
+    int32_t pad_;        // 0xC0000000 | index: "continued", no bytes of its own)
+    uint8_t bytes[AK_SLOW_BYTES];      // the span's output when it fits (else the second pass walks again)
 };
 
 struct AkNfWork {
@@ -394,6 +396,8 @@ __global__ void __launch_bounds__(AK_BLOCK, AKN_MINB) ak_nf_classify_kernel(cons
                     e.out_base = 0;
                     e.cnt = 0;
                     e.tile = tile;
+                    e.span = 16;
+                    e.pad_ = 0;
                     W.slow[idx] = e;
                 } else {
                     ak_raise(B.result, AK_ST_PATHOLOGICAL);     // too many slow chunks: the host re-runs row by row
@@ -528,33 +532,40 @@ __global__ void __launch_bounds__(AKN3_THREADS, AKN3_MINB) ak_nf3_classify_kerne
         const bool fast = akn3_phase4(L, up3p, dn1n, dn3n, info[0], info[1]);
         int cnt = 0;
         if (lane >= 1 && lane <= 30) {
+            bool act[2];
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 const int64_t hs = cs + 16 * h;
                 const int64_t ss = hs < tb ? tb : hs;
                 const int64_t se = hs + 16 > te + 1 ? te + 1 : hs + 16;
-                const int k = (int)((hs - tile_start) >> 4);                 // 16-byte chunk of the tile, 0 .. 239
-                uint32_t v = 0;
-                if (ss < se) {
-                    if (fast) {
-                        v = info[h];
-                        cnt += __popc(v);
-                    } else {
-                        const unsigned int idx = atomicAdd(W.n_slow, 1u);
-                        if (idx < W.slow_cap) {
-                            AkSlowEntry e;
-                            e.pos = hs;
-                            e.out_base = 0;
-                            e.cnt = 0;
-                            e.tile = tile;
-                            W.slow[idx] = e;
-                        } else {
-                            ak_raise(B.result, AK_ST_PATHOLOGICAL);
-                        }
-                        v = 0x80000000u | idx;
-                    }
+                act[h] = ss < se;
+            }
+            uint32_t v[2] = {0u, 0u};
+            if (fast) {
+                if (act[0]) { v[0] = info[0]; cnt += __popc(v[0]); }
+                if (act[1]) { v[1] = info[1]; cnt += __popc(v[1]); }
+            } else if (act[0] || act[1]) {
+                // one work-list entry for the lane: both chunks in one walk
+                const unsigned int idx = atomicAdd(W.n_slow, 1u);
+                if (idx < W.slow_cap) {
+                    AkSlowEntry e;
+                    e.pos = act[0] ? cs : cs + 16;
+                    e.out_base = 0;
+                    e.cnt = 0;
+                    e.tile = tile;
+                    e.span = (act[0] && act[1]) ? 32 : 16;
+                    e.pad_ = 0;
+                    W.slow[idx] = e;
+                } else {
+                    ak_raise(B.result, AK_ST_PATHOLOGICAL);
                 }
-                W.info[(size_t)tile * AK_BLOCK + (k / AKF_REAL) * 32 + 1 + (k % AKF_REAL)] = v;
+                if (act[0]) { v[0] = 0x80000000u | idx; if (act[1]) v[1] = 0xC0000000u | idx; }
+                else v[1] = 0x80000000u | idx;
+            }
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int k = (int)((cs + 16 * h - tile_start) >> 4);                 // 16-byte chunk of the tile, 0 .. 239
+                W.info[(size_t)tile * AK_BLOCK + (k / AKF_REAL) * 32 + 1 + (k % AKF_REAL)] = v[h];
             }
         }
         if (tid < 2 * AKF_WARPS) W.info[(size_t)tile * AK_BLOCK + (tid >> 1) * 32 + (tid & 1) * 31] = 0;   // the v2 halo slots
@@ -592,7 +603,7 @@ __global__ void __launch_bounds__(128) ak_nf_slow_kernel(const AkNfSlowArgs A) {
     for (unsigned int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
         AkSlowEntry e = A.W.slow[j];
         const int64_t ss = e.pos < B.text_begin ? B.text_begin : e.pos;
-        const int64_t se = e.pos + 16 > B.text_end + 1 ? B.text_end + 1 : e.pos + 16;
+        const int64_t se = e.pos + e.span > B.text_end + 1 ? B.text_end + 1 : e.pos + e.span;
         const int64_t r0 = A.tile_row[(size_t)e.tile * AKF_WARPS], r1 = A.tile_row[(size_t)(e.tile + 1) * AKF_WARPS];
         const int64_t rlo = r0 > 0 ? r0 - 1 : 0, rhi = r1 > B.n_rows ? B.n_rows : r1;
         uint32_t st = 0;
@@ -677,9 +688,10 @@ __global__ void __launch_bounds__(AK_BLOCK) ak_nf_write_kernel(const AkFastNormA
         akf_load_lane(B, cs, c);
         const uint32_t info = W.info[(size_t)tile * AK_BLOCK + tid];
         const bool slow = (info & 0x80000000u) != 0;
-        const unsigned int sidx = info & 0x7FFFFFFFu;
+        const bool cont = slow && (info & 0x40000000u);          // second chunk of a 32-byte slow span: nothing of its own
+        const unsigned int sidx = info & 0x3FFFFFFFu;
         int cnt = 0;
-        if (slow) { if (sidx < W.slow_cap) cnt = W.slow[sidx].cnt; }
+        if (slow) { if (sidx < W.slow_cap && !cont) cnt = W.slow[sidx].cnt; }
         else cnt = __popc(info);
         int total;
         const int pre = ak_block_exscan<AK_BLOCK>(cnt, ws, total);
@@ -691,7 +703,7 @@ __global__ void __launch_bounds__(AK_BLOCK) ak_nf_write_kernel(const AkFastNormA
         s_emit[tid] = info;
         s_pre[tid] = (uint32_t)pre;
         if (slow) {
-            if (sidx < W.slow_cap) {
+            if (sidx < W.slow_cap && !cont) {
                 W.slow[sidx].out_base = base + pre;
                 if (cnt <= AK_SLOW_BYTES && fits) {
                     uint8_t* dst = staged ? stage + pad + pre : A.out + base + pre;
@@ -723,7 +735,12 @@ __global__ void __launch_bounds__(AK_BLOCK) ak_nf_write_kernel(const AkFastNormA
             const int th = wq * 32 + 1 + (within >> 4), i = within & 15;
             const uint32_t e = s_emit[th];
             if (!(e & 0x80000000u)) A.out_off[r] = base + s_pre[th] + __popc(e & ((1u << i) - 1u));
-            else A.out_off[r] += base + s_pre[th];       // the slow pass left it relative to the chunk's output
+            else {
+                // the slow pass left it relative to the span's output; a continued chunk's prefix already includes the span
+                int64_t adj = 0;
+                if ((e & 0x40000000u) && (e & 0x3FFFFFFFu) < W.slow_cap) adj = W.slow[e & 0x3FFFFFFFu].cnt;
+                A.out_off[r] += base + s_pre[th] - adj;
+            }
         }
         __syncthreads();
     }
@@ -1181,16 +1198,15 @@ __global__ void __launch_bounds__(AKS3_THREADS, AKS3_MINB) ak_sf3_kernel(const A
                 int64_t a, b;
                 ak_seg_span(A.T, B.text, B.off, B.n_rows, rlo, rhi, ss, se, A.flags, AK_LOOKBACK_LIMIT, true, o, a, b, st2);
             } else {
-                int64_t row_last = nr;
-                if (want_c) {
-                    aks3_emit(L, L.brk, rows_ev, cs, B.off, B.n_rows, nr, fits ? cdst + cpre : nullptr, nullptr, A.o.cluster_splits, row_last);
-                    for (int64_t r = nr; r < row_last; ++r) A.o.cluster_splits[r] += cpre_t;
+                const uint32_t mc = want_c ? (L.brk | rows_ev) : 0u, mr = want_r ? (L.rchg | rows_ev) : 0u;
+                if (fits) {
+                    const int64_t rs_in = nr > 0 ? B.off[nr - 1] : B.off[0];
+                    if (want_c) aks3_emit(L, mc, cs, rs_in, cdst + cpre, nullptr);
+                    if (want_r) aks3_emit(L, mr, cs, rs_in, rdst + rpre, tdst + rpre);
                 }
-                if (want_r) {
-                    aks3_emit(L, L.rchg, rows_ev, cs, B.off, B.n_rows, nr, fits ? rdst + rpre : nullptr, fits ? tdst + rpre : nullptr,
-                              A.o.run_splits, row_last);
-                    for (int64_t r = nr; r < row_last; ++r) A.o.run_splits[r] += rpre_t;
-                }
+                if (L.rows)
+                    aks3_splits(L, mc, mr, cs, B.off, B.n_rows, nr, cpre_t, rpre_t, want_c ? A.o.cluster_splits : nullptr,
+                                want_r ? A.o.run_splits : nullptr);
             }
         }
         ak_raise(B.result, st);
@@ -1765,13 +1781,10 @@ __global__ void __launch_bounds__(AKB3_THREADS, AKB3_MINB) ak_bf3_encode_kernel(
                         long long hit = -1, slot = -1;
                         unsigned long long h = 0, want = 0;
                         const bool cacheable = len <= AKW_MAXLEN && A.C.e != nullptr;
-                        if (cacheable) {
-                            h = akw_hash(B.text, p, len);
-                            want = akw_want(h, len);
-                            hit = akw_find(A.C, h, want, B.text, p, len, &slot);
-                        }
+                        unsigned long long tag = 0;
+                        if (cacheable) hit = akw_lookup(A.C, B.text, p, len, &h, &want, &slot, &tag);
                         if (hit >= 0) {
-                            n = (int)((akw_ld(A.C.e + (unsigned long long)hit * AKW_ENTRY) & AKW_NTOK_MASK) >> 3);
+                            n = (int)((tag & AKW_NTOK_MASK) >> 3);
                             rr = ((uint32_t)hit << 5) | (uint32_t)n;
                         } else {
                             rr = akb_event_slow(A, B, p, len, kc, h, want, slot, cacheable, r_lo, r_hi, st);
@@ -1835,7 +1848,7 @@ __global__ void __launch_bounds__(AKB3_THREADS, AKB3_MINB) ak_bf3_encode_kernel(
                         const unsigned long long* en = A.C.e + (unsigned long long)((rr >> 5) & 0x3FFFFu) * AKW_ENTRY;
 #pragma unroll 1
                         for (int i = 0; i < n; i += 2) {
-                            const unsigned long long q = akw_ld(en + 8 + (i >> 1));
+                            const unsigned long long q = akw_ldc(en + 8 + (i >> 1));
                             tbase[o + i] = (int32_t)(uint32_t)q;
                             if (i + 1 < n) tbase[o + i + 1] = (int32_t)(uint32_t)(q >> 32);
                         }

@@ -225,33 +225,40 @@ AK_HD uint32_t aks3_tag_at(const AkS3Lane& L, int i) {
     return (L.PD & b) ? (uint32_t)TAG_DEVANAGARI : (L.PR & b) ? (uint32_t)TAG_ROMAN : (L.PO & b) ? (uint32_t)TAG_OTHER : (uint32_t)TAG_NONE;
 }
 
-// Emission of one stream (cluster ends, or run ends + tags when `tags` is set) for a fast lane.  ev = the stream's
-// in-row events (brk / rchg), rows_ev = row starts that close a non-empty row.  nr = index of the first row that
-// starts at or after the lane's first position.  dst may be null (count / splits only).  Returns the count.
-AK_HD int aks3_emit(const AkS3Lane& L, uint32_t ev, uint32_t rows_ev, int64_t cs, const int64_t* off, int64_t n_rows, int64_t nr,
-                    int32_t* dst, uint8_t* tags, int64_t* splits, int64_t& row_last) {
+// Emission of one stream for a fast lane: every event (an in-row boundary, or a row start that closes a non-empty row)
+// becomes its offset from the start of the row it ends in -- the highest row start strictly below it in the lane, else
+// rs_in, the start of the row that was open when the lane began.  No row bookkeeping in the loop; the row splits are
+// written separately (aks3_splits) from popcounts of the same masks.
+AK_HD int aks3_emit(const AkS3Lane& L, uint32_t m, int64_t cs, int64_t rs_in, int32_t* dst, uint8_t* tags) {
     int k = 0;
-    int64_t rs = nr > 0 ? off[nr - 1] : off[0];
-    uint32_t m = ev | L.rows;
+    const uint32_t rows = L.rows;
     while (m) {
         const int i = akb_ctz(m);
         m &= m - 1u;
+        const uint32_t below = rows & ((1u << i) - 1u);
+        const int64_t rs = below ? cs + (31 - akb_clz(below)) : rs_in;
+        dst[k] = (int32_t)(cs + i - rs);
+        if (tags) tags[k] = (uint8_t)aks3_tag_at(L, i);
+        ++k;
+    }
+    return k;
+}
+
+// splits of the rows that start in the lane: events of each stream at or before the row's position (+ the lane's base).
+// nr = index of the first row that starts at or after the lane's first position; returns the next row index.
+AK_HD int64_t aks3_splits(const AkS3Lane& L, uint32_t mc, uint32_t mr, int64_t cs, const int64_t* off, int64_t n_rows, int64_t nr,
+                          int64_t cbase, int64_t rbase, int64_t* csplits, int64_t* rsplits) {
+    for (uint32_t m = L.rows; m;) {
+        const int i = akb_ctz(m);
+        m &= m - 1u;
         const int64_t p = cs + i;
-        if ((L.rows >> i) & 1u) {
-            if ((rows_ev >> i) & 1u) {
-                if (dst) { dst[k] = (int32_t)(p - rs); if (tags) tags[k] = (uint8_t)aks3_tag_at(L, i); }
-                ++k;
-            }
-            while (nr <= n_rows && off[nr] == p) {
-                if (splits) splits[nr] = k;
-                ++nr;
-            }
-            rs = p;
-        } else {
-            if (dst) { dst[k] = (int32_t)(p - rs); if (tags) tags[k] = (uint8_t)aks3_tag_at(L, i); }
-            ++k;
+        const uint32_t upto = (2u << i) - 1u;
+        const int64_t kc = cbase + akb_popc(mc & upto), kr = rbase + akb_popc(mr & upto);
+        while (nr <= n_rows && off[nr] == p) {
+            if (csplits) csplits[nr] = kc;
+            if (rsplits) rsplits[nr] = kr;
+            ++nr;
         }
     }
-    row_last = nr;
-    return k;
+    return nr;
 }

@@ -32,10 +32,10 @@ MODELS = os.path.join(ROOT, 'tests', 'golden', 'models')
 # DRAM traffic per INPUT byte of each hot kernel: (dram__bytes_read.sum + dram__bytes_write.sum) / input bytes from the
 # `ncu --set full` captures at 256 MiB summarised in profiles/r01_ncu_full_summary.csv; scaled to the run's size below
 TRAFFIC_PER_INPUT_BYTE = {
-    'ak_nf_classify_kernel': (286.12 + 60.63) / 268.44,
-    'ak_nf_write_kernel': (362.62 + 249.38) / 268.44,
-    'ak_bf_encode_kernel': (977.09 + 891.86) / 268.44,      # local-memory (stack) spill traffic included
-    'ak_sf_kernel': (335.89 + 663.33) / 268.44,
+    'ak_nf3_classify_kernel': (293.63 + 64.25) / 268.44,
+    'ak_nf_write_kernel': (375.82 + 253.00) / 268.44,
+    'ak_bf3_encode_kernel': (429.62 + 342.56) / 268.44,
+    'ak_sf3_kernel': (304.72 + 497.09) / 268.44,
 }
 CHUNK = 32 << 20
 SEED = 20261018
@@ -339,8 +339,8 @@ def main():
     # ---- dominant kernel: the library brackets its hot kernels with CUDA events on the launching stream
     # (akshar_timing_enable); average over a few full steps of the same workload
     eng.timing(True)
-    names = ['ak_nf_classify_kernel', 'ak_nf_write_kernel'] + (['ak_bf_encode_kernel'] if mkind == 0 else
-                                                                 ['ak_unigram_kernel'] if mkind == 1 else ['ak_sf_kernel'])
+    names = ['ak_nf3_classify_kernel', 'ak_nf_write_kernel'] + (['ak_bf3_encode_kernel'] if mkind == 0 else
+                                                                 ['ak_unigram_kernel'] if mkind == 1 else ['ak_sf3_kernel'])
     acc = {k: [] for k in names}
     for _ in range(3):
         device_step()
@@ -355,11 +355,11 @@ def main():
     n_r = int(res[1]) if mkind is None else 0
     # algorithmic bytes per launch: logical input read once + required output written once
     alg = {
-        'ak_nf_classify_kernel': nbytes + 4 * (nbytes // 15),                 # text in, one 4-byte emit mask per 16-byte chunk out
+        'ak_nf3_classify_kernel': nbytes + 4 * (nbytes // 15),                 # text in, one 4-byte emit mask per 16-byte chunk out
         'ak_nf_write_kernel': nbytes + 4 * (nbytes // 15) + n_norm + 8 * (n_rows + 1),
-        'ak_bf_encode_kernel': n_norm + 4 * n_tokens + 8 * (n_rows + 1),
+        'ak_bf3_encode_kernel': n_norm + 4 * n_tokens + 8 * (n_rows + 1),
         'ak_unigram_kernel': n_norm + 4 * n_tokens + 8 * (n_rows + 1),
-        'ak_sf_kernel': n_norm + 4 * n_c + 5 * n_r + 16 * (n_rows + 1),
+        'ak_sf3_kernel': n_norm + 4 * n_c + 5 * n_r + 16 * (n_rows + 1),
     }
     stages = {k: (kms[k], alg[k]) for k in kms}
     dom = max(stages, key=lambda k: stages[k][0])
@@ -395,7 +395,7 @@ def main():
         'roofline': {'bound': 'hbm', 'kernel': dom, 'achieved': ach, 'peak': peak, 'peak_source': peak_kind, 'unit': 'GB/s',
                      'frac': ach / peak,
                      'traffic': (int(TRAFFIC_PER_INPUT_BYTE[dom] * nbytes) if dom in TRAFFIC_PER_INPUT_BYTE else None),
-                     'traffic_source': 'ncu --set full at 256 MiB, scaled by input bytes (profiles/r01_ncu_full_summary.csv)',
+                     'traffic_source': 'ncu --set full at 256 MiB, scaled by input bytes (profiles/r01_v3_ncu_full_summary.csv)',
                      'ms': stages[dom][0], 'algorithmic_bytes': stages[dom][1],
                      'kernels_ms': {k: v[0] for k, v in stages.items()},
                      'kernels_frac': {k: v[1] / (v[0] * 1e-3) / 1e9 / peak for k, v in stages.items()}},

@@ -134,10 +134,10 @@ int akshar_tokenizer_encode_batch(akshar_ctx* ctx, const uint8_t* d_text, const 
  * library brackets that one launch with CUDA events on the caller's stream; akshar_timing_read waits for the
  * kernel and returns its duration of the most recent call. */
 enum {
-    AKSHAR_TIMER_NORMALIZE_CLASSIFY = 0,   /* ak_nf_classify_kernel */
+    AKSHAR_TIMER_NORMALIZE_CLASSIFY = 0,   /* ak_nf3_classify_kernel */
     AKSHAR_TIMER_NORMALIZE_WRITE = 1,      /* ak_nf_write_kernel */
-    AKSHAR_TIMER_BPE_ENCODE = 2,           /* ak_bf_encode_kernel */
-    AKSHAR_TIMER_SEGMENT = 3,              /* ak_sf_kernel */
+    AKSHAR_TIMER_BPE_ENCODE = 2,           /* ak_bf3_encode_kernel */
+    AKSHAR_TIMER_SEGMENT = 3,              /* ak_sf3_kernel */
     AKSHAR_TIMER_UNIGRAM = 4,              /* ak_unigram_kernel */
     AKSHAR_TIMER_COUNT = 5
 };

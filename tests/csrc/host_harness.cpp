@@ -369,20 +369,13 @@ void hh_seg_fast3(const uint8_t* text, const int64_t* off, int64_t n_rows, uint3
                 while (nr <= n_rows && off[nr] < se) ++nr;
             } else {
                 const uint32_t rows_ev = L.rows & ~tb_bit;
-                int64_t rl = nr, rl2 = nr;
-                if (want_c) {
-                    const int k = aks3_emit(L, L.brk, rows_ev, cs, off, n_rows, nr, cluster_ends + cbase, nullptr, cluster_splits, rl);
-                    if (k != akb_popc(L.brk) + akb_popc(rows_ev)) st |= 0x40000000u;
-                    for (int64_t r = nr; r < rl; ++r) cluster_splits[r] += cbase;
-                    cbase += k;
-                }
-                if (want_r) {
-                    const int k = aks3_emit(L, L.rchg, rows_ev, cs, off, n_rows, nr, run_ends + rbase, run_tags + rbase, run_splits, rl2);
-                    if (k != akb_popc(L.rchg) + akb_popc(rows_ev)) st |= 0x40000000u;
-                    for (int64_t r = nr; r < rl2; ++r) run_splits[r] += rbase;
-                    rbase += k;
-                }
-                nr = want_c ? rl : rl2;
+                const uint32_t mc = want_c ? (L.brk | rows_ev) : 0u, mr = want_r ? (L.rchg | rows_ev) : 0u;
+                const int64_t rs_in = nr > 0 ? off[nr - 1] : off[0];
+                if (want_c) aks3_emit(L, mc, cs, rs_in, cluster_ends + cbase, nullptr);
+                if (want_r) aks3_emit(L, mr, cs, rs_in, run_ends + rbase, run_tags + rbase);
+                nr = aks3_splits(L, mc, mr, cs, off, n_rows, nr, cbase, rbase, want_c ? cluster_splits : nullptr, want_r ? run_splits : nullptr);
+                cbase += akb_popc(mc);
+                rbase += akb_popc(mr);
             }
         }
     }
