@@ -15,7 +15,7 @@
 #define AKW_KW 7
 #define AKW_MAXTOK 16          // ids per entry
 #define AKW_ENTRY 16           // u64 per entry: tag, 7 key words, 8 x (2 ids)  = 128 bytes
-#define AKW_PROBES 4
+#define AKW_PROBES 16         // linear probing; a look-up stops at the first empty slot, so long chains only cost the words that need them
 #define AKW_READY 1ull
 #define AKW_BUSY 2ull
 
