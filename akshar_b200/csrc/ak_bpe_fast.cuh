@@ -121,12 +121,40 @@ AK_HD long long akw_find(const AkWordCache& C, unsigned long long h, unsigned lo
     return -1;
 }
 
+// the first two key words of the word [s, s + len) without a branch: five aligned 32-bit loads (clamped to the last
+// word of the text, whose bytes are masked off anyway) and four funnel shifts
+AK_HD void akw_key01(const uint8_t* t, int64_t s, uint32_t len, int64_t te, unsigned long long& k0, unsigned long long& k1) {
+#ifdef __CUDA_ARCH__
+    const uintptr_t a = (uintptr_t)(t + s);
+    const uint32_t* w = (const uint32_t*)(a & ~(uintptr_t)3);
+    const uint32_t* last = (const uint32_t*)(((uintptr_t)(t + te) - 1u) & ~(uintptr_t)3);
+    const uint32_t sh = (uint32_t)(a & 3u) * 8u;
+    const uint32_t w0 = __ldg(w);
+    const uint32_t w1 = __ldg(w + 1 <= last ? w + 1 : last);
+    const uint32_t w2 = __ldg(w + 2 <= last ? w + 2 : last);
+    const uint32_t w3 = __ldg(w + 3 <= last ? w + 3 : last);
+    const uint32_t w4 = __ldg(w + 4 <= last ? w + 4 : last);
+    const uint32_t f0 = __funnelshift_r(w0, w1, sh), f1 = __funnelshift_r(w1, w2, sh);
+    const uint32_t f2 = __funnelshift_r(w2, w3, sh), f3 = __funnelshift_r(w3, w4, sh);
+    k0 = ((unsigned long long)f1 << 32) | f0;
+    k1 = ((unsigned long long)f3 << 32) | f2;
+    const unsigned long long m0 = len >= 8u ? ~0ull : ((1ull << (8u * len)) - 1ull);
+    const unsigned long long m1 = len >= 16u ? ~0ull : (len > 8u ? ((1ull << (8u * (len - 8u))) - 1ull) : 0ull);
+    k0 &= m0;
+    k1 &= m1;
+#else
+    (void)te;
+    k0 = akw_key_word(t, s, len, 0);
+    k1 = len > 8u ? akw_key_word(t, s, len, 1) : 0ull;
+#endif
+}
+
 // hash + probe with the first two key words computed once (they decide every word up to 16 bytes)
-AK_HD long long akw_lookup(const AkWordCache& C, const uint8_t* t, int64_t s, uint32_t len, unsigned long long* h_out,
+AK_HD long long akw_lookup(const AkWordCache& C, const uint8_t* t, int64_t s, uint32_t len, int64_t te, unsigned long long* h_out,
                            unsigned long long* want_out, long long* free_slot, unsigned long long* tag_out) {
     const uint32_t nw = (len + 7u) >> 3;
-    const unsigned long long k0 = akw_key_word(t, s, len, 0);
-    const unsigned long long k1 = nw > 1u ? akw_key_word(t, s, len, 1) : 0ull;
+    unsigned long long k0, k1;
+    akw_key01(t, s, len, te, k0, k1);
     unsigned long long h = 0x9E3779B97F4A7C15ull + len;
     h = (h ^ k0) * 0xBF58476D1CE4E5B9ull;
     h = (h << 27) | (h >> 37);

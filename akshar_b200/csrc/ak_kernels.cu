@@ -1741,7 +1741,22 @@ __global__ void __launch_bounds__(AKB3_THREADS, AKB3_MINB) ak_bf3_encode_kernel(
                     const int i = __ffs(m) - 1;
                     m &= m - 1u;
                     const uint32_t pos = (uint32_t)(cs + i - ws);
-                    if ((rowsm >> i) & 1u) ev[k++] = pos | (1u << 10) | ((uint32_t)rord++ << 13);
+                    if ((rowsm >> i) & 1u) {
+                        // the rows that start here (several when rows are empty): their </s> <s> count, and the index
+                        // of the first one, are settled now so that the two passes below never search the offsets
+                        int64_t g = r_w0 + rord++;
+                        const int64_t p = cs + i;
+                        while (g < B.n_rows && B.off[g] < p) ++g;
+                        const int64_t g0 = g;
+                        int n = 0;
+                        while (g <= B.n_rows && B.off[g] == p) {
+                            if (g > 0 && A.M.eos >= 0) ++n;
+                            if (g < B.n_rows && A.M.bos >= 0) ++n;
+                            ++g;
+                        }
+                        res[k] = 0x40000000u | (uint32_t)n;
+                        ev[k++] = pos | (1u << 10) | ((uint32_t)(g0 - r_w0) << 13);
+                    }
                     if ((wstart >> i) & 1u) {
                         const uint32_t kc = (L.CW >> i) & 1u;
                         const uint32_t above = L.bnd & ~((2u << i) - 1u);
@@ -1766,14 +1781,8 @@ __global__ void __launch_bounds__(AKB3_THREADS, AKB3_MINB) ak_bf3_encode_kernel(
                     const uint32_t v = ev[e];
                     const int64_t p = ws + (v & 1023u);
                     if (v & (1u << 10)) {
-                        int64_t g = r_w0 + (v >> 13);
-                        while (g < B.n_rows && B.off[g] < p) ++g;
-                        while (g <= B.n_rows && B.off[g] == p) {
-                            if (g > 0 && A.M.eos >= 0) ++n;
-                            if (g < B.n_rows && A.M.bos >= 0) ++n;
-                            ++g;
-                        }
-                        rr = 0x40000000u | (uint32_t)n;
+                        rr = res[e];
+                        n = (int)(rr & 0x3FFFFFFFu);
                     } else {
                         const uint32_t kc = (v >> 11) & 3u;
                         uint32_t len = v >> 13;
@@ -1782,7 +1791,7 @@ __global__ void __launch_bounds__(AKB3_THREADS, AKB3_MINB) ak_bf3_encode_kernel(
                         unsigned long long h = 0, want = 0;
                         const bool cacheable = len <= AKW_MAXLEN && A.C.e != nullptr;
                         unsigned long long tag = 0;
-                        if (cacheable) hit = akw_lookup(A.C, B.text, p, len, &h, &want, &slot, &tag);
+                        if (cacheable) hit = akw_lookup(A.C, B.text, p, len, B.text_end, &h, &want, &slot, &tag);
                         if (hit >= 0) {
                             n = (int)((tag & AKW_NTOK_MASK) >> 3);
                             rr = ((uint32_t)hit << 5) | (uint32_t)n;
@@ -1834,7 +1843,6 @@ __global__ void __launch_bounds__(AKB3_THREADS, AKB3_MINB) ak_bf3_encode_kernel(
                 if (v & (1u << 10)) {
                     const int rel = (v & 1023u) >= (uint32_t)AKF_WARP_BYTES ? first_total : 0;
                     int64_t g = r_w0 + (v >> 13);
-                    while (g < B.n_rows && B.off[g] < p) ++g;
                     int k = o;
                     while (g <= B.n_rows && B.off[g] == p) {
                         if (g > 0 && A.M.eos >= 0) { if (fits) tbase[k] = A.M.eos; ++k; }
