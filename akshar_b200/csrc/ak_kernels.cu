@@ -467,7 +467,7 @@ __device__ __noinline__ void akn3_load_edge(const uint8_t* text, int64_t cs, int
 }
 
 #ifndef AKN3_MINB
-#define AKN3_MINB 6
+#define AKN3_MINB 8
 #endif
 __global__ void __launch_bounds__(AKN3_THREADS, AKN3_MINB) ak_nf3_classify_kernel(const AkFastNormArgs A, const AkNfWork W) {
     __shared__ int s_red[AKN3_THREADS / 32];
@@ -1065,7 +1065,7 @@ __global__ void __launch_bounds__(AK_BLOCK, 4) ak_sf_kernel(const AkSfArgs A) {
 // place in the temporary stream.
 #define AKS3_THREADS 128
 #ifndef AKS3_MINB
-#define AKS3_MINB 6
+#define AKS3_MINB 8
 #endif
 __global__ void __launch_bounds__(AKS3_THREADS, AKS3_MINB) ak_sf3_kernel(const AkSfArgs A) {
     __shared__ unsigned int s_cursor[2];
@@ -1612,9 +1612,11 @@ __global__ void __launch_bounds__(AK_BLOCK, AKB_MINB) ak_bf_encode_kernel(const 
 // word length or row ordinal (from bit 13).
 #define AKB3_THREADS 128
 #define AKB3_WARPS (AKB3_THREADS / 32)
-#define AKB3_EVCAP 768
+#ifndef AKB3_EVCAP
+#define AKB3_EVCAP 512       // events per 960 bytes kept in shared memory (a denser tile takes the v2 routine)
+#endif
 #ifndef AKB3_MINB
-#define AKB3_MINB 5
+#define AKB3_MINB 8         // measured: 5 -> 3.28 ms, 6 -> 3.26, 8 (64 registers, 512-event lists) -> 3.09 per 256 MiB
 #endif
 
 // exact NFC check of the troubled code points (cold): does NFC change the text?
