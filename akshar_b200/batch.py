@@ -446,21 +446,20 @@ class Engine:
             S = sets[k & 1]
             b0, b1 = int(off_np[lo]), int(off_np[hi])
             nb, nr = b1 - b0, hi - lo
-            np.subtract(off_np[lo:hi + 1], b0, out=S['h_off'].numpy()[:nr + 1]) if k < 2 else None
             with torch.cuda.stream(s_in):
                 if k >= 2:
                     s_in.wait_event(S['ev_comp'])      # the kernels that read this input buffer have finished
-                    S['ev_in'].synchronize()            # and its pinned offset staging was consumed
-                    np.subtract(off_np[lo:hi + 1], b0, out=S['h_off'].numpy()[:nr + 1])
+                # the rows keep their ABSOLUTE offsets (the C ABI takes text_begin / text_end): no per-chunk rebasing on
+                # the host, the offsets go to the device straight from the caller's (pinned) array
                 S['text'][:nb].copy_(h_data[b0:b1], non_blocking=True)
-                S['off'][:nr + 1].copy_(S['h_off'][:nr + 1], non_blocking=True)
+                S['off'][:nr + 1].copy_(h_off[lo:hi + 1], non_blocking=True)
                 S['ev_in'].record(s_in)
             with torch.cuda.stream(s_comp):
                 s_comp.wait_event(S['ev_in'])
                 if k >= 2:
                     s_comp.wait_event(S['ev_out'])     # chunk k-2's results left this set's output buffers
                 rc = self.lib.akshar_tokenizer_encode_batch(
-                    self._h, S['text'].data_ptr(), S['off'].data_ptr(), nr, 0, nb, flags, kind, C.MODE_TILES, S['norm'].data_ptr(),
+                    self._h, S['text'].data_ptr() - b0, S['off'].data_ptr(), nr, b0, b1, flags, kind, C.MODE_TILES, S['norm'].data_ptr(),
                     ncap, S['norm_off'].data_ptr(), S['ids'].data_ptr(), cap, S['splits'].data_ptr(), S['result'].data_ptr(),
                     ws.data_ptr(), ws.numel(), ctypes.c_void_p(s_comp.cuda_stream))
                 if rc != 0:
