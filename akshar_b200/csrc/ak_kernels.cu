@@ -638,9 +638,16 @@ __global__ void __launch_bounds__(1024) ak_nf_scan_kernel(const int32_t* tile_to
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) carry = 0;
     __syncthreads();
-    for (int b = 0; b < n_tiles; b += 1024) {
-        const int i = b + tid;
-        long long v = i < n_tiles ? tile_total[i] : 0;
+    // 8 consecutive entries per thread (a serial prefix in registers), so one trip of the block scan covers 8192 entries
+    for (int b = 0; b < n_tiles; b += 8192) {
+        const int i0 = b + tid * 8;
+        int v8[8];
+        long long v = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            v8[k] = (i0 + k < n_tiles) ? tile_total[i0 + k] : 0;
+            v += v8[k];
+        }
         long long inc = v;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
@@ -660,8 +667,12 @@ __global__ void __launch_bounds__(1024) ak_nf_scan_kernel(const int32_t* tile_to
             if (lane == 31) ws[32] = xi;
         }
         __syncthreads();
-        const long long ex = carry + ws[warp] + inc - v;
-        if (i < n_tiles) tile_base[i] = ex;
+        long long ex = carry + ws[warp] + inc - v;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            if (i0 + k < n_tiles) tile_base[i0 + k] = ex;
+            ex += v8[k];
+        }
         __syncthreads();
         if (tid == 0) carry += ws[32];
         __syncthreads();
@@ -1213,10 +1224,35 @@ __global__ void __launch_bounds__(AKS3_THREADS, AKS3_MINB) ak_sf3_kernel(const A
     }
 }
 
+// Flat copy of one warp's 32 consecutive warp-tile blocks from the temporary stream to their (contiguous) final range:
+// lane k moves elements k, k + 32, ... of the whole range, four loads in flight; the tile an element belongs to comes
+// from the exclusive prefix in shared memory (s_excl[0..32], s_delta[j] = block start in temp - exclusive prefix).
+template <class T>
+__device__ __forceinline__ void akw_flat_copy(const T* temp, T* out, int64_t dst0, int W, const int* s_excl, const long long* s_delta,
+                                              int lane) {
+    int j = 0;
+    for (int k = lane; k < W; k += 128) {
+        long long sidx[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int kk = k + 32 * u;
+            if (kk < W) {
+                while (kk >= s_excl[j + 1]) ++j;
+                sidx[u] = s_delta[j] + kk;
+            } else sidx[u] = -1;
+        }
+        T v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) if (sidx[u] >= 0) v[u] = temp[sidx[u]];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) if (sidx[u] >= 0) out[dst0 + k + 32 * u] = v[u];
+    }
+}
+
 __global__ void __launch_bounds__(AKW_GROUP) ak_sf_copy_kernel(const AkSfArgs A) {
     __shared__ int ws[33];
-    __shared__ long long s_cb[AKW_GROUP];
-    __shared__ long long s_rb[AKW_GROUP];
+    __shared__ int s_excl[AKW_GROUP / 32][33];
+    __shared__ long long s_delta[AKW_GROUP / 32][32];
     AkBatch B = A.B;
     if (!ak_batch_begin(B)) return;
     const bool want_c = (A.flags & AK_SEG_CLUSTERS) != 0, want_r = (A.flags & AK_SEG_RUNS) != 0;
@@ -1225,36 +1261,33 @@ __global__ void __launch_bounds__(AKW_GROUP) ak_sf_copy_kernel(const AkSfArgs A)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int gidx = blockIdx.x; gidx < n_groups; gidx += gridDim.x) {
         const int t = gidx * AKW_GROUP + tid;
-        int total;
-        if (want_c) {
-            const int pre = ak_block_exscan<AKW_GROUP>(t < n_wt ? A.c_total[t] : 0, ws, total);
-            s_cb[tid] = A.c_sum_base[gidx] + pre;
-        }
-        if (want_r) {
-            const int pre = ak_block_exscan<AKW_GROUP>(t < n_wt ? A.r_total[t] : 0, ws, total);
-            s_rb[tid] = A.r_sum_base[gidx] + pre;
-        }
-        __syncthreads();
-        for (int j = 0; j < 32; ++j) {
-            const int tj = gidx * AKW_GROUP + warp * 32 + j;
-            if (tj >= n_wt) break;
-            const int64_t r0 = A.wrow[tj], r1 = A.wrow[tj + 1];
-            if (want_c) {
-                const int n = A.c_total[tj];
-                const int64_t src = A.c_toff[tj], dst = s_cb[warp * 32 + j];
-                if (dst + n > A.o.ccap) { if (lane == 0 && n > 0) ak_raise(B.result, AK_ST_OVERFLOW); }
-                else for (int i = lane; i < n; i += 32) A.o.cluster_ends[dst + i] = A.tc[src + i];
-                for (int64_t r = r0 + lane; r < r1 && r <= B.n_rows; r += 32) A.o.cluster_splits[r] += dst;
+        const int64_t r0 = t < n_wt ? A.wrow[t] : 0, r1 = t < n_wt ? A.wrow[t + 1] : 0;
+        for (int pass = 0; pass < 2; ++pass) {
+            if (pass == 0 ? !want_c : !want_r) continue;
+            const int32_t* totals = pass == 0 ? A.c_total : A.r_total;
+            const int64_t* toffs = pass == 0 ? A.c_toff : A.r_toff;
+            int64_t* splits = pass == 0 ? A.o.cluster_splits : A.o.run_splits;
+            const int mine = t < n_wt ? totals[t] : 0;
+            int total;
+            const int pre = ak_block_exscan<AKW_GROUP>(mine, ws, total);
+            const int64_t dst = (pass == 0 ? A.c_sum_base[gidx] : A.r_sum_base[gidx]) + pre;
+            for (int64_t r = r0; r < r1 && r <= B.n_rows; ++r) splits[r] += dst;       // rows that start in my warp tile
+            const int pre_w = __shfl_sync(0xFFFFFFFFu, pre, 0);
+            __syncwarp();
+            s_excl[warp][lane] = pre - pre_w;
+            s_delta[warp][lane] = (t < n_wt ? toffs[t] : 0) - (long long)(pre - pre_w);
+            const int W = __shfl_sync(0xFFFFFFFFu, pre + mine, 31) - pre_w;
+            if (lane == 0) s_excl[warp][32] = 0x7FFFFFFF;
+            __syncwarp();
+            const int64_t dst0 = __shfl_sync(0xFFFFFFFFu, dst, 0);
+            if (dst0 + W > (pass == 0 ? A.o.ccap : A.o.rcap)) { if (lane == 0 && W > 0) ak_raise(B.result, AK_ST_OVERFLOW); }
+            else if (pass == 0) akw_flat_copy<int32_t>(A.tc, A.o.cluster_ends, dst0, W, s_excl[warp], s_delta[warp], lane);
+            else {
+                akw_flat_copy<int32_t>(A.tr, A.o.run_ends, dst0, W, s_excl[warp], s_delta[warp], lane);
+                akw_flat_copy<uint8_t>(A.tt, A.o.run_tags, dst0, W, s_excl[warp], s_delta[warp], lane);
             }
-            if (want_r) {
-                const int n = A.r_total[tj];
-                const int64_t src = A.r_toff[tj], dst = s_rb[warp * 32 + j];
-                if (dst + n > A.o.rcap) { if (lane == 0 && n > 0) ak_raise(B.result, AK_ST_OVERFLOW); }
-                else for (int i = lane; i < n; i += 32) { A.o.run_ends[dst + i] = A.tr[src + i]; A.o.run_tags[dst + i] = A.tt[src + i]; }
-                for (int64_t r = r0 + lane; r < r1 && r <= B.n_rows; r += 32) A.o.run_splits[r] += dst;
-            }
+            __syncthreads();
         }
-        __syncthreads();
     }
 }
 
@@ -1881,10 +1914,12 @@ __global__ void __launch_bounds__(AKB3_THREADS, AKB3_MINB) ak_bf3_encode_kernel(
     }
 }
 
+
 // move every warp tile's block to its final place and make the row splits global
 __global__ void __launch_bounds__(AKW_GROUP) ak_bf_copy_kernel(const AkBfArgs A) {
     __shared__ int ws[33];
-    __shared__ long long s_base[AKW_GROUP];
+    __shared__ int s_excl[AKW_GROUP / 32][33];
+    __shared__ long long s_delta[AKW_GROUP / 32][32];
     AkBatch B = A.B;
     if (!ak_batch_begin(B)) return;
     const int n_wt = akw_n_tiles(B, A.base0);
@@ -1895,19 +1930,22 @@ __global__ void __launch_bounds__(AKW_GROUP) ak_bf_copy_kernel(const AkBfArgs A)
         const int mine = t < n_wt ? A.wt_total[t] : 0;
         int total;
         const int pre = ak_block_exscan<AKW_GROUP>(mine, ws, total);
-        s_base[tid] = A.sum_base[gidx] + pre;
-        __syncthreads();
-        // each warp moves the blocks of its 32 warp tiles, one at a time, coalesced
-        for (int j = 0; j < 32; ++j) {
-            const int tj = gidx * AKW_GROUP + warp * 32 + j;
-            if (tj >= n_wt) break;
-            const int n = A.wt_total[tj];
-            const int64_t src = A.wt_toff[tj], dst = s_base[warp * 32 + j];
-            if (dst + n > A.id_cap) { if (lane == 0 && n > 0) ak_raise(B.result, AK_ST_OVERFLOW); }
-            else for (int i = lane; i < n; i += 32) A.ids[dst + i] = A.temp[src + i];
-            const int64_t r0 = A.wrow[tj], r1 = A.wrow[tj + 1];
-            for (int64_t r = r0 + lane; r < r1 && r <= B.n_rows; r += 32) A.id_splits[r] += dst;
+        const int64_t dst = A.sum_base[gidx] + pre;                   // final position of this lane's warp tile
+        // the rows that start in my warp tile: splits made global
+        if (t < n_wt) {
+            const int64_t r0 = A.wrow[t], r1 = A.wrow[t + 1];
+            for (int64_t r = r0; r < r1 && r <= B.n_rows; ++r) A.id_splits[r] += dst;
         }
+        // the warp's 32 blocks are contiguous in the output: one flat, coalesced copy
+        const int pre_w = __shfl_sync(0xFFFFFFFFu, pre, 0);
+        s_excl[warp][lane] = pre - pre_w;
+        s_delta[warp][lane] = (t < n_wt ? A.wt_toff[t] : 0) - (long long)(pre - pre_w);
+        const int W = __shfl_sync(0xFFFFFFFFu, pre + mine, 31) - pre_w;
+        if (lane == 0) s_excl[warp][32] = 0x7FFFFFFF;
+        __syncwarp();
+        const int64_t dst0 = __shfl_sync(0xFFFFFFFFu, dst, 0);
+        if (dst0 + W > A.id_cap) { if (lane == 0 && W > 0) ak_raise(B.result, AK_ST_OVERFLOW); }
+        else akw_flat_copy<int32_t>(A.temp, A.ids, dst0, W, s_excl[warp], s_delta[warp], lane);
         __syncthreads();
     }
 }
