@@ -39,7 +39,11 @@ AK_HD unsigned long long akw_ld(const unsigned long long* p) {
 AK_HD unsigned long long akw_ldc(const unsigned long long* p) {
 #ifdef __CUDA_ARCH__
     unsigned long long v;
+#ifdef AKW_PROBE_L2
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+#else
     asm volatile("ld.global.ca.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+#endif
     return v;
 #else
     return *p;

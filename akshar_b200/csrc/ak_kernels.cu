@@ -595,7 +595,10 @@ struct AkNfSlowArgs {
     int write;
 };
 
-__global__ void __launch_bounds__(128) ak_nf_slow_kernel(const AkNfSlowArgs A) {
+#ifndef AKN_SLOW_MINB
+#define AKN_SLOW_MINB 12       // measured 4 / 6 / 8 / 12: 8.18 / 8.02 / 8.01 / 7.89 ms per 512 MiB of the BPE workload
+#endif
+__global__ void __launch_bounds__(128, AKN_SLOW_MINB) ak_nf_slow_kernel(const AkNfSlowArgs A) {
     const AkBatch& B = A.B;
     unsigned int n = *A.W.n_slow;
     if (n > A.W.slow_cap) n = A.W.slow_cap;
@@ -2400,7 +2403,7 @@ static int ak_run_normalize(akshar_ctx* ctx, AkCall& C, const AkBatch& B, uint32
         S.out_cap = out_cap;
         S.out_off = out_off;
         S.write = 0;
-        const int slow_grid = ctx->sm_count * 4;
+        const int slow_grid = ctx->sm_count * AKN_SLOW_MINB;      // latency bound: as many walkers in flight as fit
         ak_nf_slow_kernel<<<slow_grid, 128, 0, C.stream>>>(S);
         if ((rc = ak_after_launch(ctx, "normalize-slow-count"))) return rc;
         ak_nf_scan_kernel<<<1, 1024, 0, C.stream>>>(W.tile_total, W.tile_base, F.B.n_tiles, B.totals, B, F.base0);
