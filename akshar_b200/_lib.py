@@ -20,7 +20,7 @@ SYMBOLS = (
     'akshar_version', 'akshar_status_str', 'akshar_ctx_create', 'akshar_ctx_destroy', 'akshar_last_error',
     'akshar_workspace_bytes', 'akshar_normalize_batch', 'akshar_segment_batch', 'akshar_signature_batch',
     'akshar_load_bpe_json', 'akshar_load_spm_model', 'akshar_vocab_size', 'akshar_vocab_token',
-    'akshar_encode_bpe_batch', 'akshar_encode_unigram_batch', 'akshar_tokenizer_encode_batch', 'akshar_launch_count', 'akshar_timing_enable', 'akshar_timing_read',
+    'akshar_encode_bpe_batch', 'akshar_encode_unigram_batch', 'akshar_tokenizer_encode_batch', 'akshar_launch_count', 'akshar_timing_enable', 'akshar_timing_read', 'akshar_word_cache_hold',
 )
 
 _lib = None
@@ -63,6 +63,7 @@ def load():
     L.akshar_encode_unigram_batch.argtypes = [vp, vp, vp, i64, i64, i64, i32, vp, i64, vp, vp, vp, sz, vp]
     L.akshar_tokenizer_encode_batch.argtypes = [vp, vp, vp, i64, i64, i64, u32, i32, i32, vp, i64, vp, vp, i64, vp, vp, vp, sz, vp]
     L.akshar_timing_enable.argtypes = [vp, i32]
+    L.akshar_word_cache_hold.argtypes = [vp, i32]
     L.akshar_timing_read.argtypes = [vp, i32, c.POINTER(c.c_float)]
     L.akshar_launch_count.argtypes = [vp]
     L.akshar_launch_count.restype = i64

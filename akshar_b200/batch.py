@@ -371,7 +371,7 @@ class Engine:
         import numpy as np
         from . import shard
         if chunk_bytes is None:
-            chunk_bytes = int(os.environ.get('AKSHAR_CHUNK_MB', '128')) << 20
+            chunk_bytes = int(os.environ.get('AKSHAR_CHUNK_MB', '64')) << 20
         dev = self.device
         n_rows = h_off.numel() - 1
         off_np = h_off.numpy()
@@ -398,11 +398,12 @@ class Engine:
         if 'streams' not in pc:
             pc['streams'] = tuple(torch.cuda.Stream(device=dev) for _ in range(3))
         s_in, s_comp, s_out = pc['streams']
-        key = (max_b, max_r)
+        NSETS = 3        # input / compute / output of three consecutive chunks in flight; the host trails two chunks behind
+        key = (max_b, max_r, NSETS)
         sets = pc.get('sets') if pc.get('sets_key') == key else None
         if sets is None:
             sets = []
-            for _ in range(2):
+            for _ in range(NSETS):
                 sets.append({
                     'text': torch.empty(max(max_b, 1), dtype=torch.uint8, device=dev),
                     'off': torch.empty(max_r + 1, dtype=torch.int64, device=dev),
@@ -420,10 +421,20 @@ class Engine:
             st.wait_stream(cur)
         state = {'tok': 0, 'ok': True}
         out_splits[0] = 0
+        trace = [] if os.environ.get('AKSHAR_PIPE_TRACE') else None
+        if trace is not None:
+            t0ev = torch.cuda.Event(enable_timing=True)
+            t0ev.record(cur)
+
+        def mark(stream, what, k):
+            if trace is not None:
+                e = torch.cuda.Event(enable_timing=True)
+                e.record(stream)
+                trace.append((what, k, e))
 
         def finish(k):
             lo, hi = ranges[k]
-            S = sets[k & 1]
+            S = sets[k % NSETS]
             with torch.cuda.stream(s_out):
                 s_out.wait_event(S['ev_comp'])
                 r = S['result'].cpu()          # waits for chunk k's kernels only; later chunks are already enqueued
@@ -434,46 +445,59 @@ class Engine:
                 if state['tok'] + n > out_ids.numel():
                     state['ok'] = False
                     return
+                mark(s_out, 'd2h_begin', k)
                 out_ids[state['tok']:state['tok'] + n].copy_(S['ids'][:n], non_blocking=True)
                 sp = S['splits'][1:hi - lo + 1]
                 if state['tok']:
                     sp = sp + state['tok']
                 out_splits[lo + 1:hi + 1].copy_(sp, non_blocking=True)
                 S['ev_out'].record(s_out)
+                mark(s_out, 'd2h_end', k)
                 state['tok'] += n
 
         for k, (lo, hi) in enumerate(ranges):
-            S = sets[k & 1]
+            S = sets[k % NSETS]
             b0, b1 = int(off_np[lo]), int(off_np[hi])
             nb, nr = b1 - b0, hi - lo
             with torch.cuda.stream(s_in):
-                if k >= 2:
+                if k >= NSETS:
                     s_in.wait_event(S['ev_comp'])      # the kernels that read this input buffer have finished
                 # the rows keep their ABSOLUTE offsets (the C ABI takes text_begin / text_end): no per-chunk rebasing on
                 # the host, the offsets go to the device straight from the caller's (pinned) array
+                mark(s_in, 'h2d_begin', k)
                 S['text'][:nb].copy_(h_data[b0:b1], non_blocking=True)
                 S['off'][:nr + 1].copy_(h_off[lo:hi + 1], non_blocking=True)
                 S['ev_in'].record(s_in)
+                mark(s_in, 'h2d_end', k)
             with torch.cuda.stream(s_comp):
                 s_comp.wait_event(S['ev_in'])
-                if k >= 2:
-                    s_comp.wait_event(S['ev_out'])     # chunk k-2's results left this set's output buffers
+                if k >= NSETS:
+                    s_comp.wait_event(S['ev_out'])     # chunk k-NSETS's results left this set's output buffers
                 rc = self.lib.akshar_tokenizer_encode_batch(
                     self._h, S['text'].data_ptr() - b0, S['off'].data_ptr(), nr, b0, b1, flags, kind, C.MODE_TILES, S['norm'].data_ptr(),
                     ncap, S['norm_off'].data_ptr(), S['ids'].data_ptr(), cap, S['splits'].data_ptr(), S['result'].data_ptr(),
                     ws.data_ptr(), ws.numel(), ctypes.c_void_p(s_comp.cuda_stream))
                 if rc != 0:
+                    self.lib.akshar_word_cache_hold(self._h, 0)
                     self._err(rc, 'akshar_tokenizer_encode_batch')
+                if k == 0 and kind == 0:
+                    # the chunks are ONE batch: the ones that follow keep the words this one added to the cache
+                    self.lib.akshar_word_cache_hold(self._h, 1)
                 S['ev_comp'].record(s_comp)
-            if k >= 1:
-                finish(k - 1)
+                mark(s_comp, 'comp_end', k)
+            if k >= 2:
+                finish(k - 2)          # its kernels ended while chunk k-1 ran: no wait, the copy engines never idle
                 if not state['ok']:
                     break
-        if state['ok']:
-            finish(len(ranges) - 1)
+        self.lib.akshar_word_cache_hold(self._h, 0)
+        for k in range(max(0, len(ranges) - 2), len(ranges)):
+            if state['ok']:
+                finish(k)
         for st in (s_in, s_comp, s_out):
             cur.wait_stream(st)
         torch.cuda.synchronize(dev)
+        if trace:
+            print('pipe trace (ms): ' + ' '.join('%s%d=%.2f' % (w, k, t0ev.elapsed_time(e)) for w, k, e in trace))
         if not state['ok']:
             # a chunk overflowed or needs the row-by-row mode: the plain path handles retries
             ids, _ = self.tokenizer_encode_batch((h_data, h_off), kind, normalize_roman, clean_hinglish)

@@ -2081,6 +2081,7 @@ struct akshar_ctx {
     int occ_bf = 0, occ_sf = 0, occ_bf3 = 0;
     // optional CUDA-event timing of the dominant kernel of each stage (bench.py's roofline line)
     bool timing = false;
+    bool wc_hold = false;          // akshar_word_cache_hold: skip the per-call restore of the word cache
     cudaEvent_t tev[AKSHAR_TIMER_COUNT][2] = {};
     bool tev_valid[AKSHAR_TIMER_COUNT] = {};
     int occ_norm = 0, occ_seg = 0, occ_bpe = 0, occ_uni = 0, occ_sig = 0, occ_nf_classify = 0, occ_nf_write = 0, occ_nf3 = 0, occ_sf3 = 0;
@@ -2189,6 +2190,12 @@ void akshar_ctx_destroy(akshar_ctx* ctx) {
 }
 
 const char* akshar_last_error(akshar_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int akshar_word_cache_hold(akshar_ctx* ctx, int hold) {
+    if (!ctx) return AKSHAR_E_ARG;
+    ctx->wc_hold = hold != 0;
+    return AKSHAR_OK;
+}
 
 int akshar_timing_enable(akshar_ctx* ctx, int enable) {
     if (!ctx) return AKSHAR_E_ARG;
@@ -2770,7 +2777,8 @@ static int ak_run_bpe(akshar_ctx* ctx, AkCall& C, const AkBatch& B, int64_t max_
         F.id_cap = id_capacity;
         F.id_splits = d_id_splits;
         F.changed = changed;
-        AK_CUDA(ctx, cudaMemcpyAsync(ctx->wc.e, ctx->wc_image, ctx->wc_bytes, cudaMemcpyDeviceToDevice, C.stream));
+        if (!ctx->wc_hold)
+            AK_CUDA(ctx, cudaMemcpyAsync(ctx->wc.e, ctx->wc_image, ctx->wc_bytes, cudaMemcpyDeviceToDevice, C.stream));
         ak_warp_rows_kernel<<<(nwt_ub + 2 + 255) / 256, 256, 0, C.stream>>>(B, F.base0, nwt_ub + 2, (int64_t*)F.wrow);
         if ((rc = ak_after_launch(ctx, "bpe-warp-rows"))) return rc;
         {

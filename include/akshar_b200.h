@@ -142,6 +142,13 @@ enum {
     AKSHAR_TIMER_COUNT = 5
 };
 int akshar_timing_enable(akshar_ctx* ctx, int enable);
+
+/* BPE word cache across calls.  By default every encode call starts from the cache image built at model load (nothing
+ * learned in one call is reused by the next).  hold = 1: the calls that follow keep what earlier calls added -- for ONE
+ * logical batch fed in several calls (akshar_b200.batch.encode_host_pipelined cuts a host batch into chunks that
+ * overlap copy and compute); hold = 0 restores the default.  HF tokenizers keeps its word cache for the lifetime of the
+ * Tokenizer (reference tokenizer.py:96-98 -> tokenizers BPE `cache`). */
+int akshar_word_cache_hold(akshar_ctx* ctx, int hold);
 int akshar_timing_read(akshar_ctx* ctx, int timer, float* ms);
 
 /* number of kernels this library has launched on this context since creation (bench.py's gpu_launches) */
