@@ -272,7 +272,13 @@ AK_HD unsigned long long ak_uni_child(const AkUniDev& U, uint32_t node, uint32_t
 // U+0020 run it stands for when remove_extra_whitespaces)
 AK_HD uint32_t ak_uni_next(const AkUniDev& U, const uint8_t* t, int64_t& q, int64_t te) {
     int len;
-    uint32_t cp = ak_decode(t, q, te, len);
+    uint32_t cp;
+    const uint32_t b0 = t[q];
+    if (b0 < 0x80u) { cp = b0; len = 1; }                       // the two shapes that make up the corpus, straight-line:
+    else if ((b0 & 0xF0u) == 0xE0u && q + 3 <= te) {            // ASCII and three-byte code points (every Indic block)
+        cp = ((b0 & 0x0Fu) << 12) | (((uint32_t)t[q + 1] & 0x3Fu) << 6) | ((uint32_t)t[q + 2] & 0x3Fu);
+        len = 3;
+    } else cp = ak_decode(t, q, te, len);
     q += len;
     if (cp == 0x20u) {
         if (U.flags & 2) while (q < te && t[q] == 0x20u) ++q;
