@@ -499,29 +499,24 @@ __global__ void __launch_bounds__(AKN3_THREADS, AKN3_MINB) ak_nf3_classify_kerne
         }
         uint32_t up1p = __shfl_up_sync(0xFFFFFFFFu, L.up1, 1);
         uint32_t dn1n = __shfl_down_sync(0xFFFFFFFFu, L.dn1, 1);
-        if (lane == 0) {
-            uint32_t b[3];
-#pragma unroll
-            for (int i = 0; i < 3; ++i) {
-                const int64_t q = cs - 3 + i;
-                b[i] = (q >= tb && q < te) ? B.text[q] : 0u;
-            }
-            up1p = akn3_up1_from_bytes(b[0], b[1], b[2]);
-        }
+        if (lane == 0) up1p = 0;
         if (lane == 31) dn1n = 0;
         akn3_phase2(L, up1p, dn1n);
         uint32_t up2p = __shfl_up_sync(0xFFFFFFFFu, L.up2, 1);
         uint32_t dn2n = __shfl_down_sync(0xFFFFFFFFu, L.dn2, 1);
-        if (lane == 0) up2p = akn3_up2_from_text(A.T, B.text, cs, tb, te);
+        if (lane == 0) up2p = AKN3_HALO_UP2;
         if (lane == 31) dn2n = 0;
         akn3_phase3(A.T, B.text, cs, te, L, up2p, dn2n);
         {
             uint32_t rest = 0;
             if (L.ge) rest = akn3_gaps_local(B.text, cs, te, L);
+            if (lane == 0) {                                       // the halo lane cannot look further left
+                akn3_gaps_remote(B.text, cs, te, L, rest, 0u);
+                rest = 0;
+            }
             if (__any_sync(0xFFFFFFFFu, rest != 0u)) {
                 const uint32_t lk = akn3_last_kept(B.text, cs, te, L);
-                uint32_t plk = __shfl_up_sync(0xFFFFFFFFu, lk, 1);
-                if (lane == 0) plk = 0;
+                const uint32_t plk = __shfl_up_sync(0xFFFFFFFFu, lk, 1);
                 akn3_gaps_remote(B.text, cs, te, L, rest, plk);
             }
         }

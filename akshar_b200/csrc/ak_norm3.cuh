@@ -101,28 +101,11 @@ AK_HD void akn3_phase1(const uint32_t* x, AkN3Lane& L) {
             ((L.A6b & 1u) << 16) | ((L.A7b & 1u) << 17) | ((L.B6b & 3u) << 18) | ((L.B7b & 3u) << 20);
 }
 
-// up1 of a lane that is not there (left of the warp's first lane): from the three bytes before the lane (0 outside the text)
-AK_HD uint32_t akn3_up1_from_bytes(uint32_t b0, uint32_t b1, uint32_t b2) {
-    if (b0 - 'A' < 26u) b0 += 32u;
-    if (b1 - 'A' < 26u) b1 += 32u;
-    if (b2 - 'A' < 26u) b2 += 32u;
-    uint32_t up = 0;
-    for (int k = 0; k < 8; ++k) up = (up << 3) | ((b0 >> k) & 1u) | (((b1 >> k) & 1u) << 1) | (((b2 >> k) & 1u) << 2);
-    return up;
-}
-
-// up2 of a lane that is not there: the code point that ends right before cs.  Only "dropped" has to be exact (it decides
-// whether the lane's first kept code point is a gap end); inert / accent are the conservative answers.
-AK_HD uint32_t akn3_up2_from_text(const AkTables& Tb, const uint8_t* text, int64_t cs, int64_t tb, int64_t te) {
-    if (cs <= tb || cs > te) return 2u;
-    int64_t q = cs - 1;
-    for (int k = 0; k < 3 && q > tb && (text[q] & 0xC0u) == 0x80u; ++k) --q;
-    const uint32_t b0 = text[q];
-    bool kept;
-    if (b0 < 0x80u) kept = AK_ALLOW(ak_props(Tb, b0)) != 0u;
-    else kept = b0 == 0xE0u && q + 1 < te && (text[q + 1] & 0xFCu) == 0xA4u;
-    return 2u | (kept ? 0u : 4u);
-}
+// The warp's left halo lane has no left neighbour: it runs with up1 = 0 and the conservative up2 below (previous code
+// point not inert, an accent, dropped).  Its own masks may then be off in its first bytes, but everything it hands to
+// lane 1 is taken at its LAST leads; akn3_phase3b marks the hand-over unreliable in the rare lanes where those are the
+// same code points (a last kept code point within the first three bytes, a blind gap end among the last two kept).
+#define AKN3_HALO_UP2 6u
 
 // ---- phase 2: byte comparisons, look-ahead roles, code-point classes ------------------------------------------
 // up1p = the previous lane's up1, dn1n = the next lane's dn1
@@ -233,7 +216,7 @@ AK_HD uint32_t akn3_last_kept(const uint8_t* text, int64_t cs, int64_t te, const
 AK_HD void akn3_gaps_remote(const uint8_t* text, int64_t cs, int64_t te, AkN3Lane& L, uint32_t rest, uint32_t prev_last) {
     if (!rest) return;
     if (prev_last == 1u) return;
-    if (prev_last == 0u) { L.flags |= AKN3_SLOW | 0x400u; return; }
+    if (prev_last == 0u) { L.flags |= AKN3_SLOW | 0x400u; L.ge = rest; return; }     // L.ge now holds the blind gap end
     const int n = akb_ctz(rest);
     if (akn3_cp_bytes(text, cs + n, te) == prev_last) L.E |= 1u << n;
 }
@@ -250,7 +233,9 @@ AK_HD void akn3_phase3b(AkN3Lane& L) {
     // tail trouble: a T bit at or after the head of the segment that holds the second-last kept code point --
     // what the next lane reads from this one (its last kept code point and that one's E) is then not to be trusted
     uint32_t tail_t = has_t;
-    const bool blind = (L.flags & 0x400u) != 0;                  // a gap end whose other side nobody could see
+    // a gap end whose other side nobody could see (L.ge then holds just that bit): it only matters to the next lane when it
+    // is one of the last two kept code points
+    const uint32_t blind = (L.flags & 0x400u) ? L.ge : 0u;
     uint32_t e_last = 0, unknown = 0;
     if (L.KL) {
         const int k1 = 31 - akb_clz(L.KL);
@@ -261,7 +246,12 @@ AK_HD void akn3_phase3b(AkN3Lane& L) {
             const uint32_t hb = heads & ((2u << k2) - 1u);        // heads at or below k2
             if (hb) tail_t = (L.T >> (31 - akb_clz(hb))) ? 1u : 0u;
         }
+        if (blind && (!k2m || (blind >> (31 - akb_clz(k2m))))) tail_t = 1u;
+        // E at a lead in the first three bytes was compared with the previous lane's bytes: a lane without a left
+        // neighbour (the warp's halo) has none, so a last kept code point that early is not to be trusted either
+        if (k1 < 3) tail_t = 1u;
     } else if (!bar) unknown = 1u;
+    if (blind && !L.KL) tail_t = 1u;
     // what the previous lane reads: E at the first kept code point -- not to be trusted when this lane has a T bit, or
     // when that code point's segment runs on to the lane's end (the trouble may sit in the lane after this one)
     uint32_t e_first = 0, head_bad = has_t;
@@ -270,7 +260,6 @@ AK_HD void akn3_phase3b(AkN3Lane& L) {
         if (!(bar & ((1u << f) - 1u))) e_first = (L.E >> f) & 1u;
         if (((heads >> f) >> 1) == 0u) head_bad = 1u;
     }
-    if (blind) tail_t = 1u;
     L.up3 = e_last | (tail_t << 1) | (no_boundary << 2) | (unknown << 3);
     L.dn3 = lead_t | (no_boundary << 1) | (head_bad << 2) | (e_first << 3) | (unknown << 4);
     if (L.T || no_boundary) L.flags |= AKN3_SLOW | 0x1000u;

@@ -236,20 +236,13 @@ int64_t hh_fast_normalize3(const uint8_t* text, const int64_t* off, int64_t n_ro
             akn3_phase1(x, L);
         }
         for (int l = 0; l < NL; ++l) {
-            uint32_t up1p;
-            if (l > 0) up1p = lanes[(size_t)l - 1].up1;
-            else {
-                const int64_t cs = base0 + (w0 - 1) * 32;
-                uint32_t b[3];
-                for (int i = 0; i < 3; ++i) { const int64_t q = cs - 3 + i; b[i] = (q >= tb && q < te) ? text[q] : 0u; }
-                up1p = akn3_up1_from_bytes(b[0], b[1], b[2]);
-            }
+            const uint32_t up1p = l > 0 ? lanes[(size_t)l - 1].up1 : 0u;
             akn3_phase2(lanes[(size_t)l], up1p, l + 1 < NL ? lanes[(size_t)l + 1].dn1 : 0u);
         }
         for (int l = 0; l < NL; ++l) {
             const int64_t cs = base0 + (w0 - 1 + l) * 32;
             // lane 0 has no left neighbour: conservative carries (previous not inert, previous an accent, previous dropped)
-            akn3_phase3(T, text, cs, te, lanes[(size_t)l], l > 0 ? lanes[(size_t)l - 1].up2 : akn3_up2_from_text(T, text, cs, tb, te), l + 1 < NL ? lanes[(size_t)l + 1].dn2 : 0u);
+            akn3_phase3(T, text, cs, te, lanes[(size_t)l], l > 0 ? lanes[(size_t)l - 1].up2 : AKN3_HALO_UP2, l + 1 < NL ? lanes[(size_t)l + 1].dn2 : 0u);
             rest[(size_t)l] = akn3_gaps_local(text, cs, te, lanes[(size_t)l]);
             lastk[(size_t)l] = akn3_last_kept(text, cs, te, lanes[(size_t)l]);
         }
