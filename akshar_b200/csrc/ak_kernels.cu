@@ -681,6 +681,48 @@ __global__ void __launch_bounds__(1024) ak_nf_scan_kernel(const int32_t* tile_to
     }
 }
 
+// The writer's common case: the emitted bytes of a chunk are ONE contiguous stretch of its 20-byte window (nothing dropped
+// inside; the first bytes may belong to the previous chunk's last code point, the last code point may reach into the next
+// chunk).  A-Z lowered four bytes at a time, the stretch moved with funnel shifts: bytes up to the destination's next word
+// boundary one by one, then whole words, then the tail.
+__device__ __forceinline__ void akf_write_run(const AkChunk& c, uint32_t emit, uint8_t* dst) {
+    uint32_t w[7];
+#pragma unroll
+    for (int j = 0; j < 5; ++j) {
+        const uint32_t x = c.w[j];
+        const uint32_t t7 = x & 0x7F7F7F7Fu;
+        const uint32_t up = ((t7 + 0x3F3F3F3Fu) & ~(t7 + 0x25252525u) & ~x) & 0x80808080u;      // 0x41 .. 0x5A
+        w[j] = x | (up >> 2);
+    }
+    w[5] = w[6] = 0;
+    const int a = __ffs(emit) - 1, n = __popc(emit);
+    int h = (int)((4u - ((uint32_t)(uintptr_t)dst & 3u)) & 3u);
+    if (h > n) h = n;
+    const int t = a + h;                                  // window byte where the word-aligned part starts (0 .. 6)
+    const uint32_t sh = (uint32_t)(t & 3) * 8u;
+    uint32_t x[6];
+#pragma unroll
+    for (int j = 0; j < 6; ++j) x[j] = t >= 4 ? w[j + 1] : w[j];
+    uint32_t f[5];
+#pragma unroll
+    for (int j = 0; j < 5; ++j) f[j] = __funnelshift_r(x[j], x[j + 1], sh);
+    {   // head: window bytes a .. a + h - 1
+        const uint32_t hv = __funnelshift_r(w[0], w[1], (uint32_t)a * 8u);      // a <= 3
+        if (h > 0) dst[0] = (uint8_t)hv;
+        if (h > 1) dst[1] = (uint8_t)(hv >> 8);
+        if (h > 2) dst[2] = (uint8_t)(hv >> 16);
+    }
+    const int nw = (n - h) >> 2, r = (n - h) & 3;
+    uint32_t* d32 = reinterpret_cast<uint32_t*>(dst + h);
+#pragma unroll
+    for (int m = 0; m < 4; ++m) if (m < nw) d32[m] = f[m];
+    const uint32_t tv = nw == 0 ? f[0] : nw == 1 ? f[1] : nw == 2 ? f[2] : nw == 3 ? f[3] : f[4];
+    uint8_t* dt = dst + h + 4 * nw;
+    if (r > 0) dt[0] = (uint8_t)tv;
+    if (r > 1) dt[1] = (uint8_t)(tv >> 8);
+    if (r > 2) dt[2] = (uint8_t)(tv >> 16);
+}
+
 // ---- K1d: write the fast lanes' bytes (staged in shared memory, 16-byte stores) and the row offsets
 __global__ void __launch_bounds__(AK_BLOCK) ak_nf_write_kernel(const AkFastNormArgs A, const AkNfWork W) {
     __shared__ __align__(16) uint8_t stage[AKF_STAGE + 32];
@@ -721,7 +763,10 @@ __global__ void __launch_bounds__(AK_BLOCK) ak_nf_write_kernel(const AkFastNormA
                 }
             }
         } else if (info && fits) {
-            akf_write(c, info, staged ? stage + pad + pre : A.out + base + pre);
+            uint8_t* dst = staged ? stage + pad + pre : A.out + base + pre;
+            const uint32_t lowbit = info & (0u - info);
+            if (staged && ((info + lowbit) & info) == 0u && lowbit <= 8u) akf_write_run(c, info, dst);     // one contiguous stretch
+            else akf_write(c, info, dst);
         }
         __syncthreads();
         if (staged) {
