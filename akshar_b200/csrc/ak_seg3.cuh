@@ -232,12 +232,12 @@ AK_HD uint32_t aks3_tag_at(const AkS3Lane& L, int i) {
 AK_HD int aks3_emit(const AkS3Lane& L, uint32_t m, int64_t cs, int64_t rs_in, int32_t* dst, uint8_t* tags) {
     int k = 0;
     const uint32_t rows = L.rows;
+    const int d0 = (int)(cs - rs_in);                       // 32-bit arithmetic in the loop: offsets are int32 by contract
     while (m) {
         const int i = akb_ctz(m);
         m &= m - 1u;
         const uint32_t below = rows & ((1u << i) - 1u);
-        const int64_t rs = below ? cs + (31 - akb_clz(below)) : rs_in;
-        dst[k] = (int32_t)(cs + i - rs);
+        dst[k] = below ? i - (31 - akb_clz(below)) : d0 + i;
         if (tags) tags[k] = (uint8_t)aks3_tag_at(L, i);
         ++k;
     }
