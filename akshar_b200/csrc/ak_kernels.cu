@@ -2725,6 +2725,11 @@ int akshar_load_spm_model(akshar_ctx* ctx, const void* proto, size_t len) {
     int rc;
     if ((rc = ak_upload<unsigned long long>(ctx, ctx->uni_allocs, h.tkeys.data(), h.tkeys.size(), &d.tkeys))) return rc;
     if ((rc = ak_upload<unsigned long long>(ctx, ctx->uni_allocs, h.tvals.data(), h.tvals.size(), &d.tvals))) return rc;
+    {
+        std::vector<unsigned long long> kv(2 * h.tkeys.size());
+        for (size_t i = 0; i < h.tkeys.size(); ++i) { kv[2 * i] = h.tkeys[i]; kv[2 * i + 1] = h.tvals[i]; }
+        if ((rc = ak_upload<unsigned long long>(ctx, ctx->uni_allocs, kv.data(), kv.size(), &d.tkv))) return rc;
+    }
     if ((rc = ak_upload<float>(ctx, ctx->uni_allocs, h.score.data(), h.score.size(), &d.score))) return rc;
     if ((rc = ak_upload<uint8_t>(ctx, ctx->uni_allocs, h.usable.data(), h.usable.size(), &d.usable))) return rc;
     if ((rc = ak_upload<int32_t>(ctx, ctx->uni_allocs, h.byte_id, 256, &d.byte_id))) return rc;

@@ -247,6 +247,7 @@ AK_HD_NOINLINE void ak_bpe_span(const AkBpeDev& M, const AkTables& T, const uint
 struct AkUniDev {
     const unsigned long long* tkeys;      // (node << 21) | cp, AK_EMPTY_KEY when free
     const unsigned long long* tvals;      // (child << 32) | (piece_id + 1), low word 0 when no piece ends here
+    const unsigned long long* tkv;        // optional: the same table interleaved (key, value) -- one 16-byte load per probe
     uint32_t tbits;
     const float* score;                   // per piece id (USER_DEFINED already resolved to len * max - 0.1)
     const uint8_t* usable;                // per piece id: 1 = takes part in the lattice (NORMAL / USER_DEFINED)
@@ -260,6 +261,16 @@ AK_HD unsigned long long ak_uni_child(const AkUniDev& U, uint32_t node, uint32_t
     const unsigned long long key = ((unsigned long long)node << 21) | cp;
     uint32_t h = ak_hash64(key, U.tbits);
     const uint32_t mask = (1u << U.tbits) - 1u;
+#ifdef __CUDA_ARCH__
+    if (U.tkv) {
+        for (;;) {
+            const ulonglong2 e = *reinterpret_cast<const ulonglong2*>(U.tkv + 2u * (size_t)h);
+            if (e.x == key) return e.y;
+            if (e.x == AK_EMPTY_KEY) return AK_EMPTY_KEY;
+            h = (h + 1) & mask;
+        }
+    }
+#endif
     for (;;) {
         unsigned long long k = U.tkeys[h];
         if (k == key) return U.tvals[h];

@@ -713,7 +713,7 @@ void hh_seg_fast(const uint8_t* text, const int64_t* off, int64_t n_rows, uint32
 
 int64_t hh_unigram(const uint8_t* text, const int64_t* off, int64_t n_rows, int32_t* ids, int64_t id_cap, int64_t* splits) {
     AkUniDev U;
-    U.tkeys = g_uni.tkeys.data(); U.tvals = g_uni.tvals.data(); U.tbits = g_uni.tbits; U.score = g_uni.score.data();
+    U.tkeys = g_uni.tkeys.data(); U.tvals = g_uni.tvals.data(); U.tkv = nullptr; U.tbits = g_uni.tbits; U.score = g_uni.score.data();
     U.usable = g_uni.usable.data(); U.byte_id = g_uni.byte_id; U.unk_id = g_uni.unk_id; U.unk_score = g_uni.unk_score;
     U.flags = g_uni.flags;
     int64_t base = 0;
