@@ -1842,7 +1842,8 @@ __global__ void __launch_bounds__(AKB3_THREADS, AKB3_MINB) ak_bf3_encode_kernel(
                         if (above) len = (__ffs(above) - 1) - i;
                         else if (nb1) len = 32 - i + (__ffs(nb1) - 1);
                         else if (nb2) len = 64 - i + (__ffs(nb2) - 1);
-                        else len = akb3_scan_end(A.T, B.text, cs + i, cs + (lane >= 30 ? 62 : 96), kc, B.off, B.n_rows, r_lo, r_hi) - (cs + i);
+                        else    // no boundary in what the warp knows: 96 bytes, less where the right halo lane's last two bytes are masked off
+                            len = akb3_scan_end(A.T, B.text, cs + i, cs + (lane >= 30 ? 62 : lane == 29 ? 94 : 96), kc, B.off, B.n_rows, r_lo, r_hi) - (cs + i);
                         if (len > 0x7FFFF) len = 0x7FFFF;
                         ev[k++] = pos | (kc << 11) | ((uint32_t)len << 13);
                     }

@@ -616,7 +616,7 @@ int64_t hh_bpe_fast3(const uint8_t* text, const int64_t* off, int64_t n_rows, in
                         // the kernel's cold scan (akb3_scan_end)
                         const int64_t er = ak_row_lower_bound(off, 0, n_rows, p + 1);
                         const int64_t re = off[er];
-                        int64_t q = cs + (l >= real ? 62 : 96);
+                        int64_t q = cs + (l >= real ? 62 : l == real - 1 ? 94 : 96);
                         if (q > re) q = re;
                         while (q < re && (text[q] & 0xC0u) == 0x80u) ++q;
                         while (q < re) {

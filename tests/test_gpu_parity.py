@@ -234,6 +234,30 @@ def test_bpe_dense_events(A, models_dir):
     assert tk.encode_batch(lines) == got
 
 
+def test_bpe_long_words_every_alignment(A, models_dir):
+    # word ends beyond the boundary masks a lane sees (its 32 bytes + the next two lanes'), at every alignment
+    import numpy as np
+    tk = A.aksharTokenizer(os.path.join(models_dir, 'bpe24k.json'), 'bpe')
+    om = O.BpeModel(os.path.join(models_dir, 'bpe24k.json'))
+    rng = np.random.default_rng(11)
+    lines = []
+    for _ in range(600):
+        parts = []
+        for _ in range(int(rng.integers(1, 6))):
+            n = int(rng.integers(40, 120))
+            parts.append(('ab' * 80)[:n] if rng.random() < 0.5 else ('\u0915\u0916' * 40)[:n // 3])
+            parts.append('.' if rng.random() < 0.5 else ' ')
+            parts.append('c' * int(rng.integers(0, 3)))
+        lines.append(''.join(parts))
+    for s0 in range(896, 928, 3):
+        for end in (988, 989, 990, 991, 992):
+            lines.append('y' * (s0 - 2) + '. ' + 'a' * (end - s0) + '.' + 'c' * 20)
+    got = [x.tolist() for x in tk._eng.encode_bpe_batch(lines).rows()]
+    assert got == [O.bpe_encode(om, s) for s in lines]
+    for s in lines[-55:]:           # each crafted row as its own batch: it then starts at byte 0 of the first warp
+        assert tk._eng.encode_bpe_batch([s]).rows()[0].tolist() == O.bpe_encode(om, s)
+
+
 def test_bpe_renormalizes_on_device(A, models_dir):
     # rows that are not in NFC make the kernel take its conditional NFC + re-encode passes
     tk = A.aksharTokenizer(os.path.join(models_dir, 'bpe24k.json'), 'bpe', clean_hinglish=True)

@@ -135,6 +135,38 @@ def test_bpe_bit_parallel_front_end(golden, bpe_rows, models_dir, real):
     assert ids.tolist() == [i for e in exp for i in e]
 
 
+def test_bpe_bit_parallel_long_words(models_dir):
+    """words longer than the boundary masks a lane can see (its own 32 bytes + the next two lanes'): every alignment of
+    the word end against the lanes, including the right halo lane whose last two bytes are not classified"""
+    W.load_bpe(os.path.join(models_dir, 'bpe24k.json'))
+    m = O.BpeModel(os.path.join(models_dir, 'bpe24k.json'))
+    rng = np.random.default_rng(11)
+    lines = []
+    for _ in range(400):
+        parts = []
+        for _ in range(int(rng.integers(1, 6))):
+            n = int(rng.integers(40, 120))
+            parts.append(('ab' * 80)[:n] if rng.random() < 0.5 else ('\u0915\u0916' * 40)[:n // 3])
+            parts.append('.' if rng.random() < 0.5 else ' ')
+            parts.append('c' * int(rng.integers(0, 3)))
+        lines.append(''.join(parts))
+    # a word that starts in the warp's last-but-one real lane and ends exactly where the halo lane's mask stops
+    for s0 in range(896, 928, 3):
+        for end in (988, 989, 990, 991, 992):
+            lines.append('y' * (s0 - 2) + '. ' + 'a' * (end - s0) + '.' + 'c' * 20)
+    data, off = sc.pack(lines)
+    exp = [O.bpe_encode(m, s) for s in lines]
+    for real in (30, 5):
+        ids, splits, st, _ = W.bpe_fast3(data, off, real=real)
+        assert st == 0
+        assert ids.tolist() == [i for e in exp for i in e]
+    # the crafted rows again, each as its own batch: the row then starts at byte 0 of the first warp
+    for s in lines[-55:]:
+        data, off = sc.pack([s])
+        ids, splits, st, _ = W.bpe_fast3(data, off, real=30)
+        assert st == 0 and ids.tolist() == O.bpe_encode(m, s)
+
+
 def test_bpe_bit_parallel_classes_match_the_tables():
     """the plane logic hard-codes HF's pre-tokenizer classes and the encoder's alphabet for ASCII and U+0900-097F"""
     T = O.tables()
