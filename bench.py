@@ -32,10 +32,10 @@ MODELS = os.path.join(ROOT, 'tests', 'golden', 'models')
 # DRAM traffic per INPUT byte of each hot kernel: (dram__bytes_read.sum + dram__bytes_write.sum) / input bytes from the
 # `ncu --set full` captures at 256 MiB summarised in profiles/r01_ncu_full_summary.csv; scaled to the run's size below
 TRAFFIC_PER_INPUT_BYTE = {
-    'ak_nf3_classify_kernel': (293.63 + 64.25) / 268.44,
-    'ak_nf_write_kernel': (375.82 + 253.00) / 268.44,
-    'ak_bf3_encode_kernel': (429.62 + 342.56) / 268.44,
-    'ak_sf3_kernel': (304.72 + 497.09) / 268.44,
+    'ak_nf3_classify_kernel': (292.68 + 63.60) / 268.44,
+    'ak_nf_write_kernel': (372.49 + 248.46) / 268.44,
+    'ak_bf3_encode_kernel': (446.12 + 398.04) / 268.44,
+    'ak_sf3_kernel': (301.27 + 496.13) / 268.44,
 }
 CHUNK = 32 << 20
 SEED = 20261018
