@@ -287,6 +287,7 @@ class Engine:
         b = self.put(batch)
         cap = capacity if capacity is not None else (b.n_bytes >> 1) + 2 * b.n_rows + 1024
         ws = self._workspace(b.n_bytes, b.n_rows)
+        word_extra = 0
         for _ in range(self.MAX_TRIES):
             ids = torch.empty(max(cap, 1), dtype=torch.int32, device=self.device)
             splits = torch.empty(b.n_rows + 1, dtype=torch.int64, device=self.device)
@@ -300,6 +301,12 @@ class Engine:
             total, _, bits = self._finish(result, what, True)
             if bits & C.ST_PATHOLOGICAL and mode == C.MODE_TILES:
                 mode = C.MODE_ROWS
+                continue
+            if bits & C.ST_WORD and word_extra < 64:
+                # a batch full of very long words ran out of the long-word pool: half of the workspace beyond the library's
+                # minimum goes to that pool (include/akshar_b200.h), so grow the workspace and call again
+                word_extra = 16 if word_extra == 0 else 64
+                ws = self._workspace(b.n_bytes, b.n_rows, extra=word_extra * b.n_bytes + (4 << 20))
                 continue
             if bits & C.ST_OVERFLOW:
                 cap = max(cap, total)
@@ -328,6 +335,7 @@ class Engine:
         ncap = b.n_bytes + (b.n_bytes >> 3) + 1024
         cap = capacity if capacity is not None else (b.n_bytes >> 1) + 2 * b.n_rows + 1024
         ws = self._workspace(ncap, b.n_rows)
+        word_extra = 0
         for _ in range(self.MAX_TRIES):
             dev = self.device
             norm = torch.empty(max(ncap, 1), dtype=torch.uint8, device=dev)
@@ -346,6 +354,10 @@ class Engine:
             total, nbytes, bits = self._finish(result, 'tokenizer_encode', True)
             if bits & C.ST_PATHOLOGICAL and mode == C.MODE_TILES:
                 mode = C.MODE_ROWS
+                continue
+            if bits & C.ST_WORD and word_extra < 64:
+                word_extra = 16 if word_extra == 0 else 64         # long-word pool: see _encode
+                ws = self._workspace(ncap, b.n_rows, extra=word_extra * b.n_bytes + (4 << 20))
                 continue
             if bits & C.ST_OVERFLOW:
                 # totals are exact even when a capacity was too small

@@ -2783,6 +2783,17 @@ static int ak_run_bpe(akshar_ctx* ctx, AkCall& C, const AkBatch& B, int64_t max_
     pool.base = (int32_t*)(C.ws + C.L.pool);
     pool.used = (unsigned long long*)(C.ws + 128);
     pool.cap = ak_pool_ints(max_bytes);
+    // A workspace larger than the minimum gives half of the surplus to the long-word pool (the other half enlarges the
+    // temporary id stream): a batch full of words beyond AK_BPE_LOCAL symbols raises AKSHAR_ST_WORD with the minimum,
+    // the caller grows the workspace and calls again.  The pool then lives at the workspace's tail.
+    size_t pool_tail = 0;
+    if (C.ws_bytes > C.L.total + (1u << 20)) {
+        pool_tail = ((C.ws_bytes - C.L.total) / 2) & ~(size_t)255;
+        if (pool_tail / 4 > pool.cap) {
+            pool.base = (int32_t*)(C.ws + ((C.ws_bytes - pool_tail) & ~(size_t)255));
+            pool.cap = pool_tail / 4 - 64;
+        } else pool_tail = 0;
+    }
     // pass 1: encode the text as it is; raises `changed` when some NFC segment is not already normalized
     AkBpeArgs A;
     A.B = B;
@@ -2818,7 +2829,7 @@ static int ak_run_bpe(akshar_ctx* ctx, AkCall& C, const AkBatch& B, int64_t max_
         const bool v2 = getenv("AKSHAR_BPE_V2") != nullptr;
         const int grid = v2 ? ak_grid(ctx, ctx->occ_bf, (nwt_ub + AKF_WARPS - 1) / AKF_WARPS)
                             : ak_grid(ctx, ctx->occ_bf3, ((nwt_ub + 1) / 2 + AKB3_WARPS - 1) / AKB3_WARPS);
-        F.slice_cap = (int64_t)((C.ws_bytes - (size_t)(wp - C.ws)) / 4 / (size_t)grid);      // a larger workspace = larger slices
+        F.slice_cap = (int64_t)((C.ws_bytes - pool_tail - 512 - (size_t)(wp - C.ws)) / 4 / (size_t)grid);      // a larger workspace = larger slices
         F.ids = d_ids;
         F.id_cap = id_capacity;
         F.id_splits = d_id_splits;

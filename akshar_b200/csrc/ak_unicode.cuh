@@ -65,6 +65,21 @@ AK_HD int ak_utf8_len(uint32_t cp) { return cp < 0x80u ? 1 : cp < 0x800u ? 2 : c
 AK_HD uint32_t ak_decode(const uint8_t* t, int64_t pos, int64_t end, int& len) {
     uint32_t b0 = t[pos];
     if (b0 < 0x80u) { len = 1; return b0; }
+    // complete sequences straight-line (every walker decodes the same code points several times; the rolled loop below was
+    // a tenth of the slow-lane kernel's instructions); the loop keeps the truncated tails
+    if (b0 >= 0xE0u && b0 < 0xF0u && pos + 3 <= end) {
+        len = 3;
+        return ((b0 & 0x0Fu) << 12) | (((uint32_t)t[pos + 1] & 0x3Fu) << 6) | ((uint32_t)t[pos + 2] & 0x3Fu);
+    }
+    if (b0 >= 0xC0u && b0 < 0xE0u && pos + 2 <= end) {
+        len = 2;
+        return ((b0 & 0x1Fu) << 6) | ((uint32_t)t[pos + 1] & 0x3Fu);
+    }
+    if (b0 >= 0xF0u && pos + 4 <= end) {
+        len = 4;
+        return ((b0 & 0x07u) << 18) | (((uint32_t)t[pos + 1] & 0x3Fu) << 12) | (((uint32_t)t[pos + 2] & 0x3Fu) << 6) |
+               ((uint32_t)t[pos + 3] & 0x3Fu);
+    }
     int n = b0 >= 0xF0u ? 4 : b0 >= 0xE0u ? 3 : b0 >= 0xC0u ? 2 : 1;
     if (pos + n > end) n = (int)(end - pos);
     uint32_t cp = n == 1 ? b0 : (b0 & (0xFFu >> (n + 1)));

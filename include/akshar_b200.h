@@ -43,7 +43,8 @@ enum {
     AKSHAR_ST_ALPHABET = 8,      /* BPE encode met a code point on which HF's NFKC differs from NFC (compatibility
                                   * characters, marks newer than its Unicode tables) or a '<' (added-token syntax) */
     AKSHAR_ST_SPIN = 16,
-    AKSHAR_ST_WORD = 32,         /* BPE word longer than the per-word capacity: re-run with AKSHAR_MODE_ROWS */
+    AKSHAR_ST_WORD = 32,         /* the long-word pool ran out (many words beyond 48 symbols): call again with a larger
+                                    workspace -- half of what exceeds akshar_workspace_bytes() goes to that pool */
 };
 
 /* normalize flags: normalize_text(text, normalize_roman, clean_hinglish) (normalize.py:117) is
