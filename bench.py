@@ -133,11 +133,12 @@ class ClockSampler:
         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
 
     def __init__(self, index):
-        self.rows = []
+        self.rows = []             # (arrival time, line)
         self.proc = None
+        self.t_from = 0.0
         try:
             self.proc = subprocess.Popen(['nvidia-smi', '-i', str(index), '--query-gpu=' + self.Q, '--format=csv,noheader,nounits',
-                                          '-lms', '100'], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          '-lms', '20'], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
         except Exception:
@@ -145,7 +146,18 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append(line.strip())
+            self.rows.append((time.perf_counter(), line.strip()))
+
+    def wait_first(self, timeout=5.0):
+        """nvidia-smi takes a few hundred ms to deliver its first line: wait for it so that the (short) measured phases
+        are covered"""
+        t0 = time.perf_counter()
+        while self.proc and not self.rows and time.perf_counter() - t0 < timeout:
+            time.sleep(0.01)
+
+    def mark(self):
+        """only samples that arrive from now on count (the measured phases start here)"""
+        self.t_from = time.perf_counter()
 
     def stop(self):
         if not self.proc:
@@ -157,7 +169,9 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], None, set()
         names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-        for r in self.rows:
+        for ts, r in self.rows:
+            if ts < self.t_from:
+                continue
             f = [x.strip() for x in r.split(',')]
             if len(f) < 6:
                 continue
@@ -285,11 +299,15 @@ def main():
     n_tokens = int(res[0]) + (int(res[1]) if mkind is None else 0)
     n_norm = int(res[1]) if mkind is not None else int(out[1].end)
     del out
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.wait_first()
     for _ in range(max(0, a.warmup - 1)):
         device_step()
     barrier()
-    sampler = ClockSampler(local) if rank == 0 else None
-    l0 = eng.launch_count()
+    if sampler:
+        sampler.mark()          # clocks are sampled every 20 ms from here to the end of the measured phases (timed steps,
+    l0 = eng.launch_count()     # end-to-end steps, per-kernel timing steps): the timed region alone lasts < 100 ms
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(a.steps):
@@ -298,8 +316,6 @@ def main():
     barrier()
     launches = eng.launch_count() - l0
     ms = e0.elapsed_time(e1) / a.steps
-    clocks = sampler.stop() if sampler else None
-
     # ---- end to end through the public batch API: pinned host text in, ids (or offsets) on the host out
     def e2e_step():
         if mkind is not None:
@@ -350,6 +366,7 @@ def main():
             if v is not None:
                 acc[k].append(v)
     eng.timing(False)
+    clocks = sampler.stop() if sampler else None
     kms = {k: sum(v) / len(v) for k, v in acc.items() if v}
     n_c = int(res[0]) if mkind is None else 0
     n_r = int(res[1]) if mkind is None else 0
