@@ -410,7 +410,7 @@ def main():
                 'd2h_bytes_per_step': int(tot_d2h / world), 'ms_per_step': e2e_ms},
         'gpu_launches': int(tot_launch),
         'roofline': {'bound': 'hbm', 'kernel': dom, 'achieved': ach, 'peak': peak, 'peak_source': peak_kind, 'unit': 'GB/s',
-                     'frac': ach / peak,
+                     'frac': ach / peak, 'frac_of_nominal_8000': ach / 8000.0,
                      'traffic': (int(TRAFFIC_PER_INPUT_BYTE[dom] * nbytes) if dom in TRAFFIC_PER_INPUT_BYTE else None),
                      'traffic_source': 'ncu --set full at 256 MiB, scaled by input bytes (profiles/r01_v3_ncu_full_summary.csv)',
                      'ms': stages[dom][0], 'algorithmic_bytes': stages[dom][1],
