@@ -1162,6 +1162,7 @@ __global__ void __launch_bounds__(AKS3_THREADS, AKS3_MINB) ak_sf3_kernel(const A
         uint32_t dn1n = __shfl_down_sync(0xFFFFFFFFu, L.dn1, 1);
         if (lane == 31) dn1n = 0;
         aks3_phase2(L, dn1n);
+        if (L.FOR) aks3_foreign(A.T, B.text, cs, te, L);
         aks3_summary(L);
         const uint32_t up2p = __shfl_up_sync(0xFFFFFFFFu, L.up2, 1);
         const bool real = lane >= 1 && lane <= 30;

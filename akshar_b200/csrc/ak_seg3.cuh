@@ -12,8 +12,10 @@
 //   rchg               a script run ends before the strong (not digit / punct) code point led here: its label differs
 //                      from the previous strong one's, which travels to it over the weak ones by carry propagation
 //   PD / PR / PO       label of the previous strong code point, at every event position (run tags)
-// Everything else (Bengali, NBSP, emoji when the input is not normalized ...) is FOREIGN: the lane takes the slow
-// lane = the walker ak_seg_span on its 32 bytes, and tells its successor that its end state is not to be trusted.
+// Code points outside ASCII / U+0900-097F (Bengali, NBSP, emoji when the input is not normalized ...) are classified one
+// by one from the property table and join the same masks: GB11 (ExtPict Extend* ZWJ x ExtPict) is one more MatchStar,
+// GB12/13 a parity over runs of regional indicators.  Only the classes the masks do not model (Prepend, Hangul syllable
+// types) make the lane slow = the walker ak_seg_span on its 32 bytes, and tell its successor not to trust its end state.
 // Cross-lane context: one packed word down (look-ahead byte roles), one up (end-of-lane summaries).
 #pragma once
 #include "ak_bits.cuh"
@@ -28,6 +30,10 @@ struct AkS3Lane {
     uint32_t CR, LF, CTL, ROM, WEAK;                            // ASCII leads
     // code-point masks (phase 2)
     uint32_t DEV, FOR, X, SM, CONS, LK, MAT, strong_d, strong_r, strong_o;
+    // X = GCB Extend or ZWJ (GB9); XI = InCB Extend / Linker (transparent for GB9c); XE = GCB Extend only (transparent for
+    // GB11); ZW / EP / RI = ZWJ, Extended_Pictographic, regional indicators; UNS = foreign code points of a class the masks
+    // do not model (Prepend, Hangul syllable types): the lane then takes the walker
+    uint32_t XI, XE, ZW, EP, RI, UNS;
     // results
     uint32_t brk, rchg, PD, PR, PO;
     uint32_t dn1, up2;
@@ -41,7 +47,11 @@ struct AkS3Lane {
 #define AKS3_S2 16u
 #define AKS3_G_OPEN 32u         // no lead that fixes the grapheme state (all Extend / Linker, no barrier), or a foreign one after it
 #define AKS3_LAB_SHIFT 6        // 3 bits: 0 none (barrier, no strong after it), 1 dev, 2 roman, 3 other, 7 open (no strong, no barrier / foreign)
-#define AKS3_LAST_FOR 512u      // last lead is foreign
+#define AKS3_LAST_UNS 512u      // last lead is of an unsupported class
+#define AKS3_P1 1024u           // GB11 state after the last code point: ExtPict Extend* / ... ZWJ
+#define AKS3_P2 2048u
+#define AKS3_LAST_RI 4096u      // last lead is a regional indicator / an odd number of them ends the lane
+#define AKS3_RI_ODD 8192u
 
 // ---- phase 1: planes and byte roles ----------------------------------------------------------------------------
 AK_HD void aks3_phase1(const uint32_t* x, AkS3Lane& L) {
@@ -119,10 +129,48 @@ AK_HD void aks3_phase2(AkS3Lane& L, uint32_t dn1n) {
     L.CONS = (d4 & akb_fsr(L.C4b, dn1n >> 6, 2)) | (d5 & akb_fsr(L.C5b, dn1n >> 12, 2));
     L.LK = d5 & akb_fsr(L.LKb, dn1n >> 14, 2);
     L.MAT = (d4 & akb_fsr(L.M4b, dn1n >> 16, 2)) | (d5 & akb_fsr(L.M5b, dn1n >> 18, 2));
+    L.XI = x;
+    L.XE = x;
+    L.ZW = L.EP = L.RI = L.UNS = 0;
     const uint32_t ascl = L.lead & ~L.hl;
     L.strong_d = L.DEV;
     L.strong_r = L.ROM;
     L.strong_o = ascl & ~L.ROM & ~L.WEAK;
+}
+
+// code points outside ASCII / U+0900-097F, one by one from the property table (emoji, ZWJ, variation selectors, accents,
+// other scripts when the text was not normalized first): they join the same masks, so the rules below hold for them too
+AK_HD void aks3_foreign(const AkTables& Tb, const uint8_t* text, int64_t cs, int64_t te, AkS3Lane& L) {
+    for (uint32_t m = L.FOR; m;) {
+        const int i = akb_ctz(m);
+        m &= m - 1u;
+        const uint32_t bit = 1u << i;
+        int len;
+        const uint32_t cp = ak_decode(text, cs + i, te, len);
+        const uint32_t w = ak_props(Tb, cp);
+        const uint32_t g = AK_GCB(w), ib = AK_INCB(w), tg = AK_TAG(w);
+        if (g == GCB_EXTEND) { L.X |= bit; L.XE |= bit; }
+        else if (g == GCB_ZWJ) { L.X |= bit; L.ZW |= bit; }
+        else if (g == GCB_SPACINGMARK) L.SM |= bit;
+        else if (g == GCB_CONTROL) L.CTL |= bit;
+        else if (g == GCB_RI) L.RI |= bit;
+        else if (g != GCB_OTHER) L.UNS |= bit;                  // Prepend, Hangul L / V / T / LV / LVT (CR / LF are ASCII)
+        if (ib == INCB_CONSONANT) L.CONS |= bit;
+        else if (ib == INCB_LINKER) { L.LK |= bit; L.XI |= bit; }
+        else if (ib == INCB_EXTEND) L.XI |= bit;
+        if (AK_EXTPICT(w)) L.EP |= bit;
+        if (tg == TAG_DIGIT || tg == TAG_PUNCT) L.WEAK |= bit;
+        else L.strong_o |= bit;                                  // identify_script: neither Devanagari nor A-Z a-z -> other
+    }
+}
+
+// bytes of the code points led at M (lead + continuation bytes)
+AK_HD uint32_t aks3_bytes_of(uint32_t M, uint32_t C) {
+    uint32_t s = M;
+    s |= (s << 1) & C;
+    s |= (s << 1) & C;
+    s |= (s << 1) & C;
+    return s;
 }
 
 // conjunct state (GB9c) BEFORE the code point led at each position: r1 = "a consonant, then only Extend / Linker",
@@ -131,13 +179,41 @@ AK_HD void aks3_conj(const AkS3Lane& L, uint32_t c1, uint32_t c2, uint32_t& r1, 
     const uint32_t C = L.cont;
     const uint32_t bar = L.rows | ~L.own;
     const uint32_t fl = L.lead & (0u - L.lead);
-    // bytes of the Extend / Linker code points (all 3 bytes long); the byte before a barrier is taken out so that no
-    // state crosses a row start
-    const uint32_t xb = (L.X | (L.X << 1) | (L.X << 2)) & ~(bar >> 1);
+    // bytes of the InCB Extend / Linker code points; the byte before a barrier is taken out so that no state crosses a
+    // row start
+    const uint32_t xb = aks3_bytes_of(L.XI, C) & ~(bar >> 1);
     const uint32_t t1 = (akb_fwd(L.CONS, C, 0u) | (c1 ? fl : 0u)) & ~bar;
     r1 = aks3_star(t1, xb) & L.lead;
     const uint32_t t2 = (akb_fwd(L.LK & r1, C, 0u) | (c2 ? fl : 0u)) & ~bar;
     r2 = aks3_star(t2, xb) & L.lead;
+}
+// GB11 state BEFORE each lead: p1 = "an ExtPict, then only Extend".  c1 = the state after the last code point before the lane.
+AK_HD uint32_t aks3_pict(const AkS3Lane& L, uint32_t c1) {
+    const uint32_t C = L.cont;
+    const uint32_t bar = L.rows | ~L.own;
+    const uint32_t fl = L.lead & (0u - L.lead);
+    const uint32_t xb = aks3_bytes_of(L.XE, C) & ~(bar >> 1);
+    const uint32_t t1 = (akb_fwd(L.EP, C, 0u) | (c1 ? fl : 0u)) & ~bar;
+    return aks3_star(t1, xb) & L.lead;
+}
+// GB12 / GB13: leads with an ODD number of regional indicators right before them (in the same row).
+// c_ri = the last code point before the lane is an RI, c_odd = an odd number of them ends there.
+AK_HD uint32_t aks3_ri_odd(const AkS3Lane& L, uint32_t c_ri, uint32_t c_odd) {
+    if (!L.RI && !c_odd) return 0u;
+    const uint32_t C = L.cont;
+    const uint32_t bar = L.rows | ~L.own;
+    const uint32_t fl = L.lead & (0u - L.lead);
+    const uint32_t prev_ri = akb_fwd(L.RI, C, c_ri) & ~bar;
+    // pair starts: an RI with an even number of RIs before it -- the first of a run, or the lane's first lead when an even
+    // number of RIs ends the previous lane
+    const uint32_t starts = (L.RI & ~prev_ri) | ((c_ri && !c_odd) ? (L.RI & fl & ~bar) : 0u);
+    uint32_t odd = (akb_fwd(starts, C, 0u) | (c_odd ? fl : 0u)) & ~bar;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const uint32_t even = akb_fwd(odd & L.RI, C, 0u) & ~bar;
+        odd |= akb_fwd(even & L.RI, C, 0u) & ~bar;
+    }
+    return odd;
 }
 
 // ---- phase 2b: end-of-lane summary for the next lane (computed with nothing coming in) --------------------------
@@ -152,18 +228,28 @@ AK_HD void aks3_summary(AkS3Lane& L) {
         if ((L.CTL | L.CR | L.LF) & ll) up |= AKS3_LAST_CTL;
         if (L.CR & ll) up |= AKS3_LAST_CR;
         if (L.MAT & ll) up |= AKS3_LAST_MAT;
-        if ((L.CONS | (L.X & r1)) & ll) up |= AKS3_S1;
-        if (((L.LK & r1) | (L.X & r2)) & ll) up |= AKS3_S2;
-        if (L.FOR & ll) up |= AKS3_LAST_FOR;
+        if ((L.CONS | (L.XI & r1)) & ll) up |= AKS3_S1;
+        if (((L.LK & r1) | (L.XI & r2)) & ll) up |= AKS3_S2;
+        if (L.UNS & ll) up |= AKS3_LAST_UNS;
+        if (L.EP | L.ZW) {
+            const uint32_t p1 = aks3_pict(L, 0u);
+            if ((L.EP | (L.XE & p1)) & ll) up |= AKS3_P1;
+            if (L.ZW & p1 & ll) up |= AKS3_P2;
+        }
+        if (L.RI & ll) {
+            up |= AKS3_LAST_RI;
+            if (!(aks3_ri_odd(L, 0u, 0u) & ll)) up |= AKS3_RI_ODD;       // even before it -> odd with it
+        }
     }
-    // grapheme state: fixed by the last lead that is neither Extend / Linker nor foreign, or by a barrier
+    // grapheme state: fixed by the last lead that is neither transparent for one of the rules (Extend, ZWJ, InCB Extend /
+    // Linker, RI) nor unsupported, or by a barrier
     {
-        const uint32_t sync = (lead & ~L.X & ~L.FOR) | bar;
+        const uint32_t sync = (lead & ~L.X & ~L.XI & ~L.RI & ~L.UNS) | bar;
         if (!sync) up |= AKS3_G_OPEN;
-        else if (L.FOR && akb_clz(L.FOR) <= akb_clz(sync)) up |= AKS3_G_OPEN;      // (a barrier can sit on a foreign lead)
+        else if (L.UNS && akb_clz(L.UNS) <= akb_clz(sync)) up |= AKS3_G_OPEN;      // (a barrier can sit on such a lead)
     }
     // run label at the lane's end: class of the last strong code point, none when a barrier follows it, open when the
-    // lane has neither (or ends in foreign code points)
+    // lane has neither (or ends in unsupported code points)
     {
         const uint32_t strong = L.strong_d | L.strong_r | L.strong_o;
         const uint32_t known = strong | bar;
@@ -171,7 +257,7 @@ AK_HD void aks3_summary(AkS3Lane& L) {
         if (known) {
             const uint32_t top = 0x80000000u >> akb_clz(known);
             lab = (L.strong_d & top) ? 1u : (L.strong_r & top) ? 2u : (L.strong_o & top) ? 3u : 0u;
-            if (L.FOR && akb_clz(L.FOR) <= akb_clz(known)) lab = 7u;
+            if (L.UNS && akb_clz(L.UNS) <= akb_clz(known)) lab = 7u;
         }
         up |= lab << AKS3_LAB_SHIFT;
     }
@@ -183,17 +269,23 @@ AK_HD bool aks3_phase3(AkS3Lane& L, uint32_t up2p, uint32_t tb_bit, bool matras,
     const uint32_t C = L.cont;
     const uint32_t bar = L.rows | ~L.own;
     const uint32_t lead = L.lead;
-    if (L.FOR) return false;
+    if (L.UNS) return false;
     if (!lead && !L.rows) { L.brk = L.rchg = L.PD = L.PR = L.PO = 0; return true; }
     const uint32_t fl = lead & (0u - lead);
     const bool first_at_bar = (fl & bar) != 0u || lead == 0u;
     if (want_c) {
-        if (!first_at_bar && (up2p & (AKS3_LAST_FOR | AKS3_G_OPEN))) return false;
+        if (!first_at_bar && (up2p & (AKS3_LAST_UNS | AKS3_G_OPEN))) return false;
         uint32_t r1, r2;
         aks3_conj(L, (up2p & AKS3_S1) ? 1u : 0u, (up2p & AKS3_S2) ? 1u : 0u, r1, r2);
         const uint32_t p_ctl = akb_fwd(L.CTL | L.CR | L.LF, C, (up2p & AKS3_LAST_CTL) ? 1u : 0u);
         const uint32_t p_cr = akb_fwd(L.CR, C, (up2p & AKS3_LAST_CR) ? 1u : 0u);
-        const uint32_t nobreak = ((L.X | L.SM) & ~p_ctl) | (L.LF & p_cr) | (L.CONS & r2);
+        uint32_t nobreak = ((L.X | L.SM) & ~p_ctl) | (L.LF & p_cr) | (L.CONS & r2);
+        if (L.EP) {                                                          // GB11: ExtPict Extend* ZWJ x ExtPict
+            const uint32_t p1 = aks3_pict(L, (up2p & AKS3_P1) ? 1u : 0u);
+            nobreak |= L.EP & akb_fwd(L.ZW & p1, C, (up2p & AKS3_P2) ? 1u : 0u) & ~bar;
+        }
+        if (L.RI)                                                            // GB12 / GB13: RI pairs
+            nobreak |= L.RI & aks3_ri_odd(L, (up2p & AKS3_LAST_RI) ? 1u : 0u, (up2p & AKS3_RI_ODD) ? 1u : 0u);
         uint32_t brk = lead & ~nobreak;
         if (matras) brk |= (L.MAT | akb_fwd(L.MAT, C, (up2p & AKS3_LAST_MAT) ? 1u : 0u)) & lead;
         L.brk = brk & ~L.rows;

@@ -343,6 +343,7 @@ void hh_seg_fast3(const uint8_t* text, const int64_t* off, int64_t n_rows, uint3
         }
         for (int l = 0; l < NL; ++l) {
             aks3_phase2(lanes[(size_t)l], l + 1 < NL ? lanes[(size_t)l + 1].dn1 : 0u);
+            if (lanes[(size_t)l].FOR) aks3_foreign(T, text, base0 + (w0 - 1 + l) * 32, te, lanes[(size_t)l]);
             aks3_summary(lanes[(size_t)l]);
         }
         for (int l = 1; l <= real; ++l) {

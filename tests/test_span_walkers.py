@@ -308,6 +308,34 @@ def test_segment_bit_parallel_fuzz():
                  '\u0915\u094d' + '\u093c' * 30 + '\u0915', '\r\n' * 40, ''], 30)
 
 
+def test_segment_bit_parallel_emoji_and_flags():
+    """code points outside ASCII / U+0900-097F join the masks from the property table: GB11 (ZWJ sequences), GB12/13 (pairs
+    of regional indicators, also across lanes), variation selectors, accents, other scripts; Hangul / Prepend take the walker"""
+    rng = np.random.default_rng(4)
+    alpha = ['\U0001F600', '\U0001F468', '\U0001F469', '\U0001F467', '\u200d', '\u200d', '\U0001F3FD', '\ufe0f', '\U0001F1EE',
+             '\U0001F1F3', '\U0001F1FA', '\U0001F1F8', '\u2764', '\u2728', 'a', ' ', '\u0915', '\u094d', '\u0937', '\u00e9', '\u0301',
+             '\u200b', '\u00ad', '1', '.', '\u00a9', '\u20e3', '#', '\U0001F3F3', '\U0001F308', '\n', '\r', '\u200c', '\u0995',
+             '\u09cd', '\u09b7', '\u0966', '\u0663']
+
+    def rand_lines(n, max_len, alpha):
+        out = []
+        for _ in range(n):
+            n_ch = int(rng.integers(0, max_len + 1))
+            if rng.random() < 0.5:
+                s = ''.join(alpha[int(i)] for i in rng.integers(0, len(alpha), size=n_ch))
+            else:
+                s = ''
+                while len(s) < n_ch:
+                    s += alpha[int(rng.integers(len(alpha)))] * int(rng.integers(1, 12))
+            out.append(s)
+        return out
+    for max_len, real in [(60, 30), (200, 7), (12, 2)]:
+        assert _seg3_check(rand_lines(1500, max_len, alpha), real) < 0.10
+        _seg3_check(rand_lines(500, max_len, alpha + ['\uac00', '\u1100', '\u1161', '\u0600']), real)          # + unsupported classes
+    raw = sc.Corpus('social', 8).lines(100000)
+    assert _seg3_check(raw, 30) < 0.001                  # emoji, ZWJ families, flags, accents: all in the fast lanes
+
+
 def test_segment_bit_parallel_is_all_fast_on_normalized_text():
     for kind in ('hinglish', 'hindi', 'social'):
         lines = [O.normalize_text(s) for s in sc.Corpus(kind, 8).lines(100000)]
