@@ -192,6 +192,7 @@ struct AkFastNormArgs {
     int64_t* out_off;
     const int64_t* tile_row;     // [n_tiles + 1]: first row r in [0, n_rows] with off[r] >= start of tile k (n_rows + 1 if none)
     int64_t base0;               // 16-byte aligned (as an address) start of tile 0, <= text_begin
+    uint32_t flags;              // AK_NORM_ROMAN | AK_NORM_CLEAN, or AK_NORM_ROMAN alone (clean_hinglish=False; bit-stream kernel only)
 };
 
 // a chunk that straddles the start / end of the text: byte by byte, guarded.  Cold, kept out of line.
@@ -474,6 +475,7 @@ __global__ void __launch_bounds__(AKN3_THREADS, AKN3_MINB) ak_nf3_classify_kerne
     const AkBatch& B = A.B;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t tb = B.text_begin, te = B.text_end;
+    const bool raw = !(A.flags & AK_NORM_CLEAN);
     for (int tile = blockIdx.x; tile < B.n_tiles; tile += gridDim.x) {
         const int64_t tile_start = A.base0 + (int64_t)tile * AKF_TILE;
         const int64_t ws = tile_start + (int64_t)warp * AKN3_WARP_BYTES;
@@ -501,12 +503,12 @@ __global__ void __launch_bounds__(AKN3_THREADS, AKN3_MINB) ak_nf3_classify_kerne
         uint32_t dn1n = __shfl_down_sync(0xFFFFFFFFu, L.dn1, 1);
         if (lane == 0) up1p = 0;
         if (lane == 31) dn1n = 0;
-        akn3_phase2(L, up1p, dn1n);
+        akn3_phase2(L, up1p, dn1n, raw);
         uint32_t up2p = __shfl_up_sync(0xFFFFFFFFu, L.up2, 1);
         uint32_t dn2n = __shfl_down_sync(0xFFFFFFFFu, L.dn2, 1);
         if (lane == 0) up2p = AKN3_HALO_UP2;
         if (lane == 31) dn2n = 0;
-        akn3_phase3(A.T, B.text, cs, te, L, up2p, dn2n);
+        akn3_phase3(A.T, B.text, cs, te, L, up2p, dn2n, raw);
         {
             uint32_t rest = 0;
             if (L.ge) rest = akn3_gaps_local(B.text, cs, te, L);
@@ -588,6 +590,7 @@ struct AkNfSlowArgs {
     int64_t out_cap;
     int64_t* out_off;
     int write;
+    uint32_t flags;
 };
 
 #ifndef AKN_SLOW_MINB
@@ -597,7 +600,7 @@ __global__ void __launch_bounds__(128, AKN_SLOW_MINB) ak_nf_slow_kernel(const Ak
     const AkBatch& B = A.B;
     unsigned int n = *A.W.n_slow;
     if (n > A.W.slow_cap) n = A.W.slow_cap;
-    const uint32_t NFLAGS = AK_NORM_ROMAN | AK_NORM_CLEAN;
+    const uint32_t NFLAGS = A.flags;
     for (unsigned int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
         AkSlowEntry e = A.W.slow[j];
         const int64_t ss = e.pos < B.text_begin ? B.text_begin : e.pos;
@@ -2411,8 +2414,10 @@ static int ak_empty_rows(akshar_ctx* ctx, int64_t* a, int64_t* b, cudaStream_t s
 // normalize_text launch: the fast kernel for the default flags in tile mode, the generic walker kernel otherwise
 static int ak_run_normalize(akshar_ctx* ctx, AkCall& C, const AkBatch& B, uint32_t flags, uint8_t* out, int64_t out_cap,
                             int64_t* out_off) {
-    if (flags == (AK_NORM_ROMAN | AK_NORM_CLEAN) && B.mode == AKSHAR_MODE_TILES && !B.dyn_end) {
+    const bool raw_fast = flags == AK_NORM_ROMAN;            // clean_hinglish=False: bit-stream kernel only
+    if ((flags == (AK_NORM_ROMAN | AK_NORM_CLEAN) || raw_fast) && B.mode == AKSHAR_MODE_TILES && !B.dyn_end) {
         AkFastNormArgs F;
+        F.flags = flags;
         F.B = B;
         F.T = ctx->T;
         F.out = out;
@@ -2437,7 +2442,7 @@ static int ak_run_normalize(akshar_ctx* ctx, AkCall& C, const AkBatch& B, uint32
         W.slow_cap = (unsigned int)(nt * AK_BLOCK / 16 + 1024);
         {
             AkTimed tm(ctx, AKSHAR_TIMER_NORMALIZE_CLASSIFY, C.stream);
-            if (getenv("AKSHAR_NORM_V2"))
+            if (getenv("AKSHAR_NORM_V2") && !raw_fast)
                 ak_nf_classify_kernel<<<ak_grid(ctx, ctx->occ_nf_classify, F.B.n_tiles), AK_BLOCK, 0, C.stream>>>(F, W);
             else
                 ak_nf3_classify_kernel<<<ak_grid(ctx, ctx->occ_nf3, F.B.n_tiles), AKN3_THREADS, 0, C.stream>>>(F, W);
@@ -2452,6 +2457,7 @@ static int ak_run_normalize(akshar_ctx* ctx, AkCall& C, const AkBatch& B, uint32
         S.out_cap = out_cap;
         S.out_off = out_off;
         S.write = 0;
+        S.flags = flags;
         const int slow_grid = ctx->sm_count * AKN_SLOW_MINB;      // latency bound: as many walkers in flight as fit
         ak_nf_slow_kernel<<<slow_grid, 128, 0, C.stream>>>(S);
         if ((rc = ak_after_launch(ctx, "normalize-slow-count"))) return rc;

@@ -109,7 +109,9 @@ AK_HD void akn3_phase1(const uint32_t* x, AkN3Lane& L) {
 
 // ---- phase 2: byte comparisons, look-ahead roles, code-point classes ------------------------------------------
 // up1p = the previous lane's up1, dn1n = the next lane's dn1
-AK_HD void akn3_phase2(AkN3Lane& L, uint32_t up1p, uint32_t dn1n) {
+// raw = normalize_text(clean_hinglish=False): NFC + Roman lowercase only -- nothing is dropped, nothing collapses, so every
+// lead is kept and E stays empty; the trouble logic is the same
+AK_HD void akn3_phase2(AkN3Lane& L, uint32_t up1p, uint32_t dn1n, bool raw = false) {
     uint32_t q1 = 0xFFFFFFFFu, q3 = 0xFFFFFFFFu;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
@@ -137,7 +139,7 @@ AK_HD void akn3_phase2(AkN3Lane& L, uint32_t up1p, uint32_t dn1n) {
     L.MARK = L.NK | L.VIAC | L.QNBT;
     L.INERT = (d4 | d5) & ~L.MARK & ~(d4 & ni_2);
     L.loopm = (L.LXo | (L.E0b & ~L.D3) | (L.F0b & ~x9f_1)) & own;
-    L.KL = L.K | L.D3;
+    L.KL = raw ? L.lead : (L.K | L.D3);
     L.DROP = L.lead & ~L.KL;
     L.up2 = akb_at_last(L.INERT, L.lead) | (akb_at_last(L.AC, L.lead) << 1) | (akb_at_last(L.DROP, L.lead) << 2);
     L.dn2 = q3 & 3u;
@@ -155,11 +157,12 @@ AK_HD uint32_t akn3_cp_bytes(const uint8_t* t, int64_t pos, int64_t te) {
 
 // ---- phase 3: E between adjacent code points, the loop class, trouble bits, gap ends ---------------------------
 // up2p / dn2n: neighbours' words; cs = absolute position of byte 0
-AK_HD void akn3_phase3(const AkTables& Tb, const uint8_t* text, int64_t cs, int64_t te, AkN3Lane& L, uint32_t up2p, uint32_t dn2n) {
+AK_HD void akn3_phase3(const AkTables& Tb, const uint8_t* text, int64_t cs, int64_t te, AkN3Lane& L, uint32_t up2p, uint32_t dn2n,
+                       bool raw = false) {
     const uint32_t C = L.cont;
     {
         const uint32_t q3 = L.Q3;
-        L.E = ((L.K & L.Q1) | (L.D3 & q3 & akb_fsr(q3, dn2n, 1) & akb_fsr(q3, dn2n, 2))) & ~L.rows & ~L.NL;
+        L.E = raw ? 0u : ((L.K & L.Q1) | (L.D3 & q3 & akb_fsr(q3, dn2n, 1) & akb_fsr(q3, dn2n, 2))) & ~L.rows & ~L.NL;
     }
     uint32_t flags = 0;
     uint32_t XT = 0;
@@ -172,14 +175,14 @@ AK_HD void akn3_phase3(const AkTables& Tb, const uint8_t* text, int64_t cs, int6
         const uint32_t w = ak_props(Tb, cp);
         // not plain, or kept / turned into something kept (U+0130 -> i): the walker's business, and -- like a T bit --
         // the neighbours must not read this lane's kept code points as bytes
-        if (!AK_NFC_HEAD(w) || AK_LATIN_LOWER(w) || AK_ALLOW(w)) XT |= 1u << i;
+        if (!AK_NFC_HEAD(w) || AK_LATIN_LOWER(w) || (!raw && AK_ALLOW(w))) XT |= 1u << i;
     }
     const uint32_t p_inert = akb_fwd(L.INERT, C, up2p & 1u) & ~L.rows;
     const uint32_t p_ac = akb_fwd(L.AC, C, (up2p >> 1) & 1u) & ~L.rows;
     L.MARK |= XT;
     L.T = ((L.QNBT | (L.NK & ~p_inert) | (L.VIAC & p_ac)) & L.own) | XT;
     // kept code points right after a dropped stretch (same row): compared with the kept one before the stretch
-    L.ge = L.KL & akb_fwd(L.DROP, C, (up2p >> 2) & 1u) & ~L.rows & ~L.NL;
+    L.ge = raw ? 0u : (L.KL & akb_fwd(L.DROP, C, (up2p >> 2) & 1u) & ~L.rows & ~L.NL);
     L.flags = flags;
 }
 

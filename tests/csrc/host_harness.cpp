@@ -209,14 +209,15 @@ void hh_n3_planes(const uint8_t* b, uint32_t* P) {
     akb_planes(x, P);
 }
 
-int64_t hh_fast_normalize3(const uint8_t* text, const int64_t* off, int64_t n_rows, int real, uint8_t* out, int64_t* out_off,
-                           uint32_t* status, int64_t* n_slow) {
+int64_t hh_fast_normalize3(const uint8_t* text, const int64_t* off, int64_t n_rows, int real, uint32_t nflags, uint8_t* out,
+                           int64_t* out_off, uint32_t* status, int64_t* n_slow) {
     AkTables T = host_tables();
     const int64_t tb = off[0], te = off[n_rows], base0 = tb;
     std::vector<uint8_t> rowstart((size_t)(te - base0) + 128, 0);
     for (int64_t r = 0; r <= n_rows; ++r) rowstart[(size_t)(off[r] - base0)] = 1;
     const int64_t n_lanes = (te - base0 + 1 + 31) / 32;
-    const uint32_t NFLAGS = AK_NORM_ROMAN | AK_NORM_CLEAN;
+    const uint32_t NFLAGS = nflags;
+    const bool raw = !(nflags & AK_NORM_CLEAN);
     int64_t base = 0, row = 0, slow_cnt = 0;
     uint32_t st = 0;
     const int NL = real + 2;
@@ -237,12 +238,12 @@ int64_t hh_fast_normalize3(const uint8_t* text, const int64_t* off, int64_t n_ro
         }
         for (int l = 0; l < NL; ++l) {
             const uint32_t up1p = l > 0 ? lanes[(size_t)l - 1].up1 : 0u;
-            akn3_phase2(lanes[(size_t)l], up1p, l + 1 < NL ? lanes[(size_t)l + 1].dn1 : 0u);
+            akn3_phase2(lanes[(size_t)l], up1p, l + 1 < NL ? lanes[(size_t)l + 1].dn1 : 0u, raw);
         }
         for (int l = 0; l < NL; ++l) {
             const int64_t cs = base0 + (w0 - 1 + l) * 32;
             // lane 0 has no left neighbour: conservative carries (previous not inert, previous an accent, previous dropped)
-            akn3_phase3(T, text, cs, te, lanes[(size_t)l], l > 0 ? lanes[(size_t)l - 1].up2 : AKN3_HALO_UP2, l + 1 < NL ? lanes[(size_t)l + 1].dn2 : 0u);
+            akn3_phase3(T, text, cs, te, lanes[(size_t)l], l > 0 ? lanes[(size_t)l - 1].up2 : AKN3_HALO_UP2, l + 1 < NL ? lanes[(size_t)l + 1].dn2 : 0u, raw);
             rest[(size_t)l] = akn3_gaps_local(text, cs, te, lanes[(size_t)l]);
             lastk[(size_t)l] = akn3_last_kept(text, cs, te, lanes[(size_t)l]);
         }

@@ -188,6 +188,25 @@ def test_bit_parallel_lane_structure(real):
     assert out.tobytes() == exp.tobytes()
 
 
+@pytest.mark.parametrize('real', [30, 3])
+def test_bit_parallel_raw_mode(real):
+    """normalize_text(clean_hinglish=False) through the same lanes: NFC + Roman lowercase, nothing dropped or collapsed"""
+    lines = list(_lines()) + ['\u0130x', '\u00c9a', 'AAA\U0001F600aaa']
+    data, off = sc.pack(lines)
+    exp, exp_off = OB.normalize_batch(lines, True, False)
+    out, out_off, st, n_slow = W.fast_normalize3(data, off, real=real, flags=1)
+    assert st == 0
+    assert np.array_equal(out_off, exp_off)
+    assert out.tobytes() == exp.tobytes()
+    for kind in ('hinglish', 'social'):
+        lines = sc.Corpus(kind, 8).lines(100000)
+        data, off = sc.pack(lines)
+        exp, exp_off = OB.normalize_batch(lines, True, False)
+        out, out_off, st, n_slow = W.fast_normalize3(data, off, real=real, flags=1)
+        assert st == 0 and np.array_equal(out_off, exp_off) and out.tobytes() == exp.tobytes()
+        assert n_slow / (data.size / 16) < 0.02
+
+
 def test_bit_parallel_fuzz():
     """alphabets that keep most lanes fast: elongations across dropped stretches, row starts everywhere, rare trouble"""
     alpha = ['a', 'A', 'e', ' ', ' ', '\U0001F600', '\u0915', '\u093e', '\u094d', '\n', '!', '#', 'x', '\u0921', '\u0950',

@@ -152,7 +152,7 @@ def fast_normalize(data, off, real=30):
     return out[:n], out_off, st.value, ns.value
 
 
-def fast_normalize3(data, off, real=30):
+def fast_normalize3(data, off, real=30, flags=7):
     """normalize_text (default flags) through the bit-parallel kernel's lane / exchange / slow-lane structure"""
     data = np.ascontiguousarray(data, dtype=np.uint8)
     off = np.ascontiguousarray(off, dtype=np.int64)
@@ -160,7 +160,7 @@ def fast_normalize3(data, off, real=30):
     out_off = np.full(off.size, -1, dtype=np.int64)
     st = ctypes.c_uint32(0)
     ns = ctypes.c_int64(0)
-    n = lib().hh_fast_normalize3(_p(data), _p(off), ctypes.c_int64(off.size - 1), ctypes.c_int(real), _p(out), _p(out_off),
+    n = lib().hh_fast_normalize3(_p(data), _p(off), ctypes.c_int64(off.size - 1), ctypes.c_int(real), ctypes.c_uint32(flags), _p(out), _p(out_off),
                                  ctypes.byref(st), ctypes.byref(ns))
     return out[:n], out_off, st.value, ns.value
 
