@@ -83,8 +83,10 @@ def main():
     with open(os.path.join(REF, 'data', 'corpus.txt'), encoding='utf-8') as f:
         inputs += [l.strip() for l in f if l.strip()]
     inputs += sc.adversarial(1200, 7, 40)
-    for kind in ('hinglish', 'hindi', 'social'):
-        inputs += sc.Corpus(kind, 9).lines(40000)
+    # seeded corpus lines: >= 1000 rows per model of text that is in-vocabulary for the 24k models (the lexicon is fixed,
+    # tools/synth_corpus.py LEXICON_SEED; the corpus seed only draws sentences), plus social noise
+    for kind, nbytes in (('hinglish', 200000), ('hindi', 290000), ('social', 60000)):
+        inputs += sc.Corpus(kind, 9).lines(nbytes)
     # a few long rows for the chunked lanes
     inputs.append(' '.join(sc.Corpus('social', 10).lines(30000)))
     inputs.append(''.join(sc.adversarial(300, 8, 40)))
@@ -124,6 +126,16 @@ def main():
         r['pieces_bpe24k'] = toks['bpe24k'].tokenize(s)
         r['dec_bpe24k'] = toks['bpe24k'].decode(r['ids_bpe24k'])
         r['dec_spm24k'] = toks['spm24k'].decode(r['ids_spm24k'])
+        # detokenize (tokenizer.py:221-246), tokenize(return_metadata) / explain values (tokenizer.py:123-165, 248-276)
+        r['detok_bpe24k'] = toks['bpe24k'].detokenize(r['pieces_bpe24k'])
+        r['detok_spm24k'] = toks['spm24k'].detokenize(r['pieces_spm24k'])
+        r['detok_akshar'] = fallback.detokenize(r['tokenize'])
+        r['meta'] = fallback.tokenize(s, return_metadata=True)
+        r['explain_bpe24k'] = toks['bpe24k'].explain(s)
+        # word tokenizers (segment.py:239-401)
+        r['words_hi'] = RS.word_tokenize_hindi(s)
+        r['words_sa'] = RS.word_tokenize_sanskrit(s)
+        r['words_auto'] = RS.word_tokenize(s)
         rows.append(r)
     sig = {w: RN.roman_phonetic_signature(w) for w in SIG_WORDS}
     words = set()

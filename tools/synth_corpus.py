@@ -90,8 +90,16 @@ class Lexicon:
         self.bytes = np.frombuffer(b''.join(enc), dtype=np.uint8)
 
 
-def _build(kind, seed):
-    rng = np.random.default_rng(seed)
+# The LEXICON is a property of the language, not of a corpus draw: it is always built from these seeds -- the ones the
+# 24k models under tests/golden/models were trained with (tools/make_golden.py: hinglish 101, hindi 102) -- so that every
+# corpus, whatever its own seed, is in-vocabulary for them the way real text is for a model trained on the same language.
+# (`social` shares the hinglish base words: the same generator calls in the same order, then the noisy variants.)
+# A corpus seed only decides which words are drawn and how the sentences are put together.
+LEXICON_SEED = {'hinglish': 101, 'social': 101, 'hindi': 102}
+
+
+def _build(kind, seed=None):
+    rng = np.random.default_rng(LEXICON_SEED[kind] if seed is None else seed)
     nd, nr = (60000, 40000)
     if kind == 'hindi':
         dev = [_dev_word(rng, vedic=True, nukta_p=0.03) for _ in range(nd)]
@@ -119,7 +127,7 @@ class Corpus:
         assert kind in ('hinglish', 'hindi', 'social')
         self.kind = kind
         self.seed = seed
-        self.dev, self.rom, self.extra = _build(kind, seed)
+        self.dev, self.rom, self.extra = _build(kind)
         self.suf = Lexicon.__new__(Lexicon)
         self.suf.n = len(_SUFFIX)
         self.suf.len = np.array([len(s) for s in _SUFFIX], dtype=np.int64)
