@@ -10,17 +10,20 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get('AKSHAR_B200_LIB') or os.path.join(_HERE, 'lib', 'libakshar_b200.so')
 
 OK, E_ARG, E_CUDA, E_MODEL, E_NOMODEL, E_WORKSPACE = 0, -1, -2, -3, -4, -5
-ST_OVERFLOW, ST_NFC_SEGMENT, ST_PATHOLOGICAL, ST_ALPHABET, ST_SPIN, ST_WORD = 1, 2, 4, 8, 16, 32
+ST_OVERFLOW, ST_NFC_SEGMENT, ST_PATHOLOGICAL, ST_ALPHABET, ST_SPIN, ST_WORD, ST_INTERNAL = 1, 2, 4, 8, 16, 32, 64
 NORM_ROMAN, NORM_FILTER, NORM_COLLAPSE, NORM_CLEAN, NORM_NO_NFC = 1, 2, 4, 6, 8
 SEG_CLUSTERS, SEG_MATRAS, SEG_RUNS = 1, 2, 4
 MODE_TILES, MODE_ROWS = 0, 1
-TIMERS = {'ak_nf3_classify_kernel': 0, 'ak_nf_write_kernel': 1, 'ak_bf3_encode_kernel': 2, 'ak_sf3_kernel': 3, 'ak_unigram_kernel': 4}
+OUT_IDS_U16, OUT_SPLITS_I32 = 1, 2
+TIMERS = {'ak_nf3_classify_kernel': 0, 'ak_nf_write_kernel': 1, 'ak_resolve_kernel<bpe>': 2, 'ak_sf3_kernel': 3,
+          'ak_resolve_kernel<unigram>': 4, 'ak_words_kernel': 5, 'ak_emit_kernel': 6}
 
 SYMBOLS = (
     'akshar_version', 'akshar_status_str', 'akshar_ctx_create', 'akshar_ctx_destroy', 'akshar_last_error',
     'akshar_workspace_bytes', 'akshar_normalize_batch', 'akshar_segment_batch', 'akshar_signature_batch',
     'akshar_load_bpe_json', 'akshar_load_spm_model', 'akshar_vocab_size', 'akshar_vocab_token',
-    'akshar_encode_bpe_batch', 'akshar_encode_unigram_batch', 'akshar_tokenizer_encode_batch', 'akshar_launch_count', 'akshar_timing_enable', 'akshar_timing_read', 'akshar_word_cache_hold',
+    'akshar_encode_bpe_batch', 'akshar_encode_unigram_batch', 'akshar_tokenizer_encode_batch', 'akshar_tokenizer_encode_batch_ex',
+    'akshar_launch_count', 'akshar_timing_enable', 'akshar_timing_read', 'akshar_word_cache_hold',
 )
 
 _lib = None
@@ -62,6 +65,7 @@ def load():
     L.akshar_encode_bpe_batch.argtypes = [vp, vp, vp, i64, i64, i64, i32, vp, i64, vp, vp, vp, sz, vp]
     L.akshar_encode_unigram_batch.argtypes = [vp, vp, vp, i64, i64, i64, i32, vp, i64, vp, vp, vp, sz, vp]
     L.akshar_tokenizer_encode_batch.argtypes = [vp, vp, vp, i64, i64, i64, u32, i32, i32, vp, i64, vp, vp, i64, vp, vp, vp, sz, vp]
+    L.akshar_tokenizer_encode_batch_ex.argtypes = [vp, vp, vp, i64, i64, i64, u32, i32, i32, vp, i64, vp, vp, i64, vp, u32, vp, vp, sz, vp]
     L.akshar_timing_enable.argtypes = [vp, i32]
     L.akshar_word_cache_hold.argtypes = [vp, i32]
     L.akshar_timing_read.argtypes = [vp, i32, c.POINTER(c.c_float)]

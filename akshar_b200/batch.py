@@ -53,7 +53,8 @@ class BatchStatusError(RuntimeError):
         self.bits = bits
         names = [n for b, n in ((C.ST_OVERFLOW, 'overflow'), (C.ST_NFC_SEGMENT, 'combining sequence longer than 64'),
                                 (C.ST_PATHOLOGICAL, 'look-back limit'), (C.ST_ALPHABET, 'code point outside the closed alphabet'),
-                                (C.ST_SPIN, 'tile-prefix spin limit'), (C.ST_WORD, 'word longer than the scratch pool')) if bits & b]
+                                (C.ST_SPIN, 'tile-prefix spin limit'), (C.ST_WORD, 'word longer than the scratch pool'),
+                                (C.ST_INTERNAL, 'internal consistency check (bits 0x%x)' % bits)) if bits & b]
         super().__init__('%s: %s' % (what, ', '.join(names)))
 
 
@@ -112,6 +113,17 @@ class Engine:
 
     MAX_TRIES = 5
 
+    def _slot_extra(self, n_bytes):
+        """workspace beyond the minimum that gives every 960-byte warp tile the event slots the last call asked for
+        (half of a surplus goes to the slots, 20 bytes each; include/akshar_b200.h)"""
+        need = getattr(self, '_slots_needed', 0)
+        if need <= 256:
+            return 0
+        cap = 512
+        while cap < need:
+            cap *= 2                        # slots per warp tile are a power of two
+        return 2 * (n_bytes // 960 + 4) * 21 * (cap - 256) + (1 << 20)
+
     @staticmethod
     def _stream():
         return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
@@ -149,6 +161,7 @@ class Engine:
             return None
         r = result.cpu()
         bits = int(r[2])
+        self._slots_needed = int(r[3])        # encoders: event slots per 960 text bytes that were needed (on overflow)
         return int(r[0]), int(r[1]), bits
 
     # ------------------------------------------------------------------ K1
@@ -310,7 +323,7 @@ class Engine:
                 continue
             if bits & C.ST_OVERFLOW:
                 cap = max(cap, total)
-                ws = self._workspace(b.n_bytes, b.n_rows, extra=4 * total + (1 << 16))
+                ws = self._workspace(b.n_bytes, b.n_rows, extra=max(ws.numel() - self.lib.akshar_workspace_bytes(b.n_bytes, b.n_rows), self._slot_extra(b.n_bytes)))
                 continue
             if bits:
                 raise BatchStatusError(bits, what)
@@ -321,9 +334,9 @@ class Engine:
         """Tokenizer.encode(norm).ids over ALREADY NORMALIZED rows (reference tokenizer.py:193) -> Ragged int32 ids"""
         return self._encode(self.lib.akshar_encode_bpe_batch, 'encode_bpe_batch', batch, mode, capacity, check)
 
-    def encode_unigram_batch(self, batch, capacity=None, check=True):
+    def encode_unigram_batch(self, batch, mode=C.MODE_TILES, capacity=None, check=True):
         """SentencePieceProcessor.EncodeAsIds(norm) over ALREADY NORMALIZED rows (reference tokenizer.py:191)"""
-        return self._encode(self.lib.akshar_encode_unigram_batch, 'encode_unigram_batch', batch, C.MODE_ROWS, capacity, check)
+        return self._encode(self.lib.akshar_encode_unigram_batch, 'encode_unigram_batch', batch, mode, capacity, check)
 
 
     def tokenizer_encode_batch(self, batch, kind, normalize_roman=True, clean_hinglish=True, mode=C.MODE_TILES,
@@ -365,7 +378,7 @@ class Engine:
                 if nbytes > ncap:
                     ncap = nbytes
                     cap = max(cap, (ncap >> 1) + 2 * b.n_rows + 1024)
-                ws = self._workspace(ncap, b.n_rows, extra=4 * max(cap, total) + (1 << 16))
+                ws = self._workspace(ncap, b.n_rows, extra=max(ws.numel() - self.lib.akshar_workspace_bytes(ncap, b.n_rows), self._slot_extra(ncap)))
                 continue
             if bits:
                 raise BatchStatusError(bits, 'tokenizer_encode_batch')
@@ -492,7 +505,7 @@ class Engine:
                 if rc != 0:
                     self.lib.akshar_word_cache_hold(self._h, 0)
                     self._err(rc, 'akshar_tokenizer_encode_batch')
-                if k == 0 and kind == 0:
+                if k == 0:
                     # the chunks are ONE batch: the ones that follow keep the words this one added to the cache
                     self.lib.akshar_word_cache_hold(self._h, 1)
                 S['ev_comp'].record(s_comp)

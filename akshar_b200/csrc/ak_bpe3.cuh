@@ -10,6 +10,7 @@
 #pragma once
 #include "ak_bits.cuh"
 #include "ak_text_core.cuh"
+#include "ak_subword.cuh"
 
 struct AkB3Lane {
     uint32_t own, rows;
@@ -120,3 +121,39 @@ AK_HD void akb3_phase3(AkB3Lane& L, uint32_t up2p) {
     const uint32_t p_ac = akb_fwd(L.AC, C, (up2p >> 4) & 1u) & ~L.rows;
     L.trb = (L.QN | (L.NK & ~p_inert) | (L.VIAC & p_ac)) & L.own;
 }
+
+// exact NFC check of the troubled code points (cold): does NFC change the text?
+AK_HD_NOINLINE bool akb3_changes(const AkTables& T, const uint8_t* text, const int64_t* off, int64_t n_rows, int64_t r_lo,
+                                          uint32_t trb, int64_t cs, uint32_t& status) {
+    bool changed = false;
+    int64_t checked_until = -1;
+    while (trb) {
+        const int i = akb_ctz(trb);
+        trb &= trb - 1u;
+        const int64_t p = cs + i;
+        if (p < checked_until) continue;
+        const int64_t r = ak_row_lower_bound(off, r_lo, n_rows, p + 1);
+        const int64_t rs = off[r - 1], re = off[r];
+        if (ak_segment_changes(T, text, p, rs, re, 4096, &checked_until, status)) changed = true;
+    }
+    return changed;
+}
+
+// end of a word of class k with no boundary before `from` (cold: words longer than 64 bytes)
+AK_HD_NOINLINE int64_t akb3_scan_end(const AkTables& T, const uint8_t* t, int64_t wpos, int64_t from, uint32_t k,
+                                              const int64_t* off, int64_t n_rows, int64_t r_lo, int64_t r_hi) {
+    int64_t er = ak_row_lower_bound(off, r_lo, r_hi, wpos + 1);
+    if (off[er] < wpos + 1) er = ak_row_lower_bound(off, r_hi, n_rows, wpos + 1);
+    const int64_t re = off[er];
+    int64_t q = from;
+    if (q > re) q = re;
+    while (q < re && (t[q] & 0xC0u) == 0x80u) ++q;
+    while (q < re) {
+        int len;
+        const uint32_t cp = ak_decode(t, q, re, len);
+        if (AK_HFCLASS(ak_props(T, cp)) != k) break;
+        q += len;
+    }
+    return q;
+}
+

@@ -10,6 +10,7 @@
 
 #define AK_BPE_DIRECT 0x0A00
 #define AK_EMPTY_KEY 0xFFFFFFFFFFFFFFFFull
+#define AK_MAX_TOKEN_ID (1 << 24)      // ids index host vectors and device tables
 
 namespace {
 
@@ -222,9 +223,15 @@ std::string ak_parse_bpe_json(const char* json, size_t len, AkBpeHost& out) {
     if (!vocab || vocab->kind != JVal::Obj || !merges || merges->kind != JVal::Arr) return "tokenizer JSON: vocab / merges missing";
     std::unordered_map<std::string, int32_t> v2i;
     int32_t max_id = -1;
+    // ids index host vectors and device tables: integral, non-negative, bounded -- anything else is a malformed model
+    auto id_of = [](const JVal& v, int32_t& id) -> bool {
+        if (v.kind != JVal::Num || !(v.num >= 0.0) || v.num > (double)AK_MAX_TOKEN_ID || v.num != (double)(int64_t)v.num) return false;
+        id = (int32_t)v.num;
+        return true;
+    };
     for (auto& kv : vocab->obj) {
-        if (kv.second.kind != JVal::Num) return "tokenizer JSON: vocab id is not a number";
-        int32_t id = (int32_t)kv.second.num;
+        int32_t id;
+        if (!id_of(kv.second, id)) return "tokenizer JSON: vocab id is not an integer in [0, 2^24]";
         v2i[kv.first] = id;
         if (id > max_id) max_id = id;
     }
@@ -234,9 +241,10 @@ std::string ak_parse_bpe_json(const char* json, size_t len, AkBpeHost& out) {
             for (auto& a : added->arr) {
                 const JVal* c = a.get("content");
                 const JVal* i = a.get("id");
-                if (!c || !i || c->kind != JVal::Str || i->kind != JVal::Num) return "tokenizer JSON: bad added_tokens entry";
-                specials.emplace_back(c->str, (int32_t)i->num);
-                if ((int32_t)i->num > max_id) max_id = (int32_t)i->num;
+                int32_t id;
+                if (!c || !i || c->kind != JVal::Str || !id_of(*i, id)) return "tokenizer JSON: bad added_tokens entry";
+                specials.emplace_back(c->str, id);
+                if (id > max_id) max_id = id;
             }
     }
     out.id_to_token.assign((size_t)max_id + 1, "");
@@ -316,7 +324,8 @@ std::string ak_parse_bpe_json(const char* json, size_t len, AkBpeHost& out) {
             if (!ent) return false;
             const JVal* ids = ent->get("ids");
             if (!ids || ids->kind != JVal::Arr || ids->arr.size() != 1) return false;
-            id = (int32_t)ids->arr[0].num;
+            // the template's ids are emitted as they are: they must name tokens of this vocabulary
+            if (!id_of(ids->arr[0], id) || id > max_id || out.id_to_token[(size_t)id].empty()) return false;
             return true;
         };
         if (seq_at == 1 && !special_id(single->arr[0], out.bos)) return "unsupported TemplateProcessing layout";

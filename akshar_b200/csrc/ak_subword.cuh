@@ -300,7 +300,9 @@ AK_HD uint32_t ak_uni_next(const AkUniDev& U, const uint8_t* t, int64_t& q, int6
 
 // forward Viterbi of one row; back[1..n] receives the final back-pointer of each position:
 //   UNK edge: AK_UNI_UNKBIT | code point;  piece edge: (len << 24) | piece id.  Returns n (0 for an empty row).
-AK_HD_NOINLINE int64_t ak_unigram_forward(const AkUniDev& U, const uint8_t* t, int64_t rs, int64_t re, uint32_t* back) {
+// mark_byte / mark_index: *mark_index receives the lattice position of the code point that starts at byte mark_byte.
+AK_HD_NOINLINE int64_t ak_unigram_forward(const AkUniDev& U, const uint8_t* t, int64_t rs, int64_t re, uint32_t* back,
+                                          int64_t mark_byte = -1, int64_t* mark_index = nullptr) {
     int64_t ts = rs, te = re;
     if (U.flags & 2) {
         while (ts < te && t[ts] == 0x20u) ++ts;
@@ -324,6 +326,7 @@ AK_HD_NOINLINE int64_t ak_unigram_forward(const AkUniDev& U, const uint8_t* t, i
     for (;;) {
         const bool at_dummy = dummy && i == 0;
         if (!at_dummy && cur >= te) break;
+        if (!at_dummy && cur == mark_byte && mark_index) *mark_index = i;
         if (i > 0) back[i] = bk[i & (AK_UNI_RING - 1)];
         const float bi = best[i & (AK_UNI_RING - 1)];
         // the slot that position i + RING - 1 will use is free from now on

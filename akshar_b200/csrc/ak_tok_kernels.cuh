@@ -1,0 +1,447 @@
+// Kernels of the event-stream subword encoders (cores and rationale: ak_tok.cuh).  Included by ak_kernels.cu after the
+// common kernel plumbing (ak_common.cuh: AkBatch, ak_batch_begin, akn3_lane_rows, akn3_load_edge).
+//
+//   ak_words_kernel<KIND>      text -> event slots              (KIND 0: HF Whitespace pre-tokenizer, 1: SentencePiece words)
+//   ak_rowfix_kernel           exotic rows -> exact ids in a side pool, their word events struck out
+//   ak_resolve_kernel<KIND>    event slot -> resolved record (word cache look-up, exact encoder on a miss)
+//   ak_unicheck_kernel         Unigram: which cached word lattices need the exact Viterbi of their row
+//   ak_emit_kernel             resolved records -> ids + row splits at their final place
+#pragma once
+
+#define AKT_WARP_BYTES 960                             // text bytes per warp tile (30 lanes x 32 bytes)
+#define AKW_THREADS 128                                // words kernel: four independent warps
+#define AKR_THREADS 256                                // resolve kernel
+#define AKL_THREADS 256                                // check / emit kernels
+#define AKL_PER 4                                      // slots per thread
+#define AKL_TILE (AKL_THREADS * AKL_PER)               // 1024 slots per CTA tile
+#define AKT_LONG_ROW 8192                              // Unigram: longer rows go to the exact row encoder
+
+// event slots: warp tile w owns slots [w * cap, (w + 1) * cap), the first count[w] of them hold its events in text order
+struct AkSlots {
+    AkEvent* ev;
+    uint32_t* count;
+    int cap;                           // a power of two >= 256: slot -> warp tile is a shift
+    int shift;                         // log2(cap)
+};
+
+__device__ __forceinline__ long long akt_n_wt(const AkBatch& B, int64_t base0) {
+    return (B.text_end - base0 + AKT_WARP_BYTES) / AKT_WARP_BYTES;      // covers position text_end itself
+}
+
+// The word cache lives as long as its model (like HF's): words learned in one call serve the next.  It has no eviction,
+// so once the entries added since the last restore pass `limit` the pristine image (built at model load) is copied back
+// over it at the start of a call -- decided on the device, no host synchronisation.  force != 0 restores unconditionally.
+__global__ void ak_cache_guard_kernel(unsigned long long* work, const unsigned long long* image, size_t n_words,
+                                      const unsigned long long* inserted, unsigned long long limit, int force) {
+    if (!force && *inserted <= limit) return;
+    const size_t n2 = n_words / 2;
+    const ulonglong2* src = reinterpret_cast<const ulonglong2*>(image);
+    ulonglong2* dst = reinterpret_cast<ulonglong2*>(work);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (size_t)gridDim.x * blockDim.x) dst[i] = src[i];
+}
+__global__ void ak_cache_guard_reset_kernel(unsigned long long* inserted, unsigned long long limit, int force) {
+    if (force || *inserted > limit) *inserted = 0ull;
+}
+
+// =================================================================================================================
+// words kernel
+// =================================================================================================================
+struct AkWordsArgs {
+    AkBatch B;
+    AkTables T;
+    const int64_t* wrow;               // first row at or after base0 + 480 k
+    int64_t base0;
+    AkSlots S;
+    uint8_t* row_flag;                 // per row: 1 = exotic (encoded by the row-fix kernel)
+    unsigned int* any_flag;
+    uint32_t* row_ev;                  // [n_rows + 1] slot of the event that starts the row
+    long long* n_wt_out;               // number of warp tiles (for the scans over the per-warp-tile aggregates)
+};
+
+// end of a word with no boundary within what the warp knows (cold)
+template <int KIND>
+struct AkScanEnd {
+    const AkTables* T;
+    const uint8_t* text;
+    const int64_t* off;
+    int64_t n_rows, cs;
+    uint32_t cw;
+    __device__ int64_t operator()(int64_t p, int64_t from) const {
+        if (KIND == 0) return akb3_scan_end(*T, text, p, from, (cw >> (int)(p - cs)) & 1u, off, n_rows, 0, n_rows);
+        // SentencePiece word: up to the next space or the end of the row
+        const int64_t er = ak_row_lower_bound(off, 0, n_rows, p + 1);
+        const int64_t re = off[er];
+        int64_t q = from > re ? re : from;
+        while (q < re && text[q] != 0x20u) ++q;
+        return q;
+    }
+};
+
+#ifndef AKW_MINB
+#define AKW_MINB 8
+#endif
+template <int KIND>
+__global__ void __launch_bounds__(AKW_THREADS, AKW_MINB) ak_words_kernel(const AkWordsArgs A) {
+    AkBatch B = A.B;
+    if (!ak_batch_begin(B)) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t tb = B.text_begin, te = B.text_end;
+    const long long n_wt = akt_n_wt(B, A.base0);
+    if (blockIdx.x == 0 && threadIdx.x == 0) *A.n_wt_out = n_wt;
+    uint32_t st = 0;
+    for (long long wt = (long long)blockIdx.x * (AKW_THREADS / 32) + warp; wt < n_wt; wt += (long long)gridDim.x * (AKW_THREADS / 32)) {
+        const int64_t ws0 = A.base0 + wt * AKT_WARP_BYTES;
+        const int64_t cs = ws0 + (int64_t)(lane - 1) * 32;
+        const int64_t r_w0 = A.wrow[2 * wt];
+        uint32_t x[8];
+        uint32_t own;
+        {
+            int64_t lo = tb - cs, hi = te - cs;
+            lo = lo < 0 ? 0 : (lo > 32 ? 32 : lo);
+            hi = hi < 0 ? 0 : (hi > 32 ? 32 : hi);
+            if (lo == 0 && hi == 32) {
+                const uint4 v0 = *reinterpret_cast<const uint4*>(B.text + cs);
+                const uint4 v1 = *reinterpret_cast<const uint4*>(B.text + cs + 16);
+                x[0] = v0.x; x[1] = v0.y; x[2] = v0.z; x[3] = v0.w;
+                x[4] = v1.x; x[5] = v1.y; x[6] = v1.z; x[7] = v1.w;
+                own = 0xFFFFFFFFu;
+            } else {
+                akn3_load_edge(B.text, cs, (int)lo, (int)hi, x);
+                own = hi > lo ? ((hi == 32 ? 0xFFFFFFFFu : ((1u << hi) - 1u)) & ~((1u << lo) - 1u)) : 0u;
+            }
+        }
+        const uint32_t rows = akn3_lane_rows(B.off, B.n_rows, r_w0, ws0, lane);
+        const bool real = lane >= 1 && lane <= 30;
+        const int64_t ss = cs < tb ? tb : cs;
+        const int64_t se = cs + 32 > te + 1 ? te + 1 : cs + 32;
+        const bool active = real && ss < se;
+        // index of the first row that starts at or after this lane's first position
+        int64_t nr;
+        {
+            const int mine = real ? __popc(rows) : 0;
+            int inc = mine;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int y = __shfl_up_sync(0xFFFFFFFFu, inc, d);
+                if (lane >= d) inc += y;
+            }
+            nr = r_w0 + (inc - mine);
+            if (active) while (nr <= B.n_rows && B.off[nr] < ss) ++nr;
+        }
+        uint32_t rowsm, wstart, cw, bnd, nb1, nb2;
+        if (KIND == 0) {
+            AkB3Lane L;
+            L.own = own;
+            L.rows = rows;
+            akb3_phase1(x, L);
+            uint32_t dn1n = __shfl_down_sync(0xFFFFFFFFu, L.dn1, 1);
+            if (lane == 31) dn1n = 0;
+            akb3_phase2(L, dn1n);
+            if (L.FOR) akb3_foreign(A.T, B.text, cs, te, L);
+            akb3_summary(L);
+            const uint32_t up2p = __shfl_up_sync(0xFFFFFFFFu, L.up2, 1);
+            akb3_phase3(L, up2p);
+            if (active) {
+                if (L.flags & 1u) st |= AK_ST_ALPHABET;
+                if (L.trb) {
+                    const int64_t r_lo = r_w0 > 0 ? r_w0 - 1 : 0;
+                    if (akb3_changes(A.T, B.text, B.off, B.n_rows, r_lo, L.trb, cs, st)) {
+                        // NFC (which HF's NFKC includes) would change a code point of this lane: its row is normalized
+                        // and encoded on its own by the row-fix kernel
+                        ake_flag_rows(B.off, B.n_rows, cs, L.trb, A.row_flag);
+                        atomicOr(A.any_flag, 1u);
+                    }
+                }
+            }
+            const uint32_t bsend = lane == 31 ? (L.bnd & 0x3FFFFFFFu) : L.bnd;
+            nb1 = __shfl_down_sync(0xFFFFFFFFu, bsend, 1);
+            nb2 = __shfl_down_sync(0xFFFFFFFFu, bsend, 2);
+            if (lane >= 30) nb2 = 0;
+            wstart = active ? L.wstart : 0u;
+            rowsm = active ? L.rows : 0u;
+            cw = L.CW;
+            bnd = L.bnd;
+        } else {
+            AkU3Lane L;
+            L.own = own;
+            L.rows = rows;
+            aku3_phase1(x, L);
+            uint32_t upp = __shfl_up_sync(0xFFFFFFFFu, L.up, 1);
+            if (lane == 0) upp = 0;
+            aku3_phase2(L, upp);
+            nb1 = __shfl_down_sync(0xFFFFFFFFu, L.bnd, 1);
+            nb2 = __shfl_down_sync(0xFFFFFFFFu, L.bnd, 2);
+            if (lane >= 30) nb2 = 0;
+            wstart = active ? L.wstart : 0u;
+            rowsm = active ? L.rows : 0u;
+            cw = 0xFFFFFFFFu;
+            bnd = L.bnd;
+            if (active && L.exotic) {
+                // a (possible) literal U+2581: the rows that hold it go to the exact row encoder
+                ake_flag_rows(B.off, B.n_rows, cs, L.exotic, A.row_flag);
+                atomicOr(A.any_flag, 1u);
+            }
+        }
+        // the lane's place among the warp tile's slots
+        const int n_ev = __popc(rowsm) + __popc(wstart);
+        int inc = n_ev;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int y = __shfl_up_sync(0xFFFFFFFFu, inc, d);
+            if (lane >= d) inc += y;
+        }
+        const int total = __shfl_sync(0xFFFFFFFFu, inc, 31);
+        const int pre = inc - n_ev;
+        if (lane == 0) {
+            A.S.count[wt] = (uint32_t)(total < A.S.cap ? total : A.S.cap);
+            if (total > A.S.cap) {
+                // too many events in 960 bytes for the slots this workspace gives a warp tile: say how many were needed
+                st |= AK_ST_OVERFLOW;
+                atomicMax((unsigned long long*)&B.result[3], (unsigned long long)total);
+            }
+        }
+        if (n_ev) {
+            const int64_t at = (wt << A.S.shift) + pre;
+            const int lane_tail = lane >= 30 ? 62 : lane == 29 ? 94 : 96;       // bytes from cs on whose boundaries the warp knows
+            if (rowsm && ake_lane_rows(rowsm, wstart, cs, B.off, B.n_rows, nr, at, A.row_ev, KIND == 1 ? AKT_LONG_ROW : 0, A.row_flag))
+                atomicOr(A.any_flag, 1u);
+            AkScanEnd<KIND> se;
+            se.T = &A.T; se.text = B.text; se.off = B.off; se.n_rows = B.n_rows; se.cs = cs; se.cw = cw;
+            ake_lane_events(rowsm, wstart, cw, bnd, nb1, nb2, lane_tail, cs, tb, B.off, B.n_rows, nr, A.S.ev + at,
+                            (int64_t)A.S.cap - pre, se);
+        }
+    }
+    ak_raise(B.result, st);
+}
+
+// =================================================================================================================
+// row fix: the rows the fast path does not handle (BPE: not in NFC; Unigram: a literal U+2581 or a row longer than
+// AKT_LONG_ROW) are encoded whole by the exact row encoder into a side pool; their word events are struck out and the
+// row's start event hands the ids over.  One thread per flagged row (rare).
+// =================================================================================================================
+struct AkRowFixArgs {
+    AkBatch B;
+    AkRowFixCtx X;
+    int64_t base0;
+    int cap;
+    const uint8_t* row_flag;
+    const unsigned int* any_flag;
+};
+
+__global__ void __launch_bounds__(128) ak_rowfix_kernel(const AkRowFixArgs A) {
+    AkBatch B = A.B;
+    if (!ak_batch_begin(B)) return;
+    if (*A.any_flag == 0u) return;
+    AkRowFixCtx X = A.X;
+    X.n_events = (unsigned long long)akt_n_wt(B, A.base0) * (unsigned long long)A.cap;
+    X.text = B.text;
+    X.off = B.off;
+    X.n_rows = B.n_rows;
+    X.result = B.result;
+    for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < B.n_rows; g += (int64_t)gridDim.x * blockDim.x)
+        if (A.row_flag[g]) akr_fix_row(X, g);
+}
+
+// =================================================================================================================
+// resolve kernel: one WARP per warp tile, one slot per lane and round.  The lanes of a round run the same look-up side by
+// side and meet again (__syncwarp) before the next one -- without that, lanes that finish early (an empty slot, a short
+// word) run ahead through the loop on their own and the warp degenerates into 32 single-lane instruction streams.
+// Per warp tile it leaves the number of ids its events emit and (Unigram) the segmented sum of wmag.
+// =================================================================================================================
+struct AkResolveArgs {
+    AkBatch B;
+    AkLookupCtx X;
+    int64_t base0;
+    AkSlots S;
+    unsigned long long* resolved;      // per slot
+    uint32_t* aux;                     // per slot (Unigram)
+    int32_t* wt_ids;                   // per warp tile: ids emitted
+    unsigned long long* wt_seg;        // per warp tile (Unigram): (has a row start << 32) | float sum of wmag after the last one
+    const unsigned int* any_flag;
+};
+
+#ifndef AKR_MINB0
+#define AKR_MINB0 3
+#endif
+#ifndef AKR_MINB1
+#define AKR_MINB1 3
+#endif
+template <int KIND>
+__global__ void __launch_bounds__(AKR_THREADS, KIND == 0 ? AKR_MINB0 : AKR_MINB1) ak_resolve_kernel(const AkResolveArgs A) {
+    AkBatch B = A.B;
+    if (!ak_batch_begin(B)) return;
+    AkLookupCtx X = A.X;
+    X.text = B.text;
+    X.off = B.off;
+    X.n_rows = B.n_rows;
+    X.tb = B.text_begin;
+    X.te = B.text_end;
+    X.result = B.result;
+    X.any_fix = *A.any_flag != 0u ? 1 : 0;
+    const int lane = threadIdx.x & 31;
+    const long long n_wt = akt_n_wt(B, A.base0);
+    const long long warp0 = ((long long)blockIdx.x * AKR_THREADS + threadIdx.x) >> 5, n_warps = ((long long)gridDim.x * AKR_THREADS) >> 5;
+    uint32_t st = 0;
+    for (long long wt = warp0; wt < n_wt; wt += n_warps) {
+        const int cnt = (int)A.S.count[wt];
+        const long long s_wt = wt << A.S.shift;
+        int ids = 0;
+        unsigned long long seg = 0ull;                         // (flag, sum) over the rounds so far
+        for (int o = 0; o < cnt; o += 32) {
+            const int i = o + lane;
+            unsigned long long r = 0ull;
+            uint32_t aux = 0u;
+            if (i < cnt) {
+                const long long s = s_wt + i;
+                AkEvent ev = A.S.ev[s];
+                const uint32_t kind = ev.meta & 7u, len = ev.meta >> 3;
+                unsigned long long k0 = 0ull, k1 = 0ull;
+                if (kind <= AKE_WORD && len <= AKC_MAXLEN) akc_key01(X.text, X.tb + ev.pos, len, X.te, k0, k1);
+                r = akl_resolve<KIND>(X, ev, k0, k1, aux, st);
+                A.resolved[s] = r;
+                if (KIND == 1) A.aux[s] = aux;
+            }
+            __syncwarp();
+            ids += akr_n(r);
+            if (KIND == 1) {
+                // my element, then the warp's aggregate of this round appended to the running one
+                unsigned long long e = (r >> 62) == AKR_EVENT ? AKS_SEG_FLAG : (unsigned long long)__float_as_uint(aku_aux_wmag(aux));
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const unsigned long long y = __shfl_up_sync(0xFFFFFFFFu, e, d);
+                    if (lane >= d) e = aks_seg_op(y, e);
+                }
+                seg = aks_seg_op(seg, __shfl_sync(0xFFFFFFFFu, e, 31));
+            }
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) ids += __shfl_xor_sync(0xFFFFFFFFu, ids, d);
+        if (lane == 0) {
+            A.wt_ids[wt] = ids;
+            if (KIND == 1) A.wt_seg[wt] = seg;
+        }
+    }
+    ak_raise(B.result, st);
+}
+
+// =================================================================================================================
+// Unigram check: d = segmented sum of wmag along each row (a row event starts a segment); a word whose cached lattice
+// is not robust at that magnitude takes its ids from the exact Viterbi of its row.  One warp per warp tile; the sum that
+// reaches the warp tile comes from the scan over the warp tiles' aggregates (ak_scan_seg_kernel).
+// =================================================================================================================
+struct AkCheckArgs {
+    AkBatch B;
+    AkLookupCtx X;
+    int64_t base0;
+    AkSlots S;
+    unsigned long long* resolved;
+    const uint32_t* aux;
+    const float* wt_seg_before;        // per warp tile: sum of wmag since the last row start before it
+    int32_t* wt_ids;
+    const unsigned int* any_flag;
+};
+
+__global__ void __launch_bounds__(AKL_THREADS, 4) ak_unicheck_kernel(const AkCheckArgs A) {
+    AkBatch B = A.B;
+    if (!ak_batch_begin(B)) return;
+    AkLookupCtx X = A.X;
+    X.text = B.text;
+    X.off = B.off;
+    X.n_rows = B.n_rows;
+    X.tb = B.text_begin;
+    X.te = B.text_end;
+    X.result = B.result;
+    X.any_fix = *A.any_flag != 0u ? 1 : 0;
+    const int lane = threadIdx.x & 31;
+    const long long n_wt = akt_n_wt(B, A.base0);
+    const long long warp0 = ((long long)blockIdx.x * AKL_THREADS + threadIdx.x) >> 5, n_warps = ((long long)gridDim.x * AKL_THREADS) >> 5;
+    for (long long wt = warp0; wt < n_wt; wt += n_warps) {
+        const int cnt = (int)A.S.count[wt];
+        const long long s_wt = wt << A.S.shift;
+        unsigned long long run = (unsigned long long)__float_as_uint(A.wt_seg_before[wt]);     // (flag, sum) before this round
+        int delta = 0;
+        for (int o = 0; o < cnt; o += 32) {
+            const int i = o + lane;
+            uint32_t aux = 0u;
+            bool isrow = false;
+            if (i < cnt) {
+                aux = A.aux[s_wt + i];
+                isrow = (A.resolved[s_wt + i] >> 62) == AKR_EVENT;
+            }
+            unsigned long long e = isrow ? AKS_SEG_FLAG : (unsigned long long)__float_as_uint(aku_aux_wmag(aux));
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const unsigned long long y = __shfl_up_sync(0xFFFFFFFFu, e, d);
+                if (lane >= d) e = aks_seg_op(y, e);
+            }
+            const unsigned long long incl = aks_seg_op(run, e);                 // up to and including my slot
+            run = aks_seg_op(run, __shfl_sync(0xFFFFFFFFu, e, 31));
+            if (i < cnt && !isrow && aux != 0u && !aku_robust(aku_aux_ratio(aux), __uint_as_float((uint32_t)incl))) {
+                const AkEvent ev = A.S.ev[s_wt + i];
+                if ((ev.meta & 7u) <= AKE_WORD) {
+                    long long pa;
+                    const int n = akl_uni_exact(X, X.tb + ev.pos, ev.meta >> 3, &pa);
+                    const unsigned long long r = pa >= 0 ? akr_pool(n, (unsigned long long)pa) : 0ull;
+                    delta += akr_n(r) - akr_n(A.resolved[s_wt + i]);
+                    A.resolved[s_wt + i] = r;
+                }
+            }
+            __syncwarp();
+        }
+        if (delta) atomicAdd(&A.wt_ids[wt], delta);
+    }
+}
+
+// =================================================================================================================
+// emit kernel: one warp per warp tile; its first id goes to wt_base[wt] (scan over the warp tiles' id counts)
+// =================================================================================================================
+struct AkEmitArgs {
+    AkBatch B;
+    AkLookupCtx X;
+    int64_t base0;
+    AkSlots S;
+    const unsigned long long* resolved;
+    const int64_t* wt_base;
+    const unsigned int* any_flag;
+};
+
+__global__ void __launch_bounds__(AKL_THREADS, 4) ak_emit_kernel(const AkEmitArgs A) {
+    AkBatch B = A.B;
+    if (!ak_batch_begin(B)) return;
+    AkLookupCtx X = A.X;
+    X.text = B.text;
+    X.off = B.off;
+    X.n_rows = B.n_rows;
+    X.tb = B.text_begin;
+    X.te = B.text_end;
+    X.result = B.result;
+    X.any_fix = *A.any_flag != 0u ? 1 : 0;
+    const int lane = threadIdx.x & 31;
+    const long long n_wt = akt_n_wt(B, A.base0);
+    const long long warp0 = ((long long)blockIdx.x * AKL_THREADS + threadIdx.x) >> 5, n_warps = ((long long)gridDim.x * AKL_THREADS) >> 5;
+    uint32_t st = 0;
+    for (long long wt = warp0; wt < n_wt; wt += n_warps) {
+        const int cnt = (int)A.S.count[wt];
+        const long long s_wt = wt << A.S.shift;
+        int64_t at0 = A.wt_base[wt];
+        for (int o = 0; o < cnt; o += 32) {
+            const int i = o + lane;
+            const unsigned long long r = i < cnt ? A.resolved[s_wt + i] : 0ull;
+            const int n = akr_n(r);
+            int inc = n;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int y = __shfl_up_sync(0xFFFFFFFFu, inc, d);
+                if (lane >= d) inc += y;
+            }
+            const int64_t at = at0 + (inc - n);
+            if (r) {
+                if (at + n > X.id_cap) st |= AK_ST_OVERFLOW;
+                akl_emit(X, r, A.S.ev + s_wt + i, at);
+            }
+            at0 += __shfl_sync(0xFFFFFFFFu, inc, 31);
+            __syncwarp();
+        }
+    }
+    ak_raise(B.result, st);
+}

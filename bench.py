@@ -355,8 +355,8 @@ def main():
     # ---- dominant kernel: the library brackets its hot kernels with CUDA events on the launching stream
     # (akshar_timing_enable); average over a few full steps of the same workload
     eng.timing(True)
-    names = ['ak_nf3_classify_kernel', 'ak_nf_write_kernel'] + (['ak_bf3_encode_kernel'] if mkind == 0 else
-                                                                 ['ak_unigram_kernel'] if mkind == 1 else ['ak_sf3_kernel'])
+    names = ['ak_nf3_classify_kernel', 'ak_nf_write_kernel'] + (['ak_words_kernel', 'ak_resolve_kernel<bpe>', 'ak_emit_kernel'] if mkind == 0 else
+                                                                 ['ak_words_kernel', 'ak_resolve_kernel<unigram>', 'ak_emit_kernel'] if mkind == 1 else ['ak_sf3_kernel'])
     acc = {k: [] for k in names}
     for _ in range(3):
         device_step()
@@ -374,8 +374,10 @@ def main():
     alg = {
         'ak_nf3_classify_kernel': nbytes + 4 * (nbytes // 15),                 # text in, one 4-byte emit mask per 16-byte chunk out
         'ak_nf_write_kernel': nbytes + 4 * (nbytes // 15) + n_norm + 8 * (n_rows + 1),
-        'ak_bf3_encode_kernel': n_norm + 4 * n_tokens + 8 * (n_rows + 1),
-        'ak_unigram_kernel': n_norm + 4 * n_tokens + 8 * (n_rows + 1),
+        'ak_words_kernel': n_norm + 8 * (n_rows + 1),
+        'ak_resolve_kernel<bpe>': n_norm + 4 * n_tokens + 8 * (n_rows + 1),
+        'ak_resolve_kernel<unigram>': n_norm + 4 * n_tokens + 8 * (n_rows + 1),
+        'ak_emit_kernel': 4 * n_tokens + 8 * (n_rows + 1),
         'ak_sf3_kernel': n_norm + 4 * n_c + 5 * n_r + 16 * (n_rows + 1),
     }
     stages = {k: (kms[k], alg[k]) for k in kms}

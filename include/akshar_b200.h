@@ -11,7 +11,8 @@
  *   - all work is enqueued on `stream` (a cudaStream_t passed as void*); nothing synchronises.
  *   - ragged outputs: values + `row_splits[n_rows + 1]` (int64).  Capacities are in elements; writes beyond a
  *     capacity are dropped, totals stay exact and AKSHAR_ST_OVERFLOW is raised in the result block.
- *   - `d_result` is 4 x int64 in device memory: [0] primary total, [1] secondary total, [2] status bits, [3] 0.
+ *   - `d_result` is 4 x int64 in device memory: [0] primary total, [1] secondary total, [2] status bits, [3] 0 (encoders
+ *     that raise AKSHAR_ST_OVERFLOW for want of event slots: the slots per 960 text bytes that were needed).
  *   - return value: 0 on success, negative AKSHAR_E_* for host-side errors (bad argument, CUDA launch failure).
  *   - one context per device; a context is not thread-safe.
  */
@@ -45,6 +46,7 @@ enum {
     AKSHAR_ST_SPIN = 16,
     AKSHAR_ST_WORD = 32,         /* the long-word pool ran out (many words beyond 48 symbols): call again with a larger
                                     workspace -- half of what exceeds akshar_workspace_bytes() goes to that pool */
+    AKSHAR_ST_INTERNAL = 64,     /* an internal consistency check failed (never expected): the result is not to be used */
 };
 
 /* normalize flags: normalize_text(text, normalize_roman, clean_hinglish) (normalize.py:117) is
@@ -131,24 +133,39 @@ int akshar_tokenizer_encode_batch(akshar_ctx* ctx, const uint8_t* d_text, const 
                                   int64_t id_capacity, int64_t* d_id_splits, int64_t* d_result, void* d_workspace,
                                   size_t workspace_bytes, void* stream);
 
+/* The same call with compact outputs for callers that ship the result over a host link (the ids of a 24k vocabulary
+ * need 16 bits, the splits of a chunk 32): out_flags = AKSHAR_OUT_IDS_U16 -> d_ids is uint16_t[id_capacity] (refused when
+ * the vocabulary has more than 65536 entries), AKSHAR_OUT_SPLITS_I32 -> d_id_splits is int32_t[n_rows + 1].
+ * Needs AKSHAR_MODE_TILES. */
+#define AKSHAR_OUT_IDS_U16 1u
+#define AKSHAR_OUT_SPLITS_I32 2u
+int akshar_tokenizer_encode_batch_ex(akshar_ctx* ctx, const uint8_t* d_text, const int64_t* d_row_offsets, int64_t n_rows,
+                                     int64_t text_begin, int64_t text_end, uint32_t norm_flags, int kind, int mode,
+                                     uint8_t* d_norm_text, int64_t norm_capacity, int64_t* d_norm_row_offsets, void* d_ids,
+                                     int64_t id_capacity, void* d_id_splits, uint32_t out_flags, int64_t* d_result,
+                                     void* d_workspace, size_t workspace_bytes, void* stream);
+
 /* Optional device-side timing of the dominant kernel of each stage, for roofline reporting: when enabled, the
  * library brackets that one launch with CUDA events on the caller's stream; akshar_timing_read waits for the
  * kernel and returns its duration of the most recent call. */
 enum {
     AKSHAR_TIMER_NORMALIZE_CLASSIFY = 0,   /* ak_nf3_classify_kernel */
     AKSHAR_TIMER_NORMALIZE_WRITE = 1,      /* ak_nf_write_kernel */
-    AKSHAR_TIMER_BPE_ENCODE = 2,           /* ak_bf3_encode_kernel */
+    AKSHAR_TIMER_BPE_ENCODE = 2,           /* ak_resolve_kernel<0> (word events -> BPE ids through the word cache) */
     AKSHAR_TIMER_SEGMENT = 3,              /* ak_sf3_kernel */
-    AKSHAR_TIMER_UNIGRAM = 4,              /* ak_unigram_kernel */
-    AKSHAR_TIMER_COUNT = 5
+    AKSHAR_TIMER_UNIGRAM = 4,              /* ak_resolve_kernel<1> (word events -> Unigram ids), or ak_unigram_kernel in row mode */
+    AKSHAR_TIMER_WORDS = 5,                /* ak_words_kernel (text -> word / row events) */
+    AKSHAR_TIMER_EMIT = 6,                 /* ak_emit_kernel (ids to their final place) */
+    AKSHAR_TIMER_COUNT = 7
 };
 int akshar_timing_enable(akshar_ctx* ctx, int enable);
 
-/* BPE word cache across calls.  By default every encode call starts from the cache image built at model load (nothing
- * learned in one call is reused by the next).  hold = 1: the calls that follow keep what earlier calls added -- for ONE
- * logical batch fed in several calls (akshar_b200.batch.encode_host_pipelined cuts a host batch into chunks that
- * overlap copy and compute); hold = 0 restores the default.  HF tokenizers keeps its word cache for the lifetime of the
- * Tokenizer (reference tokenizer.py:96-98 -> tokenizers BPE `cache`). */
+/* Word caches of the encoders (pre-tokenized word -> ids; HF tokenizers keeps the same kind of cache for the lifetime of
+ * its Tokenizer, reference tokenizer.py:96-98 -> tokenizers BPE `cache`).  A cache lives as long as its model: words
+ * met in one call serve the next ones; results never depend on its contents.  It has no eviction: when the words learned
+ * since the last restore fill a quarter of the table, the image built at model load is copied back at the start of the
+ * next call (decided on the device).  hold = 1 switches that restore off, hold = 0 (default) on again, hold < 0
+ * restores the image at the next encode call whatever the fill. */
 int akshar_word_cache_hold(akshar_ctx* ctx, int hold);
 int akshar_timing_read(akshar_ctx* ctx, int timer, float* ms);
 

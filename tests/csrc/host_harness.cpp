@@ -12,8 +12,8 @@
 #include "../../akshar_b200/csrc/ak_norm3.cuh"
 #include "../../akshar_b200/csrc/ak_seg3.cuh"
 #include "../../akshar_b200/csrc/ak_bpe3.cuh"
-#include "../../akshar_b200/csrc/ak_bpe_fast.cuh"
-#include "../../akshar_b200/csrc/ak_seg_fast.cuh"
+#include "../../akshar_b200/csrc/ak_tok.cuh"
+#include "../../akshar_b200/csrc/ak_tok_host.h"
 #include "../../akshar_b200/csrc/ak_models.h"
 #include "../../akshar_b200/csrc/unicode_tables.inc"
 
@@ -91,97 +91,6 @@ static void hh_make_chunk(const uint8_t* text, int64_t cs, int64_t tb, int64_t t
         if (i < 16 && q >= base0 && q - base0 < (int64_t)rowstart.size() && rowstart[(size_t)(q - base0)]) c.rows |= 1u << i;
     }
 }
-
-int64_t hh_fast_normalize(const uint8_t* text, const int64_t* off, int64_t n_rows, int real, uint8_t* out, int64_t* out_off,
-                          uint32_t* status, int64_t* n_slow) {
-    AkTables T = host_tables();
-    std::vector<uint32_t> lut(384);
-    for (int i = 0; i < 384; ++i) lut[(size_t)i] = i < 128 ? ak_props(T, (uint32_t)i) : ak_props(T, 0x900u + (uint32_t)(i - 128));
-    const int64_t tb = off[0], te = off[n_rows], base0 = tb;
-    std::vector<uint8_t> rowstart((size_t)(te - base0) + 64, 0);
-    for (int64_t r = 0; r <= n_rows; ++r) rowstart[(size_t)(off[r] - base0)] = 1;
-    const int64_t n_chunks = (te - base0 + 1 + 15) / 16;
-    const uint32_t NFLAGS = AK_NORM_ROMAN | AK_NORM_CLEAN;
-    int64_t base = 0, row = 0, slow_cnt = 0;
-    uint32_t st = 0;
-    std::vector<AkChunk> lanes((size_t)real + 2);
-    for (int64_t w0 = 0; w0 < n_chunks; w0 += real) {
-        for (int l = 0; l < real + 2; ++l) {
-            AkChunk& c = lanes[(size_t)l];
-            int64_t cs = base0 + (w0 - 1 + l) * 16;
-            hh_make_chunk(text, cs, tb, te, rowstart, base0, c);
-            if (c.own == 0 && c.rows == 0) {
-                c.kept = c.lead = 0;
-                c.flags = AKF_BOUNDARY | AKF_ROWSTART;
-                c.first_w = c.last_w = c.F = c.L1 = c.L2 = AKF_NONE;
-            } else {
-                akf_phase_a(T, lut.data(), c);
-            }
-        }
-        for (int l = 0; l < real + 2; ++l) {
-            AkChunk& c = lanes[(size_t)l];
-            if (l == 0) {
-                // left halo: the kernel decodes the code point that ends right before the chunk
-                uint32_t pl = AKF_NONE;
-                int64_t cs = base0 + (w0 - 1) * 16;
-                if (c.first_w != AKF_NONE && cs > tb) {
-                    int64_t q = cs - 1;
-                    int k = 0;
-                    while (q > tb && k < 3 && (text[q] & 0xC0u) == 0x80u) { --q; ++k; }
-                    int len;
-                    pl = akf_props(T, lut.data(), ak_decode(text, q, te, len));
-                }
-                akf_resolve_first(c, pl);
-            } else {
-                akf_resolve_first(c, lanes[(size_t)l - 1].last_w);
-            }
-        }
-        for (int l = 1; l <= real; ++l) {
-            AkChunk& c = lanes[(size_t)l];
-            int64_t cs = base0 + (w0 - 1 + l) * 16;
-            int64_t ss = cs < tb ? tb : cs, se = cs + 16 > te + 1 ? te + 1 : cs + 16;
-            if (ss >= se) continue;
-            AkNeighbor pv, nx;
-            pv.flags = lanes[(size_t)l - 1].flags; pv.F = AKF_NONE; pv.L1 = lanes[(size_t)l - 1].L1; pv.L2 = lanes[(size_t)l - 1].L2;
-            nx.flags = lanes[(size_t)l + 1].flags; nx.F = lanes[(size_t)l + 1].F; nx.L1 = nx.L2 = AKF_NONE;
-            uint32_t emit = 0;
-            bool slow = akf_is_slow(c, pv, nx) || !akf_collapse(c, pv, nx, emit);
-            if (slow && getenv("AKF_REASONS")) {
-                int why = (c.flags & AKF_TROUBLE) ? 0 : ((c.flags & AKF_FIRST_DEP) && ((pv.flags & AKF_TROUBLE) || !(pv.flags & AKF_BOUNDARY))) ? 1
-                        : ((nx.flags & AKF_LEAD_TROUBLE) || !(nx.flags & AKF_BOUNDARY)) ? 2
-                        : ((c.flags & AKF_KEPT_BEFORE_ROW) && ((pv.flags & AKF_TROUBLE) || (!(pv.flags & AKF_ROWSTART) && pv.L2 == AKF_NONE))) ? 3 : 4;
-                static long cnts[5];
-                cnts[why]++;
-                if ((cnts[0] + cnts[1] + cnts[2] + cnts[3] + cnts[4]) % 500 == 0)
-                    fprintf(stderr, "reasons own-trouble %ld first-dep %ld next %ld prev-kept %ld lookahead %ld\n", cnts[0], cnts[1], cnts[2], cnts[3], cnts[4]);
-                if (why == 0 && cnts[0] < 12) {
-                    fprintf(stderr, "  trouble chunk: ");
-                    for (int i = 0; i < 19; ++i) fprintf(stderr, "%02x ", akf_byte(c, i));
-                    fprintf(stderr, "\n");
-                }
-            }
-            while (row <= n_rows && off[row] < ss) ++row;
-            if (slow) {
-                ++slow_cnt;
-                base += ak_norm_span(T, text, off, n_rows, 0, n_rows, ss, se, NFLAGS, 0, out + base, out_off, base, st);
-                while (row <= n_rows && off[row] < se) ++row;
-            } else {
-                while (row <= n_rows && off[row] < se) {
-                    int i = (int)(off[row] - cs);
-                    int before = 0;
-                    for (int b = 0; b < i; ++b) before += (emit >> b) & 1u;
-                    out_off[row] = base + before;
-                    ++row;
-                }
-                base += akf_write(c, emit, out + base);
-            }
-        }
-    }
-    *status = st;
-    *n_slow = slow_cnt;
-    return base;
-}
-
 
 // ---- bit-parallel normalize (ak_norm3.cuh): 32-byte lanes, `real` lanes + 2 halo lanes per "warp", the kernel's
 // three exchange rounds, its emit masks fed to the same 16-byte writer, the walker for slow lanes.
@@ -450,267 +359,188 @@ int64_t hh_bpe(const uint8_t* text, const int64_t* off, int64_t n_rows, const in
     return base;
 }
 
-// The fast BPE kernel's structure on the CPU: chunks, halo lanes, word cache (starting empty, `cache_bits` slots so
-// that small tables exercise probing / eviction-free misses), lane emit with relative splits.
-int64_t hh_bpe_fast(const uint8_t* text, const int64_t* off, int64_t n_rows, int real, int cache_bits, int stage_cap,
-                    int32_t* ids, int64_t id_cap, int64_t* splits, int* changed_out, uint32_t* status) {
-    AkTables T = host_tables();
-    std::vector<uint32_t> lut(384);
-    for (int i = 0; i < 384; ++i) lut[(size_t)i] = i < 128 ? ak_props(T, (uint32_t)i) : ak_props(T, 0x900u + (uint32_t)(i - 128));
-    AkBpeDev M;
-    M.cp_direct = g_bpe.cp_direct.data(); M.cp_keys = g_bpe.cp_keys.data(); M.cp_ids = g_bpe.cp_ids.data();
-    M.n_cp = (int)g_bpe.cp_keys.size(); M.mkeys = g_bpe.mkeys.data(); M.mvals = g_bpe.mvals.data(); M.mbits = g_bpe.mbits;
-    M.bos = g_bpe.bos; M.eos = g_bpe.eos;
-    std::vector<unsigned long long> img((size_t)AKW_ENTRY << cache_bits, 0ull);
-    AkWordCache C; C.e = img.data(); C.bits = (uint32_t)cache_bits;
-    std::vector<int32_t> poolbuf(1 << 20);
-    unsigned long long used = 0;
-    AkPool pool; pool.base = poolbuf.data(); pool.used = &used; pool.cap = poolbuf.size();
-    const int64_t tb = off[0], te = off[n_rows], base0 = tb;
-    std::vector<uint8_t> rowstart((size_t)(te - base0) + 64, 0);
-    for (int64_t r = 0; r <= n_rows; ++r) rowstart[(size_t)(off[r] - base0)] = 1;
-    const int64_t n_chunks = (te - base0 + 1 + 15) / 16;
-    AkBLaneCtx X; X.M = &M; X.T = &T; X.C = &C; X.text = text; X.off = off; X.n_rows = n_rows; X.r_lo = 0; X.r_hi = n_rows; X.pool = &pool;
-    uint32_t st = 0;
-    bool changed = false;
-    int64_t base = 0;
-    std::vector<AkBChunk> lanes((size_t)real + 2);
-    std::vector<int32_t> stage((size_t)stage_cap + 1);
-    for (int64_t w0 = 0; w0 < n_chunks; w0 += real) {
-        for (int l = 0; l < real + 2; ++l) {
-            AkBChunk& c = lanes[(size_t)l];
-            int64_t cs = base0 + (w0 - 1 + l) * 16;
-            AkChunk tmp;
-            hh_make_chunk(text, cs, tb, te, rowstart, base0, tmp);
-            for (int k = 0; k < 5; ++k) c.w[k] = tmp.w[k];
-            c.rows = tmp.rows; c.own = tmp.own;
-            akb_phase_a(T, lut.data(), c);
-        }
-        for (int l = 0; l < real + 2; ++l) {
-            AkBChunk& c = lanes[(size_t)l];
-            uint32_t pw = AKF_NONE, pk = 2;
-            if (l == 0) {
-                int64_t cs = base0 + (w0 - 1) * 16;
-                if (c.first_pos < 32u && cs > tb) {
-                    int64_t q = cs - 1;
-                    int k = 0;
-                    while (q > tb && k < 3 && (text[q] & 0xC0u) == 0x80u) { --q; ++k; }
-                    int len;
-                    pw = akf_props(T, lut.data(), ak_decode(text, q, te, len));
-                    pk = AK_HFCLASS(pw);
-                }
-            } else {
-                pw = lanes[(size_t)l - 1].last_w; pk = lanes[(size_t)l - 1].last_cls;
-            }
-            akb_resolve_first(c, pw, pk);
-        }
-        for (int l = 1; l <= real; ++l) {
-            AkBChunk& c = lanes[(size_t)l];
-            int64_t cs = base0 + (w0 - 1 + l) * 16;
-            int64_t ss = cs < tb ? tb : cs, se = cs + 16 > te + 1 ? te + 1 : cs + 16;
-            if (ss >= se) continue;
-            if (c.flags & AKB_ALPHABET) st |= AK_ST_ALPHABET;
-            if ((c.flags & AKF_TROUBLE) && akb_chunk_changes(X, c, cs, 0, st)) changed = true;
-            AkIdSink sink; sink.buf = stage.data(); sink.cap = stage_cap; sink.stride = 1; sink.cnt = 0; sink.direct = false;
-            sink.gout = ids; sink.gbase = 0; sink.gcap = id_cap;
-            int64_t rf, rl;
-            const uint32_t nb = (lanes[(size_t)l + 1].bnd & 0xFFFFu) | (l + 2 <= real + 1 && l < real ? (lanes[(size_t)l + 2].bnd & 0xFFFFu) << 16 : 0u);
-            akb_lane_emit(X, c, nb, cs, sink, splits, rf, rl, st);
-            for (int64_t r = rf; r < rl; ++r) splits[r] += base;
-            if (sink.cnt <= stage_cap) {
-                for (int k = 0; k < sink.cnt; ++k) if (base + k < id_cap) ids[base + k] = stage[(size_t)k];
-            } else {
-                AkIdSink s2 = sink; s2.cnt = 0; s2.direct = true; s2.gbase = base;
-                int64_t a, b;
-                akb_lane_emit(X, c, nb, cs, s2, nullptr, a, b, st);
-                if (s2.cnt != sink.cnt) st |= 0x80000000u;
-            }
-            base += sink.cnt;
-        }
-    }
-    *changed_out = changed ? 1 : 0;
-    *status = st;
-    return base;
-}
 
-
-// ---- bit-parallel BPE front end (ak_bpe3.cuh): lanes of 32 bytes, boundaries / word starts / trouble bits from the
-// planes, every word through the exact merge loop (the word cache is the kernel's business)
-int64_t hh_bpe_fast3(const uint8_t* text, const int64_t* off, int64_t n_rows, int real, int32_t* ids, int64_t id_cap,
-                     int64_t* splits, int* changed_out, uint32_t* status) {
+// ---- the event-stream encoders (ak_tok.cuh) on the CPU: the words kernel's lanes ("warps" of `real` lanes + 2 halo lanes,
+// each with its block of `cap` event slots), then the row-fix, resolve, check and emit cores slot by slot in stream order.
+// kind 0 BPE, 1 Unigram.  cache_bits: size of the word cache (small tables exercise probing and uncached words);
+// prewarm = 0 starts it empty.  stats: [events, flagged rows, words sent to the exact Viterbi, cache misses, slots needed]
+int64_t hh_tok(int kind, const uint8_t* text, const int64_t* off, int64_t n_rows, int real, int cap, int cache_bits, int prewarm,
+               int u16, int splits_i32, void* ids, int64_t id_cap, void* splits, uint32_t* status, int64_t* stats) {
     AkTables T = host_tables();
-    AkBpeDev M;
-    M.cp_direct = g_bpe.cp_direct.data(); M.cp_keys = g_bpe.cp_keys.data(); M.cp_ids = g_bpe.cp_ids.data();
-    M.n_cp = (int)g_bpe.cp_keys.size(); M.mkeys = g_bpe.mkeys.data(); M.mvals = g_bpe.mvals.data(); M.mbits = g_bpe.mbits;
-    M.bos = g_bpe.bos; M.eos = g_bpe.eos;
-    std::vector<int32_t> poolbuf(1 << 20);
-    unsigned long long used = 0;
-    AkPool pool; pool.base = poolbuf.data(); pool.used = &used; pool.cap = poolbuf.size();
     const int64_t tb = off[0], te = off[n_rows], base0 = tb;
     std::vector<uint8_t> rowstart((size_t)(te - base0) + 128, 0);
     for (int64_t r = 0; r <= n_rows; ++r) rowstart[(size_t)(off[r] - base0)] = 1;
     const int64_t n_lanes = (te - base0 + 1 + 31) / 32;
+    const int64_t n_wt = (n_lanes + real - 1) / real;
     const int NL = real + 2;
-    std::vector<AkB3Lane> lanes((size_t)NL);
+    std::vector<AkEvent> slots((size_t)n_wt * cap);
+    std::vector<uint32_t> count((size_t)n_wt, 0);
+    std::vector<uint8_t> row_flag((size_t)n_rows + 2, 0);
+    std::vector<uint32_t> row_ev((size_t)n_rows + 2, 0);
+    int64_t result[4] = {0, 0, 0, 0};
     uint32_t st = 0;
-    bool changed = false;
-    int64_t nr = 0;
-    AkIdSink sink; sink.buf = nullptr; sink.cap = 0; sink.stride = 1; sink.cnt = 0; sink.direct = true;
-    sink.gout = ids; sink.gbase = 0; sink.gcap = id_cap;
-    for (int64_t w0 = 0; w0 < n_lanes; w0 += real) {
+    std::vector<AkB3Lane> lb((size_t)NL);
+    std::vector<AkU3Lane> lu((size_t)NL);
+    int64_t need = 0, n_events = 0;
+    for (int64_t wt = 0; wt < n_wt; ++wt) {
+        const int64_t w0 = wt * real;
         for (int l = 0; l < NL; ++l) {
-            AkB3Lane& L = lanes[(size_t)l];
-            memset(&L, 0, sizeof(L));
             const int64_t cs = base0 + (w0 - 1 + l) * 32;
             uint32_t x[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            uint32_t own = 0, rows = 0;
             for (int i = 0; i < 32; ++i) {
                 const int64_t q = cs + i;
-                if (q >= tb && q < te) { x[i >> 2] |= (uint32_t)text[q] << ((i & 3) * 8); L.own |= 1u << i; }
-                if (q >= base0 && q - base0 < (int64_t)rowstart.size() && rowstart[(size_t)(q - base0)]) L.rows |= 1u << i;
+                if (q >= tb && q < te) { x[i >> 2] |= (uint32_t)text[q] << ((i & 3) * 8); own |= 1u << i; }
+                if (q >= base0 && q - base0 < (int64_t)rowstart.size() && rowstart[(size_t)(q - base0)]) rows |= 1u << i;
             }
-            akb3_phase1(x, L);
+            if (kind == 0) {
+                AkB3Lane& L = lb[(size_t)l];
+                memset(&L, 0, sizeof(L));
+                L.own = own; L.rows = rows;
+                akb3_phase1(x, L);
+            } else {
+                AkU3Lane& L = lu[(size_t)l];
+                memset(&L, 0, sizeof(L));
+                L.own = own; L.rows = rows;
+                aku3_phase1(x, L);
+            }
         }
-        for (int l = 0; l < NL; ++l) {
-            AkB3Lane& L = lanes[(size_t)l];
-            const int64_t cs = base0 + (w0 - 1 + l) * 32;
-            akb3_phase2(L, l + 1 < NL ? lanes[(size_t)l + 1].dn1 : 0u);
-            if (L.FOR) akb3_foreign(T, text, cs, te, L);
-            akb3_summary(L);
+        if (kind == 0) {
+            for (int l = 0; l < NL; ++l) {
+                AkB3Lane& L = lb[(size_t)l];
+                const int64_t cs = base0 + (w0 - 1 + l) * 32;
+                akb3_phase2(L, l + 1 < NL ? lb[(size_t)l + 1].dn1 : 0u);
+                if (L.FOR) akb3_foreign(T, text, cs, te, L);
+                akb3_summary(L);
+            }
+            for (int l = 0; l < NL; ++l) akb3_phase3(lb[(size_t)l], l > 0 ? lb[(size_t)l - 1].up2 : 0u);
+            lb[(size_t)NL - 1].bnd &= 0x3FFFFFFFu;
+        } else {
+            for (int l = 0; l < NL; ++l) aku3_phase2(lu[(size_t)l], l > 0 ? lu[(size_t)l - 1].up : 0u);
         }
-        for (int l = 0; l < NL; ++l) akb3_phase3(lanes[(size_t)l], l > 0 ? lanes[(size_t)l - 1].up2 : 0u);
-        lanes[(size_t)NL - 1].bnd &= 0x3FFFFFFFu;
+        int pre = 0;
         for (int l = 1; l <= real; ++l) {
-            AkB3Lane& L = lanes[(size_t)l];
             const int64_t cs = base0 + (w0 - 1 + l) * 32;
             const int64_t ss = cs < tb ? tb : cs, se = cs + 32 > te + 1 ? te + 1 : cs + 32;
             if (ss >= se) continue;
-            if (L.flags & 1u) st |= AK_ST_ALPHABET;
-            for (uint32_t m = L.trb; m;) {
-                const int i = akb_ctz(m);
-                m &= m - 1u;
-                const int64_t p = cs + i;
-                const int64_t r = ak_row_lower_bound(off, 0, n_rows, p + 1);
-                int64_t cu = -1;
-                if (ak_segment_changes(T, text, p, off[r - 1], off[r], 0, &cu, st)) changed = true;
-            }
-            const uint32_t nb1 = lanes[(size_t)l + 1].bnd, nb2 = l + 2 < NL ? lanes[(size_t)l + 2].bnd : 0u;
-            for (uint32_t m = L.rows | L.wstart; m;) {
-                const int i = akb_ctz(m);
-                m &= m - 1u;
-                const int64_t p = cs + i;
-                if ((L.rows >> i) & 1u) {
-                    while (nr <= n_rows && off[nr] < p) ++nr;
-                    while (nr <= n_rows && off[nr] == p) {
-                        if (nr > 0 && M.eos >= 0) ak_id_put(sink, M.eos);
-                        splits[nr] = sink.cnt;
-                        if (nr < n_rows && M.bos >= 0) ak_id_put(sink, M.bos);
-                        ++nr;
-                    }
-                }
-                if ((L.wstart >> i) & 1u) {
-                    const uint32_t kc = (L.CW >> i) & 1u;
-                    const uint32_t above = L.bnd & ~((2u << i) - 1u);
-                    int64_t e;
-                    if (above) e = cs + akb_ctz(above);
-                    else if (nb1) e = cs + 32 + akb_ctz(nb1);
-                    else if (nb2) e = cs + 64 + akb_ctz(nb2);
-                    else {
-                        // the kernel's cold scan (akb3_scan_end)
-                        const int64_t er = ak_row_lower_bound(off, 0, n_rows, p + 1);
-                        const int64_t re = off[er];
-                        int64_t q = cs + (l >= real ? 62 : l == real - 1 ? 94 : 96);
-                        if (q > re) q = re;
-                        while (q < re && (text[q] & 0xC0u) == 0x80u) ++q;
-                        while (q < re) {
-                            int len;
-                            const uint32_t cp = ak_decode(text, q, re, len);
-                            if (AK_HFCLASS(ak_props(T, cp)) != kc) break;
-                            q += len;
-                        }
-                        e = q;
-                    }
-                    ak_bpe_word(M, T, text, p, e, kc, sink, pool, st);
-                }
-            }
-        }
-    }
-    *changed_out = changed ? 1 : 0;
-    *status = st;
-    return sink.cnt;
-}
-
-// The fast segment kernel's structure on the CPU (chunks, halo lanes, phase A / B, lane emit, walker slow lane).
-void hh_seg_fast(const uint8_t* text, const int64_t* off, int64_t n_rows, uint32_t flags, int real, int stage_cap,
-                 int32_t* cluster_ends, int64_t* cluster_splits, int32_t* run_ends, uint8_t* run_tags, int64_t* run_splits,
-                 int64_t cap, int64_t* totals, uint32_t* status, int64_t* n_slow) {
-    AkTables T = host_tables();
-    std::vector<uint32_t> lut(384);
-    for (int i = 0; i < 384; ++i) lut[(size_t)i] = i < 128 ? ak_props(T, (uint32_t)i) : ak_props(T, 0x900u + (uint32_t)(i - 128));
-    lut.resize(400);
-    for (uint32_t ga = 0; ga < 16; ++ga) lut[384 + ga] = ga < 14 ? aks_pair_row(ga) : 0u;
-    const bool want_c = (flags & AK_SEG_CLUSTERS) != 0, want_r = (flags & AK_SEG_RUNS) != 0, matras = (flags & AK_SEG_MATRAS) != 0;
-    const int64_t tb = off[0], te = off[n_rows], base0 = tb;
-    std::vector<uint8_t> rowstart((size_t)(te - base0) + 64, 0);
-    for (int64_t r = 0; r <= n_rows; ++r) rowstart[(size_t)(off[r] - base0)] = 1;
-    const int64_t n_chunks = (te - base0 + 1 + 15) / 16;
-    uint32_t st = 0;
-    int64_t cbase = 0, rbase = 0, slow_cnt = 0;
-    std::vector<AkSChunk> lanes((size_t)real + 2);
-    std::vector<int32_t> cst((size_t)stage_cap + 1), rst((size_t)stage_cap + 1);
-    std::vector<uint8_t> tst((size_t)stage_cap + 1);
-    for (int64_t w0 = 0; w0 < n_chunks; w0 += real) {
-        for (int l = 0; l < real + 2; ++l) {
-            AkSChunk& c = lanes[(size_t)l];
-            int64_t cs = base0 + (w0 - 1 + l) * 16;
-            AkChunk tmp;
-            hh_make_chunk(text, cs, tb, te, rowstart, base0, tmp);
-            for (int k = 0; k < 5; ++k) c.w[k] = tmp.w[k];
-            c.rows = tmp.rows; c.own = tmp.own;
-            aks_phase_a(T, lut.data(), c, matras);
-        }
-        for (int l = 1; l <= real; ++l) {
-            AkSChunk c = lanes[(size_t)l];
-            int64_t cs = base0 + (w0 - 1 + l) * 16;
-            int64_t ss = cs < tb ? tb : cs, se = cs + 16 > te + 1 ? te + 1 : cs + 16;
-            if (ss >= se) continue;
-            AkSNeighbor pv;
-            pv.g = lanes[(size_t)l - 1].end_g; pv.flags = lanes[(size_t)l - 1].flags; pv.end_cur = lanes[(size_t)l - 1].end_cur;
-            uint32_t in_cur = AKS_CUR_NONE;
-            bool slow = !aks_phase_b(T, lut.data(), c, pv, matras, want_c, want_r, in_cur);
-            if (slow) {
-                ++slow_cnt;
-                AkSegOut o;
-                o.cluster_ends = cluster_ends; o.cluster_splits = cluster_splits; o.run_ends = run_ends; o.run_tags = run_tags;
-                o.run_splits = run_splits; o.ccap = cap; o.rcap = cap; o.cbase = cbase; o.rbase = rbase;
-                int64_t a, b;
-                ak_seg_span(T, text, off, n_rows, 0, n_rows, ss, se, flags, 0, true, o, a, b, st);
-                cbase += a; rbase += b;
-                continue;
-            }
-            int64_t nr = 0;
-            while (nr <= n_rows && off[nr] < ss) ++nr;
-            AkSegSink sink;
-            sink.cbuf = cst.data(); sink.rbuf = rst.data(); sink.tbuf = tst.data(); sink.cap = stage_cap; sink.stride = 1;
-            sink.cc = sink.rc = 0; sink.direct = false; sink.gc = sink.gr = nullptr; sink.gt = nullptr; sink.gccap = sink.grcap = 0;
-            int64_t rf, rl;
-            aks_lane_emit(c, in_cur, cs, off, n_rows, nr, want_c, want_r, sink, want_c ? cluster_splits : nullptr,
-                          want_r ? run_splits : nullptr, rf, rl);
-            for (int64_t r = rf; r < rl; ++r) { if (want_c) cluster_splits[r] += cbase; if (want_r) run_splits[r] += rbase; }
-            if (sink.cc <= stage_cap && sink.rc <= stage_cap) {
-                for (int k = 0; k < sink.cc; ++k) if (cbase + k < cap) cluster_ends[cbase + k] = cst[(size_t)k];
-                for (int k = 0; k < sink.rc; ++k) if (rbase + k < cap) { run_ends[rbase + k] = rst[(size_t)k]; run_tags[rbase + k] = tst[(size_t)k]; }
+            uint32_t rowsm, wstart, cw, bnd, nb1, nb2;
+            if (kind == 0) {
+                AkB3Lane& L = lb[(size_t)l];
+                if (L.flags & 1u) st |= AK_ST_ALPHABET;
+                if (L.trb && akb3_changes(T, text, off, n_rows, 0, L.trb, cs, st)) ake_flag_rows(off, n_rows, cs, L.trb, row_flag.data());
+                rowsm = L.rows; wstart = L.wstart; cw = L.CW; bnd = L.bnd;
+                nb1 = lb[(size_t)l + 1].bnd;
+                nb2 = l + 2 < NL ? lb[(size_t)l + 2].bnd : 0u;
             } else {
-                AkSegSink s2 = sink; s2.cc = s2.rc = 0; s2.direct = true; s2.gc = cluster_ends + cbase; s2.gr = run_ends + rbase;
-                s2.gt = run_tags + rbase; s2.gccap = cap - cbase; s2.grcap = cap - rbase;
-                int64_t a, b;
-                aks_lane_emit(c, in_cur, cs, off, n_rows, nr, want_c, want_r, s2, nullptr, nullptr, a, b);
+                AkU3Lane& L = lu[(size_t)l];
+                if (L.exotic) ake_flag_rows(off, n_rows, cs, L.exotic, row_flag.data());
+                rowsm = L.rows; wstart = L.wstart; cw = 0xFFFFFFFFu; bnd = L.bnd;
+                nb1 = lu[(size_t)l + 1].bnd;
+                nb2 = l + 2 < NL ? lu[(size_t)l + 2].bnd : 0u;
             }
-            cbase += sink.cc; rbase += sink.rc;
+            const int64_t nr = ak_row_lower_bound(off, 0, n_rows, ss);
+            const int tail = l >= real ? 62 : l == real - 1 ? 94 : 96;
+            const int64_t at = wt * cap + pre;
+            ake_lane_rows(rowsm, wstart, cs, off, n_rows, nr, at, row_ev.data(), kind == 1 ? 8192 : 0, row_flag.data());
+            pre += ake_lane_events(rowsm, wstart, cw, bnd, nb1, nb2, tail, cs, tb, off, n_rows, nr, slots.data() + at, (int64_t)cap - pre,
+                                   [&](int64_t p, int64_t from) -> int64_t {
+                                       if (kind == 0) return akb3_scan_end(T, text, p, from, (cw >> (int)(p - cs)) & 1u, off, n_rows, 0, n_rows);
+                                       const int64_t er = ak_row_lower_bound(off, 0, n_rows, p + 1);
+                                       const int64_t re = off[er];
+                                       int64_t q = from > re ? re : from;
+                                       while (q < re && text[q] != 0x20u) ++q;
+                                       return q;
+                                   });
         }
+        count[(size_t)wt] = (uint32_t)(pre < cap ? pre : cap);
+        if (pre > cap) st |= AK_ST_OVERFLOW;
+        if (pre > need) need = pre;
+        n_events += pre;
     }
-    totals[0] = cbase; totals[1] = rbase;
-    *status = st;
-    *n_slow = slow_cnt;
+    stats[0] = n_events;
+    stats[4] = need;
+    if (st & AK_ST_OVERFLOW) { *status = st; stats[1] = stats[2] = stats[3] = 0; return 0; }
+    // model + cache
+    AkTokModel M;
+    memset(&M, 0, sizeof(M));
+    M.kind = kind;
+    M.T = T;
+    std::vector<unsigned long long> img;
+    if (kind == 0) {
+        M.bpe = ak_bpe_host_view(g_bpe);
+        img = prewarm ? ak_build_bpe_image(g_bpe, T, (uint32_t)cache_bits) : std::vector<unsigned long long>((size_t)AKC_ENTRY << cache_bits, 0ull);
+    } else {
+        M.uni = ak_uni_host_view(g_uni);
+        if (!ak_uni_wordwise(g_uni)) { *status = 0x40000000u; return -1; }
+        img = prewarm ? ak_build_uni_image(g_uni, (uint32_t)cache_bits) : std::vector<unsigned long long>((size_t)AKC_ENTRY << cache_bits, 0ull);
+    }
+    M.cache.e = img.data();
+    M.cache.bits = (uint32_t)cache_bits;
+    M.cache.inserted = nullptr;
+    std::vector<int32_t> longpool(1 << 20), pool((size_t)(te - tb) * 3 + (1 << 20));
+    unsigned long long long_used = 0, pool_used = 0;
+    M.pool.base = longpool.data(); M.pool.used = &long_used; M.pool.cap = longpool.size();
+    std::vector<unsigned long long> row_fix((size_t)n_rows + 1, 0ull);
+    // row fix
+    AkRowFixCtx RX;
+    RX.M = M; RX.text = text; RX.off = off; RX.n_rows = n_rows; RX.result = result; RX.ev = slots.data();
+    RX.n_events = slots.size(); RX.row_ev = row_ev.data(); RX.row_fix = row_fix.data();
+    RX.pool = pool.data(); RX.pool_used = &pool_used; RX.pool_cap = pool.size();
+    int64_t n_flagged = 0;
+    for (int64_t g = 0; g < n_rows; ++g) if (row_flag[(size_t)g]) { akr_fix_row(RX, g); ++n_flagged; }
+    AkLookupCtx X;
+    X.M = M; X.text = text; X.off = off; X.n_rows = n_rows; X.tb = tb; X.te = te; X.result = result;
+    X.ids = ids; X.id_cap = id_cap; X.ids_u16 = u16; X.splits = splits; X.splits_i32 = splits_i32;
+    X.row_flag = row_flag.data(); X.row_fix = row_fix.data(); X.pool = pool.data(); X.pool_used = &pool_used; X.pool_cap = pool.size();
+    X.any_fix = n_flagged ? 1 : 0;
+    // resolve
+    std::vector<unsigned long long> resolved(slots.size(), 0ull);
+    std::vector<uint32_t> aux(slots.size(), 0u);
+    int64_t n_miss = 0, n_exact = 0;
+    for (int64_t wt = 0; wt < n_wt; ++wt)
+        for (uint32_t o = 0; o < count[(size_t)wt]; ++o) {
+            const size_t s = (size_t)wt * cap + o;
+            AkEvent& ev = slots[s];
+            const uint32_t k = ev.meta & 7u, len = ev.meta >> 3;
+            unsigned long long k0 = 0, k1 = 0;
+            if (k <= AKE_WORD && len <= AKC_MAXLEN) akc_key01(text, tb + ev.pos, len, te, k0, k1);
+            const unsigned long long before = long_used + pool_used;
+            resolved[s] = kind == 0 ? akl_resolve<0>(X, ev, k0, k1, aux[s], st) : akl_resolve<1>(X, ev, k0, k1, aux[s], st);
+            if (k <= AKE_WORD && (resolved[s] >> 62) != AKR_CACHE && long_used + pool_used != before) ++n_miss;
+        }
+    // check (Unigram)
+    if (kind == 1) {
+        float d = 0.f;
+        for (int64_t wt = 0; wt < n_wt; ++wt)
+            for (uint32_t o = 0; o < count[(size_t)wt]; ++o) {
+                const size_t s = (size_t)wt * cap + o;
+                if ((resolved[s] >> 62) == AKR_EVENT) { d = 0.f; continue; }
+                if (aux[s] == 0u) continue;
+                d += aku_aux_wmag(aux[s]);
+                if (!aku_robust(aku_aux_ratio(aux[s]), d)) {
+                    const AkEvent ev = slots[s];
+                    long long pa;
+                    const int n = akl_uni_exact(X, tb + ev.pos, ev.meta >> 3, &pa);
+                    resolved[s] = pa >= 0 ? akr_pool(n, (unsigned long long)pa) : 0ull;
+                    ++n_exact;
+                }
+            }
+    }
+    // emit
+    int64_t at = 0;
+    for (int64_t wt = 0; wt < n_wt; ++wt)
+        for (uint32_t o = 0; o < count[(size_t)wt]; ++o) {
+            const size_t s = (size_t)wt * cap + o;
+            const int n = akr_n(resolved[s]);
+            if (n && at + n > id_cap) st |= AK_ST_OVERFLOW;
+            if (resolved[s]) akl_emit(X, resolved[s], &slots[s], at);
+            at += n;
+        }
+    stats[1] = n_flagged;
+    stats[2] = n_exact;
+    stats[3] = n_miss;
+    *status = st | (uint32_t)result[2];
+    return at;
 }
 
 int64_t hh_unigram(const uint8_t* text, const int64_t* off, int64_t n_rows, int32_t* ids, int64_t id_cap, int64_t* splits) {
@@ -732,3 +562,4 @@ int64_t hh_unigram(const uint8_t* text, const int64_t* off, int64_t n_rows, int3
 }
 
 }  // extern "C"
+

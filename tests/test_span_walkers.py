@@ -98,30 +98,6 @@ def test_single_stage_flags(flags, fn):
         assert [b[out_off[i]:out_off[i + 1]] for i in range(len(lines))] == exp
 
 
-@pytest.mark.parametrize('real', [30, 1, 2, 7])
-def test_fast_lane_structure(real):
-    """the fast kernel's chunk / halo / slow-lane structure gives the oracle's bytes and row offsets"""
-    lines = list(_lines())
-    data, off = sc.pack(lines)
-    exp, exp_off = _exp_norm(7)
-    out, out_off, st, n_slow = W.fast_normalize(data, off, real=real)
-    assert st == 0
-    assert np.array_equal(out_off, exp_off)
-    assert out.tobytes() == exp.tobytes()
-
-
-def test_fast_lane_is_mostly_fast():
-    for kind in ('hinglish', 'hindi', 'social'):
-        lines = sc.Corpus(kind, 8).lines(200000)
-        data, off = sc.pack(lines)
-        out, out_off, st, n_slow = W.fast_normalize(data, off)
-        exp, exp_off = OB.normalize_batch(lines)
-        assert st == 0 and np.array_equal(out_off, exp_off) and out.tobytes() == exp.tobytes()
-        n_chunks = data.size / 16
-        print(kind, 'slow chunks: %.2f %%' % (100.0 * n_slow / n_chunks))
-        assert n_slow / n_chunks < 0.05
-
-
 # ---- bit-parallel normalize (ak_bits.cuh / ak_norm3.cuh): the kernel's lane phases and exchange rounds on the CPU
 def test_basis_planes():
     rng = np.random.default_rng(1)
@@ -231,22 +207,6 @@ def test_bit_parallel_is_mostly_fast():
         exp, exp_off = OB.normalize_batch(lines)
         assert st == 0 and np.array_equal(out_off, exp_off) and out.tobytes() == exp.tobytes()
         assert n_slow / (data.size / 16) < 0.03
-
-
-@pytest.mark.parametrize('real,stage_cap', [(30, 18), (1, 18), (4, 1)])
-def test_segment_fast_structure(real, stage_cap):
-    lines = list(_lines())
-    data, off = sc.pack(lines)
-    ce, cs = _exp_seg(False)
-    re_, rt, rs = _exp_runs()
-    gce, gcs, gre, grt, grs, st, n_slow = W.seg_fast(data, off, flags=1 | 4, real=real, stage_cap=stage_cap)
-    assert st == 0
-    assert np.array_equal(gcs, cs) and np.array_equal(gce, ce)
-    assert np.array_equal(grs, rs) and np.array_equal(gre, re_) and np.array_equal(grt, rt)
-    me, ms = _exp_seg(True)
-    gce, gcs, _, _, _, st, _ = W.seg_fast(data, off, flags=1 | 2, real=real, stage_cap=stage_cap)
-    assert st == 0
-    assert np.array_equal(gcs, ms) and np.array_equal(gce, me)
 
 
 # ---- bit-parallel segmentation (ak_seg3.cuh)
@@ -359,16 +319,3 @@ def test_segment_bit_parallel_is_all_fast_on_normalized_text():
     for kind in ('hinglish', 'hindi', 'social'):
         lines = [O.normalize_text(s) for s in sc.Corpus(kind, 8).lines(100000)]
         assert _seg3_check(lines, 30) < 0.001
-
-
-def test_segment_fast_is_mostly_fast():
-    for kind in ('hinglish', 'hindi', 'social'):
-        lines = sc.Corpus(kind, 8).lines(200000)
-        data, off = sc.pack(lines)
-        gce, gcs, gre, grt, grs, st, n_slow = W.seg_fast(data, off, flags=5)
-        ce, cs = OB.segment_batch(lines)
-        re_, rt, rs = OB.runs_batch(lines)
-        assert st == 0 and np.array_equal(gce, ce) and np.array_equal(gcs, cs)
-        assert np.array_equal(gre, re_) and np.array_equal(grt, rt) and np.array_equal(grs, rs)
-        print(kind, 'slow chunks: %.3f %%' % (100.0 * n_slow / (data.size / 16)))
-        assert n_slow / (data.size / 16) < 0.02

@@ -101,41 +101,38 @@ def test_loader_rejects_unsupported(models_dir):
         W.load_spm(p)
 
 
-@pytest.mark.parametrize('real,cache_bits,stage_cap', [(30, 14, 24), (1, 4, 2), (3, 8, 24), (30, 2, 24)])
-def test_bpe_fast_structure(golden, bpe_rows, models_dir, real, cache_bits, stage_cap):
-    """chunked classification + word cache (tiny tables force probing and misses) == the reference ids"""
-    W.load_bpe(os.path.join(models_dir, 'bpe24k.json'))
-    rows = bpe_rows
-    lines = [r['norm'] for r in rows] + ['', '', 'ab' * 200 + ' ' + 'कख' * 90, '']
-    m = O.BpeModel(os.path.join(models_dir, 'bpe24k.json'))
-    exp = [r['ids_bpe24k'] for r in rows] + [[2, 3], [2, 3], O.bpe_encode(m, lines[-2]), [2, 3]]
-    data, off = sc.pack(lines)
-    ids, splits, st, _ = W.bpe_fast(data, off, real=real, cache_bits=cache_bits, stage_cap=stage_cap)
-    assert st == 0
-    exp_splits = np.zeros(len(lines) + 1, dtype=np.int64)
-    np.cumsum([len(e) for e in exp], out=exp_splits[1:])
-    assert np.array_equal(splits, exp_splits)
-    assert ids.tolist() == [i for e in exp for i in e]
+def _flat(exp):
+    sp = np.zeros(len(exp) + 1, dtype=np.int64)
+    np.cumsum([len(e) for e in exp], out=sp[1:])
+    return [i for e in exp for i in e], sp
 
 
-@pytest.mark.parametrize('real', [30, 1, 3])
-def test_bpe_bit_parallel_front_end(golden, bpe_rows, models_dir, real):
-    """ak_bpe3.cuh: classes / boundaries / word starts from the basis planes == the reference ids"""
+@pytest.mark.parametrize('real,cache_bits,prewarm', [(30, 14, 1), (1, 4, 0), (3, 8, 1), (30, 2, 0)])
+def test_bpe_event_stream(golden, bpe_rows, models_dir, real, cache_bits, prewarm):
+    """ak_tok.cuh, BPE: lanes -> word / row events -> word cache (tiny tables force probing and uncached words) -> ids
+    == the reference's ids"""
     W.load_bpe(os.path.join(models_dir, 'bpe24k.json'))
     rows = bpe_rows
     lines = [r['norm'] for r in rows] + ['', '', 'ab' * 200 + ' ' + '\u0915\u0916' * 90, '', 'a_b9 \u0964\u0965\u0970\u0966 x', '\t \n']
     m = O.BpeModel(os.path.join(models_dir, 'bpe24k.json'))
     exp = [r['ids_bpe24k'] for r in rows] + [O.bpe_encode(m, s) for s in lines[len(rows):]]
     data, off = sc.pack(lines)
-    ids, splits, st, _ = W.bpe_fast3(data, off, real=real)
+    ids, splits, st, stats = W.tok(0, data, off, real=real, cache_bits=cache_bits, prewarm=prewarm)
     assert st == 0
-    exp_splits = np.zeros(len(lines) + 1, dtype=np.int64)
-    np.cumsum([len(e) for e in exp], out=exp_splits[1:])
-    assert np.array_equal(splits, exp_splits)
-    assert ids.tolist() == [i for e in exp for i in e]
+    flat, sp = _flat(exp)
+    assert np.array_equal(splits, sp)
+    assert ids.tolist() == flat
+    # compact outputs: uint16 ids, int32 splits
+    ids16, sp32, st, _ = W.tok(0, data, off, real=real, cache_bits=cache_bits, prewarm=prewarm, u16=True, splits_i32=True)
+    assert st == 0 and ids16.dtype == np.uint16 and ids16.tolist() == flat and np.array_equal(sp32, sp)
+    # too few event slots per warp tile: refused with the number that was needed, and that number works
+    _, _, st, stats = W.tok(0, data, off, real=30, cap=40)
+    assert st & 1 and stats['slots_needed'] > 40
+    ids, splits, st, _ = W.tok(0, data, off, real=30, cap=(stats['slots_needed'] + 3) & ~3)
+    assert st == 0 and ids.tolist() == flat
 
 
-def test_bpe_bit_parallel_long_words(models_dir):
+def test_bpe_event_stream_long_words(models_dir):
     """words longer than the boundary masks a lane can see (its own 32 bytes + the next two lanes'): every alignment of
     the word end against the lanes, including the right halo lane whose last two bytes are not classified"""
     W.load_bpe(os.path.join(models_dir, 'bpe24k.json'))
@@ -157,13 +154,13 @@ def test_bpe_bit_parallel_long_words(models_dir):
     data, off = sc.pack(lines)
     exp = [O.bpe_encode(m, s) for s in lines]
     for real in (30, 5):
-        ids, splits, st, _ = W.bpe_fast3(data, off, real=real)
+        ids, splits, st, _ = W.tok(0, data, off, real=real)
         assert st == 0
         assert ids.tolist() == [i for e in exp for i in e]
     # the crafted rows again, each as its own batch: the row then starts at byte 0 of the first warp
     for s in lines[-55:]:
         data, off = sc.pack([s])
-        ids, splits, st, _ = W.bpe_fast3(data, off, real=30)
+        ids, splits, st, _ = W.tok(0, data, off, real=30)
         assert st == 0 and ids.tolist() == O.bpe_encode(m, s)
 
 
@@ -179,16 +176,70 @@ def test_bpe_bit_parallel_classes_match_the_tables():
     assert not T.bpe_safe[0x9FE]
 
 
-def test_bpe_fast_renormalizes(models_dir):
+def test_bpe_rows_that_are_not_nfc_are_fixed_row_by_row(models_dir):
+    """a row NFC would change is normalized and encoded on its own (row fix); the others stay on the fast path"""
     m = O.BpeModel(os.path.join(models_dir, 'bpe24k.json'))
     W.load_bpe(os.path.join(models_dir, 'bpe24k.json'))
-    lines = ['\u0928\u093c \u0915\u094d\u0937', 'abc', '\u0930\u093c\u093e', 'x']
+    lines = ['\u0928\u093c \u0915\u094d\u0937', 'abc', '\u0930\u093c\u093e', 'x', '', 'kya \u0928\u093c haal']
     data, off = sc.pack(lines)
     exp = [O.bpe_encode(m, s) for s in lines]
-    for fn in (W.bpe_fast, W.bpe_fast3):
-        ids, splits, st, attempt = fn(data, off)
-        assert attempt == 1 and st == 0
-        assert ids.tolist() == [i for e in exp for i in e]
+    ids, splits, st, stats = W.tok(0, data, off)
+    assert st == 0 and stats['flagged_rows'] == 3
+    flat, sp = _flat(exp)
+    assert ids.tolist() == flat and np.array_equal(splits, sp)
+    ids, splits, st, attempt = W.bpe(data, off)
+    assert attempt == 1 and st == 0 and ids.tolist() == flat
+
+
+@pytest.mark.parametrize('real,cache_bits,prewarm', [(30, 14, 1), (1, 4, 0), (7, 9, 1)])
+def test_unigram_event_stream(golden, models_dir, real, cache_bits, prewarm):
+    """ak_tok.cuh, Unigram: words -> cached word lattices (robustness test against the score accumulated before the
+    word, exact row Viterbi otherwise) == SentencePiece's ids"""
+    W.load_spm(os.path.join(models_dir, 'spm24k.model'))
+    rows = golden['rows']
+    lines = [r['norm'] for r in rows]
+    data, off = sc.pack(lines)
+    ids, splits, st, stats = W.tok(1, data, off, real=real, cache_bits=cache_bits, prewarm=prewarm)
+    assert st == 0
+    flat, sp = _flat([r['ids_spm24k'] for r in rows])
+    assert np.array_equal(splits, sp)
+    assert ids.tolist() == flat
+    print(stats)
+
+
+def test_unigram_event_stream_exotic_rows(golden_raw, models_dir):
+    """literal U+2581, rows longer than the word-wise path takes, other white space, leading / trailing / repeated spaces"""
+    W.load_spm(os.path.join(models_dir, 'spm24k.model'))
+    um = O.UnigramModel(os.path.join(models_dir, 'spm24k.model'))
+    rows = golden_raw['rows']
+    lines = [r['norm_nc'] for r in rows]
+    extra = ['a\u2581b', '\u2581', 'x \u2581', ' \u2581y', 'a\u2581', '  lead', 'trail  ', 'a   b', '\ta\tb ', ' ', '', '\u00a0x',
+             ' '.join(['\u0915\u092e\u0932', 'kya', 'haal'] * 1500), 'z' * 70 + ' ' + '\u0915' * 80, 'a' * 9000]
+    data, off = sc.pack(lines + extra)
+    ids, splits, st, stats = W.tok(1, data, off)
+    assert st == 0
+    exp = [r['ids_spm24k'] for r in rows] + [O.unigram_encode(um, s) for s in extra]
+    flat, sp = _flat(exp)
+    assert np.array_equal(splits, sp)
+    assert ids.tolist() == flat
+    assert stats['flagged_rows'] >= 7
+
+
+def test_unigram_near_ties_take_the_exact_viterbi(models_dir):
+    """rows made long enough that the accumulated score makes cached word lattices untrustworthy: those words are
+    solved again by the exact row Viterbi, and the ids still equal SentencePiece's"""
+    W.load_spm(os.path.join(models_dir, 'spm24k.model'))
+    um = O.UnigramModel(os.path.join(models_dir, 'spm24k.model'))
+    base = sc.Corpus('hindi', 5).lines(60000)
+    lines = [' '.join(base[i:i + 25]) for i in range(0, len(base) - 25, 25)]       # ~6 KB rows (below the long-row limit)
+    lines = [s for s in lines if len(s.encode('utf-8')) <= 8000]
+    data, off = sc.pack(lines)
+    ids, splits, st, stats = W.tok(1, data, off)
+    assert st == 0
+    assert stats['exact_words'] > 0
+    exp = [O.unigram_encode(um, s) for s in lines]
+    flat, sp = _flat(exp)
+    assert np.array_equal(splits, sp) and ids.tolist() == flat
 
 
 def test_raw_mode_cores(golden_raw, models_dir):
@@ -201,10 +252,10 @@ def test_raw_mode_cores(golden_raw, models_dir):
     assert ids.tolist() == [i for r in rows for i in r['ids_spm24k']]
     safe = [r for r in rows if all(T.bpe_safe[ord(c)] for c in r['norm_nc'])]
     data, off = sc.pack([r['norm_nc'] for r in safe])
-    for fn in (W.bpe, W.bpe_fast, W.bpe_fast3):
+    for fn in (W.bpe, lambda a, b: W.tok(0, a, b)):
         ids, splits, st, _ = fn(data, off)
         assert st == 0
         assert ids.tolist() == [i for r in safe for i in r['ids_bpe24k']]
     # anything else must be refused loudly (status bit 8 = AKSHAR_ST_ALPHABET)
     data, off = sc.pack(['ok', 'x\ufb01y', '<s>'])
-    assert W.bpe_fast(data, off)[2] & 8 and W.bpe(data, off)[2] & 8 and W.bpe_fast3(data, off)[2] & 8
+    assert W.tok(0, data, off)[2] & 8 and W.bpe(data, off)[2] & 8

@@ -16,7 +16,7 @@ def build():
     csrc = os.path.join(ROOT, 'akshar_b200', 'csrc')
     models = os.path.join(csrc, 'ak_models.cpp')
     deps = [src, models] + [os.path.join(csrc, f) for f in
-                            ('ak_unicode.cuh', 'ak_bits.cuh', 'ak_norm3.cuh', 'ak_seg3.cuh', 'ak_bpe3.cuh', 'ak_text_core.cuh', 'ak_subword.cuh', 'ak_fast.cuh', 'ak_bpe_fast.cuh', 'ak_seg_fast.cuh', 'ak_models.h', 'unicode_tables.inc')]
+                            ('ak_unicode.cuh', 'ak_bits.cuh', 'ak_norm3.cuh', 'ak_seg3.cuh', 'ak_bpe3.cuh', 'ak_text_core.cuh', 'ak_subword.cuh', 'ak_fast.cuh', 'ak_tok.cuh', 'ak_tok_host.h', 'ak_wordcache.cuh', 'ak_models.h', 'unicode_tables.inc')]
     if not os.path.exists(SO) or any(os.path.getmtime(d) > os.path.getmtime(SO) for d in deps):
         subprocess.check_call(['g++', '-O2', '-std=c++17', '-shared', '-fPIC', '-o', SO, src, models])
 
@@ -28,13 +28,11 @@ def lib():
         _lib = ctypes.CDLL(SO)
         _lib.hh_normalize.restype = ctypes.c_int64
         _lib.hh_signature.restype = ctypes.c_int64
-        _lib.hh_fast_normalize.restype = ctypes.c_int64
         _lib.hh_fast_normalize3.restype = ctypes.c_int64
         _lib.hh_n3_roles.restype = ctypes.c_uint32
         _lib.hh_s3_roles.restype = ctypes.c_uint32
         _lib.hh_bpe.restype = ctypes.c_int64
-        _lib.hh_bpe_fast.restype = ctypes.c_int64
-        _lib.hh_bpe_fast3.restype = ctypes.c_int64
+        _lib.hh_tok.restype = ctypes.c_int64
         _lib.hh_unigram.restype = ctypes.c_int64
         _lib.hh_error.restype = ctypes.c_char_p
     return _lib
@@ -139,19 +137,6 @@ def unigram(data, off):
     return ids[:n], splits
 
 
-def fast_normalize(data, off, real=30):
-    """normalize_text (default flags) through the fast kernel's chunk / halo / slow-lane structure"""
-    data = np.ascontiguousarray(data, dtype=np.uint8)
-    off = np.ascontiguousarray(off, dtype=np.int64)
-    out = np.zeros(int(data.size) * 3 + 64, dtype=np.uint8)
-    out_off = np.full(off.size, -1, dtype=np.int64)
-    st = ctypes.c_uint32(0)
-    ns = ctypes.c_int64(0)
-    n = lib().hh_fast_normalize(_p(data), _p(off), ctypes.c_int64(off.size - 1), ctypes.c_int(real), _p(out), _p(out_off),
-                                ctypes.byref(st), ctypes.byref(ns))
-    return out[:n], out_off, st.value, ns.value
-
-
 def fast_normalize3(data, off, real=30, flags=7):
     """normalize_text (default flags) through the bit-parallel kernel's lane / exchange / slow-lane structure"""
     data = np.ascontiguousarray(data, dtype=np.uint8)
@@ -176,44 +161,6 @@ def n3_planes(b32):
     return P
 
 
-def bpe_fast(data, off, real=30, cache_bits=12, stage_cap=24):
-    """the fast BPE kernel's chunk / word-cache structure; same three-pass protocol as bpe()"""
-    data = np.ascontiguousarray(data, dtype=np.uint8)
-    off = np.ascontiguousarray(off, dtype=np.int64)
-    for attempt in range(2):
-        cap = int(data.size) + 2 * off.size + 16
-        ids = np.zeros(cap, dtype=np.int32)
-        splits = np.full(off.size, -1, dtype=np.int64)
-        ch = ctypes.c_int(0)
-        st = ctypes.c_uint32(0)
-        n = lib().hh_bpe_fast(_p(data), _p(off), ctypes.c_int64(off.size - 1), ctypes.c_int(real), ctypes.c_int(cache_bits),
-                              ctypes.c_int(stage_cap), _p(ids), ctypes.c_int64(cap), _p(splits), ctypes.byref(ch), ctypes.byref(st))
-        if not ch.value:
-            return ids[:n], splits, st.value, attempt
-        assert attempt == 0
-        data, off, _ = normalize(data, off, flags=0, span=32)
-        data = np.ascontiguousarray(data)
-    raise AssertionError
-
-
-def seg_fast(data, off, flags=1, real=30, stage_cap=18):
-    data = np.ascontiguousarray(data, dtype=np.uint8)
-    off = np.ascontiguousarray(off, dtype=np.int64)
-    cap = int(data.size) + off.size + 1
-    ce = np.zeros(cap, dtype=np.int32)
-    cs = np.full(off.size, -1, dtype=np.int64)
-    re_ = np.zeros(cap, dtype=np.int32)
-    rt = np.zeros(cap, dtype=np.uint8)
-    rs = np.full(off.size, -1, dtype=np.int64)
-    tot = np.zeros(2, dtype=np.int64)
-    st = ctypes.c_uint32(0)
-    ns = ctypes.c_int64(0)
-    lib().hh_seg_fast(_p(data), _p(off), ctypes.c_int64(off.size - 1), ctypes.c_uint32(flags), ctypes.c_int(real),
-                      ctypes.c_int(stage_cap), _p(ce), _p(cs), _p(re_), _p(rt), _p(rs), ctypes.c_int64(cap), _p(tot),
-                      ctypes.byref(st), ctypes.byref(ns))
-    return ce[:tot[0]], cs, re_[:tot[1]], rt[:tot[1]], rs, st.value, ns.value
-
-
 def s3_roles(byte):
     return int(lib().hh_s3_roles(ctypes.c_uint32(byte)))
 
@@ -236,21 +183,20 @@ def seg_fast3(data, off, flags=1, real=30):
     return ce[:tot[0]], cs, re_[:tot[1]], rt[:tot[1]], rs, st.value, ns.value
 
 
-def bpe_fast3(data, off, real=30):
-    """the bit-parallel BPE front end (ak_bpe3.cuh); same three-pass protocol as bpe()"""
+def tok(kind, data, off, real=30, cache_bits=14, prewarm=1, u16=False, splits_i32=False, cap=None):
+    """the event-stream encoders (ak_tok.cuh) on the CPU: lanes -> event slots -> row fix -> resolve -> check -> emit.
+    kind 0 BPE, 1 Unigram; cap = event slots per emulated warp tile -> (ids, splits, status, stats dict)"""
     data = np.ascontiguousarray(data, dtype=np.uint8)
     off = np.ascontiguousarray(off, dtype=np.int64)
-    for attempt in range(2):
-        cap = int(data.size) + 2 * off.size + 16
-        ids = np.zeros(cap, dtype=np.int32)
-        splits = np.full(off.size, -1, dtype=np.int64)
-        ch = ctypes.c_int(0)
-        st = ctypes.c_uint32(0)
-        n = lib().hh_bpe_fast3(_p(data), _p(off), ctypes.c_int64(off.size - 1), ctypes.c_int(real), _p(ids), ctypes.c_int64(cap),
-                               _p(splits), ctypes.byref(ch), ctypes.byref(st))
-        if not ch.value:
-            return ids[:n], splits, st.value, attempt
-        assert attempt == 0
-        data, off, _ = normalize(data, off, flags=0, span=32)
-        data = np.ascontiguousarray(data)
-    raise AssertionError
+    id_cap = int(data.size) * 4 + 2 * off.size + 16
+    ids = np.zeros(id_cap, dtype=np.uint16 if u16 else np.int32)
+    splits = np.full(off.size, -1, dtype=np.int32 if splits_i32 else np.int64)
+    st = ctypes.c_uint32(0)
+    stats = np.zeros(5, dtype=np.int64)
+    if cap is None:
+        cap = 64 * real + 8             # a row start and a word start at every byte
+    n = lib().hh_tok(ctypes.c_int(kind), _p(data), _p(off), ctypes.c_int64(off.size - 1), ctypes.c_int(real), ctypes.c_int(cap), ctypes.c_int(cache_bits),
+                     ctypes.c_int(prewarm), ctypes.c_int(1 if u16 else 0), ctypes.c_int(1 if splits_i32 else 0), _p(ids),
+                     ctypes.c_int64(id_cap), _p(splits), ctypes.byref(st), _p(stats))
+    assert n >= 0, 'the model does not have the shape the word-wise Unigram path needs'
+    return ids[:n], splits, st.value, dict(events=int(stats[0]), flagged_rows=int(stats[1]), exact_words=int(stats[2]), misses=int(stats[3]), slots_needed=int(stats[4]))
