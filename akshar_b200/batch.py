@@ -124,9 +124,9 @@ class Engine:
             cap *= 2                        # slots per warp tile are a power of two
         return 2 * (n_bytes // 960 + 4) * 21 * (cap - 256) + (1 << 20)
 
-    @staticmethod
-    def _stream():
-        return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    def _stream(self):
+        # the stream of THIS engine's device, whatever the caller's current device is
+        return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
     def launch_count(self):
         return int(self.lib.akshar_launch_count(self._h))
@@ -388,10 +388,20 @@ class Engine:
 
     # ------------------------------------------------------------------ host -> ids, pipelined
     def encode_host_pipelined(self, h_data, h_off, kind, normalize_roman=True, clean_hinglish=True, chunk_bytes=None,
-                              out_ids=None, out_splits=None):
-        """aksharTokenizer.encode over a batch that lives in (pinned) HOST memory, returning host tensors:
-        the batch is cut into row ranges of ~chunk_bytes; the H2D copy of chunk k+1, the kernels of chunk k and the
-        D2H copy of chunk k-1 run on three streams.  -> (ids int32 [total] pinned, row_splits int64 [n_rows + 1] pinned)"""
+                              out_ids=None, out_splits=None, compact=False):
+        """aksharTokenizer.encode over a batch that lives in (pinned) HOST memory, returning host tensors: the batch is cut
+        into row ranges of ~chunk_bytes; the H2D copy of chunk k+1, the kernels of chunk k and the D2H copy of chunk k-2
+        run on three streams.
+
+        compact=False -> (ids int32 [total], row_splits int64 [n_rows + 1])
+        compact=True  -> `CompactIds`: uint16 ids (the vocabulary must fit) and int32 row splits RELATIVE TO THEIR CHUNK
+                         (+ the chunks' first rows and first ids): a third of the bytes over the host link;
+                         `.row_splits()` widens them on the host.
+
+        Without out_ids / out_splits the results are views of pinned buffers that the engine keeps and REUSES: they are
+        valid until the next call of this method on the same engine (pinning fresh memory for every call would cost more
+        than the call).  A caller that needs them longer passes its own pinned tensors; a tensor that is too small is an
+        error, it is never swapped silently."""
         import os
         import numpy as np
         from . import shard
@@ -406,25 +416,36 @@ class Engine:
         max_b = max(int(off_np[hi] - off_np[lo]) for lo, hi in ranges)
         max_r = max(hi - lo for lo, hi in ranges)
         flags = (C.NORM_ROMAN if normalize_roman else 0) | (C.NORM_CLEAN if clean_hinglish else 0)
+        if compact and self.lib.akshar_vocab_size(self._h, kind) > 65536:
+            raise ValueError('compact ids need a vocabulary of at most 65536 entries')
+        out_flags = (C.OUT_IDS_U16 | C.OUT_SPLITS_I32) if compact else 0
+        id_dtype = torch.int16 if compact else torch.int32          # (uint16 bit patterns; torch copies them as they are)
+        sp_dtype = torch.int32 if compact else torch.int64
         ncap = max_b + (max_b >> 3) + 1024
         cap = (max_b >> 1) + 2 * max_r + 1024
         ws = self._workspace(ncap, max_r)
         # pinned result buffers, device double buffers and streams are kept by the engine: repeated calls allocate nothing
         pc = self.__dict__.setdefault('_pipe_cache', {})
         est = (total_bytes >> 1) + 2 * n_rows + 1024
+        key_sp, key_id = ('splits', sp_dtype), ('ids', id_dtype)
         if out_splits is None:
-            if pc.get('splits') is None or pc['splits'].numel() != n_rows + 1:
-                pc['splits'] = torch.empty(n_rows + 1, dtype=torch.int64).pin_memory()
-            out_splits = pc['splits']
-        if out_ids is None or out_ids.numel() < est:
-            if pc.get('ids') is None or pc['ids'].numel() < est:
-                pc['ids'] = torch.empty(est, dtype=torch.int32).pin_memory()
-            out_ids = pc['ids']
+            if pc.get(key_sp) is None or pc[key_sp].numel() != n_rows + 1:
+                pc[key_sp] = torch.empty(n_rows + 1, dtype=sp_dtype).pin_memory()
+            out_splits = pc[key_sp]
+        elif out_splits.numel() < n_rows + 1 or out_splits.dtype != sp_dtype:
+            raise ValueError('out_splits must hold n_rows + 1 = %d entries of %s' % (n_rows + 1, sp_dtype))
+        own_ids = out_ids is not None
+        if out_ids is None:
+            if pc.get(key_id) is None or pc[key_id].numel() < est:
+                pc[key_id] = torch.empty(est, dtype=id_dtype).pin_memory()
+            out_ids = pc[key_id]
+        elif out_ids.dtype != id_dtype:
+            raise ValueError('out_ids must be %s' % id_dtype)
         if 'streams' not in pc:
             pc['streams'] = tuple(torch.cuda.Stream(device=dev) for _ in range(3))
         s_in, s_comp, s_out = pc['streams']
         NSETS = 3        # input / compute / output of three consecutive chunks in flight; the host trails two chunks behind
-        key = (max_b, max_r, NSETS)
+        key = (max_b, max_r, NSETS, compact)
         sets = pc.get('sets') if pc.get('sets_key') == key else None
         if sets is None:
             sets = []
@@ -434,18 +455,18 @@ class Engine:
                     'off': torch.empty(max_r + 1, dtype=torch.int64, device=dev),
                     'norm': torch.empty(max(ncap, 1), dtype=torch.uint8, device=dev),
                     'norm_off': torch.empty(max_r + 1, dtype=torch.int64, device=dev),
-                    'ids': torch.empty(max(cap, 1), dtype=torch.int32, device=dev),
-                    'splits': torch.empty(max_r + 1, dtype=torch.int64, device=dev),
+                    'ids': torch.empty(max(cap, 1), dtype=id_dtype, device=dev),
+                    'splits': torch.empty(max_r + 1, dtype=sp_dtype, device=dev),
                     'result': torch.empty(4, dtype=torch.int64, device=dev),
-                    'h_off': torch.empty(max_r + 1, dtype=torch.int64).pin_memory(),
                     'ev_in': torch.cuda.Event(), 'ev_comp': torch.cuda.Event(), 'ev_out': torch.cuda.Event(),
                 })
         pc['sets'], pc['sets_key'] = sets, key
         cur = torch.cuda.current_stream(dev)
         for st in (s_in, s_comp, s_out):
             st.wait_stream(cur)
-        state = {'tok': 0, 'ok': True}
-        out_splits[0] = 0
+        state = {'tok': 0}
+        chunk_rows = np.array([lo for lo, _ in ranges] + [n_rows], dtype=np.int64)
+        chunk_ids = np.zeros(len(ranges) + 1, dtype=np.int64)
         trace = [] if os.environ.get('AKSHAR_PIPE_TRACE') else None
         if trace is not None:
             t0ev = torch.cuda.Event(enable_timing=True)
@@ -457,6 +478,21 @@ class Engine:
                 e.record(stream)
                 trace.append((what, k, e))
 
+        def redo_chunk(k):
+            """a chunk whose fast call raised a status: the same rows through the plain path (which retries with larger
+            capacities / the row-by-row mode) -- only this chunk, the others keep their results"""
+            lo, hi = ranges[k]
+            b0, b1 = int(off_np[lo]), int(off_np[hi])
+            sub = (h_data[b0:b1], (h_off[lo:hi + 1] - b0))
+            with torch.cuda.stream(s_out):
+                ids, _ = self.tokenizer_encode_batch(sub, kind, normalize_roman, clean_hinglish)
+                v = ids.values
+                sp = ids.splits
+                if compact:
+                    v = v.to(torch.int16)
+                    sp = sp.to(torch.int32)
+                return v, sp, int(v.numel())
+
         def finish(k):
             lo, hi = ranges[k]
             S = sets[k % NSETS]
@@ -464,75 +500,103 @@ class Engine:
                 s_out.wait_event(S['ev_comp'])
                 r = S['result'].cpu()          # waits for chunk k's kernels only; later chunks are already enqueued
                 n, bits = int(r[0]), int(r[2])
+                d_ids, d_sp = S['ids'], S['splits']
                 if bits:
-                    state['ok'] = False
-                    return
+                    self.redone_chunks = getattr(self, 'redone_chunks', 0) + 1
+                    d_ids, d_sp, n = redo_chunk(k)
                 if state['tok'] + n > out_ids.numel():
-                    state['ok'] = False
-                    return
+                    if own_ids:
+                        raise ValueError('out_ids is too small: %d ids so far, %d more in this chunk' % (state['tok'], n))
+                    grown = torch.empty(max(2 * out_ids.numel(), state['tok'] + n), dtype=id_dtype).pin_memory()
+                    torch.cuda.synchronize(dev)
+                    grown[:state['tok']].copy_(out_ids[:state['tok']])
+                    pc[key_id] = grown
+                    state['out_ids'] = grown
+                dst = state.get('out_ids', out_ids)
                 mark(s_out, 'd2h_begin', k)
-                out_ids[state['tok']:state['tok'] + n].copy_(S['ids'][:n], non_blocking=True)
-                sp = S['splits'][1:hi - lo + 1]
-                if state['tok']:
+                dst[state['tok']:state['tok'] + n].copy_(d_ids[:n], non_blocking=True)
+                sp = d_sp[1:hi - lo + 1]
+                if not compact and state['tok']:
                     sp = sp + state['tok']
                 out_splits[lo + 1:hi + 1].copy_(sp, non_blocking=True)
                 S['ev_out'].record(s_out)
                 mark(s_out, 'd2h_end', k)
+                chunk_ids[k] = state['tok']
                 state['tok'] += n
 
-        for k, (lo, hi) in enumerate(ranges):
-            S = sets[k % NSETS]
-            b0, b1 = int(off_np[lo]), int(off_np[hi])
-            nb, nr = b1 - b0, hi - lo
-            with torch.cuda.stream(s_in):
-                if k >= NSETS:
-                    s_in.wait_event(S['ev_comp'])      # the kernels that read this input buffer have finished
-                # the rows keep their ABSOLUTE offsets (the C ABI takes text_begin / text_end): no per-chunk rebasing on
-                # the host, the offsets go to the device straight from the caller's (pinned) array
-                mark(s_in, 'h2d_begin', k)
-                S['text'][:nb].copy_(h_data[b0:b1], non_blocking=True)
-                S['off'][:nr + 1].copy_(h_off[lo:hi + 1], non_blocking=True)
-                S['ev_in'].record(s_in)
-                mark(s_in, 'h2d_end', k)
-            with torch.cuda.stream(s_comp):
-                s_comp.wait_event(S['ev_in'])
-                if k >= NSETS:
-                    s_comp.wait_event(S['ev_out'])     # chunk k-NSETS's results left this set's output buffers
-                rc = self.lib.akshar_tokenizer_encode_batch(
-                    self._h, S['text'].data_ptr() - b0, S['off'].data_ptr(), nr, b0, b1, flags, kind, C.MODE_TILES, S['norm'].data_ptr(),
-                    ncap, S['norm_off'].data_ptr(), S['ids'].data_ptr(), cap, S['splits'].data_ptr(), S['result'].data_ptr(),
-                    ws.data_ptr(), ws.numel(), ctypes.c_void_p(s_comp.cuda_stream))
-                if rc != 0:
-                    self.lib.akshar_word_cache_hold(self._h, 0)
-                    self._err(rc, 'akshar_tokenizer_encode_batch')
-                if k == 0:
-                    # the chunks are ONE batch: the ones that follow keep the words this one added to the cache
-                    self.lib.akshar_word_cache_hold(self._h, 1)
-                S['ev_comp'].record(s_comp)
-                mark(s_comp, 'comp_end', k)
-            if k >= 2:
-                finish(k - 2)          # its kernels ended while chunk k-1 ran: no wait, the copy engines never idle
-                if not state['ok']:
-                    break
-        self.lib.akshar_word_cache_hold(self._h, 0)
-        for k in range(max(0, len(ranges) - 2), len(ranges)):
-            if state['ok']:
+        out_splits[0] = 0
+        try:
+            for k, (lo, hi) in enumerate(ranges):
+                S = sets[k % NSETS]
+                b0, b1 = int(off_np[lo]), int(off_np[hi])
+                nb, nr = b1 - b0, hi - lo
+                with torch.cuda.stream(s_in):
+                    if k >= NSETS:
+                        s_in.wait_event(S['ev_comp'])      # the kernels that read this input buffer have finished
+                    # the rows keep their ABSOLUTE offsets (the C ABI takes text_begin / text_end): no per-chunk rebasing on
+                    # the host, the offsets go to the device straight from the caller's (pinned) array
+                    mark(s_in, 'h2d_begin', k)
+                    S['text'][:nb].copy_(h_data[b0:b1], non_blocking=True)
+                    S['off'][:nr + 1].copy_(h_off[lo:hi + 1], non_blocking=True)
+                    S['ev_in'].record(s_in)
+                    mark(s_in, 'h2d_end', k)
+                with torch.cuda.stream(s_comp):
+                    s_comp.wait_event(S['ev_in'])
+                    if k >= NSETS:
+                        s_comp.wait_event(S['ev_out'])     # chunk k-NSETS's results left this set's output buffers
+                    rc = self.lib.akshar_tokenizer_encode_batch_ex(
+                        self._h, S['text'].data_ptr() - b0, S['off'].data_ptr(), nr, b0, b1, flags, kind, C.MODE_TILES,
+                        S['norm'].data_ptr(), ncap, S['norm_off'].data_ptr(), S['ids'].data_ptr(), cap, S['splits'].data_ptr(),
+                        out_flags, S['result'].data_ptr(), ws.data_ptr(), ws.numel(), ctypes.c_void_p(s_comp.cuda_stream))
+                    if rc != 0:
+                        self._err(rc, 'akshar_tokenizer_encode_batch_ex')
+                    S['ev_comp'].record(s_comp)
+                    mark(s_comp, 'comp_end', k)
+                if k >= 2:
+                    finish(k - 2)          # its kernels ended while chunk k-1 ran: no wait, the copy engines never idle
+            for k in range(max(0, len(ranges) - 2), len(ranges)):
                 finish(k)
-        for st in (s_in, s_comp, s_out):
-            cur.wait_stream(st)
-        torch.cuda.synchronize(dev)
+        finally:
+            for st in (s_in, s_comp, s_out):
+                cur.wait_stream(st)
+            torch.cuda.synchronize(dev)
         if trace:
             print('pipe trace (ms): ' + ' '.join('%s%d=%.2f' % (w, k, t0ev.elapsed_time(e)) for w, k, e in trace))
-        if not state['ok']:
-            # a chunk overflowed or needs the row-by-row mode: the plain path handles retries
-            ids, _ = self.tokenizer_encode_batch((h_data, h_off), kind, normalize_roman, clean_hinglish)
-            n = ids.values.numel()
-            if out_ids.numel() < n:
-                out_ids = torch.empty(n, dtype=torch.int32).pin_memory()
-            out_ids[:n].copy_(ids.values)
-            out_splits.copy_(ids.splits)
-            return out_ids[:n], out_splits
-        return out_ids[:state['tok']], out_splits
+        out_ids = state.get('out_ids', out_ids)
+        chunk_ids[len(ranges)] = state['tok']
+        if compact:
+            return CompactIds(out_ids[:state['tok']], out_splits[:n_rows + 1], chunk_rows, chunk_ids)
+        return out_ids[:state['tok']], out_splits[:n_rows + 1]
+
+
+class CompactIds:
+    """ids of a batch as they cross the host link: uint16 ids (held in an int16 tensor, same bits) and int32 row splits
+    relative to the first id of the row's CHUNK; chunk c holds rows chunk_rows[c] .. chunk_rows[c + 1] - 1 and its first
+    id is ids[chunk_ids[c]]"""
+
+    def __init__(self, ids, splits32, chunk_rows, chunk_ids):
+        self.ids16 = ids
+        self.splits32 = splits32
+        self.chunk_rows = chunk_rows
+        self.chunk_ids = chunk_ids
+
+    def numel(self):
+        return self.ids16.numel()
+
+    def ids(self):
+        """uint16 numpy view of the ids"""
+        import numpy as np
+        return self.ids16.numpy().view(np.uint16)
+
+    def row_splits(self):
+        """int64 row splits of the whole batch (widened on the host)"""
+        import numpy as np
+        sp = self.splits32.numpy().astype(np.int64)
+        for c in range(len(self.chunk_rows) - 1):
+            lo, hi = int(self.chunk_rows[c]), int(self.chunk_rows[c + 1])
+            sp[lo + 1:hi + 1] += int(self.chunk_ids[c])
+        sp[0] = 0
+        return sp
 
 
 _engines = {}

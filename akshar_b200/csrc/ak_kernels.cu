@@ -69,6 +69,18 @@ struct akshar_ctx {
     int occ_norm = 0, occ_seg = 0, occ_bpe = 0, occ_uni = 0, occ_sig = 0, occ_nf_write = 0, occ_nf3 = 0, occ_sf3 = 0;
 };
 
+// the entry points run on the context's device and leave the caller's current device as they found it
+struct AkDeviceGuard {
+    int prev = -1;
+    bool switched = false;
+    explicit AkDeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) == cudaSuccess && prev != dev) switched = cudaSetDevice(dev) == cudaSuccess;
+    }
+    ~AkDeviceGuard() {
+        if (switched) cudaSetDevice(prev);
+    }
+};
+
 #define AK_CUDA(ctx, call)                                                                         \
     do {                                                                                           \
         cudaError_t e_ = (call);                                                                   \
@@ -112,6 +124,7 @@ int akshar_ctx_create(int device, akshar_ctx** out) {
     if (!ctx) return AKSHAR_E_ARG;
     ctx->device = device;
     *out = ctx;      // returned even on failure so that akshar_last_error can be read; caller destroys it
+    AkDeviceGuard device_guard(device);
     AK_CUDA(ctx, cudaSetDevice(device));
     cudaDeviceProp prop;
     AK_CUDA(ctx, cudaGetDeviceProperties(&prop, device));
@@ -163,7 +176,7 @@ static void ak_free_list(std::vector<void*>& v) {
 
 void akshar_ctx_destroy(akshar_ctx* ctx) {
     if (!ctx) return;
-    cudaSetDevice(ctx->device);
+    AkDeviceGuard device_guard(ctx->device);
     ak_free_list(ctx->allocs);
     ak_free_list(ctx->bpe_allocs);
     ak_free_list(ctx->uni_allocs);
@@ -186,6 +199,7 @@ int akshar_word_cache_hold(akshar_ctx* ctx, int hold) {
 }
 
 int akshar_timing_enable(akshar_ctx* ctx, int enable) {
+    AkDeviceGuard device_guard(ctx ? ctx->device : 0);
     if (!ctx) return AKSHAR_E_ARG;
     AK_CUDA(ctx, cudaSetDevice(ctx->device));
     if (enable)
@@ -467,6 +481,7 @@ int akshar_normalize_batch(akshar_ctx* ctx, const uint8_t* d_text, const int64_t
                            int64_t text_begin, int64_t text_end, uint32_t flags, int mode, uint8_t* d_out_text,
                            int64_t out_capacity, int64_t* d_out_row_offsets, int64_t* d_result, void* d_workspace,
                            size_t workspace_bytes, void* stream) {
+    AkDeviceGuard device_guard(ctx ? ctx->device : 0);
     AkCall C;
     int rc = ak_begin(ctx, d_text, d_row_offsets, n_rows, text_begin, text_end, mode, 0, d_result, d_workspace, workspace_bytes,
                       stream, C);
@@ -484,6 +499,7 @@ int akshar_segment_batch(akshar_ctx* ctx, const uint8_t* d_text, const int64_t* 
                          int64_t cluster_capacity, int64_t* d_cluster_splits, int32_t* d_run_ends, uint8_t* d_run_tags,
                          int64_t run_capacity, int64_t* d_run_splits, int64_t* d_result, void* d_workspace,
                          size_t workspace_bytes, void* stream) {
+    AkDeviceGuard device_guard(ctx ? ctx->device : 0);
     AkCall C;
     int rc = ak_begin(ctx, d_text, d_row_offsets, n_rows, text_begin, text_end, mode, 0, d_result, d_workspace, workspace_bytes,
                       stream, C);
@@ -573,6 +589,7 @@ int akshar_signature_batch(akshar_ctx* ctx, const uint8_t* d_text, const int64_t
                            int64_t text_begin, int64_t text_end, uint8_t* d_out_text, int64_t out_capacity,
                            int64_t* d_out_row_offsets, int64_t* d_result, void* d_workspace, size_t workspace_bytes,
                            void* stream) {
+    AkDeviceGuard device_guard(ctx ? ctx->device : 0);
     AkCall C;
     int rc = ak_begin(ctx, d_text, d_row_offsets, n_rows, text_begin, text_end, AKSHAR_MODE_ROWS, AK_ROWS_BLOCK, d_result,
                       d_workspace, workspace_bytes, stream, C);
@@ -599,6 +616,7 @@ static int ak_load_spm_model(akshar_ctx* ctx, const void* proto, size_t len);
 // no exception crosses the ABI: a model that makes a parser or an allocation throw is a model error
 int akshar_load_bpe_json(akshar_ctx* ctx, const char* json, size_t len) {
     if (!ctx || !json) return AKSHAR_E_ARG;
+    AkDeviceGuard device_guard(ctx->device);
     try {
         return ak_load_bpe_json(ctx, json, len);
     } catch (const std::exception& e) {
@@ -611,6 +629,7 @@ int akshar_load_bpe_json(akshar_ctx* ctx, const char* json, size_t len) {
 }
 int akshar_load_spm_model(akshar_ctx* ctx, const void* proto, size_t len) {
     if (!ctx || !proto) return AKSHAR_E_ARG;
+    AkDeviceGuard device_guard(ctx->device);
     try {
         return ak_load_spm_model(ctx, proto, len);
     } catch (const std::exception& e) {
@@ -1034,6 +1053,7 @@ int akshar_encode_bpe_batch(akshar_ctx* ctx, const uint8_t* d_text, const int64_
                             int64_t text_begin, int64_t text_end, int mode, int32_t* d_ids, int64_t id_capacity,
                             int64_t* d_id_splits, int64_t* d_result, void* d_workspace, size_t workspace_bytes,
                             void* stream) {
+    AkDeviceGuard device_guard(ctx ? ctx->device : 0);
     AkCall C;
     int rc = ak_begin(ctx, d_text, d_row_offsets, n_rows, text_begin, text_end, mode, 0, d_result, d_workspace, workspace_bytes,
                       stream, C);
@@ -1055,6 +1075,7 @@ int akshar_encode_unigram_batch(akshar_ctx* ctx, const uint8_t* d_text, const in
                                 int64_t text_begin, int64_t text_end, int mode, int32_t* d_ids, int64_t id_capacity,
                                 int64_t* d_id_splits, int64_t* d_result, void* d_workspace, size_t workspace_bytes,
                                 void* stream) {
+    AkDeviceGuard device_guard(ctx ? ctx->device : 0);
     AkCall C;
     if (mode != AKSHAR_MODE_TILES && mode != AKSHAR_MODE_ROWS) return AKSHAR_E_ARG;
     int rc = ak_begin(ctx, d_text, d_row_offsets, n_rows, text_begin, text_end, AKSHAR_MODE_ROWS, AK_ROWS_BLOCK, d_result,
@@ -1088,6 +1109,7 @@ int akshar_tokenizer_encode_batch_ex(akshar_ctx* ctx, const uint8_t* d_text, con
                                      uint8_t* d_norm_text, int64_t norm_capacity, int64_t* d_norm_row_offsets, void* d_ids,
                                      int64_t id_capacity, void* d_id_splits, uint32_t out_flags, int64_t* d_result,
                                      void* d_workspace, size_t workspace_bytes, void* stream) {
+    AkDeviceGuard device_guard(ctx ? ctx->device : 0);
     if (!ctx) return AKSHAR_E_ARG;
     if (norm_capacity < 0 || !d_norm_row_offsets || (!d_norm_text && norm_capacity > 0) || (norm_flags & ~15u) ||
         (kind != 0 && kind != 1) || !d_id_splits || id_capacity < 0 || (!d_ids && id_capacity > 0) || (out_flags & ~3u)) {

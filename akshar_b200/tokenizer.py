@@ -12,7 +12,7 @@ from . import _lib as C
 from .batch import engine
 from .normalize import normalize_text, normalize_batch
 from .segment import (segment_akshars, detect_code_switches, analyze_text_composition, segment_akshars_batch,
-                      analyze_text_composition_batch)
+                      analyze_text_composition_batch, detect_code_switches_batch)
 
 _SPM_NORMAL, _SPM_UNKNOWN, _SPM_CONTROL, _SPM_USER, _SPM_UNUSED, _SPM_BYTE = 1, 2, 3, 4, 5, 6
 
@@ -69,14 +69,14 @@ class aksharTokenizer:
 
     # ------------------------------------------------------------------ reference API
     def preprocess(self, text: str) -> str:
-        return normalize_text(text, normalize_roman=self.normalize_roman, clean_hinglish=self.clean_hinglish)
+        return normalize_batch([text], self.normalize_roman, self.clean_hinglish, device=self._device)[0]
 
     def tokenize(self, text: str, return_metadata: bool = False) -> Union[List[str], dict]:
         norm = self.preprocess(text)
         if return_metadata:
-            meta = analyze_text_composition(norm)
+            meta = analyze_text_composition_batch([norm], device=self._device)[0]
         if self.model is None:
-            tokens = segment_akshars(norm)
+            tokens = segment_akshars_batch([norm], device=self._device)[0]
         else:
             tokens = self._pieces(self._encode_normalized([norm])[0])
         if return_metadata:
@@ -112,10 +112,10 @@ class aksharTokenizer:
         return {
             'original': text,
             'normalized': norm,
-            'akshars': segment_akshars(norm),
-            'code_switches': detect_code_switches(norm),
+            'akshars': segment_akshars_batch([norm], device=self._device)[0],
+            'code_switches': detect_code_switches_batch([norm], device=self._device)[0],
             'tokens': self.tokenize(text),
-            'stats': analyze_text_composition(norm),
+            'stats': analyze_text_composition_batch([norm], device=self._device)[0],
         }
 
     def vocab_size(self) -> int:
@@ -132,27 +132,28 @@ class aksharTokenizer:
             return ids, norm
         return [r.tolist() for r in ids.rows()]
 
-    def encode_batch_host(self, h_data, h_offsets, out_ids=None, out_splits=None):
+    def encode_batch_host(self, h_data, h_offsets, out_ids=None, out_splits=None, compact=False):
         """encode() over a batch given as pinned host tensors (uint8 text, int64 row offsets) -> pinned host tensors
-        (int32 ids, int64 row_splits); copies and kernels are pipelined over three streams"""
+        (int32 ids, int64 row_splits), or with compact=True a `CompactIds` (uint16 ids, int32 chunk-relative splits: a third
+        of the bytes over the host link); copies and kernels are pipelined over three streams.  The results live in buffers
+        the engine reuses: see Engine.encode_host_pipelined."""
         if self.model is None:
             raise ValueError("need model for IDs")
         return self._eng.encode_host_pipelined(h_data, h_offsets, self.model.kind, self.normalize_roman, self.clean_hinglish,
-                                               out_ids=out_ids, out_splits=out_splits)
+                                               out_ids=out_ids, out_splits=out_splits, compact=compact)
 
     def tokenize_batch(self, texts):
         """tokenize() over a batch -> list[list[str]]"""
         if self.model is None:
-            norm = normalize_batch(texts, self.normalize_roman, self.clean_hinglish)
-            return segment_akshars_batch(norm)
+            norm = normalize_batch(texts, self.normalize_roman, self.clean_hinglish, device=self._device)
+            return segment_akshars_batch(norm, device=self._device)
         return [self._pieces(ids) for ids in self.encode_batch(texts)]
 
     def explain_batch(self, texts):
-        norm = normalize_batch(texts, self.normalize_roman, self.clean_hinglish)
-        from .segment import detect_code_switches_batch
-        ak = segment_akshars_batch(norm)
-        cs = detect_code_switches_batch(norm)
-        st = analyze_text_composition_batch(norm)
+        norm = normalize_batch(texts, self.normalize_roman, self.clean_hinglish, device=self._device)
+        ak = segment_akshars_batch(norm, device=self._device)
+        cs = detect_code_switches_batch(norm, device=self._device)
+        st = analyze_text_composition_batch(norm, device=self._device)
         tk = self.tokenize_batch(texts)
         return [{'original': t, 'normalized': n, 'akshars': a, 'code_switches': c, 'tokens': k, 'stats': s}
                 for t, n, a, c, k, s in zip(texts, norm, ak, cs, tk, st)]

@@ -1,17 +1,21 @@
 #!/usr/bin/env python
 """bench.py -- the hot path's headline metric on B200 (BASELINE.json): UTF-8 input GB/s (+ tokens/s) of batch encode.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--mb MB] [--workload bpe|unigram|pipeline]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--mb MB] [--workload bpe|unigram|pipeline|mixed]
 
 One step = one pass of aksharTokenizer.encode over one batch: normalize_text -> BPE-24k ids for every row of the
-batch (BASELINE.json configs[1]: "BPE vocab 24k batch encode of 1 GB synthetic Hinglish, 1 B200").  With N > 1 every
-rank (one process per GPU, launched by torchrun) encodes its own 1 GB shard of sentences -- weak scaling, no collective
-on the data path; only the timing is reduced (max over ranks).
+batch (BASELINE.json configs[1]: "BPE vocab 24k batch encode of 1 GB synthetic Hinglish, 1 B200").  Run without
+--workload on one GPU, the line also carries `also`: configs[2] (Unigram-24k, 1 GiB Hindi) and configs[3] (normalize +
+akshars + script runs, 4 GiB social Hinglish) measured the same way.  With N > 1 every rank (one process per GPU, launched
+by torchrun) encodes its own shard of configs[4]'s mixed corpus (2 : 1 : 1 Hinglish / Hindi / social, 4 GiB per GPU = 32 GiB
+at N = 8, fed as 1 GiB batches) -- weak scaling, no collective on the data path; only the timing is reduced (max over
+ranks).
 
-Prints ONE JSON line.  `value` is device-timed with the input already in HBM; `e2e` is the same metric through the
-public batch API from pinned host buffers with the H2D copy of the text and the D2H read of the ids inside the
-timed region.  `roofline` is the dominant kernel's algorithmic bytes / its CUDA-event time against
-MEASURED_PEAKS.json; `cpu_baseline` is the oracle port of the same path on the host cores (bounded sample).
+Prints ONE JSON line.  `value` is device-timed with the input already in HBM; `e2e` is the same metric through the public
+batch API from pinned host buffers with the H2D copy of the text and the D2H read of the ids inside the timed region.
+`roofline` is the dominant kernel's algorithmic bytes / its CUDA-event time against MEASURED_PEAKS.json (and, per stage,
+SURVEY section 8d's bytes over the stage's kernels); `cpu_baseline` is the oracle port of the same path on the host cores
+(bounded sample) -- the same rows are compared id for id with the GPU's before anything is timed (`parity_in_run`).
 --impl reference times that CPU implementation alone, with every host core.
 """
 import argparse
@@ -22,6 +26,7 @@ import subprocess
 import sys
 import threading
 import time
+import zlib
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 for p in (ROOT, os.path.join(ROOT, 'tools')):
@@ -29,16 +34,10 @@ for p in (ROOT, os.path.join(ROOT, 'tools')):
         sys.path.insert(0, p)
 
 MODELS = os.path.join(ROOT, 'tests', 'golden', 'models')
-# DRAM traffic per INPUT byte of each hot kernel: (dram__bytes_read.sum + dram__bytes_write.sum) / input bytes from the
-# `ncu --set full` captures at 256 MiB summarised in profiles/r01_ncu_full_summary.csv; scaled to the run's size below
-TRAFFIC_PER_INPUT_BYTE = {
-    'ak_nf3_classify_kernel': (292.68 + 63.60) / 268.44,
-    'ak_nf_write_kernel': (372.49 + 248.46) / 268.44,
-    'ak_bf3_encode_kernel': (446.12 + 398.04) / 268.44,
-    'ak_sf3_kernel': (301.27 + 496.13) / 268.44,
-}
 CHUNK = 32 << 20
 SEED = 20261018
+KIND = {'bpe': 'hinglish', 'unigram': 'hindi', 'pipeline': 'social', 'mixed': 'mixed'}
+MIX = ('hinglish', 'hinglish', 'hindi', 'social')        # configs[4]: 2 : 1 : 1, chunk by chunk
 
 
 # ------------------------------------------------------------------ synthetic corpus
@@ -48,6 +47,8 @@ _corpus = {}
 def _gen_chunk(args):
     kind, index, nbytes = args
     import synth_corpus as sc
+    if kind == 'mixed':
+        kind = MIX[index % len(MIX)]
     if kind not in _corpus:
         _corpus[kind] = sc.Corpus(kind, SEED)
     return _corpus[kind].chunk(index, nbytes)
@@ -73,12 +74,17 @@ def make_corpus(kind, nbytes, first_chunk=0, procs=None):
 
 
 # ------------------------------------------------------------------ CPU arm: the oracle port on the host cores
+def _crc(a):
+    import numpy as np
+    return zlib.crc32(np.ascontiguousarray(a).tobytes())
+
+
 def _cpu_init(workload):
     sys.path.insert(0, os.path.join(ROOT, 'oracle'))
     import akshar_oracle as O
     global _O, _M
     _O = O
-    if workload == 'bpe':
+    if workload in ('bpe', 'mixed'):
         _M = O.BpeModel(os.path.join(MODELS, 'bpe24k.json'))
     elif workload == 'unigram':
         _M = O.UnigramModel(os.path.join(MODELS, 'spm24k.model'))
@@ -87,18 +93,29 @@ def _cpu_init(workload):
 
 
 def _cpu_work(args):
+    """-> (token count, one checksum per row of what the reference returns for it)"""
+    import numpy as np
     workload, lines = args
     n = 0
+    sums = []
     for s in lines:
         norm = _O.normalize_text(s)
-        if workload == 'bpe':
-            n += len(_O.bpe_encode(_M, norm))
+        if workload in ('bpe', 'mixed'):
+            ids = _O.bpe_encode(_M, norm)
+            n += len(ids)
+            sums.append(_crc(np.asarray(ids, dtype=np.int32)))
         elif workload == 'unigram':
-            n += len(_O.unigram_encode(_M, norm))
+            ids = _O.unigram_encode(_M, norm)
+            n += len(ids)
+            sums.append(_crc(np.asarray(ids, dtype=np.int32)))
         else:
             cps = [ord(c) for c in norm]
-            n += len(_O.grapheme_breaks(cps)) + len(_O.script_runs(cps))
-    return n
+            ce = _O.cp_ends_to_byte_ends(cps, _O.segment_breaks(cps))
+            runs = _O.detect_code_switches(norm)
+            n += len(ce) + len(runs)
+            sums.append(zlib.crc32(norm.encode('utf-8')) ^ _crc(np.asarray(ce, dtype=np.int32)) ^
+                        zlib.crc32(repr([(len(seg.encode('utf-8')), lab) for seg, lab in runs]).encode()))
+    return n, sums
 
 
 class CpuArm:
@@ -116,11 +133,44 @@ class CpuArm:
         self.pool = mp.get_context('fork').Pool(self.cores, initializer=_cpu_init, initargs=(workload,))
         per = max(1, len(self.lines) // (self.cores * 4))
         self.jobs = [(workload, self.lines[i:i + per]) for i in range(0, len(self.lines), per)]
+        self.sums = None
 
     def step(self):
         t = time.perf_counter()
-        tokens = sum(self.pool.map(_cpu_work, self.jobs))
-        return time.perf_counter() - t, tokens
+        res = self.pool.map(_cpu_work, self.jobs)
+        dt = time.perf_counter() - t
+        self.sums = [c for _, s in res for c in s]
+        return dt, sum(n for n, _ in res)
+
+    def native_libs(self):
+        """the third-party engines the reference delegates to, alone, with their own native batching (SURVEY 8d's
+        "fairer second CPU line"): HF tokenizers encode_batch / SentencePiece encode with num_threads on already
+        normalized rows.  -> dict, or why it is not available on this box"""
+        try:
+            sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+            import akshar_oracle as O
+            norm = [O.normalize_text(s) for s in self.lines[:20000]]
+            nb = sum(len(s.encode('utf-8')) for s in norm)
+            if self.workload in ('bpe', 'mixed'):
+                from tokenizers import Tokenizer
+                tk = Tokenizer.from_file(os.path.join(MODELS, 'bpe24k.json'))
+                tk.encode_batch(norm[:1000])
+                t = time.perf_counter()
+                tk.encode_batch(norm)
+                what = 'tokenizers.Tokenizer.encode_batch (Rust, rayon) on normalized rows'
+            elif self.workload == 'unigram':
+                import sentencepiece as spm
+                sp = spm.SentencePieceProcessor()
+                sp.Load(os.path.join(MODELS, 'spm24k.model'))
+                t = time.perf_counter()
+                sp.encode(norm, num_threads=self.cores)
+                what = 'sentencepiece encode(num_threads=%d) on normalized rows' % self.cores
+            else:
+                return None
+            dt = time.perf_counter() - t
+            return {'value': nb / dt / 1e9, 'unit': 'GB/s', 'what': what, 'sample_mb': nb / 1e6}
+        except Exception as e:      # library not on this box
+            return {'unavailable': repr(e)[:120]}
 
     def close(self):
         self.pool.close()
@@ -194,172 +244,199 @@ def peaks():
     return 6650.0, 'fallback'
 
 
-# ------------------------------------------------------------------ main
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=5)
-    ap.add_argument('--warmup', type=int, default=3)
-    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--mb', type=int, default=1024, help='synthetic input per GPU in MiB (1024 = the configuration the metric is quoted on)')
-    ap.add_argument('--workload', default='bpe', choices=['bpe', 'unigram', 'pipeline'])
-    ap.add_argument('--cpu-sample-mb', type=float, default=24.0)
-    a = ap.parse_args()
-    rank = int(os.environ.get('RANK', '0'))
-    world = int(os.environ.get('WORLD_SIZE', '1'))
-    local = int(os.environ.get('LOCAL_RANK', '0'))
-    kind = {'bpe': 'hinglish', 'unigram': 'hindi', 'pipeline': 'social'}[a.workload]
-    cfg = {'workload': {'bpe': 'BPE-24k batch encode (normalize_text -> ids) of %d MiB synthetic Hinglish per GPU' % a.mb,
-                        'unigram': 'Unigram-24k Viterbi encode of %d MiB synthetic Hindi per GPU' % a.mb,
-                        'pipeline': 'normalize + akshar + code-switch on %d MiB synthetic social Hinglish per GPU' % a.mb}[a.workload],
-           'bytes_per_gpu': a.mb << 20, 'model': {'bpe': 'tests/golden/models/bpe24k.json', 'unigram': 'tests/golden/models/spm24k.model',
-                                                  'pipeline': None}[a.workload],
-           'l2': 'inputs larger than L2 (no flush needed)' if a.mb >= 256 else 'input smaller than 2x L2', 'sharding': 'sentences, no collective'}
-    metric = 'utf8_input_GBps_batch_encode' if a.workload != 'pipeline' else 'utf8_input_GBps_normalize_segment'
+def traffic_table():
+    """DRAM bytes per input byte of each hot kernel from the committed `ncu --set full` summary (profiles/r02_traffic.json:
+    (dram__bytes_read.sum + dram__bytes_write.sum) / input bytes at the size stated there)"""
+    p = os.path.join(ROOT, 'profiles', 'r02_traffic.json')
+    if os.path.exists(p):
+        return json.load(open(p))
+    return {}
 
-    if a.impl == 'reference':
-        if rank != 0:
-            return
-        sample = int(a.cpu_sample_mb * (1 << 20))
-        data, off = make_corpus(kind, sample + (1 << 20), 0)
-        arm = CpuArm(a.workload, data, off, sample)
-        for _ in range(a.warmup):
-            arm.step()
-        t = tok = 0.0
-        for _ in range(a.steps):
-            dt, n = arm.step()
-            t += dt
-            tok += n
-        arm.close()
-        v = arm.nbytes * a.steps / t / 1e9
-        print(json.dumps({
-            'impl': 'reference', 'metric': metric, 'value': v, 'unit': 'GB/s', 'tokens_per_s': tok / t, 'n_gpus': a.gpus,
-            'steps': a.steps, 'warmup': a.warmup, 'ms_per_step': t / a.steps * 1e3, 'higher_is_better': True, 'scaling': 'weak',
-            'vs_baseline': None, 'dtype': 'u8', 'data': 'synthetic', 'config': cfg,
-            'cpu_baseline': {'value': v, 'unit': 'GB/s', 'cores': arm.cores, 'kind': 'port',
-                             'sample': '%d rows / %.1f MB of the same synthetic workload per step; oracle/akshar_oracle.py '
-                                       '(pure-Python restatement; the reference itself is Python and cannot travel to this box)'
-                                       % (len(arm.lines), arm.nbytes / 1e6)},
-            'e2e': {'value': v, 'unit': 'GB/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}))
-        return
 
-    # host-side work that forks (corpus generation, the CPU arm's worker pool) happens before CUDA is touched
-    nbytes = a.mb << 20
-    chunks_per_rank = (nbytes + CHUNK - 1) // CHUNK
-    data, off = make_corpus(kind, nbytes, rank * chunks_per_rank, procs=max(1, (os.cpu_count() or 1) // world))
-    n_rows = off.size - 1
-    arm = CpuArm(a.workload, data, off, int(a.cpu_sample_mb * (1 << 20))) if rank == 0 else None
+# ------------------------------------------------------------------ one workload on this rank
+class Rank:
+    def __init__(self):
+        self.rank = int(os.environ.get('RANK', '0'))
+        self.world = int(os.environ.get('WORLD_SIZE', '1'))
+        self.local = int(os.environ.get('LOCAL_RANK', '0'))
+
+
+def describe(workload, mb, world):
+    return {'bpe': 'BPE-24k batch encode (normalize_text -> ids) of %d MiB synthetic Hinglish per GPU' % mb,
+            'unigram': 'Unigram-24k Viterbi encode (normalize_text -> ids) of %d MiB synthetic Hindi per GPU' % mb,
+            'pipeline': 'normalize + akshars + script runs on %d MiB synthetic social Hinglish per GPU' % mb,
+            'mixed': 'sentence-sharded BPE-24k encode of %d MiB per GPU (%d GPUs) of the 2:1:1 Hinglish / Hindi / social mix, '
+                     'in 1 GiB batches' % (mb, world)}[workload]
+
+
+def run_workload(R, workload, mb, steps, warmup, cpu_sample_mb, dist, with_cpu=True):
+    """-> the JSON line (a dict) on rank 0, None elsewhere"""
+    import numpy as np
     import torch
-    import torch.distributed as dist
-    torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
-    import __graft_entry__ as g
-    if rank == 0:
-        g.build()
-    if world > 1:
-        dist.barrier()
+    kind = KIND[workload]
+    nbytes = mb << 20
+    sub = 1 << 30                                   # batches of at most 1 GiB (event positions are 32-bit)
+    chunks_per_rank = (nbytes + CHUNK - 1) // CHUNK
+    # host-side work that forks (corpus generation, the CPU arm's worker pool) comes first
+    data, off = make_corpus(kind, nbytes, R.rank * chunks_per_rank, procs=max(1, (os.cpu_count() or 1) // R.world))
+    n_rows = off.size - 1
+    arm = CpuArm(workload, data, off, int(cpu_sample_mb * (1 << 20))) if (R.rank == 0 and with_cpu) else None
     import akshar_b200 as A
-    from akshar_b200 import _lib as C
+    from akshar_b200 import shard
 
-    h_data = torch.from_numpy(data).pin_memory()
-    h_off = torch.from_numpy(off).pin_memory()
-    if a.workload == 'bpe':
-        tk = A.aksharTokenizer(os.path.join(MODELS, 'bpe24k.json'), 'bpe', device=local)
+    # the rank's shard as batches of <= 1 GiB (row ranges)
+    n_sub = max(1, (int(off[-1]) + sub - 1) // sub)
+    ranges = [r for r in shard.shard_rows(off, n_sub) if r[1] > r[0]]
+    h_batches = []
+    for lo, hi in ranges:
+        d, o = shard.take_shard(data, off, lo, hi)
+        h_batches.append((torch.from_numpy(np.ascontiguousarray(d)).pin_memory(), torch.from_numpy(np.ascontiguousarray(o)).pin_memory()))
+    if workload in ('bpe', 'mixed'):
+        tk = A.aksharTokenizer(os.path.join(MODELS, 'bpe24k.json'), 'bpe', device=R.local)
         eng, mkind = tk._eng, 0
-    elif a.workload == 'unigram':
-        tk = A.aksharTokenizer(os.path.join(MODELS, 'spm24k.model'), 'sentencepiece', device=local)
+    elif workload == 'unigram':
+        tk = A.aksharTokenizer(os.path.join(MODELS, 'spm24k.model'), 'sentencepiece', device=R.local)
         eng, mkind = tk._eng, 1
     else:
-        eng, mkind = A.Engine(local), None
-    dev_batch = eng.put((h_data, h_off))
+        eng, mkind = A.Engine(R.local), None
+    dev_batches = [eng.put(hb) for hb in h_batches]
     torch.cuda.synchronize()
 
-    def device_step():
-        if mkind is not None:
-            return eng.tokenizer_encode_batch(dev_batch, mkind, check=False)
-        norm, r1 = eng.normalize_batch(dev_batch, check=False)
-        # the normalized length stays on the device in the fused entry point; here (two ABI calls) it is read back once
-        total = int(r1[0].item())
-        norm.end = total
-        c, r, r2 = eng.segment_batch(norm, clusters=True, runs=True, check=False)
-        return (c, r), norm, r2
+    def device_step(batches):
+        outs = []
+        for b in batches:
+            if mkind is not None:
+                outs.append(eng.tokenizer_encode_batch(b, mkind, check=False))
+            else:
+                norm, r1 = eng.normalize_batch(b, check=False)
+                # the normalized length stays on the device in the fused entry point; here (two ABI calls) it is read back
+                norm.end = int(r1[0].item())
+                c, r, r2 = eng.segment_batch(norm, clusters=True, runs=True, check=False)
+                outs.append(((c, r), norm, r2))
+        return outs
 
     def barrier():
         torch.cuda.synchronize()
-        if world > 1:
+        if R.world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # correctness of the run that is about to be timed: status bits clear, totals sane
-    out = device_step()
+    # ---- correctness of the run that is about to be timed: status bits clear, and the CPU arm's rows id for id
+    outs = device_step(dev_batches)
     torch.cuda.synchronize()
-    res = out[-1].cpu()
-    assert int(res[2]) == 0, 'status bits %d' % int(res[2])
-    n_tokens = int(res[0]) + (int(res[1]) if mkind is None else 0)
-    n_norm = int(res[1]) if mkind is not None else int(out[1].end)
-    del out
-    sampler = ClockSampler(local) if rank == 0 else None
+    n_tokens = n_norm = n_c = n_r = 0
+    for o in outs:
+        res = o[-1].cpu()
+        assert int(res[2]) == 0, 'status bits %d' % int(res[2])
+        if mkind is not None:
+            n_tokens += int(res[0])
+            n_norm += int(res[1])
+        else:
+            n_c += int(res[0])
+            n_r += int(res[1])
+            n_norm += int(o[1].end)
+    if mkind is None:
+        n_tokens = n_c + n_r
+    parity = None
+    if arm is not None:
+        arm.step()
+        k = len(arm.lines)
+        o = outs[0]
+        if mkind is not None:
+            sp = o[0].splits[:k + 1].cpu().numpy()
+            iv = o[0].values[:int(sp[-1])].cpu().numpy().astype(np.int32)
+            got = [_crc(iv[sp[i]:sp[i + 1]]) for i in range(k)]
+        else:
+            (c, r), norm, _ = o
+            no = norm.offsets[:k + 1].cpu().numpy()
+            nb = norm.data[:int(no[-1])].cpu().numpy()
+            cs = c.splits[:k + 1].cpu().numpy()
+            ce = c.values[:int(cs[-1])].cpu().numpy().astype(np.int32)
+            rs = r.splits[:k + 1].cpu().numpy()
+            re_ = r.values[:int(rs[-1])].cpu().numpy()
+            rt = r.extra[:int(rs[-1])].cpu().numpy()
+            tags = ['devanagari', 'roman', 'digit', 'punct', 'other']
+            got = []
+            for i in range(k):
+                ends = re_[rs[i]:rs[i + 1]].tolist()
+                lens = [e - (ends[j - 1] if j else 0) for j, e in enumerate(ends)]
+                labs = [None if t == 255 else tags[t] for t in rt[rs[i]:rs[i + 1]].tolist()]
+                got.append(zlib.crc32(nb[no[i]:no[i + 1]].tobytes()) ^ _crc(ce[cs[i]:cs[i + 1]]) ^
+                           zlib.crc32(repr(list(zip(lens, labs))).encode()))
+        bad = [i for i in range(k) if got[i] != arm.sums[i]]
+        assert not bad, 'GPU result differs from the CPU reference port on rows %s of the timed batch' % bad[:5]
+        parity = k
+    del outs
+    sampler = ClockSampler(R.local) if R.rank == 0 else None
     if sampler:
         sampler.wait_first()
-    for _ in range(max(0, a.warmup - 1)):
-        device_step()
+    for _ in range(max(0, warmup - 1)):
+        device_step(dev_batches)
     barrier()
     if sampler:
         sampler.mark()          # clocks are sampled every 20 ms from here to the end of the measured phases (timed steps,
-    l0 = eng.launch_count()     # end-to-end steps, per-kernel timing steps): the timed region alone lasts < 100 ms
+    l0 = eng.launch_count()     # end-to-end steps, per-kernel timing steps)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(a.steps):
-        device_step()
+    for _ in range(steps):
+        device_step(dev_batches)
     e1.record()
     barrier()
     launches = eng.launch_count() - l0
-    ms = e0.elapsed_time(e1) / a.steps
+    ms = e0.elapsed_time(e1) / steps
+
     # ---- end to end through the public batch API: pinned host text in, ids (or offsets) on the host out
+    bufs = {}
+
     def e2e_step():
-        if mkind is not None:
-            # the public host -> ids call: H2D of chunk k+1, kernels of chunk k and D2H of chunk k-1 overlap
-            ids, splits = eng.encode_host_pipelined(h_data, h_off, mkind)
-            assert int(splits[-1]) == ids.numel()
-            return ids.numel() * 4 + splits.numel() * 8 + 32
-        b = eng.put((h_data, h_off))
-        norm, r1 = eng.normalize_batch(b, check=False)
-        norm.end = int(r1[0].item())
-        c, r, r2 = eng.segment_batch(norm, clusters=True, runs=True, check=False)
-        rr = r2.cpu()
-        nc, nr = int(rr[0]), int(rr[1])
-        if not hasattr(e2e_step, 'bufs'):
-            e2e_step.bufs = [torch.empty(nc, dtype=torch.int32).pin_memory(), torch.empty(nr, dtype=torch.int32).pin_memory(),
-                             torch.empty(nr, dtype=torch.uint8).pin_memory(), torch.empty(n_rows + 1, dtype=torch.int64).pin_memory(),
-                             torch.empty(n_rows + 1, dtype=torch.int64).pin_memory(), torch.empty(norm.end, dtype=torch.uint8).pin_memory()]
-        hb = e2e_step.bufs
-        hb[0][:nc].copy_(c.values[:nc], non_blocking=True)
-        hb[1][:nr].copy_(r.values[:nr], non_blocking=True)
-        hb[2][:nr].copy_(r.extra[:nr], non_blocking=True)
-        hb[3].copy_(c.splits, non_blocking=True)
-        hb[4].copy_(r.splits, non_blocking=True)
-        hb[5][:norm.end].copy_(norm.data[:norm.end], non_blocking=True)
-        torch.cuda.synchronize()
-        return nc * 4 + nr * 5 + 2 * (n_rows + 1) * 8 + norm.end + 64
+        moved = 0
+        for hb in h_batches:
+            if mkind is not None:
+                # the public host -> ids call: H2D of chunk k+1, kernels of chunk k and D2H of chunk k-2 overlap; the ids
+                # cross the link as uint16, the row splits as int32 (akshar_tokenizer_encode_batch_ex)
+                res = eng.encode_host_pipelined(hb[0], hb[1], mkind, compact=True)
+                moved += res.ids16.numel() * 2 + res.splits32.numel() * 4 + 32 * len(res.chunk_ids)
+                continue
+            b = eng.put(hb)
+            norm, r1 = eng.normalize_batch(b, check=False)
+            norm.end = int(r1[0].item())
+            c, r, r2 = eng.segment_batch(norm, clusters=True, runs=True, check=False)
+            rr = r2.cpu()
+            nc, nr = int(rr[0]), int(rr[1])
+            nrow = c.splits.numel()
+            if not bufs:
+                bufs['v'] = [torch.empty(int(nc * 1.2) + 1024, dtype=torch.int32).pin_memory(), torch.empty(int(nr * 1.2) + 1024, dtype=torch.int32).pin_memory(),
+                             torch.empty(int(nr * 1.2) + 1024, dtype=torch.uint8).pin_memory(), torch.empty(int(nrow * 1.2) + 1024, dtype=torch.int64).pin_memory(),
+                             torch.empty(int(nrow * 1.2) + 1024, dtype=torch.int64).pin_memory(),
+                             torch.empty(int(norm.end * 1.1) + 1024, dtype=torch.uint8).pin_memory()]
+            hbuf = bufs['v']
+            hbuf[0][:nc].copy_(c.values[:nc], non_blocking=True)
+            hbuf[1][:nr].copy_(r.values[:nr], non_blocking=True)
+            hbuf[2][:nr].copy_(r.extra[:nr], non_blocking=True)
+            hbuf[3][:nrow].copy_(c.splits, non_blocking=True)
+            hbuf[4][:nrow].copy_(r.splits, non_blocking=True)
+            hbuf[5][:norm.end].copy_(norm.data[:norm.end], non_blocking=True)
+            torch.cuda.synchronize()
+            moved += nc * 4 + nr * 5 + 2 * nrow * 8 + norm.end + 64
+        return moved
 
     d2h = e2e_step()
     barrier()
     t0 = time.perf_counter()
-    e2e_steps = max(1, min(a.steps, 3))
-    for _ in range(e2e_steps):
+    for _ in range(steps):
         d2h = e2e_step()
     barrier()
-    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    e2e_s = (time.perf_counter() - t0) / steps
 
     # ---- dominant kernel: the library brackets its hot kernels with CUDA events on the launching stream
-    # (akshar_timing_enable); average over a few full steps of the same workload
+    # (akshar_timing_enable); average over a few passes over the first batch
     eng.timing(True)
     names = ['ak_nf3_classify_kernel', 'ak_nf_write_kernel'] + (['ak_words_kernel', 'ak_resolve_kernel<bpe>', 'ak_emit_kernel'] if mkind == 0 else
-                                                                 ['ak_words_kernel', 'ak_resolve_kernel<unigram>', 'ak_emit_kernel'] if mkind == 1 else ['ak_sf3_kernel'])
+                                                                 ['ak_words_kernel', 'ak_resolve_kernel<unigram>', 'ak_emit_kernel'] if mkind == 1 else
+                                                                 ['ak_sf3_kernel'])
     acc = {k: [] for k in names}
     for _ in range(3):
-        device_step()
+        device_step(dev_batches[:1])
         torch.cuda.synchronize()
         for k in names:
             v = eng.kernel_ms(k)
@@ -368,60 +445,152 @@ def main():
     eng.timing(False)
     clocks = sampler.stop() if sampler else None
     kms = {k: sum(v) / len(v) for k, v in acc.items() if v}
-    n_c = int(res[0]) if mkind is None else 0
-    n_r = int(res[1]) if mkind is None else 0
-    # algorithmic bytes per launch: logical input read once + required output written once
+    # algorithmic bytes per launch (what the kernel must read and write once), first batch
+    f = dev_batches[0].n_bytes / max(1, int(off[-1]))
+    b_in, b_norm, rows1, tok1 = dev_batches[0].n_bytes, n_norm * f, dev_batches[0].n_rows, n_tokens * f
+    ev1 = tok1 / 1.25 + rows1                                                   # events: words (1.25 ids each) + row starts
     alg = {
-        'ak_nf3_classify_kernel': nbytes + 4 * (nbytes // 15),                 # text in, one 4-byte emit mask per 16-byte chunk out
-        'ak_nf_write_kernel': nbytes + 4 * (nbytes // 15) + n_norm + 8 * (n_rows + 1),
-        'ak_words_kernel': n_norm + 8 * (n_rows + 1),
-        'ak_resolve_kernel<bpe>': n_norm + 4 * n_tokens + 8 * (n_rows + 1),
-        'ak_resolve_kernel<unigram>': n_norm + 4 * n_tokens + 8 * (n_rows + 1),
-        'ak_emit_kernel': 4 * n_tokens + 8 * (n_rows + 1),
-        'ak_sf3_kernel': n_norm + 4 * n_c + 5 * n_r + 16 * (n_rows + 1),
+        'ak_nf3_classify_kernel': b_in + 4 * (b_in // 16),                      # text in, one emit mask per 16-byte chunk out
+        'ak_nf_write_kernel': b_in + 4 * (b_in // 16) + b_norm + 8 * (rows1 + 1),
+        'ak_words_kernel': b_norm + 8 * ev1,                                    # text in, one 8-byte event per word / row out
+        'ak_resolve_kernel<bpe>': b_norm + 16 * ev1,                            # the words' bytes + events in, resolved records out
+        'ak_resolve_kernel<unigram>': b_norm + 20 * ev1,
+        'ak_emit_kernel': 8 * ev1 + 4 * tok1 + 8 * (rows1 + 1),
+        'ak_sf3_kernel': b_norm + 4 * n_c * f + 5 * n_r * f + 16 * (rows1 + 1),
     }
-    stages = {k: (kms[k], alg[k]) for k in kms}
-    dom = max(stages, key=lambda k: stages[k][0])
+    kern = {k: (kms[k], alg[k]) for k in kms}
+    dom = max(kern, key=lambda k: kern[k][0])
     peak, peak_kind = peaks()
-    ach = stages[dom][1] / (stages[dom][0] * 1e-3) / 1e9
+    ach = kern[dom][1] / (kern[dom][0] * 1e-3) / 1e9
+    # SURVEY 8d's bytes per STAGE over the device time of the whole step: text in + normalized text out + row offsets,
+    # and what the stage after it adds (ids, or cluster / run ends)
+    if mkind is not None:
+        stage_bytes = int(off[-1]) + n_norm + 4 * n_tokens + 2 * 8 * (n_rows + 1)
+    else:
+        stage_bytes = int(off[-1]) + n_norm + 4 * n_c + 5 * n_r + 3 * 8 * (n_rows + 1)
 
     # ---- reduce over ranks
     t = torch.tensor([ms, e2e_s * 1e3], dtype=torch.float64, device='cuda')
-    cnt = torch.tensor([nbytes, n_tokens, launches, d2h], dtype=torch.float64, device='cuda')
-    if world > 1:
+    cnt = torch.tensor([int(off[-1]), n_tokens, launches, d2h, int(off[-1]) + 8 * (n_rows + len(h_batches))], dtype=torch.float64, device='cuda')
+    if R.world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
     ms_max, e2e_ms = float(t[0]), float(t[1])
-    tot_bytes, tot_tokens, tot_launch, tot_d2h = (float(x) for x in cnt)
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
-    arm.step()
-    dt, ctok = arm.step()
-    arm.close()
-    cpu = {'value': arm.nbytes / dt / 1e9, 'unit': 'GB/s', 'cores': arm.cores, 'kind': 'port', 'tokens_per_s': ctok / dt,
-           'sample': '%d rows / %.1f MB of this workload, oracle/akshar_oracle.py on %d processes, %.1f s'
-                     % (len(arm.lines), arm.nbytes / 1e6, arm.cores, dt)}
-    line = {
+    tot_bytes, tot_tokens, tot_launch, tot_d2h, tot_h2d = (float(x) for x in cnt)
+    if R.rank != 0:
+        return None
+    cpu = None
+    if arm is not None:
+        dt, ctok = arm.step()
+        cpu = {'value': arm.nbytes / dt / 1e9, 'unit': 'GB/s', 'cores': arm.cores, 'kind': 'port', 'tokens_per_s': ctok / dt,
+               'sample': '%d rows / %.1f MB of this workload, oracle/akshar_oracle.py on %d processes, %.1f s'
+                         % (len(arm.lines), arm.nbytes / 1e6, arm.cores, dt),
+               'native_libs_alone': arm.native_libs()}
+        arm.close()
+    metric = 'utf8_input_GBps_batch_encode' if workload != 'pipeline' else 'utf8_input_GBps_normalize_segment'
+    tt = traffic_table()
+    return {
         'metric': metric, 'value': tot_bytes / (ms_max * 1e-3) / 1e9, 'unit': 'GB/s', 'tokens_per_s': tot_tokens / (ms_max * 1e-3),
-        'n_gpus': world, 'steps': a.steps, 'warmup': a.warmup, 'ms_per_step': ms_max, 'higher_is_better': True, 'scaling': 'weak',
-        'vs_baseline': None, 'dtype': 'u8', 'data': 'synthetic', 'config': cfg,
+        'n_gpus': R.world, 'steps': steps, 'warmup': warmup, 'ms_per_step': ms_max, 'higher_is_better': True, 'scaling': 'weak',
+        'vs_baseline': None, 'dtype': 'u8', 'data': 'synthetic',
+        'config': {'workload': describe(workload, mb, R.world), 'bytes_per_gpu': int(off[-1]),
+                   'model': {'bpe': 'tests/golden/models/bpe24k.json', 'mixed': 'tests/golden/models/bpe24k.json',
+                             'unigram': 'tests/golden/models/spm24k.model', 'pipeline': None}[workload],
+                   'l2': 'inputs larger than L2 (no flush needed)' if mb >= 256 else 'input smaller than 2x L2',
+                   'sharding': 'sentences, no collective',
+                   'word_cache': 'lives as long as the model (as in HF tokenizers); every step still hashes and looks up every word'},
         'rows_per_gpu': n_rows, 'tokens_per_gpu': n_tokens, 'normalized_bytes_per_gpu': n_norm,
-        'e2e': {'value': tot_bytes / (e2e_ms * 1e-3) / 1e9, 'unit': 'GB/s', 'h2d_bytes_per_step': int(nbytes + 8 * (n_rows + 1)),
-                'd2h_bytes_per_step': int(tot_d2h / world), 'ms_per_step': e2e_ms},
+        'bytes_per_token': int(off[-1]) / max(1, n_tokens) if mkind is not None else None,
+        'parity_in_run': parity is not None, 'rows_compared': parity or 0,
+        'e2e': {'value': tot_bytes / (e2e_ms * 1e-3) / 1e9, 'unit': 'GB/s', 'h2d_bytes_per_step': int(tot_h2d / R.world),
+                'd2h_bytes_per_step': int(tot_d2h / R.world), 'ms_per_step': e2e_ms, 'chunks_redone': getattr(eng, 'redone_chunks', 0),
+                'out': 'uint16 ids + int32 chunk-relative row splits' if mkind is not None else 'int32 ends + uint8 tags + int64 splits + normalized text'},
         'gpu_launches': int(tot_launch),
         'roofline': {'bound': 'hbm', 'kernel': dom, 'achieved': ach, 'peak': peak, 'peak_source': peak_kind, 'unit': 'GB/s',
                      'frac': ach / peak, 'frac_of_nominal_8000': ach / 8000.0,
-                     'traffic': (int(TRAFFIC_PER_INPUT_BYTE[dom] * nbytes) if dom in TRAFFIC_PER_INPUT_BYTE else None),
-                     'traffic_source': 'ncu --set full at 256 MiB, scaled by input bytes (profiles/r01_v3_ncu_full_summary.csv)',
-                     'ms': stages[dom][0], 'algorithmic_bytes': stages[dom][1],
-                     'kernels_ms': {k: v[0] for k, v in stages.items()},
-                     'kernels_frac': {k: v[1] / (v[0] * 1e-3) / 1e9 / peak for k, v in stages.items()}},
+                     'traffic': (int(tt[dom]['dram_bytes_per_input_byte'] * b_in) if dom in tt else None),
+                     'traffic_source': 'profiles/r02_traffic.json (ncu --set full, dram read + write per input byte, scaled)' if dom in tt else None,
+                     'ms': kern[dom][0], 'algorithmic_bytes': kern[dom][1],
+                     'kernels_ms': {k: v[0] for k, v in kern.items()},
+                     'kernels_frac': {k: v[1] / (v[0] * 1e-3) / 1e9 / peak for k, v in kern.items()},
+                     'stage': {'algorithmic_bytes': stage_bytes, 'ms': ms,
+                               'frac': stage_bytes / (ms * 1e-3) / 1e9 / peak,
+                               'what': 'SURVEY 8d bytes of the whole step on this rank (text in, normalized text, ids / ends, row '
+                                       'offsets) over its device time'}},
         'cpu_baseline': cpu, 'clocks': clocks,
     }
-    print(json.dumps(line))
-    if world > 1:
+
+
+# ------------------------------------------------------------------ main
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--mb', type=int, default=None, help='synthetic input per GPU in MiB (default: the configuration the metric is quoted on)')
+    ap.add_argument('--workload', default=None, choices=['bpe', 'unigram', 'pipeline', 'mixed'])
+    ap.add_argument('--cpu-sample-mb', type=float, default=24.0)
+    ap.add_argument('--no-also', action='store_true', help='headline workload only')
+    a = ap.parse_args()
+    R = Rank()
+    workload = a.workload or ('bpe' if R.world == 1 else 'mixed')
+    mb = a.mb or {'bpe': 1024, 'unigram': 1024, 'pipeline': 4096, 'mixed': 4096}[workload]
+
+    if a.impl == 'reference':
+        if R.rank != 0:
+            return
+        sample = int(a.cpu_sample_mb * (1 << 20))
+        data, off = make_corpus(KIND[workload], sample + (1 << 20), 0)
+        arm = CpuArm(workload, data, off, sample)
+        for _ in range(a.warmup):
+            arm.step()
+        t = tok = 0.0
+        for _ in range(a.steps):
+            dt, n = arm.step()
+            t += dt
+            tok += n
+        native = arm.native_libs()
+        arm.close()
+        v = arm.nbytes * a.steps / t / 1e9
+        metric = 'utf8_input_GBps_batch_encode' if workload != 'pipeline' else 'utf8_input_GBps_normalize_segment'
+        print(json.dumps({
+            'impl': 'reference', 'metric': metric, 'value': v, 'unit': 'GB/s', 'tokens_per_s': tok / t, 'n_gpus': a.gpus,
+            'steps': a.steps, 'warmup': a.warmup, 'ms_per_step': t / a.steps * 1e3, 'higher_is_better': True, 'scaling': 'weak',
+            'vs_baseline': None, 'dtype': 'u8', 'data': 'synthetic',
+            'config': {'workload': describe(workload, mb, R.world), 'bytes_per_gpu': mb << 20},
+            'cpu_baseline': {'value': v, 'unit': 'GB/s', 'cores': arm.cores, 'kind': 'port',
+                             'sample': '%d rows / %.1f MB of the same synthetic workload per step; oracle/akshar_oracle.py '
+                                       '(pure-Python restatement; the reference itself is Python and cannot travel to this box)'
+                                       % (len(arm.lines), arm.nbytes / 1e6),
+                             'native_libs_alone': native},
+            'e2e': {'value': v, 'unit': 'GB/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}))
+        return
+
+    import torch
+    dist = None
+    torch.cuda.set_device(R.local)
+    if R.world > 1:
+        import torch.distributed as dist
+        dist.init_process_group('nccl', device_id=torch.device('cuda', R.local))
+    import __graft_entry__ as g
+    if R.rank == 0:
+        g.build()
+    if R.world > 1:
+        dist.barrier()
+    line = run_workload(R, workload, mb, a.steps, a.warmup, a.cpu_sample_mb, dist)
+    if a.workload is None and R.world == 1 and not a.no_also:
+        # BASELINE.json configs[2] and configs[3], measured the same way (fewer steps, smaller CPU samples)
+        import gc
+        also = []
+        for w, wmb in (('unigram', 1024), ('pipeline', 4096)):
+            gc.collect()
+            torch.cuda.empty_cache()
+            also.append(run_workload(R, w, wmb, min(a.steps, 3), 3, min(a.cpu_sample_mb, 8.0), dist))
+        line['also'] = also
+    if R.rank == 0:
+        print(json.dumps(line))
+    if R.world > 1:
         dist.destroy_process_group()
 
 
