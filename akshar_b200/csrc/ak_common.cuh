@@ -181,6 +181,49 @@ __device__ __forceinline__ uint32_t akn3_lane_rows(const int64_t* off, int64_t n
     return rows;
 }
 
+// the same, plus what the event-stream kernels need to number their rows without touching the offsets again: the index of
+// the first row that starts in the lane's 32 bytes and how many rows start there (more than the mask's bits when rows are empty)
+__device__ __forceinline__ uint32_t akn3_lane_rows2(const int64_t* off, int64_t n_rows, int64_t r_w0, int64_t ws, int lane,
+                                                    int64_t& first_row, int& nrows) {
+    uint32_t rows = 0;
+    int64_t first = 0x7FFFFFFFFFFFFFFFll;
+    int cntl = 0;
+    const int64_t lo = ws - 32, hi = ws + AKN3_WARP_BYTES + 32;
+    for (int64_t r = r_w0;; r += 32) {
+        const int64_t mr = r + lane;
+        const int64_t p = mr <= n_rows ? off[mr] : hi;
+        const unsigned m = __ballot_sync(0xFFFFFFFFu, p < hi);
+        const int cnt = __popc(m);
+        for (int j = 0; j < cnt; ++j) {
+            const int rel = (int)(__shfl_sync(0xFFFFFFFFu, p, j) - lo);
+            if ((rel >> 5) == lane) {
+                rows |= 1u << (rel & 31);
+                ++cntl;
+                if (r + j < first) first = r + j;
+            }
+        }
+        if (cnt < 32) break;
+    }
+    for (int64_t r = r_w0 - 1;; r -= 32) {
+        const int64_t mr = r - lane;
+        const int64_t p = mr >= 0 ? off[mr] : lo - 1;
+        const unsigned m = __ballot_sync(0xFFFFFFFFu, p >= lo);
+        const int cnt = __popc(m);
+        for (int j = 0; j < cnt; ++j) {
+            const int rel = (int)(__shfl_sync(0xFFFFFFFFu, p, j) - lo);
+            if ((rel >> 5) == lane) {
+                rows |= 1u << (rel & 31);
+                ++cntl;
+                if (r - j < first) first = r - j;
+            }
+        }
+        if (cnt < 32) break;
+    }
+    first_row = first;
+    nrows = cntl;
+    return rows;
+}
+
 __device__ __noinline__ void akn3_load_edge(const uint8_t* text, int64_t cs, int lo, int hi, uint32_t* x) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) x[i] = 0;

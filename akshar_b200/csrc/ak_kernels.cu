@@ -165,7 +165,7 @@ int akshar_ctx_create(int device, akshar_ctx** out) {
     AK_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_resolve[0], ak_resolve_kernel<0>, AKR_THREADS, 0));
     AK_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_resolve[1], ak_resolve_kernel<1>, AKR_THREADS, 0));
     AK_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_check, ak_unicheck_kernel, AKL_THREADS, 0));
-    AK_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_emit, ak_emit_kernel, AKL_THREADS, 0));
+    AK_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_emit, ak_emit_kernel<int32_t>, AKL_THREADS, 0));
     return AKSHAR_OK;
 }
 
@@ -841,6 +841,10 @@ static int ak_run_tok(akshar_ctx* ctx, AkCall& C, const AkBatch& B, int64_t max_
     const int entries = (int)(n_wt_ub * 2 + 3);
     ak_warp_rows_kernel<<<(entries + 255) / 256, 256, 0, C.stream>>>(B, base0, entries, (int64_t*)(base + W.wrow));
     if ((rc = ak_after_launch(ctx, "tok-warp-rows"))) return rc;
+    if (kind == 1) {
+        ak_long_rows_kernel<<<ctx->sm_count * 4, 256, 0, C.stream>>>(B, AKT_LONG_ROW, A.row_flag, any_flag);
+        if ((rc = ak_after_launch(ctx, "tok-long-rows"))) return rc;
+    }
     {
         AkTimed tm(ctx, AKSHAR_TIMER_WORDS, C.stream);
         const int g = ak_grid(ctx, ctx->occ_words[kind], (int)((n_wt_ub + AKW_THREADS / 32 - 1) / (AKW_THREADS / 32)));
@@ -942,7 +946,8 @@ static int ak_run_tok(akshar_ctx* ctx, AkCall& C, const AkBatch& B, int64_t max_
     E.any_flag = any_flag;
     {
         AkTimed tm(ctx, AKSHAR_TIMER_EMIT, C.stream);
-        ak_emit_kernel<<<ak_grid(ctx, ctx->occ_emit, warp_ctas), AKL_THREADS, 0, C.stream>>>(E);
+        if (O.ids_u16) ak_emit_kernel<uint16_t><<<ak_grid(ctx, ctx->occ_emit, warp_ctas), AKL_THREADS, 0, C.stream>>>(E);
+        else ak_emit_kernel<int32_t><<<ak_grid(ctx, ctx->occ_emit, warp_ctas), AKL_THREADS, 0, C.stream>>>(E);
     }
     return ak_after_launch(ctx, "tok-emit");
 }

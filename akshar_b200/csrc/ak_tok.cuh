@@ -25,7 +25,8 @@
 // event = (pos, meta): pos = byte offset from text_begin, meta = (payload << 3) | kind
 #define AKE_OTHER 0u        // word of pre-tokenizer class "other" ([^\w\s]+)
 #define AKE_WORD 1u         // word of class \w (HF) / a SentencePiece word
-#define AKE_ROW 2u          // payload = index of the first row that starts at pos
+#define AKE_ROW 2u          // payload = index of the (one) row that starts at pos
+#define AKE_ROWS 3u         // several rows start at pos (all but the last are empty): payload = index of the first
 #define AKE_DEAD 4u         // overridden (its row is encoded by the row-fix kernel)
 #define AKE_LEN_MAX 0x1FFFFFFFu
 
@@ -37,21 +38,30 @@ struct AkEvent {
 // rowsm / wstart: the lane's row starts / word starts; cw: class-word mask; bnd + nb1 + nb2: boundary masks of this lane and
 // the next two (a word's end = the next boundary); nr = index of the first row that starts at or after the lane's first
 // byte.  `scan_end(p, from)` is called for the (cold) words with no boundary within what the warp knows.
+// first_row / nrows: index of the first row that starts in the lane and how many do (akn3_lane_rows2): when every row
+// bit stands for one row the rows are numbered from there, the offsets are only read again when rows are empty.
 template <class ScanEnd>
 AK_HD int ake_lane_events(uint32_t rowsm, uint32_t wstart, uint32_t cw, uint32_t bnd, uint32_t nb1, uint32_t nb2, int tail_known,
-                          int64_t cs, int64_t tb, const int64_t* off, int64_t n_rows, int64_t nr, AkEvent* dst, int64_t cap_left,
-                          ScanEnd scan_end) {
+                          int64_t cs, int64_t tb, const int64_t* off, int64_t n_rows, int64_t first_row, int nrows, int64_t at,
+                          uint32_t* row_ev, AkEvent* dst, int64_t cap_left, ScanEnd scan_end) {
     int k = 0;
     uint32_t m = rowsm | wstart;
+    const bool simple = nrows == akb_popc(rowsm);
+    int64_t nr = first_row;
     while (m) {
         const int i = akb_ctz(m);
         m &= m - 1u;
         const int64_t p = cs + i;
         if ((rowsm >> i) & 1u) {
-            while (nr < n_rows && off[nr] < p) ++nr;
-            if (k < cap_left) { dst[k].pos = (uint32_t)(p - tb); dst[k].meta = ((uint32_t)nr << 3) | AKE_ROW; }
+            uint32_t kind = AKE_ROW;
+            if (!simple) {
+                while (nr < n_rows && off[nr] < p) ++nr;
+                if (nr < n_rows && off[nr + 1] == p) kind = AKE_ROWS;
+            }
+            if (k < cap_left) { dst[k].pos = (uint32_t)(p - tb); dst[k].meta = ((uint32_t)nr << 3) | kind; }
+            if (simple) row_ev[nr++] = (uint32_t)(at + k);
+            else while (nr <= n_rows && off[nr] == p) row_ev[nr++] = (uint32_t)(at + k);      // empty rows share the position: one event
             ++k;
-            while (nr <= n_rows && off[nr] == p) ++nr;            // empty rows share the position: one event for all of them
         }
         if ((wstart >> i) & 1u) {
             const uint32_t above = bnd & ~((2u << i) - 1u);
@@ -76,31 +86,6 @@ AK_HD void ake_flag_rows(const int64_t* off, int64_t n_rows, int64_t cs, uint32_
         const int64_t g = ak_row_lower_bound(off, 0, n_rows, cs + i + 1) - 1;
         if (g >= 0) row_flag[g] = 1;
     }
-}
-
-// row bookkeeping of a lane: row_ev[g] = index of the event that starts row g (`at` = index of the lane's first event),
-// rows longer than long_row (> 0) are flagged.  Returns true when a row was flagged.
-AK_HD bool ake_lane_rows(uint32_t rowsm, uint32_t wstart, int64_t cs, const int64_t* off, int64_t n_rows, int64_t nr, int64_t at,
-                         uint32_t* row_ev, int64_t long_row, uint8_t* row_flag) {
-    bool flagged = false;
-    int k = 0;
-    uint32_t m = rowsm | wstart;
-    while (m) {
-        const int i = akb_ctz(m);
-        m &= m - 1u;
-        if ((rowsm >> i) & 1u) {
-            const int64_t p = cs + i;
-            while (nr < n_rows && off[nr] < p) ++nr;
-            while (nr <= n_rows && off[nr] == p) {
-                row_ev[nr] = (uint32_t)(at + k);
-                if (long_row > 0 && nr < n_rows && off[nr + 1] - p > long_row) { row_flag[nr] = 1; flagged = true; }
-                ++nr;
-            }
-            ++k;
-        }
-        if ((wstart >> i) & 1u) ++k;
-    }
-    return flagged;
 }
 
 // ---- SentencePiece front end: words = maximal runs of bytes other than U+0020 -----------------------------------
@@ -467,7 +452,7 @@ AK_HD_NOINLINE int akl_uni_exact(const AkLookupCtx& X, int64_t p, uint32_t len, 
 //   [63:62] 0 inline : [61:60] n (0..2), [59:30] id 1, [29:0] id 0          (an empty slot is all zero: n = 0)
 //           1 cache  : [61:56] n (3..14), [55:0] cache entry
 //           2 pool   : [61:38] n, [37:0] offset of the ids in the pool
-//           3 event  : [61:38] n; a row start: the emit kernel reads the event itself
+//           3 event  : [61:38] n, [37] several rows start here (or the row was fixed), [36:0] index of the (first) row: a row start
 #define AKR_INLINE 0ull
 #define AKR_CACHE 1ull
 #define AKR_POOL 2ull
@@ -477,17 +462,18 @@ AK_HD unsigned long long akr_inline(int n, unsigned long long ids01) {
 }
 AK_HD unsigned long long akr_cache(int n, long long slot) { return (AKR_CACHE << 62) | ((unsigned long long)n << 56) | (unsigned long long)slot; }
 AK_HD unsigned long long akr_pool(int n, unsigned long long at) { return (AKR_POOL << 62) | ((unsigned long long)n << 38) | at; }
-AK_HD unsigned long long akr_event(int n) { return (AKR_EVENT << 62) | ((unsigned long long)n << 38); }
+AK_HD unsigned long long akr_event(int n, int64_t g, bool multi) {
+    return (AKR_EVENT << 62) | ((unsigned long long)n << 38) | (multi ? (1ull << 37) : 0ull) | (unsigned long long)g;
+}
 AK_HD int akr_n(unsigned long long r) {
     const unsigned long long ty = r >> 62;
     return ty == AKR_INLINE ? (int)((r >> 60) & 3ull) : ty == AKR_CACHE ? (int)((r >> 56) & 63ull) : (int)((r >> 38) & 0xFFFFFFull);
 }
 
-// resolve one event.  k0 / k1: the word's first two key words (akc_key01) when it is a cacheable word.
+// resolve one event.  k[0..3]: the word's first four key words (akc_key0123) when it is a cacheable word.
 // aux (Unigram): (ratio bf16 << 16) | wmag bf16 of the word, 0 for anything else.
 template <int KIND>
-AK_HD unsigned long long akl_resolve(const AkLookupCtx& X, AkEvent& ev, unsigned long long k0, unsigned long long k1, uint32_t& aux,
-                                     uint32_t& st) {
+AK_HD unsigned long long akl_resolve(const AkLookupCtx& X, AkEvent& ev, const unsigned long long* k, uint32_t& aux, uint32_t& st) {
     const uint32_t kind = ev.meta & 7u;
     uint32_t len = ev.meta >> 3;
     const int64_t p = X.tb + ev.pos;
@@ -503,7 +489,7 @@ AK_HD unsigned long long akl_resolve(const AkLookupCtx& X, AkEvent& ev, unsigned
         h.slot = -1;
         h.free_slot = -1;
         h.h = h.want = h.tag = h.ids01 = 0ull;
-        if (cacheable) akc_lookup(X.M.cache, X.text, p, len, k0, k1, h);
+        if (cacheable) akc_lookup4(X.M.cache, X.text, p, len, k, h);
         if (h.slot >= 0) {
             const int n = AKC_NTOK(h.tag);
             if (KIND == 1) aux = (uint32_t)(h.tag >> 32);
@@ -516,7 +502,14 @@ AK_HD unsigned long long akl_resolve(const AkLookupCtx& X, AkEvent& ev, unsigned
         if (o.slot == -1) return akr_inline(o.n, o.ids01);
         return akr_pool(o.n, (unsigned long long)(-3 - o.slot));
     }
-    if (kind == AKE_ROW) return akr_event(akl_row_event(X, p, (int64_t)(ev.meta >> 3), false, 0));
+    if (kind == AKE_ROW) {
+        // one row starts here: </s> of the previous row, <s> of this one (no look at the offsets)
+        const int64_t g = (int64_t)(ev.meta >> 3);
+        if (X.any_fix && g < X.n_rows && X.row_flag[g]) return akr_event(akl_row_event(X, p, g, false, 0), g, true);
+        const int32_t bos = X.M.kind == 0 ? X.M.bpe.bos : -1, eos = X.M.kind == 0 ? X.M.bpe.eos : -1;
+        return akr_event((g > 0 && eos >= 0 ? 1 : 0) + (g < X.n_rows && bos >= 0 ? 1 : 0), g, false);
+    }
+    if (kind == AKE_ROWS) return akr_event(akl_row_event(X, p, (int64_t)(ev.meta >> 3), false, 0), (int64_t)(ev.meta >> 3), true);
     return 0ull;
 }
 
@@ -540,7 +533,7 @@ AK_HD_NOINLINE void akl_emit(const AkLookupCtx& X, unsigned long long r, const A
     // a record that points outside its table would be a bug of the resolve pass: say so instead of reading there
     if ((ty == AKR_CACHE && (r & 0xFFFFFFFFFFFFFFull) >= (1ull << X.M.cache.bits)) ||
         (ty == AKR_POOL && (r & 0x3FFFFFFFFFull) + ((r >> 38) & 0xFFFFFFull) > X.pool_cap) ||
-        (ty == AKR_EVENT && ((ev_slot->meta & 7u) != AKE_ROW || (int64_t)(ev_slot->meta >> 3) > X.n_rows))) {
+        (ty == AKR_EVENT && (((ev_slot->meta & 7u) != AKE_ROW && (ev_slot->meta & 7u) != AKE_ROWS) || (int64_t)(ev_slot->meta >> 3) > X.n_rows))) {
         ak_status_or(X.result, AK_ST_INTERNAL | ((uint32_t)(ty + 1) << 8));
         return;
     }
@@ -562,7 +555,7 @@ AK_HD_NOINLINE void akl_emit(const AkLookupCtx& X, unsigned long long r, const A
     } else {
         const AkEvent ev = *ev_slot;
         const uint32_t kind = ev.meta & 7u;
-        if (kind == AKE_ROW) akl_row_event(X, X.tb + ev.pos, (int64_t)(ev.meta >> 3), true, at);
+        if (kind == AKE_ROW || kind == AKE_ROWS) akl_row_event(X, X.tb + ev.pos, (int64_t)(ev.meta >> 3), true, at);
     }
 }
 
@@ -591,7 +584,7 @@ AK_HD_NOINLINE void akr_fix_row(const AkRowFixCtx& X, int64_t g) {
         unsigned long long e0 = X.row_ev[g], e1 = X.row_ev[g + 1];
         if (e1 > X.n_events) e1 = X.n_events;
         for (unsigned long long e = e0 + 1; e < e1; ++e)
-            if ((X.ev[e].meta & 7u) != AKE_ROW) X.ev[e].meta = AKE_DEAD;
+            if ((X.ev[e].meta & 7u) != AKE_ROW && (X.ev[e].meta & 7u) != AKE_ROWS) X.ev[e].meta = AKE_DEAD;
     }
     X.row_fix[g] = 0ull;
     if (X.M.kind == 1) {

@@ -39,10 +39,10 @@ inline AkUniDev ak_uni_host_view(const AkUniHost& h) {
 }
 
 inline void ak_image_put(AkWordCache& hc, const uint8_t* tb, uint32_t n, const int32_t* ids, int cnt, unsigned long long aux) {
-    unsigned long long k0, k1;
-    akc_key01(tb, 0, n, (int64_t)n, k0, k1);
+    unsigned long long k[4];
+    akc_key0123(tb, 0, n, (int64_t)n, k);
     AkcHit h;
-    akc_lookup(hc, tb, 0, n, k0, k1, h);
+    akc_lookup4(hc, tb, 0, n, k, h);
     if (h.slot < 0 && h.free_slot >= 0) akc_insert(hc, h.free_slot, h.want, tb, 0, n, ids, cnt, aux);
 }
 

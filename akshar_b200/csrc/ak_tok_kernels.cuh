@@ -110,24 +110,13 @@ __global__ void __launch_bounds__(AKW_THREADS, AKW_MINB) ak_words_kernel(const A
                 own = hi > lo ? ((hi == 32 ? 0xFFFFFFFFu : ((1u << hi) - 1u)) & ~((1u << lo) - 1u)) : 0u;
             }
         }
-        const uint32_t rows = akn3_lane_rows(B.off, B.n_rows, r_w0, ws0, lane);
+        int64_t first_row;
+        int nrows;
+        const uint32_t rows = akn3_lane_rows2(B.off, B.n_rows, r_w0, ws0, lane, first_row, nrows);
         const bool real = lane >= 1 && lane <= 30;
         const int64_t ss = cs < tb ? tb : cs;
         const int64_t se = cs + 32 > te + 1 ? te + 1 : cs + 32;
         const bool active = real && ss < se;
-        // index of the first row that starts at or after this lane's first position
-        int64_t nr;
-        {
-            const int mine = real ? __popc(rows) : 0;
-            int inc = mine;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const int y = __shfl_up_sync(0xFFFFFFFFu, inc, d);
-                if (lane >= d) inc += y;
-            }
-            nr = r_w0 + (inc - mine);
-            if (active) while (nr <= B.n_rows && B.off[nr] < ss) ++nr;
-        }
         uint32_t rowsm, wstart, cw, bnd, nb1, nb2;
         if (KIND == 0) {
             AkB3Lane L;
@@ -203,15 +192,23 @@ __global__ void __launch_bounds__(AKW_THREADS, AKW_MINB) ak_words_kernel(const A
         if (n_ev) {
             const int64_t at = (wt << A.S.shift) + pre;
             const int lane_tail = lane >= 30 ? 62 : lane == 29 ? 94 : 96;       // bytes from cs on whose boundaries the warp knows
-            if (rowsm && ake_lane_rows(rowsm, wstart, cs, B.off, B.n_rows, nr, at, A.row_ev, KIND == 1 ? AKT_LONG_ROW : 0, A.row_flag))
-                atomicOr(A.any_flag, 1u);
             AkScanEnd<KIND> se;
             se.T = &A.T; se.text = B.text; se.off = B.off; se.n_rows = B.n_rows; se.cs = cs; se.cw = cw;
-            ake_lane_events(rowsm, wstart, cw, bnd, nb1, nb2, lane_tail, cs, tb, B.off, B.n_rows, nr, A.S.ev + at,
-                            (int64_t)A.S.cap - pre, se);
+            ake_lane_events(rowsm, wstart, cw, bnd, nb1, nb2, lane_tail, cs, tb, B.off, B.n_rows, first_row, nrows, at, A.row_ev,
+                            A.S.ev + at, (int64_t)A.S.cap - pre, se);
         }
     }
     ak_raise(B.result, st);
+}
+
+// Unigram: rows longer than AKT_LONG_ROW go to the exact row encoder (the word-wise path would send most of their words to
+// the exact Viterbi anyway: the accumulated score grows with the row)
+__global__ void ak_long_rows_kernel(AkBatch B, int64_t limit, uint8_t* row_flag, unsigned int* any_flag) {
+    if (!ak_batch_begin(B)) return;
+    bool any = false;
+    for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < B.n_rows; g += (int64_t)gridDim.x * blockDim.x)
+        if (B.off[g + 1] - B.off[g] > limit) { row_flag[g] = 1; any = true; }
+    if (any) atomicOr(any_flag, 1u);
 }
 
 // =================================================================================================================
@@ -295,9 +292,9 @@ __global__ void __launch_bounds__(AKR_THREADS, KIND == 0 ? AKR_MINB0 : AKR_MINB1
                 const long long s = s_wt + i;
                 AkEvent ev = A.S.ev[s];
                 const uint32_t kind = ev.meta & 7u, len = ev.meta >> 3;
-                unsigned long long k0 = 0ull, k1 = 0ull;
-                if (kind <= AKE_WORD && len <= AKC_MAXLEN) akc_key01(X.text, X.tb + ev.pos, len, X.te, k0, k1);
-                r = akl_resolve<KIND>(X, ev, k0, k1, aux, st);
+                unsigned long long k[4] = {0ull, 0ull, 0ull, 0ull};
+                if (kind <= AKE_WORD && len <= AKC_MAXLEN) akc_key0123(X.text, X.tb + ev.pos, len, X.te, k);
+                r = akl_resolve<KIND>(X, ev, k, aux, st);
                 A.resolved[s] = r;
                 if (KIND == 1) A.aux[s] = aux;
             }
@@ -405,6 +402,7 @@ struct AkEmitArgs {
     const unsigned int* any_flag;
 };
 
+template <class IdT>
 __global__ void __launch_bounds__(AKL_THREADS, 4) ak_emit_kernel(const AkEmitArgs A) {
     AkBatch B = A.B;
     if (!ak_batch_begin(B)) return;
@@ -416,6 +414,10 @@ __global__ void __launch_bounds__(AKL_THREADS, 4) ak_emit_kernel(const AkEmitArg
     X.te = B.text_end;
     X.result = B.result;
     X.any_fix = *A.any_flag != 0u ? 1 : 0;
+    IdT* const ids = (IdT*)A.X.ids;
+    const int64_t id_cap = A.X.id_cap;
+    const int32_t bos = A.X.M.kind == 0 ? A.X.M.bpe.bos : -1, eos = A.X.M.kind == 0 ? A.X.M.bpe.eos : -1;
+    const int splits_i32 = A.X.splits_i32;
     const int lane = threadIdx.x & 31;
     const long long n_wt = akt_n_wt(B, A.base0);
     const long long warp0 = ((long long)blockIdx.x * AKL_THREADS + threadIdx.x) >> 5, n_warps = ((long long)gridDim.x * AKL_THREADS) >> 5;
@@ -427,7 +429,8 @@ __global__ void __launch_bounds__(AKL_THREADS, 4) ak_emit_kernel(const AkEmitArg
         for (int o = 0; o < cnt; o += 32) {
             const int i = o + lane;
             const unsigned long long r = i < cnt ? A.resolved[s_wt + i] : 0ull;
-            const int n = akr_n(r);
+            const unsigned long long ty = r >> 62;
+            const int n = ty == AKR_INLINE ? (int)((r >> 60) & 3ull) : akr_n(r);
             int inc = n;
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) {
@@ -435,8 +438,28 @@ __global__ void __launch_bounds__(AKL_THREADS, 4) ak_emit_kernel(const AkEmitArg
                 if (lane >= d) inc += y;
             }
             const int64_t at = at0 + (inc - n);
-            if (r) {
-                if (at + n > X.id_cap) st |= AK_ST_OVERFLOW;
+            if (ty == AKR_INLINE) {
+                // the common case: one or two ids held in the record itself
+                if (n > 0) {
+                    if (at + n > id_cap) st |= AK_ST_OVERFLOW;
+                    else {
+                        ids[at] = (IdT)(r & 0x3FFFFFFFull);
+                        if (n > 1) ids[at + 1] = (IdT)((r >> 30) & 0x3FFFFFFFull);
+                    }
+                }
+            } else if (ty == AKR_EVENT && !(r & (1ull << 37))) {
+                // one (unfixed) row starts here: </s> of the previous row, the split, <s>
+                const int64_t g = (int64_t)(r & ((1ull << 37) - 1ull));
+                int64_t k2 = at;
+                if (at + n > id_cap) st |= AK_ST_OVERFLOW;
+                else {
+                    if (g > 0 && eos >= 0) ids[k2++] = (IdT)eos;
+                    if (splits_i32) ((int32_t*)A.X.splits)[g] = (int32_t)k2;
+                    else ((int64_t*)A.X.splits)[g] = k2;
+                    if (g < B.n_rows && bos >= 0) ids[k2] = (IdT)bos;
+                }
+            } else {
+                if (at + n > id_cap) st |= AK_ST_OVERFLOW;
                 akl_emit(X, r, A.S.ev + s_wt + i, at);
             }
             at0 += __shfl_sync(0xFFFFFFFFu, inc, 31);

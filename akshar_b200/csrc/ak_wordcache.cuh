@@ -81,32 +81,37 @@ AK_HD unsigned long long akc_key_word(const uint8_t* t, int64_t s, uint32_t len,
     return v;
 }
 
-// the first two key words without a branch: five aligned 32-bit loads (clamped to the last word of the text, whose
-// bytes are masked off anyway) and four funnel shifts
-AK_HD void akc_key01(const uint8_t* t, int64_t s, uint32_t len, int64_t te, unsigned long long& k0, unsigned long long& k1) {
+// the first four key words (32 bytes) without a branch: nine aligned 32-bit loads (clamped to the last word of the text,
+// whose bytes are masked off anyway), eight funnel shifts, byte masks from the length
+AK_HD void akc_key0123(const uint8_t* t, int64_t s, uint32_t len, int64_t te, unsigned long long* k) {
 #ifdef __CUDA_ARCH__
     const uintptr_t a = (uintptr_t)(t + s);
     const uint32_t* w = (const uint32_t*)(a & ~(uintptr_t)3);
     const uint32_t* last = (const uint32_t*)(((uintptr_t)(t + te) - 1u) & ~(uintptr_t)3);
     const uint32_t sh = (uint32_t)(a & 3u) * 8u;
-    const uint32_t w0 = __ldg(w);
-    const uint32_t w1 = __ldg(w + 1 <= last ? w + 1 : last);
-    const uint32_t w2 = __ldg(w + 2 <= last ? w + 2 : last);
-    const uint32_t w3 = __ldg(w + 3 <= last ? w + 3 : last);
-    const uint32_t w4 = __ldg(w + 4 <= last ? w + 4 : last);
-    const uint32_t f0 = __funnelshift_r(w0, w1, sh), f1 = __funnelshift_r(w1, w2, sh);
-    const uint32_t f2 = __funnelshift_r(w2, w3, sh), f3 = __funnelshift_r(w3, w4, sh);
-    k0 = ((unsigned long long)f1 << 32) | f0;
-    k1 = ((unsigned long long)f3 << 32) | f2;
-    const unsigned long long m0 = len >= 8u ? ~0ull : ((1ull << (8u * len)) - 1ull);
-    const unsigned long long m1 = len >= 16u ? ~0ull : (len > 8u ? ((1ull << (8u * (len - 8u))) - 1ull) : 0ull);
-    k0 &= m0;
-    k1 &= m1;
+    uint32_t x[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) x[i] = __ldg(w + i <= last ? w + i : last);
+    uint32_t f[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        f[i] = __funnelshift_r(x[i], x[i + 1], sh);
+        const int rb = (int)len - 4 * i;                            // bytes of the word in this 32-bit piece
+        f[i] = rb >= 4 ? f[i] : rb <= 0 ? 0u : (f[i] & ((1u << (8 * rb)) - 1u));
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) k[j] = ((unsigned long long)f[2 * j + 1] << 32) | f[2 * j];
 #else
     (void)te;
-    k0 = akc_key_word(t, s, len, 0);
-    k1 = len > 8u ? akc_key_word(t, s, len, 1) : 0ull;
+    for (uint32_t j = 0; j < 4; ++j) k[j] = len > 8u * j ? akc_key_word(t, s, len, j) : 0ull;
 #endif
+}
+// (host image builder)
+AK_HD void akc_key01(const uint8_t* t, int64_t s, uint32_t len, int64_t te, unsigned long long& k0, unsigned long long& k1) {
+    unsigned long long k[4];
+    akc_key0123(t, s, len, te, k);
+    k0 = k[0];
+    k1 = k[1];
 }
 
 AK_HD unsigned long long akc_mix(unsigned long long h, unsigned long long k) {
@@ -149,16 +154,17 @@ struct AkcHit {
     unsigned long long tag, ids01;  // on a hit: the tag (id count) and the first two ids
 };
 
-// hash + probe; len <= AKC_MAXLEN.  k0 / k1 = the first two key words (akc_key01).
-AK_HD void akc_lookup(const AkWordCache& C, const uint8_t* t, int64_t s, uint32_t len, unsigned long long k0, unsigned long long k1,
-                      AkcHit& r) {
+// hash + probe; len <= AKC_MAXLEN.  k[0..3] = the first four key words (akc_key0123).
+AK_HD void akc_lookup4(const AkWordCache& C, const uint8_t* t, int64_t s, uint32_t len, const unsigned long long* k, AkcHit& r) {
     const uint32_t nw = (len + 7u) >> 3;
     unsigned long long h = 0x9E3779B97F4A7C15ull + len;
-    h = akc_mix(h, k0);
-    if (nw > 1u) {
-        h = akc_mix(h, k1);
+    h = akc_mix(h, k[0]);
+    if (nw > 1u) h = akc_mix(h, k[1]);
+    if (nw > 2u) h = akc_mix(h, k[2]);
+    if (nw > 3u) h = akc_mix(h, k[3]);
+    if (nw > 4u) {
 #pragma unroll 1
-        for (uint32_t j = 2; j < nw; ++j) h = akc_mix(h, akc_key_word(t, s, len, j));
+        for (uint32_t j = 4; j < nw; ++j) h = akc_mix(h, akc_key_word(t, s, len, j));
     }
     h = akc_fin(h);
     const unsigned long long want = akc_want(h, len);
@@ -185,11 +191,23 @@ AK_HD void akc_lookup(const AkWordCache& C, const uint8_t* t, int64_t s, uint32_
         if (tag == 0ull) { r.free_slot = (long long)slot; return; }
         // the two loads are independent requests: (k1 ^ AKC_K1_SALT) is stored last but the tag, behind a fence, so a
         // second half that is older than the first one never matches (an all-zero half cannot: the salt is not UTF-8)
-        if ((tag & AKC_MATCH_MASK) != want || e0 != k0 || e1 != (k1 ^ AKC_K1_SALT)) continue;
+        if ((tag & AKC_MATCH_MASK) != want || e0 != k[0] || e1 != (k[1] ^ AKC_K1_SALT)) continue;
         bool same = true;
+        if (nw > 2u) {
+            // key bytes 16..31: half of the entry's second sector
+#ifdef __CUDA_ARCH__
+            ulonglong2 c;
+            asm volatile("ld.global.ca.v2.u64 {%0, %1}, [%2];" : "=l"(c.x), "=l"(c.y) : "l"(e + 4) : "memory");
+            same = c.x == k[2] && (nw <= 3u || c.y == k[3]);
+#else
+            same = e[4] == k[2] && (nw <= 3u || e[5] == k[3]);
+#endif
+            if (same && nw > 4u) {
 #pragma unroll 1
-        for (uint32_t j = 2; j < nw; ++j)
-            if (akc_ld(e + 2 + j) != akc_key_word(t, s, len, j)) { same = false; break; }
+                for (uint32_t j = 4; j < nw; ++j)
+                    if (akc_ld(e + 2 + j) != akc_key_word(t, s, len, j)) { same = false; break; }
+            }
+        }
         if (same) {
             r.slot = (long long)slot;
             r.tag = tag;
@@ -197,6 +215,11 @@ AK_HD void akc_lookup(const AkWordCache& C, const uint8_t* t, int64_t s, uint32_
             return;
         }
     }
+}
+AK_HD void akc_lookup(const AkWordCache& C, const uint8_t* t, int64_t s, uint32_t len, unsigned long long k0, unsigned long long k1,
+                      AkcHit& r) {
+    unsigned long long k[4] = {k0, k1, len > 16u ? akc_key_word(t, s, len, 2) : 0ull, len > 24u ? akc_key_word(t, s, len, 3) : 0ull};
+    akc_lookup4(C, t, s, len, k, r);
 }
 
 // id i (>= 2) of entry e

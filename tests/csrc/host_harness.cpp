@@ -438,11 +438,14 @@ int64_t hh_tok(int kind, const uint8_t* text, const int64_t* off, int64_t n_rows
                 nb1 = lu[(size_t)l + 1].bnd;
                 nb2 = l + 2 < NL ? lu[(size_t)l + 2].bnd : 0u;
             }
-            const int64_t nr = ak_row_lower_bound(off, 0, n_rows, ss);
+            // what akn3_lane_rows2 hands the lane: the first row that starts in its 32 bytes and how many do
+            const int64_t first_row = ak_row_lower_bound(off, 0, n_rows, cs);
+            int nrows = 0;
+            for (int64_t g = first_row; g <= n_rows && off[g] < cs + 32; ++g) ++nrows;
             const int tail = l >= real ? 62 : l == real - 1 ? 94 : 96;
             const int64_t at = wt * cap + pre;
-            ake_lane_rows(rowsm, wstart, cs, off, n_rows, nr, at, row_ev.data(), kind == 1 ? 8192 : 0, row_flag.data());
-            pre += ake_lane_events(rowsm, wstart, cw, bnd, nb1, nb2, tail, cs, tb, off, n_rows, nr, slots.data() + at, (int64_t)cap - pre,
+            pre += ake_lane_events(rowsm, wstart, cw, bnd, nb1, nb2, tail, cs, tb, off, n_rows, first_row, nrows, at, row_ev.data(),
+                                   slots.data() + at, (int64_t)cap - pre,
                                    [&](int64_t p, int64_t from) -> int64_t {
                                        if (kind == 0) return akb3_scan_end(T, text, p, from, (cw >> (int)(p - cs)) & 1u, off, n_rows, 0, n_rows);
                                        const int64_t er = ak_row_lower_bound(off, 0, n_rows, p + 1);
@@ -457,6 +460,9 @@ int64_t hh_tok(int kind, const uint8_t* text, const int64_t* off, int64_t n_rows
         if (pre > need) need = pre;
         n_events += pre;
     }
+    if (kind == 1)
+        for (int64_t g = 0; g < n_rows; ++g)
+            if (off[g + 1] - off[g] > 8192) row_flag[(size_t)g] = 1;       // ak_long_rows_kernel
     stats[0] = n_events;
     stats[4] = need;
     if (st & AK_ST_OVERFLOW) { *status = st; stats[1] = stats[2] = stats[3] = 0; return 0; }
@@ -502,10 +508,10 @@ int64_t hh_tok(int kind, const uint8_t* text, const int64_t* off, int64_t n_rows
             const size_t s = (size_t)wt * cap + o;
             AkEvent& ev = slots[s];
             const uint32_t k = ev.meta & 7u, len = ev.meta >> 3;
-            unsigned long long k0 = 0, k1 = 0;
-            if (k <= AKE_WORD && len <= AKC_MAXLEN) akc_key01(text, tb + ev.pos, len, te, k0, k1);
+            unsigned long long kw[4] = {0, 0, 0, 0};
+            if (k <= AKE_WORD && len <= AKC_MAXLEN) akc_key0123(text, tb + ev.pos, len, te, kw);
             const unsigned long long before = long_used + pool_used;
-            resolved[s] = kind == 0 ? akl_resolve<0>(X, ev, k0, k1, aux[s], st) : akl_resolve<1>(X, ev, k0, k1, aux[s], st);
+            resolved[s] = kind == 0 ? akl_resolve<0>(X, ev, kw, aux[s], st) : akl_resolve<1>(X, ev, kw, aux[s], st);
             if (k <= AKE_WORD && (resolved[s] >> 62) != AKR_CACHE && long_used + pool_used != before) ++n_miss;
         }
     // check (Unigram)
