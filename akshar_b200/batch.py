@@ -241,6 +241,38 @@ class Engine:
             return (co, ro) if check else (co, ro, result)
         raise BatchStatusError(bits, 'segment_batch (retries exhausted)')
 
+    # ------------------------------------------------------------------ word tokenizers
+    def word_tokenize_batch(self, batch, rule=C.WORDS_HINDI, row_flags=False, capacity=None):
+        """the word loop of word_tokenize_hindi / word_tokenize_sanskrit (reference segment.py:270-297) over text that is
+        already normalized, or `str.split()` (rule WORDS_SPLIT, segment.py:391-393).
+        -> (begin, end, splits[, flags]): int32 byte offsets of every token relative to its row start, int64 row splits,
+        and with row_flags=True one byte per row: 1 = the row holds a code point of U+0900-097F"""
+        b = self.put(batch)
+        cap = capacity if capacity is not None else (b.n_bytes >> 2) + b.n_rows + 1024
+        ws = self._workspace(b.n_bytes, b.n_rows)
+        dev = self.device
+        for _ in range(self.MAX_TRIES):
+            wb = torch.empty(max(cap, 1), dtype=torch.int32, device=dev)
+            we = torch.empty(max(cap, 1), dtype=torch.int32, device=dev)
+            sp = torch.empty(b.n_rows + 1, dtype=torch.int64, device=dev)
+            fl = torch.empty(max(b.n_rows, 1), dtype=torch.uint8, device=dev) if row_flags else None
+            result = torch.empty(4, dtype=torch.int64, device=dev)
+            rc = self.lib.akshar_word_tokenize_batch(self._h, b.data.data_ptr(), b.offsets.data_ptr(), b.n_rows, b.begin, b.end,
+                                                     rule, wb.data_ptr(), we.data_ptr(), cap, sp.data_ptr(),
+                                                     fl.data_ptr() if row_flags else None, result.data_ptr(), ws.data_ptr(),
+                                                     ws.numel(), self._stream())
+            if rc != 0:
+                self._err(rc, 'akshar_word_tokenize_batch')
+            total, _, bits = self._finish(result, 'word_tokenize', True)
+            if bits & C.ST_OVERFLOW:
+                cap = total
+                continue
+            if bits:
+                raise BatchStatusError(bits, 'word_tokenize_batch')
+            out = (wb[:total], we[:total], sp)
+            return out + (fl[:b.n_rows],) if row_flags else out
+        raise BatchStatusError(bits, 'word_tokenize_batch (retries exhausted)')
+
     # ------------------------------------------------------------------ K1b
     def signature_batch(self, batch):
         """roman_phonetic_signature over a batch of words, one per row (reference normalize.py:59-89) -> TextBatch"""

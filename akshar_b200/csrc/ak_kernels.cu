@@ -33,6 +33,7 @@
 #include "ak_seg_kernels.cuh"
 #include "ak_sub_kernels.cuh"
 #include "ak_tok_kernels.cuh"
+#include "ak_wtok_kernels.cuh"
 
 // ================================================================================================
 // host side: context, model upload, C ABI
@@ -583,6 +584,54 @@ int akshar_segment_batch(akshar_ctx* ctx, const uint8_t* d_text, const int64_t* 
     }
     ak_segment_kernel<<<ak_grid(ctx, ctx->occ_seg, A.B.n_tiles), AK_BLOCK, 0, C.stream>>>(A);
     return ak_after_launch(ctx, "segment");
+}
+
+int akshar_word_tokenize_batch(akshar_ctx* ctx, const uint8_t* d_text, const int64_t* d_row_offsets, int64_t n_rows,
+                               int64_t text_begin, int64_t text_end, int rule, int32_t* d_word_begin, int32_t* d_word_end,
+                               int64_t word_capacity, int64_t* d_word_splits, uint8_t* d_row_flags, int64_t* d_result,
+                               void* d_workspace, size_t workspace_bytes, void* stream) {
+    AkDeviceGuard device_guard(ctx ? ctx->device : 0);
+    AkCall C;
+    int rc = ak_begin(ctx, d_text, d_row_offsets, n_rows, text_begin, text_end, AKSHAR_MODE_TILES, 0, d_result, d_workspace,
+                      workspace_bytes, stream, C);
+    if (rc) return rc;
+    if ((rule != AKSHAR_WORDS_HINDI && rule != AKSHAR_WORDS_SPLIT) || !d_word_splits || word_capacity < 0 ||
+        ((!d_word_begin || !d_word_end) && word_capacity > 0)) {
+        ctx->err = "bad argument";
+        return AKSHAR_E_ARG;
+    }
+    if (n_rows == 0) return ak_empty_rows(ctx, d_word_splits, nullptr, C.stream);
+    if (d_row_flags) AK_CUDA(ctx, cudaMemsetAsync(d_row_flags, 0, (size_t)n_rows, C.stream));
+    AkWtArgs A;
+    A.B = C.B;
+    A.base0 = text_begin - (int64_t)(((uintptr_t)d_text + (uintptr_t)text_begin) & 15u);
+    const int64_t n_wt = (text_end - A.base0 + AKT_WARP_BYTES) / AKT_WARP_BYTES;
+    char* wp = C.ws + C.L.scratch;
+    int64_t* wrow = (int64_t*)wp;       wp += ak_align(((size_t)n_wt * 2 + 3) * 8);
+    A.count = (int32_t*)wp;             wp += ak_align((size_t)n_wt * 4);
+    int64_t* wt_base = (int64_t*)wp;
+    A.wrow = wrow;
+    A.base = wt_base;
+    A.mode = rule == AKSHAR_WORDS_HINDI ? AKW_MODE_HINDI : AKW_MODE_SPLIT;
+    A.begin = d_word_begin;
+    A.end = d_word_end;
+    A.cap = word_capacity;
+    A.splits = d_word_splits;
+    A.row_flags = d_row_flags;
+    const int entries = (int)(n_wt * 2 + 3);
+    ak_warp_rows_kernel<<<(entries + 255) / 256, 256, 0, C.stream>>>(C.B, A.base0, entries, wrow);
+    if ((rc = ak_after_launch(ctx, "words-warp-rows"))) return rc;
+    const int grid = ak_grid(ctx, 8, (int)((n_wt + AKWT_THREADS / 32 - 1) / (AKWT_THREADS / 32)));
+    ak_wtok_kernel<false><<<grid, AKWT_THREADS, 0, C.stream>>>(A);
+    if ((rc = ak_after_launch(ctx, "words-count"))) return rc;
+    ak_scan_counts_kernel<<<ak_grid(ctx, 4, (int)(n_wt / AKS_TILE + 1)), AKS_THREADS, 0, C.stream>>>(
+        A.count, (long long)n_wt, nullptr, 1, wt_base, d_result, (int*)C.ws + 5, C.B.state0, (unsigned int*)&d_result[2]);
+    if ((rc = ak_after_launch(ctx, "words-scan"))) return rc;
+    {
+        AkTimed tm(ctx, AKSHAR_TIMER_WORDTOK, C.stream);
+        ak_wtok_kernel<true><<<grid, AKWT_THREADS, 0, C.stream>>>(A);
+    }
+    return ak_after_launch(ctx, "words-emit");
 }
 
 int akshar_signature_batch(akshar_ctx* ctx, const uint8_t* d_text, const int64_t* d_row_offsets, int64_t n_rows,

@@ -2,6 +2,7 @@
 CUDA grapheme-cluster / script-run kernel.  Same names, arguments, return types and label strings."""
 import numpy as np
 
+from . import _lib as C
 from .batch import engine
 
 MATRA_RANGES = [          # reference segment.py:20-24
@@ -99,7 +100,69 @@ def analyze_text_composition_batch(texts, device=0):
     return out
 
 
+def _word_slices(tb, begin, end, splits, rows=None):
+    """cut the rows of the device TextBatch `tb` at the token offsets -> list[list[str]] (all rows, or just `rows`)"""
+    n = tb.n_rows
+    data = tb.data[:max(tb.end, 0)].cpu().numpy().tobytes() if tb.end > 0 else b''
+    off = tb.offsets.cpu().numpy()
+    wb, we, sp = begin.cpu().numpy(), end.cpu().numpy(), splits.cpu().numpy()
+    out = []
+    for i in (range(n) if rows is None else rows):
+        base = int(off[i])
+        lo, hi = int(sp[i]), int(sp[i + 1])
+        out.append([data[base + b:base + e].decode('utf-8') for b, e in zip(wb[lo:hi].tolist(), we[lo:hi].tolist())])
+    return out
+
+
+def word_tokenize_hindi_batch(texts, use_morphology=False, device=0):
+    """word_tokenize_hindi over a batch: normalize_text on the device, then the word kernel over the normalized text"""
+    eng = engine(device)
+    norm = eng.normalize_batch(texts)
+    wb, we, sp = eng.word_tokenize_batch(norm, rule=C.WORDS_HINDI)
+    return _word_slices(norm, wb, we, sp)
+
+
+word_tokenize_sanskrit_batch = word_tokenize_hindi_batch      # the reference's two loops are the same (segment.py:335-362)
+
+
+def word_tokenize_batch(texts, language='auto', use_morphology=False, device=0):
+    """word_tokenize over a batch (reference segment.py:365-401)"""
+    lang = language.lower()
+    if language != 'auto':
+        if lang in ('hindi', 'hi', 'hin', 'sanskrit', 'sa', 'san', 'skr'):
+            return word_tokenize_hindi_batch(texts, use_morphology, device)
+    eng = engine(device)
+    raw = eng.put(texts)
+    wb, we, sp, fl = eng.word_tokenize_batch(raw, rule=C.WORDS_SPLIT, row_flags=True)
+    out = _word_slices(raw, wb, we, sp)
+    if language != 'auto':
+        return out                                            # unknown language: whitespace split (segment.py:399-401)
+    deva = [i for i, f in enumerate(fl.cpu().numpy().tolist()) if f]
+    if deva:
+        # rows with a code point of U+0900-097F take the Hindi route (segment.py:384-388)
+        sub = word_tokenize_hindi_batch([texts[i] for i in deva], use_morphology, device)
+        for i, w in zip(deva, sub):
+            out[i] = w
+    return out
+
+
 # ---- reference API (same signatures) ------------------------------------------------------------------
+def word_tokenize_hindi(text, use_morphology=False):
+    """reference segment.py:239-300.  `use_morphology` asks the reference for its Morfessor model when one is loaded and
+    silently takes this same loop when none is (morph.py is out of scope here: no model is ever loaded)."""
+    return word_tokenize_hindi_batch([text], use_morphology)[0]
+
+
+def word_tokenize_sanskrit(text, use_morphology=False):
+    """reference segment.py:303-362"""
+    return word_tokenize_sanskrit_batch([text], use_morphology)[0]
+
+
+def word_tokenize(text, language='auto', use_morphology=False):
+    """reference segment.py:365-401"""
+    return word_tokenize_batch([text], language, use_morphology)[0]
+
+
 def segment_akshars(text, matras=False, separate_matras=None):
     """reference segment.py:40-125"""
     if separate_matras is not None:

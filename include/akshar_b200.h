@@ -92,6 +92,21 @@ int akshar_segment_batch(akshar_ctx* ctx, const uint8_t* d_text, const int64_t* 
                          int64_t run_capacity, int64_t* d_run_splits, int64_t* d_result, void* d_workspace,
                          size_t workspace_bytes, void* stream);
 
+/* word_tokenize_hindi / word_tokenize_sanskrit / word_tokenize over a batch (segment.py:239-401).
+ * rule AKSHAR_WORDS_HINDI: the loop of segment.py:270-297 (= :335-362) over text that normalize_text has already been
+ *   applied to (segment.py:258): str.isspace() separates, U+0964 / U+0965 are tokens of their own, .,!?;:()[]{}"' separate
+ *   and are dropped.  rule AKSHAR_WORDS_SPLIT: text.split() (segment.py:391-393, 400-401) -- only str.isspace() separates.
+ * word_begin / word_end: int32 byte offsets of each token (end exclusive) relative to its row start; word_splits[r] =
+ * tokens in rows before r (n_rows + 1 entries).  row_flags (optional, n_rows bytes): bit 0 = the row holds a code point of
+ * U+0900-097F, the test `word_tokenize(language='auto')` routes on (segment.py:384-388).  result[0] = tokens (exact also
+ * when AKSHAR_ST_OVERFLOW says word_capacity was too small). */
+#define AKSHAR_WORDS_HINDI 0
+#define AKSHAR_WORDS_SPLIT 1
+int akshar_word_tokenize_batch(akshar_ctx* ctx, const uint8_t* d_text, const int64_t* d_row_offsets, int64_t n_rows,
+                               int64_t text_begin, int64_t text_end, int rule, int32_t* d_word_begin, int32_t* d_word_end,
+                               int64_t word_capacity, int64_t* d_word_splits, uint8_t* d_row_flags, int64_t* d_result,
+                               void* d_workspace, size_t workspace_bytes, void* stream);
+
 /* roman_phonetic_signature over a batch of words (normalize.py:59-89); one word per row. result[0] = out bytes */
 int akshar_signature_batch(akshar_ctx* ctx, const uint8_t* d_text, const int64_t* d_row_offsets, int64_t n_rows,
                            int64_t text_begin, int64_t text_end, uint8_t* d_out_text, int64_t out_capacity,
@@ -156,7 +171,8 @@ enum {
     AKSHAR_TIMER_UNIGRAM = 4,              /* ak_resolve_kernel<1> (word events -> Unigram ids), or ak_unigram_kernel in row mode */
     AKSHAR_TIMER_WORDS = 5,                /* ak_words_kernel (text -> word / row events) */
     AKSHAR_TIMER_EMIT = 6,                 /* ak_emit_kernel (ids to their final place) */
-    AKSHAR_TIMER_COUNT = 7
+    AKSHAR_TIMER_WORDTOK = 7,              /* ak_wtok_kernel<emit> (word tokenizers) */
+    AKSHAR_TIMER_COUNT = 8
 };
 int akshar_timing_enable(akshar_ctx* ctx, int enable);
 

@@ -466,6 +466,77 @@ def analyze_text_composition(text):
 
 
 # --------------------------------------------------------------------------------------------------
+# f3  word tokenizers (reference segment.py:239-401)
+# --------------------------------------------------------------------------------------------------
+# str.isspace() (CPython, Unicode 15.0: bidirectional class WS / B / S or category Zs), written out
+_PY_SPACE = frozenset([0x09, 0x0A, 0x0B, 0x0C, 0x0D, 0x1C, 0x1D, 0x1E, 0x1F, 0x20, 0x85, 0xA0, 0x1680] + list(range(0x2000, 0x200B)) +
+                      [0x2028, 0x2029, 0x202F, 0x205F, 0x3000])
+_WORD_PUNCT = frozenset(ord(c) for c in '.,!?;:()[]{}"\'')      # segment.py:272 `other_punct`
+
+
+def _word_loop(cps):
+    """segment.py:270-297 (Hindi) == segment.py:335-362 (Sanskrit): -> list of (begin, end) code point ranges"""
+    out = []
+    start = -1
+    for i, cp in enumerate(cps):
+        if cp in _PY_SPACE or cp in _WORD_PUNCT:
+            if start >= 0:
+                out.append((start, i))
+                start = -1
+        elif cp == 0x0964 or cp == 0x0965:
+            if start >= 0:
+                out.append((start, i))
+                start = -1
+            out.append((i, i + 1))
+        elif start < 0:
+            start = i
+    if start >= 0:
+        out.append((start, len(cps)))
+    return out
+
+
+def _split_loop(cps):
+    """str.split(): runs of non-space code points"""
+    out = []
+    start = -1
+    for i, cp in enumerate(cps):
+        if cp in _PY_SPACE:
+            if start >= 0:
+                out.append((start, i))
+                start = -1
+        elif start < 0:
+            start = i
+    if start >= 0:
+        out.append((start, len(cps)))
+    return out
+
+
+def word_tokenize_hindi(text, use_morphology=False):
+    """segment.py:239-300 without a Morfessor model (none ships with the reference: morph.py falls through to this loop)"""
+    n = normalize_text(text, normalize_roman=True, clean_hinglish=True)
+    return [n[b:e] for b, e in _word_loop([ord(c) for c in n])]
+
+
+def word_tokenize_sanskrit(text, use_morphology=False):
+    """segment.py:303-362"""
+    return word_tokenize_hindi(text, use_morphology)
+
+
+def word_tokenize(text, language='auto', use_morphology=False):
+    """segment.py:365-401"""
+    if language == 'auto':
+        if any(0x0900 <= ord(c) <= 0x097F for c in text):
+            language = 'hindi'
+        else:
+            return [text[b:e] for b, e in _split_loop([ord(c) for c in text])]
+    if language.lower() in ('hindi', 'hi', 'hin'):
+        return word_tokenize_hindi(text, use_morphology)
+    if language.lower() in ('sanskrit', 'sa', 'san', 'skr'):
+        return word_tokenize_sanskrit(text, use_morphology)
+    return [text[b:e] for b, e in _split_loop([ord(c) for c in text])]
+
+
+# --------------------------------------------------------------------------------------------------
 # a17  BPE (HuggingFace tokenizers JSON written by the reference's scripts/train_bpe.py:68-98; SURVEY.md B4)
 # --------------------------------------------------------------------------------------------------
 class BpeModel:

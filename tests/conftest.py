@@ -13,6 +13,9 @@ for p in (ROOT, os.path.join(ROOT, 'oracle'), os.path.join(ROOT, 'tools')):
 GOLDEN = os.path.join(ROOT, 'tests', 'golden')
 MODELS = os.path.join(GOLDEN, 'models')
 
+# the reference's own test files kept as fixtures: run (unmodified) by test_gpu_parity.py, never collected directly
+collect_ignore_glob = ['golden/ref_tests/*']
+
 
 def pytest_configure(config):
     config.addinivalue_line('markers', 'gpu: needs a CUDA device (run on the B200 box with -m gpu)')

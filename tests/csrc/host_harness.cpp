@@ -13,6 +13,7 @@
 #include "../../akshar_b200/csrc/ak_seg3.cuh"
 #include "../../akshar_b200/csrc/ak_bpe3.cuh"
 #include "../../akshar_b200/csrc/ak_tok.cuh"
+#include "../../akshar_b200/csrc/ak_wordtok.cuh"
 #include "../../akshar_b200/csrc/ak_tok_host.h"
 #include "../../akshar_b200/csrc/ak_models.h"
 #include "../../akshar_b200/csrc/unicode_tables.inc"
@@ -287,6 +288,62 @@ void hh_seg_fast3(const uint8_t* text, const int64_t* off, int64_t n_rows, uint3
     totals[1] = rbase;
     *status = st;
     *n_slow = slow_cnt;
+}
+
+// word tokenizers (ak_wordtok.cuh): the kernel's lane structure -- `real` lanes + 2 halo lanes per "warp", count pass, prefix,
+// emit pass through the same akwt_emit_lane
+int64_t hh_wordtok(const uint8_t* text, const int64_t* off, int64_t n_rows, int mode, int real, int32_t* begin, int32_t* end,
+                   int64_t cap, int64_t* splits, uint8_t* row_flags, uint32_t* status) {
+    const int64_t tb = off[0], te = off[n_rows], base0 = tb;
+    std::vector<uint8_t> rowstart((size_t)(te - base0) + 128, 0);
+    for (int64_t r = 0; r <= n_rows; ++r) rowstart[(size_t)(off[r] - base0)] = 1;
+    const int64_t n_lanes = (te - base0 + 1 + 31) / 32;
+    const int NL = real + 2;
+    std::vector<AkWtLane> lanes((size_t)NL);
+    std::vector<uint32_t> open((size_t)NL);
+    uint32_t st = 0;
+    if (row_flags) memset(row_flags, 0, (size_t)n_rows);
+    int64_t total = 0;
+    for (int pass = 0; pass < 2; ++pass) {
+        int64_t t_at = 0, nr = 0;
+        for (int64_t w0 = 0; w0 < n_lanes; w0 += real) {
+            for (int l = 0; l < NL; ++l) {
+                AkWtLane& L = lanes[(size_t)l];
+                memset(&L, 0, sizeof(L));
+                const int64_t cs = base0 + (w0 - 1 + l) * 32;
+                uint32_t x[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+                for (int i = 0; i < 32; ++i) {
+                    const int64_t q = cs + i;
+                    if (q >= tb && q < te) { x[i >> 2] |= (uint32_t)text[q] << ((i & 3) * 8); L.own |= 1u << i; }
+                    if (q == te) L.endbit = 1u << i;
+                    if (q >= base0 && q - base0 < (int64_t)rowstart.size() && rowstart[(size_t)(q - base0)]) L.rows |= 1u << i;
+                }
+                akwt_phase1(x, L);
+            }
+            for (int l = 0; l < NL; ++l) {
+                AkWtLane& L = lanes[(size_t)l];
+                akwt_phase2(L, l + 1 < NL ? lanes[(size_t)l + 1].dn : 0u, mode);
+                if (L.hl & ~L.DEV) akwt_wide(text, base0 + (w0 - 1 + l) * 32, te, L);
+                akwt_summary(L);
+            }
+            for (int l = 0; l < NL; ++l) open[(size_t)l] = akwt_phase3(lanes[(size_t)l], l > 0 ? lanes[(size_t)l - 1].up : 0u);
+            for (int l = 1; l <= real; ++l) {
+                const AkWtLane& L = lanes[(size_t)l];
+                const int64_t cs = base0 + (w0 - 1 + l) * 32;
+                if (pass == 1) {
+                    while (nr <= n_rows && off[nr] < cs) ++nr;
+                    int nrows = 0;
+                    while (nr + nrows <= n_rows && off[nr + nrows] < cs + 32) ++nrows;
+                    akwt_emit_lane(L, cs, off, n_rows, nr, nrows, nr - 1, t_at, t_at - (int64_t)open[(size_t)l], begin, end, cap, splits,
+                                   row_flags, st);
+                }
+                t_at += akb_popc(L.T);
+            }
+        }
+        total = t_at;
+    }
+    *status = st;
+    return total;
 }
 
 // roman_phonetic_signature of every row; returns output bytes

@@ -66,6 +66,57 @@ def test_code_switch_golden(A, golden):
     assert A.analyze_text_composition_batch([r['norm'] for r in rows]) == [r['comp'] for r in rows]
 
 
+def test_word_tokenizers_golden(A, golden):
+    """reference segment.py:239-401 (recorded from the unmodified reference): Hindi / Sanskrit loops and the auto route"""
+    rows = golden['rows']
+    ins = [r['in'] for r in rows]
+    assert A.word_tokenize_hindi_batch(ins) == [r['words_hi'] for r in rows]
+    assert A.word_tokenize_sanskrit_batch(ins) == [r['words_sa'] for r in rows]
+    assert A.word_tokenize_batch(ins) == [r['words_auto'] for r in rows]
+    assert A.word_tokenize_batch(ins, language='hi') == [r['words_hi'] for r in rows]
+    assert A.word_tokenize_batch(ins[:500], language='tamil') == [s.split() for s in ins[:500]]
+    assert A.word_tokenize("\u0930\u093e\u092e\u0964 \u0938\u0940\u0924\u093e\u0965 (x)") == \
+        ['\u0930\u093e\u092e', '\u0964', '\u0938\u0940\u0924\u093e', '\u0965', 'x']
+    assert A.word_tokenize("Hello,  World \u2003 again") == ['Hello,', 'World', 'again']
+    assert A.word_tokenize("") == [] and A.word_tokenize_hindi("   ") == [] and A.word_tokenize_batch([]) == []
+
+
+def test_word_tokenizers_oracle_large(A, eng):
+    """64 MB of mixed text against the oracle's loops, both rules, row flags; then a property at 512 MB: every token is a
+    maximal run of non-separator bytes (checked on the device output with numpy)"""
+    lines = sc.Corpus('social', 31).lines(20 << 20) + sc.adversarial(3000, 77, 64) + sc.Corpus('hindi', 32).lines(20 << 20)
+    from akshar_b200 import _lib as C
+    b = eng.put(lines)
+    import test_span_walkers as TW
+    for mode, rule in ((0, C.WORDS_HINDI), (1, C.WORDS_SPLIT)):
+        eb, ee, es, ef = TW._words_expected(lines, mode)
+        wb, we, sp, fl = eng.word_tokenize_batch(b, rule=rule, row_flags=True)
+        assert np.array_equal(_np(sp), es)
+        assert np.array_equal(_np(wb), eb) and np.array_equal(_np(we), ee)
+        assert np.array_equal(_np(fl), ef)
+    big = sc.Corpus('hinglish', 33)
+    data, off = big.generate(512 << 20)
+    import torch
+    tb = A.TextBatch(torch.from_numpy(data).cuda(), torch.from_numpy(off).cuda(), 0, int(off[-1]))
+    wb, we, sp = eng.word_tokenize_batch(tb, rule=C.WORDS_SPLIT)
+    spn = _np(sp)
+    assert spn[0] == 0 and spn[-1] == wb.numel() and np.all(np.diff(spn) >= 0)
+    # the corpus is ASCII + Devanagari (no wide spaces): words = non-space bytes after a space or a row start
+    lut = np.zeros(256, dtype=bool)
+    lut[[9, 10, 11, 12, 13, 28, 29, 30, 31, 32]] = True
+    space = lut[data]
+    starts = np.zeros(data.size + 1, dtype=bool)
+    starts[off[:-1]] = True
+    prev_space = np.concatenate(([True], space[:-1]))
+    n_words = int(np.count_nonzero(~space & (prev_space | starts[:-1])))
+    assert wb.numel() == n_words
+    row_of = np.repeat(np.arange(off.size - 1), np.diff(spn))
+    ab = off[row_of] + _np(wb)
+    ae = off[row_of] + _np(we)
+    assert np.all(ae > ab) and np.all(ab[1:] >= ae[:-1])
+    assert int((ae - ab).sum()) == int(np.count_nonzero(~space))          # tokens cover exactly the non-space bytes
+
+
 def test_signature_golden(A, golden):
     words = list(golden['signature'])
     assert A.roman_phonetic_signature_batch(words) == [golden['signature'][w] for w in words]
@@ -142,6 +193,18 @@ def test_reference_unit_expectations(A):
         A.aksharTokenizer(os.path.join(os.path.dirname(__file__), 'conftest.py'), 'nonsense')
     # executed notebook cell
     assert tk.tokenize("aaj मौसम बहुत अच्छा है") == ['a', 'a', 'j', ' ', 'मौ', 'स', 'म', ' ', 'ब', 'हु', 'त', ' ', 'अ', 'च्छा', ' ', 'है']
+
+
+def test_reference_test_files_run_unmodified(A):
+    """the reference's three test files (byte-for-byte copies kept as fixtures under tests/golden/ref_tests) against the
+    `akshar` drop-in package: `from akshar.tokenizer import AksharTokenizer`, `from akshar.normalize import ...`"""
+    import unittest
+    here = os.path.join(os.path.dirname(__file__), 'golden', 'ref_tests')
+    import akshar
+    assert akshar.aksharTokenizer is A.aksharTokenizer
+    suite = unittest.defaultTestLoader.discover(here, pattern='test_*.py', top_level_dir=here)
+    res = unittest.TextTestRunner(verbosity=0).run(suite)
+    assert res.testsRun >= 25 and res.wasSuccessful(), (res.errors, res.failures)
 
 
 # ------------------------------------------------------------------ oracle on seeded synthetic + adversarial input

@@ -46,6 +46,19 @@ def test_reference_test_expectations():
     assert [O.roman_phonetic_signature(w) for w in ('nahi', 'nahii', 'nahee')] == ['nahi', 'nahii', 'nahi']
 
 
+def test_word_tokenizers(golden):
+    # reference segment.py:239-401, recorded by tools/make_golden.py
+    for r in golden['rows']:
+        s = r['in']
+        assert O.word_tokenize_hindi(s) == r['words_hi']
+        assert O.word_tokenize_sanskrit(s) == r['words_sa']
+        assert O.word_tokenize(s) == r['words_auto']
+    # str.isspace() written out in the oracle == this interpreter's (Unicode 15.0, pinned above)
+    assert sorted(O._PY_SPACE) == [c for c in range(0x110000) if chr(c).isspace()]
+    assert O.word_tokenize("राम। सीता॥ (गीता)") == ['राम', '।', 'सीता', '॥', 'गीता']
+    assert O.word_tokenize("a\u2003b\x1fc  d", language='xx') == ['a', 'b', 'c', 'd']
+
+
 def test_segment_and_runs(golden):
     for r in golden['rows']:
         s, n = r['in'], r['norm']

@@ -319,3 +319,61 @@ def test_segment_bit_parallel_is_all_fast_on_normalized_text():
     for kind in ('hinglish', 'hindi', 'social'):
         lines = [O.normalize_text(s) for s in sc.Corpus(kind, 8).lines(100000)]
         assert _seg3_check(lines, 30) < 0.001
+
+
+# ---- word tokenizers (ak_wordtok.cuh; reference segment.py:239-401) -------------------------------------------------
+def _words_expected(lines, mode):
+    """token (begin, end) byte offsets per row from the oracle's loops over the text AS IT IS (normalizing is the caller's job)"""
+    loop = O._word_loop if mode == 0 else O._split_loop
+    begin, end, splits, flags = [], [], [0], []
+    for s in lines:
+        cps = [ord(c) for c in s]
+        pre = [0]
+        for cp in cps:
+            pre.append(pre[-1] + O.utf8_len(cp))
+        for b, e in loop(cps):
+            begin.append(pre[b])
+            end.append(pre[e])
+        splits.append(len(begin))
+        flags.append(1 if any(0x0900 <= cp <= 0x097F for cp in cps) else 0)
+    return np.array(begin, dtype=np.int32), np.array(end, dtype=np.int32), np.array(splits, dtype=np.int64), np.array(flags, dtype=np.uint8)
+
+
+def _words_check(lines, real):
+    data, off = sc.pack(lines)
+    for mode in (0, 1):
+        eb, ee, es, ef = _words_expected(lines, mode)
+        wb, we, sp, fl, st = W.wordtok(data, off, mode=mode, real=real)
+        assert st == 0
+        assert np.array_equal(sp, es)
+        assert np.array_equal(wb, eb) and np.array_equal(we, ee)
+        assert np.array_equal(fl, ef)
+
+
+@pytest.mark.parametrize('real', [30, 1, 5])
+def test_word_tokenizer_lane_structure(real):
+    lines = list(_lines())
+    _words_check(lines, real)                                           # raw text: every kind of character
+    _words_check([O.normalize_text(s) for s in lines[:3000]], real)     # what word_tokenize_hindi feeds the loop
+
+
+def test_word_tokenizer_fuzz():
+    alpha = ['a', 'Z', ' ', ' ', '1', '.', ',', '!', '?', ';', ':', '(', ')', '[', ']', '{', '}', '"', "'", '-', '_', 'क', 'ा',
+             '्', '।', '॥', '।', '॰', '\t', '\n', '\x0b', '\x0c', '\r', '\x1c', '\x1d', '\x1e', '\x1f', '\x00',
+             '\x7f', '\x85', '\xa0', ' ', ' ', ' ', '​', ' ', ' ', ' ', ' ', '　',
+             '、', '\U0001F600', 'ক', '\xe9', 'ॣ', '०', '@', '/', '\\']
+    rng = np.random.default_rng(12)
+    for max_len, real in [(150, 30), (500, 3), (5, 2), (40, 30)]:
+        lines = []
+        for _ in range(1500):
+            n_ch = int(rng.integers(0, max_len + 1))
+            if rng.random() < 0.7:
+                lines.append(''.join(alpha[int(i)] for i in rng.integers(0, len(alpha), size=n_ch)))
+            else:
+                s = ''
+                while len(s) < n_ch:
+                    s += alpha[int(rng.integers(len(alpha)))] * int(rng.integers(1, 70))
+                lines.append(s)
+        _words_check(lines, real)
+    _words_check(['', '', '।', '', 'a' * 200, '', ' ' * 100, '॥' * 50, 'a।', '।a', ''], 30)
+    _words_check(['क' * 31 + '।', 'ab' + '।' * 10 + 'c', 'x' * 29 + '।' + 'y'], 30)           # danda across lanes

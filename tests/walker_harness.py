@@ -183,6 +183,22 @@ def seg_fast3(data, off, flags=1, real=30):
     return ce[:tot[0]], cs, re_[:tot[1]], rt[:tot[1]], rs, st.value, ns.value
 
 
+def wordtok(data, off, mode=0, real=30):
+    """the word tokenizers (ak_wordtok.cuh) through the kernel's lane structure -> (begin, end, splits, row_flags, status)"""
+    data = np.ascontiguousarray(data, dtype=np.uint8)
+    off = np.ascontiguousarray(off, dtype=np.int64)
+    cap = int(data.size) + 8
+    wb = np.full(cap, -1, dtype=np.int32)
+    we = np.full(cap, -1, dtype=np.int32)
+    sp = np.full(off.size, -1, dtype=np.int64)
+    fl = np.zeros(max(off.size - 1, 1), dtype=np.uint8)
+    st = ctypes.c_uint32(0)
+    lib().hh_wordtok.restype = ctypes.c_int64
+    n = lib().hh_wordtok(_p(data), _p(off), ctypes.c_int64(off.size - 1), ctypes.c_int(mode), ctypes.c_int(real), _p(wb), _p(we),
+                         ctypes.c_int64(cap), _p(sp), _p(fl), ctypes.byref(st))
+    return wb[:n], we[:n], sp, fl[:off.size - 1], st.value
+
+
 def tok(kind, data, off, real=30, cache_bits=14, prewarm=1, u16=False, splits_i32=False, cap=None):
     """the event-stream encoders (ak_tok.cuh) on the CPU: lanes -> event slots -> row fix -> resolve -> check -> emit.
     kind 0 BPE, 1 Unigram; cap = event slots per emulated warp tile -> (ids, splits, status, stats dict)"""
