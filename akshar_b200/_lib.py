@@ -10,21 +10,22 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get('AKSHAR_B200_LIB') or os.path.join(_HERE, 'lib', 'libakshar_b200.so')
 
 OK, E_ARG, E_CUDA, E_MODEL, E_NOMODEL, E_WORKSPACE = 0, -1, -2, -3, -4, -5
-ST_OVERFLOW, ST_NFC_SEGMENT, ST_PATHOLOGICAL, ST_ALPHABET, ST_SPIN, ST_WORD, ST_INTERNAL = 1, 2, 4, 8, 16, 32, 64
+ST_OVERFLOW, ST_NFC_SEGMENT, ST_PATHOLOGICAL, ST_ALPHABET, ST_SPIN, ST_WORD, ST_INTERNAL, ST_BAD_ID = 1, 2, 4, 8, 16, 32, 64, 128
 NORM_ROMAN, NORM_FILTER, NORM_COLLAPSE, NORM_CLEAN, NORM_NO_NFC = 1, 2, 4, 6, 8
 SEG_CLUSTERS, SEG_MATRAS, SEG_RUNS = 1, 2, 4
 MODE_TILES, MODE_ROWS = 0, 1
 OUT_IDS_U16, OUT_SPLITS_I32 = 1, 2
 WORDS_HINDI, WORDS_SPLIT = 0, 1
+FORM_DECODE, FORM_DETOKENIZE = 0, 1
 TIMERS = {'ak_nf3_classify_kernel': 0, 'ak_nf_write_kernel': 1, 'ak_resolve_kernel<bpe>': 2, 'ak_sf3_kernel': 3,
-          'ak_resolve_kernel<unigram>': 4, 'ak_words_kernel': 5, 'ak_emit_kernel': 6, 'ak_wtok_kernel': 7}
+          'ak_resolve_kernel<unigram>': 4, 'ak_words_kernel': 5, 'ak_emit_kernel': 6, 'ak_wtok_kernel': 7, 'ak_dec_kernel': 8}
 
 SYMBOLS = (
     'akshar_version', 'akshar_status_str', 'akshar_ctx_create', 'akshar_ctx_destroy', 'akshar_last_error',
     'akshar_workspace_bytes', 'akshar_normalize_batch', 'akshar_segment_batch', 'akshar_signature_batch',
     'akshar_load_bpe_json', 'akshar_load_spm_model', 'akshar_vocab_size', 'akshar_vocab_token',
     'akshar_encode_bpe_batch', 'akshar_encode_unigram_batch', 'akshar_tokenizer_encode_batch', 'akshar_tokenizer_encode_batch_ex',
-    'akshar_launch_count', 'akshar_timing_enable', 'akshar_timing_read', 'akshar_word_cache_hold', 'akshar_word_tokenize_batch',
+    'akshar_launch_count', 'akshar_timing_enable', 'akshar_timing_read', 'akshar_word_cache_hold', 'akshar_word_tokenize_batch', 'akshar_decode_workspace_bytes', 'akshar_decode_batch',
 )
 
 _lib = None
@@ -60,6 +61,9 @@ def load():
     L.akshar_segment_batch.argtypes = [vp, vp, vp, i64, i64, i64, u32, i32, vp, i64, vp, vp, vp, i64, vp, vp, vp, sz, vp]
     L.akshar_signature_batch.argtypes = [vp, vp, vp, i64, i64, i64, vp, i64, vp, vp, vp, sz, vp]
     L.akshar_word_tokenize_batch.argtypes = [vp, vp, vp, i64, i64, i64, i32, vp, vp, i64, vp, vp, vp, vp, sz, vp]
+    L.akshar_decode_workspace_bytes.argtypes = [i64, i64]
+    L.akshar_decode_workspace_bytes.restype = sz
+    L.akshar_decode_batch.argtypes = [vp, i32, i32, vp, i32, i64, vp, i64, vp, i64, vp, vp, vp, sz, vp]
     L.akshar_load_bpe_json.argtypes = [vp, c.c_char_p, sz]
     L.akshar_load_spm_model.argtypes = [vp, c.c_char_p, sz]
     L.akshar_vocab_size.argtypes = [vp, i32]

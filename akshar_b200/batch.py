@@ -273,6 +273,44 @@ class Engine:
             return out + (fl[:b.n_rows],) if row_flags else out
         raise BatchStatusError(bits, 'word_tokenize_batch (retries exhausted)')
 
+    # ------------------------------------------------------------------ ids -> text
+    def decode_batch(self, ids, splits, kind, form=C.FORM_DECODE, capacity=None):
+        """aksharTokenizer.decode / detokenize over a batch of id rows (reference tokenizer.py:195-246) -> TextBatch.
+        ids: device int32 (or uint16) tensor, or a Ragged from encode; splits: int64 [n_rows + 1] positions in ids"""
+        if isinstance(ids, Ragged):
+            ids, splits = ids.values, ids.splits
+        dev = self.device
+        ids = ids.to(dev)
+        splits = splits.to(dev)
+        if ids.dtype not in (torch.int32, torch.uint16, torch.int16):
+            ids = ids.to(torch.int32)
+        n_ids, n_rows = ids.numel(), splits.numel() - 1
+        need = self.lib.akshar_decode_workspace_bytes(n_ids, n_rows)
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = None
+            self._ws = torch.empty(need + (need >> 3), dtype=torch.uint8, device=dev)
+        ws = self._ws
+        cap = capacity if capacity is not None else 6 * n_ids + 1024
+        for _ in range(self.MAX_TRIES):
+            out = torch.empty(max(cap, 1), dtype=torch.uint8, device=dev)
+            out_off = torch.empty(n_rows + 1, dtype=torch.int64, device=dev)
+            result = torch.empty(4, dtype=torch.int64, device=dev)
+            rc = self.lib.akshar_decode_batch(self._h, kind, form, ids.data_ptr(), 0 if ids.dtype == torch.int32 else 1, n_ids,
+                                              splits.data_ptr(), n_rows, out.data_ptr(), cap, out_off.data_ptr(), result.data_ptr(),
+                                              ws.data_ptr(), ws.numel(), self._stream())
+            if rc != 0:
+                self._err(rc, 'akshar_decode_batch')
+            total, _, bits = self._finish(result, 'decode', True)
+            if bits & C.ST_BAD_ID:
+                raise IndexError('piece id is out of range.')         # what SentencePiece's DecodeIds raises
+            if bits & C.ST_OVERFLOW:
+                cap = total
+                continue
+            if bits:
+                raise BatchStatusError(bits, 'decode_batch')
+            return TextBatch(out, out_off, 0, total)
+        raise BatchStatusError(bits, 'decode_batch (retries exhausted)')
+
     # ------------------------------------------------------------------ K1b
     def signature_batch(self, batch):
         """roman_phonetic_signature over a batch of words, one per row (reference normalize.py:59-89) -> TextBatch"""

@@ -16,7 +16,8 @@
 
 static_assert((int)AK_ST_OVERFLOW == (int)AKSHAR_ST_OVERFLOW && (int)AK_ST_NFC_SEGMENT == (int)AKSHAR_ST_NFC_SEGMENT &&
               (int)AK_ST_PATHOLOGICAL == (int)AKSHAR_ST_PATHOLOGICAL && (int)AK_ST_ALPHABET == (int)AKSHAR_ST_ALPHABET &&
-              (int)AK_ST_SPIN == (int)AKSHAR_ST_SPIN && (int)AK_ST_WORD == (int)AKSHAR_ST_WORD, "status bits out of sync");
+              (int)AK_ST_SPIN == (int)AKSHAR_ST_SPIN && (int)AK_ST_WORD == (int)AKSHAR_ST_WORD &&
+              (int)AK_ST_INTERNAL == (int)AKSHAR_ST_INTERNAL && (int)AK_ST_BAD_ID == (int)AKSHAR_ST_BAD_ID, "status bits out of sync");
 static_assert(AK_NORM_ROMAN == AKSHAR_NORM_ROMAN && AK_NORM_CLEAN == AKSHAR_NORM_CLEAN && AK_NORM_FILTER == AKSHAR_NORM_FILTER &&
               AK_NORM_COLLAPSE == AKSHAR_NORM_COLLAPSE && AK_NORM_NO_NFC == AKSHAR_NORM_NO_NFC, "flags out of sync");
 static_assert(AK_SEG_CLUSTERS == AKSHAR_SEG_CLUSTERS && AK_SEG_MATRAS == AKSHAR_SEG_MATRAS &&

@@ -25,6 +25,7 @@
 #include "ak_bpe3.cuh"
 #include "ak_tok.cuh"
 #include "ak_tok_host.h"
+#include "ak_decode_host.h"
 #include "unicode_tables.inc"
 
 
@@ -34,6 +35,7 @@
 #include "ak_sub_kernels.cuh"
 #include "ak_tok_kernels.cuh"
 #include "ak_wtok_kernels.cuh"
+#include "ak_decode_kernels.cuh"
 
 // ================================================================================================
 // host side: context, model upload, C ABI
@@ -60,6 +62,7 @@ struct akshar_ctx {
     std::vector<void*> bpe_allocs, uni_allocs;
     // event-stream encoders (ak_tok.cuh): one word cache per model, image built at load
     AkcTable tok_cache[2];
+    AkDecTable dec[2][2] = {};     // [kind][form]: piece tables of the on-device decode / detokenize (ak_decode.cuh)
     bool uni_fast = false;         // the Unigram model has the shape the word-wise path needs
     int occ_words[2] = {0, 0}, occ_resolve[2] = {0, 0}, occ_check = 0, occ_emit = 0;
     // optional CUDA-event timing of the dominant kernel of each stage (bench.py's roofline line)
@@ -634,6 +637,102 @@ int akshar_word_tokenize_batch(akshar_ctx* ctx, const uint8_t* d_text, const int
     return ak_after_launch(ctx, "words-emit");
 }
 
+}  // extern "C"
+
+// ---- ids -> text ----------------------------------------------------------------------------------------------------
+struct AkDecWs {
+    size_t mark, count, base, tpre, state, total;
+};
+static AkDecWs ak_dec_ws(int64_t n_ids) {
+    AkDecWs W;
+    const size_t tiles = (size_t)(n_ids / AKD_TILE + 2);
+    W.mark = 256;
+    W.count = W.mark + ak_align((size_t)n_ids + 16);
+    W.base = W.count + ak_align(tiles * 4);
+    W.tpre = W.base + ak_align(tiles * 8);
+    W.state = W.tpre + ak_align(((size_t)n_ids / AKD_PER + 2) * 4);
+    W.total = W.state + ak_align((tiles / AKS_TILE + 2) * 8);
+    return W;
+}
+
+template <class IdT>
+static int ak_run_decode(akshar_ctx* ctx, const AkDecTable& D, int form, const void* d_ids, int64_t n_ids, const int64_t* d_row_splits,
+                         int64_t n_rows, uint8_t* d_out_text, int64_t out_capacity, int64_t* d_out_row_offsets, int64_t* d_result,
+                         char* ws, cudaStream_t s) {
+    const AkDecWs W = ak_dec_ws(n_ids);
+    int rc;
+    AK_CUDA(ctx, cudaMemsetAsync(ws, 0, W.count, s));                          // control block + marks
+    AK_CUDA(ctx, cudaMemsetAsync(ws + W.state, 0, W.total - W.state, s));
+    AK_CUDA(ctx, cudaMemsetAsync(d_result, 0, 4 * sizeof(int64_t), s));
+    AkDecArgs<IdT> A;
+    A.D = D;
+    A.form = form;
+    A.ids = (const IdT*)d_ids;
+    A.n_ids = n_ids;
+    A.splits = d_row_splits;
+    A.n_rows = n_rows;
+    A.mark = (uint8_t*)(ws + W.mark);
+    A.count = (int32_t*)(ws + W.count);
+    A.base = (const int64_t*)(ws + W.base);
+    A.tpre = (int32_t*)(ws + W.tpre);
+    A.out = d_out_text;
+    A.cap = out_capacity;
+    A.out_off = d_out_row_offsets;
+    A.result = d_result;
+    const int64_t n_tiles = (n_ids + AKD_TILE - 1) / AKD_TILE;
+    ak_dec_mark_kernel<IdT><<<ak_grid(ctx, 8, (int)((n_rows + 255) / 256)), 256, 0, s>>>(A);
+    if ((rc = ak_after_launch(ctx, "decode-mark"))) return rc;
+    const int grid = ak_grid(ctx, 8, (int)n_tiles);
+    ak_dec_kernel<IdT, false><<<grid, AKD_THREADS, 0, s>>>(A);
+    if ((rc = ak_after_launch(ctx, "decode-count"))) return rc;
+    ak_scan_counts_kernel<<<ak_grid(ctx, 4, (int)(n_tiles / AKS_TILE + 1)), AKS_THREADS, 0, s>>>(
+        A.count, (long long)n_tiles, nullptr, 1, (int64_t*)(ws + W.base), d_result, (int*)ws, (unsigned long long*)(ws + W.state),
+        (unsigned int*)&d_result[2]);
+    if ((rc = ak_after_launch(ctx, "decode-scan"))) return rc;
+    {
+        AkTimed tm(ctx, AKSHAR_TIMER_DECODE, s);
+        ak_dec_kernel<IdT, true><<<grid, AKD_THREADS, 0, s>>>(A);
+    }
+    if ((rc = ak_after_launch(ctx, "decode-write"))) return rc;
+    ak_dec_rowoff_kernel<IdT><<<ak_grid(ctx, 8, (int)((n_rows + 256) / 256)), 256, 0, s>>>(A);
+    return ak_after_launch(ctx, "decode-row-offsets");
+}
+
+extern "C" {
+
+size_t akshar_decode_workspace_bytes(int64_t n_ids, int64_t n_rows) {
+    if (n_ids < 0 || n_rows < 0) return 0;
+    return ak_dec_ws(n_ids).total;
+}
+
+int akshar_decode_batch(akshar_ctx* ctx, int kind, int form, const void* d_ids, int ids_u16, int64_t n_ids, const int64_t* d_row_splits,
+                        int64_t n_rows, uint8_t* d_out_text, int64_t out_capacity, int64_t* d_out_row_offsets, int64_t* d_result,
+                        void* d_workspace, size_t workspace_bytes, void* stream) {
+    if (!ctx) return AKSHAR_E_ARG;
+    AkDeviceGuard device_guard(ctx->device);
+    if ((kind != 0 && kind != 1) || (form != AKSHAR_FORM_DECODE && form != AKSHAR_FORM_DETOKENIZE) || n_ids < 0 || n_rows < 0 ||
+        (!d_ids && n_ids > 0) || !d_row_splits || !d_out_row_offsets || !d_result || out_capacity < 0 || (!d_out_text && out_capacity > 0)) {
+        ctx->err = "bad argument";
+        return AKSHAR_E_ARG;
+    }
+    if (!(kind == 0 ? ctx->has_bpe : ctx->has_uni)) {
+        ctx->err = "no model loaded";
+        return AKSHAR_E_NOMODEL;
+    }
+    const size_t need = ak_dec_ws(n_ids).total;
+    if (!d_workspace || workspace_bytes < need) {
+        ctx->err = "workspace too small: need " + std::to_string(need) + " bytes";
+        return AKSHAR_E_WORKSPACE;
+    }
+    const AkDecTable& D = ctx->dec[kind][form == AKSHAR_FORM_DECODE ? AKD_FORM_DECODE : AKD_FORM_DETOK];
+    const int f = form == AKSHAR_FORM_DECODE ? AKD_FORM_DECODE : AKD_FORM_DETOK;
+    if (ids_u16)
+        return ak_run_decode<uint16_t>(ctx, D, f, d_ids, n_ids, d_row_splits, n_rows, d_out_text, out_capacity, d_out_row_offsets,
+                                       d_result, (char*)d_workspace, (cudaStream_t)stream);
+    return ak_run_decode<int32_t>(ctx, D, f, d_ids, n_ids, d_row_splits, n_rows, d_out_text, out_capacity, d_out_row_offsets, d_result,
+                                  (char*)d_workspace, (cudaStream_t)stream);
+}
+
 int akshar_signature_batch(akshar_ctx* ctx, const uint8_t* d_text, const int64_t* d_row_offsets, int64_t n_rows,
                            int64_t text_begin, int64_t text_end, uint8_t* d_out_text, int64_t out_capacity,
                            int64_t* d_out_row_offsets, int64_t* d_result, void* d_workspace, size_t workspace_bytes,
@@ -715,6 +814,17 @@ static int ak_install_cache(akshar_ctx* ctx, std::vector<void*>& owner, const st
     return AKSHAR_OK;
 }
 
+// piece tables of decode / detokenize (ak_decode_host.h) to the device
+static int ak_install_decode(akshar_ctx* ctx, std::vector<void*>& owner, const AkDecHost& h, AkDecTable& t) {
+    int rc;
+    if ((rc = ak_upload<uint32_t>(ctx, owner, h.off.data(), h.off.size(), &t.off))) return rc;
+    if ((rc = ak_upload<uint8_t>(ctx, owner, h.bytes.data(), h.bytes.size(), &t.bytes))) return rc;
+    if ((rc = ak_upload<uint8_t>(ctx, owner, h.flags.data(), h.flags.size(), &t.flags))) return rc;
+    t.size = (int32_t)h.flags.size();
+    t.strict = h.strict;
+    return AKSHAR_OK;
+}
+
 static int ak_load_bpe_json(akshar_ctx* ctx, const char* json, size_t len) {
     AkBpeHost h;
     std::string e = ak_parse_bpe_json(json, len, h);
@@ -744,6 +854,8 @@ static int ak_load_bpe_json(akshar_ctx* ctx, const char* json, size_t len) {
         const std::vector<unsigned long long> img = ak_build_bpe_image(h, ht, AKC_BITS);
         if ((rc = ak_install_cache(ctx, ctx->bpe_allocs, img, ctx->tok_cache[0]))) return rc;
     }
+    for (int form = 0; form < 2; ++form)
+        if ((rc = ak_install_decode(ctx, ctx->bpe_allocs, ak_build_bpe_decode(h, form), ctx->dec[0][form]))) return rc;
     ctx->bpe_d = d;
     ctx->bpe_h = std::move(h);
     ctx->has_bpe = true;
@@ -782,6 +894,8 @@ static int ak_load_spm_model(akshar_ctx* ctx, const void* proto, size_t len) {
         const std::vector<unsigned long long> img = ak_build_uni_image(h, AKC_BITS);
         if ((rc = ak_install_cache(ctx, ctx->uni_allocs, img, ctx->tok_cache[1]))) return rc;
     }
+    for (int form = 0; form < 2; ++form)
+        if ((rc = ak_install_decode(ctx, ctx->uni_allocs, ak_build_spm_decode(h, form), ctx->dec[1][form]))) return rc;
     ctx->uni_d = d;
     ctx->uni_h = std::move(h);
     ctx->has_uni = true;

@@ -21,6 +21,7 @@ enum {
     AK_ST_SPIN = 16,           // decoupled look-back exceeded its spin budget (never expected)
     AK_ST_WORD = 32,           // BPE word longer than the per-word symbol capacity
     AK_ST_INTERNAL = 64,       // an internal consistency check failed (never expected)
+    AK_ST_BAD_ID = 128,        // decode: a token id outside the vocabulary (SentencePiece: 'piece id is out of range.')
 };
 #define AK_NORM_ROMAN 1u       // semantic_normalize: reference normalize_text(normalize_roman=True)
 #define AK_NORM_FILTER 2u      // filter_garbage      \ together: normalize_hinglish =

@@ -23,9 +23,18 @@ class _CudaModel:
     def __init__(self, eng, kind):
         self.kind = kind                       # 0 BPE, 1 Unigram
         self.size, self.vocab = eng.vocab(kind)
+        self._ids = None
 
     def token(self, i):
         return self.vocab[i][0]
+
+    def piece_id(self, piece):
+        if self._ids is None:
+            self._ids = {}
+            for i, (p, _) in enumerate(self.vocab):
+                if p is not None and p != '':
+                    self._ids.setdefault(p, i)
+        return self._ids.get(piece)
 
 
 class aksharTokenizer:
@@ -96,11 +105,16 @@ class aksharTokenizer:
     def decode(self, ids: List[int]) -> str:
         if self.model is None:
             raise ValueError("need model to decode")
-        if self.model_type == "sentencepiece":
-            return self._decode_spm(ids)
-        return ' '.join(self.model.token(i) for i in ids if not self.model.vocab[i][1])     # HF decode, decoder = null
+        return self.decode_batch([ids])[0]
 
     def detokenize(self, tokens: List[str]) -> str:
+        """reference tokenizer.py:221-246.  Token strings that are pieces of the loaded model (what `tokenize` returns) are
+        joined on the device from their ids; the reference also accepts arbitrary strings, which have no ids: for those
+        (and without a model) the joining expression of tokenizer.py:236-246 is evaluated as it stands."""
+        if self.model is not None:
+            ids = [self.model.piece_id(t) for t in tokens]
+            if all(i is not None for i in ids):
+                return self.detokenize_batch([ids])[0]
         if self.model_type == "sentencepiece":
             return ''.join(tokens).replace('▁', ' ').strip()
         elif self.model_type == "bpe":
@@ -142,6 +156,35 @@ class aksharTokenizer:
         return self._eng.encode_host_pipelined(h_data, h_offsets, self.model.kind, self.normalize_roman, self.clean_hinglish,
                                                out_ids=out_ids, out_splits=out_splits, compact=compact)
 
+    def _ids_to_text(self, rows, form):
+        import torch
+        if isinstance(rows, tuple):                       # (ids tensor, splits tensor) already on the device
+            return self._eng.decode_batch(rows[0], rows[1], self.model.kind, form)
+        if hasattr(rows, 'values') and hasattr(rows, 'splits'):
+            return self._eng.decode_batch(rows, None, self.model.kind, form)
+        import numpy as np
+        sp = np.zeros(len(rows) + 1, dtype=np.int64)
+        np.cumsum([len(r) for r in rows], out=sp[1:])
+        flat = np.fromiter((i for r in rows for i in r), dtype=np.int64, count=int(sp[-1]))
+        if flat.size and (flat.min() < -2 ** 31 or flat.max() >= 2 ** 31):
+            raise IndexError('piece id is out of range.')
+        return self._eng.decode_batch(torch.from_numpy(flat.astype(np.int32)), torch.from_numpy(sp), self.model.kind, form)
+
+    def decode_batch(self, id_rows, as_device=False):
+        """decode() over a batch: list of id lists, a Ragged from encode_batch(as_device=True), or (ids, splits) device
+        tensors -> list[str] (or the TextBatch on the device)"""
+        if self.model is None:
+            raise ValueError("need model to decode")
+        tb = self._ids_to_text(id_rows, C.FORM_DECODE)
+        return tb if as_device else tb.to_strings()
+
+    def detokenize_batch(self, id_rows, as_device=False):
+        """detokenize(pieces of the ids) over a batch (reference tokenizer.py:236-246)"""
+        if self.model is None:
+            raise ValueError("need model to detokenize ids")
+        tb = self._ids_to_text(id_rows, C.FORM_DETOKENIZE)
+        return tb if as_device else tb.to_strings()
+
     def tokenize_batch(self, texts):
         """tokenize() over a batch -> list[list[str]]"""
         if self.model is None:
@@ -168,60 +211,6 @@ class aksharTokenizer:
 
     def _pieces(self, ids):
         return [self.model.token(i) for i in ids]
-
-    def _decode_spm(self, ids):
-        """SentencePiece DecodeIds for a Unigram model with byte fallback: pieces are concatenated, runs of <0xNN>
-        pieces are reassembled into UTF-8 (invalid bytes -> U+FFFD each), <unk> decodes to ' ⁇ ', control pieces
-        are dropped, U+2581 becomes a space and the dummy-prefix space is removed."""
-        out = []
-        pend = bytearray()
-
-        def flush():
-            if pend:
-                out.append(_decode_bytes_spm(bytes(pend)))
-                pend.clear()
-
-        first = True
-        for i in ids:
-            if i < 0 or i >= self.model.size:
-                raise IndexError('piece id is out of range.')
-            piece, ty = self.model.vocab[i]
-            if ty == _SPM_BYTE:
-                pend.append(int(piece[3:5], 16))
-                continue
-            flush()
-            if ty == _SPM_CONTROL:
-                continue
-            if ty == _SPM_UNKNOWN:
-                out.append(' ⁇ ')
-                first = False
-                continue
-            if first and piece.startswith('▁'):
-                piece = piece[1:]
-            first = False
-            out.append(piece.replace('▁', ' '))
-        flush()
-        return ''.join(out)
-
-
-def _decode_bytes_spm(b):
-    # maximal valid UTF-8 prefixes, each invalid byte becomes U+FFFD
-    out = []
-    i = 0
-    while i < len(b):
-        for n in (1, 2, 3, 4):
-            try:
-                ch = b[i:i + n].decode('utf-8')
-                if len(ch) == 1:
-                    out.append(ch)
-                    i += n
-                    break
-            except UnicodeDecodeError:
-                continue
-        else:
-            out.append('�')
-            i += 1
-    return ''.join(out)
 
 
 AksharTokenizer = aksharTokenizer      # the name the reference's tests/test_tokenizer.py:11 imports

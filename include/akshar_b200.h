@@ -47,6 +47,8 @@ enum {
     AKSHAR_ST_WORD = 32,         /* the long-word pool ran out (many words beyond 48 symbols): call again with a larger
                                     workspace -- half of what exceeds akshar_workspace_bytes() goes to that pool */
     AKSHAR_ST_INTERNAL = 64,     /* an internal consistency check failed (never expected): the result is not to be used */
+    AKSHAR_ST_BAD_ID = 128,      /* decode: a token id outside the vocabulary of a SentencePiece model (DecodeIds raises
+                                    IndexError "piece id is out of range."); HF's decode skips such ids */
 };
 
 /* normalize flags: normalize_text(text, normalize_roman, clean_hinglish) (normalize.py:117) is
@@ -106,6 +108,23 @@ int akshar_word_tokenize_batch(akshar_ctx* ctx, const uint8_t* d_text, const int
                                int64_t text_begin, int64_t text_end, int rule, int32_t* d_word_begin, int32_t* d_word_end,
                                int64_t word_capacity, int64_t* d_word_splits, uint8_t* d_row_flags, int64_t* d_result,
                                void* d_workspace, size_t workspace_bytes, void* stream);
+
+/* aksharTokenizer.decode / detokenize over a batch of id rows (tokenizer.py:195-246); kind 0 BPE, 1 Unigram.
+ * form AKSHAR_FORM_DECODE: SentencePiece DecodeIds (control pieces dropped, <unk> -> " \u2047 ", runs of byte pieces
+ *   reassembled as UTF-8 with U+FFFD for every byte that is not part of a well-formed sequence, U+2581 -> ' ', the dummy
+ *   prefix consumed) / HF Tokenizer.decode with `decoder: null` (the tokens of the non-special ids joined by ' ').
+ * form AKSHAR_FORM_DETOKENIZE: `detokenize(tokenize pieces)` -- the piece strings of the ids joined the way
+ *   tokenizer.py:236-246 joins them (SentencePiece: ''.join, U+2581 -> ' ', strip; BPE: ' '.join, ' ##' removed,
+ *   U+0120 -> ' ', strip).
+ * d_ids: int32 (or uint16 with ids_u16 != 0: the compact output of akshar_tokenizer_encode_batch_ex), n_ids of them;
+ * d_row_splits: int64 [n_rows + 1] positions in d_ids.  Output: UTF-8 bytes + int64 [n_rows + 1] row offsets.
+ * result[0] = output bytes (exact also when AKSHAR_ST_OVERFLOW says out_capacity was too small). */
+#define AKSHAR_FORM_DECODE 0
+#define AKSHAR_FORM_DETOKENIZE 1
+size_t akshar_decode_workspace_bytes(int64_t n_ids, int64_t n_rows);
+int akshar_decode_batch(akshar_ctx* ctx, int kind, int form, const void* d_ids, int ids_u16, int64_t n_ids, const int64_t* d_row_splits,
+                        int64_t n_rows, uint8_t* d_out_text, int64_t out_capacity, int64_t* d_out_row_offsets, int64_t* d_result,
+                        void* d_workspace, size_t workspace_bytes, void* stream);
 
 /* roman_phonetic_signature over a batch of words (normalize.py:59-89); one word per row. result[0] = out bytes */
 int akshar_signature_batch(akshar_ctx* ctx, const uint8_t* d_text, const int64_t* d_row_offsets, int64_t n_rows,
@@ -172,7 +191,8 @@ enum {
     AKSHAR_TIMER_WORDS = 5,                /* ak_words_kernel (text -> word / row events) */
     AKSHAR_TIMER_EMIT = 6,                 /* ak_emit_kernel (ids to their final place) */
     AKSHAR_TIMER_WORDTOK = 7,              /* ak_wtok_kernel<emit> (word tokenizers) */
-    AKSHAR_TIMER_COUNT = 8
+    AKSHAR_TIMER_DECODE = 8,               /* ak_dec_kernel<write> (ids -> text) */
+    AKSHAR_TIMER_COUNT = 9
 };
 int akshar_timing_enable(akshar_ctx* ctx, int enable);
 

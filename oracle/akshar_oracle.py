@@ -636,7 +636,19 @@ def bpe_encode(model, text):
 
 
 def bpe_decode(model, ids):
-    return ' '.join(model.id_to_token[i] for i in ids if i not in model.special_ids)
+    """tokenizer.py:219-220 -> HF Tokenizer.decode(ids) with `decoder: null`: the tokens of the ids that are in the vocabulary
+    and not special, joined by one space (tokenizers 0.22.2; ids without a token are skipped -- tests/golden decode_fuzz)"""
+    return ' '.join(model.id_to_token[i] for i in ids if i in model.id_to_token and i not in model.special_ids)
+
+
+def bpe_detokenize(tokens):
+    """tokenizer.py:240-244"""
+    return ' '.join(tokens).replace(' ##', '').replace('\u0120', ' ').strip()
+
+
+def spm_detokenize(tokens):
+    """tokenizer.py:236-239"""
+    return ''.join(tokens).replace('\u2581', ' ').strip()
 
 
 # --------------------------------------------------------------------------------------------------
@@ -841,6 +853,61 @@ def unigram_encode(model, text):
         else:
             ids.append(pid)
     return ids
+
+
+def _utf8_or_replacement(b):
+    """a run of byte pieces: every well-formed UTF-8 sequence decodes, every other byte becomes U+FFFD"""
+    out = []
+    i = 0
+    while i < len(b):
+        for n in (1, 2, 3, 4):
+            try:
+                ch = bytes(b[i:i + n]).decode('utf-8')
+            except UnicodeDecodeError:
+                continue
+            if len(ch) == 1:
+                out.append(ch)
+                i += n
+                break
+        else:
+            out.append('\ufffd')
+            i += 1
+    return ''.join(out)
+
+
+def unigram_decode(model, ids):
+    """tokenizer.py:217-218 -> SentencePieceProcessor.DecodeIds (sentencepiece 0.2.1, sentencepiece_processor.cc Decode;
+    behaviour pinned by tests/golden decode_fuzz): control pieces vanish, <unk> decodes to its surface ' \u2047 ', a run of
+    byte pieces is decoded as UTF-8, U+2581 becomes a space, and while the text decoded so far is empty one leading U+2581 of
+    a piece is consumed (add_dummy_prefix)"""
+    out = []
+    pend = []
+    empty = True
+    for i in ids:
+        if i < 0 or i >= len(model.pieces):
+            raise IndexError('piece id is out of range.')
+        piece, _, typ = model.pieces[i]
+        if typ == model.BYTE:
+            pend.append(int(piece[3:5], 16))
+            continue
+        if pend:
+            out.append(_utf8_or_replacement(pend))
+            pend = []
+            empty = False
+        if typ == model.CONTROL:
+            continue
+        if typ == model.UNKNOWN:
+            out.append(' \u2047 ')
+            empty = False
+            continue
+        if empty and piece.startswith('\u2581'):
+            piece = piece[1:]
+        if piece:
+            empty = False
+        out.append(piece.replace('\u2581', ' '))
+    if pend:
+        out.append(_utf8_or_replacement(pend))
+    return ''.join(out)
 
 
 def unigram_pieces(model, text):

@@ -28,6 +28,13 @@ def golden():
 
 
 @pytest.fixture(scope='session')
+def decode_fuzz():
+    """id rows decoded / detokenized by the unmodified reference (tools/make_golden_decode.py)"""
+    with gzip.open(os.path.join(GOLDEN, 'decode_fuzz.json.gz'), 'rb') as f:
+        return json.loads(f.read().decode('utf-8'))
+
+
+@pytest.fixture(scope='session')
 def models_dir():
     return MODELS
 

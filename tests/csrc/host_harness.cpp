@@ -15,6 +15,7 @@
 #include "../../akshar_b200/csrc/ak_tok.cuh"
 #include "../../akshar_b200/csrc/ak_wordtok.cuh"
 #include "../../akshar_b200/csrc/ak_tok_host.h"
+#include "../../akshar_b200/csrc/ak_decode_host.h"
 #include "../../akshar_b200/csrc/ak_models.h"
 #include "../../akshar_b200/csrc/unicode_tables.inc"
 
@@ -375,6 +376,27 @@ int hh_load_spm(const uint8_t* proto, int64_t len) {
     g_err = ak_parse_spm_model(proto, (size_t)len, g_uni);
     return g_err.empty() ? 0 : -1;
 }
+// ids -> text (ak_decode.cuh) with the kernels' steps: marks row by row, lengths, prefix, bytes, row offsets
+int64_t hh_decode(int kind, int form, const int32_t* ids, int64_t n_ids, const int64_t* splits, int64_t n_rows, uint8_t* out, int64_t cap,
+                  int64_t* out_off, uint32_t* status) {
+    const AkDecHost H = kind == 0 ? ak_build_bpe_decode(g_bpe, form) : ak_build_spm_decode(g_uni, form);
+    const AkDecTable D = H.view();
+    std::vector<uint8_t> mark((size_t)n_ids + 1, 0);
+    uint32_t st = 0;
+    for (int64_t r = 0; r < n_rows; ++r) akd_mark_row(D, form, ids, splits[r], splits[r + 1], mark.data(), st);
+    std::vector<int64_t> at((size_t)n_ids + 1, 0);
+    for (int64_t i = 0; i < n_ids; ++i) at[(size_t)i + 1] = at[(size_t)i] + akd_emit(D, ids, mark.data(), n_ids, i, (uint8_t*)nullptr, st);
+    for (int64_t i = 0; i < n_ids; ++i) {
+        const int64_t len = at[(size_t)i + 1] - at[(size_t)i];
+        if (!len) continue;
+        if (at[(size_t)i] + len <= cap) akd_emit(D, ids, mark.data(), n_ids, i, out + at[(size_t)i], st);
+        else st |= AK_ST_OVERFLOW;
+    }
+    for (int64_t r = 0; r <= n_rows; ++r) out_off[r] = at[(size_t)splits[r]];
+    *status = st;
+    return at[(size_t)n_ids];
+}
+
 int hh_bpe_vocab_size() { return g_bpe.vocab_size; }
 int hh_spm_vocab_size() { return (int)g_uni.piece.size(); }
 

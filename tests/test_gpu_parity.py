@@ -150,6 +150,60 @@ def test_pieces_and_decode_golden(A, golden, bpe_rows, models_dir):
         assert tu.decode(r['ids_spm24k']) == r['dec_spm24k']
 
 
+@pytest.mark.parametrize('name,kind', [('spm24k', 'sentencepiece'), ('spm_corpus', 'sentencepiece'), ('bpe24k', 'bpe'), ('bpe_corpus', 'bpe')])
+def test_decode_on_device(A, golden, decode_fuzz, bpe_rows, models_dir, name, kind):
+    """tokenizer.py:195-246 on the device: what the unmodified reference decoded / detokenized, on the ids the encoders
+    produce and on fuzzed id rows (byte pieces out of order, control / unknown / special / unused ids)"""
+    tk = A.aksharTokenizer(os.path.join(models_dir, name + ('.json' if kind == 'bpe' else '.model')), kind)
+    F = decode_fuzz[name]
+    assert tk.decode_batch(F['ids']) == F['decode']
+    assert tk.detokenize_batch(F['ids_detok'] if kind == 'bpe' else F['ids']) == F['detokenize']
+    for ids, dec in list(zip(F['ids'], F['decode']))[:40]:
+        assert tk.decode(ids) == dec
+    if name in ('spm24k', 'bpe24k'):
+        rows = bpe_rows if kind == 'bpe' else golden['rows']
+        assert tk.decode_batch([r['ids_' + name] for r in rows]) == [r['dec_' + name] for r in rows]
+        assert tk.detokenize_batch([r['ids_' + name] for r in rows]) == [r['detok_' + name] for r in rows]
+        for r in rows[:60]:
+            assert tk.detokenize(r['pieces_' + name]) == r['detok_' + name]
+        S = decode_fuzz['detokenize_strings']
+        assert [tk.detokenize(t) for t in S['tokens']] == S[kind]
+        # straight from the encoder's device output, int32 and compact uint16 ids
+        ins = [r['in'] for r in rows[:3000]]
+        ids, _ = tk.encode_batch(ins, as_device=True)
+        assert tk.decode_batch(ids) == [r['dec_' + name] for r in rows[:3000]]
+        import torch
+        assert tk.decode_batch((ids.values.to(torch.uint16), ids.splits)) == [r['dec_' + name] for r in rows[:3000]]
+    if kind == 'sentencepiece':
+        with pytest.raises(IndexError):
+            tk.decode([5, tk.vocab_size()])
+    assert tk.decode_batch([]) == [] and tk.decode([]) == '' and tk.decode_batch([[], []]) == ['', '']
+    assert A.aksharTokenizer().detokenize(['a', 'b']) == 'ab'
+    with pytest.raises(ValueError):
+        A.aksharTokenizer().decode([1])
+
+
+def test_decode_round_trip_1gib(A, models_dir):
+    """encode -> decode at 1 GiB: for text that normalize_text has produced (single spaces, nothing to strip) the Unigram
+    model's DecodeIds(EncodeAsIds(x)) is x, byte for byte -- compared on the device"""
+    import torch
+    tk = A.aksharTokenizer(os.path.join(models_dir, 'spm24k.model'), 'sentencepiece')
+    eng = tk._eng
+    data, off = sc.Corpus('hindi', 41).generate(1 << 30)
+    raw = A.TextBatch(torch.from_numpy(data).cuda(), torch.from_numpy(off).cuda(), 0, int(off[-1]))
+    norm = eng.normalize_batch(raw)
+    del raw
+    ids = eng.encode_unigram_batch(norm)
+    eng.timing(True)
+    back = eng.decode_batch(ids, None, 1)
+    ms = eng.kernel_ms('ak_dec_kernel')
+    eng.timing(False)
+    assert back.end == norm.end
+    assert torch.equal(back.offsets, norm.offsets)
+    assert torch.equal(back.data[:back.end], norm.data[:norm.end])
+    print('decode 1 GiB: %d ids, write kernel %.2f ms' % (ids.values.numel(), ms))
+
+
 # ------------------------------------------------------------------ the reference's own test expectations, via the drop-in API
 def test_reference_unit_expectations(A):
     # reference tests/test_normalize.py

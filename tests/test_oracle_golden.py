@@ -127,3 +127,32 @@ def test_raw_mode_ids(golden_raw, models_dir):
         if all(T.bpe_safe[ord(c)] for c in raw):
             assert O.bpe_encode(bm, raw) == r['ids_bpe24k_raw'], r['in']
     assert n_bpe > 1500
+
+
+def test_decode_and_detokenize(golden, decode_fuzz, models_dir):
+    """tokenizer.py:195-246: decode on the rows the encoders produce (golden) and on fuzzed id rows (decode_fuzz)"""
+    bm = O.BpeModel(os.path.join(models_dir, 'bpe24k.json'))
+    um = O.UnigramModel(os.path.join(models_dir, 'spm24k.model'))
+    for r in golden['rows']:
+        assert O.bpe_decode(bm, r['ids_bpe24k']) == r['dec_bpe24k']
+        assert O.unigram_decode(um, r['ids_spm24k']) == r['dec_spm24k']
+        assert O.bpe_detokenize(r['pieces_bpe24k']) == r['detok_bpe24k']
+        assert O.spm_detokenize(r['pieces_spm24k']) == r['detok_spm24k']
+    for name in ('spm24k', 'spm_corpus'):
+        m = O.UnigramModel(os.path.join(models_dir, name + '.model'))
+        F = decode_fuzz[name]
+        for ids, dec, det in zip(F['ids'], F['decode'], F['detokenize']):
+            assert O.unigram_decode(m, ids) == dec
+            assert O.spm_detokenize([m.pieces[i][0] for i in ids]) == det
+        with pytest.raises(IndexError):
+            O.unigram_decode(m, [len(m.pieces)])
+    for name in ('bpe24k', 'bpe_corpus'):
+        m = O.BpeModel(os.path.join(models_dir, name + '.json'))
+        F = decode_fuzz[name]
+        for ids, dec in zip(F['ids'], F['decode']):
+            assert O.bpe_decode(m, ids) == dec
+        for ids, det in zip(F['ids_detok'], F['detokenize']):
+            assert O.bpe_detokenize([m.id_to_token[i] for i in ids]) == det
+    S = decode_fuzz['detokenize_strings']
+    assert [O.bpe_detokenize(t) for t in S['tokens']] == S['bpe']
+    assert [O.spm_detokenize(t) for t in S['tokens']] == S['sentencepiece']

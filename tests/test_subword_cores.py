@@ -259,3 +259,26 @@ def test_raw_mode_cores(golden_raw, models_dir):
     # anything else must be refused loudly (status bit 8 = AKSHAR_ST_ALPHABET)
     data, off = sc.pack(['ok', 'x\ufb01y', '<s>'])
     assert W.tok(0, data, off)[2] & 8 and W.bpe(data, off)[2] & 8
+
+
+# ---- ids -> text (ak_decode.cuh; reference tokenizer.py:195-246) ------------------------------------------------------
+@pytest.mark.parametrize('name,kind', [('spm24k', 1), ('spm_corpus', 1), ('bpe24k', 0), ('bpe_corpus', 0)])
+def test_decode_cores_against_the_reference(decode_fuzz, golden, models_dir, name, kind):
+    """the piece tables, the row marks and the byte-run rule on the CPU, against what the unmodified reference decoded"""
+    (W.load_spm if kind == 1 else W.load_bpe)(os.path.join(models_dir, name + ('.model' if kind == 1 else '.json')))
+    F = decode_fuzz[name]
+    got, st = W.decode(kind, 0, F['ids'])
+    assert st == 0
+    assert [g.decode('utf-8') for g in got] == F['decode']
+    got, st = W.decode(kind, 1, F['ids_detok'] if kind == 0 else F['ids'])
+    assert st == 0
+    assert [g.decode('utf-8') for g in got] == F['detokenize']
+    if name in ('spm24k', 'bpe24k'):
+        rows = golden['rows'][:1500]
+        got, st = W.decode(kind, 0, [r['ids_' + name] for r in rows])
+        assert st == 0 and [g.decode('utf-8') for g in got] == [r['dec_' + name] for r in rows]
+        got, st = W.decode(kind, 1, [r['ids_' + name] for r in rows])
+        assert st == 0 and [g.decode('utf-8') for g in got] == [r['detok_' + name] for r in rows]
+    if kind == 1:
+        _, st = W.decode(kind, 0, [[5, 10 ** 6]])
+        assert st == 128                                               # AKSHAR_ST_BAD_ID: DecodeIds raises IndexError

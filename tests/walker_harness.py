@@ -199,6 +199,23 @@ def wordtok(data, off, mode=0, real=30):
     return wb[:n], we[:n], sp, fl[:off.size - 1], st.value
 
 
+def decode(kind, form, rows):
+    """ids -> text (ak_decode.cuh) on the CPU; rows = list of id lists -> (list[bytes], status)"""
+    n = sum(len(r) for r in rows)
+    ids = np.array([i for r in rows for i in r], dtype=np.int32) if n else np.zeros(1, dtype=np.int32)
+    sp = np.zeros(len(rows) + 1, dtype=np.int64)
+    np.cumsum([len(r) for r in rows], out=sp[1:])
+    cap = 64 * n + 16
+    out = np.zeros(cap, dtype=np.uint8)
+    off = np.zeros(len(rows) + 1, dtype=np.int64)
+    st = ctypes.c_uint32(0)
+    lib().hh_decode.restype = ctypes.c_int64
+    tot = lib().hh_decode(ctypes.c_int(kind), ctypes.c_int(form), _p(ids), ctypes.c_int64(n), _p(sp), ctypes.c_int64(len(rows)), _p(out),
+                          ctypes.c_int64(cap), _p(off), ctypes.byref(st))
+    b = out[:tot].tobytes()
+    return [b[off[i]:off[i + 1]] for i in range(len(rows))], st.value
+
+
 def tok(kind, data, off, real=30, cache_bits=14, prewarm=1, u16=False, splits_i32=False, cap=None):
     """the event-stream encoders (ak_tok.cuh) on the CPU: lanes -> event slots -> row fix -> resolve -> check -> emit.
     kind 0 BPE, 1 Unigram; cap = event slots per emulated warp tile -> (ids, splits, status, stats dict)"""
