@@ -19,7 +19,7 @@ struct AkB3Lane {
     uint32_t CW, CS;                 // class word / space at leads (other = lead & ~CW & ~CS)
     uint32_t NK, VIAC, AC, QN, INERT, FOR, LT;
     uint32_t bnd, wstart, trb;
-    uint32_t flags;                  // bit 0: outside the alphabet the encoder accepts
+    uint32_t UNS;                    // code points HF's NFKC treats differently from NFC: their rows take the exact row path
     uint32_t dn1, up2;
 };
 
@@ -73,7 +73,7 @@ AK_HD void akb3_phase2(AkB3Lane& L, uint32_t dn1n) {
     L.AC = r3;
     L.QN = d5 & akb_fsr(L.QNb, dn1n >> 12, 2);
     L.INERT = dev & ~(L.NK | L.VIAC | L.QN) & ~(d4 & akb_fsr(L.NIb, dn1n >> 6, 2));
-    L.flags = L.LT ? 1u : 0u;
+    L.UNS = 0u;
 }
 
 // code points outside the closed alphabet, one by one
@@ -88,7 +88,7 @@ AK_HD void akb3_foreign(const AkTables& Tb, const uint8_t* text, int64_t cs, int
         const uint32_t k = AK_HFCLASS(w);
         if (k == 1u) L.CW |= 1u << i;
         else if (k == 2u) L.CS |= 1u << i;
-        if (!AK_BPE_SAFE(w)) L.flags |= 1u;
+        if (!AK_BPE_SAFE(w)) L.UNS |= 1u << i;
         if (!AK_INERT_BASE(w)) xt |= 1u << i;          // anything NFC might care about: checked exactly (cold)
     }
     L.QN |= xt;

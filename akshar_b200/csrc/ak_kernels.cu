@@ -70,7 +70,7 @@ struct akshar_ctx {
     bool wc_hold = false;          // akshar_word_cache_hold(1): never restore the image, however full the cache
     cudaEvent_t tev[AKSHAR_TIMER_COUNT][2] = {};
     bool tev_valid[AKSHAR_TIMER_COUNT] = {};
-    int occ_norm = 0, occ_seg = 0, occ_bpe = 0, occ_uni = 0, occ_sig = 0, occ_nf_write = 0, occ_nf3 = 0, occ_sf3 = 0;
+    int occ_norm = 0, occ_seg = 0, occ_uni = 0, occ_sig = 0, occ_nf_write = 0, occ_nf3 = 0, occ_sf3 = 0;
 };
 
 // the entry points run on the context's device and leave the caller's current device as they found it
@@ -151,17 +151,22 @@ int akshar_ctx_create(int device, akshar_ctx** out) {
     UP(ll_vals, ak_tbl_latin_lower_vals, AK_N_LATIN_LOWER, uint32_t)
     UP(fl_keys, ak_tbl_full_lower_keys, AK_N_FULL_LOWER, uint32_t)
     UP(fl_vals, ak_tbl_full_lower_vals, AK_N_FULL_LOWER, uint32_t)
+    UP(kmap_keys, ak_tbl_kmap_keys, AK_N_KMAP, uint32_t)
+    UP(kmap_off, ak_tbl_kmap_off, AK_N_KMAP + 1, uint16_t)
+    UP(kmap_data, ak_tbl_kmap_data, AK_N_KMAP_DATA, uint32_t)
+    UP(hf_unknown, ak_tbl_hf_unknown, AK_N_HF_UNKNOWN, uint32_t)
 #undef UP
     ctx->T.n_decomp = AK_N_DECOMP;
     ctx->T.n_pairs = AK_N_PAIRS;
     ctx->T.n_ll = AK_N_LATIN_LOWER;
     ctx->T.n_fl = AK_N_FULL_LOWER;
+    ctx->T.n_kmap = AK_N_KMAP;
+    ctx->T.n_hf_unknown = AK_N_HF_UNKNOWN;
     AK_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_norm, ak_normalize_kernel, AK_BLOCK, 0));
     AK_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_nf_write, ak_nf_write_kernel, AK_BLOCK, 0));
     AK_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_nf3, ak_nf3_classify_kernel, AKN3_THREADS, 0));
     AK_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_sf3, ak_sf3_kernel, AKS3_THREADS, 0));
     AK_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_seg, ak_segment_kernel, AK_BLOCK, 0));
-    AK_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_bpe, ak_bpe_kernel, AK_BLOCK, 0));
     AK_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_uni, ak_unigram_kernel, AK_ROWS_BLOCK, 0));
     AK_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_sig, ak_signature_kernel, AK_ROWS_BLOCK, 0));
     AK_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_words[0], ak_words_kernel<0>, AKW_THREADS, 0));
@@ -843,6 +848,10 @@ static int ak_load_bpe_json(akshar_ctx* ctx, const char* json, size_t len) {
     if ((rc = ak_upload<int32_t>(ctx, ctx->bpe_allocs, h.cp_ids.data(), h.cp_ids.size(), &d.cp_ids))) return rc;
     if ((rc = ak_upload<unsigned long long>(ctx, ctx->bpe_allocs, h.mkeys.data(), h.mkeys.size(), &d.mkeys))) return rc;
     if ((rc = ak_upload<unsigned long long>(ctx, ctx->bpe_allocs, h.mvals.data(), h.mvals.size(), &d.mvals))) return rc;
+    if ((rc = ak_upload<uint8_t>(ctx, ctx->bpe_allocs, h.sp_bytes.data(), h.sp_bytes.size(), &d.sp_bytes))) return rc;
+    if ((rc = ak_upload<uint16_t>(ctx, ctx->bpe_allocs, h.sp_off.data(), h.sp_off.size(), &d.sp_off))) return rc;
+    if ((rc = ak_upload<int32_t>(ctx, ctx->bpe_allocs, h.sp_ids.data(), h.sp_ids.size(), &d.sp_ids))) return rc;
+    d.n_sp = (int)h.sp_ids.size();
     d.n_cp = (int)h.cp_keys.size();
     d.mbits = h.mbits;
     d.bos = h.bos;
@@ -993,6 +1002,7 @@ static int ak_run_tok(akshar_ctx* ctx, AkCall& C, const AkBatch& B, int64_t max_
     AkWordsArgs A;
     A.B = B;
     A.T = ctx->T;
+    A.bpe = ctx->bpe_d;
     A.base0 = base0;
     A.wrow = (const int64_t*)(base + W.wrow);
     A.S = S;
@@ -1117,76 +1127,10 @@ static int ak_run_tok(akshar_ctx* ctx, AkCall& C, const AkBatch& B, int64_t max_
 
 // BPE over batch B (B may carry dyn_end from an earlier stage of a pipeline): the event-stream encoder in tile mode, the
 // exact span walker (+ its conditional NFC passes) in row mode
+// The BPE encoder has no bounded look-back and no row-sequential twin: both modes run the event-stream path, whose exact
+// row kernel takes whatever the fast lanes hand over (added tokens, NFKC, rows that are not in NFC).
 static int ak_run_bpe(akshar_ctx* ctx, AkCall& C, const AkBatch& B, int64_t max_bytes, const AkTokOut& O) {
-    int rc;
-    if (B.mode == AKSHAR_MODE_TILES) return ak_run_tok(ctx, C, B, max_bytes, 0, O);
-    if (O.ids_u16 || O.splits_i32) {
-        ctx->err = "compact outputs need AKSHAR_MODE_TILES";
-        return AKSHAR_E_ARG;
-    }
-    int32_t* d_ids = (int32_t*)O.ids;
-    int64_t* d_id_splits = (int64_t*)O.splits;
-    const int64_t id_capacity = O.id_cap;
-    const size_t tiles = (size_t)ak_tiles_of(max_bytes, B.n_rows);
-    int* tickets = (int*)C.ws;
-    unsigned int* changed = (unsigned int*)(C.ws + 64);
-    AkPool pool;
-    pool.base = (int32_t*)(C.ws + C.L.pool);
-    pool.used = (unsigned long long*)(C.ws + 128);
-    pool.cap = ak_pool_ints(max_bytes);
-    // A workspace larger than the minimum gives half of the surplus to the long-word pool: a batch full of words beyond
-    // AK_BPE_LOCAL symbols raises AKSHAR_ST_WORD with the minimum, the caller grows the workspace and calls again.
-    if (C.ws_bytes > C.L.total + (1u << 20)) {
-        const size_t pool_tail = ((C.ws_bytes - C.L.total) / 2) & ~(size_t)255;
-        if (pool_tail / 4 > pool.cap) {
-            pool.base = (int32_t*)(C.ws + ((C.ws_bytes - pool_tail) & ~(size_t)255));
-            pool.cap = pool_tail / 4 - 64;
-        }
-    }
-    // pass 1: encode the text as it is; raises `changed` when some NFC segment is not already normalized
-    AkBpeArgs A;
-    A.B = B;
-    A.B.ticket = tickets + 1;
-    A.B.state0 = C.B.state0 + 1 * tiles;
-    A.T = ctx->T;
-    A.M = ctx->bpe_d;
-    A.pool = pool;
-    A.ids = d_ids;
-    A.id_cap = id_capacity;
-    A.id_splits = d_id_splits;
-    A.changed = changed;
-    const int bpe_tiles = B.dyn_end ? (int)tiles : B.n_tiles;
-    ak_bpe_kernel<<<ak_grid(ctx, ctx->occ_bpe, bpe_tiles), AK_BLOCK, 0, C.stream>>>(A);
-    if ((rc = ak_after_launch(ctx, "bpe"))) return rc;
-    // passes 2 + 3 (device-side conditional: both exit at once while `changed` is clear): NFC into the workspace,
-    // then encode that copy over the same outputs.  HF's NFKC == NFC on the closed alphabet (the exotic spaces it
-    // folds to U+0020 are all \\s and never reach a word).
-    int64_t* nfc_total = (int64_t*)(C.ws + 192);
-    AkNormArgs N;
-    N.B = B;
-    N.B.ticket = tickets + 2;
-    N.B.state0 = C.B.state0 + 2 * tiles;
-    N.B.totals = nfc_total;
-    N.B.run_if = changed;
-    N.T = ctx->T;
-    N.flags = 0;
-    N.out = (uint8_t*)(C.ws + C.L.nfc_text);
-    N.out_cap = C.L.nfc_cap;
-    N.out_off = (int64_t*)(C.ws + C.L.nfc_off);
-    ak_normalize_kernel<<<ak_grid(ctx, ctx->occ_norm, bpe_tiles), AK_BLOCK, 0, C.stream>>>(N);
-    if ((rc = ak_after_launch(ctx, "bpe-nfc"))) return rc;
-    AkBpeArgs A2 = A;
-    A2.B.text = N.out;
-    A2.B.off = N.out_off;
-    A2.B.text_begin = 0;
-    A2.B.text_end = 0;
-    A2.B.dyn_end = nfc_total;
-    A2.B.run_if = changed;
-    A2.B.ticket = tickets + 3;
-    A2.B.state0 = C.B.state0 + 3 * tiles;
-    A2.changed = (unsigned int*)(C.ws + 68);      // scratch flag: the copy is in NFC by construction
-    ak_bpe_kernel<<<ak_grid(ctx, ctx->occ_bpe, (int)tiles), AK_BLOCK, 0, C.stream>>>(A2);
-    return ak_after_launch(ctx, "bpe-renormalized");
+    return ak_run_tok(ctx, C, B, max_bytes, 0, O);
 }
 
 static int ak_run_unigram(akshar_ctx* ctx, AkCall& C, const AkBatch& B, int64_t max_bytes, const AkTokOut& O, int mode) {

@@ -1,6 +1,7 @@
 // see ak_models.h
 #include "ak_models.h"
 
+#include <algorithm>
 #include <math.h>
 #include <string.h>
 
@@ -243,9 +244,28 @@ std::string ak_parse_bpe_json(const char* json, size_t len, AkBpeHost& out) {
                 const JVal* i = a.get("id");
                 int32_t id;
                 if (!c || !i || c->kind != JVal::Str || !id_of(*i, id)) return "tokenizer JSON: bad added_tokens entry";
+                // the matcher implemented on the device is the plain one: no word-boundary / strip options, raw text
+                for (const char* opt : {"single_word", "lstrip", "rstrip", "normalized"}) {
+                    const JVal* o = a.get(opt);
+                    if (o && o->kind == JVal::Bool && o->b) return std::string("tokenizer JSON: added token option '") + opt + "' is not supported";
+                }
+                if (c->str.empty() || c->str.size() > 255) return "tokenizer JSON: bad added_tokens content";
                 specials.emplace_back(c->str, id);
                 if (id > max_id) max_id = id;
             }
+    }
+    {
+        std::vector<std::pair<std::string, int32_t>> by_len = specials;
+        std::stable_sort(by_len.begin(), by_len.end(), [](const std::pair<std::string, int32_t>& x, const std::pair<std::string, int32_t>& y) {
+            return x.first.size() > y.first.size();
+        });
+        out.sp_off.push_back(0);
+        for (auto& sp : by_len) {
+            out.sp_bytes.insert(out.sp_bytes.end(), sp.first.begin(), sp.first.end());
+            out.sp_off.push_back((uint16_t)out.sp_bytes.size());
+            out.sp_ids.push_back(sp.second);
+        }
+        if (out.sp_bytes.size() > 60000 || out.sp_ids.size() > 255) return "tokenizer JSON: too many added tokens";
     }
     out.id_to_token.assign((size_t)max_id + 1, "");
     out.is_special.assign((size_t)max_id + 1, 0);

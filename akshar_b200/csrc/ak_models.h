@@ -17,6 +17,10 @@ struct AkBpeHost {
     std::vector<unsigned long long> mkeys, mvals;  // open-addressing table, size 1 << mbits
     uint32_t mbits = 0;
     int32_t bos = -1, eos = -1;
+    // added tokens (all `special`, matched in the raw text before the normalizer), longest first
+    std::vector<uint8_t> sp_bytes;
+    std::vector<uint16_t> sp_off;                  // [n + 1]
+    std::vector<int32_t> sp_ids;
     int64_t n_merges = 0;
     int vocab_size = 0;
 };

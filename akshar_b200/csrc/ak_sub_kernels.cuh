@@ -1,88 +1,6 @@
-// Row / span walker kernels of the subword encoders and of roman_phonetic_signature (exact for any input; the fast
-// path of the encoders is ak_tok_kernels.cuh).
+// Row walker kernels: the Unigram encoder for models the word-wise path cannot take (ak_tok_host.h ak_uni_wordwise) or
+// AKSHAR_MODE_ROWS, and roman_phonetic_signature.  The encoders' fast path is ak_tok_kernels.cuh.
 #pragma once
-// ------------------------------------------------------------------------------------------------
-// K4a BPE encode  (reference tokenizer.py:193)
-// ------------------------------------------------------------------------------------------------
-struct AkBpeArgs {
-    AkBatch B;
-    AkTables T;
-    AkBpeDev M;
-    AkPool pool;
-    int32_t* ids;
-    int64_t id_cap;
-    int64_t* id_splits;
-    unsigned int* changed;          // set when NFC would change the text (results are then recomputed)
-};
-
-__global__ void __launch_bounds__(AK_BLOCK) ak_bpe_kernel(const AkBpeArgs A) {
-    __shared__ int ws[33];
-    __shared__ int s_tile;
-    __shared__ int64_t s_win[2];
-    __shared__ long long s_base;
-    __shared__ int32_t stage[AK_BPE_STAGE * AK_BLOCK];
-    AkBatch B = A.B;
-    if (!ak_batch_begin(B)) return;
-    for (;;) {
-        const int tile = ak_next_tile(B.ticket, &s_tile);
-        if (tile >= B.n_tiles) break;
-        const AkSpan sp = ak_span_of(B, tile, s_win);
-        uint32_t st = 0;
-        bool changed = false;
-        AkIdSink sink;
-        sink.buf = stage + threadIdx.x;
-        sink.cap = AK_BPE_STAGE;
-        sink.stride = AK_BLOCK;
-        sink.cnt = 0;
-        sink.direct = false;
-        sink.gout = A.ids;
-        sink.gbase = 0;
-        sink.gcap = A.id_cap;
-        int64_t row_first = 0, row_last = 0;
-        if (sp.s < sp.e)
-            ak_bpe_span(A.M, A.T, B.text, B.off, B.n_rows, sp.r_lo, sp.r_hi, sp.s, sp.e, sp.limit, sink, A.id_splits, 0,
-                        row_first, row_last, A.pool, changed, st);
-        const int cnt = sink.cnt;
-        int total;
-        const int pre = ak_block_exscan<AK_BLOCK>(cnt, ws, total);
-        if (threadIdx.x < 32) {
-            long long b = ak_tile_prefix(B.state0, tile, total, (unsigned int*)&B.result[2], AK_ST_SPIN);
-            if (threadIdx.x == 0) {
-                s_base = b;
-                if (tile == B.n_tiles - 1) B.totals[0] = b + total;
-            }
-        }
-        __syncthreads();
-        const int64_t obase = s_base + pre;
-        if (sp.s < sp.e) {
-            if (obase + cnt > A.id_cap) st |= AK_ST_OVERFLOW;
-            for (int64_t r = row_first; r < row_last; ++r) A.id_splits[r] += obase;     // span-relative -> global
-            if (cnt <= AK_BPE_STAGE) {
-                for (int i = 0; i < cnt; ++i)
-                    if (obase + i < A.id_cap) A.ids[obase + i] = stage[i * AK_BLOCK + threadIdx.x];
-            } else {
-                // did not fit the stage (many empty rows or very dense words): walk again straight to global memory
-                AkIdSink s2 = sink;
-                s2.cnt = 0;
-                s2.direct = true;
-                s2.gbase = obase;
-                uint32_t st2 = 0;
-                bool ch2 = false;
-                int64_t a, b;
-                ak_bpe_span(A.M, A.T, B.text, B.off, B.n_rows, sp.r_lo, sp.r_hi, sp.s, sp.e, sp.limit, s2, nullptr, 0, a, b,
-                            A.pool, ch2, st2);
-            }
-        }
-        if (changed) atomicOr(A.changed, 1u);
-        ak_raise(B.result, st);
-    }
-}
-
-
-// ------------------------------------------------------------------------------------------------
-// K4b Unigram encode  (reference tokenizer.py:191): one row per thread, Viterbi ring in registers / local memory,
-// final back-pointers in a global scratch (4 B per code point), ids written backwards from the row's end.
-// ------------------------------------------------------------------------------------------------
 struct AkUniArgs {
     AkBatch B;
     AkUniDev U;

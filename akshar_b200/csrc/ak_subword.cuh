@@ -27,7 +27,24 @@ struct AkBpeDev {
     const unsigned long long* mvals;      // (rank << 32) | merged_id
     uint32_t mbits;                       // table has 1 << mbits slots
     int32_t bos, eos;                     // -1: the post-processor adds none
+    const uint8_t* sp_bytes;              // added (special) tokens, longest first: bytes, offsets [n_sp + 1], ids
+    const uint16_t* sp_off;
+    const int32_t* sp_ids;
+    int n_sp;
 };
+
+// HF AddedVocabulary (scripts/train_bpe.py:80): index of the added token that starts at byte p of the raw text (the longest
+// one: they are stored longest first), or -1.  Never reads at or beyond `end`.
+AK_HD int ak_bpe_special_at(const AkBpeDev& M, const uint8_t* t, int64_t p, int64_t end) {
+    for (int k = 0; k < M.n_sp; ++k) {
+        const int lo = M.sp_off[k], n = M.sp_off[k + 1] - lo;
+        if (p + n > end) continue;
+        int i = 0;
+        while (i < n && t[p + i] == M.sp_bytes[lo + i]) ++i;
+        if (i == n) return k;
+    }
+    return -1;
+}
 
 AK_HD uint32_t ak_hash64(unsigned long long k, uint32_t bits) {
     return (uint32_t)((k * 0x9E3779B97F4A7C15ull) >> (64 - bits));
@@ -186,7 +203,8 @@ AK_HD_NOINLINE bool ak_segment_changes(const AkTables& T, const uint8_t* t, int6
 AK_HD_NOINLINE void ak_bpe_span(const AkBpeDev& M, const AkTables& T, const uint8_t* t, const int64_t* off,
                                 int64_t n_rows, int64_t r_lo, int64_t r_hi, int64_t s, int64_t e, int64_t limit,
                                 AkIdSink& sink, int64_t* id_splits, int64_t split_base, int64_t& row_first,
-                                int64_t& row_last, const AkPool& pool, bool& changed, uint32_t& status) {
+                                int64_t& row_last, const AkPool& pool, bool& changed, uint32_t& status,
+                                bool prenormalized = false) {
     const int64_t total_end = off[n_rows];
     row_first = row_last = 0;
     int64_t p = s;
@@ -225,9 +243,10 @@ AK_HD_NOINLINE void ak_bpe_span(const AkBpeDev& M, const AkTables& T, const uint
         int len;
         uint32_t cp = ak_decode(t, p, re, len);
         uint32_t w = ak_props(T, cp);
-        if (!AK_BPE_SAFE(w)) status |= AK_ST_ALPHABET;
+        // text the caller has put through HF's NFKC itself (the row-fix path) is taken as it is
+        if (!prenormalized && !AK_BPE_SAFE(w)) status |= AK_ST_ALPHABET;
         uint32_t cc = AK_CCC(w);
-        if ((AK_QC(w) != 0 || (cc != 0 && prev_ccc > cc)) && p >= checked_until) {
+        if (!prenormalized && (AK_QC(w) != 0 || (cc != 0 && prev_ccc > cc)) && p >= checked_until) {
             if (ak_segment_changes(T, t, p, rs, re, limit, &checked_until, status)) changed = true;
         }
         prev_ccc = cc;

@@ -18,6 +18,7 @@
 //
 // Reference: tokenizer.py:191-193 (`EncodeAsIds(norm)` / `Tokenizer.encode(norm).ids`).
 #pragma once
+#include "ak_nfkc.cuh"
 #include "ak_bpe3.cuh"
 #include "ak_subword.cuh"
 #include "ak_wordcache.cuh"
@@ -599,34 +600,71 @@ AK_HD_NOINLINE void akr_fix_row(const AkRowFixCtx& X, int64_t g) {
         ak_unigram_backtrack(X.M.uni, back, n, X.pool + at2, cnt, cnt);
         X.row_fix[g] = (at2 << 24) | (unsigned long long)cnt;
     } else {
-        // BPE: NFC the row into the pool (HF's NFKC == NFC on what reaches this point), then the exact walker over the
-        // normalized copy as a batch of one row; its <s> / </s> are the row event's business and are left out
+        // BPE, the way HF runs it (scripts/train_bpe.py:68-98): the added tokens are cut out of the RAW row, every other
+        // piece goes through NFKC, the Whitespace pre-tokenizer and the merges.  The normalized pieces are laid out in the
+        // pool one after the other, each added token as the marker 0xFF + its index (no UTF-8 text holds 0xFF); the exact
+        // walker then runs over each piece as a batch of one row.  <s> / </s> are the row event's business.
         uint32_t st = 0;
-        const int64_t nb = ak_norm_span(X.M.T, X.text, X.off, X.n_rows, g, g + 1, rs, re, 0u, 0, nullptr, nullptr, 0, st);
-        const unsigned long long nints = (unsigned long long)(nb + 3) / 4ull + 2ull;
-        const unsigned long long at = ak_atomic_add64(X.pool_used, nints);
-        if (at + nints > X.pool_cap) { ak_status_or(X.result, AK_ST_WORD); return; }
-        uint8_t* nt = (uint8_t*)(X.pool + at);
-        ak_norm_span(X.M.T, X.text, X.off, X.n_rows, g, g + 1, rs, re, 0u, 0, nt, nullptr, 0, st, nb);
-        int64_t loff[2] = {0, nb};
+        const AkBpeDev& M = X.M.bpe;
+        AkByteSink bs;
+        bs.out = nullptr; bs.cnt = 0; bs.cap = 0;
+        unsigned long long at = 0;
+        for (int pass = 0; pass < 2; ++pass) {
+            int64_t from = rs;
+            for (int64_t q = rs; q <= re; ++q) {
+                const int kk = q < re ? ak_bpe_special_at(M, X.text, q, re) : -1;
+                if (q < re && kk < 0) continue;
+                if (q > from) akk_nfkc(X.M.T, X.text, from, q, bs, st);
+                if (q == re) break;
+                if (bs.out && bs.cnt + 2 <= bs.cap) { bs.out[bs.cnt] = 0xFFu; bs.out[bs.cnt + 1] = (uint8_t)kk; }
+                bs.cnt += 2;
+                q += M.sp_off[kk + 1] - M.sp_off[kk] - 1;
+                from = q + 1;
+            }
+            if (pass == 0) {
+                const unsigned long long nints = (unsigned long long)(bs.cnt + 3) / 4ull + 2ull;
+                at = ak_atomic_add64(X.pool_used, nints);
+                if (at + nints > X.pool_cap) { ak_status_or(X.result, AK_ST_WORD | st); return; }
+                bs.out = (uint8_t*)(X.pool + at);
+                bs.cap = bs.cnt;
+                bs.cnt = 0;
+            }
+        }
+        const uint8_t* nt = (const uint8_t*)(X.pool + at);
+        const int64_t nb = bs.cnt;
+        AkBpeDev M2 = M;
+        M2.bos = M2.eos = -1;
         AkIdSink sink;
         sink.buf = nullptr; sink.cap = 0; sink.stride = 1; sink.cnt = 0; sink.direct = false;
         sink.gout = nullptr; sink.gbase = 0; sink.gcap = 0;
-        int64_t rf, rl;
-        bool changed = false;
-        ak_bpe_span(X.M.bpe, X.M.T, nt, loff, 1, 0, 1, 0, nb + 1, 0, sink, nullptr, 0, rf, rl, X.M.pool, changed, st);
-        const int framed = sink.cnt;
-        const int lead = X.M.bpe.bos >= 0 ? 1 : 0, trail = X.M.bpe.eos >= 0 ? 1 : 0;
-        const int cnt = framed - lead - trail;
-        const unsigned long long at2 = ak_atomic_add64(X.pool_used, (unsigned long long)framed + 1ull);
-        if (at2 + (unsigned long long)framed > X.pool_cap || cnt >= (1 << 24) || cnt < 0) { ak_status_or(X.result, AK_ST_WORD); return; }
-        sink.cnt = 0;
-        sink.direct = true;
-        sink.gout = X.pool + at2;
-        sink.gbase = 0;
-        sink.gcap = framed;
-        ak_bpe_span(X.M.bpe, X.M.T, nt, loff, 1, 0, 1, 0, nb + 1, 0, sink, nullptr, 0, rf, rl, X.M.pool, changed, st);
-        X.row_fix[g] = ((at2 + (unsigned long long)lead) << 24) | (unsigned long long)cnt;
+        unsigned long long at2 = 0;
+        for (int pass = 0; pass < 2; ++pass) {
+            int64_t from = 0;
+            for (int64_t q = 0; q <= nb; ++q) {
+                if (q < nb && nt[q] != 0xFFu) continue;
+                if (q > from) {
+                    int64_t loff[2] = {from, q};
+                    int64_t rf, rl;
+                    bool changed = false;
+                    ak_bpe_span(M2, X.M.T, nt, loff, 1, 0, 1, from, q + 1, 0, sink, nullptr, 0, rf, rl, X.M.pool, changed, st, true);
+                }
+                if (q == nb) break;
+                ak_id_put(sink, M.sp_ids[nt[q + 1]]);
+                ++q;
+                from = q + 1;
+            }
+            if (pass == 0) {
+                const int cnt = sink.cnt;
+                at2 = ak_atomic_add64(X.pool_used, (unsigned long long)cnt + 1ull);
+                if (at2 + (unsigned long long)cnt > X.pool_cap || cnt >= (1 << 24)) { ak_status_or(X.result, AK_ST_WORD | st); return; }
+                sink.cnt = 0;
+                sink.direct = true;
+                sink.gout = X.pool + at2;
+                sink.gbase = 0;
+                sink.gcap = cnt;
+            }
+        }
+        X.row_fix[g] = (at2 << 24) | (unsigned long long)sink.cnt;
         ak_status_or(X.result, st);
     }
 }

@@ -21,6 +21,10 @@ inline AkBpeDev ak_bpe_host_view(const AkBpeHost& h) {
     m.mbits = h.mbits;
     m.bos = h.bos;
     m.eos = h.eos;
+    m.sp_bytes = h.sp_bytes.data();
+    m.sp_off = h.sp_off.data();
+    m.sp_ids = h.sp_ids.data();
+    m.n_sp = (int)h.sp_ids.size();
     return m;
 }
 inline AkUniDev ak_uni_host_view(const AkUniHost& h) {

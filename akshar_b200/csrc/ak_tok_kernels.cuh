@@ -56,6 +56,7 @@ struct AkWordsArgs {
     unsigned int* any_flag;
     uint32_t* row_ev;                  // [n_rows + 1] slot of the event that starts the row
     long long* n_wt_out;               // number of warp tiles (for the scans over the per-warp-tile aggregates)
+    AkBpeDev bpe;                      // KIND 0: the added tokens
 };
 
 // end of a word with no boundary within what the warp knows (cold)
@@ -131,7 +132,18 @@ __global__ void __launch_bounds__(AKW_THREADS, AKW_MINB) ak_words_kernel(const A
             const uint32_t up2p = __shfl_up_sync(0xFFFFFFFFu, L.up2, 1);
             akb3_phase3(L, up2p);
             if (active) {
-                if (L.flags & 1u) st |= AK_ST_ALPHABET;
+                // what only HF's side of the pipeline acts on: an added token in the raw text ('<' is where each of the
+                // reference's five starts), a code point its NFKC changes -> the row is encoded by the row-fix kernel
+                uint32_t fix = L.UNS & L.own;
+                for (uint32_t m = L.LT & L.own; m;) {
+                    const int i = akb_ctz(m);
+                    m &= m - 1u;
+                    if (ak_bpe_special_at(A.bpe, B.text, cs + i, te) >= 0) fix |= 1u << i;
+                }
+                if (fix) {
+                    ake_flag_rows(B.off, B.n_rows, cs, fix, A.row_flag);
+                    atomicOr(A.any_flag, 1u);
+                }
                 if (L.trb) {
                     const int64_t r_lo = r_w0 > 0 ? r_w0 - 1 : 0;
                     if (akb3_changes(A.T, B.text, B.off, B.n_rows, r_lo, L.trb, cs, st)) {

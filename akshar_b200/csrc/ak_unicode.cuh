@@ -52,6 +52,13 @@ struct AkTables {
     const uint32_t* fl_keys;
     const uint32_t* fl_vals;
     int n_decomp, n_pairs, n_ll, n_fl;
+    // HF's NFKC (tools/gen_tables.py): compatibility decompositions as `tokenizers` applies them, and the code points its
+    // older Unicode data does not know
+    const uint32_t* kmap_keys;
+    const uint16_t* kmap_off;
+    const uint32_t* kmap_data;
+    const uint32_t* hf_unknown;
+    int n_kmap, n_hf_unknown;
 };
 
 AK_HD uint32_t ak_props(const AkTables& T, uint32_t cp) {

@@ -63,6 +63,8 @@ class _Tables:
         self.pairs = {(a, b): c for a, b, c in j['pairs']}
         self.latin_lower = {int(k, 16): v for k, v in j['latin_lower'].items()}
         self.full_lower = {int(k, 16): v for k, v in j['full_lower'].items()}
+        self.hf_kmap = {int(k, 16): v for k, v in j['hf_kmap'].items()}
+        self.hf_unknown = frozenset(j['hf_unknown'])
 
 
 _T = None
@@ -560,6 +562,7 @@ class BpeModel:
             self.merges[(self.vocab[a], self.vocab[b])] = (rank, self.vocab[a + b])
         self.specials = [(t['content'], t['id']) for t in j.get('added_tokens', [])]
         self.special_ids = set(i for _, i in self.specials)
+        self.special_first = frozenset(c[0] for c, _ in self.specials if c)
         for c, i in self.specials:
             self.id_to_token[i] = c
         self.bos = self.eos = None
@@ -604,30 +607,82 @@ def bpe_word_ids(model, word_cps):
     return sym
 
 
-def bpe_encode(model, text):
-    """ids of `Tokenizer.encode(text).ids` for text inside the closed alphabet of normalize_text's output."""
+def hf_nfkc_cps(cps):
+    """`normalizers.NFKC()` of tokenizers 0.22.2 (scripts/train_bpe.py:71) over a list of code points.  Its Unicode data is
+    older than CPython's: code points it does not know (tables().hf_unknown) pass through as inert starters, every other
+    code point is replaced by HF's compatibility decomposition (tables().hf_kmap, probed) or the canonical one, then
+    canonical ordering and composition as in NFC; a composite HF does not know is left decomposed."""
     T = tables()
-    cps = [ord(c) for c in text]
+    out = []
+    run = []
+
+    def flush():
+        if run:
+            for c in nfc_cps(run):
+                if c in T.hf_unknown:
+                    _decompose(c, out)
+                else:
+                    out.append(c)
+            del run[:]
     for c in cps:
-        if not T.bpe_safe[c]:
-            raise NotImplementedError('BPE oracle: HF NFKC differs from NFC on U+%04X (or it is "<")' % c)
-    # HF NFKC restricted to these code points == NFC, except that the exotic spaces fold to U+0020 (all of them are
-    # \\s, so the fold never shows); marks that became adjacent only after filter_garbage / remove_elongations are
-    # canonically reordered and composed (e.g. U+0928 ZWNJ U+093C -> U+0928 U+093C -> U+0929).
-    cps = nfc_cps([0x20 if (T.hf_class[c] == 2) else c for c in cps])
-    ids = []
-    i, n = 0, len(cps)
-    hf = T.hf_class
+        if c in T.hf_unknown:
+            flush()
+            out.append(c)
+        else:
+            run.extend(T.hf_kmap.get(c, (c,)))
+    flush()
+    return out
+
+
+def _split_specials(model, text):
+    """HF AddedVocabulary: the special tokens (normalized=false) are cut out of the RAW text, leftmost-longest, before the
+    normalizer runs (scripts/train_bpe.py:80) -> [(text piece, None) | (None, special id)]"""
+    specials = sorted(model.specials, key=lambda x: -len(x[0]))
+    out = []
+    i = start = 0
+    n = len(text)
     while i < n:
-        k = hf[cps[i]]
-        if k == 2:
+        hit = None
+        if text[i] in model.special_first:
+            for c, sid in specials:
+                if text.startswith(c, i):
+                    hit = (c, sid)
+                    break
+        if hit is None:
             i += 1
             continue
-        j = i
-        while j < n and hf[cps[j]] == k:
-            j += 1
-        ids.extend(bpe_word_ids(model, cps[i:j]))
-        i = j
+        if i > start:
+            out.append((text[start:i], None))
+        out.append((None, hit[1]))
+        i += len(hit[0])
+        start = i
+    if start < n:
+        out.append((text[start:], None))
+    return out
+
+
+def bpe_encode(model, text):
+    """ids of `Tokenizer.encode(text).ids` (tokenizer.py:193): special tokens cut out of the raw text, every other piece
+    through NFKC -> Whitespace pre-tokenizer (`\\w+|[^\\w\\s]+`) -> BPE merges, framed by the template's <s> ... </s>"""
+    T = tables()
+    hf = T.hf_class
+    ids = []
+    for piece, sid in _split_specials(model, text):
+        if sid is not None:
+            ids.append(sid)
+            continue
+        cps = hf_nfkc_cps([ord(c) for c in piece])
+        i, n = 0, len(cps)
+        while i < n:
+            k = hf[cps[i]]
+            if k == 2:
+                i += 1
+                continue
+            j = i
+            while j < n and hf[cps[j]] == k:
+                j += 1
+            ids.extend(bpe_word_ids(model, cps[i:j]))
+            i = j
     if model.bos is not None:
         ids = [model.bos] + ids
     if model.eos is not None:

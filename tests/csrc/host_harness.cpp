@@ -26,6 +26,8 @@ static AkTables host_tables() {
     T.pair_keys = ak_tbl_pair_keys; T.pair_vals = ak_tbl_pair_vals;
     T.ll_keys = ak_tbl_latin_lower_keys; T.ll_vals = ak_tbl_latin_lower_vals;
     T.fl_keys = ak_tbl_full_lower_keys; T.fl_vals = ak_tbl_full_lower_vals;
+    T.kmap_keys = ak_tbl_kmap_keys; T.kmap_off = ak_tbl_kmap_off; T.kmap_data = ak_tbl_kmap_data; T.n_kmap = AK_N_KMAP;
+    T.hf_unknown = ak_tbl_hf_unknown; T.n_hf_unknown = AK_N_HF_UNKNOWN;
     T.n_decomp = AK_N_DECOMP; T.n_pairs = AK_N_PAIRS; T.n_ll = AK_N_LATIN_LOWER; T.n_fl = AK_N_FULL_LOWER;
     return T;
 }
@@ -505,7 +507,16 @@ int64_t hh_tok(int kind, const uint8_t* text, const int64_t* off, int64_t n_rows
             uint32_t rowsm, wstart, cw, bnd, nb1, nb2;
             if (kind == 0) {
                 AkB3Lane& L = lb[(size_t)l];
-                if (L.flags & 1u) st |= AK_ST_ALPHABET;
+                {
+                    uint32_t fix = L.UNS & L.own;
+                    const AkBpeDev hm = ak_bpe_host_view(g_bpe);
+                    for (uint32_t m = L.LT & L.own; m;) {
+                        const int i = akb_ctz(m);
+                        m &= m - 1u;
+                        if (ak_bpe_special_at(hm, text, cs + i, te) >= 0) fix |= 1u << i;
+                    }
+                    if (fix) ake_flag_rows(off, n_rows, cs, fix, row_flag.data());
+                }
                 if (L.trb && akb3_changes(T, text, off, n_rows, 0, L.trb, cs, st)) ake_flag_rows(off, n_rows, cs, L.trb, row_flag.data());
                 rowsm = L.rows; wstart = L.wstart; cw = L.CW; bnd = L.bnd;
                 nb1 = lb[(size_t)l + 1].bnd;

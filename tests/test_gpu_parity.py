@@ -440,24 +440,26 @@ def test_large_properties(A, eng, models_dir):
 
 
 def test_raw_mode_golden(A, golden_raw, models_dir):
-    """clean_hinglish=False (reference vectors): emoji, accents and other scripts reach the models"""
-    from akshar_b200.batch import BatchStatusError
-    T = O.tables()
+    """clean_hinglish=False (reference vectors, every row): emoji, accents and other scripts reach the models, and on the
+    BPE side what only HF acts on -- added tokens in the raw text, NFKC (scripts/train_bpe.py:71,80) -- is done on the device"""
     rows = golden_raw['rows']
+    ins = [r['in'] for r in rows]
     tu = A.aksharTokenizer(os.path.join(models_dir, 'spm24k.model'), 'sentencepiece', clean_hinglish=False)
-    assert tu.encode_batch([r['in'] for r in rows]) == [r['ids_spm24k'] for r in rows]
+    assert tu.encode_batch(ins) == [r['ids_spm24k'] for r in rows]
     tb = A.aksharTokenizer(os.path.join(models_dir, 'bpe24k.json'), 'bpe', clean_hinglish=False)
-    safe = [r for r in rows if all(T.bpe_safe[ord(c)] for c in r['norm_nc'])]
-    assert len(safe) > 1500
-    assert tb.encode_batch([r['in'] for r in safe]) == [r['ids_bpe24k'] for r in safe]
+    assert tb.encode_batch(ins) == [r['ids_bpe24k'] for r in rows]
     tb2 = A.aksharTokenizer(os.path.join(models_dir, 'bpe24k.json'), 'bpe', normalize_roman=False, clean_hinglish=False)
-    safe2 = [r for r in rows if all(T.bpe_safe[ord(c)] for c in O.normalize_text(r['in'], False, False))]
-    assert tb2.encode_batch([r['in'] for r in safe2]) == [r['ids_bpe24k_raw'] for r in safe2]
-    # compatibility characters / added-token syntax: refused loudly, never answered wrongly
-    with pytest.raises(BatchStatusError):
-        tb.encode_batch(['ok', 'x\ufb01y'])
-    with pytest.raises(BatchStatusError):
-        tb.encode_batch(['<s> hi </s>'])
+    assert tb2.encode_batch(ins) == [r['ids_bpe24k_raw'] for r in rows]
+    for s in ('<s> hi </s>', 'x\ufb01y <mask>', 'a<pad>b<unk>c<', '\uff26\uff55\uff4c\uff4c \u2460 x\u00b2'):
+        om = O.BpeModel(os.path.join(models_dir, 'bpe24k.json'))
+        assert tb2.encode(s) == O.bpe_encode(om, O.normalize_text(s, False, False))
+    # the stand-alone encoder over text as it is (no normalize_text before it), in both modes
+    from akshar_b200 import _lib as C
+    om = O.BpeModel(os.path.join(models_dir, 'bpe24k.json'))
+    exp = [O.bpe_encode(om, s) for s in ins]
+    for mode in (C.MODE_TILES, C.MODE_ROWS):
+        got = [x.tolist() for x in tb._eng.encode_bpe_batch(ins, mode=mode).rows()]
+        assert got == exp
 
 
 def test_corpus_front_end(A, models_dir, tmp_path):

@@ -16,11 +16,18 @@ def _rows(golden, limit=None):
     return rows
 
 
+def _walker_rows(rows):
+    """the span walker (ak_bpe_span) on its own takes text HF's NFKC leaves alone; anything else goes through the row path
+    of the event-stream encoder (test_bpe_event_stream, test_raw_mode_cores)"""
+    T = O.tables()
+    return [r for r in rows if all(T.bpe_safe[ord(c)] for c in r['norm'])]
+
+
 @pytest.mark.parametrize('name', ['bpe24k', 'bpe_corpus'])
 @pytest.mark.parametrize('span', [32, 7, 100000])
 def test_bpe_ids_match_reference(golden, bpe_rows, models_dir, name, span):
     assert W.load_bpe(os.path.join(models_dir, name + '.json')) == golden['vocab_size'][name]
-    rows = bpe_rows
+    rows = _walker_rows(bpe_rows)
     data, off = sc.pack([r['norm'] for r in rows])
     ids, splits, st, attempt = W.bpe(data, off, span=span)
     assert st == 0
@@ -33,7 +40,7 @@ def test_bpe_ids_match_reference(golden, bpe_rows, models_dir, name, span):
 
 def test_bpe_small_stage_and_random_spans(golden, bpe_rows, models_dir):
     W.load_bpe(os.path.join(models_dir, 'bpe24k.json'))
-    rows = bpe_rows
+    rows = _walker_rows(bpe_rows)
     lines = [r['norm'] for r in rows] + ['', '', '']
     exp = [r['ids_bpe24k'] for r in rows] + [[2, 3]] * 3
     data, off = sc.pack(lines)
@@ -252,13 +259,27 @@ def test_raw_mode_cores(golden_raw, models_dir):
     assert ids.tolist() == [i for r in rows for i in r['ids_spm24k']]
     safe = [r for r in rows if all(T.bpe_safe[ord(c)] for c in r['norm_nc'])]
     data, off = sc.pack([r['norm_nc'] for r in safe])
-    for fn in (W.bpe, lambda a, b: W.tok(0, a, b)):
-        ids, splits, st, _ = fn(data, off)
-        assert st == 0
-        assert ids.tolist() == [i for r in safe for i in r['ids_bpe24k']]
-    # anything else must be refused loudly (status bit 8 = AKSHAR_ST_ALPHABET)
+    ids, splits, st, _ = W.bpe(data, off)
+    assert st == 0 and ids.tolist() == [i for r in safe for i in r['ids_bpe24k']]
+    # the event-stream encoder takes every row: added tokens in the raw text, compatibility characters, marks HF's older
+    # Unicode tables order differently -- those rows go through the exact row path (HF's NFKC + added-token split)
+    for key_in, key_ids in ((lambda r: r['norm_nc'], 'ids_bpe24k'),
+                            (lambda r: O.normalize_text(r['in'], normalize_roman=False, clean_hinglish=False), 'ids_bpe24k_raw')):
+        lines = [key_in(r) for r in rows]
+        data, off = sc.pack(lines)
+        for real, capb in ((30, 14), (3, 6)):
+            ids, splits, st, stats = W.tok(0, data, off, real=real, cache_bits=capb)
+            assert st == 0
+            exp = [r[key_ids] for r in rows]
+            assert splits.tolist() == np.concatenate(([0], np.cumsum([len(e) for e in exp]))).tolist()
+            assert ids.tolist() == [i for e in exp for i in e]
+    assert stats['flagged_rows'] > 300 and stats['flagged_rows'] < len(rows) // 2
+    # the span walker on its own still refuses them (status bit 8 = AKSHAR_ST_ALPHABET)
     data, off = sc.pack(['ok', 'x\ufb01y', '<s>'])
-    assert W.tok(0, data, off)[2] & 8 and W.bpe(data, off)[2] & 8
+    assert W.bpe(data, off)[2] & 8
+    ids, splits, st, _ = W.tok(0, data, off)
+    m = O.BpeModel(os.path.join(models_dir, 'bpe24k.json'))
+    assert st == 0 and ids.tolist() == [i for t in ('ok', 'x\ufb01y', '<s>') for i in O.bpe_encode(m, t)]
 
 
 # ---- ids -> text (ak_decode.cuh; reference tokenizer.py:195-246) ------------------------------------------------------

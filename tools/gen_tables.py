@@ -247,6 +247,43 @@ def main():
             bpe_safe[cp] = 1
     print("bpe_safe", sum(bpe_safe), "allow-list members not safe:", [hex(c) for c in range(NCP) if allow[c] and not bpe_safe[c] and nfc_qc[c] != 1])
 
+    # ---- HF's NFKC, for the rows the BPE encoder normalizes itself (scripts/train_bpe.py:71): probed from the `tokenizers`
+    # normalizers, whose Unicode data is older than CPython's.
+    #   hf_kmap[cp]   = HF NFKD(cp) wherever it differs from the canonical decomposition above (compatibility mappings)
+    #   hf_unknown    = code points with normalization properties here (ccc / canonical decomposition) that HF does not
+    #                   know: it passes them through as inert starters
+    nfkd, nfd = normalizers.NFKD(), normalizers.NFD()
+    hf_kmap = {}
+    hf_unknown = set()
+    for cp in range(NCP):
+        if 0xD800 <= cp <= 0xDFFF:
+            continue
+        ch = chr(cp)
+        ours = unicodedata.normalize('NFD', ch)
+        if nfd.normalize_str(ch) != ours:
+            hf_unknown.add(cp)
+        else:
+            h = nfkd.normalize_str(ch)
+            if h != ours:
+                hf_kmap[cp] = [ord(c) for c in h]
+        cc = unicodedata.combining(ch)
+        if cc:
+            t = ('a' + ch + '\u0334') if cc > 1 else ('a\u0301' + ch)
+            if nfd.normalize_str(t) != unicodedata.normalize('NFD', t):
+                hf_unknown.add(cp)
+    for cp in hf_unknown:
+        assert nfkc.normalize_str(chr(cp)) == chr(cp), hex(cp)
+    for cp, v in hf_kmap.items():
+        assert not any(x in hf_unknown for x in v), hex(cp)
+        assert not bpe_safe[cp] or v == [0x20], hex(cp)
+    # rows with such a code point, or with the pieces one of them decomposes into (HF does not compose those), are
+    # normalized by the exact row path
+    for cp in hf_unknown:
+        bpe_safe[cp] = 0
+        for x in decomp.get(cp, []):
+            bpe_safe[x] = 0
+    print("hf_kmap", len(hf_kmap), "data", sum(len(v) for v in hf_kmap.values()), "hf_unknown", len(hf_unknown))
+
     # ---- pack the 32-bit property word
     # first element of some canonical composition pair (incl. the algorithmic Hangul L + V; LV + T is covered by
     # the decomposition bit): a mark after such a starter may compose, after any other atomic starter it cannot
@@ -291,6 +328,14 @@ def main():
     ll_vals = [latin_lower[k][0] for k in ll_keys]
     fl_keys = sorted(full_lower)
     fl_vals = [full_lower[k][0] for k in fl_keys]
+    km_keys = sorted(hf_kmap)
+    km_off = []
+    km_data = []
+    for k in km_keys:
+        km_off.append(len(km_data))
+        km_data.extend(hf_kmap[k])
+    km_off.append(len(km_data))
+    unk_keys = sorted(hf_unknown)
 
     out = []
     out.append("// GENERATED by tools/gen_tables.py -- do not edit.")
@@ -305,6 +350,9 @@ def main():
     out.append("#define AK_N_PAIRS %d" % len(pair_keys))
     out.append("#define AK_N_LATIN_LOWER %d" % len(ll_keys))
     out.append("#define AK_N_FULL_LOWER %d" % len(fl_keys))
+    out.append("#define AK_N_KMAP %d" % len(km_keys))
+    out.append("#define AK_N_KMAP_DATA %d" % len(km_data))
+    out.append("#define AK_N_HF_UNKNOWN %d" % len(unk_keys))
     out.append(arr("ak_tbl_page_index", "unsigned short", page_index))
     out.append(arr("ak_tbl_leaves", "unsigned int", leaves, 8, "0x%xu"))
     out.append(arr("ak_tbl_decomp_keys", "unsigned int", dec_keys, 12, "0x%x"))
@@ -316,6 +364,10 @@ def main():
     out.append(arr("ak_tbl_latin_lower_vals", "unsigned int", ll_vals, 12, "0x%x"))
     out.append(arr("ak_tbl_full_lower_keys", "unsigned int", fl_keys, 12, "0x%x"))
     out.append(arr("ak_tbl_full_lower_vals", "unsigned int", fl_vals, 12, "0x%x"))
+    out.append(arr("ak_tbl_kmap_keys", "unsigned int", km_keys, 12, "0x%x"))
+    out.append(arr("ak_tbl_kmap_off", "unsigned short", km_off))
+    out.append(arr("ak_tbl_kmap_data", "unsigned int", km_data, 12, "0x%x"))
+    out.append(arr("ak_tbl_hf_unknown", "unsigned int", unk_keys, 12, "0x%x"))
     inc = os.path.join(ROOT, "akshar_b200", "csrc", "unicode_tables.inc")
     with open(inc, "w") as f:
         f.write("\n".join(out) + "\n")
@@ -343,6 +395,8 @@ def main():
         "case_ignorable": to_ranges(case_ign),
         "cased": to_ranges(cased),
         "bpe_safe": to_ranges(bpe_safe),
+        "hf_kmap": {"%x" % k: hf_kmap[k] for k in km_keys},
+        "hf_unknown": unk_keys,
     }
     oj_path = os.path.join(ROOT, "oracle", "ucd_tables.json")
     with open(oj_path, "w") as f:
