@@ -273,6 +273,41 @@ class Engine:
             return out + (fl[:b.n_rows],) if row_flags else out
         raise BatchStatusError(bits, 'word_tokenize_batch (retries exhausted)')
 
+    # ------------------------------------------------------------------ per-sentence statistics, cluster merging
+    def composition_batch(self, batch):
+        """-> int32 [n_rows, 5] on the device: akshars, script runs, code points, code points in devanagari / roman runs"""
+        b = self.put(batch)
+        clusters, runs = self.segment_batch(b, clusters=True, runs=True)
+        stats = torch.empty((max(b.n_rows, 1), 5), dtype=torch.int32, device=self.device)
+        rc = self.lib.akshar_composition_batch(self._h, b.data.data_ptr(), b.offsets.data_ptr(), b.n_rows, clusters.splits.data_ptr(),
+                                               runs.values.data_ptr(), runs.extra.data_ptr(), runs.splits.data_ptr(),
+                                               stats.data_ptr(), self._stream())
+        if rc != 0:
+            self._err(rc, 'akshar_composition_batch')
+        return stats[:b.n_rows]
+
+    def merge_clusters_batch(self, batch, clusters, rule):
+        """the cluster-merging feature wrappers (reference features.py:28-55, 173-206) -> Ragged like `clusters`"""
+        b = self.put(batch)
+        n = clusters.values.numel()
+        need = self.lib.akshar_merge_workspace_bytes(n)
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = None
+            self._ws = torch.empty(need + (need >> 3), dtype=torch.uint8, device=self.device)
+        ws = self._ws
+        out = torch.empty(max(n, 1), dtype=torch.int32, device=self.device)
+        sp = torch.empty(b.n_rows + 1, dtype=torch.int64, device=self.device)
+        result = torch.empty(4, dtype=torch.int64, device=self.device)
+        rc = self.lib.akshar_merge_clusters_batch(self._h, b.data.data_ptr(), b.offsets.data_ptr(), b.n_rows, clusters.values.data_ptr(),
+                                                  clusters.splits.data_ptr(), n, rule, out.data_ptr(), n, sp.data_ptr(),
+                                                  result.data_ptr(), ws.data_ptr(), ws.numel(), self._stream())
+        if rc != 0:
+            self._err(rc, 'akshar_merge_clusters_batch')
+        total, _, bits = self._finish(result, 'merge_clusters', True)
+        if bits:
+            raise BatchStatusError(bits, 'merge_clusters_batch')
+        return Ragged(out[:total], sp)
+
     # ------------------------------------------------------------------ ids -> text
     def decode_batch(self, ids, splits, kind, form=C.FORM_DECODE, capacity=None):
         """aksharTokenizer.decode / detokenize over a batch of id rows (reference tokenizer.py:195-246) -> TextBatch.

@@ -36,6 +36,7 @@
 #include "ak_tok_kernels.cuh"
 #include "ak_wtok_kernels.cuh"
 #include "ak_decode_kernels.cuh"
+#include "ak_feat_kernels.cuh"
 
 // ================================================================================================
 // host side: context, model upload, C ABI
@@ -736,6 +737,98 @@ int akshar_decode_batch(akshar_ctx* ctx, int kind, int form, const void* d_ids, 
                                        d_result, (char*)d_workspace, (cudaStream_t)stream);
     return ak_run_decode<int32_t>(ctx, D, f, d_ids, n_ids, d_row_splits, n_rows, d_out_text, out_capacity, d_out_row_offsets, d_result,
                                   (char*)d_workspace, (cudaStream_t)stream);
+}
+
+// ---- per-sentence statistics and cluster merging over the segment kernel's outputs -----------------------------------
+int akshar_composition_batch(akshar_ctx* ctx, const uint8_t* d_text, const int64_t* d_row_offsets, int64_t n_rows,
+                             const int64_t* d_cluster_splits, const int32_t* d_run_ends, const uint8_t* d_run_tags,
+                             const int64_t* d_run_splits, int32_t* d_stats, void* stream) {
+    if (!ctx) return AKSHAR_E_ARG;
+    AkDeviceGuard device_guard(ctx->device);
+    if (!d_row_offsets || n_rows < 0 || !d_cluster_splits || !d_run_splits || (n_rows > 0 && !d_stats)) {
+        ctx->err = "bad argument";
+        return AKSHAR_E_ARG;
+    }
+    if (n_rows == 0) return AKSHAR_OK;
+    AkCompArgs A;
+    A.text = d_text;
+    A.off = d_row_offsets;
+    A.n_rows = n_rows;
+    A.cluster_splits = d_cluster_splits;
+    A.run_ends = d_run_ends;
+    A.run_tags = d_run_tags;
+    A.run_splits = d_run_splits;
+    A.stats = d_stats;
+    ak_comp_kernel<<<ak_grid(ctx, 8, (int)((n_rows + 7) / 8)), 256, 0, (cudaStream_t)stream>>>(A);
+    return ak_after_launch(ctx, "composition");
+}
+
+static size_t ak_cm_ws(int64_t n, size_t* flag, size_t* count, size_t* base, size_t* state) {
+    const size_t tiles = (size_t)(n / AKCM_TILE + 2);
+    *flag = 256;
+    *count = *flag + ak_align((size_t)n + 16);
+    *base = *count + ak_align(tiles * 4);
+    *state = *base + ak_align(tiles * 8);
+    return *state + ak_align((tiles / AKS_TILE + 2) * 8);
+}
+
+size_t akshar_merge_workspace_bytes(int64_t n_clusters) {
+    size_t a, b, c, d;
+    return n_clusters < 0 ? 0 : ak_cm_ws(n_clusters, &a, &b, &c, &d);
+}
+
+int akshar_merge_clusters_batch(akshar_ctx* ctx, const uint8_t* d_text, const int64_t* d_row_offsets, int64_t n_rows,
+                                const int32_t* d_cluster_ends, const int64_t* d_cluster_splits, int64_t n_clusters, int rule,
+                                int32_t* d_out_ends, int64_t out_capacity, int64_t* d_out_splits, int64_t* d_result,
+                                void* d_workspace, size_t workspace_bytes, void* stream) {
+    if (!ctx) return AKSHAR_E_ARG;
+    AkDeviceGuard device_guard(ctx->device);
+    if (!d_row_offsets || n_rows < 0 || n_clusters < 0 || !d_cluster_splits || !d_out_splits || !d_result || out_capacity < 0 ||
+        (rule != AKSHAR_MERGE_AKSHARA && rule != AKSHAR_MERGE_NUKTA) || (n_clusters > 0 && (!d_cluster_ends || !d_text)) ||
+        (out_capacity > 0 && !d_out_ends)) {
+        ctx->err = "bad argument";
+        return AKSHAR_E_ARG;
+    }
+    size_t o_flag, o_count, o_base, o_state;
+    const size_t need = ak_cm_ws(n_clusters, &o_flag, &o_count, &o_base, &o_state);
+    if (!d_workspace || workspace_bytes < need) {
+        ctx->err = "workspace too small: need " + std::to_string(need) + " bytes";
+        return AKSHAR_E_WORKSPACE;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    char* ws = (char*)d_workspace;
+    int rc;
+    AK_CUDA(ctx, cudaMemsetAsync(ws, 0, 256, s));
+    AK_CUDA(ctx, cudaMemsetAsync(ws + o_state, 0, need - o_state, s));
+    AK_CUDA(ctx, cudaMemsetAsync(d_result, 0, 4 * sizeof(int64_t), s));
+    AkCmArgs A;
+    A.text = d_text;
+    A.off = d_row_offsets;
+    A.n_rows = n_rows;
+    A.ends = d_cluster_ends;
+    A.splits = d_cluster_splits;
+    A.n = n_clusters;
+    A.rule = rule == AKSHAR_MERGE_AKSHARA ? AKCM_AKSHARA : AKCM_NUKTA;
+    A.flag = (uint8_t*)(ws + o_flag);
+    A.count = (int32_t*)(ws + o_count);
+    A.base = (const int64_t*)(ws + o_base);
+    A.out_ends = d_out_ends;
+    A.out_splits = d_out_splits;
+    A.cap = out_capacity;
+    A.result = d_result;
+    const int64_t n_tiles = (n_clusters + AKCM_TILE - 1) / AKCM_TILE;
+    if (n_clusters > 0) {
+        ak_cm_flag_kernel<<<ak_grid(ctx, 8, (int)((n_clusters + 255) / 256)), 256, 0, s>>>(A);
+        if ((rc = ak_after_launch(ctx, "merge-flags"))) return rc;
+        ak_cm_kernel<false><<<ak_grid(ctx, 8, (int)n_tiles), AKCM_THREADS, 0, s>>>(A);
+        if ((rc = ak_after_launch(ctx, "merge-count"))) return rc;
+    }
+    ak_scan_counts_kernel<<<ak_grid(ctx, 4, (int)(n_tiles / AKS_TILE + 1)), AKS_THREADS, 0, s>>>(
+        A.count, (long long)n_tiles, nullptr, 1, (int64_t*)(ws + o_base), d_result, (int*)ws, (unsigned long long*)(ws + o_state),
+        (unsigned int*)&d_result[2]);
+    if ((rc = ak_after_launch(ctx, "merge-scan"))) return rc;
+    ak_cm_kernel<true><<<ak_grid(ctx, 8, (int)(n_tiles > 0 ? n_tiles : 1)), AKCM_THREADS, 0, s>>>(A);
+    return ak_after_launch(ctx, "merge-write");
 }
 
 int akshar_signature_batch(akshar_ctx* ctx, const uint8_t* d_text, const int64_t* d_row_offsets, int64_t n_rows,

@@ -71,33 +71,49 @@ def detect_code_switches_batch(texts, as_device=False, device=0):
     return out
 
 
-def analyze_text_composition_batch(texts, device=0):
-    clusters, runs = engine(device).segment_batch(texts, clusters=True, runs=True)
-    cs = clusters.splits.cpu().numpy()
-    rs = runs.splits.cpu().numpy()
-    ends = runs.values.cpu().numpy()
-    tags = runs.extra.cpu().numpy()
+def analyze_text_composition_batch(texts, as_device=False, device=0):
+    """analyze_text_composition over a batch (reference segment.py:210-236): the five counts of every row come off the
+    device (Engine.composition_batch); as_device=True returns them as an int32 [n, 5] tensor
+    (akshars, script runs, code points, code points in devanagari runs, in roman runs)"""
+    stats = engine(device).composition_batch(texts)
+    if as_device:
+        return stats
     out = []
-    for i, s in enumerate(texts):
-        total = len(s)
-        dev = rom = 0
-        if total:
-            b = s.encode('utf-8')
-            prev = 0
-            for e, t in zip(ends[rs[i]:rs[i + 1]].tolist(), tags[rs[i]:rs[i + 1]].tolist()):
-                n = len(b[prev:e].decode('utf-8'))
-                if t == 0:
-                    dev += n
-                elif t == 1:
-                    rom += n
-                prev = e
+    for ak, nr, total, dev, rom in stats.cpu().numpy().tolist():
         out.append({
-            'akshar_count': int(cs[i + 1] - cs[i]),
-            'script_switches': int(rs[i + 1] - rs[i]) - 1,
+            'akshar_count': ak,
+            'script_switches': nr - 1,
             'devanagari_ratio': dev / total if total > 0 else 0,
             'roman_ratio': rom / total if total > 0 else 0,
         })
     return out
+
+
+def _merged(texts, rule, device):
+    eng = engine(device)
+    b = eng.put(texts)
+    clusters, _ = eng.segment_batch(b, clusters=True, matras=False, runs=False)
+    return _slices(texts, eng.merge_clusters_batch(b, clusters, rule))
+
+
+def akshara_level_tokenization_batch(texts, device=0):
+    """features.py:28-55 over a batch: consecutive clusters that hold a halant are one akshara"""
+    return _merged(texts, C.MERGE_AKSHARA, device)
+
+
+def preserve_nukta_batch(texts, device=0):
+    """features.py:173-206 over a batch: a cluster that holds a nukta takes the next cluster with it"""
+    return _merged(texts, C.MERGE_NUKTA, device)
+
+
+def akshara_level_tokenization(text):
+    """reference features.py:28-55"""
+    return akshara_level_tokenization_batch([text])[0]
+
+
+def preserve_nukta(text):
+    """reference features.py:173-206"""
+    return preserve_nukta_batch([text])[0]
 
 
 def _word_slices(tb, begin, end, splits, rows=None):

@@ -126,6 +126,25 @@ int akshar_decode_batch(akshar_ctx* ctx, int kind, int form, const void* d_ids, 
                         int64_t n_rows, uint8_t* d_out_text, int64_t out_capacity, int64_t* d_out_row_offsets, int64_t* d_result,
                         void* d_workspace, size_t workspace_bytes, void* stream);
 
+/* analyze_text_composition over a batch (segment.py:210-236), from the outputs of akshar_segment_batch (clusters + runs of
+ * the same text): d_stats[5 r ..] = akshars, script runs, code points, code points in devanagari runs, in roman runs.
+ * (script_switches = runs - 1; the two ratios are the last two counts over the third.) */
+int akshar_composition_batch(akshar_ctx* ctx, const uint8_t* d_text, const int64_t* d_row_offsets, int64_t n_rows,
+                             const int64_t* d_cluster_splits, const int32_t* d_run_ends, const uint8_t* d_run_tags,
+                             const int64_t* d_run_splits, int32_t* d_stats, void* stream);
+
+/* the feature wrappers that are functions of the cluster boundaries: akshara_level_tokenization (features.py:28-55,
+ * AKSHAR_MERGE_AKSHARA: consecutive clusters that hold U+094D are one akshara) and preserve_nukta (features.py:173-206,
+ * AKSHAR_MERGE_NUKTA: a cluster that holds U+093C takes the next cluster with it).  In: the clusters of
+ * akshar_segment_batch(matras = 0); out: the merged clusters in the same form.  result[0] = merged clusters. */
+#define AKSHAR_MERGE_AKSHARA 0
+#define AKSHAR_MERGE_NUKTA 1
+size_t akshar_merge_workspace_bytes(int64_t n_clusters);
+int akshar_merge_clusters_batch(akshar_ctx* ctx, const uint8_t* d_text, const int64_t* d_row_offsets, int64_t n_rows,
+                                const int32_t* d_cluster_ends, const int64_t* d_cluster_splits, int64_t n_clusters, int rule,
+                                int32_t* d_out_ends, int64_t out_capacity, int64_t* d_out_splits, int64_t* d_result,
+                                void* d_workspace, size_t workspace_bytes, void* stream);
+
 /* roman_phonetic_signature over a batch of words (normalize.py:59-89); one word per row. result[0] = out bytes */
 int akshar_signature_batch(akshar_ctx* ctx, const uint8_t* d_text, const int64_t* d_row_offsets, int64_t n_rows,
                            int64_t text_begin, int64_t text_end, uint8_t* d_out_text, int64_t out_capacity,

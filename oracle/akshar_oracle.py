@@ -468,6 +468,41 @@ def analyze_text_composition(text):
 
 
 # --------------------------------------------------------------------------------------------------
+# f4  the feature wrappers that are functions of the cluster boundaries (reference features.py:28-55, 173-206)
+# --------------------------------------------------------------------------------------------------
+def akshara_level_tokenization(text):
+    """features.py:28-55: clusters that hold a halant pile up, a cluster without one flushes the pile and stands alone"""
+    out = []
+    pile = []
+    for c in segment_akshars(text):
+        if '\u094d' in c:
+            pile.append(c)
+        else:
+            if pile:
+                out.append(''.join(pile))
+                pile = []
+            out.append(c)
+    if pile:
+        out.append(''.join(pile))
+    return out
+
+
+def preserve_nukta(text):
+    """features.py:173-206: a cluster that holds U+093C is joined with the cluster after it (which is then skipped)"""
+    seg = segment_akshars(text)
+    out = []
+    i = 0
+    while i < len(seg):
+        if '\u093c' in seg[i] and i + 1 < len(seg):
+            out.append(seg[i] + seg[i + 1])
+            i += 2
+        else:
+            out.append(seg[i])
+            i += 1
+    return out
+
+
+# --------------------------------------------------------------------------------------------------
 # f3  word tokenizers (reference segment.py:239-401)
 # --------------------------------------------------------------------------------------------------
 # str.isspace() (CPython, Unicode 15.0: bidirectional class WS / B / S or category Zs), written out

@@ -117,6 +117,57 @@ def test_word_tokenizers_oracle_large(A, eng):
     assert int((ae - ab).sum()) == int(np.count_nonzero(~space))          # tokens cover exactly the non-space bytes
 
 
+def test_composition_and_feature_wrappers_golden(A, golden):
+    """analyze_text_composition (segment.py:210-236) from the fused per-row counts, tokenize(return_metadata) / explain values
+    (tokenizer.py:123-165, 248-276), akshara_level_tokenization / preserve_nukta (features.py:28-55, 173-206)"""
+    rows = golden['rows']
+    norm = [r['norm'] for r in rows]
+    ins = [r['in'] for r in rows]
+    assert A.analyze_text_composition_batch(norm) == [r['comp'] for r in rows]
+    assert A.akshara_level_tokenization_batch(ins) == [r['feat_akshara'] for r in rows]
+    assert A.preserve_nukta_batch(ins) == [r['feat_nukta'] for r in rows]
+    assert A.akshara_level_tokenization('') == [] and A.preserve_nukta('\u0915\u093c') == ['\u0915\u093c']
+    assert A.analyze_text_composition('') == {'akshar_count': 0, 'script_switches': -1, 'devanagari_ratio': 0, 'roman_ratio': 0}
+    fb = A.aksharTokenizer()
+    for r in rows[:300]:
+        assert fb.tokenize(r['in'], return_metadata=True) == r['meta']
+        assert fb.detokenize(r['tokenize']) == r['detok_akshar']
+    import akshar.features as F
+    assert F.preserve_nukta is A.preserve_nukta
+    tb = A.aksharTokenizer(os.path.join(os.path.dirname(__file__), 'golden', 'models', 'bpe24k.json'), 'bpe')
+    for r in rows[:150]:
+        ex = tb.explain(r['in'])
+        ex['code_switches'] = [list(x) for x in ex['code_switches']]
+        assert ex == r['explain_bpe24k']
+    exb = tb.explain_batch([r['in'] for r in rows[:600]])
+    for ex, r in zip(exb, rows[:600]):
+        ex['code_switches'] = [list(x) for x in ex['code_switches']]
+        assert ex == r['explain_bpe24k']
+    # adversarial: runs of nukta / halant clusters of every length and parity, across rows
+    lines = ['', '\u0915\u093c' * 7, 'a' + '\u0915\u093c' * 4 + 'b', '\u0915\u094d ' * 5, '\u0915\u094d\u0937 \u0924\u094d \u0930\u094d', '',
+             '\u0915\u093c', 'x'] + sc.adversarial(3000, 5, 40)
+    assert A.akshara_level_tokenization_batch(lines) == [O.akshara_level_tokenization(s) for s in lines]
+    assert A.preserve_nukta_batch(lines) == [O.preserve_nukta(s) for s in lines]
+    assert A.analyze_text_composition_batch(lines) == [O.analyze_text_composition(s) for s in lines]
+
+
+def test_identify_script_full_table(A, golden):
+    """identify_script (segment.py:128-147) for the 12 292 characters recorded from the reference, on the device: one row per
+    character through the script-run kernel"""
+    chars = list(golden['identify_script'])
+    runs = A.engine().segment_batch(chars, clusters=False, runs=True)[1]
+    tags = _np(runs.extra)
+    sp = _np(runs.splits)
+    assert np.all(np.diff(sp) == 1)
+    names = ['devanagari', 'roman', 'digit', 'punct', 'other']
+    from akshar_b200.segment import _PUNCT
+    for ch, t in zip(chars, tags.tolist()):
+        got = names[t] if t != 255 else ('punct' if ch in _PUNCT else 'digit')
+        assert got == golden['identify_script'][ch], hex(ord(ch))
+    for ch in chars[::97]:
+        assert A.identify_script(ch) == golden['identify_script'][ch]
+
+
 def test_signature_golden(A, golden):
     words = list(golden['signature'])
     assert A.roman_phonetic_signature_batch(words) == [golden['signature'][w] for w in words]

@@ -59,6 +59,12 @@ def test_word_tokenizers(golden):
     assert O.word_tokenize("a\u2003b\x1fc  d", language='xx') == ['a', 'b', 'c', 'd']
 
 
+def test_feature_wrappers(golden):
+    for r in golden['rows']:
+        assert O.akshara_level_tokenization(r['in']) == r['feat_akshara']
+        assert O.preserve_nukta(r['in']) == r['feat_nukta']
+
+
 def test_segment_and_runs(golden):
     for r in golden['rows']:
         s, n = r['in'], r['norm']

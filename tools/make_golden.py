@@ -76,7 +76,7 @@ def main():
     pins = check_pins()
     if '--train' in sys.argv:
         train()
-    from akshar import normalize as RN, segment as RS
+    from akshar import normalize as RN, segment as RS, features as RF
     from akshar.tokenizer import aksharTokenizer
 
     inputs = list(HANDPICKED)
@@ -136,6 +136,9 @@ def main():
         r['words_hi'] = RS.word_tokenize_hindi(s)
         r['words_sa'] = RS.word_tokenize_sanskrit(s)
         r['words_auto'] = RS.word_tokenize(s)
+        # the feature wrappers that are functions of the cluster boundaries (features.py:28-55, 173-206)
+        r['feat_akshara'] = RF.akshara_level_tokenization(s)
+        r['feat_nukta'] = RF.preserve_nukta(s)
         rows.append(r)
     sig = {w: RN.roman_phonetic_signature(w) for w in SIG_WORDS}
     words = set()
