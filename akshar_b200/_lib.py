@@ -19,14 +19,14 @@ WORDS_HINDI, WORDS_SPLIT = 0, 1
 FORM_DECODE, FORM_DETOKENIZE = 0, 1
 MERGE_AKSHARA, MERGE_NUKTA = 0, 1
 TIMERS = {'ak_nf3_classify_kernel': 0, 'ak_nf_write_kernel': 1, 'ak_resolve_kernel<bpe>': 2, 'ak_sf3_kernel': 3,
-          'ak_resolve_kernel<unigram>': 4, 'ak_words_kernel': 5, 'ak_emit_kernel': 6, 'ak_wtok_kernel': 7, 'ak_dec_kernel': 8}
+          'ak_resolve_kernel<unigram>': 4, 'ak_words_kernel': 5, 'ak_emit_kernel': 6, 'ak_wtok_kernel': 7, 'ak_dec_kernel': 8, 'ak_lines_kernel': 9}
 
 SYMBOLS = (
     'akshar_version', 'akshar_status_str', 'akshar_ctx_create', 'akshar_ctx_destroy', 'akshar_last_error',
     'akshar_workspace_bytes', 'akshar_normalize_batch', 'akshar_segment_batch', 'akshar_signature_batch',
     'akshar_load_bpe_json', 'akshar_load_spm_model', 'akshar_vocab_size', 'akshar_vocab_token',
     'akshar_encode_bpe_batch', 'akshar_encode_unigram_batch', 'akshar_tokenizer_encode_batch', 'akshar_tokenizer_encode_batch_ex',
-    'akshar_launch_count', 'akshar_timing_enable', 'akshar_timing_read', 'akshar_word_cache_hold', 'akshar_word_tokenize_batch', 'akshar_decode_workspace_bytes', 'akshar_decode_batch', 'akshar_composition_batch', 'akshar_merge_workspace_bytes', 'akshar_merge_clusters_batch',
+    'akshar_launch_count', 'akshar_timing_enable', 'akshar_timing_read', 'akshar_word_cache_hold', 'akshar_word_tokenize_batch', 'akshar_decode_workspace_bytes', 'akshar_decode_batch', 'akshar_composition_batch', 'akshar_merge_workspace_bytes', 'akshar_merge_clusters_batch', 'akshar_lines_workspace_bytes', 'akshar_lines_batch', 'akshar_join_rows',
 )
 
 _lib = None
@@ -69,6 +69,10 @@ def load():
     L.akshar_merge_workspace_bytes.argtypes = [i64]
     L.akshar_merge_workspace_bytes.restype = sz
     L.akshar_merge_clusters_batch.argtypes = [vp, vp, vp, i64, vp, vp, i64, i32, vp, i64, vp, vp, vp, sz, vp]
+    L.akshar_lines_workspace_bytes.argtypes = [i64, i64]
+    L.akshar_lines_workspace_bytes.restype = sz
+    L.akshar_lines_batch.argtypes = [vp, vp, i64, vp, i64, vp, i64, vp, vp, sz, vp]
+    L.akshar_join_rows.argtypes = [vp, vp, vp, i64, i32, vp, vp]
     L.akshar_load_bpe_json.argtypes = [vp, c.c_char_p, sz]
     L.akshar_load_spm_model.argtypes = [vp, c.c_char_p, sz]
     L.akshar_vocab_size.argtypes = [vp, i32]

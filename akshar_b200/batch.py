@@ -273,6 +273,44 @@ class Engine:
             return out + (fl[:b.n_rows],) if row_flags else out
         raise BatchStatusError(bits, 'word_tokenize_batch (retries exhausted)')
 
+    # ------------------------------------------------------------------ file bytes -> rows
+    def lines_batch(self, d_file, n_bytes, row_capacity=None):
+        """the lines of a text file as rows (reference cli.py:165-190: readlines / strip / skip empty) from the file's bytes
+        on the device -> TextBatch"""
+        dev = self.device
+        rcap = row_capacity if row_capacity is not None else n_bytes // 24 + 1024
+        for _ in range(self.MAX_TRIES):
+            need = self.lib.akshar_lines_workspace_bytes(n_bytes, rcap)
+            if self._ws is None or self._ws.numel() < need:
+                self._ws = None
+                self._ws = torch.empty(need + (need >> 3), dtype=torch.uint8, device=dev)
+            ws = self._ws
+            out = torch.empty(max(n_bytes, 1), dtype=torch.uint8, device=dev)
+            off = torch.empty(rcap + 1, dtype=torch.int64, device=dev)
+            result = torch.empty(4, dtype=torch.int64, device=dev)
+            rc = self.lib.akshar_lines_batch(self._h, d_file.data_ptr(), n_bytes, out.data_ptr(), n_bytes, off.data_ptr(), rcap,
+                                             result.data_ptr(), ws.data_ptr(), ws.numel(), self._stream())
+            if rc != 0:
+                self._err(rc, 'akshar_lines_batch')
+            r = result.cpu()
+            rows, total, bits = int(r[0]), int(r[1]), int(r[2])
+            if bits & C.ST_OVERFLOW:
+                rcap = rows
+                continue
+            if bits:
+                raise BatchStatusError(bits, 'lines_batch')
+            return TextBatch(out, off[:rows + 1], 0, total)
+        raise BatchStatusError(bits, 'lines_batch (retries exhausted)')
+
+    def join_rows(self, batch, sep=0x0A):
+        """every row followed by `sep`, as one uint8 tensor on the device (the file preprocess_corpus writes)"""
+        b = self.put(batch)
+        out = torch.empty(max(b.n_bytes + b.n_rows, 1), dtype=torch.uint8, device=self.device)
+        rc = self.lib.akshar_join_rows(self._h, b.data.data_ptr(), b.offsets.data_ptr(), b.n_rows, sep, out.data_ptr(), self._stream())
+        if rc != 0:
+            self._err(rc, 'akshar_join_rows')
+        return out[:b.n_bytes + b.n_rows]
+
     # ------------------------------------------------------------------ per-sentence statistics, cluster merging
     def composition_batch(self, batch):
         """-> int32 [n_rows, 5] on the device: akshars, script runs, code points, code points in devanagari / roman runs"""

@@ -37,6 +37,7 @@
 #include "ak_wtok_kernels.cuh"
 #include "ak_decode_kernels.cuh"
 #include "ak_feat_kernels.cuh"
+#include "ak_lines_kernels.cuh"
 
 // ================================================================================================
 // host side: context, model upload, C ABI
@@ -829,6 +830,93 @@ int akshar_merge_clusters_batch(akshar_ctx* ctx, const uint8_t* d_text, const in
     if ((rc = ak_after_launch(ctx, "merge-scan"))) return rc;
     ak_cm_kernel<true><<<ak_grid(ctx, 8, (int)(n_tiles > 0 ? n_tiles : 1)), AKCM_THREADS, 0, s>>>(A);
     return ak_after_launch(ctx, "merge-write");
+}
+
+// ---- file bytes -> rows -----------------------------------------------------------------------------------------------
+struct AkLinesWs {
+    size_t fn, begin, end, len, state, total;
+};
+static AkLinesWs ak_lines_ws(int64_t n_bytes, int64_t row_capacity) {
+    AkLinesWs W;
+    const size_t tiles = (size_t)(n_bytes / AKLN_TILE + 2);
+    W.fn = 256;
+    W.begin = W.fn + ak_align(tiles * sizeof(AkLineFn));
+    W.end = W.begin + ak_align(((size_t)row_capacity + 1) * 8);
+    W.len = W.end + ak_align(((size_t)row_capacity + 1) * 8);
+    W.state = W.len + ak_align(((size_t)row_capacity + 1) * 4);
+    W.total = W.state + ak_align(((size_t)row_capacity / AKS_TILE + 2) * 8);
+    return W;
+}
+
+size_t akshar_lines_workspace_bytes(int64_t n_bytes, int64_t row_capacity) {
+    if (n_bytes < 0 || row_capacity < 0) return 0;
+    return ak_lines_ws(n_bytes, row_capacity).total;
+}
+
+int akshar_lines_batch(akshar_ctx* ctx, const uint8_t* d_file, int64_t n_bytes, uint8_t* d_out_text, int64_t out_capacity,
+                       int64_t* d_out_row_offsets, int64_t row_capacity, int64_t* d_result, void* d_workspace, size_t workspace_bytes,
+                       void* stream) {
+    if (!ctx) return AKSHAR_E_ARG;
+    AkDeviceGuard device_guard(ctx->device);
+    if (n_bytes < 0 || (!d_file && n_bytes > 0) || out_capacity < 0 || (!d_out_text && out_capacity > 0) || !d_out_row_offsets ||
+        row_capacity < 0 || !d_result) {
+        ctx->err = "bad argument";
+        return AKSHAR_E_ARG;
+    }
+    const AkLinesWs W = ak_lines_ws(n_bytes, row_capacity);
+    if (!d_workspace || workspace_bytes < W.total) {
+        ctx->err = "workspace too small: need " + std::to_string(W.total) + " bytes";
+        return AKSHAR_E_WORKSPACE;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    char* ws = (char*)d_workspace;
+    int rc;
+    AK_CUDA(ctx, cudaMemsetAsync(ws, 0, 256, s));
+    AK_CUDA(ctx, cudaMemsetAsync(ws + W.state, 0, W.total - W.state, s));
+    AK_CUDA(ctx, cudaMemsetAsync(d_result, 0, 4 * sizeof(int64_t), s));
+    AkLinesArgs A;
+    A.text = d_file;
+    A.n = n_bytes;
+    A.n_tiles = n_bytes / AKLN_TILE + 1;
+    A.tile_fn = (AkLineFn*)(ws + W.fn);
+    A.begin = (int64_t*)(ws + W.begin);
+    A.end = (int64_t*)(ws + W.end);
+    A.cap = row_capacity;
+    A.result = d_result;
+    const int grid = ak_grid(ctx, 8, (int)((A.n_tiles + 7) / 8));
+    ak_lines_kernel<false><<<grid, 256, 0, s>>>(A);
+    if ((rc = ak_after_launch(ctx, "lines-summaries"))) return rc;
+    ak_lines_resolve_kernel<<<1, 1024, 0, s>>>(A);
+    if ((rc = ak_after_launch(ctx, "lines-resolve"))) return rc;
+    {
+        AkTimed tm(ctx, AKSHAR_TIMER_LINES, s);
+        ak_lines_kernel<true><<<grid, 256, 0, s>>>(A);
+    }
+    if ((rc = ak_after_launch(ctx, "lines-emit"))) return rc;
+    int32_t* len = (int32_t*)(ws + W.len);
+    const int rgrid = ak_grid(ctx, 8, (int)((row_capacity + 255) / 256));
+    ak_lines_len_kernel<<<rgrid, 256, 0, s>>>(A.begin, A.end, row_capacity, len, d_result);
+    if ((rc = ak_after_launch(ctx, "lines-lengths"))) return rc;
+    ak_scan_counts_kernel<<<ak_grid(ctx, 4, (int)(row_capacity / AKS_TILE + 1)), AKS_THREADS, 0, s>>>(
+        len, 0, (const long long*)(d_result + 3), 1, d_out_row_offsets, d_result + 1, (int*)ws, (unsigned long long*)(ws + W.state),
+        (unsigned int*)&d_result[2]);
+    if ((rc = ak_after_launch(ctx, "lines-scan"))) return rc;
+    ak_lines_gather_kernel<<<ak_grid(ctx, 8, (int)((row_capacity + 7) / 8)), 256, 0, s>>>(d_file, A.begin, len, d_out_row_offsets, d_out_text,
+                                                                                         out_capacity, d_result);
+    return ak_after_launch(ctx, "lines-gather");
+}
+
+int akshar_join_rows(akshar_ctx* ctx, const uint8_t* d_text, const int64_t* d_row_offsets, int64_t n_rows, int sep, uint8_t* d_out,
+                     void* stream) {
+    if (!ctx) return AKSHAR_E_ARG;
+    AkDeviceGuard device_guard(ctx->device);
+    if (!d_row_offsets || n_rows < 0 || sep < 0 || sep > 255 || (n_rows > 0 && !d_out)) {
+        ctx->err = "bad argument";
+        return AKSHAR_E_ARG;
+    }
+    if (n_rows == 0) return AKSHAR_OK;
+    ak_join_rows_kernel<<<ak_grid(ctx, 8, (int)((n_rows + 7) / 8)), 256, 0, (cudaStream_t)stream>>>(d_text, d_row_offsets, n_rows, (uint8_t)sep, d_out);
+    return ak_after_launch(ctx, "join-rows");
 }
 
 int akshar_signature_batch(akshar_ctx* ctx, const uint8_t* d_text, const int64_t* d_row_offsets, int64_t n_rows,

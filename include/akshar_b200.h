@@ -145,6 +145,21 @@ int akshar_merge_clusters_batch(akshar_ctx* ctx, const uint8_t* d_text, const in
                                 int32_t* d_out_ends, int64_t out_capacity, int64_t* d_out_splits, int64_t* d_result,
                                 void* d_workspace, size_t workspace_bytes, void* stream);
 
+/* The lines of a text file as rows (cli.py:165-190 = scripts/train_bpe.py:16-35 = train_spm.py:18-44: `readlines()` of a
+ * universal-newlines text file, `strip()`, empty lines skipped).  d_file: the file's bytes (valid UTF-8; Python would raise
+ * on anything else) on the device.  Output: the rows packed next to each other + int64 [rows + 1] row offsets -- the form
+ * every other entry point takes.  result[0] = rows (exact also when AKSHAR_ST_OVERFLOW says row_capacity or out_capacity
+ * was too small), result[1] = packed bytes. */
+size_t akshar_lines_workspace_bytes(int64_t n_bytes, int64_t row_capacity);
+int akshar_lines_batch(akshar_ctx* ctx, const uint8_t* d_file, int64_t n_bytes, uint8_t* d_out_text, int64_t out_capacity,
+                       int64_t* d_out_row_offsets, int64_t row_capacity, int64_t* d_result, void* d_workspace, size_t workspace_bytes,
+                       void* stream);
+
+/* rows -> one byte stream, every row followed by the byte `sep`: the file preprocess_corpus writes (cli.py:185-187).
+ * d_out holds (row_offsets[n_rows] - row_offsets[0]) + n_rows bytes. */
+int akshar_join_rows(akshar_ctx* ctx, const uint8_t* d_text, const int64_t* d_row_offsets, int64_t n_rows, int sep, uint8_t* d_out,
+                     void* stream);
+
 /* roman_phonetic_signature over a batch of words (normalize.py:59-89); one word per row. result[0] = out bytes */
 int akshar_signature_batch(akshar_ctx* ctx, const uint8_t* d_text, const int64_t* d_row_offsets, int64_t n_rows,
                            int64_t text_begin, int64_t text_end, uint8_t* d_out_text, int64_t out_capacity,
@@ -211,7 +226,8 @@ enum {
     AKSHAR_TIMER_EMIT = 6,                 /* ak_emit_kernel (ids to their final place) */
     AKSHAR_TIMER_WORDTOK = 7,              /* ak_wtok_kernel<emit> (word tokenizers) */
     AKSHAR_TIMER_DECODE = 8,               /* ak_dec_kernel<write> (ids -> text) */
-    AKSHAR_TIMER_COUNT = 9
+    AKSHAR_TIMER_LINES = 9,                /* ak_lines_kernel<emit> (file bytes -> rows) */
+    AKSHAR_TIMER_COUNT = 10
 };
 int akshar_timing_enable(akshar_ctx* ctx, int enable);
 

@@ -468,6 +468,26 @@ def analyze_text_composition(text):
 
 
 # --------------------------------------------------------------------------------------------------
+# f1  the rows of a text file (reference cli.py:165-190 = scripts/train_bpe.py:16-35 = scripts/train_spm.py:18-44)
+# --------------------------------------------------------------------------------------------------
+def file_rows(data):
+    """`open(path, 'r', encoding='utf-8').readlines()`, `strip()`, empty lines skipped -- from the file's bytes.  A text-mode
+    file translates '\\r\\n' and a lone '\\r' to '\\n' (universal newlines) and readlines() cuts after every '\\n'."""
+    text = bytes(data).decode('utf-8').replace('\r\n', '\n').replace('\r', '\n')
+    rows = []
+    for line in text.split('\n'):
+        k = len(line)
+        i = 0
+        while i < k and ord(line[i]) in _PY_SPACE:
+            i += 1
+        while k > i and ord(line[k - 1]) in _PY_SPACE:
+            k -= 1
+        if k > i:
+            rows.append(line[i:k])
+    return rows
+
+
+# --------------------------------------------------------------------------------------------------
 # f4  the feature wrappers that are functions of the cluster boundaries (reference features.py:28-55, 173-206)
 # --------------------------------------------------------------------------------------------------
 def akshara_level_tokenization(text):

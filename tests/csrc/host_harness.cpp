@@ -14,6 +14,7 @@
 #include "../../akshar_b200/csrc/ak_bpe3.cuh"
 #include "../../akshar_b200/csrc/ak_tok.cuh"
 #include "../../akshar_b200/csrc/ak_wordtok.cuh"
+#include "../../akshar_b200/csrc/ak_lines.cuh"
 #include "../../akshar_b200/csrc/ak_tok_host.h"
 #include "../../akshar_b200/csrc/ak_decode_host.h"
 #include "../../akshar_b200/csrc/ak_models.h"
@@ -347,6 +348,25 @@ int64_t hh_wordtok(const uint8_t* text, const int64_t* off, int64_t n_rows, int 
     }
     *status = st;
     return total;
+}
+
+// file bytes -> rows (ak_lines.cuh) with the kernels' structure: per-thread transducers over `span`-byte stretches, composed
+// in order, then the emit pass with the entry states; returns the number of rows
+int64_t hh_lines(const uint8_t* text, int64_t n, int span, int64_t* begin, int64_t* end, int64_t cap, uint32_t* status) {
+    uint32_t st = 0;
+    const int64_t n_spans = n / span + 1;
+    std::vector<AkLineFn> fn((size_t)n_spans);
+    for (int64_t k = 0; k < n_spans; ++k) fn[(size_t)k] = akl_span(text, k * span, (k + 1) * span, n, false, 0u, -1, 0, nullptr, nullptr, 0, st);
+    AkLineFn acc = akl_identity();
+    int64_t rows = 0;
+    for (int64_t k = 0; k < n_spans; ++k) {
+        const uint32_t state = acc.s & 1u;                      // the file starts in state 0
+        akl_span(text, k * span, (k + 1) * span, n, true, state, acc.lastk, acc.cnt0, begin, end, cap, st);
+        acc = akl_compose(acc, fn[(size_t)k]);
+    }
+    rows = acc.cnt0;
+    *status = st;
+    return rows;
 }
 
 // roman_phonetic_signature of every row; returns output bytes

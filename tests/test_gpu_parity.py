@@ -514,22 +514,44 @@ def test_raw_mode_golden(A, golden_raw, models_dir):
 
 
 def test_corpus_front_end(A, models_dir, tmp_path):
+    """the file front end (reference cli.py:46-84, 165-190): lines are found, stripped and dropped when empty ON THE DEVICE
+    from the file's bytes (akshar_lines_batch); the file is read in pieces into pinned memory, no Python per line"""
     from akshar_b200 import corpus
     lines = sc.Corpus('social', 31).lines(400000)
     src = tmp_path / 'corpus.txt'
-    src.write_text('\n'.join(['  ' + l + ' \t' if i % 7 == 0 else l for i, l in enumerate(lines)]) + '\n\n  \n', encoding='utf-8')
+    seps = ['\n', '\r\n', '\r', '\n\n', '\n \t\n', '\n\u3000\n']
+    body = ''.join((('  ' + l + ' \t') if i % 7 == 0 else ('\u00a0' + l + '\u2003') if i % 11 == 0 else l) + seps[i % len(seps)]
+                   for i, l in enumerate(lines))
+    src.write_bytes((body + '\n\n  \n' + 'last line without newline').encode('utf-8'))
+    with open(src, 'r', encoding='utf-8') as f:
+        ref_rows = [ln.strip() for ln in f.readlines() if ln.strip()]
+    assert corpus.read_rows(str(src)) == ref_rows
+    # pieces of 64 KiB: rows never straddle pieces; a single 300 KB line makes the reader grow its buffers
+    big = tmp_path / 'big.txt'
+    big.write_bytes(('x' * 300000 + '\n' + body).encode('utf-8'))
+    got = []
+    for rows in corpus.stream_rows(str(big), chunk_bytes=1 << 16):
+        got.extend(rows.to_strings())
+    assert got == ['x' * 300000] + ref_rows[:-1]
     out = tmp_path / 'corpus.preprocessed.txt'
-    corpus.preprocess_corpus(str(src), str(out))
-    exp = [O.normalize_text(l.strip()) for l in src.read_text(encoding='utf-8').split('\n') if l.strip()]
-    assert out.read_text(encoding='utf-8') == ''.join(e + '\n' for e in exp)
+    corpus.preprocess_corpus(str(src), str(out), chunk_bytes=1 << 17)
+    exp = [O.normalize_text(l) for l in ref_rows]
+    assert out.read_bytes().decode('utf-8') == ''.join(e + '\n' for e in exp)
+    empty = tmp_path / 'empty.txt'
+    empty.write_bytes(b'')
+    assert corpus.read_rows(str(empty)) == []
+    corpus.preprocess_corpus(str(empty), str(out))
+    assert out.read_bytes() == b''
     # the whole file as ONE string, like `akshar tokenize -i FILE --format id` (one long row for the kernels)
     tk = A.aksharTokenizer(os.path.join(models_dir, 'bpe24k.json'), 'bpe')
     om = O.BpeModel(os.path.join(models_dir, 'bpe24k.json'))
-    text = src.read_text(encoding='utf-8')
+    with open(src, 'r', encoding='utf-8') as f:
+        text = f.read()
     assert corpus.tokenize_file(tk, str(src), 'id') == ' '.join(map(str, O.bpe_encode(om, O.normalize_text(text))))
     fb = A.aksharTokenizer()
     assert corpus.tokenize_file(fb, str(src), 'text') == ' '.join(O.segment_akshars(O.normalize_text(text)))
-    assert corpus.encode_lines(tk, str(src))[:50] == [O.bpe_encode(om, e) for e in exp[:50]]
+    enc = corpus.encode_lines(tk, str(src), chunk_bytes=1 << 17)
+    assert len(enc) == len(exp) and enc[:50] == [O.bpe_encode(om, e) for e in exp[:50]] and enc[-1] == O.bpe_encode(om, exp[-1])
 
 
 def test_full_size_bpe_1gib(A, models_dir):

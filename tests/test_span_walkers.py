@@ -377,3 +377,29 @@ def test_word_tokenizer_fuzz():
         _words_check(lines, real)
     _words_check(['', '', '।', '', 'a' * 200, '', ' ' * 100, '॥' * 50, 'a।', '।a', ''], 30)
     _words_check(['क' * 31 + '।', 'ab' + '।' * 10 + 'c', 'x' * 29 + '।' + 'y'], 30)           # danda across lanes
+
+
+# ---- file bytes -> rows (ak_lines.cuh; reference cli.py:165-190) -----------------------------------------------------
+def test_file_rows_like_readlines_and_strip(tmp_path):
+    rng = np.random.default_rng(3)
+    alpha = ['a', 'b', ' ', ' ', '\n', '\n', '\r', '\r\n', '\t', '\x0b', '\x0c', '\x1c', '\x1d', '\x1e', '\x1f', '\x85', '\xa0', '\u1680',
+             '\u2000', '\u200a', '\u200b', '\u2028', '\u2029', '\u202f', '\u205f', '\u3000', '\u0915', '\u093e', '\U0001F600', '\ufeff', 'x y']
+    for trial in range(60):
+        n = int(rng.integers(0, 400))
+        if trial % 3 == 0:
+            s = ''.join(alpha[int(i)] for i in rng.integers(0, len(alpha), size=n))
+        else:
+            s = ''
+            while len(s) < n:
+                s += alpha[int(rng.integers(len(alpha)))] * int(rng.integers(1, 50))
+        data = s.encode('utf-8')
+        exp = O.file_rows(data)
+        # the restatement against Python's own text-mode file
+        p = tmp_path / 'f.txt'
+        p.write_bytes(data)
+        with open(p, 'r', encoding='utf-8') as f:
+            assert [ln.strip() for ln in f.readlines() if ln.strip()] == exp
+        for span in (32, 1, 5, 1000):
+            assert [r.decode('utf-8') for r in W.lines(data, span=span)] == exp
+    for s in ('', '\n', 'a', 'a\n', '\na', ' a ', '\r\r\n\r', 'a\rb\r\nc\n\nd', ' ' * 100 + 'a' + ' ' * 100, '\u3000\u0915\u3000', 'a' * 100):
+        assert [r.decode('utf-8') for r in W.lines(s.encode('utf-8'))] == O.file_rows(s.encode('utf-8'))

@@ -183,6 +183,21 @@ def seg_fast3(data, off, flags=1, real=30):
     return ce[:tot[0]], cs, re_[:tot[1]], rt[:tot[1]], rs, st.value, ns.value
 
 
+def lines(data, span=32):
+    """file bytes -> rows (ak_lines.cuh) on the CPU -> list[bytes]"""
+    data = np.ascontiguousarray(np.frombuffer(data, dtype=np.uint8) if isinstance(data, (bytes, bytearray)) else data, dtype=np.uint8)
+    pad = np.concatenate([data, np.zeros(8, dtype=np.uint8)])
+    cap = int(data.size) + 2
+    b = np.zeros(cap, dtype=np.int64)
+    e = np.zeros(cap, dtype=np.int64)
+    st = ctypes.c_uint32(0)
+    lib().hh_lines.restype = ctypes.c_int64
+    n = lib().hh_lines(_p(pad), ctypes.c_int64(data.size), ctypes.c_int(span), _p(b), _p(e), ctypes.c_int64(cap), ctypes.byref(st))
+    assert st.value == 0
+    raw = data.tobytes()
+    return [raw[b[i]:e[i]] for i in range(n)]
+
+
 def wordtok(data, off, mode=0, real=30):
     """the word tokenizers (ak_wordtok.cuh) through the kernel's lane structure -> (begin, end, splits, row_flags, status)"""
     data = np.ascontiguousarray(data, dtype=np.uint8)
