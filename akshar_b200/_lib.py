@@ -12,7 +12,7 @@ LIB_PATH = os.environ.get('AKSHAR_B200_LIB') or os.path.join(_HERE, 'lib', 'liba
 OK, E_ARG, E_CUDA, E_MODEL, E_NOMODEL, E_WORKSPACE = 0, -1, -2, -3, -4, -5
 ST_OVERFLOW, ST_NFC_SEGMENT, ST_PATHOLOGICAL, ST_ALPHABET, ST_SPIN, ST_WORD, ST_INTERNAL, ST_BAD_ID = 1, 2, 4, 8, 16, 32, 64, 128
 NORM_ROMAN, NORM_FILTER, NORM_COLLAPSE, NORM_CLEAN, NORM_NO_NFC = 1, 2, 4, 6, 8
-SEG_CLUSTERS, SEG_MATRAS, SEG_RUNS = 1, 2, 4
+SEG_CLUSTERS, SEG_MATRAS, SEG_RUNS, SEG_MASK = 1, 2, 4, 8
 MODE_TILES, MODE_ROWS = 0, 1
 OUT_IDS_U16, OUT_SPLITS_I32 = 1, 2
 WORDS_HINDI, WORDS_SPLIT = 0, 1

@@ -384,6 +384,28 @@ class Engine:
             return TextBatch(out, out_off, 0, total)
         raise BatchStatusError(bits, 'decode_batch (retries exhausted)')
 
+    def segment_masks(self, batch, clusters=True, matras=False, runs=False, out=None):
+        """segment_batch with AKSHAR_SEG_MASK: the boundaries as bit masks, one bit per text byte (bit p - begin set when a
+        cluster / run ends at byte p) -> dict(cluster=uint32 [W] | None, run=uint32 [W] | None, tags=uint32 [2, W] | None,
+        n_clusters, n_runs); W = (bytes + 32) // 32.  `out` may hold preallocated tensors under the same keys."""
+        b = self.put(batch)
+        flags = (C.SEG_CLUSTERS if clusters else 0) | (C.SEG_MATRAS if matras else 0) | (C.SEG_RUNS if runs else 0) | C.SEG_MASK
+        W = (b.n_bytes + 32) // 32
+        dev = self.device
+        out = out or {}
+        cm = (out.get('cluster') if out.get('cluster') is not None else torch.empty(W, dtype=torch.int32, device=dev)) if clusters else None
+        rm = (out.get('run') if out.get('run') is not None else torch.empty(W, dtype=torch.int32, device=dev)) if runs else None
+        tg = (out.get('tags') if out.get('tags') is not None else torch.empty((2, W), dtype=torch.int32, device=dev)) if runs else None
+        ws = self._workspace(b.n_bytes, b.n_rows)
+        result = torch.empty(4, dtype=torch.int64, device=dev)
+        p = lambda t: t.data_ptr() if t is not None else None
+        rc = self.lib.akshar_segment_batch(self._h, b.data.data_ptr(), b.offsets.data_ptr(), b.n_rows, b.begin, b.end, flags,
+                                           C.MODE_TILES, p(cm), W, None, p(rm), p(tg), W, None, result.data_ptr(),
+                                           ws.data_ptr(), ws.numel(), self._stream())
+        if rc != 0:
+            self._err(rc, 'akshar_segment_batch')
+        return {'cluster': cm, 'run': rm, 'tags': tg, 'result': result, 'words': W}
+
     # ------------------------------------------------------------------ K1b
     def signature_batch(self, batch):
         """roman_phonetic_signature over a batch of words, one per row (reference normalize.py:59-89) -> TextBatch"""

@@ -516,6 +516,38 @@ int akshar_segment_batch(akshar_ctx* ctx, const uint8_t* d_text, const int64_t* 
                       stream, C);
     if (rc) return rc;
     const bool want_c = (flags & AKSHAR_SEG_CLUSTERS) != 0, want_r = (flags & AKSHAR_SEG_RUNS) != 0;
+    if (flags & AKSHAR_SEG_MASK) {
+        // boundaries as bit masks: d_cluster_ends / d_run_ends receive mask words, d_run_tags the two tag planes
+        const int64_t n_words = (text_end - text_begin + 32) / 32;
+        if ((flags & ~15u) || (!want_c && !want_r) || ((flags & AKSHAR_SEG_MATRAS) && !want_c) || mode != AKSHAR_MODE_TILES ||
+            (want_c && (!d_cluster_ends || cluster_capacity < n_words)) ||
+            (want_r && (!d_run_ends || !d_run_tags || run_capacity < n_words))) {
+            ctx->err = "bad argument (AKSHAR_SEG_MASK: tile mode, capacities in 32-bit words >= (bytes + 32) / 32)";
+            return AKSHAR_E_ARG;
+        }
+        AkSegMaskArgs M;
+        M.B = C.B;
+        M.T = ctx->T;
+        M.flags = flags & 7u;
+        M.shift = (int)(((uintptr_t)d_text + (uintptr_t)text_begin) & 15u);
+        M.base0 = text_begin - M.shift;
+        M.cmask = (uint32_t*)d_cluster_ends;
+        M.rmask = (uint32_t*)d_run_ends;
+        M.t0 = (uint32_t*)d_run_tags;
+        M.t1 = M.t0 ? M.t0 + n_words : nullptr;
+        M.n_words = n_words;
+        const int64_t n_wt = (text_end - M.base0 + AKN3_WARP_BYTES) / AKN3_WARP_BYTES;
+        int64_t* wrow = (int64_t*)(C.ws + C.L.scratch);
+        M.wrow = wrow;
+        const int entries = (int)(n_wt * 2 + 3);
+        ak_warp_rows_kernel<<<(entries + 255) / 256, 256, 0, C.stream>>>(C.B, M.base0, entries, wrow);
+        if ((rc = ak_after_launch(ctx, "segment-warp-rows"))) return rc;
+        {
+            AkTimed tm(ctx, AKSHAR_TIMER_SEGMENT, C.stream);
+            ak_seg_mask_kernel<<<ak_grid(ctx, 8, (int)((n_wt + AKSM_THREADS / 32 - 1) / (AKSM_THREADS / 32))), AKSM_THREADS, 0, C.stream>>>(M);
+        }
+        return ak_after_launch(ctx, "segment-mask");
+    }
     if ((flags & ~7u) || (!want_c && !want_r) || ((flags & AKSHAR_SEG_MATRAS) && !want_c) ||
         (want_c && (!d_cluster_splits || cluster_capacity < 0 || (!d_cluster_ends && cluster_capacity > 0))) ||
         (want_r && (!d_run_splits || run_capacity < 0 || ((!d_run_ends || !d_run_tags) && run_capacity > 0)))) {

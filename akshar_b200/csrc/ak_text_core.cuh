@@ -408,7 +408,31 @@ struct AkSegOut {
     int64_t* run_splits;       // [n_rows + 1]
     int64_t cbase, rbase;      // global index of this span's first cluster / run
     int64_t ccap, rcap;        // capacities (writes beyond are dropped; counts stay exact)
+    // AKSHAR_SEG_MASK: instead of the arrays above, the events of a (32-byte) lane as bits relative to lane_base:
+    // lane_masks[0] cluster ends, [1] run ends, [2] / [3] the two tag planes (see ak_seg_kernels.cuh)
+    uint32_t* lane_masks = nullptr;
+    int64_t lane_base = 0;
 };
+
+AK_HD void ak_seg_put_cluster(const AkSegOut& o, bool write, int64_t cc, int64_t p, int64_t rs) {
+    if (!write) return;
+    if (o.lane_masks) { o.lane_masks[0] |= 1u << (int)(p - o.lane_base); return; }
+    if (o.cbase + cc < o.ccap) o.cluster_ends[o.cbase + cc] = (int32_t)(p - rs);
+}
+AK_HD void ak_seg_put_run(const AkSegOut& o, bool write, int64_t rc, int64_t p, int64_t rs, uint32_t cur) {
+    if (!write) return;
+    if (o.lane_masks) {
+        const uint32_t b = 1u << (int)(p - o.lane_base);
+        o.lane_masks[1] |= b;
+        if (cur == (uint32_t)TAG_ROMAN || cur == (uint32_t)TAG_NONE) o.lane_masks[2] |= b;
+        if (cur == (uint32_t)TAG_OTHER || cur == (uint32_t)TAG_NONE) o.lane_masks[3] |= b;
+        return;
+    }
+    if (o.rbase + rc < o.rcap) {
+        o.run_ends[o.rbase + rc] = (int32_t)(p - rs);
+        o.run_tags[o.rbase + rc] = (uint8_t)cur;
+    }
+}
 
 AK_HD_NOINLINE void ak_seg_span(const AkTables& T, const uint8_t* t, const int64_t* off, int64_t n_rows, int64_t r_lo,
                                 int64_t r_hi, int64_t s, int64_t e, uint32_t flags, int64_t limit, bool write,
@@ -476,18 +500,15 @@ AK_HD_NOINLINE void ak_seg_span(const AkTables& T, const uint8_t* t, const int64
         while (nr <= n_rows && off[nr] == p) {
             if (nr > 0 && p > rs) {        // the row in progress is not empty: it ends here
                 if (want_c) {
-                    if (write && o.cbase + cc < o.ccap) o.cluster_ends[o.cbase + cc] = (int32_t)(p - rs);
+                    ak_seg_put_cluster(o, write, cc, p, rs);
                     ++cc;
                 }
                 if (want_r) {
-                    if (write && o.rbase + rc < o.rcap) {
-                        o.run_ends[o.rbase + rc] = (int32_t)(p - rs);
-                        o.run_tags[o.rbase + rc] = (uint8_t)cur;
-                    }
+                    ak_seg_put_run(o, write, rc, p, rs, cur);
                     ++rc;
                 }
             }
-            if (write) {
+            if (write && !o.lane_masks) {
                 if (want_c) o.cluster_splits[nr] = o.cbase + cc;
                 if (want_r) o.run_splits[nr] = o.rbase + rc;
             }
@@ -506,7 +527,7 @@ AK_HD_NOINLINE void ak_seg_span(const AkTables& T, const uint8_t* t, const int64
                 bool brk = ak_g_break(g, w);
                 if (matras && (g.prev_m || ak_is_matra_or_halant(cp))) brk = true;
                 if (brk) {
-                    if (write && o.cbase + cc < o.ccap) o.cluster_ends[o.cbase + cc] = (int32_t)(p - rs);
+                    ak_seg_put_cluster(o, write, cc, p, rs);
                     ++cc;
                 }
             }
@@ -516,10 +537,7 @@ AK_HD_NOINLINE void ak_seg_span(const AkTables& T, const uint8_t* t, const int64
             uint32_t tg = AK_TAG(w);
             if (tg != TAG_DIGIT && tg != TAG_PUNCT) {
                 if (cur != TAG_NONE && tg != cur) {
-                    if (write && o.rbase + rc < o.rcap) {
-                        o.run_ends[o.rbase + rc] = (int32_t)(p - rs);
-                        o.run_tags[o.rbase + rc] = (uint8_t)cur;
-                    }
+                    ak_seg_put_run(o, write, rc, p, rs, cur);
                     ++rc;
                 }
                 cur = tg;

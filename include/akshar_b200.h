@@ -64,6 +64,7 @@ enum {
 #define AKSHAR_SEG_CLUSTERS 1u   /* segment_akshars(text)               (segment.py:40-78)  */
 #define AKSHAR_SEG_MATRAS 2u     /* segment_akshars(text, matras=True)  (segment.py:80-125) */
 #define AKSHAR_SEG_RUNS 4u       /* detect_code_switches(text)          (segment.py:150-201) */
+#define AKSHAR_SEG_MASK 8u       /* the same boundaries as bit masks (tile mode only), see akshar_segment_batch */
 /* mode */
 #define AKSHAR_MODE_TILES 0      /* fixed-size byte spans, one thread per span (fast path) */
 #define AKSHAR_MODE_ROWS 1       /* one span per row (exact for any input, slow for very long rows) */
@@ -87,7 +88,12 @@ int akshar_normalize_batch(akshar_ctx* ctx, const uint8_t* d_text, const int64_t
 /* segment_akshars / detect_code_switches over a batch (segment.py:40-201).
  * cluster_ends / run_ends: int32 byte offset of each cluster / run END relative to its row start;
  * run_tags: 0 devanagari 1 roman 2 digit 3 punct 4 other 255 None (identify_script, segment.py:128-147).
- * Outputs not selected by `flags` may be NULL.  result[0] = clusters, result[1] = runs. */
+ * Outputs not selected by `flags` may be NULL.  result[0] = clusters, result[1] = runs.
+ * With AKSHAR_SEG_MASK the boundaries come as one bit per text byte instead (1/8 byte per text byte and stream rather than
+ * 4 bytes per boundary): d_cluster_ends / d_run_ends receive W = (text_end - text_begin + 32) / 32 uint32 words each
+ * (capacities are counted in words), bit (p - text_begin) set when a cluster / run ENDS at byte p (the end of a non-empty
+ * row included); d_run_tags receives 2 W words: the planes t0 then t1 of the tag of the run that ends at a bit,
+ * (t1 t0) = 00 devanagari, 01 roman, 10 other, 11 none.  The split arrays are not written (may be NULL). */
 int akshar_segment_batch(akshar_ctx* ctx, const uint8_t* d_text, const int64_t* d_row_offsets, int64_t n_rows,
                          int64_t text_begin, int64_t text_end, uint32_t flags, int mode, int32_t* d_cluster_ends,
                          int64_t cluster_capacity, int64_t* d_cluster_splits, int32_t* d_run_ends, uint8_t* d_run_tags,

@@ -168,6 +168,43 @@ def test_identify_script_full_table(A, golden):
         assert A.identify_script(ch) == golden['identify_script'][ch]
 
 
+def _mask_words(pos, n_bytes):
+    m = np.zeros(((n_bytes + 32) // 32) * 32, dtype=bool)
+    m[pos] = True
+    return np.packbits(m, bitorder='little').view(np.uint32)
+
+
+def test_segment_bit_masks(A, eng, golden):
+    """AKSHAR_SEG_MASK: the cluster / run boundaries as one bit per text byte + two tag planes == the offset form of the same
+    call, on golden rows (normalized and raw), adversarial text (slow lanes), empty rows and a text that does not start on a
+    16-byte boundary"""
+    import torch
+    sets = [[r['norm'] for r in golden['rows']], [r['in'] for r in golden['rows']],
+            ['', '', 'a', '', '\u0915\u094d\u0937', ''] + sc.adversarial(4000, 3, 60) + ['', ''], [''], ['', '', '']]
+    for lines in sets:
+        for matras in (False, True):
+            data, off = sc.pack(lines)
+            for lead in (0, 5):
+                d = torch.from_numpy(np.concatenate([np.full(lead, 32, dtype=np.uint8), data])).cuda()
+                o = torch.from_numpy(off + lead).cuda()
+                tb = A.TextBatch(d, o, lead, lead + int(off[-1]))
+                cl, ru = eng.segment_batch(tb, clusters=True, matras=matras, runs=True)
+                mk = eng.segment_masks(tb, clusters=True, matras=matras, runs=True)
+                n = int(off[-1])
+                res = _np(mk['result'])
+                assert res[2] == 0 and res[0] == cl.values.numel() and res[1] == ru.values.numel()
+                for rag, key in ((cl, 'cluster'), (ru, 'run')):
+                    sp = _np(rag.splits)
+                    row_of = np.repeat(np.arange(len(sp) - 1), np.diff(sp))
+                    pos = off[row_of] + _np(rag.values)
+                    assert np.array_equal(_np(mk[key]).view(np.uint32), _mask_words(pos, n))
+                tags = _np(ru.extra)
+                t0 = _mask_words(pos[(tags == 1) | (tags == 255)], n)
+                t1 = _mask_words(pos[(tags == 4) | (tags == 255)], n)
+                planes = _np(mk['tags']).view(np.uint32)
+                assert np.array_equal(planes[0], t0) and np.array_equal(planes[1], t1)
+
+
 def test_signature_golden(A, golden):
     words = list(golden['signature'])
     assert A.roman_phonetic_signature_batch(words) == [golden['signature'][w] for w in words]
