@@ -18,7 +18,7 @@ OUT_IDS_U16, OUT_SPLITS_I32 = 1, 2
 WORDS_HINDI, WORDS_SPLIT = 0, 1
 FORM_DECODE, FORM_DETOKENIZE = 0, 1
 MERGE_AKSHARA, MERGE_NUKTA = 0, 1
-TIMERS = {'ak_nf3_classify_kernel': 0, 'ak_nf_write_kernel': 1, 'ak_resolve_kernel<bpe>': 2, 'ak_sf3_kernel': 3,
+TIMERS = {'ak_nf3_classify_kernel': 0, 'ak_nf_write_kernel': 1, 'ak_resolve_kernel<bpe>': 2, 'ak_sf3_kernel': 3, 'ak_seg_mask_kernel': 3,
           'ak_resolve_kernel<unigram>': 4, 'ak_words_kernel': 5, 'ak_emit_kernel': 6, 'ak_wtok_kernel': 7, 'ak_dec_kernel': 8, 'ak_lines_kernel': 9}
 
 SYMBOLS = (
@@ -26,7 +26,7 @@ SYMBOLS = (
     'akshar_workspace_bytes', 'akshar_normalize_batch', 'akshar_segment_batch', 'akshar_signature_batch',
     'akshar_load_bpe_json', 'akshar_load_spm_model', 'akshar_vocab_size', 'akshar_vocab_token',
     'akshar_encode_bpe_batch', 'akshar_encode_unigram_batch', 'akshar_tokenizer_encode_batch', 'akshar_tokenizer_encode_batch_ex',
-    'akshar_launch_count', 'akshar_timing_enable', 'akshar_timing_read', 'akshar_word_cache_hold', 'akshar_word_tokenize_batch', 'akshar_decode_workspace_bytes', 'akshar_decode_batch', 'akshar_composition_batch', 'akshar_merge_workspace_bytes', 'akshar_merge_clusters_batch', 'akshar_lines_workspace_bytes', 'akshar_lines_batch', 'akshar_join_rows',
+    'akshar_launch_count', 'akshar_timing_enable', 'akshar_timing_read', 'akshar_word_cache_hold', 'akshar_word_tokenize_batch', 'akshar_decode_workspace_bytes', 'akshar_decode_batch', 'akshar_composition_batch', 'akshar_merge_workspace_bytes', 'akshar_merge_clusters_batch', 'akshar_lines_workspace_bytes', 'akshar_lines_batch', 'akshar_join_rows', 'akshar_normalize_segment_batch',
 )
 
 _lib = None
@@ -73,6 +73,7 @@ def load():
     L.akshar_lines_workspace_bytes.restype = sz
     L.akshar_lines_batch.argtypes = [vp, vp, i64, vp, i64, vp, i64, vp, vp, sz, vp]
     L.akshar_join_rows.argtypes = [vp, vp, vp, i64, i32, vp, vp]
+    L.akshar_normalize_segment_batch.argtypes = [vp, vp, vp, i64, i64, i64, u32, u32, vp, i64, vp, vp, vp, vp, i64, vp, vp, sz, vp]
     L.akshar_load_bpe_json.argtypes = [vp, c.c_char_p, sz]
     L.akshar_load_spm_model.argtypes = [vp, c.c_char_p, sz]
     L.akshar_vocab_size.argtypes = [vp, i32]

@@ -406,6 +406,172 @@ class Engine:
             self._err(rc, 'akshar_segment_batch')
         return {'cluster': cm, 'run': rm, 'tags': tg, 'result': result, 'words': W}
 
+    def normalize_segment_batch(self, batch, normalize_roman=True, clean_hinglish=True, clusters=True, matras=False, runs=True,
+                                check=True):
+        """normalize_text -> akshars / script runs in ONE library call (nothing read back in between): -> (normalized
+        TextBatch, masks dict as segment_masks returns it).  check=False: no read-back at all (the caller looks at
+        masks['result'] itself: [clusters, runs, status bits, normalized bytes])"""
+        b = self.put(batch)
+        nflags = (C.NORM_ROMAN if normalize_roman else 0) | (C.NORM_CLEAN if clean_hinglish else 0)
+        sflags = (C.SEG_CLUSTERS if clusters else 0) | (C.SEG_MATRAS if matras else 0) | (C.SEG_RUNS if runs else 0)
+        dev = self.device
+        cap = b.n_bytes + (b.n_bytes >> 3) + 1024
+        for _ in range(self.MAX_TRIES):
+            W = (cap + 32) // 32
+            ws = self._workspace(max(cap, b.n_bytes), b.n_rows)
+            out = torch.empty(max(cap, 1), dtype=torch.uint8, device=dev)
+            out_off = torch.empty(b.n_rows + 1, dtype=torch.int64, device=dev)
+            cm = torch.empty(W, dtype=torch.int32, device=dev) if clusters else None
+            rm = torch.empty(W, dtype=torch.int32, device=dev) if runs else None
+            tg = torch.empty((2, W), dtype=torch.int32, device=dev) if runs else None
+            result = torch.empty(4, dtype=torch.int64, device=dev)
+            p = lambda t: t.data_ptr() if t is not None else None
+            rc = self.lib.akshar_normalize_segment_batch(self._h, b.data.data_ptr(), b.offsets.data_ptr(), b.n_rows, b.begin, b.end,
+                                                         nflags, sflags, out.data_ptr(), cap, out_off.data_ptr(), p(cm), p(rm), p(tg), W,
+                                                         result.data_ptr(), ws.data_ptr(), ws.numel(), self._stream())
+            if rc != 0:
+                self._err(rc, 'akshar_normalize_segment_batch')
+            if not check:
+                return TextBatch(out, out_off, 0, -1), {'cluster': cm, 'run': rm, 'tags': tg, 'result': result, 'words': W}
+            r = result.cpu()
+            bits, total = int(r[2]), int(r[3])
+            if bits & C.ST_PATHOLOGICAL:
+                # a bounded look-back gave up: the two stages one after the other, the first in its row-sequential mode
+                norm = self.normalize_batch(b, normalize_roman, clean_hinglish)
+                return norm, self.segment_masks(norm, clusters, matras, runs)
+            if bits & C.ST_OVERFLOW:
+                cap = total + 1024
+                continue
+            if bits:
+                raise BatchStatusError(bits, 'normalize_segment_batch')
+            return TextBatch(out, out_off, 0, total), {'cluster': cm, 'run': rm, 'tags': tg, 'result': result, 'words': W}
+        raise BatchStatusError(bits, 'normalize_segment_batch (retries exhausted)')
+
+    def pipeline_host_pipelined(self, h_data, h_off, normalize_roman=True, clean_hinglish=True, matras=False, chunk_bytes=None):
+        """normalize_text -> akshars -> script runs of a batch held in pinned host memory, results in pinned host memory
+        (`PipelineOut`): the rows go through the device in chunks, the copy in of chunk k + 1, the kernels of chunk k and the
+        copy out of chunk k - 2 overlap on three streams.  What crosses the link back is the normalized text, its row
+        offsets and 4 bits per normalized byte of boundary masks.  The results live in buffers the engine reuses (valid
+        until the next call)."""
+        import os
+        import numpy as np
+        from . import shard
+        if chunk_bytes is None:
+            chunk_bytes = int(os.environ.get('AKSHAR_CHUNK_MB', '64')) << 20
+        dev = self.device
+        n_rows = h_off.numel() - 1
+        off_np = h_off.numpy()
+        total_bytes = int(off_np[-1] - off_np[0])
+        n_chunks = max(1, (total_bytes + chunk_bytes - 1) // chunk_bytes)
+        ranges = [r for r in shard.shard_rows(off_np, n_chunks) if r[1] > r[0]] or [(0, 0)]
+        max_b = max(int(off_np[hi] - off_np[lo]) for lo, hi in ranges)
+        max_r = max(hi - lo for lo, hi in ranges)
+        nflags = (C.NORM_ROMAN if normalize_roman else 0) | (C.NORM_CLEAN if clean_hinglish else 0)
+        sflags = C.SEG_CLUSTERS | C.SEG_RUNS | (C.SEG_MATRAS if matras else 0)
+        ncap = max_b + (max_b >> 3) + 1024
+        W = (ncap + 32) // 32
+        ws = self._workspace(ncap, max_r)
+        pc = self.__dict__.setdefault('_pipe2_cache', {})
+        est_b = total_bytes + (total_bytes >> 4) + 4096
+        est_w = (est_b + 32) // 32 + len(ranges) + 8
+        if pc.get('norm') is None or pc['norm'].numel() < est_b or pc['off'].numel() != n_rows + 1 or pc['masks'].shape[1] < est_w:
+            pc['norm'] = torch.empty(est_b, dtype=torch.uint8).pin_memory()
+            pc['off'] = torch.empty(n_rows + 1, dtype=torch.int64).pin_memory()
+            pc['masks'] = torch.empty((4, est_w), dtype=torch.int32).pin_memory()
+        h_norm, h_noff, h_masks = pc['norm'], pc['off'], pc['masks']
+        if 'streams' not in pc:
+            pc['streams'] = tuple(torch.cuda.Stream(device=dev) for _ in range(3))
+        s_in, s_comp, s_out = pc['streams']
+        NSETS = 3
+        key = (max_b, max_r)
+        sets = pc.get('sets') if pc.get('sets_key') == key else None
+        if sets is None:
+            sets = [{
+                'text': torch.empty(max(max_b, 1), dtype=torch.uint8, device=dev),
+                'off': torch.empty(max_r + 1, dtype=torch.int64, device=dev),
+                'norm': torch.empty(max(ncap, 1), dtype=torch.uint8, device=dev),
+                'norm_off': torch.empty(max_r + 1, dtype=torch.int64, device=dev),
+                'masks': torch.empty((4, W), dtype=torch.int32, device=dev),
+                'result': torch.empty(4, dtype=torch.int64, device=dev),
+                'ev_in': torch.cuda.Event(), 'ev_comp': torch.cuda.Event(), 'ev_out': torch.cuda.Event(),
+            } for _ in range(NSETS)]
+        pc['sets'], pc['sets_key'] = sets, key
+        cur = torch.cuda.current_stream(dev)
+        for st in (s_in, s_comp, s_out):
+            st.wait_stream(cur)
+        chunk_rows = np.array([lo for lo, _ in ranges] + [n_rows], dtype=np.int64)
+        chunk_b = np.zeros(len(ranges) + 1, dtype=np.int64)
+        chunk_w = np.zeros(len(ranges) + 1, dtype=np.int64)
+        state = {'b': 0, 'w': 0, 'c': 0, 'r': 0}
+
+        def finish(k):
+            lo, hi = ranges[k]
+            S = sets[k % NSETS]
+            with torch.cuda.stream(s_out):
+                s_out.wait_event(S['ev_comp'])
+                r = S['result'].cpu()
+                bits, nb = int(r[2]), int(r[3])
+                norm, noff, masks = S['norm'], S['norm_off'], S['masks']
+                nc, nr = int(r[0]), int(r[1])
+                if bits:
+                    # this chunk again through the plain path (larger capacities / the row-sequential normalizer)
+                    self.redone_chunks = getattr(self, 'redone_chunks', 0) + 1
+                    b0, b1 = int(off_np[lo]), int(off_np[hi])
+                    nbatch, mk = self.normalize_segment_batch((h_data[b0:b1], h_off[lo:hi + 1] - b0), normalize_roman, clean_hinglish,
+                                                              True, matras, True)
+                    rr = mk['result'].cpu()
+                    nc, nr, nb = int(rr[0]), int(rr[1]), nbatch.end
+                    norm, noff = nbatch.data, nbatch.offsets
+                    masks = torch.stack([mk['cluster'], mk['run'], mk['tags'][0], mk['tags'][1]])
+                nw = (nb + 32) // 32
+                if state['b'] + nb > h_norm.numel() or state['w'] + nw > h_masks.shape[1]:
+                    raise BatchStatusError(C.ST_OVERFLOW, 'pipeline_host_pipelined: the normalized text grew beyond the pinned result buffers')
+                h_norm[state['b']:state['b'] + nb].copy_(norm[:nb], non_blocking=True)
+                h_noff[lo + 1:hi + 1].copy_(noff[1:hi - lo + 1] + state['b'], non_blocking=True)
+                h_masks[:, state['w']:state['w'] + nw].copy_(masks[:, :nw], non_blocking=True)
+                S['ev_out'].record(s_out)
+                chunk_b[k], chunk_w[k] = state['b'], state['w']
+                state['b'] += nb
+                state['w'] += nw
+                state['c'] += nc
+                state['r'] += nr
+
+        h_noff[0] = 0
+        try:
+            for k, (lo, hi) in enumerate(ranges):
+                S = sets[k % NSETS]
+                b0, b1 = int(off_np[lo]), int(off_np[hi])
+                nb, nr = b1 - b0, hi - lo
+                with torch.cuda.stream(s_in):
+                    if k >= NSETS:
+                        s_in.wait_event(S['ev_comp'])
+                    S['text'][:nb].copy_(h_data[b0:b1], non_blocking=True)
+                    S['off'][:nr + 1].copy_(h_off[lo:hi + 1], non_blocking=True)
+                    S['ev_in'].record(s_in)
+                with torch.cuda.stream(s_comp):
+                    s_comp.wait_event(S['ev_in'])
+                    if k >= NSETS:
+                        s_comp.wait_event(S['ev_out'])
+                    m = S['masks']
+                    rc = self.lib.akshar_normalize_segment_batch(
+                        self._h, S['text'].data_ptr() - b0, S['off'].data_ptr(), nr, b0, b1, nflags, sflags, S['norm'].data_ptr(), ncap,
+                        S['norm_off'].data_ptr(), m[0].data_ptr(), m[1].data_ptr(), m[2].data_ptr(), W, S['result'].data_ptr(),
+                        ws.data_ptr(), ws.numel(), ctypes.c_void_p(s_comp.cuda_stream))
+                    if rc != 0:
+                        self._err(rc, 'akshar_normalize_segment_batch')
+                    S['ev_comp'].record(s_comp)
+                if k >= 2:
+                    finish(k - 2)
+            for k in range(max(0, len(ranges) - 2), len(ranges)):
+                finish(k)
+        finally:
+            for st in (s_in, s_comp, s_out):
+                cur.wait_stream(st)
+            torch.cuda.synchronize(dev)
+        chunk_b[len(ranges)], chunk_w[len(ranges)] = state['b'], state['w']
+        return PipelineOut(h_norm[:state['b']], h_noff, h_masks[0], h_masks[1], h_masks[2], h_masks[3], chunk_rows, chunk_b, chunk_w,
+                           state['c'], state['r'])
+
     # ------------------------------------------------------------------ K1b
     def signature_batch(self, batch):
         """roman_phonetic_signature over a batch of words, one per row (reference normalize.py:59-89) -> TextBatch"""
@@ -732,6 +898,51 @@ class Engine:
         if compact:
             return CompactIds(out_ids[:state['tok']], out_splits[:n_rows + 1], chunk_rows, chunk_ids)
         return out_ids[:state['tok']], out_splits[:n_rows + 1]
+
+
+class PipelineOut:
+    """normalize -> akshars -> script runs of a batch as it crosses the host link (Engine.pipeline_host_pipelined): the
+    normalized rows (bytes + int64 row offsets) and, per chunk of rows, the boundary bit masks of AKSHAR_SEG_MASK.  Chunk c
+    holds rows chunk_rows[c] .. chunk_rows[c + 1] - 1; its text starts at norm byte chunk_bytes[c] and its mask words at
+    chunk_words[c] (bit i of the chunk's mask = byte chunk_bytes[c] + i)."""
+
+    def __init__(self, norm, offsets, cmask, rmask, t0, t1, chunk_rows, chunk_bytes, chunk_words, n_clusters, n_runs):
+        self.norm, self.offsets = norm, offsets
+        self.cmask, self.rmask, self.t0, self.t1 = cmask, rmask, t0, t1
+        self.chunk_rows, self.chunk_bytes, self.chunk_words = chunk_rows, chunk_bytes, chunk_words
+        self.n_clusters, self.n_runs = n_clusters, n_runs
+
+    def _ends(self, mask):
+        """absolute byte positions (in `norm`) of the set bits, ascending"""
+        import numpy as np
+        out = []
+        for c in range(len(self.chunk_rows) - 1):
+            w = mask[self.chunk_words[c]:self.chunk_words[c + 1]].numpy().view(np.uint32)
+            bits = np.unpackbits(w.view(np.uint8), bitorder='little')
+            out.append(np.flatnonzero(bits) + self.chunk_bytes[c])
+        return np.concatenate(out) if out else np.zeros(0, dtype=np.int64)
+
+    def cluster_ends(self):
+        """-> (int32 END offsets relative to the row start, int64 row splits): the form segment_batch returns"""
+        return self._ragged(self._ends(self.cmask))
+
+    def run_ends(self):
+        """-> (ends, splits, uint8 tags)"""
+        import numpy as np
+        pos = self._ends(self.rmask)
+        b0 = np.isin(pos, self._ends(self.t0), assume_unique=True)
+        b1 = np.isin(pos, self._ends(self.t1), assume_unique=True)
+        tags = np.where(b0 & b1, 255, np.where(b0, 1, np.where(b1, 4, 0))).astype(np.uint8)
+        e, sp = self._ragged(pos)
+        return e, sp, tags
+
+    def _ragged(self, pos):
+        import numpy as np
+        off = self.offsets.numpy()
+        # an end at position p belongs to the row with off[r] < p <= off[r + 1]
+        row = np.searchsorted(off, pos, side='left') - 1
+        splits = np.searchsorted(row, np.arange(off.size), side='left').astype(np.int64)
+        return (pos - off[row]).astype(np.int32), splits
 
 
 class CompactIds:

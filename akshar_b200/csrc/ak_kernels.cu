@@ -505,6 +505,35 @@ int akshar_normalize_batch(akshar_ctx* ctx, const uint8_t* d_text, const int64_t
     return ak_run_normalize(ctx, C, C.B, flags, d_out_text, out_capacity, d_out_row_offsets);
 }
 
+// AKSHAR_SEG_MASK launch: warp-tile row search + the one-pass mask kernel.  max_bytes bounds the text when its length is
+// only known on the device (B.dyn_end); the planes t0 / t1 are n_words apart
+static int ak_run_seg_mask(akshar_ctx* ctx, AkCall& C, const AkBatch& B, int64_t max_bytes, uint32_t flags, uint32_t* cmask,
+                           uint32_t* rmask, uint32_t* tags, int64_t n_words) {
+    int rc;
+    AkSegMaskArgs M;
+    M.B = B;
+    M.T = ctx->T;
+    M.flags = flags;
+    M.shift = (int)(((uintptr_t)B.text + (uintptr_t)B.text_begin) & 15u);
+    M.base0 = B.text_begin - M.shift;
+    M.cmask = cmask;
+    M.rmask = rmask;
+    M.t0 = tags;
+    M.t1 = tags ? tags + n_words : nullptr;
+    M.n_words = n_words;
+    const int64_t n_wt = (B.text_begin + max_bytes - M.base0 + AKN3_WARP_BYTES) / AKN3_WARP_BYTES;
+    int64_t* wrow = (int64_t*)(C.ws + C.L.scratch);
+    M.wrow = wrow;
+    const int entries = (int)(n_wt * 2 + 3);
+    ak_warp_rows_kernel<<<(entries + 255) / 256, 256, 0, C.stream>>>(B, M.base0, entries, wrow);
+    if ((rc = ak_after_launch(ctx, "segment-warp-rows"))) return rc;
+    {
+        AkTimed tm(ctx, AKSHAR_TIMER_SEGMENT, C.stream);
+        ak_seg_mask_kernel<<<ak_grid(ctx, 8, (int)((n_wt + AKSM_THREADS / 32 - 1) / (AKSM_THREADS / 32))), AKSM_THREADS, 0, C.stream>>>(M);
+    }
+    return ak_after_launch(ctx, "segment-mask");
+}
+
 int akshar_segment_batch(akshar_ctx* ctx, const uint8_t* d_text, const int64_t* d_row_offsets, int64_t n_rows,
                          int64_t text_begin, int64_t text_end, uint32_t flags, int mode, int32_t* d_cluster_ends,
                          int64_t cluster_capacity, int64_t* d_cluster_splits, int32_t* d_run_ends, uint8_t* d_run_tags,
@@ -525,28 +554,8 @@ int akshar_segment_batch(akshar_ctx* ctx, const uint8_t* d_text, const int64_t* 
             ctx->err = "bad argument (AKSHAR_SEG_MASK: tile mode, capacities in 32-bit words >= (bytes + 32) / 32)";
             return AKSHAR_E_ARG;
         }
-        AkSegMaskArgs M;
-        M.B = C.B;
-        M.T = ctx->T;
-        M.flags = flags & 7u;
-        M.shift = (int)(((uintptr_t)d_text + (uintptr_t)text_begin) & 15u);
-        M.base0 = text_begin - M.shift;
-        M.cmask = (uint32_t*)d_cluster_ends;
-        M.rmask = (uint32_t*)d_run_ends;
-        M.t0 = (uint32_t*)d_run_tags;
-        M.t1 = M.t0 ? M.t0 + n_words : nullptr;
-        M.n_words = n_words;
-        const int64_t n_wt = (text_end - M.base0 + AKN3_WARP_BYTES) / AKN3_WARP_BYTES;
-        int64_t* wrow = (int64_t*)(C.ws + C.L.scratch);
-        M.wrow = wrow;
-        const int entries = (int)(n_wt * 2 + 3);
-        ak_warp_rows_kernel<<<(entries + 255) / 256, 256, 0, C.stream>>>(C.B, M.base0, entries, wrow);
-        if ((rc = ak_after_launch(ctx, "segment-warp-rows"))) return rc;
-        {
-            AkTimed tm(ctx, AKSHAR_TIMER_SEGMENT, C.stream);
-            ak_seg_mask_kernel<<<ak_grid(ctx, 8, (int)((n_wt + AKSM_THREADS / 32 - 1) / (AKSM_THREADS / 32))), AKSM_THREADS, 0, C.stream>>>(M);
-        }
-        return ak_after_launch(ctx, "segment-mask");
+        return ak_run_seg_mask(ctx, C, C.B, text_end - text_begin, flags & 7u, (uint32_t*)d_cluster_ends, (uint32_t*)d_run_ends,
+                               (uint32_t*)d_run_tags, n_words);
     }
     if ((flags & ~7u) || (!want_c && !want_r) || ((flags & AKSHAR_SEG_MATRAS) && !want_c) ||
         (want_c && (!d_cluster_splits || cluster_capacity < 0 || (!d_cluster_ends && cluster_capacity > 0))) ||
@@ -949,6 +958,50 @@ int akshar_join_rows(akshar_ctx* ctx, const uint8_t* d_text, const int64_t* d_ro
     if (n_rows == 0) return AKSHAR_OK;
     ak_join_rows_kernel<<<ak_grid(ctx, 8, (int)((n_rows + 7) / 8)), 256, 0, (cudaStream_t)stream>>>(d_text, d_row_offsets, n_rows, (uint8_t)sep, d_out);
     return ak_after_launch(ctx, "join-rows");
+}
+
+int akshar_normalize_segment_batch(akshar_ctx* ctx, const uint8_t* d_text, const int64_t* d_row_offsets, int64_t n_rows,
+                                   int64_t text_begin, int64_t text_end, uint32_t norm_flags, uint32_t seg_flags, uint8_t* d_norm_text,
+                                   int64_t norm_capacity, int64_t* d_norm_row_offsets, uint32_t* d_cluster_mask, uint32_t* d_run_mask,
+                                   uint32_t* d_run_tag_planes, int64_t mask_words, int64_t* d_result, void* d_workspace,
+                                   size_t workspace_bytes, void* stream) {
+    AkDeviceGuard device_guard(ctx ? ctx->device : 0);
+    if (!ctx) return AKSHAR_E_ARG;
+    const bool want_c = (seg_flags & AKSHAR_SEG_CLUSTERS) != 0, want_r = (seg_flags & AKSHAR_SEG_RUNS) != 0;
+    const int64_t n_bytes = text_end - text_begin;
+    const int64_t max_bytes = n_bytes > norm_capacity ? n_bytes : norm_capacity;
+    if (norm_capacity < 0 || !d_norm_row_offsets || (!d_norm_text && norm_capacity > 0) || (norm_flags & ~15u) || (seg_flags & ~7u) ||
+        (!want_c && !want_r) || ((seg_flags & AKSHAR_SEG_MATRAS) && !want_c) || mask_words < (norm_capacity + 32) / 32 ||
+        (want_c && !d_cluster_mask) || (want_r && (!d_run_mask || !d_run_tag_planes))) {
+        ctx->err = "bad argument";
+        return AKSHAR_E_ARG;
+    }
+    if (workspace_bytes < ak_ws_layout(max_bytes, n_rows).total) {
+        ctx->err = "workspace too small: need " + std::to_string(ak_ws_layout(max_bytes, n_rows).total) + " bytes";
+        return AKSHAR_E_WORKSPACE;
+    }
+    AkCall C;
+    int rc = ak_begin(ctx, d_text, d_row_offsets, n_rows, text_begin, text_end, AKSHAR_MODE_TILES, 0, d_result, d_workspace,
+                      workspace_bytes, stream, C);
+    if (rc) return rc;
+    C.L = ak_ws_layout(max_bytes, n_rows);
+    const size_t tiles = (size_t)ak_tiles_of(max_bytes, n_rows);
+    AK_CUDA(ctx, cudaMemsetAsync(C.ws, 0, 256 + ak_align(4 * tiles * 8), C.stream));
+    C.B.state0 = (unsigned long long*)(C.ws + C.L.state);
+    C.B.state1 = C.B.state0 + tiles;
+    if (n_rows == 0) return ak_empty_rows(ctx, d_norm_row_offsets, nullptr, C.stream);
+    // stage 1: normalize_text; its byte total lands in result[3]
+    AkBatch B1 = C.B;
+    B1.totals = d_result + 3;
+    if ((rc = ak_run_normalize(ctx, C, B1, norm_flags, d_norm_text, norm_capacity, d_norm_row_offsets))) return rc;
+    // stage 2: akshars / script runs of the normalized rows as bit masks; their length is only known on the device
+    AkBatch B2 = C.B;
+    B2.text = d_norm_text;
+    B2.off = d_norm_row_offsets;
+    B2.text_begin = 0;
+    B2.text_end = 0;
+    B2.dyn_end = d_result + 3;
+    return ak_run_seg_mask(ctx, C, B2, norm_capacity, seg_flags, d_cluster_mask, d_run_mask, d_run_tag_planes, mask_words);
 }
 
 int akshar_signature_batch(akshar_ctx* ctx, const uint8_t* d_text, const int64_t* d_row_offsets, int64_t n_rows,

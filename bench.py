@@ -308,12 +308,18 @@ def run_workload(R, workload, mb, steps, warmup, cpu_sample_mb, dist, with_cpu=T
             if mkind is not None:
                 outs.append(eng.tokenizer_encode_batch(b, mkind, check=False))
             else:
-                norm, r1 = eng.normalize_batch(b, check=False)
-                # the normalized length stays on the device in the fused entry point; here (two ABI calls) it is read back
-                norm.end = int(r1[0].item())
-                c, r, r2 = eng.segment_batch(norm, clusters=True, runs=True, check=False)
-                outs.append(((c, r), norm, r2))
+                # one library call: normalize_text, then akshars + script runs of the normalized rows as bit masks
+                # (1 bit per byte and stream + two tag planes); nothing is read back in between
+                norm, mk = eng.normalize_segment_batch(b, check=False)
+                outs.append((mk, norm, mk['result']))
         return outs
+
+    def offsets_form(b):
+        """the same stage through the two-call offset form (int32 ends): what the CPU arm's rows are compared with, and
+        what the masks of the timed call must agree with"""
+        norm = eng.normalize_batch(b)
+        c, r = eng.segment_batch(norm, clusters=True, runs=True)
+        return c, r, norm
 
     def barrier():
         torch.cuda.synchronize()
@@ -334,7 +340,7 @@ def run_workload(R, workload, mb, steps, warmup, cpu_sample_mb, dist, with_cpu=T
         else:
             n_c += int(res[0])
             n_r += int(res[1])
-            n_norm += int(o[1].end)
+            n_norm += int(res[3])
     if mkind is None:
         n_tokens = n_c + n_r
     parity = None
@@ -347,7 +353,26 @@ def run_workload(R, workload, mb, steps, warmup, cpu_sample_mb, dist, with_cpu=T
             iv = o[0].values[:int(sp[-1])].cpu().numpy().astype(np.int32)
             got = [_crc(iv[sp[i]:sp[i + 1]]) for i in range(k)]
         else:
-            (c, r), norm, _ = o
+            c, r, norm = offsets_form(dev_batches[0])
+            # the timed call's masks == the offset form, bit for bit, over the first 64 MiB of the batch (+ all totals)
+            mk = o[0]
+            rr = mk['result'].cpu()
+            assert int(rr[0]) == c.values.numel() and int(rr[1]) == r.values.numel() and int(rr[3]) == norm.end
+            assert torch.equal(o[1].offsets, norm.offsets) and torch.equal(o[1].data[:norm.end], norm.data[:norm.end])
+            no_all = norm.offsets.cpu().numpy()
+            kk = int(np.searchsorted(no_all, 64 << 20))
+            kk = max(1, min(kk, no_all.size - 1))
+            lim = int(no_all[kk])
+            nw = lim // 32
+            for rag, key in ((c, 'cluster'), (r, 'run')):
+                sp = rag.splits[:kk + 1].cpu().numpy()
+                ev = rag.values[:int(sp[-1])].cpu().numpy().astype(np.int64)
+                pos = no_all[np.repeat(np.arange(kk), np.diff(sp))] + ev
+                m = np.zeros((lim // 32 + 1) * 32, dtype=bool)
+                m[pos] = True
+                exp_w = np.packbits(m, bitorder='little').view(np.uint32)[:nw]
+                assert np.array_equal(mk[key][:nw].cpu().numpy().view(np.uint32), exp_w), 'mask of the %s ends differs' % key
+            del mk
             no = norm.offsets[:k + 1].cpu().numpy()
             nb = norm.data[:int(no[-1])].cpu().numpy()
             cs = c.splits[:k + 1].cpu().numpy()
@@ -397,27 +422,10 @@ def run_workload(R, workload, mb, steps, warmup, cpu_sample_mb, dist, with_cpu=T
                 res = eng.encode_host_pipelined(hb[0], hb[1], mkind, compact=True)
                 moved += res.ids16.numel() * 2 + res.splits32.numel() * 4 + 32 * len(res.chunk_ids)
                 continue
-            b = eng.put(hb)
-            norm, r1 = eng.normalize_batch(b, check=False)
-            norm.end = int(r1[0].item())
-            c, r, r2 = eng.segment_batch(norm, clusters=True, runs=True, check=False)
-            rr = r2.cpu()
-            nc, nr = int(rr[0]), int(rr[1])
-            nrow = c.splits.numel()
-            if not bufs:
-                bufs['v'] = [torch.empty(int(nc * 1.2) + 1024, dtype=torch.int32).pin_memory(), torch.empty(int(nr * 1.2) + 1024, dtype=torch.int32).pin_memory(),
-                             torch.empty(int(nr * 1.2) + 1024, dtype=torch.uint8).pin_memory(), torch.empty(int(nrow * 1.2) + 1024, dtype=torch.int64).pin_memory(),
-                             torch.empty(int(nrow * 1.2) + 1024, dtype=torch.int64).pin_memory(),
-                             torch.empty(int(norm.end * 1.1) + 1024, dtype=torch.uint8).pin_memory()]
-            hbuf = bufs['v']
-            hbuf[0][:nc].copy_(c.values[:nc], non_blocking=True)
-            hbuf[1][:nr].copy_(r.values[:nr], non_blocking=True)
-            hbuf[2][:nr].copy_(r.extra[:nr], non_blocking=True)
-            hbuf[3][:nrow].copy_(c.splits, non_blocking=True)
-            hbuf[4][:nrow].copy_(r.splits, non_blocking=True)
-            hbuf[5][:norm.end].copy_(norm.data[:norm.end], non_blocking=True)
-            torch.cuda.synchronize()
-            moved += nc * 4 + nr * 5 + 2 * nrow * 8 + norm.end + 64
+            # the public host -> host call of this stage: chunks over three streams; back come the normalized text, its row
+            # offsets and four mask planes (cluster ends, run ends, two tag planes) of one bit per normalized byte
+            po = eng.pipeline_host_pipelined(hb[0], hb[1])
+            moved += po.norm.numel() + po.offsets.numel() * 8 + 16 * int(po.chunk_words[-1]) + 32 * (len(po.chunk_rows) - 1)
         return moved
 
     d2h = e2e_step()
@@ -433,7 +441,7 @@ def run_workload(R, workload, mb, steps, warmup, cpu_sample_mb, dist, with_cpu=T
     eng.timing(True)
     names = ['ak_nf3_classify_kernel', 'ak_nf_write_kernel'] + (['ak_words_kernel', 'ak_resolve_kernel<bpe>', 'ak_emit_kernel'] if mkind == 0 else
                                                                  ['ak_words_kernel', 'ak_resolve_kernel<unigram>', 'ak_emit_kernel'] if mkind == 1 else
-                                                                 ['ak_sf3_kernel'])
+                                                                 ['ak_seg_mask_kernel'])
     acc = {k: [] for k in names}
     for _ in range(3):
         device_step(dev_batches[:1])
@@ -456,7 +464,7 @@ def run_workload(R, workload, mb, steps, warmup, cpu_sample_mb, dist, with_cpu=T
         'ak_resolve_kernel<bpe>': b_norm + 16 * ev1,                            # the words' bytes + events in, resolved records out
         'ak_resolve_kernel<unigram>': b_norm + 20 * ev1,
         'ak_emit_kernel': 8 * ev1 + 4 * tok1 + 8 * (rows1 + 1),
-        'ak_sf3_kernel': b_norm + 4 * n_c * f + 5 * n_r * f + 16 * (rows1 + 1),
+        'ak_seg_mask_kernel': b_norm + 4 * (b_norm // 8) + 8 * (rows1 + 1),          # text + row offsets in, four planes of 1 bit per byte out
     }
     kern = {k: (kms[k], alg[k]) for k in kms}
     dom = max(kern, key=lambda k: kern[k][0])
@@ -467,7 +475,7 @@ def run_workload(R, workload, mb, steps, warmup, cpu_sample_mb, dist, with_cpu=T
     if mkind is not None:
         stage_bytes = int(off[-1]) + n_norm + 4 * n_tokens + 2 * 8 * (n_rows + 1)
     else:
-        stage_bytes = int(off[-1]) + n_norm + 4 * n_c + 5 * n_r + 3 * 8 * (n_rows + 1)
+        stage_bytes = int(off[-1]) + n_norm + 4 * (n_norm // 8) + 2 * 8 * (n_rows + 1)
 
     # ---- reduce over ranks
     t = torch.tensor([ms, e2e_s * 1e3], dtype=torch.float64, device='cuda')
@@ -504,7 +512,7 @@ def run_workload(R, workload, mb, steps, warmup, cpu_sample_mb, dist, with_cpu=T
         'parity_in_run': parity is not None, 'rows_compared': parity or 0,
         'e2e': {'value': tot_bytes / (e2e_ms * 1e-3) / 1e9, 'unit': 'GB/s', 'h2d_bytes_per_step': int(tot_h2d / R.world),
                 'd2h_bytes_per_step': int(tot_d2h / R.world), 'ms_per_step': e2e_ms, 'chunks_redone': getattr(eng, 'redone_chunks', 0),
-                'out': 'uint16 ids + int32 chunk-relative row splits' if mkind is not None else 'int32 ends + uint8 tags + int64 splits + normalized text'},
+                'out': 'uint16 ids + int32 chunk-relative row splits' if mkind is not None else 'normalized text + int64 row offsets + 4 boundary mask planes (1 bit per normalized byte each)'},
         'gpu_launches': int(tot_launch),
         'roofline': {'bound': 'hbm', 'kernel': dom, 'achieved': ach, 'peak': peak, 'peak_source': peak_kind, 'unit': 'GB/s',
                      'frac': ach / peak, 'frac_of_nominal_8000': ach / 8000.0,

@@ -166,6 +166,17 @@ int akshar_lines_batch(akshar_ctx* ctx, const uint8_t* d_file, int64_t n_bytes, 
 int akshar_join_rows(akshar_ctx* ctx, const uint8_t* d_text, const int64_t* d_row_offsets, int64_t n_rows, int sep, uint8_t* d_out,
                      void* stream);
 
+/* normalize_text -> akshars / script runs in one call, nothing read back in between (BASELINE config 4: "normalize +
+ * grapheme + code-switch pipeline"): the normalized rows as akshar_normalize_batch writes them, and the boundaries of the
+ * NORMALIZED text as AKSHAR_SEG_MASK bit masks (mask_words >= (norm_capacity + 32) / 32 words per mask; the tag planes
+ * t0 / t1 are mask_words apart).  result[0] = clusters, result[1] = runs, result[3] = normalized bytes.
+ * AKSHAR_ST_PATHOLOGICAL / AKSHAR_ST_OVERFLOW as in akshar_normalize_batch (call the two stages separately then). */
+int akshar_normalize_segment_batch(akshar_ctx* ctx, const uint8_t* d_text, const int64_t* d_row_offsets, int64_t n_rows,
+                                   int64_t text_begin, int64_t text_end, uint32_t norm_flags, uint32_t seg_flags, uint8_t* d_norm_text,
+                                   int64_t norm_capacity, int64_t* d_norm_row_offsets, uint32_t* d_cluster_mask, uint32_t* d_run_mask,
+                                   uint32_t* d_run_tag_planes, int64_t mask_words, int64_t* d_result, void* d_workspace,
+                                   size_t workspace_bytes, void* stream);
+
 /* roman_phonetic_signature over a batch of words (normalize.py:59-89); one word per row. result[0] = out bytes */
 int akshar_signature_batch(akshar_ctx* ctx, const uint8_t* d_text, const int64_t* d_row_offsets, int64_t n_rows,
                            int64_t text_begin, int64_t text_end, uint8_t* d_out_text, int64_t out_capacity,

@@ -205,6 +205,43 @@ def test_segment_bit_masks(A, eng, golden):
                 assert np.array_equal(planes[0], t0) and np.array_equal(planes[1], t1)
 
 
+def test_pipeline_host_pipelined(A, eng, golden):
+    """normalize -> akshars -> script runs through the pipelined host path (pinned text in; normalized text, row offsets and
+    boundary bit masks out) == the reference vectors, and == the two-call offset form on 48 MB over many chunks"""
+    import torch
+    rows = golden['rows']
+    data, off = sc.pack([r['in'] for r in rows])
+    hd, ho = torch.from_numpy(data).pin_memory(), torch.from_numpy(off).pin_memory()
+    out = eng.pipeline_host_pipelined(hd, ho, chunk_bytes=1 << 16)
+    nb = out.norm.numpy().tobytes()
+    no = out.offsets.numpy()
+    assert [nb[no[i]:no[i + 1]].decode('utf-8') for i in range(len(rows))] == [r['norm'] for r in rows]
+    ce, cs = out.cluster_ends()
+    re_, rs, rt = out.run_ends()
+    names = ['devanagari', 'roman', 'digit', 'punct', 'other']
+    for i, r in enumerate(rows):
+        b = r['norm'].encode('utf-8')
+        ends = ce[cs[i]:cs[i + 1]].tolist()
+        assert [b[(ends[j - 1] if j else 0):e].decode('utf-8') for j, e in enumerate(ends)] == r['seg']
+        ends = re_[rs[i]:rs[i + 1]].tolist()
+        labs = [None if t == 255 else names[t] for t in rt[rs[i]:rs[i + 1]].tolist()]
+        assert [[b[(ends[j - 1] if j else 0):e].decode('utf-8'), labs[j]] for j, e in enumerate(ends)] == r['cs']
+    assert out.n_clusters == ce.size and out.n_runs == re_.size
+    # 48 MB of social text + adversarial rows (the row-sequential fallback of a chunk included), 2 MiB chunks
+    lines = sc.Corpus('social', 51).lines(48 << 20) + sc.adversarial(3000, 8, 64) + ['\u0915' + '\u0301' * 3000, '', 'x']
+    data, off = sc.pack(lines)
+    hd, ho = torch.from_numpy(data).pin_memory(), torch.from_numpy(off).pin_memory()
+    out = eng.pipeline_host_pipelined(hd, ho, chunk_bytes=2 << 20)
+    norm = eng.normalize_batch((hd, ho))
+    cl, ru = eng.segment_batch(norm, clusters=True, runs=True)
+    assert out.norm.numel() == norm.end and np.array_equal(out.norm.numpy(), _np(norm.data[:norm.end]))
+    assert np.array_equal(out.offsets.numpy(), _np(norm.offsets))
+    ce, cs = out.cluster_ends()
+    assert np.array_equal(cs, _np(cl.splits)) and np.array_equal(ce, _np(cl.values))
+    re_, rs, rt = out.run_ends()
+    assert np.array_equal(rs, _np(ru.splits)) and np.array_equal(re_, _np(ru.values)) and np.array_equal(rt, _np(ru.extra))
+
+
 def test_signature_golden(A, golden):
     words = list(golden['signature'])
     assert A.roman_phonetic_signature_batch(words) == [golden['signature'][w] for w in words]
