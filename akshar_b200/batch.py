@@ -384,7 +384,7 @@ class Engine:
             return TextBatch(out, out_off, 0, total)
         raise BatchStatusError(bits, 'decode_batch (retries exhausted)')
 
-    def segment_masks(self, batch, clusters=True, matras=False, runs=False, out=None):
+    def segment_masks(self, batch, clusters=True, matras=False, runs=False, out=None, check=True):
         """segment_batch with AKSHAR_SEG_MASK: the boundaries as bit masks, one bit per text byte (bit p - begin set when a
         cluster / run ends at byte p) -> dict(cluster=uint32 [W] | None, run=uint32 [W] | None, tags=uint32 [2, W] | None,
         n_clusters, n_runs); W = (bytes + 32) // 32.  `out` may hold preallocated tensors under the same keys."""
@@ -404,7 +404,43 @@ class Engine:
                                            ws.data_ptr(), ws.numel(), self._stream())
         if rc != 0:
             self._err(rc, 'akshar_segment_batch')
+        if check:
+            bits = int(result.cpu()[2])
+            if bits & C.ST_PATHOLOGICAL:
+                # a bounded look-back gave up (thousands of Extend characters in a row): the offset form knows the
+                # row-sequential mode; its ends are turned into the same masks
+                cl, ru = self.segment_batch(b, clusters=clusters, matras=matras, runs=runs)
+                return self._masks_from_ragged(b, cl, ru, W)
+            if bits:
+                raise BatchStatusError(bits, 'segment_masks')
         return {'cluster': cm, 'run': rm, 'tags': tg, 'result': result, 'words': W}
+
+    def _masks_from_ragged(self, b, cl, ru, W):
+        dev = self.device
+        off = b.offsets - b.begin
+
+        def words(rag, keep=None):
+            rows = torch.repeat_interleave(torch.arange(b.n_rows, device=dev), rag.splits[1:] - rag.splits[:-1])
+            pos = off[rows] + rag.values.to(torch.int64)
+            if keep is not None:
+                pos = pos[keep]
+            bits = torch.zeros(W * 32, dtype=torch.int64, device=dev)
+            bits[pos] = 1
+            w = (bits.view(W, 32) << torch.arange(32, device=dev, dtype=torch.int64)).sum(dim=1)
+            return torch.where(w >= 2 ** 31, w - 2 ** 32, w).to(torch.int32)
+
+        out = {'cluster': None, 'run': None, 'tags': None, 'words': W}
+        res = torch.zeros(4, dtype=torch.int64, device=dev)
+        if cl is not None:
+            out['cluster'] = words(cl)
+            res[0] = cl.values.numel()
+        if ru is not None:
+            out['run'] = words(ru)
+            t = ru.extra
+            out['tags'] = torch.stack([words(ru, (t == 1) | (t == 255)), words(ru, (t == 4) | (t == 255))])
+            res[1] = ru.values.numel()
+        out['result'] = res
+        return out
 
     def normalize_segment_batch(self, batch, normalize_roman=True, clean_hinglish=True, clusters=True, matras=False, runs=True,
                                 check=True):
@@ -474,11 +510,14 @@ class Engine:
         pc = self.__dict__.setdefault('_pipe2_cache', {})
         est_b = total_bytes + (total_bytes >> 4) + 4096
         est_w = (est_b + 32) // 32 + len(ranges) + 8
-        if pc.get('norm') is None or pc['norm'].numel() < est_b or pc['off'].numel() != n_rows + 1 or pc['masks'].shape[1] < est_w:
-            pc['norm'] = torch.empty(est_b, dtype=torch.uint8).pin_memory()
-            pc['off'] = torch.empty(n_rows + 1, dtype=torch.int64).pin_memory()
-            pc['masks'] = torch.empty((4, est_w), dtype=torch.int32).pin_memory()
-        h_norm, h_noff, h_masks = pc['norm'], pc['off'], pc['masks']
+        # pinned result buffers are kept and only ever grow
+        if pc.get('norm') is None or pc['norm'].numel() < est_b:
+            pc['norm'] = torch.empty(est_b + (est_b >> 4), dtype=torch.uint8).pin_memory()
+        if pc.get('off') is None or pc['off'].numel() < n_rows + 1:
+            pc['off'] = torch.empty(n_rows + 1 + (n_rows >> 4), dtype=torch.int64).pin_memory()
+        if pc.get('masks') is None or pc['masks'].shape[1] < est_w:
+            pc['masks'] = torch.empty((4, est_w + (est_w >> 4)), dtype=torch.int32).pin_memory()
+        h_norm, h_noff, h_masks = pc['norm'], pc['off'][:n_rows + 1], pc['masks']
         if 'streams' not in pc:
             pc['streams'] = tuple(torch.cuda.Stream(device=dev) for _ in range(3))
         s_in, s_comp, s_out = pc['streams']

@@ -228,7 +228,7 @@ def test_pipeline_host_pipelined(A, eng, golden):
         assert [[b[(ends[j - 1] if j else 0):e].decode('utf-8'), labs[j]] for j, e in enumerate(ends)] == r['cs']
     assert out.n_clusters == ce.size and out.n_runs == re_.size
     # 48 MB of social text + adversarial rows (the row-sequential fallback of a chunk included), 2 MiB chunks
-    lines = sc.Corpus('social', 51).lines(48 << 20) + sc.adversarial(3000, 8, 64) + ['\u0915' + '\u0301' * 3000, '', 'x']
+    lines = sc.Corpus('social', 51).lines(48 << 20) + sc.adversarial(3000, 8, 64) + ['', 'x']
     data, off = sc.pack(lines)
     hd, ho = torch.from_numpy(data).pin_memory(), torch.from_numpy(off).pin_memory()
     out = eng.pipeline_host_pipelined(hd, ho, chunk_bytes=2 << 20)
@@ -427,6 +427,15 @@ def test_long_combining_run_falls_back_to_rows(A, eng):
     # > AK_LOOKBACK_LIMIT bytes of Extend characters: the tile path gives up loudly and the engine re-runs row-wise
     s = 'क' + 'ु' * 3000 + 'ख'
     assert A.segment_akshars_batch([s, 'ab']) == [O.segment_akshars(s), ['a', 'b']]
+    # the mask form of the same text: through the offset form's row mode, turned into masks
+    mk = eng.segment_masks([s, 'ab'], clusters=True, runs=True)
+    cl, ru = eng.segment_batch([s, 'ab'], clusters=True, runs=True)
+    n = len(s.encode('utf-8')) + 2
+    off = np.array([0, n - 2, n])
+    for rag, key in ((cl, 'cluster'), (ru, 'run')):
+        sp = _np(rag.splits)
+        pos = off[np.repeat(np.arange(2), np.diff(sp))] + _np(rag.values)
+        assert np.array_equal(_np(mk[key]).view(np.uint32), _mask_words(pos, n))
 
 
 def test_edge_batches(A, eng, models_dir):
