@@ -567,7 +567,8 @@ class Engine:
                     raise BatchStatusError(C.ST_OVERFLOW, 'pipeline_host_pipelined: the normalized text grew beyond the pinned result buffers')
                 h_norm[state['b']:state['b'] + nb].copy_(norm[:nb], non_blocking=True)
                 h_noff[lo + 1:hi + 1].copy_(noff[1:hi - lo + 1] + state['b'], non_blocking=True)
-                h_masks[:, state['w']:state['w'] + nw].copy_(masks[:, :nw], non_blocking=True)
+                for pl in range(4):              # plane by plane: contiguous copies (a strided 2-D copy would be staged)
+                    h_masks[pl, state['w']:state['w'] + nw].copy_(masks[pl, :nw], non_blocking=True)
                 S['ev_out'].record(s_out)
                 chunk_b[k], chunk_w[k] = state['b'], state['w']
                 state['b'] += nb
