@@ -225,12 +225,18 @@ __device__ __forceinline__ uint32_t akn3_lane_rows2(const int64_t* off, int64_t 
     return rows;
 }
 
-__device__ __noinline__ void akn3_load_edge(const uint8_t* text, int64_t cs, int lo, int hi, uint32_t* x) {
+// the lane's 32 bytes at the edge of the text: bytes [lo, hi) of [cs, cs + 32), zero elsewhere.  Fully unrolled so that
+// x[] stays in registers (a pointer handed to a non-inlined helper would put the lane's bytes of EVERY warp in local
+// memory); only the first and the last warp tile of a text ever come here
+__device__ __forceinline__ void akn3_load_edge(const uint8_t* text, int64_t cs, int lo, int hi, uint32_t* x) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) x[i] = 0;
-#pragma unroll 1
-    for (int i = lo; i < hi; ++i) x[i >> 2] |= (uint32_t)text[cs + i] << ((i & 3) * 8);
+    for (int w = 0; w < 8; ++w) {
+        uint32_t v = 0;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            const int i = 4 * w + b;
+            if (i >= lo && i < hi) v |= (uint32_t)text[cs + i] << (8 * b);
+        }
+        x[w] = v;
+    }
 }
-
-
-

@@ -466,7 +466,11 @@ static int ak_run_normalize(akshar_ctx* ctx, AkCall& C, const AkBatch& B, uint32
         const int slow_grid = ctx->sm_count * AKN_SLOW_MINB;      // latency bound: as many walkers in flight as fit
         ak_nf_slow_kernel<<<slow_grid, 128, 0, C.stream>>>(S);
         if ((rc = ak_after_launch(ctx, "normalize-slow-count"))) return rc;
-        ak_nf_scan_kernel<<<1, 1024, 0, C.stream>>>(W.tile_total, W.tile_base, F.B.n_tiles, B.totals, B, F.base0);
+        // tile totals -> tile bases + the output length (single pass, look-back over tiles of 4096 entries; the state words
+        // are the second quarter of the zeroed state area, the ticket is control word 6)
+        ak_scan_counts_kernel<<<ak_grid(ctx, 4, F.B.n_tiles / AKS_TILE + 1), AKS_THREADS, 0, C.stream>>>(
+            W.tile_total, (long long)F.B.n_tiles, nullptr, 1, W.tile_base, B.totals, (int*)C.ws + 6, C.B.state1,
+            (unsigned int*)&B.result[2]);
         if ((rc = ak_after_launch(ctx, "normalize-scan"))) return rc;
         {
             AkTimed tm(ctx, AKSHAR_TIMER_NORMALIZE_WRITE, C.stream);
