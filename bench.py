@@ -529,6 +529,47 @@ def run_workload(R, workload, mb, steps, warmup, cpu_sample_mb, dist, with_cpu=T
     }
 
 
+def config1_latency():
+    """BASELINE.json configs[0]: `aksharTokenizer().tokenize(line)` (no model: akshar-level fallback) over the reference's
+    data/corpus.txt, one string per call -- the latency of the drop-in API (each call: pinned staging, two library calls,
+    read-back), next to the same lines as ONE batch and to the CPU port of the same function on this box.  BASELINE.md
+    quotes 62 us/line for the reference's own Python path."""
+    import torch
+    import akshar_b200 as A
+    sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+    import akshar_oracle as O
+    with open(os.path.join(ROOT, 'tests', 'golden', 'corpus.txt'), encoding='utf-8') as f:
+        lines = [ln.strip() for ln in f.readlines() if ln.strip()]
+    tk = A.aksharTokenizer()
+    exp = [O.segment_akshars(O.normalize_text(s)) for s in lines]
+    assert [tk.tokenize(s) for s in lines] == exp and tk.tokenize_batch(lines) == exp
+    reps = 20
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        for s in lines:
+            tk.tokenize(s)
+    one = (time.perf_counter() - t0) / (reps * len(lines))
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        tk.tokenize_batch(lines)
+    batch = (time.perf_counter() - t0) / (reps * len(lines))
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        for s in lines:
+            O.segment_akshars(O.normalize_text(s))
+    cpu = (time.perf_counter() - t0) / (reps * len(lines))
+    nbytes = sum(len(s.encode('utf-8')) for s in lines)
+    return {'metric': 'us_per_line_tokenize_single_string', 'value': one * 1e6, 'unit': 'us/line', 'higher_is_better': False,
+            'config': {'workload': 'configs[0]: aksharTokenizer().tokenize(line), akshar-level fallback, %d lines / %d bytes of '
+                                   'data/corpus.txt, one string per call' % (len(lines), nbytes)},
+            'same_lines_as_one_batch_us_per_line': batch * 1e6, 'parity_in_run': True, 'rows_compared': len(lines),
+            'cpu_baseline': {'value': cpu * 1e6, 'unit': 'us/line', 'cores': 1, 'kind': 'port',
+                             'sample': 'oracle normalize_text + segment_akshars, same lines, %d passes' % reps},
+            'reference_published_us_per_line': 62.0,
+            'note': 'a single short string is launch- and read-back-latency bound on any GPU path; the batch entry points are the product'}
+
+
 # ------------------------------------------------------------------ main
 def main():
     ap = argparse.ArgumentParser()
@@ -595,6 +636,7 @@ def main():
             gc.collect()
             torch.cuda.empty_cache()
             also.append(run_workload(R, w, wmb, min(a.steps, 3), 3, min(a.cpu_sample_mb, 8.0), dist))
+        also.append(config1_latency())
         line['also'] = also
     if R.rank == 0:
         print(json.dumps(line))

@@ -573,6 +573,52 @@ def test_large_properties(A, eng, models_dir):
         assert iv[isp[i]:isp[i + 1]].tolist() == O.bpe_encode(om, e)
 
 
+def test_unigram_at_scale_and_long_rows(A, models_dir):
+    """the Unigram encoder beyond the golden rows: (1) 64 MB of in-vocabulary Hindi, every row against the oracle's Viterbi
+    (sampled 6000 rows) and both modes against each other on all rows; (2) one 8 MB row (a file as one string: the exact
+    whole-row Viterbi) and a batch with 40 kB rows between short ones; (3) compact outputs (uint16 ids, int32 splits)"""
+    import torch
+    tk = A.aksharTokenizer(os.path.join(models_dir, 'spm24k.model'), 'sentencepiece')
+    eng = tk._eng
+    um = O.UnigramModel(os.path.join(models_dir, 'spm24k.model'))
+    from akshar_b200 import _lib as C
+    data, off = sc.Corpus('hindi', 61).generate(64 << 20)
+    host = (torch.from_numpy(data), torch.from_numpy(off))
+    ids, norm = eng.tokenizer_encode_batch(host, 1)
+    iv, isp = _np(ids.values), _np(ids.splits)
+    rows_ids, _ = eng.tokenizer_encode_batch(host, 1, mode=C.MODE_ROWS)
+    assert np.array_equal(_np(rows_ids.splits), isp) and np.array_equal(_np(rows_ids.values), iv)
+    n = off.size - 1
+    b = data.tobytes()
+    rng = np.random.default_rng(7)
+    for i in np.sort(rng.choice(n, size=6000, replace=False)):
+        e = O.normalize_text(b[off[i]:off[i + 1]].decode('utf-8'))
+        assert iv[isp[i]:isp[i + 1]].tolist() == O.unigram_encode(um, e), i
+    # (2) long rows: rows beyond 8192 bytes take the exact row encoder
+    lines = sc.Corpus('hindi', 62).lines(9 << 20)
+    one = ' '.join(lines)[:8 << 20]
+    mid = [' '.join(lines[k:k + 400]) for k in range(0, 4000, 400)]
+    batch = lines[:50] + [one] + lines[50:100] + mid + ['', 'x']
+    got = tk.encode_batch(batch)
+    exp_short = [O.unigram_encode(um, O.normalize_text(s)) for s in lines[:100] + mid + ['', 'x']]
+    assert got[:50] + got[51:] == exp_short
+    # the 8 MB row: against the row-sequential mode, and against the oracle on its first 200 kB (a lattice cut at a space)
+    alone, _ = eng.tokenizer_encode_batch([one], 1, mode=C.MODE_ROWS)
+    assert got[50] == _np(alone.values).tolist()
+    head = one[:200000]
+    head = head[:head.rindex(' ')]
+    eh = O.unigram_encode(um, O.normalize_text(head))
+    assert got[50][:len(eh)] == eh
+    assert tk.decode(got[50]) == O.normalize_text(one)
+    # (3) compact outputs through the pipelined host path == the wide ones
+    h_data, h_off = torch.from_numpy(data[:off[200000]]).pin_memory(), torch.from_numpy(off[:200001]).pin_memory()
+    wide_ids, wide_sp = eng.encode_host_pipelined(h_data, h_off, 1, chunk_bytes=4 << 20)
+    wide_ids, wide_sp = wide_ids.clone(), wide_sp.clone()
+    cp = eng.encode_host_pipelined(h_data, h_off, 1, chunk_bytes=4 << 20, compact=True)
+    assert np.array_equal(cp.ids().astype(np.int32), wide_ids.numpy()) and np.array_equal(cp.row_splits(), wide_sp.numpy())
+    assert np.array_equal(wide_ids.numpy(), iv[:isp[200000]]) and np.array_equal(wide_sp.numpy(), isp[:200001])
+
+
 def test_raw_mode_golden(A, golden_raw, models_dir):
     """clean_hinglish=False (reference vectors, every row): emoji, accents and other scripts reach the models, and on the
     BPE side what only HF acts on -- added tokens in the raw text, NFKC (scripts/train_bpe.py:71,80) -- is done on the device"""

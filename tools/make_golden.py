@@ -150,6 +150,8 @@ def main():
            if not 0xD800 <= c <= 0xDFFF}
     out = {'pins': pins, 'rows': rows, 'signature': sig, 'identify_script': ids,
            'vocab_size': {k: v.vocab_size() for k, v in toks.items()}}
+    # BASELINE.json configs[0] runs over the reference's 1.5 KB sample corpus: kept as a data fixture (bench.py's config-1 line)
+    shutil.copyfile(os.path.join(REF, 'data', 'corpus.txt'), os.path.join(ROOT, 'tests', 'golden', 'corpus.txt'))
     path = os.path.join(ROOT, 'tests', 'golden', 'reference_vectors.json.gz')
     with gzip.GzipFile(path, 'wb', mtime=0) as f:
         f.write(json.dumps(out, ensure_ascii=False, separators=(',', ':')).encode('utf-8'))
