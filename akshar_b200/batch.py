@@ -518,8 +518,7 @@ class Engine:
         n_rows = h_off.numel() - 1
         off_np = h_off.numpy()
         total_bytes = int(off_np[-1] - off_np[0])
-        n_chunks = max(1, (total_bytes + chunk_bytes - 1) // chunk_bytes)
-        ranges = [r for r in shard.shard_rows(off_np, n_chunks) if r[1] > r[0]] or [(0, 0)]
+        ranges = shard.chunk_rows(off_np, chunk_bytes)
         max_b = max(int(off_np[hi] - off_np[lo]) for lo, hi in ranges)
         max_r = max(hi - lo for lo, hi in ranges)
         nflags = (C.NORM_ROMAN if normalize_roman else 0) | (C.NORM_CLEAN if clean_hinglish else 0)
@@ -804,8 +803,7 @@ class Engine:
         n_rows = h_off.numel() - 1
         off_np = h_off.numpy()
         total_bytes = int(off_np[-1] - off_np[0])
-        n_chunks = max(1, (total_bytes + chunk_bytes - 1) // chunk_bytes)
-        ranges = [r for r in shard.shard_rows(off_np, n_chunks) if r[1] > r[0]] or [(0, 0)]
+        ranges = shard.chunk_rows(off_np, chunk_bytes)
         max_b = max(int(off_np[hi] - off_np[lo]) for lo, hi in ranges)
         max_r = max(hi - lo for lo, hi in ranges)
         flags = (C.NORM_ROMAN if normalize_roman else 0) | (C.NORM_CLEAN if clean_hinglish else 0)
