@@ -41,11 +41,12 @@ enum {
     AKSHAR_ST_OVERFLOW = 1,      /* an output capacity was too small: re-run with capacity >= total */
     AKSHAR_ST_NFC_SEGMENT = 2,   /* a combining sequence needing NFC work exceeds 64 decomposed code points */
     AKSHAR_ST_PATHOLOGICAL = 4,  /* bounded look-back gave up: re-run the same call with AKSHAR_MODE_ROWS */
-    AKSHAR_ST_ALPHABET = 8,      /* BPE encode met a code point on which HF's NFKC differs from NFC (compatibility
-                                  * characters, marks newer than its Unicode tables) or a '<' (added-token syntax) */
+    AKSHAR_ST_ALPHABET = 8,      /* reserved: until round 2 the BPE encoder refused a batch that held an added token ('<s>' ...)
+                                  * or a code point HF's NFKC changes; such rows are now encoded exactly by the row kernel
+                                  * (HF's added-token split + NFKC on the device), no entry point raises this bit */
     AKSHAR_ST_SPIN = 16,
-    AKSHAR_ST_WORD = 32,         /* the long-word pool ran out (many words beyond 48 symbols): call again with a larger
-                                    workspace -- half of what exceeds akshar_workspace_bytes() goes to that pool */
+    AKSHAR_ST_WORD = 32,         /* the pool for long words / rows encoded by the exact row kernel ran out: call again with a
+                                    larger workspace -- half of what exceeds akshar_workspace_bytes() goes to the pools */
     AKSHAR_ST_INTERNAL = 64,     /* an internal consistency check failed (never expected): the result is not to be used */
     AKSHAR_ST_BAD_ID = 128,      /* decode: a token id outside the vocabulary of a SentencePiece model (DecodeIds raises
                                     IndexError "piece id is out of range."); HF's decode skips such ids */
