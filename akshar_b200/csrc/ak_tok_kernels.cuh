@@ -430,6 +430,8 @@ __global__ void __launch_bounds__(AKL_THREADS, 4) ak_emit_kernel(const AkEmitArg
     const int64_t id_cap = A.X.id_cap;
     const int32_t bos = A.X.M.kind == 0 ? A.X.M.bpe.bos : -1, eos = A.X.M.kind == 0 ? A.X.M.bpe.eos : -1;
     const int splits_i32 = A.X.splits_i32;
+    const unsigned long long* const cache_e = A.X.M.cache.e;
+    const unsigned long long cache_entries = 1ull << A.X.M.cache.bits;
     const int lane = threadIdx.x & 31;
     const long long n_wt = akt_n_wt(B, A.base0);
     const long long warp0 = ((long long)blockIdx.x * AKL_THREADS + threadIdx.x) >> 5, n_warps = ((long long)gridDim.x * AKL_THREADS) >> 5;
@@ -469,6 +471,20 @@ __global__ void __launch_bounds__(AKL_THREADS, 4) ak_emit_kernel(const AkEmitArg
                     if (splits_i32) ((int32_t*)A.X.splits)[g] = (int32_t)k2;
                     else ((int64_t*)A.X.splits)[g] = k2;
                     if (g < B.n_rows && bos >= 0) ids[k2] = (IdT)bos;
+                }
+            } else if (ty == AKR_CACHE && (r & 0xFFFFFFFFFFFFFFull) < cache_entries && n <= AKC_MAXTOK) {
+                // three to fourteen ids held in the word's cache entry: ids 0-1 in word 3, the rest two per word from word 9
+                if (at + n > id_cap) st |= AK_ST_OVERFLOW;
+                else {
+                    const unsigned long long* en = cache_e + (r & 0xFFFFFFFFFFFFFFull) * AKC_ENTRY;
+                    unsigned long long v = akc_ld(en + 3);
+                    ids[at] = (IdT)(uint32_t)v;
+                    ids[at + 1] = (IdT)(uint32_t)(v >> 32);
+                    for (int j = 2; j < n; j += 2) {
+                        v = akc_ld(en + 8 + (j >> 1));
+                        ids[at + j] = (IdT)(uint32_t)v;
+                        if (j + 1 < n) ids[at + j + 1] = (IdT)(uint32_t)(v >> 32);
+                    }
                 }
             } else {
                 if (at + n > id_cap) st |= AK_ST_OVERFLOW;

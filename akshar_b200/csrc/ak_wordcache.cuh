@@ -90,8 +90,13 @@ AK_HD void akc_key0123(const uint8_t* t, int64_t s, uint32_t len, int64_t te, un
     const uint32_t* last = (const uint32_t*)(((uintptr_t)(t + te) - 1u) & ~(uintptr_t)3);
     const uint32_t sh = (uint32_t)(a & 3u) * 8u;
     uint32_t x[9];
+    if (w + 8 <= last) {                                            // everywhere but in the last 36 bytes of the text
 #pragma unroll
-    for (int i = 0; i < 9; ++i) x[i] = __ldg(w + i <= last ? w + i : last);
+        for (int i = 0; i < 9; ++i) x[i] = __ldg(w + i);
+    } else {
+#pragma unroll
+        for (int i = 0; i < 9; ++i) x[i] = __ldg(w + i <= last ? w + i : last);
+    }
     uint32_t f[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
