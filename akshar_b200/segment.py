@@ -56,6 +56,47 @@ def segment_akshars_batch(texts, matras=False, as_device=False, device=0):
     return clusters if as_device else _slices(texts, clusters)
 
 
+def normalize_and_segment_batch(texts, normalize_roman=True, clean_hinglish=True, matras=False, device=0):
+    """normalize_text then segment_akshars of a batch in ONE library call (akshar_normalize_segment_batch) and two
+    host synchronisations: -> (list of normalized strings, list of akshar lists).  What `aksharTokenizer.tokenize` without a
+    model is; the boundaries come back as one bit per byte."""
+    import numpy as np
+    import torch
+    eng = engine(device)
+    norm, mk = eng.normalize_segment_batch(texts, normalize_roman, clean_hinglish, clusters=True, matras=matras, runs=False)
+    n, rows = norm.end, norm.n_rows
+    W = (n + 32) // 32
+    # everything that goes back in one pinned buffer: text, row offsets, mask words
+    pin = eng.__dict__.get('_small_pin')
+    need = n + 8 * (rows + 1) + 4 * W + 64
+    if pin is None or pin.numel() < need:
+        pin = torch.empty(max(need, 1 << 16), dtype=torch.uint8).pin_memory()
+        eng._small_pin = pin
+    a = (n + 7) & ~7
+    b = a + 8 * (rows + 1)
+    pin[:n].copy_(norm.data[:n], non_blocking=True)
+    pin[a:b].view(torch.int64).copy_(norm.offsets, non_blocking=True)
+    pin[b:b + 4 * W].view(torch.int32).copy_(mk['cluster'][:W], non_blocking=True)
+    torch.cuda.current_stream(eng.device).synchronize()
+    buf = pin.numpy()
+    data = buf[:n].tobytes()
+    off = buf[a:b].view(np.int64)
+    bits = np.unpackbits(buf[b:b + 4 * W], bitorder='little')
+    ends = np.flatnonzero(bits)                      # byte positions where a cluster ends, ascending
+    cut = np.searchsorted(ends, off, side='right')   # ends at or before each row start
+    strings, akshars = [], []
+    for i in range(rows):
+        lo, hi = int(off[i]), int(off[i + 1])
+        strings.append(data[lo:hi].decode('utf-8'))
+        prev = lo
+        parts = []
+        for e in ends[cut[i]:cut[i + 1]].tolist():
+            parts.append(data[prev:e].decode('utf-8'))
+            prev = e
+        akshars.append(parts)
+    return strings, akshars
+
+
 def detect_code_switches_batch(texts, as_device=False, device=0):
     """-> list[list[(segment, label)]]; as_device=True: Ragged(run END offsets, row_splits, uint8 tags)"""
     _, runs = engine(device).segment_batch(texts, clusters=False, runs=True)

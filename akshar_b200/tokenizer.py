@@ -12,7 +12,7 @@ from . import _lib as C
 from .batch import engine
 from .normalize import normalize_text, normalize_batch
 from .segment import (segment_akshars, detect_code_switches, analyze_text_composition, segment_akshars_batch,
-                      analyze_text_composition_batch, detect_code_switches_batch)
+                      analyze_text_composition_batch, detect_code_switches_batch, normalize_and_segment_batch)
 
 _SPM_NORMAL, _SPM_UNKNOWN, _SPM_CONTROL, _SPM_USER, _SPM_UNUSED, _SPM_BYTE = 1, 2, 3, 4, 5, 6
 
@@ -81,13 +81,15 @@ class aksharTokenizer:
         return normalize_batch([text], self.normalize_roman, self.clean_hinglish, device=self._device)[0]
 
     def tokenize(self, text: str, return_metadata: bool = False) -> Union[List[str], dict]:
-        norm = self.preprocess(text)
+        if self.model is None:
+            # normalize + akshars in one library call (two host synchronisations instead of eight)
+            norms, aks = normalize_and_segment_batch([text], self.normalize_roman, self.clean_hinglish, device=self._device)
+            norm, tokens = norms[0], aks[0]
+        else:
+            norm = self.preprocess(text)
+            tokens = self._pieces(self._encode_normalized([norm])[0])
         if return_metadata:
             meta = analyze_text_composition_batch([norm], device=self._device)[0]
-        if self.model is None:
-            tokens = segment_akshars_batch([norm], device=self._device)[0]
-        else:
-            tokens = self._pieces(self._encode_normalized([norm])[0])
         if return_metadata:
             meta['tokens'] = tokens
             meta['token_count'] = len(tokens)
@@ -188,8 +190,7 @@ class aksharTokenizer:
     def tokenize_batch(self, texts):
         """tokenize() over a batch -> list[list[str]]"""
         if self.model is None:
-            norm = normalize_batch(texts, self.normalize_roman, self.clean_hinglish, device=self._device)
-            return segment_akshars_batch(norm, device=self._device)
+            return normalize_and_segment_batch(texts, self.normalize_roman, self.clean_hinglish, device=self._device)[1]
         return [self._pieces(ids) for ids in self.encode_batch(texts)]
 
     def explain_batch(self, texts):

@@ -132,6 +132,11 @@ def test_composition_and_feature_wrappers_golden(A, golden):
     for r in rows[:300]:
         assert fb.tokenize(r['in'], return_metadata=True) == r['meta']
         assert fb.detokenize(r['tokenize']) == r['detok_akshar']
+    # tokenize without a model = normalize + akshars in one library call, boundaries back as bit masks
+    assert fb.tokenize_batch([r['in'] for r in rows]) == [r['tokenize'] for r in rows]
+    for r in rows[::37]:
+        assert fb.tokenize(r['in']) == r['tokenize']
+    assert fb.tokenize_batch([]) == [] and fb.tokenize('') == []
     import akshar.features as F
     assert F.preserve_nukta is A.preserve_nukta
     tb = A.aksharTokenizer(os.path.join(os.path.dirname(__file__), 'golden', 'models', 'bpe24k.json'), 'bpe')
