@@ -303,3 +303,48 @@ def test_decode_cores_against_the_reference(decode_fuzz, golden, models_dir, nam
     if kind == 1:
         _, st = W.decode(kind, 0, [[5, 10 ** 6]])
         assert st == 128                                               # AKSHAR_ST_BAD_ID: DecodeIds raises IndexError
+
+
+# ---- model loaders refuse what they cannot represent (ak_models.cpp) ---------------------------------------------------
+def test_malformed_models_are_refused(models_dir, tmp_path):
+    """ids outside [0, 2^24), non-integral ids, template ids the vocabulary does not hold, added-token options the device
+    matcher does not implement, truncated files: an error string, never a crash (the C ABI wraps the loaders in try/catch
+    and returns AKSHAR_E_MODEL)"""
+    import json
+    good = json.load(open(os.path.join(models_dir, 'bpe_corpus.json'), encoding='utf-8'))
+
+    def load(j):
+        p = tmp_path / 'm.json'
+        p.write_text(json.dumps(j, ensure_ascii=False), encoding='utf-8')
+        return W.load_bpe(str(p))
+
+    assert load(good) == len(set(good['model']['vocab'].values()) | {t['id'] for t in good['added_tokens']})
+    for mutate in (lambda j: j['model']['vocab'].__setitem__('zz', -5),
+                   lambda j: j['model']['vocab'].__setitem__('zz', 1 << 40),
+                   lambda j: j['model']['vocab'].__setitem__('zz', 7.5),
+                   lambda j: j['added_tokens'][0].__setitem__('id', -1),
+                   lambda j: j['added_tokens'][0].__setitem__('single_word', True),
+                   lambda j: j['added_tokens'][0].__setitem__('content', ''),
+                   lambda j: j['post_processor']['special_tokens']['<s>'].__setitem__('ids', [1 << 30]),
+                   lambda j: j['model'].__setitem__('merges', ['a']),
+                   lambda j: j.__setitem__('model', {'type': 'WordPiece'})):
+        j = json.loads(json.dumps(good))
+        mutate(j)
+        with pytest.raises(ValueError):
+            load(j)
+    raw = open(os.path.join(models_dir, 'bpe_corpus.json'), 'rb').read()
+    (tmp_path / 't.json').write_bytes(raw[:len(raw) // 2])
+    with pytest.raises(ValueError):
+        W.load_bpe(str(tmp_path / 't.json'))
+    spm = open(os.path.join(models_dir, 'spm_corpus.model'), 'rb').read()
+    for cut in (0, 1, 7, len(spm) // 3, len(spm) - 3):
+        (tmp_path / 't.model').write_bytes(spm[:cut])
+        try:
+            W.load_spm(str(tmp_path / 't.model'))          # a prefix that happens to parse is fine; a crash is not
+        except ValueError:
+            pass
+    (tmp_path / 't.model').write_bytes(b'\xff' * 64)
+    with pytest.raises(ValueError):
+        W.load_spm(str(tmp_path / 't.model'))
+    W.load_bpe(os.path.join(models_dir, 'bpe24k.json'))
+    W.load_spm(os.path.join(models_dir, 'spm24k.model'))
