@@ -754,6 +754,35 @@ def test_cabi_error_codes(A, eng, models_dir):
     assert lib.akshar_vocab_size(fresh._h, 0) == C.E_NOMODEL and lib.akshar_vocab_size(fresh._h, 7) == C.E_ARG
     assert lib.akshar_load_bpe_json(fresh._h, b'{"not": "a tokenizer"}', 22) == C.E_MODEL
     assert lib.akshar_load_spm_model(fresh._h, b'\x00\x01\x02', 3) == C.E_MODEL
+    # the round-2 entry points: same conventions
+    i32 = torch.empty(64, dtype=torch.int32, device=dev)
+    sp = torch.zeros(3, dtype=torch.int64, device=dev)
+    assert lib.akshar_word_tokenize_batch(eng._h, b.data.data_ptr(), b.offsets.data_ptr(), 2, 0, b.end, 9, i32.data_ptr(),
+                                          i32.data_ptr(), 64, sp.data_ptr(), None, res.data_ptr(), ws.data_ptr(), ws.numel(), None) == C.E_ARG
+    assert lib.akshar_word_tokenize_batch(eng._h, b.data.data_ptr(), b.offsets.data_ptr(), 2, 0, b.end, 0, i32.data_ptr(),
+                                          i32.data_ptr(), 64, sp.data_ptr(), None, res.data_ptr(), ws.data_ptr(), 16, None) == C.E_WORKSPACE
+    assert lib.akshar_decode_batch(fresh._h, 0, 0, i32.data_ptr(), 0, 2, sp.data_ptr(), 2, out.data_ptr(), 64, off.data_ptr(),
+                                   res.data_ptr(), ws.data_ptr(), ws.numel(), None) == C.E_NOMODEL
+    assert lib.akshar_decode_batch(eng._h, 3, 0, i32.data_ptr(), 0, 2, sp.data_ptr(), 2, out.data_ptr(), 64, off.data_ptr(),
+                                   res.data_ptr(), ws.data_ptr(), ws.numel(), None) == C.E_ARG
+    assert lib.akshar_lines_batch(eng._h, b.data.data_ptr(), b.end, out.data_ptr(), 64, off.data_ptr(), 2, res.data_ptr(),
+                                  ws.data_ptr(), 8, None) == C.E_WORKSPACE
+    assert lib.akshar_lines_batch(eng._h, None, 5, out.data_ptr(), 64, off.data_ptr(), 2, res.data_ptr(), ws.data_ptr(),
+                                  ws.numel(), None) == C.E_ARG
+    assert lib.akshar_segment_batch(eng._h, b.data.data_ptr(), b.offsets.data_ptr(), 2, 0, b.end, C.SEG_CLUSTERS | C.SEG_MASK,
+                                    C.MODE_ROWS, i32.data_ptr(), 64, None, None, None, 0, None, res.data_ptr(), ws.data_ptr(),
+                                    ws.numel(), None) == C.E_ARG           # masks: tile mode only
+    assert lib.akshar_segment_batch(eng._h, b.data.data_ptr(), b.offsets.data_ptr(), 2, 0, b.end, C.SEG_CLUSTERS | C.SEG_MASK,
+                                    C.MODE_TILES, i32.data_ptr(), 0, None, None, None, 0, None, res.data_ptr(), ws.data_ptr(),
+                                    ws.numel(), None) == C.E_ARG           # mask capacity in words too small
+    assert lib.akshar_merge_clusters_batch(eng._h, b.data.data_ptr(), b.offsets.data_ptr(), 2, i32.data_ptr(), sp.data_ptr(), 0, 5,
+                                           i32.data_ptr(), 64, sp.data_ptr(), res.data_ptr(), ws.data_ptr(), ws.numel(), None) == C.E_ARG
+    assert lib.akshar_join_rows(eng._h, b.data.data_ptr(), b.offsets.data_ptr(), 2, 300, out.data_ptr(), None) == C.E_ARG
+    # a row too short for the output capacity: totals exact, AKSHAR_ST_OVERFLOW, nothing written out of bounds
+    assert lib.akshar_word_tokenize_batch(eng._h, b.data.data_ptr(), b.offsets.data_ptr(), 2, 0, b.end, 1, i32.data_ptr(),
+                                          i32.data_ptr(), 1, sp.data_ptr(), None, res.data_ptr(), ws.data_ptr(), ws.numel(), None) == C.OK
+    r = res.cpu()
+    assert int(r[0]) == 2 and int(r[2]) & C.ST_OVERFLOW
     # the Python layer maps them onto the reference's exceptions (tokenizer.py:88-102)
     with pytest.raises(RuntimeError):
         A.aksharTokenizer(os.path.join(models_dir, 'bpe24k.json'))            # a BPE JSON loaded as sentencepiece
