@@ -4,11 +4,6 @@
 #define AK_SPAN 32
 #define AK_TILE (AK_BLOCK * AK_SPAN)
 #define AK_LOOKBACK_LIMIT 4096          // bytes a span may walk backwards in AKSHAR_MODE_TILES
-#define AK_BPE_STAGE 40                 // ids per thread staged in shared memory (>= AK_SPAN + a few <s> / </s>)
-#define AKB_STAGE 24                    // same, fast kernel (16-byte chunks)
-#define AKB_EVCAP 512                   // events (row starts + word starts) per warp tile kept in shared memory
-#define AKW_GROUP 256                   // warp tiles per scan group (one CTA of the sums / copy kernels)
-#define AKS_STAGE 18                    // cluster / run ends per lane staged in shared memory (fast segment kernel)
 #define AK_ROWS_BLOCK 128               // rows per tile for the row-per-thread kernels
 #define AKF_WARPS (AK_BLOCK / 32)
 #define AKF_TILE (AKF_WARPS * AKF_WARP_BYTES)     // 3840 text bytes per CTA tile in the fast kernels
@@ -106,11 +101,10 @@ __device__ __forceinline__ int ak_next_tile(int* ticket, int* sh) {
 
 
 // ------------------------------------------------------------------------------------------------
-// Warp tiles.  The fast BPE and segment kernels are warp-autonomous: a warp owns 480 text bytes (30 real lanes +
-// 2 halo lanes), finds the rows that start in them with shuffles, encodes, and appends its output to its CTA's
-// private slice of a temporary stream (cursor in shared memory) -- no CTA barrier and no global atomic on the hot
-// path, so a slow lane (cache miss, long word, slow-lane walker) only delays its own warp.  A scan over the
-// per-warp-tile totals then gives the final positions and a copy kernel moves the blocks.
+// Warp tiles.  The bit-stream kernels are warp-autonomous: a warp owns 960 text bytes (30 real lanes of 32 bytes + 2 halo
+// lanes), finds the rows that start in them with shuffles and counts / writes its outputs without a CTA barrier or a
+// global atomic, so a slow lane only delays its own warp.  Where outputs are compacted, a count pass and a scan over the
+// per-warp-tile totals give every warp its final position before the emit pass runs.
 // ------------------------------------------------------------------------------------------------
 
 // wrow[k] = first row r in [0, n_rows] with off[r] >= base0 + k * 480 (n_rows + 1 if none); one thread per entry
@@ -122,27 +116,6 @@ __global__ void ak_warp_rows_kernel(AkBatch B, int64_t base0, int n_entries, int
     int64_t r = ak_row_lower_bound(B.off, 0, B.n_rows, pos);
     if (B.off[r] < pos) r = B.n_rows + 1;
     wrow[k] = r;
-}
-
-__device__ __forceinline__ int akw_n_tiles(const AkBatch& B, int64_t base0) {
-    return (int)((B.text_end - base0 + AKF_WARP_BYTES) / AKF_WARP_BYTES);      // covers position text_end itself
-}
-
-// each lane's 16-bit row-start mask for its chunk [cs, cs + 16), from the sorted row offsets (no shared memory)
-
-
-// sums of AKW_GROUP consecutive warp-tile totals
-__global__ void __launch_bounds__(AKW_GROUP) ak_wt_sums_kernel(AkBatch B, int64_t base0, const int32_t* wt_total, int32_t* sums) {
-    __shared__ int ws[33];
-    if (!ak_batch_begin(B)) return;
-    const int n_wt = akw_n_tiles(B, base0);
-    const int n_groups = (n_wt + AKW_GROUP - 1) / AKW_GROUP;
-    for (int gidx = blockIdx.x; gidx < n_groups; gidx += gridDim.x) {
-        const int t = gidx * AKW_GROUP + threadIdx.x;
-        int total;
-        ak_block_exscan<AKW_GROUP>(t < n_wt ? wt_total[t] : 0, ws, total);
-        if (threadIdx.x == 0) sums[gidx] = total;
-    }
 }
 
 // Slow chunks are not processed where they are found: a lane that cannot take the fast lane appends its chunk to a

@@ -72,7 +72,7 @@ struct akshar_ctx {
     bool wc_hold = false;          // akshar_word_cache_hold(1): never restore the image, however full the cache
     cudaEvent_t tev[AKSHAR_TIMER_COUNT][2] = {};
     bool tev_valid[AKSHAR_TIMER_COUNT] = {};
-    int occ_norm = 0, occ_seg = 0, occ_uni = 0, occ_sig = 0, occ_nf_write = 0, occ_nf3 = 0, occ_sf3 = 0;
+    int occ_norm = 0, occ_seg = 0, occ_uni = 0, occ_sig = 0, occ_nf_write = 0, occ_nf3 = 0;
 };
 
 // the entry points run on the context's device and leave the caller's current device as they found it
@@ -167,7 +167,6 @@ int akshar_ctx_create(int device, akshar_ctx** out) {
     AK_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_norm, ak_normalize_kernel, AK_BLOCK, 0));
     AK_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_nf_write, ak_nf_write_kernel, AK_BLOCK, 0));
     AK_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_nf3, ak_nf3_classify_kernel, AKN3_THREADS, 0));
-    AK_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_sf3, ak_sf3_kernel, AKS3_THREADS, 0));
     AK_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_seg, ak_segment_kernel, AK_BLOCK, 0));
     AK_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_uni, ak_unigram_kernel, AK_ROWS_BLOCK, 0));
     AK_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_sig, ak_signature_kernel, AK_ROWS_BLOCK, 0));
@@ -243,10 +242,6 @@ static inline int64_t ak_tiles_of(int64_t n_bytes, int64_t n_rows) {
     int64_t b = (n_rows + AK_ROWS_BLOCK - 1) / AK_ROWS_BLOCK;
     return (a > b ? a : b) + 1;
 }
-static inline size_t ak_pool_ints(int64_t n_bytes) {
-    int64_t p = n_bytes / 2 + (1 << 16);
-    return (size_t)p;
-}
 struct AkTokWs {
     size_t wrow, count, wt_ids, wt_base, wt_seg, wt_segx, scan_state, row_flag, row_ev, row_fix, pool, longpool, slots, total;
     size_t pool_ints, longpool_ints;
@@ -280,10 +275,11 @@ static AkTokWs ak_tok_ws(int64_t n_bytes, int64_t n_rows) {
 }
 
 struct AkWsLayout {
-    size_t control, state, tile_row, nfc_text, nfc_off, pool, bf_tiles, bf_temp, scratch, total;
-    int64_t bf_temp_cap;
-    int64_t nfc_cap;
+    size_t control, state, tile_row, scratch, total;
 };
+// [0, 256) control block, then the zeroed tile-state area (look-back states of the walker kernels, scan states), the
+// tile -> row table of the normalize kernels, and a scratch region shared by whatever stage runs: its size is the largest
+// any entry point needs for this text
 static AkWsLayout ak_ws_layout(int64_t n_bytes, int64_t n_rows) {
     AkWsLayout L;
     size_t tiles = (size_t)ak_tiles_of(n_bytes, n_rows);
@@ -292,31 +288,19 @@ static AkWsLayout ak_ws_layout(int64_t n_bytes, int64_t n_rows) {
     L.tile_row = L.state + ak_align(4 * tiles * 8);
     size_t at = L.tile_row + ak_align(8 * (tiles * AKF_WARPS + 2));
     L.scratch = at;
-    size_t uni = 4 * (size_t)(n_bytes + 2 * n_rows + 2);
-    L.nfc_cap = n_bytes + n_bytes / 8 + 1024;
-    L.nfc_text = at;
-    L.nfc_off = L.nfc_text + ak_align((size_t)L.nfc_cap);
-    L.pool = L.nfc_off + ak_align(8 * (size_t)(n_rows + 1));
-    L.bf_tiles = L.pool + ak_align(4 * ak_pool_ints(n_bytes));
-    {
-        const size_t nwt = tiles * AKF_WARPS + 8, ng = nwt / AKW_GROUP + 2;
-        L.bf_temp = L.bf_tiles + ak_align((nwt + 2) * 8) + ak_align(nwt * 4) + ak_align(nwt * 8) + ak_align(ng * 4) + ak_align((ng + 1) * 8);
-    }
-    L.bf_temp_cap = n_bytes / 2 + 2 * n_rows + 1024;
-    size_t bpe = (L.bf_temp + ak_align(4 * (size_t)L.bf_temp_cap)) - at;
+    // Unigram row kernel / signatures: one 4-byte slot per code point (+ 2 per row)
+    size_t m = 4 * (size_t)(n_bytes + 2 * n_rows + 2);
     // fast normalize: per-lane info words, tile totals / bases, slow work list
-    size_t nf = ak_align(tiles * AK_BLOCK * 4) + ak_align(tiles * 4) + ak_align((tiles + 1) * 8) +
-                ak_align((tiles * AK_BLOCK / 16 + 1024) * sizeof(AkSlowEntry));
-    // fast segment: tile totals / offsets / bases for two streams + the temporary streams
-    const size_t sf_nwt = tiles * AKF_WARPS + 8, sf_ng = sf_nwt / AKW_GROUP + 2;
-    size_t sf = ak_align((sf_nwt + 2) * 8) + 2 * ak_align(sf_nwt * 4) + 2 * ak_align(sf_nwt * 8) + 2 * ak_align(sf_ng * 4) +
-                2 * ak_align((sf_ng + 1) * 8) +
-                ak_align((size_t)(n_bytes / 2 + n_rows + 1024) * 4) + ak_align((size_t)(n_bytes / 8 + n_rows + 1024) * 5);
-    size_t m = uni > bpe ? uni : bpe;
-    if (sf > m) m = sf;
+    const size_t nf = ak_align(tiles * AK_BLOCK * 4) + ak_align(tiles * 4) + ak_align((tiles + 1) * 8) +
+                      ak_align((tiles * AK_BLOCK / 16 + 1024) * sizeof(AkSlowEntry));
+    if (nf > m) m = nf;
+    // segment / word tokenizers: warp-tile row table, two counts and two bases per 960-byte warp tile
+    const size_t n_wt = (size_t)n_bytes / AKN3_WARP_BYTES + 3;
+    const size_t sg = ak_align((2 * n_wt + 3) * 8) + 2 * ak_align(n_wt * 4) + 2 * ak_align(n_wt * 8);
+    if (sg > m) m = sg;
     const size_t tok = ak_tok_ws(n_bytes, n_rows).total;
     if (tok > m) m = tok;
-    L.total = at + ak_align(m > nf ? m : nf);
+    L.total = at + ak_align(m);
     return L;
 }
 

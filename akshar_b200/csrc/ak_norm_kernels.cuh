@@ -283,68 +283,6 @@ __global__ void __launch_bounds__(128, AKN_SLOW_MINB) ak_nf_slow_kernel(const Ak
     }
 }
 
-// ---- K1c: exclusive prefix of the tile totals (one CTA; the array has one entry per 3840 bytes of text)
-__global__ void __launch_bounds__(1024) ak_nf_scan_kernel(const int32_t* tile_total, int64_t* tile_base, int n_tiles,
-                                                          int64_t* total_out, AkBatch B, int64_t base0,
-                                                          int64_t bytes_per_entry = AKF_TILE) {
-    __shared__ long long ws[33];
-    __shared__ long long carry;
-    if (!ak_batch_begin(B)) return;
-    if (B.dyn_end) {
-        if (bytes_per_entry == AKF_TILE) n_tiles = (int)((B.text_end - base0 + AKF_TILE) / AKF_TILE);
-        else {
-            const int n_wt = (int)((B.text_end - base0 + AKF_WARP_BYTES) / AKF_WARP_BYTES);
-            n_tiles = (n_wt + AKW_GROUP - 1) / AKW_GROUP;
-        }
-    }
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) carry = 0;
-    __syncthreads();
-    // 8 consecutive entries per thread (a serial prefix in registers), so one trip of the block scan covers 8192 entries
-    for (int b = 0; b < n_tiles; b += 8192) {
-        const int i0 = b + tid * 8;
-        int v8[8];
-        long long v = 0;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            v8[k] = (i0 + k < n_tiles) ? tile_total[i0 + k] : 0;
-            v += v8[k];
-        }
-        long long inc = v;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            long long y = __shfl_up_sync(0xFFFFFFFFu, inc, d);
-            if (lane >= d) inc += y;
-        }
-        if (lane == 31) ws[warp] = inc;
-        __syncthreads();
-        if (warp == 0) {
-            long long x = ws[lane], xi = x;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                long long y = __shfl_up_sync(0xFFFFFFFFu, xi, d);
-                if (lane >= d) xi += y;
-            }
-            ws[lane] = xi - x;
-            if (lane == 31) ws[32] = xi;
-        }
-        __syncthreads();
-        long long ex = carry + ws[warp] + inc - v;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            if (i0 + k < n_tiles) tile_base[i0 + k] = ex;
-            ex += v8[k];
-        }
-        __syncthreads();
-        if (tid == 0) carry += ws[32];
-        __syncthreads();
-    }
-    if (tid == 0) {
-        tile_base[n_tiles] = carry;
-        *total_out = carry;
-    }
-}
-
 // The writer's common case: the emitted bytes of a chunk are ONE contiguous stretch of its 20-byte window (nothing dropped
 // inside; the first bytes may belong to the previous chunk's last code point, the last code point may reach into the next
 // chunk).  A-Z lowered four bytes at a time, the stretch moved with funnel shifts: bytes up to the destination's next word

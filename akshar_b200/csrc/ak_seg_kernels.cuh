@@ -53,58 +53,40 @@ __global__ void __launch_bounds__(AK_BLOCK) ak_segment_kernel(const AkSegArgs A)
 
 
 // ------------------------------------------------------------------------------------------------
-// K2 + K3 fast: grapheme clusters and script runs (ak_seg_fast.cuh), warp tiles.  Two temporary streams (cluster
-// ends; run ends + tags), each with per-CTA slices.
+// K2 + K3 from parallel bit streams (ak_seg3.cuh), offset form: END byte offsets of the clusters / runs of every row.
+// Two passes over the text, both warp-autonomous (a warp owns 960 text bytes: 30 real lanes + 2 halo lanes): the count pass
+// leaves the number of cluster ends and run ends of every warp tile (popcounts of the event masks; the exact walker counts
+// for its slow lanes), two scans (ak_scan_counts_kernel) turn them into bases, the emit pass classifies again and writes
+// every offset, tag and row split at its final place.  No temporary stream, no copy kernel, no ordering between warps
+// (round 1 wrote to per-CTA slices of a temporary stream and copied: twice the output traffic, 1.5 ms per GiB of copies).
 // ------------------------------------------------------------------------------------------------
-struct AkSfArgs {
+struct AkSegOffArgs {
     AkBatch B;
     AkTables T;
     uint32_t flags;
-    const int64_t* wrow;
+    const int64_t* wrow;               // first row at or after base0 + 480 k
     int64_t base0;
-    int32_t* tc;                 // temporary streams (sliced per CTA)
-    int32_t* tr;
-    uint8_t* tt;
-    int64_t c_slice, r_slice;
-    int32_t* c_total;            // per warp tile
-    int64_t* c_toff;
-    int32_t* r_total;
-    int64_t* r_toff;
-    int32_t* c_sums;             // per group of AKW_GROUP warp tiles, and their exclusive prefix
-    int64_t* c_sum_base;
-    int32_t* r_sums;
-    int64_t* r_sum_base;
-    AkSegOut o;                  // final outputs
+    int32_t* c_count;                  // [n_wt]
+    int32_t* r_count;
+    const int64_t* c_base;             // [n_wt] exclusive prefixes
+    const int64_t* r_base;
+    AkSegOut o;                        // the final outputs
 };
 
-
-// ---- K2 + K3 v3: the same outputs from parallel bit streams (ak_seg3.cuh): 32 bytes per lane, a warp covers two
-// 480-byte warp tiles (lanes 1-15 and 16-30), so the bookkeeping per warp tile -- totals, temporary-stream offsets,
-// tile-relative splits -- and with it the sums / scan / copy kernels stay as they are.  Counts are popcounts of the
-// event masks, known before anything is written: no shared-memory staging, the events go straight to the lane's
-// place in the temporary stream.
-#define AKS3_THREADS 128
-#ifndef AKS3_MINB
-#define AKS3_MINB 8
-#endif
-__global__ void __launch_bounds__(AKS3_THREADS, AKS3_MINB) ak_sf3_kernel(const AkSfArgs A) {
-    __shared__ unsigned int s_cursor[2];
+#define AKSO_THREADS 128
+template <bool EMIT>
+__global__ void __launch_bounds__(AKSO_THREADS, 8) ak_seg_off_kernel(const AkSegOffArgs A) {
     AkBatch B = A.B;
     if (!ak_batch_begin(B)) return;
     const bool want_c = (A.flags & AK_SEG_CLUSTERS) != 0, want_r = (A.flags & AK_SEG_RUNS) != 0;
     const bool matras = (A.flags & AK_SEG_MATRAS) != 0;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid < 2) s_cursor[tid] = 0;
-    __syncthreads();
-    const int n_wt = akw_n_tiles(B, A.base0);
-    const int n_w3 = (n_wt + 1) >> 1;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t tb = B.text_begin, te = B.text_end;
-    const int64_t cslice = (int64_t)blockIdx.x * A.c_slice, rslice = (int64_t)blockIdx.x * A.r_slice;
-    for (int w3 = blockIdx.x * (AKS3_THREADS / 32) + warp; w3 < n_w3; w3 += gridDim.x * (AKS3_THREADS / 32)) {
-        const int wt0 = 2 * w3;
-        const bool two = wt0 + 1 < n_wt;
-        const int64_t ws = A.base0 + (int64_t)wt0 * AKF_WARP_BYTES;
-        const int64_t r_w0 = A.wrow[wt0], r_w2 = A.wrow[two ? wt0 + 2 : wt0 + 1];
+    const long long n_wt = (te - A.base0 + AKN3_WARP_BYTES) / AKN3_WARP_BYTES;
+    uint32_t st = 0;
+    for (long long wt = (long long)blockIdx.x * (AKSO_THREADS / 32) + warp; wt < n_wt; wt += (long long)gridDim.x * (AKSO_THREADS / 32)) {
+        const int64_t ws = A.base0 + wt * AKN3_WARP_BYTES;
+        const int64_t r_w0 = A.wrow[2 * wt], r_w2 = A.wrow[2 * wt + 2];
         const int64_t cs = ws + (int64_t)(lane - 1) * 32;
         AkS3Lane L;
         {
@@ -134,10 +116,10 @@ __global__ void __launch_bounds__(AKS3_THREADS, AKS3_MINB) ak_sf3_kernel(const A
         const bool real = lane >= 1 && lane <= 30;
         const int64_t ss = cs < tb ? tb : cs;
         const int64_t se = cs + 32 > te + 1 ? te + 1 : cs + 32;
-        const bool active = real && ss < se && (two || lane <= 15);
+        const bool active = real && ss < se;
         // index of the first row that starts at or after this lane's first position
-        int64_t nr;
-        {
+        int64_t nr = 0;
+        if (EMIT) {
             const int mine = real ? __popc(L.rows) : 0;
             int inc = mine;
 #pragma unroll
@@ -150,10 +132,9 @@ __global__ void __launch_bounds__(AKS3_THREADS, AKS3_MINB) ak_sf3_kernel(const A
         }
         const uint32_t tb_bit = (tb >= cs && tb < cs + 32) ? 1u << (int)(tb - cs) : 0u;
         const uint32_t rows_ev = L.rows & ~tb_bit;
-        bool slow = false;
-        uint32_t st = 0;
-        int cc = 0, rc = 0;
         const int64_t rlo = r_w0 > 0 ? r_w0 - 1 : 0, rhi = r_w2 > B.n_rows ? B.n_rows : r_w2;
+        bool slow = false;
+        int cc = 0, rc = 0;
         if (active) {
             slow = !aks3_phase3(L, up2p, tb_bit, matras, want_c, want_r);
             if (slow) {
@@ -168,7 +149,6 @@ __global__ void __launch_bounds__(AKS3_THREADS, AKS3_MINB) ak_sf3_kernel(const A
                 if (want_r) rc = __popc(L.rchg) + nre;
             }
         }
-        // one scan for both counts (a lane has at most 33 events per stream)
         int inc2 = cc | (rc << 16);
         const int mine2 = inc2;
 #pragma unroll
@@ -176,132 +156,40 @@ __global__ void __launch_bounds__(AKS3_THREADS, AKS3_MINB) ak_sf3_kernel(const A
             const int y = __shfl_up_sync(0xFFFFFFFFu, inc2, d);
             if (lane >= d) inc2 += y;
         }
-        const int tot2 = __shfl_sync(0xFFFFFFFFu, inc2, 31), half2 = __shfl_sync(0xFFFFFFFFu, inc2, 15);
-        const int ctot = tot2 & 0xFFFF, rtot = tot2 >> 16, chalf = half2 & 0xFFFF, rhalf = half2 >> 16;
-        const int cpre = (inc2 - mine2) & 0xFFFF, rpre = (inc2 - mine2) >> 16;
-        unsigned int ctoff = 0, rtoff = 0;
-        if (lane == 0) {
-            ctoff = atomicAdd(&s_cursor[0], (unsigned int)ctot);
-            rtoff = atomicAdd(&s_cursor[1], (unsigned int)rtot);
-        }
-        ctoff = __shfl_sync(0xFFFFFFFFu, ctoff, 0);
-        rtoff = __shfl_sync(0xFFFFFFFFu, rtoff, 0);
-        const bool fits = (int64_t)ctoff + ctot <= A.c_slice && (int64_t)rtoff + rtot <= A.r_slice;
-        if (lane == 0) {
-            A.c_total[wt0] = chalf;
-            A.c_toff[wt0] = cslice + ctoff;
-            A.r_total[wt0] = rhalf;
-            A.r_toff[wt0] = rslice + rtoff;
-            if (two) {
-                A.c_total[wt0 + 1] = ctot - chalf;
-                A.c_toff[wt0 + 1] = cslice + ctoff + chalf;
-                A.r_total[wt0 + 1] = rtot - rhalf;
-                A.r_toff[wt0 + 1] = rslice + rtoff + rhalf;
+        if (!EMIT) {
+            if (lane == 31) {
+                A.c_count[wt] = inc2 & 0xFFFF;
+                A.r_count[wt] = inc2 >> 16;
             }
-            if (!fits) st |= AK_ST_OVERFLOW;
+            continue;
         }
-        if (active) {
-            const bool second = lane > 15;
-            const int cpre_t = second ? cpre - chalf : cpre, rpre_t = second ? rpre - rhalf : rpre;      // tile-relative
-            int32_t* cdst = A.tc + cslice + ctoff;
-            int32_t* rdst = A.tr + rslice + rtoff;
-            uint8_t* tdst = A.tt + rslice + rtoff;
-            if (slow) {
-                AkSegOut o = A.o;
-                o.cluster_ends = cdst + (second ? chalf : 0);
-                o.run_ends = rdst + (second ? rhalf : 0);
-                o.run_tags = tdst + (second ? rhalf : 0);
-                o.cbase = cpre_t;
-                o.rbase = rpre_t;
-                o.ccap = fits ? (second ? ctot - chalf : chalf) : 0;
-                o.rcap = fits ? (second ? rtot - rhalf : rhalf) : 0;
-                uint32_t st2 = 0;
-                int64_t a, b;
-                ak_seg_span(A.T, B.text, B.off, B.n_rows, rlo, rhi, ss, se, A.flags, AK_LOOKBACK_LIMIT, true, o, a, b, st2);
-            } else {
-                const uint32_t mc = want_c ? (L.brk | rows_ev) : 0u, mr = want_r ? (L.rchg | rows_ev) : 0u;
-                if (fits) {
-                    const int64_t rs_in = nr > 0 ? B.off[nr - 1] : B.off[0];
-                    if (want_c) aks3_emit(L, mc, cs, rs_in, cdst + cpre, nullptr);
-                    if (want_r) aks3_emit(L, mr, cs, rs_in, rdst + rpre, tdst + rpre);
-                }
-                if (L.rows)
-                    aks3_splits(L, mc, mr, cs, B.off, B.n_rows, nr, cpre_t, rpre_t, want_c ? A.o.cluster_splits : nullptr,
-                                want_r ? A.o.run_splits : nullptr);
+        if (!active) continue;
+        const int64_t cat = (want_c ? A.c_base[wt] : 0) + ((inc2 - mine2) & 0xFFFF);       // my first cluster end / run end
+        const int64_t rat = (want_r ? A.r_base[wt] : 0) + ((inc2 - mine2) >> 16);
+        const bool fits = cat + cc <= A.o.ccap && rat + rc <= A.o.rcap;
+        if (!fits) st |= AK_ST_OVERFLOW;
+        if (slow) {
+            AkSegOut o = A.o;
+            o.cbase = cat;
+            o.rbase = rat;
+            if (!fits) o.ccap = o.rcap = 0;
+            uint32_t st2 = 0;
+            int64_t a, b;
+            ak_seg_span(A.T, B.text, B.off, B.n_rows, rlo, rhi, ss, se, A.flags, AK_LOOKBACK_LIMIT, true, o, a, b, st2);
+        } else {
+            const uint32_t mc = want_c ? (L.brk | rows_ev) : 0u, mr = want_r ? (L.rchg | rows_ev) : 0u;
+            if (fits) {
+                const int64_t rs_in = nr > 0 ? B.off[nr - 1] : B.off[0];
+                if (want_c) aks3_emit(L, mc, cs, rs_in, A.o.cluster_ends + cat, nullptr);
+                if (want_r) aks3_emit(L, mr, cs, rs_in, A.o.run_ends + rat, A.o.run_tags + rat);
             }
-        }
-        ak_raise(B.result, st);
-    }
-}
-
-// Flat copy of one warp's 32 consecutive warp-tile blocks from the temporary stream to their (contiguous) final range:
-// lane k moves elements k, k + 32, ... of the whole range, four loads in flight; the tile an element belongs to comes
-// from the exclusive prefix in shared memory (s_excl[0..32], s_delta[j] = block start in temp - exclusive prefix).
-template <class T>
-__device__ __forceinline__ void akw_flat_copy(const T* temp, T* out, int64_t dst0, int W, const int* s_excl, const long long* s_delta,
-                                              int lane) {
-    int j = 0;
-    for (int k = lane; k < W; k += 128) {
-        long long sidx[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int kk = k + 32 * u;
-            if (kk < W) {
-                while (kk >= s_excl[j + 1]) ++j;
-                sidx[u] = s_delta[j] + kk;
-            } else sidx[u] = -1;
-        }
-        T v[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) if (sidx[u] >= 0) v[u] = temp[sidx[u]];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) if (sidx[u] >= 0) out[dst0 + k + 32 * u] = v[u];
-    }
-}
-
-__global__ void __launch_bounds__(AKW_GROUP) ak_sf_copy_kernel(const AkSfArgs A) {
-    __shared__ int ws[33];
-    __shared__ int s_excl[AKW_GROUP / 32][33];
-    __shared__ long long s_delta[AKW_GROUP / 32][32];
-    AkBatch B = A.B;
-    if (!ak_batch_begin(B)) return;
-    const bool want_c = (A.flags & AK_SEG_CLUSTERS) != 0, want_r = (A.flags & AK_SEG_RUNS) != 0;
-    const int n_wt = akw_n_tiles(B, A.base0);
-    const int n_groups = (n_wt + AKW_GROUP - 1) / AKW_GROUP;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int gidx = blockIdx.x; gidx < n_groups; gidx += gridDim.x) {
-        const int t = gidx * AKW_GROUP + tid;
-        const int64_t r0 = t < n_wt ? A.wrow[t] : 0, r1 = t < n_wt ? A.wrow[t + 1] : 0;
-        for (int pass = 0; pass < 2; ++pass) {
-            if (pass == 0 ? !want_c : !want_r) continue;
-            const int32_t* totals = pass == 0 ? A.c_total : A.r_total;
-            const int64_t* toffs = pass == 0 ? A.c_toff : A.r_toff;
-            int64_t* splits = pass == 0 ? A.o.cluster_splits : A.o.run_splits;
-            const int mine = t < n_wt ? totals[t] : 0;
-            int total;
-            const int pre = ak_block_exscan<AKW_GROUP>(mine, ws, total);
-            const int64_t dst = (pass == 0 ? A.c_sum_base[gidx] : A.r_sum_base[gidx]) + pre;
-            for (int64_t r = r0; r < r1 && r <= B.n_rows; ++r) splits[r] += dst;       // rows that start in my warp tile
-            const int pre_w = __shfl_sync(0xFFFFFFFFu, pre, 0);
-            __syncwarp();
-            s_excl[warp][lane] = pre - pre_w;
-            s_delta[warp][lane] = (t < n_wt ? toffs[t] : 0) - (long long)(pre - pre_w);
-            const int W = __shfl_sync(0xFFFFFFFFu, pre + mine, 31) - pre_w;
-            if (lane == 0) s_excl[warp][32] = 0x7FFFFFFF;
-            __syncwarp();
-            const int64_t dst0 = __shfl_sync(0xFFFFFFFFu, dst, 0);
-            if (dst0 + W > (pass == 0 ? A.o.ccap : A.o.rcap)) { if (lane == 0 && W > 0) ak_raise(B.result, AK_ST_OVERFLOW); }
-            else if (pass == 0) akw_flat_copy<int32_t>(A.tc, A.o.cluster_ends, dst0, W, s_excl[warp], s_delta[warp], lane);
-            else {
-                akw_flat_copy<int32_t>(A.tr, A.o.run_ends, dst0, W, s_excl[warp], s_delta[warp], lane);
-                akw_flat_copy<uint8_t>(A.tt, A.o.run_tags, dst0, W, s_excl[warp], s_delta[warp], lane);
-            }
-            __syncthreads();
+            if (L.rows)
+                aks3_splits(L, mc, mr, cs, B.off, B.n_rows, nr, cat, rat, want_c ? A.o.cluster_splits : nullptr,
+                            want_r ? A.o.run_splits : nullptr);
         }
     }
+    ak_raise(B.result, st);
 }
-
-
 
 // ---- AKSHAR_SEG_MASK: the same boundaries as bit masks, one bit per text byte -------------------------------------------
 // Bit (p - text_begin) of a mask is set when a cluster / script run ENDS at byte position p (text_begin < p <= text_end;
