@@ -329,6 +329,12 @@ static int ak_begin(akshar_ctx* ctx, const uint8_t* d_text, const int64_t* d_row
         return AKSHAR_E_ARG;
     }
     const int64_t n_bytes = text_end - text_begin;
+    // positions inside a call are 32-bit (event records, tile-relative offsets) and a row index shares a 32-bit word with
+    // three kind bits: larger inputs are fed as several calls (row ranges keep their absolute offsets: text_begin / text_end)
+    if (n_bytes >= AKSHAR_MAX_CALL_BYTES || n_rows >= AKSHAR_MAX_CALL_ROWS) {
+        ctx->err = "batch too large for one call: at most 4 GiB - 64 KiB of text and 2^29 - 1 rows; split it by row ranges";
+        return AKSHAR_E_ARG;
+    }
     C.ctx = ctx;
     C.L = ak_ws_layout(n_bytes, n_rows);
     if (!d_workspace || workspace_bytes < C.L.total) {

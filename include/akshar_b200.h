@@ -36,6 +36,11 @@ enum {
     AKSHAR_E_WORKSPACE = -5,
 };
 
+/* one call takes at most this much: positions inside a call are 32-bit.  Larger inputs go in as several calls over row
+ * ranges of the same buffers (text_begin / text_end are absolute, nothing is rebased) */
+#define AKSHAR_MAX_CALL_BYTES ((int64_t)4294901760)        /* 4 GiB - 64 KiB */
+#define AKSHAR_MAX_CALL_ROWS ((int64_t)536870911)          /* 2^29 - 1 */
+
 /* status bits in d_result[2] */
 enum {
     AKSHAR_ST_OVERFLOW = 1,      /* an output capacity was too small: re-run with capacity >= total */

@@ -745,6 +745,9 @@ def test_cabi_error_codes(A, eng, models_dir):
     assert call(7, 5, ws.numel(), b.end) == C.E_ARG                 # unknown mode
     assert call(7, 0, ws.numel(), -1) == C.E_ARG                    # text_end < text_begin
     assert call(7, 0, 16, b.end) == C.E_WORKSPACE
+    assert call(7, 0, ws.numel(), 1 << 33) == C.E_ARG               # more than one call takes (4 GiB - 64 KiB)
+    assert b'too large' in lib.akshar_last_error(eng._h)
+    assert call(7, 0, 16, b.end) == C.E_WORKSPACE
     assert b'workspace' in lib.akshar_last_error(eng._h)
     fresh = Engine(0)                                               # a context without models
     ids = torch.empty(64, dtype=torch.int32, device=dev)
