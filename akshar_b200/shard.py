@@ -54,3 +54,22 @@ def gather_ragged(values, splits, group=None):
     parts = [None] * world
     dist.all_gather_object(parts, (np.asarray(values), np.asarray(splits)), group=group)
     return concat_ragged(parts)
+
+
+def encode_sharded(encode_fn, data, row_offsets, group=None, gather=True):
+    """The N > 1 entry point: every rank of the process group (one process per GPU, torchrun) calls this with the SAME
+    batch (`data` uint8, `row_offsets` int64, host arrays); rank r encodes the rows shard_rows(...)[r] with
+    `encode_fn(shard_data, shard_offsets) -> (values, splits)` -- e.g. `aksharTokenizer.encode_batch_host` on this rank's
+    GPU -- and, with gather=True, every rank gets the ragged result of the whole batch (host-side gather, nothing is
+    exchanged on the data path).  gather=False returns (row_lo, row_hi, values, splits) of this rank's shard."""
+    import torch.distributed as dist
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    lo, hi = shard_rows(row_offsets, world)[rank]
+    d, o = take_shard(np.asarray(data), row_offsets, lo, hi)
+    values, splits = encode_fn(d, o)
+    if not gather:
+        return lo, hi, values, splits
+    if world == 1:
+        return np.asarray(values), np.asarray(splits, dtype=np.int64)
+    return gather_ragged(values, splits, group)

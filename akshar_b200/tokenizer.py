@@ -187,6 +187,23 @@ class aksharTokenizer:
         tb = self._ids_to_text(id_rows, C.FORM_DETOKENIZE)
         return tb if as_device else tb.to_strings()
 
+    def encode_batch_sharded(self, h_data, h_offsets, group=None, gather=True):
+        """encode() of one batch by all the GPUs of the box: every rank of the torch.distributed group (one process per
+        GPU) passes the same host arrays (uint8 text, int64 row offsets); each encodes its contiguous share of the rows on
+        its own GPU through the pipelined host path and the ragged ids are gathered on the host (shard.encode_sharded)."""
+        import numpy as np
+        import torch
+        from . import shard
+        if self.model is None:
+            raise ValueError("need model for IDs")
+
+        def enc(d, o):
+            hd = torch.from_numpy(np.ascontiguousarray(d)).pin_memory() if d.size else torch.zeros(0, dtype=torch.uint8)
+            ho = torch.from_numpy(np.ascontiguousarray(o))
+            ids, sp = self.encode_batch_host(hd, ho)
+            return ids.numpy().copy(), sp.numpy().copy()
+        return shard.encode_sharded(enc, h_data, h_offsets, group, gather)
+
     def tokenize_batch(self, texts):
         """tokenize() over a batch -> list[list[str]]"""
         if self.model is None:

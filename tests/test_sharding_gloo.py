@@ -47,6 +47,18 @@ def _worker(rank, world, port, q):
     np.cumsum([len(x) for x in ids], out=splits[1:])
     vals = np.array([t for x in ids for t in x], dtype=np.int32)
     gv, gs = shard.gather_ragged(vals, splits)
+    # the product-level entry point over the same batch: every rank passes the whole batch, encodes its share, all get all
+
+    def enc(dd, oo):
+        bb = dd.tobytes()
+        rows = [O.bpe_encode(m, O.normalize_text(bb[oo[i]:oo[i + 1]].decode('utf-8'))) for i in range(len(oo) - 1)]
+        sp = np.zeros(len(rows) + 1, dtype=np.int64)
+        np.cumsum([len(x) for x in rows], out=sp[1:])
+        return np.array([t for x in rows for t in x], dtype=np.int32), sp
+    ev, es = shard.encode_sharded(enc, data, off)
+    assert ev.tolist() == gv.tolist() and es.tolist() == gs.tolist()
+    lo2, hi2, sv, ss = shard.encode_sharded(enc, data, off, gather=False)
+    assert (lo2, hi2) == (lo, hi) and sv.tolist() == vals.tolist()
     if rank == 0:
         q.put((gv.tolist(), gs.tolist()))
     dist.barrier()
