@@ -792,3 +792,18 @@ def test_cabi_error_codes(A, eng, models_dir):
     with pytest.raises(Exception):
         A.aksharTokenizer(os.path.join(models_dir, 'spm24k.model'), 'bpe')
     assert A.aksharTokenizer('/nonexistent/model').model_type == 'akshar'      # silent fallback, like the reference
+
+
+def test_sharded_encode_two_gpus(A):
+    """the N > 1 entry point on real GPUs (skipped on a one-GPU box): two ranks under torchrun, gathered ids == one GPU's"""
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs two GPUs')
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '2', '--master-addr', '127.0.0.1',
+                          '--master-port', '29533', os.path.join(root, 'tools', 'sharded_check.py')], capture_output=True, text=True,
+                         timeout=900)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert out.stdout.count(': True') == 2
