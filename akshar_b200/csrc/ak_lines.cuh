@@ -94,3 +94,73 @@ AK_HD AkLineFn akl_span(const uint8_t* t, int64_t s, int64_t e, int64_t te, bool
     f.lastk = lk;
     return f;
 }
+
+// ---- the same transducer of a 32-byte lane from bit masks (the kernels' path; akl_span above is the byte-by-byte statement
+// of it that the CPU tests also run over other span sizes) --------------------------------------------------------------
+struct AkLnLane {
+    uint32_t own, endbit;            // in: bytes of the file in this lane, the position n (end of file) if it is here
+    uint32_t lead, K, TERM, WIDE;    // lead bytes; kept code points and terminators (at their lead bytes); leads to decode
+};
+
+AK_HD void akln_phase1(const uint32_t* x, AkLnLane& L) {
+    uint32_t P[8];
+    akb_planes(x, P);
+    const uint32_t p0 = P[0], p1 = P[1], p2 = P[2], p3 = P[3], p4 = P[4], p5 = P[5], p6 = P[6], p7 = P[7];
+    const uint32_t asc = ~p7;
+    L.lead = ~(p7 & ~p6) & L.own;
+    const uint32_t c0 = asc & ~p6 & ~p5;
+    // ASCII isspace: 09-0D 1C-1F 20; terminators 0A 0D
+    const uint32_t sp = (c0 & ~p4 & akb_nibble<0x3E00u>(p3, p2, p1, p0)) | (c0 & p4 & p3 & p2) | (asc & ~p6 & p5 & ~(p4 | p3 | p2 | p1 | p0));
+    L.TERM = (c0 & ~p4 & akb_nibble<0x2400u>(p3, p2, p1, p0) & L.own) | L.endbit;
+    // leads of the code points str.isspace() accepts beyond ASCII: C2 (85 A0), E1 (9A 80), E2 (80 .. / 81 9F), E3 (80 80)
+    L.WIDE = p7 & p6 & L.own & ((~p5 & ~p4 & ~p3 & ~p2 & p1 & ~p0) | (p5 & ~p4 & ~p3 & ~p2 & (p1 | p0)));
+    L.K = L.lead & ~sp;
+}
+AK_HD void akln_wide(const uint8_t* t, int64_t cs, int64_t te, AkLnLane& L) {
+    for (uint32_t m = L.WIDE; m;) {
+        const int i = akb_ctz(m);
+        m &= m - 1u;
+        int len;
+        if (akw_isspace_wide(ak_decode(t, cs + i, te, len))) L.K &= ~(1u << i);
+    }
+}
+// position after the code point whose lead byte is bit i of the lane
+AK_HD int64_t akln_cp_end(const uint8_t* t, int64_t cs, int i, int64_t te) {
+    const uint32_t b = t[cs + i];
+    int64_t e = cs + i + (b < 0x80u ? 1 : b < 0xE0u ? 2 : b < 0xF0u ? 3 : 4);
+    return e > te ? te : e;
+}
+AK_HD AkLineFn akln_summary(const AkLnLane& L, const uint8_t* t, int64_t cs, int64_t te) {
+    AkLineFn f;
+    const uint32_t ev = L.K | L.TERM;
+    if (!ev) return akl_identity();
+    const uint32_t first0 = L.K & akb_fwd(L.TERM, ~ev, 1u), first1 = L.K & akb_fwd(L.TERM, ~ev, 0u);
+    const uint32_t top = 0x80000000u >> akb_clz(ev);
+    const uint32_t out = (L.K & top) ? 1u : 0u;
+    f.s = out | (out << 1);
+    f.cnt0 = akb_popc(first0);
+    f.cnt1 = akb_popc(first1);
+    f.lastk = L.K ? akln_cp_end(t, cs, 31 - akb_clz(L.K), te) : -1;
+    return f;
+}
+AK_HD void akln_emit(const AkLnLane& L, const uint8_t* t, int64_t cs, int64_t te, uint32_t state, int64_t lastk, int64_t rank,
+                     int64_t* begin, int64_t* end, int64_t cap, uint32_t& st) {
+    const uint32_t ev = L.K | L.TERM;
+    if (!ev) return;
+    const uint32_t first = L.K & akb_fwd(L.TERM, ~ev, state ? 0u : 1u);
+    const uint32_t ends = L.TERM & akb_fwd(L.K, ~ev, state ? 1u : 0u);
+    for (uint32_t m = first; m;) {
+        const int i = akb_ctz(m);
+        m &= m - 1u;
+        const int64_t k = rank + akb_popc(first & ((1u << i) - 1u));
+        if (k < cap) begin[k] = cs + i; else st |= AK_ST_OVERFLOW;
+    }
+    for (uint32_t m = ends; m;) {
+        const int i = akb_ctz(m);
+        m &= m - 1u;
+        const uint32_t below = L.K & ((1u << i) - 1u);
+        const int64_t e = below ? akln_cp_end(t, cs, 31 - akb_clz(below), te) : lastk;
+        const int64_t k = rank + akb_popc(first & ((1u << i) - 1u)) - 1;          // the row that is open at this terminator
+        if (k >= 0 && k < cap) end[k] = e;
+    }
+}

@@ -12,7 +12,8 @@
 struct AkLinesArgs {
     const uint8_t* text;
     int64_t n;                         // file bytes
-    int64_t n_tiles;                   // tiles of AKLN_TILE bytes covering positions 0 .. n (n itself included)
+    int64_t base0;                     // -(address of the file & 15): tiles are 16-byte aligned in the address space
+    int64_t n_tiles;                   // tiles of AKLN_TILE bytes covering positions base0 .. n (n itself included)
     AkLineFn* tile_fn;                 // [n_tiles] summaries, then (resolve) the state BEFORE each tile: s = entry state,
                                        //           cnt0 = rows begun before it (low 32 bits), cnt1 = (high 32 bits), lastk
     int64_t* begin;
@@ -36,8 +37,29 @@ __global__ void __launch_bounds__(256) ak_lines_kernel(const AkLinesArgs A) {
     const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
     uint32_t st = 0;
     for (int64_t tile = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); tile < A.n_tiles; tile += warps) {
-        const int64_t s = tile * AKLN_TILE + (int64_t)lane * AKLN_SPAN;
-        const AkLineFn mine = akl_span(A.text, s, s + AKLN_SPAN, A.n, false, 0u, -1, 0, nullptr, nullptr, 0, st);
+        // the lane's 32 bytes (tiles start at a 16-byte boundary of the address space: base0 <= 0)
+        const int64_t cs = A.base0 + tile * AKLN_TILE + (int64_t)lane * AKLN_SPAN;
+        AkLnLane L;
+        {
+            uint32_t x[8];
+            int64_t lo = -cs, hi = A.n - cs;
+            lo = lo < 0 ? 0 : (lo > 32 ? 32 : lo);
+            hi = hi < 0 ? 0 : (hi > 32 ? 32 : hi);
+            if (lo == 0 && hi == 32) {
+                const uint4 v0 = *reinterpret_cast<const uint4*>(A.text + cs);
+                const uint4 v1 = *reinterpret_cast<const uint4*>(A.text + cs + 16);
+                x[0] = v0.x; x[1] = v0.y; x[2] = v0.z; x[3] = v0.w;
+                x[4] = v1.x; x[5] = v1.y; x[6] = v1.z; x[7] = v1.w;
+                L.own = 0xFFFFFFFFu;
+            } else {
+                akn3_load_edge(A.text, cs, (int)lo, (int)hi, x);
+                L.own = hi > lo ? ((hi == 32 ? 0xFFFFFFFFu : ((1u << hi) - 1u)) & ~((1u << lo) - 1u)) : 0u;
+            }
+            L.endbit = (A.n >= cs && A.n < cs + 32) ? 1u << (int)(A.n - cs) : 0u;
+            akln_phase1(x, L);
+            if (L.WIDE) akln_wide(A.text, cs, A.n, L);
+        }
+        const AkLineFn mine = akln_summary(L, A.text, cs, A.n);
         // inclusive scan of the lanes' transducers
         AkLineFn inc = mine;
 #pragma unroll
@@ -57,7 +79,7 @@ __global__ void __launch_bounds__(256) ak_lines_kernel(const AkLinesArgs A) {
         const uint32_t state = (before.s >> in.s) & 1u;
         const int64_t rank = tile_rank + (in.s ? before.cnt1 : before.cnt0);
         const int64_t lastk = before.lastk >= 0 ? before.lastk : in.lastk;
-        akl_span(A.text, s, s + AKLN_SPAN, A.n, true, state, lastk, rank, A.begin, A.end, A.cap, st);
+        akln_emit(L, A.text, cs, A.n, state, lastk, rank, A.begin, A.end, A.cap, st);
     }
     ak_raise(A.result, st);
 }

@@ -369,6 +369,37 @@ int64_t hh_lines(const uint8_t* text, int64_t n, int span, int64_t* begin, int64
     return rows;
 }
 
+// the same through the kernels' 32-byte mask lanes (akln_*): `lead` bytes of padding in front make the lanes start before
+// the file, as they do when the file's address is not 16-byte aligned
+int64_t hh_lines32(const uint8_t* text, int64_t n, int lead, int64_t* begin, int64_t* end, int64_t cap, uint32_t* status) {
+    uint32_t st = 0;
+    const int64_t base0 = -(int64_t)lead;
+    const int64_t n_lanes = (n - base0) / 32 + 1;
+    std::vector<AkLnLane> L((size_t)n_lanes);
+    std::vector<AkLineFn> fn((size_t)n_lanes);
+    for (int64_t k = 0; k < n_lanes; ++k) {
+        const int64_t cs = base0 + 32 * k;
+        uint32_t x[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        AkLnLane& l = L[(size_t)k];
+        memset(&l, 0, sizeof(l));
+        for (int i = 0; i < 32; ++i) {
+            const int64_t q = cs + i;
+            if (q >= 0 && q < n) { x[i >> 2] |= (uint32_t)text[q] << ((i & 3) * 8); l.own |= 1u << i; }
+            if (q == n) l.endbit = 1u << i;
+        }
+        akln_phase1(x, l);
+        if (l.WIDE) akln_wide(text, cs, n, l);
+        fn[(size_t)k] = akln_summary(l, text, cs, n);
+    }
+    AkLineFn acc = akl_identity();
+    for (int64_t k = 0; k < n_lanes; ++k) {
+        akln_emit(L[(size_t)k], text, base0 + 32 * k, n, acc.s & 1u, acc.lastk, acc.cnt0, begin, end, cap, st);
+        acc = akl_compose(acc, fn[(size_t)k]);
+    }
+    *status = st;
+    return acc.cnt0;
+}
+
 // roman_phonetic_signature of every row; returns output bytes
 int64_t hh_signature(const uint8_t* text, const int64_t* off, int64_t n_rows, uint8_t* out, int64_t* out_off) {
     AkTables T = host_tables();

@@ -401,5 +401,8 @@ def test_file_rows_like_readlines_and_strip(tmp_path):
             assert [ln.strip() for ln in f.readlines() if ln.strip()] == exp
         for span in (32, 1, 5, 1000):
             assert [r.decode('utf-8') for r in W.lines(data, span=span)] == exp
+        for lead in (0, 7, 15):                                       # the kernels' lanes: bit masks per 32 bytes
+            assert [r.decode('utf-8') for r in W.lines32(data, lead=lead)] == exp
     for s in ('', '\n', 'a', 'a\n', '\na', ' a ', '\r\r\n\r', 'a\rb\r\nc\n\nd', ' ' * 100 + 'a' + ' ' * 100, '\u3000\u0915\u3000', 'a' * 100):
         assert [r.decode('utf-8') for r in W.lines(s.encode('utf-8'))] == O.file_rows(s.encode('utf-8'))
+        assert [r.decode('utf-8') for r in W.lines32(s.encode('utf-8'))] == O.file_rows(s.encode('utf-8'))

@@ -198,6 +198,21 @@ def lines(data, span=32):
     return [raw[b[i]:e[i]] for i in range(n)]
 
 
+def lines32(data, lead=0):
+    """file bytes -> rows through the kernels' 32-byte mask lanes (akln_*) -> list[bytes]"""
+    data = np.ascontiguousarray(np.frombuffer(data, dtype=np.uint8) if isinstance(data, (bytes, bytearray)) else data, dtype=np.uint8)
+    pad = np.concatenate([data, np.zeros(8, dtype=np.uint8)])
+    cap = int(data.size) + 2
+    b = np.zeros(cap, dtype=np.int64)
+    e = np.zeros(cap, dtype=np.int64)
+    st = ctypes.c_uint32(0)
+    lib().hh_lines32.restype = ctypes.c_int64
+    n = lib().hh_lines32(_p(pad), ctypes.c_int64(data.size), ctypes.c_int(lead), _p(b), _p(e), ctypes.c_int64(cap), ctypes.byref(st))
+    assert st.value == 0
+    raw = data.tobytes()
+    return [raw[b[i]:e[i]] for i in range(n)]
+
+
 def wordtok(data, off, mode=0, real=30):
     """the word tokenizers (ak_wordtok.cuh) through the kernel's lane structure -> (begin, end, splits, row_flags, status)"""
     data = np.ascontiguousarray(data, dtype=np.uint8)
