@@ -243,8 +243,7 @@ static inline int64_t ak_tiles_of(int64_t n_bytes, int64_t n_rows) {
     return (a > b ? a : b) + 1;
 }
 struct AkTokWs {
-    size_t wrow, count, wt_ids, wt_base, wt_seg, wt_segx, scan_state, row_flag, row_ev, row_fix, miss, pool, longpool, slots, total;
-    size_t miss_cap;
+    size_t wrow, count, wt_ids, wt_base, wt_seg, wt_segx, scan_state, row_flag, row_ev, row_fix, pool, longpool, slots, total;
     size_t pool_ints, longpool_ints;
     int64_t n_wt;
 };
@@ -265,8 +264,6 @@ static AkTokWs ak_tok_ws(int64_t n_bytes, int64_t n_rows) {
     W.row_flag = at;   at += ak_align((size_t)n_rows + 1);
     W.row_ev = at;     at += ak_align(((size_t)n_rows + 2) * 4);
     W.row_fix = at;    at += ak_align(((size_t)n_rows + 1) * 8);
-    W.miss_cap = (size_t)W.n_wt * 4 + 1024;               // Unigram: words not in the cache, per call (more are encoded in place)
-    W.miss = at;       at += ak_align(W.miss_cap * 8);
     W.pool_ints = (size_t)n_bytes / 4 + 65536;
     W.pool = at;       at += ak_align(W.pool_ints * 4);
     W.longpool_ints = (size_t)n_bytes / 8 + 65536;

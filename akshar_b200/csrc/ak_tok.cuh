@@ -473,11 +473,8 @@ AK_HD int akr_n(unsigned long long r) {
 
 // resolve one event.  k[0..3]: the word's first four key words (akc_key0123) when it is a cacheable word.
 // aux (Unigram): (ratio bf16 << 16) | wmag bf16 of the word, 0 for anything else.
-// DEFER: a word that is not in the cache is not encoded here -- *deferred is set and the caller puts the slot on the miss
-// list (ak_miss_kernel encodes it with one thread per word; inside the resolve kernel it would hold up its 31 neighbours)
-template <int KIND, bool DEFER = false>
-AK_HD unsigned long long akl_resolve(const AkLookupCtx& X, AkEvent& ev, const unsigned long long* k, uint32_t& aux, uint32_t& st,
-                                     bool* deferred = nullptr) {
+template <int KIND>
+AK_HD unsigned long long akl_resolve(const AkLookupCtx& X, AkEvent& ev, const unsigned long long* k, uint32_t& aux, uint32_t& st) {
     const uint32_t kind = ev.meta & 7u;
     uint32_t len = ev.meta >> 3;
     const int64_t p = X.tb + ev.pos;
@@ -498,10 +495,6 @@ AK_HD unsigned long long akl_resolve(const AkLookupCtx& X, AkEvent& ev, const un
             const int n = AKC_NTOK(h.tag);
             if (KIND == 1) aux = (uint32_t)(h.tag >> 32);
             return n <= 2 ? akr_inline(n, h.ids01) : akr_cache(n, h.slot);
-        }
-        if (DEFER) {
-            *deferred = true;
-            return 0ull;
         }
         const AkMissOut o = KIND == 0 ? akl_bpe_miss(X, p, len, kind, h.free_slot, h.want, cacheable)
                                       : akl_uni_miss(X, p, len, h.free_slot, h.want, cacheable);

@@ -267,9 +267,6 @@ struct AkResolveArgs {
     int32_t* wt_ids;                   // per warp tile: ids emitted
     unsigned long long* wt_seg;        // per warp tile (Unigram): (has a row start << 32) | float sum of wmag after the last one
     const unsigned int* any_flag;
-    long long* miss_list;              // Unigram: slots whose word was not in the cache (encoded by ak_miss_kernel)
-    unsigned long long* miss_n;
-    unsigned long long miss_cap;
 };
 
 #ifndef AKR_MINB0
@@ -298,6 +295,7 @@ __global__ void __launch_bounds__(AKR_THREADS, KIND == 0 ? AKR_MINB0 : AKR_MINB1
         const int cnt = (int)A.S.count[wt];
         const long long s_wt = wt << A.S.shift;
         int ids = 0;
+        unsigned long long seg = 0ull;                         // (flag, sum) over the rounds so far
         for (int o = 0; o < cnt; o += 32) {
             const int i = o + lane;
             unsigned long long r = 0ull;
@@ -308,89 +306,31 @@ __global__ void __launch_bounds__(AKR_THREADS, KIND == 0 ? AKR_MINB0 : AKR_MINB1
                 const uint32_t kind = ev.meta & 7u, len = ev.meta >> 3;
                 unsigned long long k[4] = {0ull, 0ull, 0ull, 0ull};
                 if (kind <= AKE_WORD && len <= AKC_MAXLEN) akc_key0123(X.text, X.tb + ev.pos, len, X.te, k);
-                if (KIND == 1) {
-                    // Unigram: a word that is not in the cache needs its lattice solved (thousands of dependent
-                    // instructions): it goes to the miss list, its record and its ids are filled in by ak_miss_kernel
-                    bool deferred = false;
-                    r = akl_resolve<KIND, true>(X, ev, k, aux, st, &deferred);
-                    if (deferred) {
-                        const unsigned long long at = atomicAdd(A.miss_n, 1ull);
-                        if (at < A.miss_cap) A.miss_list[at] = s;
-                        else r = akl_resolve<KIND>(X, ev, k, aux, st);          // list full: here and now
-                    }
-                } else r = akl_resolve<KIND>(X, ev, k, aux, st);
+                r = akl_resolve<KIND>(X, ev, k, aux, st);
                 A.resolved[s] = r;
                 if (KIND == 1) A.aux[s] = aux;
             }
             __syncwarp();
             ids += akr_n(r);
+            if (KIND == 1) {
+                // my element, then the warp's aggregate of this round appended to the running one
+                unsigned long long e = (r >> 62) == AKR_EVENT ? AKS_SEG_FLAG : (unsigned long long)__float_as_uint(aku_aux_wmag(aux));
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const unsigned long long y = __shfl_up_sync(0xFFFFFFFFu, e, d);
+                    if (lane >= d) e = aks_seg_op(y, e);
+                }
+                seg = aks_seg_op(seg, __shfl_sync(0xFFFFFFFFu, e, 31));
+            }
         }
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) ids += __shfl_xor_sync(0xFFFFFFFFu, ids, d);
-        if (lane == 0) A.wt_ids[wt] = ids;
-    }
-    ak_raise(B.result, st);
-}
-
-// Unigram: the words the resolve kernel did not find in the cache, one thread per word (thousands of lattices in flight
-// instead of one per warp): look the word up again (another thread may have published it meanwhile), else solve and
-// publish; record, aux word and the warp tile's id count are completed.
-__global__ void __launch_bounds__(128) ak_miss_kernel(const AkResolveArgs A) {
-    AkBatch B = A.B;
-    if (!ak_batch_begin(B)) return;
-    AkLookupCtx X = A.X;
-    X.text = B.text;
-    X.off = B.off;
-    X.n_rows = B.n_rows;
-    X.tb = B.text_begin;
-    X.te = B.text_end;
-    X.result = B.result;
-    X.any_fix = *A.any_flag != 0u ? 1 : 0;
-    unsigned long long n = *A.miss_n;
-    if (n > A.miss_cap) n = A.miss_cap;
-    uint32_t st = 0;
-    for (unsigned long long q = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (unsigned long long)gridDim.x * blockDim.x) {
-        const long long s = A.miss_list[q];
-        AkEvent ev = A.S.ev[s];
-        const uint32_t len = ev.meta >> 3;
-        unsigned long long k[4] = {0ull, 0ull, 0ull, 0ull};
-        if (len <= AKC_MAXLEN) akc_key0123(X.text, X.tb + ev.pos, len, X.te, k);
-        uint32_t aux = 0u;
-        const unsigned long long r = akl_resolve<1>(X, ev, k, aux, st);
-        A.resolved[s] = r;
-        A.aux[s] = aux;
-        const int ids = akr_n(r);
-        if (ids) atomicAdd(&A.wt_ids[s >> A.S.shift], ids);
-    }
-    ak_raise(B.result, st);
-}
-
-// Unigram: per warp tile (has a row start, float sum of wmag after the last one) -- the aggregates the scan over the warp
-// tiles turns into "sum of wmag since the last row start" at every tile's first slot
-__global__ void __launch_bounds__(AKL_THREADS, 4) ak_segagg_kernel(const AkResolveArgs A) {
-    AkBatch B = A.B;
-    if (!ak_batch_begin(B)) return;
-    const int lane = threadIdx.x & 31;
-    const long long n_wt = akt_n_wt(B, A.base0);
-    const long long warp0 = ((long long)blockIdx.x * AKL_THREADS + threadIdx.x) >> 5, n_warps = ((long long)gridDim.x * AKL_THREADS) >> 5;
-    for (long long wt = warp0; wt < n_wt; wt += n_warps) {
-        const int cnt = (int)A.S.count[wt];
-        const long long s_wt = wt << A.S.shift;
-        unsigned long long seg = 0ull;
-        for (int o = 0; o < cnt; o += 32) {
-            const int i = o + lane;
-            unsigned long long e = 0ull;
-            if (i < cnt)
-                e = (A.resolved[s_wt + i] >> 62) == AKR_EVENT ? AKS_SEG_FLAG : (unsigned long long)__float_as_uint(aku_aux_wmag(A.aux[s_wt + i]));
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const unsigned long long y = __shfl_up_sync(0xFFFFFFFFu, e, d);
-                if (lane >= d) e = aks_seg_op(y, e);
-            }
-            seg = aks_seg_op(seg, __shfl_sync(0xFFFFFFFFu, e, 31));
+        if (lane == 0) {
+            A.wt_ids[wt] = ids;
+            if (KIND == 1) A.wt_seg[wt] = seg;
         }
-        if (lane == 0) A.wt_seg[wt] = seg;
     }
+    ak_raise(B.result, st);
 }
 
 // =================================================================================================================
