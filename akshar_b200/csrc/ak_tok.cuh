@@ -369,37 +369,41 @@ AK_HD_NOINLINE AkMissOut akl_bpe_miss(const AkLookupCtx& X, int64_t p, uint32_t 
 
 // cold: a Unigram word that is not in the cache: solve its lattice, publish it when it fits an entry; the ids of this
 // occurrence go to the pool.  Returns the id count.
-AK_HD_NOINLINE AkMissOut akl_uni_miss(const AkLookupCtx& X, int64_t p, uint32_t len, long long free_slot, unsigned long long want,
-                                      bool cacheable) {
+AK_HD AkMissOut akl_uni_finish(const AkLookupCtx& X, int64_t p, uint32_t len, long long free_slot, unsigned long long want, bool cacheable,
+                               bool ok, int n_ids, const int32_t* ids, float ratio, float wmag) {
     AkMissOut o;
     o.n = 0;
     o.slot = -1;
     o.ids01 = 0ull;
     o.st = 0;
-    AkUniWord W;
-    aku_word_lattice(X.M.uni, X.text, p, len, W);
-    if (!W.ok) {
+    if (!ok) {
         // too long for the word lattice: always taken from the exact row Viterbi
         o.ratio = 0.f;
         o.wmag = (float)(len + 1u) * (X.M.uni.unk_score < 0 ? -X.M.uni.unk_score : X.M.uni.unk_score);
         return o;
     }
     // the tag's (bf16, conservative) numbers are what later look-ups see: use the same ones now
-    const unsigned long long aux = akc_aux(W.ratio, W.wmag);
+    const unsigned long long aux = akc_aux(ratio, wmag);
     o.ratio = akc_ratio(aux);
     o.wmag = akc_wmag(aux);
-    if (cacheable && W.n_ids <= AKC_MAXTOK && free_slot >= 0) akc_insert(X.M.cache, free_slot, want, X.text, p, len, W.ids, W.n_ids, aux);
-    if (W.n_ids <= 2) {
-        o.ids01 = (W.n_ids > 0 ? (unsigned long long)(uint32_t)W.ids[0] : 0ull) | (W.n_ids > 1 ? (unsigned long long)(uint32_t)W.ids[1] << 32 : 0ull);
-        o.n = W.n_ids;
+    if (cacheable && n_ids <= AKC_MAXTOK && free_slot >= 0) akc_insert(X.M.cache, free_slot, want, X.text, p, len, ids, n_ids, aux);
+    if (n_ids <= 2) {
+        o.ids01 = (n_ids > 0 ? (unsigned long long)(uint32_t)ids[0] : 0ull) | (n_ids > 1 ? (unsigned long long)(uint32_t)ids[1] << 32 : 0ull);
+        o.n = n_ids;
         return o;
     }
-    const unsigned long long at = ak_atomic_add64(X.pool_used, (unsigned long long)W.n_ids + 1ull);
-    if (at + (unsigned long long)W.n_ids > X.pool_cap) { ak_status_or(X.result, AK_ST_WORD); return o; }
-    for (int i = 0; i < W.n_ids; ++i) X.pool[at + i] = W.ids[i];
+    const unsigned long long at = ak_atomic_add64(X.pool_used, (unsigned long long)n_ids + 1ull);
+    if (at + (unsigned long long)n_ids > X.pool_cap) { ak_status_or(X.result, AK_ST_WORD); return o; }
+    for (int i = 0; i < n_ids; ++i) X.pool[at + i] = ids[i];
     o.slot = -3 - (long long)at;
-    o.n = W.n_ids;
+    o.n = n_ids;
     return o;
+}
+AK_HD_NOINLINE AkMissOut akl_uni_miss(const AkLookupCtx& X, int64_t p, uint32_t len, long long free_slot, unsigned long long want,
+                                      bool cacheable) {
+    AkUniWord W;
+    aku_word_lattice(X.M.uni, X.text, p, len, W);
+    return akl_uni_finish(X, p, len, free_slot, want, cacheable, W.ok, W.n_ids, W.ids, W.ratio, W.wmag);
 }
 
 // cold: a Unigram word whose cached segmentation may depend on the score accumulated before it: its ids from the exact

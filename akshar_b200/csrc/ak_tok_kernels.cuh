@@ -269,6 +269,152 @@ struct AkResolveArgs {
     const unsigned int* any_flag;
 };
 
+// ---- Unigram: the lattice of one word, solved by the whole warp --------------------------------------------------------
+// A word that is not in the cache needs its lattice (aku_word_lattice: a trie walk from every code point, then the Viterbi
+// recursion).  One lane doing that alone holds up the 31 others of its round for thousands of dependent instructions; here
+// the warp does it together: the lanes decode the word, every lane walks the trie from its own start position (the longest
+// dependent chain is now one walk, not the sum of all), and the recursion takes the candidates of a position from 17 lanes
+// at once.  Same arithmetic (double sums of the float scores, first-come tie break = longest piece), same ratio / wmag.
+#define AKU_W_KMAX 16                                  // pieces of up to 16 code points (the trainer's max_sentencepiece_length)
+struct AkUniWarpScratch {
+    uint32_t cps[AKU_WORD_CPS];
+    uint32_t epid[AKU_WORD_CPS][AKU_W_KMAX];           // [start][length - 1] = piece id + 1 of a usable piece, else 0; later: the ids
+    double best[AKU_WORD_CPS + 1];
+    uint32_t bk[AKU_WORD_CPS + 1];
+    int n_ids;
+    float ratio, wmag;
+};
+
+__device__ __forceinline__ double aku_shfl_xor_d(double v, int d) {
+    return __hiloint2double(__shfl_xor_sync(0xFFFFFFFFu, __double2hiint(v), d), __shfl_xor_sync(0xFFFFFFFFu, __double2loint(v), d));
+}
+__device__ __forceinline__ double aku_warp_max_d(double v) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        const double y = aku_shfl_xor_d(v, d);
+        v = y > v ? y : v;
+    }
+    return v;
+}
+
+// all 32 lanes call this with the same word; false = the word does not fit the cooperative scheme (the caller's serial path
+// takes it).  The result is in S (ids in S.epid as int32).
+__device__ __noinline__ bool aku_word_lattice_warp(const AkUniDev& U, const uint8_t* t, int64_t s, uint32_t len, AkUniWarpScratch& S) {
+    const int lane = threadIdx.x & 31;
+    if (len > 2u * 32u - 8u) return false;
+    // code points: lane l looks at bytes 2l and 2l + 1
+    uint32_t mine = 0;
+    uint32_t c[2] = {0u, 0u};
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const uint32_t q = 2u * (uint32_t)lane + (uint32_t)h;
+        if (q < len && (t[s + q] & 0xC0u) != 0x80u) {
+            int l;
+            c[h] = ak_decode(t, s + q, s + len, l);
+            mine |= 1u << h;
+        }
+    }
+    int inc = __popc(mine);
+    const int own = inc;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int y = __shfl_up_sync(0xFFFFFFFFu, inc, d);
+        if (lane >= d) inc += y;
+    }
+    const int n = 1 + __shfl_sync(0xFFFFFFFFu, inc, 31);
+    if (n > AKU_WORD_CPS) return false;
+    {
+        int at = 1 + inc - own;
+        if (mine & 1u) S.cps[at++] = c[0];
+        if (mine & 2u) S.cps[at] = c[1];
+        if (lane == 0) S.cps[0] = (U.flags & 4) ? 0x2581u : 0x20u;
+    }
+    __syncwarp();
+    // trie walks: start positions lane and lane + 32
+    bool deep = false;
+    for (int i = lane; i < n; i += 32) {
+#pragma unroll
+        for (int k = 0; k < AKU_W_KMAX; ++k) S.epid[i][k] = 0u;
+        uint32_t node = 0;
+        for (int k = 1; i + k <= n; ++k) {
+            const unsigned long long v = ak_uni_child(U, node, S.cps[i + k - 1]);
+            if (v == AK_EMPTY_KEY) break;
+            if (k > AKU_W_KMAX) { deep = true; break; }
+            node = (uint32_t)(v >> 32);
+            const uint32_t pid1 = (uint32_t)v;
+            if (pid1 && U.usable[pid1 - 1u]) S.epid[i][k - 1] = pid1;
+        }
+    }
+    if (__any_sync(0xFFFFFFFFu, deep)) return false;
+    if (lane == 0) { S.best[0] = 0.0; S.bk[0] = 0u; }
+    __syncwarp();
+    // the recursion, position by position: lanes 1 .. 16 bring the pieces that end here, lane 0 the unknown-character edge
+    double margin = INFINITY, wmag = 0.0;
+    for (int j = 1; j <= n; ++j) {
+        double cand = -INFINITY;
+        uint32_t b = 0u;
+        if (lane >= 1 && lane <= AKU_W_KMAX && j - lane >= 0) {
+            const int i = j - lane;
+            const uint32_t pid1 = S.epid[i][lane - 1];
+            const double bi = S.best[i];
+            if (pid1 && bi != -INFINITY) {
+                cand = bi + (double)U.score[pid1 - 1u];
+                b = ((uint32_t)lane << 24) | (pid1 - 1u);
+            }
+        } else if (lane == 0) {
+            const double bi = S.best[j - 1];
+            if (bi != -INFINITY && S.epid[j - 1][0] == 0u) {
+                cand = bi + (double)U.unk_score;
+                b = AK_UNI_UNKBIT | S.cps[j - 1];
+            }
+        }
+        const double a = cand == -INFINITY ? 0.0 : (cand < 0 ? -cand : cand);
+        const double m1 = aku_warp_max_d(cand);
+        const double wm = aku_warp_max_d(a);
+        if (wm > wmag) wmag = wm;
+        // the first candidate to arrive with the best value wins: the longest piece (the unknown edge comes last)
+        const unsigned tie = __ballot_sync(0xFFFFFFFFu, cand == m1 && m1 != -INFINITY);
+        const int win = tie ? 31 - __clz((int)tie) : 0;
+        const double m2 = aku_warp_max_d(lane == win ? -INFINITY : cand);
+        const uint32_t wb = __shfl_sync(0xFFFFFFFFu, b, win);
+        if (m1 != -INFINITY && m1 - m2 < margin) margin = m1 - m2;
+        if (lane == 0) { S.best[j] = m1; S.bk[j] = wb; }
+        __syncwarp();
+    }
+    // ids, back to front (one lane; the edge table is done with and takes them)
+    if (lane == 0) {
+        int32_t* ids = reinterpret_cast<int32_t*>(&S.epid[0][0]);
+        int cnt = 0;
+        for (int j = n; j > 0;) {
+            const uint32_t b = S.bk[j];
+            if (b & AK_UNI_UNKBIT) { cnt += (U.flags & 8) ? ak_utf8_len(b & 0x1FFFFFu) : 1; j -= 1; }
+            else { cnt += 1; j -= (int)((b >> 24) & 0x7Fu); }
+        }
+        S.n_ids = cnt;
+        int at = cnt;
+        for (int j = n; j > 0;) {
+            const uint32_t b = S.bk[j];
+            if (b & AK_UNI_UNKBIT) {
+                const uint32_t cp = b & 0x1FFFFFu;
+                if (U.flags & 8) {
+                    uint8_t enc[4];
+                    const int m = ak_encode(cp, enc);
+                    for (int q = m - 1; q >= 0; --q) ids[--at] = U.byte_id[enc[q]];
+                } else ids[--at] = U.unk_id;
+                j -= 1;
+            } else {
+                ids[--at] = (int32_t)(b & 0xFFFFFFu);
+                j -= (int)((b >> 24) & 0x7Fu);
+            }
+        }
+        const double r = margin / (double)n;
+        S.ratio = r > 1e30 ? 1e30f : (float)r * 0.999f;
+        S.wmag = (float)wmag * 1.001f + 1e-30f;
+    }
+    __syncwarp();
+    return true;
+}
+
 #ifndef AKR_MINB0
 #define AKR_MINB0 3
 #endif
@@ -288,6 +434,8 @@ __global__ void __launch_bounds__(AKR_THREADS, KIND == 0 ? AKR_MINB0 : AKR_MINB1
     X.result = B.result;
     X.any_fix = *A.any_flag != 0u ? 1 : 0;
     const int lane = threadIdx.x & 31;
+    __shared__ AkUniWarpScratch s_uni[KIND == 1 ? AKR_THREADS / 32 : 1];
+    AkUniWarpScratch* const scratch = &s_uni[KIND == 1 ? (threadIdx.x >> 5) : 0];
     const long long n_wt = akt_n_wt(B, A.base0);
     const long long warp0 = ((long long)blockIdx.x * AKR_THREADS + threadIdx.x) >> 5, n_warps = ((long long)gridDim.x * AKR_THREADS) >> 5;
     uint32_t st = 0;
@@ -300,15 +448,54 @@ __global__ void __launch_bounds__(AKR_THREADS, KIND == 0 ? AKR_MINB0 : AKR_MINB1
             const int i = o + lane;
             unsigned long long r = 0ull;
             uint32_t aux = 0u;
+            bool miss = false;
+            int64_t miss_p = 0;
+            uint32_t miss_len = 0u;
+            AkcHit hit;
+            hit.slot = hit.free_slot = -1;
+            hit.h = hit.want = hit.tag = hit.ids01 = 0ull;
             if (i < cnt) {
                 const long long s = s_wt + i;
                 AkEvent ev = A.S.ev[s];
                 const uint32_t kind = ev.meta & 7u, len = ev.meta >> 3;
                 unsigned long long k[4] = {0ull, 0ull, 0ull, 0ull};
                 if (kind <= AKE_WORD && len <= AKC_MAXLEN) akc_key0123(X.text, X.tb + ev.pos, len, X.te, k);
-                r = akl_resolve<KIND>(X, ev, k, aux, st);
-                A.resolved[s] = r;
-                if (KIND == 1) A.aux[s] = aux;
+                if (KIND == 1 && kind <= AKE_WORD && len <= 56u && len != AKE_LEN_MAX) {
+                    // Unigram word: look it up here; a miss is solved by the whole warp below
+                    akc_lookup4(X.M.cache, X.text, X.tb + ev.pos, len, k, hit);
+                    if (hit.slot >= 0) {
+                        const int n = AKC_NTOK(hit.tag);
+                        aux = (uint32_t)(hit.tag >> 32);
+                        r = n <= 2 ? akr_inline(n, hit.ids01) : akr_cache(n, hit.slot);
+                    } else {
+                        miss = true;
+                        miss_p = X.tb + ev.pos;
+                        miss_len = len;
+                    }
+                } else r = akl_resolve<KIND>(X, ev, k, aux, st);
+            }
+            if (KIND == 1) {
+                for (unsigned mm = __ballot_sync(0xFFFFFFFFu, miss); mm; mm &= mm - 1u) {
+                    const int src = __ffs((int)mm) - 1;
+                    const int64_t wp = __shfl_sync(0xFFFFFFFFu, miss_p, src);
+                    const uint32_t wl = __shfl_sync(0xFFFFFFFFu, miss_len, src);
+                    const bool solved = aku_word_lattice_warp(X.M.uni, X.text, wp, wl, *scratch);
+                    if (lane == src) {
+                        AkMissOut o;
+                        if (solved)
+                            o = akl_uni_finish(X, wp, wl, hit.free_slot, hit.want, true, true, scratch->n_ids,
+                                               reinterpret_cast<const int32_t*>(&scratch->epid[0][0]), scratch->ratio, scratch->wmag);
+                        else o = akl_uni_miss(X, wp, wl, hit.free_slot, hit.want, true);
+                        st |= o.st;
+                        aux = (uint32_t)(akc_aux(o.ratio, o.wmag) >> 32);
+                        r = o.slot == -1 ? akr_inline(o.n, o.ids01) : akr_pool(o.n, (unsigned long long)(-3 - o.slot));
+                    }
+                    __syncwarp();
+                }
+            }
+            if (i < cnt) {
+                A.resolved[s_wt + i] = r;
+                if (KIND == 1) A.aux[s_wt + i] = aux;
             }
             __syncwarp();
             ids += akr_n(r);
