@@ -556,14 +556,27 @@ __global__ void __launch_bounds__(AKL_THREADS, 4) ak_unicheck_kernel(const AkChe
         const long long s_wt = wt << A.S.shift;
         unsigned long long run = (unsigned long long)__float_as_uint(A.wt_seg_before[wt]);     // (flag, sum) before this round
         int delta = 0;
-        for (int o = 0; o < cnt; o += 32) {
+        for (int o4 = 0; o4 < cnt; o4 += 128) {
+          // the loads of four rounds go out together (a round's work is a dependent chain of shuffles behind them)
+          uint32_t aux4[4];
+          bool row4[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+              const int i = o4 + 32 * q + lane;
+              aux4[q] = 0u;
+              row4[q] = false;
+              if (i < cnt) {
+                  aux4[q] = A.aux[s_wt + i];
+                  row4[q] = (A.resolved[s_wt + i] >> 62) == AKR_EVENT;
+              }
+          }
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int o = o4 + 32 * q;
+            if (o >= cnt) break;
             const int i = o + lane;
-            uint32_t aux = 0u;
-            bool isrow = false;
-            if (i < cnt) {
-                aux = A.aux[s_wt + i];
-                isrow = (A.resolved[s_wt + i] >> 62) == AKR_EVENT;
-            }
+            const uint32_t aux = aux4[q];
+            const bool isrow = row4[q];
             unsigned long long e = isrow ? AKS_SEG_FLAG : (unsigned long long)__float_as_uint(aku_aux_wmag(aux));
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) {
@@ -583,6 +596,7 @@ __global__ void __launch_bounds__(AKL_THREADS, 4) ak_unicheck_kernel(const AkChe
                 }
             }
             __syncwarp();
+          }
         }
         if (delta) atomicAdd(&A.wt_ids[wt], delta);
     }
@@ -627,9 +641,19 @@ __global__ void __launch_bounds__(AKL_THREADS, 4) ak_emit_kernel(const AkEmitArg
         const int cnt = (int)A.S.count[wt];
         const long long s_wt = wt << A.S.shift;
         int64_t at0 = A.wt_base[wt];
-        for (int o = 0; o < cnt; o += 32) {
+        for (int o4 = 0; o4 < cnt; o4 += 128) {
+          unsigned long long r4[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+              const int i = o4 + 32 * q + lane;
+              r4[q] = i < cnt ? A.resolved[s_wt + i] : 0ull;
+          }
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int o = o4 + 32 * q;
+            if (o >= cnt) break;
             const int i = o + lane;
-            const unsigned long long r = i < cnt ? A.resolved[s_wt + i] : 0ull;
+            const unsigned long long r = r4[q];
             const unsigned long long ty = r >> 62;
             const int n = ty == AKR_INLINE ? (int)((r >> 60) & 3ull) : akr_n(r);
             int inc = n;
@@ -679,6 +703,7 @@ __global__ void __launch_bounds__(AKL_THREADS, 4) ak_emit_kernel(const AkEmitArg
             }
             at0 += __shfl_sync(0xFFFFFFFFu, inc, 31);
             __syncwarp();
+          }
         }
     }
     ak_raise(B.result, st);
