@@ -444,8 +444,15 @@ __global__ void __launch_bounds__(AKR_THREADS, KIND == 0 ? AKR_MINB0 : AKR_MINB1
         const long long s_wt = wt << A.S.shift;
         int ids = 0;
         unsigned long long seg = 0ull;                         // (flag, sum) over the rounds so far
+        // the next round's event is fetched while this round is looked up (one round trip less in the chain)
+        AkEvent ev_next;
+        ev_next.pos = 0u;
+        ev_next.meta = AKE_DEAD;
+        if (lane < cnt) ev_next = A.S.ev[s_wt + lane];
         for (int o = 0; o < cnt; o += 32) {
             const int i = o + lane;
+            const AkEvent ev_cur = ev_next;
+            if (i + 32 < cnt) ev_next = A.S.ev[s_wt + i + 32];
             unsigned long long r = 0ull;
             uint32_t aux = 0u;
             bool miss = false;
@@ -455,8 +462,7 @@ __global__ void __launch_bounds__(AKR_THREADS, KIND == 0 ? AKR_MINB0 : AKR_MINB1
             hit.slot = hit.free_slot = -1;
             hit.h = hit.want = hit.tag = hit.ids01 = 0ull;
             if (i < cnt) {
-                const long long s = s_wt + i;
-                AkEvent ev = A.S.ev[s];
+                AkEvent ev = ev_cur;
                 const uint32_t kind = ev.meta & 7u, len = ev.meta >> 3;
                 unsigned long long k[4] = {0ull, 0ull, 0ull, 0ull};
                 if (kind <= AKE_WORD && len <= AKC_MAXLEN) akc_key0123(X.text, X.tb + ev.pos, len, X.te, k);
