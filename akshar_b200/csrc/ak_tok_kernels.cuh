@@ -415,11 +415,20 @@ __device__ __noinline__ bool aku_word_lattice_warp(const AkUniDev& U, const uint
     return true;
 }
 
+// CTAs per SM the resolve kernel is compiled for: 4 (64 registers) since the next round's event is fetched ahead -- the loop
+// is bound by round trips, and a fourth CTA's warps hide more of them than the 14 extra registers of 3 CTAs saved
+// (3.38 -> 2.83 ms BPE, 4.07 -> 3.76 ms Unigram; 5 and 6 CTAs: 2.89 / 2.85 ms BPE, 4.46 ms Unigram)
 #ifndef AKR_MINB0
-#define AKR_MINB0 3
+#define AKR_MINB0 4
 #endif
 #ifndef AKR_MINB1
-#define AKR_MINB1 3
+#define AKR_MINB1 4
+#endif
+#ifndef AKE_MINB
+#define AKE_MINB 5                                     // emit: 1.10 -> 1.04 ms at 5 CTAs per SM (6: 1.11)
+#endif
+#ifndef AKC_MINB
+#define AKC_MINB 4
 #endif
 template <int KIND>
 __global__ void __launch_bounds__(AKR_THREADS, KIND == 0 ? AKR_MINB0 : AKR_MINB1) ak_resolve_kernel(const AkResolveArgs A) {
@@ -543,7 +552,7 @@ struct AkCheckArgs {
     const unsigned int* any_flag;
 };
 
-__global__ void __launch_bounds__(AKL_THREADS, 4) ak_unicheck_kernel(const AkCheckArgs A) {
+__global__ void __launch_bounds__(AKL_THREADS, AKC_MINB) ak_unicheck_kernel(const AkCheckArgs A) {
     AkBatch B = A.B;
     if (!ak_batch_begin(B)) return;
     AkLookupCtx X = A.X;
@@ -622,7 +631,7 @@ struct AkEmitArgs {
 };
 
 template <class IdT>
-__global__ void __launch_bounds__(AKL_THREADS, 4) ak_emit_kernel(const AkEmitArgs A) {
+__global__ void __launch_bounds__(AKL_THREADS, AKE_MINB) ak_emit_kernel(const AkEmitArgs A) {
     AkBatch B = A.B;
     if (!ak_batch_begin(B)) return;
     AkLookupCtx X = A.X;
