@@ -428,7 +428,7 @@ __device__ __noinline__ bool aku_word_lattice_warp(const AkUniDev& U, const uint
 #define AKE_MINB 5                                     // emit: 1.10 -> 1.04 ms at 5 CTAs per SM (6: 1.11)
 #endif
 #ifndef AKC_MINB
-#define AKC_MINB 4
+#define AKC_MINB 8                                     // unicheck: latency bound, 32 registers are enough (12.15 -> 11.56 ms per GiB step)
 #endif
 template <int KIND>
 __global__ void __launch_bounds__(AKR_THREADS, KIND == 0 ? AKR_MINB0 : AKR_MINB1) ak_resolve_kernel(const AkResolveArgs A) {
