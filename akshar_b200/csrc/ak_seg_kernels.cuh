@@ -212,7 +212,10 @@ struct AkSegMaskArgs {
 };
 
 #define AKSM_THREADS 128
-__global__ void __launch_bounds__(AKSM_THREADS, 8) ak_seg_mask_kernel(const AkSegMaskArgs A) {
+#ifndef AKSM_MINB
+#define AKSM_MINB 8
+#endif
+__global__ void __launch_bounds__(AKSM_THREADS, AKSM_MINB) ak_seg_mask_kernel(const AkSegMaskArgs A) {
     AkBatch B = A.B;
     if (!ak_batch_begin(B)) return;
     const bool want_c = (A.flags & AK_SEG_CLUSTERS) != 0, want_r = (A.flags & AK_SEG_RUNS) != 0;

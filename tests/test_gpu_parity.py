@@ -807,3 +807,46 @@ def test_sharded_encode_two_gpus(A):
                          timeout=900)
     assert out.returncode == 0, out.stderr[-2000:]
     assert out.stdout.count(': True') == 2
+
+
+def test_invalid_utf8_is_survived(A, eng, models_dir):
+    """the reference only ever sees Python strings; the C ABI takes bytes.  Arbitrary bytes (stray continuation bytes,
+    truncated sequences, 0xFF, overlong forms) must come back as a status or as garbage -- never as a fault or a hang"""
+    import torch
+    from akshar_b200 import _lib as C
+    rng = np.random.default_rng(99)
+    tb = A.aksharTokenizer(os.path.join(models_dir, 'bpe24k.json'), 'bpe')
+    tu = A.aksharTokenizer(os.path.join(models_dir, 'spm24k.model'), 'sentencepiece')
+    pools = [np.arange(256, dtype=np.uint8),
+             np.array([0x80, 0xBF, 0xC0, 0xC2, 0xE0, 0xA4, 0xA5, 0xBC, 0x8D, 0xED, 0xF0, 0xF4, 0xFF, 0x20, 0x61, 0x0A, 0x3C, 0x73, 0x3E], dtype=np.uint8)]
+    for pool in pools:
+        for n_rows, max_len in ((3000, 200), (20, 20000), (1, 300000)):
+            lens = rng.integers(0, max_len + 1, size=n_rows)
+            off = np.zeros(n_rows + 1, dtype=np.int64)
+            np.cumsum(lens, out=off[1:])
+            data = pool[rng.integers(0, pool.size, size=int(off[-1]))]
+            host = (torch.from_numpy(data), torch.from_numpy(off))
+            for e in (eng, tb._eng, tu._eng):
+                b = e.put(host)
+                e.normalize_batch(b, check=False)
+                e.normalize_batch(b, clean_hinglish=False, check=False)
+                e.segment_batch(b, clusters=True, runs=True, check=False)
+                e.segment_masks(b, clusters=True, runs=True, check=False)
+                e.normalize_segment_batch(b, check=False)
+                for rule in (C.WORDS_HINDI, C.WORDS_SPLIT):
+                    try:
+                        e.word_tokenize_batch(b, rule=rule, row_flags=True)
+                    except Exception as ex:
+                        assert 'word_tokenize' in str(ex)
+                try:
+                    e.lines_batch(b.data, b.n_bytes)
+                except Exception as ex:
+                    assert 'lines' in str(ex)
+            for tk, kind in ((tb, 0), (tu, 1)):
+                for mode in (C.MODE_TILES, C.MODE_ROWS):
+                    tk._eng.tokenizer_encode_batch(host, kind, mode=mode, check=False)
+                    tk._eng.tokenizer_encode_batch(host, kind, clean_hinglish=False, mode=mode, check=False)
+            torch.cuda.synchronize()
+    # the contexts are still good for real work afterwards
+    assert tb.encode('hello') == O.bpe_encode(O.BpeModel(os.path.join(models_dir, 'bpe24k.json')), 'hello')
+    assert tu.decode(tu.encode('\u0928\u092e\u0938\u094d\u0924\u0947 world')) == '\u0928\u092e\u0938\u094d\u0924\u0947 world'
