@@ -5,6 +5,7 @@ struct AkUniArgs {
     AkBatch B;
     AkUniDev U;
     uint32_t* back;            // scratch: row r uses back[(off[r] - text_begin) + 2 r ...]
+    int64_t back_cap;          // entries the scratch holds
     int32_t* ids;
     int64_t id_cap;
     int64_t* id_splits;
@@ -24,9 +25,15 @@ __global__ void __launch_bounds__(AK_ROWS_BLOCK) ak_unigram_kernel(const AkUniAr
         uint32_t* back = nullptr;
         if (r < B.n_rows) {
             const int64_t rs = B.off[r], re = B.off[r + 1];
-            back = A.back + (rs - B.text_begin) + 2 * r;
-            n = ak_unigram_forward(A.U, B.text, rs, re, back);
-            cnt = ak_unigram_backtrack(A.U, back, n, nullptr, 0, 0);
+            const int64_t at = (rs - B.text_begin) + 2 * r;
+            if (rs < B.text_begin || re < rs || re > B.text_end || at + (re - rs) + 2 > A.back_cap) {
+                // offsets that do not describe rows of this text, or a scratch that is too small: say so instead of walking
+                ak_raise(B.result, AK_ST_INTERNAL);
+            } else {
+                back = A.back + at;
+                n = ak_unigram_forward(A.U, B.text, rs, re, back);
+                cnt = ak_unigram_backtrack(A.U, back, n, nullptr, 0, 0);
+            }
         }
         int total;
         const int pre = ak_block_exscan<AK_ROWS_BLOCK>((int)cnt, ws, total);
@@ -43,7 +50,7 @@ __global__ void __launch_bounds__(AK_ROWS_BLOCK) ak_unigram_kernel(const AkUniAr
             A.id_splits[r] = obase;
             if (r == B.n_rows - 1) A.id_splits[B.n_rows] = obase + cnt;
             if (obase + cnt > A.id_cap) ak_raise(B.result, AK_ST_OVERFLOW);
-            ak_unigram_backtrack(A.U, back, n, A.ids, obase + cnt, A.id_cap);
+            if (back) ak_unigram_backtrack(A.U, back, n, A.ids, obase + cnt, A.id_cap);
         }
     }
 }

@@ -209,8 +209,11 @@ AK_HD_NOINLINE void ak_bpe_span(const AkBpeDev& M, const AkTables& T, const uint
     row_first = row_last = 0;
     int64_t p = s;
     if (p < total_end && p > off[0]) {
+        // (only inside a row: a row that BEGINS with continuation bytes -- bytes that are not UTF-8 -- keeps them, so that
+        // its row-start event is still met; nothing is skipped across the next row start either)
+        const int64_t nr0 = ak_row_lower_bound(off, r_lo, r_hi, p);
         int k = 0;
-        while (p < e && p < total_end && k < 3 && (t[p] & 0xC0u) == 0x80u) { ++p; ++k; }
+        while (off[nr0] != s && p < e && p < total_end && p < off[nr0] && k < 3 && (t[p] & 0xC0u) == 0x80u) { ++p; ++k; }
     }
     if (p >= e) return;
     int64_t nr = ak_row_lower_bound(off, r_lo, r_hi, p);

@@ -251,8 +251,11 @@ AK_HD_NOINLINE int64_t ak_norm_span(const AkTables& T, const uint8_t* t, const i
     int64_t p = s;
     // skip continuation bytes of a code point owned by the previous span (never past a row start: valid UTF-8)
     if (p < total_end && p > off[0]) {
+        // (only inside a row: a row that BEGINS with continuation bytes -- bytes that are not UTF-8 -- keeps them, so that
+        // its row-start event is still met; nothing is skipped across the next row start either)
+        const int64_t nr0 = ak_row_lower_bound(off, r_lo, r_hi, p);
         int k = 0;
-        while (p < e && p < total_end && k < 3 && (t[p] & 0xC0u) == 0x80u) { ++p; ++k; }
+        while (off[nr0] != s && p < e && p < total_end && p < off[nr0] && k < 3 && (t[p] & 0xC0u) == 0x80u) { ++p; ++k; }
     }
     if (p >= e) return 0;
     int64_t nr = ak_row_lower_bound(off, r_lo, r_hi, p);       // next row-start event
@@ -445,8 +448,11 @@ AK_HD_NOINLINE void ak_seg_span(const AkTables& T, const uint8_t* t, const int64
     n_runs = 0;
     int64_t p = s;
     if (p < total_end && p > off[0]) {
+        // (only inside a row: a row that BEGINS with continuation bytes -- bytes that are not UTF-8 -- keeps them, so that
+        // its row-start event is still met; nothing is skipped across the next row start either)
+        const int64_t nr0 = ak_row_lower_bound(off, r_lo, r_hi, p);
         int k = 0;
-        while (p < e && p < total_end && k < 3 && (t[p] & 0xC0u) == 0x80u) { ++p; ++k; }
+        while (off[nr0] != s && p < e && p < total_end && p < off[nr0] && k < 3 && (t[p] & 0xC0u) == 0x80u) { ++p; ++k; }
     }
     if (p >= e) return;
     int64_t nr = ak_row_lower_bound(off, r_lo, r_hi, p);
