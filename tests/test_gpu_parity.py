@@ -846,6 +846,18 @@ def test_invalid_utf8_is_survived(A, eng, models_dir):
                 for mode in (C.MODE_TILES, C.MODE_ROWS):
                     tk._eng.tokenizer_encode_batch(host, kind, mode=mode, check=False)
                     tk._eng.tokenizer_encode_batch(host, kind, clean_hinglish=False, mode=mode, check=False)
+                # ids that are no ids: negative, beyond the vocabulary, as int32
+                ids = torch.from_numpy(rng.integers(-5, 40000, size=int(off[-1]) // 4 + 1).astype(np.int32))
+                sp = torch.from_numpy(np.minimum(off // 4, ids.numel()).astype(np.int64))
+                for form in (C.FORM_DECODE, C.FORM_DETOKENIZE):
+                    try:
+                        tk._eng.decode_batch(ids, sp, kind, form)
+                    except IndexError:
+                        assert kind == 1                              # SentencePiece: 'piece id is out of range.'
+            try:
+                eng.signature_batch(eng.put(host))
+            except Exception as ex:
+                assert 'signature' in str(ex)
             torch.cuda.synchronize()
     # the contexts are still good for real work afterwards
     assert tb.encode('hello') == O.bpe_encode(O.BpeModel(os.path.join(models_dir, 'bpe24k.json')), 'hello')
