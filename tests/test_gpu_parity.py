@@ -862,3 +862,36 @@ def test_invalid_utf8_is_survived(A, eng, models_dir):
     # the contexts are still good for real work afterwards
     assert tb.encode('hello') == O.bpe_encode(O.BpeModel(os.path.join(models_dir, 'bpe24k.json')), 'hello')
     assert tu.decode(tu.encode('\u0928\u092e\u0938\u094d\u0924\u0947 world')) == '\u0928\u092e\u0938\u094d\u0924\u0947 world'
+
+
+def test_texts_that_do_not_start_at_an_aligned_zero(A, eng, golden):
+    """text_begin != 0 and addresses that are not 16-byte aligned through the round-2 entry points: same results"""
+    import torch
+    from akshar_b200 import _lib as C
+    lines = [r['in'] for r in golden['rows'][:1500]] + ['', 'x']
+    data, off = sc.pack(lines)
+    base = eng.put((torch.from_numpy(data), torch.from_numpy(off)))
+    nb = eng.normalize_batch(base)
+    wb0, we0, sp0, fl0 = eng.word_tokenize_batch(nb, rule=C.WORDS_HINDI, row_flags=True)
+    n0, mk0 = eng.normalize_segment_batch(base)
+    for lead in (1, 5, 16, 21):
+        pad = np.full(lead, 0x61, dtype=np.uint8)
+        d = torch.from_numpy(np.concatenate([pad, data])).cuda()
+        o = torch.from_numpy(off + lead).cuda()
+        tb = A.TextBatch(d, o, lead, lead + int(off[-1]))
+        nd = torch.cat([torch.from_numpy(pad).cuda(), nb.data[:nb.end]])
+        tn = A.TextBatch(nd, nb.offsets + lead, lead, lead + nb.end)
+        wb, we, sp, fl = eng.word_tokenize_batch(tn, rule=C.WORDS_HINDI, row_flags=True)
+        assert torch.equal(wb, wb0) and torch.equal(we, we0) and torch.equal(sp, sp0) and torch.equal(fl, fl0)
+        n1, mk1 = eng.normalize_segment_batch(tb)
+        assert n1.end == n0.end and torch.equal(n1.data[:n1.end], n0.data[:n0.end]) and torch.equal(n1.offsets, n0.offsets)
+        W = (n0.end + 32) // 32
+        for key in ('cluster', 'run'):
+            assert torch.equal(mk1[key][:W], mk0[key][:W])
+        assert torch.equal(mk1['tags'][:, :W], mk0['tags'][:, :W])
+        # a file whose first byte sits at an odd address
+        f = eng.join_rows(base)
+        shifted = torch.cat([torch.from_numpy(pad).cuda(), f])[lead:]
+        rows_a, rows_b = eng.lines_batch(f, f.numel()), eng.lines_batch(shifted, shifted.numel())
+        assert rows_a.end == rows_b.end and torch.equal(rows_a.offsets, rows_b.offsets)
+        assert torch.equal(rows_a.data[:rows_a.end], rows_b.data[:rows_b.end])
