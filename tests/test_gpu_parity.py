@@ -895,3 +895,34 @@ def test_texts_that_do_not_start_at_an_aligned_zero(A, eng, golden):
         rows_a, rows_b = eng.lines_batch(f, f.numel()), eng.lines_batch(shifted, shifted.numel())
         assert rows_a.end == rows_b.end and torch.equal(rows_a.offsets, rows_b.offsets)
         assert torch.equal(rows_a.data[:rows_a.end], rows_b.data[:rows_b.end])
+
+
+def test_edge_batches_round2_entries(A, eng, models_dir, tmp_path):
+    """no rows, empty rows, one-byte rows and files of nothing but line ends through the word tokenizers, decode,
+    composition, cluster merges, the fused normalize + segment call and the file front end"""
+    from akshar_b200 import corpus, segment as S
+    for fn in (S.word_tokenize_hindi_batch, S.word_tokenize_batch, S.akshara_level_tokenization_batch, S.preserve_nukta_batch,
+               S.analyze_text_composition_batch):
+        assert fn([]) == []
+    assert S.normalize_and_segment_batch([]) == ([], [])
+    edge = ['', ' ', '\u0964', 'a', '', '\u093c', '\u0915\u094d', '.', '\u3000', '']
+    assert S.word_tokenize_hindi_batch(edge) == [O.word_tokenize_hindi(t) for t in edge]
+    assert S.word_tokenize_batch(edge) == [O.word_tokenize(t) for t in edge]
+    assert S.akshara_level_tokenization_batch(edge) == [O.akshara_level_tokenization(t) for t in edge]
+    assert S.preserve_nukta_batch(edge) == [O.preserve_nukta(t) for t in edge]
+    assert S.analyze_text_composition_batch(edge) == [O.analyze_text_composition(t) for t in edge]
+    strings, akshars = S.normalize_and_segment_batch(edge)
+    assert strings == [O.normalize_text(t) for t in edge]
+    assert akshars == [O.segment_akshars(O.normalize_text(t)) for t in edge]
+    for name, kind in (('bpe24k.json', 'bpe'), ('spm24k.model', 'sentencepiece')):
+        tk = A.aksharTokenizer(os.path.join(models_dir, name), kind)
+        assert tk.decode_batch([]) == [] and tk.detokenize_batch([]) == []
+        assert tk.decode_batch([[], [], []]) == ['', '', ''] and tk.detokenize_batch([[], []]) == ['', '']
+        one = tk.encode('a')
+        assert tk.decode_batch([[], one, []]) == ['', tk.decode(one), '']
+    for i, body in enumerate((b'', b'\n', b'\r\n\r\n', b' \t \n\n  ', b'x', b'\nx', b'x\n', b'\r', b' x \r y ')):
+        f = tmp_path / f'e{i}.txt'
+        f.write_bytes(body)
+        with open(f, 'r', encoding='utf-8') as h:
+            ref = [ln.strip() for ln in h.readlines() if ln.strip()]
+        assert corpus.read_rows(str(f)) == ref, body
