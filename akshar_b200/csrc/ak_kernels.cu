@@ -291,7 +291,7 @@ static AkWsLayout ak_ws_layout(int64_t n_bytes, int64_t n_rows) {
     // Unigram row kernel / signatures: one 4-byte slot per code point (+ 2 per row)
     size_t m = 4 * (size_t)(n_bytes + 2 * n_rows + 2);
     // fast normalize: per-lane info words, tile totals / bases, slow work list
-    const size_t nf = ak_align(tiles * AK_BLOCK * 4) + ak_align(tiles * 4) + ak_align((tiles + 1) * 8) +
+    const size_t nf = ak_align(tiles * AK_BLOCK * 4) + ak_align(tiles * AKF_WARPS * 4) + ak_align((tiles * AKF_WARPS + 1) * 8) +
                       ak_align((tiles * AK_BLOCK / 16 + 1024) * sizeof(AkSlowEntry));
     if (nf > m) m = nf;
     // segment / word tokenizers: warp-tile row table, two counts and two bases per 960-byte warp tile

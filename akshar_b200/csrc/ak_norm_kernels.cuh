@@ -96,7 +96,7 @@ struct AkSlowEntry {
     int64_t pos;         // span start (absolute byte index)
     int64_t out_base;    // filled by the write kernel: where this span's output starts
     int32_t cnt;         // filled by the slow kernel's first pass
-    int32_t tile;
+    int32_t tile;        // the 480-byte warp tile the span lies in (tile * AKF_WARPS + warp)
     int32_t span;        // 16, or 32: both chunks of a bit-parallel lane in one walk (the second chunk's info word is
     int32_t pad_;        // 0xC0000000 | index: "continued", no bytes of its own)
     uint8_t bytes[AK_SLOW_BYTES];      // the span's output when it fits (else the second pass walks again)
@@ -104,8 +104,8 @@ struct AkSlowEntry {
 
 struct AkNfWork {
     uint32_t* info;            // [n_tiles * AK_BLOCK] per lane: emit mask, or 0x80000000 | work-list index
-    int32_t* tile_total;       // [n_tiles] output bytes of the tile
-    int64_t* tile_base;        // [n_tiles + 1] exclusive prefix
+    int32_t* tile_total;       // [n_tiles * AKF_WARPS] output bytes of every 480-byte warp tile
+    int64_t* tile_base;        // [n_tiles * AKF_WARPS + 1] exclusive prefix
     AkSlowEntry* slow;
     unsigned int* n_slow;
     unsigned int slow_cap;
@@ -132,7 +132,6 @@ __device__ __forceinline__ void akf_load_lane(const AkBatch& B, int64_t cs, CH& 
 #define AKN3_MINB 8
 #endif
 __global__ void __launch_bounds__(AKN3_THREADS, AKN3_MINB) ak_nf3_classify_kernel(const AkFastNormArgs A, const AkNfWork W) {
-    __shared__ int s_red[AKN3_THREADS / 32];
     const AkBatch& B = A.B;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t tb = B.text_begin, te = B.text_end;
@@ -210,7 +209,7 @@ __global__ void __launch_bounds__(AKN3_THREADS, AKN3_MINB) ak_nf3_classify_kerne
                     e.pos = act[0] ? cs : cs + 16;
                     e.out_base = 0;
                     e.cnt = 0;
-                    e.tile = tile;
+                    e.tile = tile * AKF_WARPS + 2 * warp + (lane >> 4);
                     e.span = (act[0] && act[1]) ? 32 : 16;
                     e.pad_ = 0;
                     W.slow[idx] = e;
@@ -227,17 +226,10 @@ __global__ void __launch_bounds__(AKN3_THREADS, AKN3_MINB) ak_nf3_classify_kerne
             }
         }
         if (tid < 2 * AKF_WARPS) W.info[(size_t)tile * AK_BLOCK + (tid >> 1) * 32 + (tid & 1) * 31] = 0;   // the v2 halo slots
+        // the warp's 960 bytes are two of the writer's 480-byte warp tiles: lanes 1-15 and lanes 16-30 (the halo lanes count 0)
 #pragma unroll
-        for (int d = 16; d > 0; d >>= 1) cnt += __shfl_xor_sync(0xFFFFFFFFu, cnt, d);
-        if (lane == 0) s_red[warp] = cnt;
-        __syncthreads();
-        if (tid == 0) {
-            int t = 0;
-#pragma unroll
-            for (int w = 0; w < AKN3_THREADS / 32; ++w) t += s_red[w];
-            W.tile_total[tile] = t;
-        }
-        __syncthreads();
+        for (int d = 8; d > 0; d >>= 1) cnt += __shfl_xor_sync(0xFFFFFFFFu, cnt, d);
+        if ((lane & 15) == 0) W.tile_total[(size_t)tile * AKF_WARPS + 2 * warp + (lane >> 4)] = cnt;
     }
 }
 
@@ -266,7 +258,8 @@ __global__ void __launch_bounds__(128, AKN_SLOW_MINB) ak_nf_slow_kernel(const Ak
         AkSlowEntry e = A.W.slow[j];
         const int64_t ss = e.pos < B.text_begin ? B.text_begin : e.pos;
         const int64_t se = e.pos + e.span > B.text_end + 1 ? B.text_end + 1 : e.pos + e.span;
-        const int64_t r0 = A.tile_row[(size_t)e.tile * AKF_WARPS], r1 = A.tile_row[(size_t)(e.tile + 1) * AKF_WARPS];
+        const size_t cta_tile = (size_t)e.tile / AKF_WARPS;
+        const int64_t r0 = A.tile_row[cta_tile * AKF_WARPS], r1 = A.tile_row[(cta_tile + 1) * AKF_WARPS];
         const int64_t rlo = r0 > 0 ? r0 - 1 : 0, rhi = r1 > B.n_rows ? B.n_rows : r1;
         uint32_t st = 0;
         if (!A.write) {
@@ -325,36 +318,42 @@ __device__ __forceinline__ void akf_write_run(const AkChunk& c, uint32_t emit, u
     if (r > 2) dt[2] = (uint8_t)(tv >> 16);
 }
 
-// ---- K1d: write the fast lanes' bytes (staged in shared memory, 16-byte stores) and the row offsets
+// ---- K1d: write the fast lanes' bytes (staged in shared memory, 16-byte stores) and the row offsets.  Warp-autonomous:
+// a warp owns 480 text bytes (30 real lanes of 16 + the two halo slots of the info layout), its output base comes from
+// the scan over the warp tiles' totals, its stage is its own -- no CTA barrier, no CTA scan.
+#define AKF_WSTAGE (AKF_WARP_BYTES + 160)
 __global__ void __launch_bounds__(AK_BLOCK) ak_nf_write_kernel(const AkFastNormArgs A, const AkNfWork W) {
-    __shared__ __align__(16) uint8_t stage[AKF_STAGE + 32];
-    __shared__ uint32_t s_emit[AK_BLOCK];
-    __shared__ uint32_t s_pre[AK_BLOCK];
-    __shared__ int ws[33];
+    __shared__ __align__(16) uint8_t stage_all[AKF_WARPS][AKF_WSTAGE + 32];
     const AkBatch& B = A.B;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int tile = blockIdx.x; tile < B.n_tiles; tile += gridDim.x) {
-        const int64_t tile_start = A.base0 + (int64_t)tile * AKF_TILE;
-        const int64_t r0 = A.tile_row[(size_t)tile * AKF_WARPS], r1 = A.tile_row[(size_t)(tile + 1) * AKF_WARPS];
-        const int64_t cs = tile_start + (int64_t)warp * AKF_WARP_BYTES + (int64_t)(lane - 1) * 16;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint8_t* stage = stage_all[warp];
+    const long long n_wt = (long long)B.n_tiles * AKF_WARPS;
+    for (long long wt = (long long)blockIdx.x * AKF_WARPS + warp; wt < n_wt; wt += (long long)gridDim.x * AKF_WARPS) {
+        const int64_t ws0 = A.base0 + wt * AKF_WARP_BYTES;
+        const int64_t r0 = A.tile_row[wt], r1 = A.tile_row[wt + 1];
+        const int64_t cs = ws0 + (int64_t)(lane - 1) * 16;
         AkChunk c;
         akf_load_lane(B, cs, c);
-        const uint32_t info = W.info[(size_t)tile * AK_BLOCK + tid];
+        const uint32_t info = W.info[(size_t)wt * 32 + lane];
         const bool slow = (info & 0x80000000u) != 0;
         const bool cont = slow && (info & 0x40000000u);          // second chunk of a 32-byte slow span: nothing of its own
         const unsigned int sidx = info & 0x3FFFFFFFu;
         int cnt = 0;
         if (slow) { if (sidx < W.slow_cap && !cont) cnt = W.slow[sidx].cnt; }
         else cnt = __popc(info);
-        int total;
-        const int pre = ak_block_exscan<AK_BLOCK>(cnt, ws, total);
-        const int64_t base = W.tile_base[tile];
+        int inc = cnt;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int y = __shfl_up_sync(0xFFFFFFFFu, inc, d);
+            if (lane >= d) inc += y;
+        }
+        const int total = __shfl_sync(0xFFFFFFFFu, inc, 31);
+        const int pre = inc - cnt;
+        const int64_t base = W.tile_base[wt];
         const bool fits = base + total <= A.out_cap;
-        const bool staged = fits && total <= AKF_STAGE;
+        const bool staged = fits && total <= AKF_WSTAGE;
         const int pad = (int)((uintptr_t)(A.out + base) & 15);
-        if (!fits && tid == 0 && total > 0) ak_raise(B.result, AK_ST_OVERFLOW);
-        s_emit[tid] = info;
-        s_pre[tid] = (uint32_t)pre;
+        if (!fits && lane == 0 && total > 0) ak_raise(B.result, AK_ST_OVERFLOW);
         if (slow) {
             if (sidx < W.slow_cap && !cont) {
                 W.slow[sidx].out_base = base + pre;
@@ -370,35 +369,38 @@ __global__ void __launch_bounds__(AK_BLOCK) ak_nf_write_kernel(const AkFastNormA
             if (staged && ((info + lowbit) & info) == 0u && lowbit <= 8u) akf_write_run(c, info, dst);     // one contiguous stretch
             else akf_write(c, info, dst);
         }
-        __syncthreads();
+        __syncwarp();
         if (staged) {
             // stage[pad .. pad + total) -> out[base ..): stage and global share their alignment modulo 16.  The holes
             // of slow chunks are copied as garbage here and filled by the slow write kernel afterwards.
             uint8_t* g = A.out + base;
             int head = (16 - pad) & 15;
             if (head > total) head = total;
-            if (tid < head) g[tid] = stage[pad + tid];
+            if (lane < head) g[lane] = stage[pad + lane];
             const int body = (total - head) >> 4;
-            for (int i = tid; i < body; i += AK_BLOCK)
+            for (int i = lane; i < body; i += 32)
                 *reinterpret_cast<uint4*>(g + head + 16 * i) = *reinterpret_cast<const uint4*>(stage + pad + head + 16 * i);
             const int tail0 = head + (body << 4);
-            if (tid < total - tail0) g[tail0 + tid] = stage[pad + tail0 + tid];
+            if (lane < total - tail0) g[tail0 + lane] = stage[pad + tail0 + lane];
         }
-        // row offsets of the rows that start in a fast chunk of this tile (slow chunks write their own)
-        for (int64_t r = r0 + tid; r < r1 && r <= B.n_rows; r += AK_BLOCK) {
-            const int rel = (int)(B.off[r] - tile_start);
-            const int wq = rel / AKF_WARP_BYTES, within = rel - wq * AKF_WARP_BYTES;
-            const int th = wq * 32 + 1 + (within >> 4), i = within & 15;
-            const uint32_t e = s_emit[th];
-            if (!(e & 0x80000000u)) A.out_off[r] = base + s_pre[th] + __popc(e & ((1u << i) - 1u));
+        // row offsets of the rows that start in a fast chunk of this warp tile (slow chunks write their own)
+        const int64_t r_end = r1 <= B.n_rows ? r1 : B.n_rows + 1;
+        for (int64_t rr = r0; rr < r_end; rr += 32) {
+            const int64_t r = rr + lane;
+            const bool have = r < r_end;
+            const int rel = have ? (int)(B.off[r] - ws0) : 0;
+            const int th = 1 + (rel >> 4), i = rel & 15;
+            const uint32_t e = __shfl_sync(0xFFFFFFFFu, info, th);
+            const int p = __shfl_sync(0xFFFFFFFFu, pre, th);
+            if (!have) continue;
+            if (!(e & 0x80000000u)) A.out_off[r] = base + p + __popc(e & ((1u << i) - 1u));
             else {
                 // the slow pass left it relative to the span's output; a continued chunk's prefix already includes the span
                 int64_t adj = 0;
                 if ((e & 0x40000000u) && (e & 0x3FFFFFFFu) < W.slow_cap) adj = W.slow[e & 0x3FFFFFFFu].cnt;
-                A.out_off[r] += base + s_pre[th] - adj;
+                A.out_off[r] += base + p - adj;
             }
         }
-        __syncthreads();
+        __syncwarp();
     }
 }
-
