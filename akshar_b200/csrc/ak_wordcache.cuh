@@ -98,11 +98,14 @@ AK_HD void akc_key0123(const uint8_t* t, int64_t s, uint32_t len, int64_t te, un
         for (int i = 0; i < 9; ++i) x[i] = __ldg(w + i <= last ? w + i : last);
     }
     uint32_t f[8];
+    const int len8 = 8 * (int)len;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-        f[i] = __funnelshift_r(x[i], x[i + 1], sh);
-        const int rb = (int)len - 4 * i;                            // bytes of the word in this 32-bit piece
-        f[i] = rb >= 4 ? f[i] : rb <= 0 ? 0u : (f[i] & ((1u << (8 * rb)) - 1u));
+        // bits of the word in this 32-bit piece: 0 .. 32 and beyond.  PTX shl clamps the amount at 32 (-> 0, mask of ones)
+        const int bits = max(len8 - 32 * i, 0);
+        uint32_t m;
+        asm("shl.b32 %0, %1, %2;" : "=r"(m) : "r"(1u), "r"((uint32_t)bits));
+        f[i] = __funnelshift_r(x[i], x[i + 1], sh) & (m - 1u);
     }
 #pragma unroll
     for (int j = 0; j < 4; ++j) k[j] = ((unsigned long long)f[2 * j + 1] << 32) | f[2 * j];
