@@ -285,16 +285,16 @@ struct AkUniWarpScratch {
     float ratio, wmag;
 };
 
-__device__ __forceinline__ double aku_shfl_xor_d(double v, int d) {
-    return __hiloint2double(__shfl_xor_sync(0xFFFFFFFFu, __double2hiint(v), d), __shfl_xor_sync(0xFFFFFFFFu, __double2loint(v), d));
-}
+// warp maximum of a double (no NaNs): the bits mapped to an unsigned key of the same order, one `redux.sync` for the high
+// words, one for the low words of the lanes that hold the highest -- a selection, so the result is the exact maximum
 __device__ __forceinline__ double aku_warp_max_d(double v) {
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) {
-        const double y = aku_shfl_xor_d(v, d);
-        v = y > v ? y : v;
-    }
-    return v;
+    const uint32_t hi = (uint32_t)__double2hiint(v), lo = (uint32_t)__double2loint(v);
+    const uint32_t neg = (uint32_t)((int32_t)hi >> 31);
+    const uint32_t khi = hi ^ (neg | 0x80000000u), klo = lo ^ neg;
+    const uint32_t H = __reduce_max_sync(0xFFFFFFFFu, khi);
+    const uint32_t L = __reduce_max_sync(0xFFFFFFFFu, khi == H ? klo : 0u);
+    const uint32_t back = (H & 0x80000000u) ? 0u : 0xFFFFFFFFu;
+    return __hiloint2double((int)(H ^ (back | 0x80000000u)), (int)(L ^ back));
 }
 
 // all 32 lanes call this with the same word; false = the word does not fit the cooperative scheme (the caller's serial path
