@@ -926,3 +926,30 @@ def test_edge_batches_round2_entries(A, eng, models_dir, tmp_path):
         with open(f, 'r', encoding='utf-8') as h:
             ref = [ln.strip() for ln in h.readlines() if ln.strip()]
         assert corpus.read_rows(str(f)) == ref, body
+
+
+def test_normalize_text_that_expands(A, eng):
+    """NFC makes composition exclusions longer (U+0958-095F: 3 -> 6 bytes, U+FB2A-FB4E: 3 -> 4-6 bytes): warp tiles full
+    of them overflow the writer's shared-memory stage (the direct path) and nearly every lane is a slow lane.  Runs of
+    such letters are kept below the 64 code points one NFC segment may have (AKSHAR_ST_NFC_SEGMENT, checked last)."""
+    import random
+    from akshar_b200 import segment as S
+    from akshar_b200.batch import BatchStatusError
+    rng = random.Random(5)
+    excl = [chr(c) for c in range(0x958, 0x960)] + ['\ufb2a', '\ufb2b', '\ufb2e', '\ufb4b', '\u0f43', '\u2adc']
+    lines = []
+    for i in range(600):
+        n = rng.choice((1, 7, 40, 200, 700, 3000))
+        body = []
+        for k in range(n):
+            body.append(rng.choice('\u0915\u093e\u0964') if k % 20 == 19 else rng.choice(excl) if rng.random() < 0.95 else rng.choice('ab '))
+        lines.append(''.join(body))
+    lines += ['\u0958\u093e' * 2500, 'x' + '\u095c\u094d\u0915' * 1700, '']
+    for nr, nc in ((True, True), (True, False), (False, False)):
+        got = A.normalize_batch(lines, normalize_roman=nr, clean_hinglish=nc)
+        assert got == [O.normalize_text(t, nr, nc) for t in lines]
+    strings, akshars = S.normalize_and_segment_batch(lines)
+    assert strings == [O.normalize_text(t) for t in lines]
+    assert akshars == [O.segment_akshars(t) for t in strings]
+    with pytest.raises(BatchStatusError):       # 65+ code points in a row that NFC decomposes: one segment, refused loudly
+        A.normalize_batch(['\u0958' * 80])
