@@ -45,38 +45,41 @@ template <class ScanEnd>
 AK_HD int ake_lane_events(uint32_t rowsm, uint32_t wstart, uint32_t cw, uint32_t bnd, uint32_t nb1, uint32_t nb2, int tail_known,
                           int64_t cs, int64_t tb, const int64_t* off, int64_t n_rows, int64_t first_row, int nrows, int64_t at,
                           uint32_t* row_ev, AkEvent* dst, int64_t cap_left, ScanEnd scan_end) {
-    int k = 0;
-    uint32_t m = rowsm | wstart;
+    // Two loops instead of one over (rowsm | wstart): a slot index is a popcount, so the (few) row events do not hold up the
+    // word events of the other lanes in every iteration.  At one position the row event comes first.
     const bool simple = nrows == akb_popc(rowsm);
     int64_t nr = first_row;
-    while (m) {
+    int kr = 0;
+    for (uint32_t m = rowsm; m; ++kr) {
         const int i = akb_ctz(m);
         m &= m - 1u;
         const int64_t p = cs + i;
-        if ((rowsm >> i) & 1u) {
-            uint32_t kind = AKE_ROW;
-            if (!simple) {
-                while (nr < n_rows && off[nr] < p) ++nr;
-                if (nr < n_rows && off[nr + 1] == p) kind = AKE_ROWS;
-            }
-            if (k < cap_left) { dst[k].pos = (uint32_t)(p - tb); dst[k].meta = ((uint32_t)nr << 3) | kind; }
-            if (simple) row_ev[nr++] = (uint32_t)(at + k);
-            else while (nr <= n_rows && off[nr] == p) row_ev[nr++] = (uint32_t)(at + k);      // empty rows share the position: one event
-            ++k;
+        const int k = kr + akb_popc(wstart & ((1u << i) - 1u));
+        uint32_t kind = AKE_ROW;
+        if (!simple) {
+            while (nr < n_rows && off[nr] < p) ++nr;
+            if (nr < n_rows && off[nr + 1] == p) kind = AKE_ROWS;
         }
-        if ((wstart >> i) & 1u) {
-            const uint32_t above = bnd & ~((2u << i) - 1u);
-            int64_t len;
-            if (above) len = akb_ctz(above) - i;
-            else if (nb1) len = 32 - i + akb_ctz(nb1);
-            else if (nb2) len = 64 - i + akb_ctz(nb2);
-            else len = scan_end(p, cs + tail_known) - p;
-            if (len > (int64_t)AKE_LEN_MAX) len = AKE_LEN_MAX;
-            if (k < cap_left) { dst[k].pos = (uint32_t)(p - tb); dst[k].meta = ((uint32_t)len << 3) | ((cw >> i) & 1u); }
-            ++k;
-        }
+        if (k < cap_left) { dst[k].pos = (uint32_t)(p - tb); dst[k].meta = ((uint32_t)nr << 3) | kind; }
+        if (simple) row_ev[nr++] = (uint32_t)(at + k);
+        else while (nr <= n_rows && off[nr] == p) row_ev[nr++] = (uint32_t)(at + k);      // empty rows share the position: one event
     }
-    return k;
+    int kw = 0;
+    for (uint32_t m = wstart; m; ++kw) {
+        const int i = akb_ctz(m);
+        m &= m - 1u;
+        const int64_t p = cs + i;
+        const int k = kw + akb_popc(rowsm & ((2u << i) - 1u));
+        const uint32_t above = bnd & ~((2u << i) - 1u);
+        int64_t len;
+        if (above) len = akb_ctz(above) - i;
+        else if (nb1) len = 32 - i + akb_ctz(nb1);
+        else if (nb2) len = 64 - i + akb_ctz(nb2);
+        else len = scan_end(p, cs + tail_known) - p;
+        if (len > (int64_t)AKE_LEN_MAX) len = AKE_LEN_MAX;
+        if (k < cap_left) { dst[k].pos = (uint32_t)(p - tb); dst[k].meta = ((uint32_t)len << 3) | ((cw >> i) & 1u); }
+    }
+    return kr + kw;
 }
 
 // the rows that hold the marked bytes of a lane are flagged for the row-fix kernel
