@@ -663,11 +663,17 @@ __global__ void __launch_bounds__(AKL_THREADS, AKE_MINB) ak_emit_kernel(const Ak
               const int i = o4 + 32 * q + lane;
               r4[q] = i < cnt ? A.resolved[s_wt + i] : 0ull;
           }
+          // the four rounds: the scans, and the common case (one or two ids held in the record itself) at once.  Row events
+          // and cache-entry records are rare per lane but present in nearly every round: they wait (their round in `later`,
+          // their place in rel4) and are written after the four scans, each lane walking its own -- ~8 lanes busy per
+          // pass instead of ~2 in every round.
+          const int64_t at_blk = at0;
+          int rel4[4] = {0, 0, 0, 0};
+          uint32_t later = 0u;
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             const int o = o4 + 32 * q;
             if (o >= cnt) break;
-            const int i = o + lane;
             const unsigned long long r = r4[q];
             const unsigned long long ty = r >> 62;
             const int n = ty == AKR_INLINE ? (int)((r >> 60) & 3ull) : akr_n(r);
@@ -678,8 +684,8 @@ __global__ void __launch_bounds__(AKL_THREADS, AKE_MINB) ak_emit_kernel(const Ak
                 if (lane >= d) inc += y;
             }
             const int64_t at = at0 + (inc - n);
+            rel4[q] = (int)(at - at_blk);
             if (ty == AKR_INLINE) {
-                // the common case: one or two ids held in the record itself
                 if (n > 0) {
                     if (at + n > id_cap) st |= AK_ST_OVERFLOW;
                     else {
@@ -687,7 +693,18 @@ __global__ void __launch_bounds__(AKL_THREADS, AKE_MINB) ak_emit_kernel(const Ak
                         if (n > 1) ids[at + 1] = (IdT)((r >> 30) & 0x3FFFFFFFull);
                     }
                 }
-            } else if (ty == AKR_EVENT && !(r & (1ull << 37))) {
+            } else if (o + lane < cnt) later |= 1u << q;
+            at0 += __shfl_sync(0xFFFFFFFFu, inc, 31);
+          }
+          while (later) {
+            const int q = __ffs(later) - 1;
+            later &= later - 1u;
+            const unsigned long long r = q == 0 ? r4[0] : q == 1 ? r4[1] : q == 2 ? r4[2] : r4[3];
+            const int64_t at = at_blk + (q == 0 ? rel4[0] : q == 1 ? rel4[1] : q == 2 ? rel4[2] : rel4[3]);
+            const int i = o4 + 32 * q + lane;
+            const unsigned long long ty = r >> 62;
+            const int n = akr_n(r);
+            if (ty == AKR_EVENT && !(r & (1ull << 37))) {
                 // one (unfixed) row starts here: </s> of the previous row, the split, <s>
                 const int64_t g = (int64_t)(r & ((1ull << 37) - 1ull));
                 int64_t k2 = at;
@@ -716,9 +733,8 @@ __global__ void __launch_bounds__(AKL_THREADS, AKE_MINB) ak_emit_kernel(const Ak
                 if (at + n > id_cap) st |= AK_ST_OVERFLOW;
                 akl_emit(X, r, A.S.ev + s_wt + i, at);
             }
-            at0 += __shfl_sync(0xFFFFFFFFu, inc, 31);
-            __syncwarp();
           }
+          __syncwarp();
         }
     }
     ak_raise(B.result, st);
