@@ -425,7 +425,7 @@ __device__ __noinline__ bool aku_word_lattice_warp(const AkUniDev& U, const uint
 #define AKR_MINB1 4
 #endif
 #ifndef AKE_MINB
-#define AKE_MINB 5                                     // emit: 1.10 -> 1.04 ms at 5 CTAs per SM (6: 1.11)
+#define AKE_MINB 4                                     // emit, with the rare records deferred per four-round block: 4 / 5 / 6 / 3 CTAs per SM = 0.92 / 1.01 / 1.17 / 1.12 ms (64 registers at 4)
 #endif
 #ifndef AKC_MINB
 #define AKC_MINB 8                                     // unicheck: latency bound, 32 registers are enough (12.15 -> 11.56 ms per GiB step)
