@@ -7,7 +7,6 @@
 #define AK_ROWS_BLOCK 128               // rows per tile for the row-per-thread kernels
 #define AKF_WARPS (AK_BLOCK / 32)
 #define AKF_TILE (AKF_WARPS * AKF_WARP_BYTES)     // 3840 text bytes per CTA tile in the fast kernels
-#define AKF_STAGE (AKF_TILE + 1280)               // shared-memory output stage (normalize can expand a little)
 
 static_assert((int)AK_ST_OVERFLOW == (int)AKSHAR_ST_OVERFLOW && (int)AK_ST_NFC_SEGMENT == (int)AKSHAR_ST_NFC_SEGMENT &&
               (int)AK_ST_PATHOLOGICAL == (int)AKSHAR_ST_PATHOLOGICAL && (int)AK_ST_ALPHABET == (int)AKSHAR_ST_ALPHABET &&
