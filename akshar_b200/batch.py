@@ -51,7 +51,7 @@ class TextBatch:
 class BatchStatusError(RuntimeError):
     def __init__(self, bits, what):
         self.bits = bits
-        names = [n for b, n in ((C.ST_OVERFLOW, 'overflow'), (C.ST_NFC_SEGMENT, 'combining sequence longer than 64'),
+        names = [n for b, n in ((C.ST_OVERFLOW, 'overflow'), (C.ST_NFC_SEGMENT, 'NFC segment longer than 256 code points'),
                                 (C.ST_PATHOLOGICAL, 'look-back limit'), (C.ST_ALPHABET, 'code point outside the closed alphabet'),
                                 (C.ST_SPIN, 'tile-prefix spin limit'), (C.ST_WORD, 'word longer than the scratch pool'),
                                 (C.ST_INTERNAL, 'internal consistency check (bits 0x%x)' % bits)) if bits & b]

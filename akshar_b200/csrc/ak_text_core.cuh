@@ -12,7 +12,7 @@
 #pragma once
 #include "ak_unicode.cuh"
 
-#define AK_MAXSEG 64           // decomposed code points per NFC segment handled by the slow lane
+#define AK_MAXSEG 256          // decomposed code points per NFC segment handled by the slow lane
 enum {
     AK_ST_OVERFLOW = 1,        // an output buffer was too small; totals are still exact
     AK_ST_NFC_SEGMENT = 2,     // a non-inert NFC segment exceeded AK_MAXSEG decomposed code points

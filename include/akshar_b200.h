@@ -44,7 +44,7 @@ enum {
 /* status bits in d_result[2] */
 enum {
     AKSHAR_ST_OVERFLOW = 1,      /* an output capacity was too small: re-run with capacity >= total */
-    AKSHAR_ST_NFC_SEGMENT = 2,   /* an NFC segment that needs work exceeds 64 decomposed code points: a starter followed by
+    AKSHAR_ST_NFC_SEGMENT = 2,   /* an NFC segment that needs work exceeds 256 decomposed code points: a starter followed by
                                     that many combining marks, or that many letters in a row that NFC itself decomposes
                                     (U+0958-095F, compatibility ideographs ...) with no other character between them */
     AKSHAR_ST_PATHOLOGICAL = 4,  /* bounded look-back gave up: re-run the same call with AKSHAR_MODE_ROWS */

@@ -951,5 +951,33 @@ def test_normalize_text_that_expands(A, eng):
     strings, akshars = S.normalize_and_segment_batch(lines)
     assert strings == [O.normalize_text(t) for t in lines]
     assert akshars == [O.segment_akshars(t) for t in strings]
-    with pytest.raises(BatchStatusError):       # 65+ code points in a row that NFC decomposes: one segment, refused loudly
-        A.normalize_batch(['\u0958' * 80])
+    with pytest.raises(BatchStatusError):       # 127+ such letters in a row are one NFC segment of more than 256 code points: refused loudly
+        A.normalize_batch(['\u0958' * 200])
+
+
+def test_zalgo_text(A, eng, models_dir):
+    """stacked combining marks (social text has them): up to ~250 marks on one base are reordered / composed exactly as
+    the reference does; the encoders see the same rows"""
+    import random
+    rng = random.Random(11)
+    marks = [chr(c) for c in (0x300, 0x301, 0x302, 0x303, 0x308, 0x30a, 0x316, 0x317, 0x323, 0x324, 0x325, 0x327, 0x328, 0x32d,
+                              0x334, 0x335, 0x336, 0x338, 0x340, 0x341, 0x343, 0x344, 0x345, 0x35c, 0x360, 0x489, 0x93c, 0x94d,
+                              0x951, 0x952)]
+    lines = []
+    for i in range(400):
+        parts = []
+        for _ in range(rng.choice((1, 3, 8))):
+            base = rng.choice('aeou AEH\u0915\u0930\u0928z')
+            k = rng.choice((0, 1, 5, 20, 45, 70, 120, 200, 240))
+            parts.append(base + ''.join(rng.choice(marks) for _ in range(k)))
+        lines.append(' '.join(parts))
+    for nr, nc in ((True, True), (True, False), (False, False)):
+        assert A.normalize_batch(lines, normalize_roman=nr, clean_hinglish=nc) == [O.normalize_text(t, nr, nc) for t in lines]
+    norm = [O.normalize_text(t) for t in lines]
+    assert A.segment_akshars_batch(norm) == [O.segment_akshars(t) for t in norm]
+    tk = A.aksharTokenizer(os.path.join(models_dir, 'bpe24k.json'), 'bpe')
+    om = O.BpeModel(os.path.join(models_dir, 'bpe24k.json'))
+    assert tk.encode_batch(lines) == [O.bpe_encode(om, t) for t in norm]
+    tu = A.aksharTokenizer(os.path.join(models_dir, 'spm24k.model'))
+    ou = O.UnigramModel(os.path.join(models_dir, 'spm24k.model'))
+    assert tu.encode_batch(lines[:150]) == [O.unigram_encode(ou, t) for t in norm[:150]]
