@@ -18,7 +18,7 @@ OUT_IDS_U16, OUT_SPLITS_I32 = 1, 2
 WORDS_HINDI, WORDS_SPLIT = 0, 1
 FORM_DECODE, FORM_DETOKENIZE = 0, 1
 MERGE_AKSHARA, MERGE_NUKTA = 0, 1
-TIMERS = {'ak_nf3_classify_kernel': 0, 'ak_nf_write_kernel': 1, 'ak_resolve_kernel<bpe>': 2, 'ak_sf3_kernel': 3, 'ak_seg_mask_kernel': 3,
+TIMERS = {'ak_nf3_classify_kernel': 0, 'ak_nf_write_kernel': 1, 'ak_resolve_kernel<bpe>': 2, 'ak_seg_off_kernel<emit>': 3, 'ak_seg_mask_kernel': 3,
           'ak_resolve_kernel<unigram>': 4, 'ak_words_kernel': 5, 'ak_emit_kernel': 6, 'ak_wtok_kernel': 7, 'ak_dec_kernel': 8, 'ak_lines_kernel': 9}
 
 SYMBOLS = (

@@ -245,7 +245,7 @@ enum {
     AKSHAR_TIMER_NORMALIZE_CLASSIFY = 0,   /* ak_nf3_classify_kernel */
     AKSHAR_TIMER_NORMALIZE_WRITE = 1,      /* ak_nf_write_kernel */
     AKSHAR_TIMER_BPE_ENCODE = 2,           /* ak_resolve_kernel<0> (word events -> BPE ids through the word cache) */
-    AKSHAR_TIMER_SEGMENT = 3,              /* ak_sf3_kernel */
+    AKSHAR_TIMER_SEGMENT = 3,              /* ak_seg_off_kernel<emit> / ak_seg_mask_kernel */
     AKSHAR_TIMER_UNIGRAM = 4,              /* ak_resolve_kernel<1> (word events -> Unigram ids), or ak_unigram_kernel in row mode */
     AKSHAR_TIMER_WORDS = 5,                /* ak_words_kernel (text -> word / row events) */
     AKSHAR_TIMER_EMIT = 6,                 /* ak_emit_kernel (ids to their final place) */
