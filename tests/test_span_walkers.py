@@ -199,6 +199,43 @@ def test_bit_parallel_fuzz():
         assert st == 0 and np.array_equal(out_off, exp_off) and out.tobytes() == exp.tobytes()
 
 
+def _zalgo_lines():
+    import random
+    rng = random.Random(11)
+    marks = [chr(c) for c in (0x300, 0x301, 0x302, 0x303, 0x308, 0x30a, 0x316, 0x317, 0x323, 0x324, 0x325, 0x327, 0x328, 0x32d,
+                              0x334, 0x335, 0x336, 0x338, 0x340, 0x341, 0x343, 0x344, 0x345, 0x35c, 0x360, 0x489, 0x93c, 0x94d,
+                              0x951, 0x952)]
+    excl = [chr(c) for c in range(0x958, 0x960)] + ['\ufb2a', '\ufb2b', '\ufb2e', '\ufb4b', '\u0f43', '\u2adc']
+    lines = []
+    for i in range(300):
+        parts = []
+        for _ in range(rng.choice((1, 3, 8))):
+            base = rng.choice('aeou AEH\u0915\u0930\u0928z')
+            k = rng.choice((0, 1, 5, 20, 45, 70, 120, 200, 240))
+            parts.append(base + ''.join(rng.choice(marks) for _ in range(k)))
+        lines.append(' '.join(parts))
+    for i in range(200):
+        n = rng.choice((1, 7, 40, 200, 700))
+        lines.append(''.join(rng.choice('\u0915\u093e\u0964') if k % 20 == 19 else rng.choice(excl) for k in range(n)))
+    return lines
+
+
+def test_zalgo_and_expanding_text():
+    """up to 240 stacked marks on one base (one NFC segment of up to 256 code points) and letters NFC makes longer:
+    the walker alone (spans of 32 bytes) and the bit-parallel lanes with their slow-lane walker agree with the oracle;
+    past the segment buffer the status says so"""
+    lines = _zalgo_lines()
+    data, off = sc.pack(lines)
+    for flags, (nr, nc) in ((7, (True, True)), (1, (True, False))):
+        exp, exp_off = OB.normalize_batch(lines, nr, nc)
+        out, out_off, st = W.normalize(data, off, flags=flags, span=32)
+        assert st == 0 and np.array_equal(out_off, exp_off) and out.tobytes() == exp.tobytes()
+        out, out_off, st, _ = W.fast_normalize3(data, off, real=30, flags=flags)
+        assert st == 0 and np.array_equal(out_off, exp_off) and out.tobytes() == exp.tobytes()
+    data, off = sc.pack(['a' + '\u0301' * 300, '\u0958' * 200])
+    assert W.normalize(data, off, flags=7, span=32)[2] & 2          # AKSHAR_ST_NFC_SEGMENT
+
+
 def test_bit_parallel_is_mostly_fast():
     for kind in ('hinglish', 'hindi', 'social'):
         lines = sc.Corpus(kind, 8).lines(200000)
