@@ -234,6 +234,14 @@ def test_zalgo_and_expanding_text():
         assert st == 0 and np.array_equal(out_off, exp_off) and out.tobytes() == exp.tobytes()
     data, off = sc.pack(['a' + '\u0301' * 300, '\u0958' * 200])
     assert W.normalize(data, off, flags=7, span=32)[2] & 2          # AKSHAR_ST_NFC_SEGMENT
+    # akshars and script runs of the same text (normalized with nothing dropped, so the marks are still there)
+    norm = [O.normalize_text(t, True, False) for t in lines]
+    data, off = sc.pack(norm)
+    ce, cs = OB.segment_batch(norm)
+    re_, rt, rs = OB.runs_batch(norm)
+    gce, gcs, gre, grt, grs, st = W.segment(data, off, flags=1 | 4, span=32)
+    assert st == 0 and np.array_equal(gcs, cs) and np.array_equal(gce, ce)
+    assert np.array_equal(grs, rs) and np.array_equal(gre, re_) and np.array_equal(grt, rt)
 
 
 def test_bit_parallel_is_mostly_fast():
