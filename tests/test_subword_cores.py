@@ -348,3 +348,34 @@ def test_malformed_models_are_refused(models_dir, tmp_path):
         W.load_spm(str(tmp_path / 't.model'))
     W.load_bpe(os.path.join(models_dir, 'bpe24k.json'))
     W.load_spm(os.path.join(models_dir, 'spm24k.model'))
+
+
+def test_zalgo_rows_through_the_event_stream_encoders(models_dir):
+    """rows with up to 240 stacked marks on a base (NFC-normalized, as the encoders get them from normalize_text): the
+    event-stream cores (words, row fix, resolve, emit) give the oracle's ids for both models"""
+    import random
+    rng = random.Random(11)
+    marks = [chr(c) for c in (0x300, 0x301, 0x302, 0x303, 0x308, 0x30a, 0x316, 0x317, 0x323, 0x324, 0x325, 0x327, 0x328, 0x32d,
+                              0x334, 0x335, 0x336, 0x338, 0x345, 0x35c, 0x360, 0x489, 0x93c, 0x94d, 0x951, 0x952)]
+    lines = []
+    for i in range(120):
+        parts = []
+        for _ in range(rng.choice((1, 3, 8))):
+            base = rng.choice('aeou AEH\u0915\u0930\u0928z')
+            k = rng.choice((0, 1, 5, 20, 45, 70, 120, 200, 240))
+            parts.append(base + ''.join(rng.choice(marks) for _ in range(k)))
+        lines.append(' '.join(parts))
+    raw = [O.normalize_text(t, True, False) for t in lines]       # marks kept
+    clean = [O.normalize_text(t) for t in lines]                  # marks dropped by the allow-list
+    mb = O.BpeModel(os.path.join(models_dir, 'bpe24k.json'))
+    mu = O.UnigramModel(os.path.join(models_dir, 'spm24k.model'))
+    for rows in (raw, clean):
+        data, off = sc.pack(rows)
+        W.load_bpe(os.path.join(models_dir, 'bpe24k.json'))
+        ids, splits, st, _ = W.tok(0, data, off)
+        flat, sp = _flat([O.bpe_encode(mb, s) for s in rows])
+        assert st == 0 and np.array_equal(splits, sp) and ids.tolist() == flat
+        W.load_spm(os.path.join(models_dir, 'spm24k.model'))
+        ids, splits, st, _ = W.tok(1, data, off)
+        flat, sp = _flat([O.unigram_encode(mu, s) for s in rows])
+        assert st == 0 and np.array_equal(splits, sp) and ids.tolist() == flat
