@@ -244,6 +244,56 @@ def test_zalgo_and_expanding_text():
     assert np.array_equal(grs, rs) and np.array_equal(gre, re_) and np.array_equal(grt, rt)
 
 
+def test_wide_unicode_fuzz():
+    """strings drawn from 38 blocks (combining marks, Hebrew / Arabic, nine Indic scripts, Hangul jamo and syllables,
+    compatibility ideographs, variation selectors, tags, flags, emoji ...): the oracle agrees with the libraries the
+    reference calls (unicodedata NFC, regex \\X), and walkers + bit-parallel lanes agree with the oracle"""
+    import random
+    import unicodedata as u
+    import regex
+    rng = random.Random(2026)
+    blocks = [(0x20, 0x7f), (0xa0, 0x17f), (0x300, 0x36f), (0x370, 0x3ff), (0x590, 0x5ff), (0x600, 0x6ff), (0x900, 0x97f),
+              (0x980, 0x9ff), (0xa00, 0xa7f), (0xb80, 0xbff), (0xc00, 0xc7f), (0xd00, 0xd7f), (0xe00, 0xe7f), (0xf00, 0xfff),
+              (0x1000, 0x109f), (0x1100, 0x11ff), (0x1b00, 0x1b7f), (0x1e00, 0x1eff), (0x1f00, 0x1fff), (0x2000, 0x206f),
+              (0x20d0, 0x20ff), (0x2190, 0x21ff), (0x2600, 0x27bf), (0x3040, 0x30ff), (0xa960, 0xa97f), (0xac00, 0xd7ff),
+              (0xf900, 0xfaff), (0xfb00, 0xfb4f), (0xfe00, 0xfe0f), (0xfe20, 0xfe2f), (0x11000, 0x1107f), (0x11300, 0x1137f),
+              (0x1d100, 0x1d1ff), (0x1f1e6, 0x1f1ff), (0x1f300, 0x1f6ff), (0x1f900, 0x1f9ff), (0xe0020, 0xe007f),
+              (0xe0100, 0xe01ef)]
+
+    def rcp():
+        while True:
+            a, b = rng.choice(blocks)
+            c = rng.randint(a, b)
+            if 0xd800 <= c <= 0xdfff or (u.category(chr(c)) == 'Cn' and rng.random() < 0.9):
+                continue
+            return chr(c)
+    lines = []
+    for i in range(3000):
+        n = rng.choice((1, 2, 5, 12, 30, 80))
+        pool = [rcp() for _ in range(rng.choice((2, 4, 8)))]
+        s = ''.join(rng.choice(pool) if rng.random() < 0.6 else rcp() for _ in range(n))
+        lines.append(s.replace('\n', ' ').replace('\r', ' '))
+    assert all(O.normalize_unicode(s) == u.normalize('NFC', s) for s in lines)
+    assert all(O.segment_akshars(s) == regex.findall(r'\X', s) for s in lines)
+    data, off = sc.pack(lines)
+    for flags, (nr, nc) in ((1, (True, False)), (7, (True, True)), (0, (False, False))):
+        exp, exp_off = OB.normalize_batch(lines, nr, nc)
+        out, out_off, st = W.normalize(data, off, flags=flags, span=32)
+        assert st == 0 and np.array_equal(out_off, exp_off) and out.tobytes() == exp.tobytes()
+        if flags:
+            out, out_off, st, _ = W.fast_normalize3(data, off, real=30, flags=flags)
+            assert st == 0 and np.array_equal(out_off, exp_off) and out.tobytes() == exp.tobytes()
+    ce, cs = OB.segment_batch(lines)
+    re_, rt, rs = OB.runs_batch(lines)
+    for got in (W.segment(data, off, flags=1 | 4, span=32), W.seg_fast3(data, off, flags=1 | 4, real=30)):
+        gce, gcs, gre, grt, grs, st = got[:6]
+        assert st == 0 and np.array_equal(gcs, cs) and np.array_equal(gce, ce)
+        assert np.array_equal(grs, rs) and np.array_equal(gre, re_) and np.array_equal(grt, rt)
+    me, ms = OB.segment_batch(lines, matras=True)
+    for got in (W.segment(data, off, flags=1 | 2, span=32), W.seg_fast3(data, off, flags=1 | 2, real=30)):
+        assert got[5] == 0 and np.array_equal(got[1], ms) and np.array_equal(got[0], me)
+
+
 def test_bit_parallel_is_mostly_fast():
     for kind in ('hinglish', 'hindi', 'social'):
         lines = sc.Corpus(kind, 8).lines(200000)
