@@ -379,3 +379,58 @@ def test_zalgo_rows_through_the_event_stream_encoders(models_dir):
         ids, splits, st, _ = W.tok(1, data, off)
         flat, sp = _flat([O.unigram_encode(mu, s) for s in rows])
         assert st == 0 and np.array_equal(splits, sp) and ids.tolist() == flat
+
+
+def test_wide_unicode_fuzz_through_the_encoders(models_dir):
+    """rows drawn from 27 blocks (compatibility forms HF's NFKC rewrites, marks, Hangul, full-width forms, mathematical
+    alphanumerics, enclosed characters ...) with added-token syntax sprinkled in, `clean_hinglish=False`: the oracle gives
+    the ids of the libraries the reference calls (when they are installed), and the event-stream cores give the oracle's"""
+    import random
+    import unicodedata as u
+    rng = random.Random(77)
+    blocks = [(0x20, 0x7f), (0x20, 0x7f), (0xa0, 0x17f), (0x300, 0x36f), (0x370, 0x3ff), (0x590, 0x5ff), (0x600, 0x6ff),
+              (0x900, 0x97f), (0x900, 0x97f), (0x980, 0x9ff), (0xe00, 0xe7f), (0xf00, 0xfff), (0x1100, 0x11ff), (0x1e00, 0x1eff),
+              (0x2000, 0x206f), (0x2100, 0x214f), (0x2460, 0x24ff), (0x3040, 0x30ff), (0x3300, 0x33ff), (0xac00, 0xd7ff),
+              (0xf900, 0xfaff), (0xfb00, 0xfb4f), (0xfe00, 0xfe0f), (0xff00, 0xffef), (0x1d400, 0x1d7ff), (0x1f100, 0x1f1ff),
+              (0x1f300, 0x1f6ff)]
+
+    def rcp():
+        while True:
+            a, b = rng.choice(blocks)
+            c = rng.randint(a, b)
+            if 0xd800 <= c <= 0xdfff or (u.category(chr(c)) == 'Cn' and rng.random() < 0.9):
+                continue
+            return chr(c)
+    lines = []
+    for i in range(1500):
+        n = rng.choice((1, 2, 5, 12, 30, 60))
+        pool = [rcp() for _ in range(rng.choice((2, 4, 8)))] + [' ', '<s>', '</s>', '<unk>', '<']
+        s = ''.join(rng.choice(pool) if rng.random() < 0.6 else rcp() for _ in range(n))
+        lines.append(s.replace('\n', ' ').replace('\r', ' ').replace('\x00', ' '))
+    norm = [O.normalize_text(s, True, False) for s in lines]
+    mb = O.BpeModel(os.path.join(models_dir, 'bpe24k.json'))
+    mu = O.UnigramModel(os.path.join(models_dir, 'spm24k.model'))
+    exp_b = [O.bpe_encode(mb, s) for s in norm]
+    exp_u = [O.unigram_encode(mu, s) for s in norm]
+    try:
+        from tokenizers import Tokenizer
+        tk = Tokenizer.from_file(os.path.join(models_dir, 'bpe24k.json'))
+        assert [tk.encode(s).ids for s in norm] == exp_b
+    except ImportError:
+        pass
+    try:
+        import sentencepiece as spm
+        sp = spm.SentencePieceProcessor()
+        sp.Load(os.path.join(models_dir, 'spm24k.model'))
+        assert [sp.EncodeAsIds(s) for s in norm] == exp_u
+    except ImportError:
+        pass
+    data, off = sc.pack(norm)
+    W.load_bpe(os.path.join(models_dir, 'bpe24k.json'))
+    ids, splits, st, _ = W.tok(0, data, off)
+    flat, sp_ = _flat(exp_b)
+    assert st == 0 and np.array_equal(splits, sp_) and ids.tolist() == flat
+    W.load_spm(os.path.join(models_dir, 'spm24k.model'))
+    ids, splits, st, _ = W.tok(1, data, off)
+    flat, sp_ = _flat(exp_u)
+    assert st == 0 and np.array_equal(splits, sp_) and ids.tolist() == flat
